@@ -1,0 +1,64 @@
+"""ctypes binding of the C ABI declared in include/heon_b200.h."""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libheon_b200.so")
+
+u64p = C.POINTER(C.c_uint64)
+i32p = C.POINTER(C.c_int)
+i64p = C.POINTER(C.c_longlong)
+vp = C.c_void_p
+ll = C.c_longlong
+ci = C.c_int
+
+
+class heon_info(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("scheme", "n", "log_n", "q_size", "p_size", "keyswitch_method", "device")]
+
+
+# name -> (restype, argtypes); mirrors include/heon_b200.h one to one
+SIGNATURES = {
+    "heon_last_error": (C.c_char_p, []),
+    "heon_version": (C.c_char_p, []),
+    "heon_ckks_context_create": (ci, [ci, ci, i32p, ci, i32p, ci, C.POINTER(vp)]),
+    "heon_ckks_context_create_values": (ci, [ci, ci, u64p, ci, u64p, ci, C.POINTER(vp)]),
+    "heon_context_destroy": (None, [vp]),
+    "heon_context_info": (ci, [vp, C.POINTER(heon_info)]),
+    "heon_context_table": (ci, [vp, ci, ci, u64p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "heon_steps_to_galois_elt": (ci, [ci, ci, ci]),
+    "heon_ntt": (ci, [vp, vp, vp, ll, i32p, ci, ci, vp]),
+    "heon_ntt_poly_ordered": (ci, [vp, vp, i64p, ci, ci, ci, vp]),
+    "heon_add": (ci, [vp, vp, ll, vp, ll, vp, ll, ci, ci, ci, vp]),
+    "heon_sub": (ci, [vp, vp, ll, vp, ll, vp, ll, ci, ci, ci, vp]),
+    "heon_negate": (ci, [vp, vp, ll, vp, ll, ci, ci, ci, vp]),
+    "heon_ckks_multiply": (ci, [vp, vp, ll, vp, ll, vp, ll, ci, ci, vp]),
+    "heon_ckks_relinearize": (ci, [vp, vp, ll, vp, ci, ci, vp]),
+    "heon_ckks_rescale": (ci, [vp, vp, ll, ci, ci, vp]),
+    "heon_ckks_mod_drop_inplace": (ci, [vp, vp, ll, ci, ci, ci, vp]),
+    "heon_ckks_mod_drop": (ci, [vp, vp, ll, vp, ll, ci, ci, vp]),
+    "heon_ckks_apply_galois": (ci, [vp, vp, ll, vp, ll, vp, C.c_uint32, ci, ci, vp]),
+    "heon_kernel_launches": (ll, [ci]),
+}
+
+
+def build_library(force=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.check_call([os.path.join(_HERE, "build.sh")])
+    return LIB_PATH
+
+
+def load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built. "
+            "Run heongpu_b200/build.sh (or __graft_entry__.build()). There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib

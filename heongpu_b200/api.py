@@ -1,0 +1,272 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+Names, argument meaning and error behaviour follow the reference classes
+(src/include/heongpu/host/ckks/{context,ciphertext,evaluationkey,operator}.cuh):
+``HEContext`` / ``Ciphertext`` / ``Relinkey`` / ``Galoiskey`` /
+``HEArithmeticOperator.{add,sub,multiply,relinearize_inplace,rescale_inplace,
+mod_drop_inplace,rotate_rows,apply_galois}``.  Additive extension: a
+ciphertext object may carry a batch of B independent ciphertexts
+(``data`` of shape [B, components, L, N]); the reference is the B = 1 case.
+
+PyTorch is used only for device memory and streams.  Every operator calls the
+C ABI of ``libheon_b200.so``; nothing here computes on the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import build_library  # noqa: F401
+
+lib = _lib.load()
+
+TBL = dict(
+    modulus=0, psi=1, ntt=2, intt=3, n_inverse=4, last_q_modinv=5, half=6, half_mod=7, factor=8,
+    rescaled_last_q_modinv=9, rescaled_half_mod=10, rescaled_half=11,
+    ii_base_change=12, ii_mi_inv=13, ii_prod=14, ii_i_j=15, ii_i_location=16,
+)
+
+_EXC = {-1: ValueError, -2: RuntimeError, -3: RuntimeError, -4: RuntimeError}
+
+
+class HeonError(RuntimeError):
+    pass
+
+
+class HeonInvalidArgument(HeonError, ValueError):  # std::invalid_argument
+    pass
+
+
+class HeonLogicError(HeonError):  # std::logic_error
+    pass
+
+
+def _check(status):
+    if status == 0:
+        return
+    msg = lib.heon_last_error().decode()
+    if status == -1:
+        raise HeonInvalidArgument(msg)
+    if status == -2:
+        raise HeonLogicError(msg)
+    raise HeonError(msg)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream(stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+class HEContext:
+    """HEContext<Scheme::CKKS> (reference: src/lib/host/ckks/context.cu:26-539)."""
+
+    def __init__(self, log_n, q_bits=None, p_bits=None, q_values=None, p_values=None, device=0):
+        h = C.c_void_p()
+        if q_values is not None:
+            q = (C.c_uint64 * len(q_values))(*q_values)
+            p = (C.c_uint64 * len(p_values))(*p_values)
+            _check(lib.heon_ckks_context_create_values(device, log_n, q, len(q_values), p, len(p_values), C.byref(h)))
+        else:
+            q = (C.c_int * len(q_bits))(*q_bits)
+            p = (C.c_int * len(p_bits))(*p_bits)
+            _check(lib.heon_ckks_context_create(device, log_n, q, len(q_bits), p, len(p_bits), C.byref(h)))
+        self._h = h
+        info = _lib.heon_info()
+        _check(lib.heon_context_info(h, C.byref(info)))
+        self.n, self.n_power = info.n, info.log_n
+        self.Q_size, self.P_size = info.q_size, info.p_size
+        self.Q_prime_size = info.q_size + info.p_size
+        self.keyswitch_method = info.keyswitch_method
+        self.device = info.device
+        self.primes = [int(v) for v in self.table("modulus").reshape(-1, 3)[:, 0]]
+
+    def __del__(self):
+        if getattr(self, "_h", None) and lib is not None:
+            lib.heon_context_destroy(self._h)
+            self._h = None
+
+    def table(self, name, depth=0):
+        cnt = C.c_size_t()
+        _check(lib.heon_context_table(self._h, TBL[name], depth, None, 0, C.byref(cnt)))
+        out = np.zeros(cnt.value, dtype=np.uint64)
+        _check(lib.heon_context_table(self._h, TBL[name], depth, out.ctypes.data_as(_lib.u64p), cnt.value, C.byref(cnt)))
+        return out
+
+    def digits(self, depth=0):
+        L = self.Q_size - depth
+        return L if self.keyswitch_method == 1 else -(-L // self.P_size)
+
+    # ---- NTT (gpuntt::GPU_NTT / GPU_INTT / *_Modulus_Ordered) ----
+    def ntt(self, data, prime_index=None, inverse=False, out=None, stream=None):
+        """data: uint64/int64 cuda tensor [..., N]; poly z uses prime_index[z % len]."""
+        n_polys = data.numel() // self.n
+        out = data if out is None else out
+        if prime_index is None:
+            raise ValueError("prime_index required")
+        arr = (C.c_int * len(prime_index))(*prime_index)
+        _check(lib.heon_ntt(self._h, _ptr(data), _ptr(out), n_polys, arr, len(prime_index), int(inverse), _stream(stream)))
+        return out
+
+    def ntt_poly_ordered(self, base, offsets, prime_index, inverse=False, stream=None):
+        arr = (C.c_longlong * len(offsets))(*offsets)
+        _check(lib.heon_ntt_poly_ordered(self._h, _ptr(base), arr, len(offsets), prime_index, int(inverse), _stream(stream)))
+
+    def level_primes(self, depth=0):
+        L = self.Q_size - depth
+        return list(range(L)) + [self.Q_size + j for j in range(self.P_size)]
+
+
+class Ciphertext:
+    """Ciphertext<Scheme::CKKS>: flat [cipher_size][L][N] words, NTT domain
+    (reference: src/lib/host/ckks/ciphertext.cu:20-31), optionally batched."""
+
+    def __init__(self, context, data, depth=0, cipher_size=None, scale=1.0,
+                 relinearization_required=False, rescale_required=False):
+        self.context = context
+        if data.dim() == 3:
+            data = data.unsqueeze(0)
+        self.data = data  # [B, comps_allocated, L_allocated, N] int64 view of uint64 words
+        self.depth_ = depth
+        self.cipher_size_ = cipher_size if cipher_size is not None else data.shape[1]
+        self.scale_ = scale
+        self.relinearization_required_ = relinearization_required
+        self.rescale_required_ = rescale_required
+        self.in_ntt_domain_ = True
+
+    @property
+    def batch(self):
+        return self.data.shape[0]
+
+    @property
+    def stride(self):
+        return self.data.stride(0)
+
+    def level_count(self):
+        return self.context.Q_size - self.depth_
+
+    def words(self):
+        """The live [B, cipher_size, L, N] words (the buffer may be larger after in-place ops)."""
+        L, N = self.level_count(), self.context.n
+        flat = self.data.reshape(self.batch, -1)[:, : self.cipher_size_ * L * N]
+        return flat.reshape(self.batch, self.cipher_size_, L, N)
+
+
+class _EvalKey:
+    def __init__(self, context, data):
+        self.context = context
+        self.data = data
+
+
+class Relinkey(_EvalKey):
+    """Relinkey<Scheme::CKKS>: [digit][2][Q'_0][N] NTT-domain words
+    (reference: src/lib/kernel/keygeneration.cu:180-183)."""
+
+
+class Galoiskey:
+    """Galoiskey<Scheme::CKKS>: map galois_elt -> key of the Relinkey layout
+    (reference: src/lib/host/ckks/evaluationkey.cu, device_location_)."""
+
+    group_order_ = 5
+
+    def __init__(self, context, keys):
+        self.context = context
+        self.device_location_ = dict(keys)
+
+
+class HEArithmeticOperator:
+    """HEArithmeticOperator<Scheme::CKKS>, hot-path subset
+    (reference: src/include/heongpu/host/ckks/operator.cuh:95-1600)."""
+
+    def __init__(self, context):
+        self.context_ = context
+
+    # -- element-wise --
+    def _binary(self, fn, a, b, out):
+        if a.depth_ != b.depth_:
+            raise HeonLogicError("Ciphertexts leveled are not equal")
+        c = self.context_
+        comps = max(a.cipher_size_, b.cipher_size_)
+        if a.cipher_size_ != b.cipher_size_:
+            raise HeonInvalidArgument("Ciphertexts should have the same size")
+        _check(fn(c._h, _ptr(a.data), a.stride, _ptr(b.data), b.stride, _ptr(out.data), out.stride,
+                  comps, a.depth_, a.batch, _stream()))
+        out.depth_, out.cipher_size_, out.scale_ = a.depth_, comps, a.scale_
+        out.relinearization_required_ = a.relinearization_required_
+        out.rescale_required_ = a.rescale_required_
+        return out
+
+    def add(self, a, b, out):
+        return self._binary(lib.heon_add, a, b, out)
+
+    def sub(self, a, b, out):
+        return self._binary(lib.heon_sub, a, b, out)
+
+    def negate(self, a, out):
+        c = self.context_
+        _check(lib.heon_negate(c._h, _ptr(a.data), a.stride, _ptr(out.data), out.stride, a.cipher_size_, a.depth_, a.batch, _stream()))
+        out.depth_, out.cipher_size_ = a.depth_, a.cipher_size_
+        return out
+
+    # -- multiply / relinearize / rescale (operator.cuh:631-707,1053-1094,1423-1445) --
+    def multiply(self, a, b, out):
+        if a.relinearization_required_ or b.relinearization_required_:
+            raise HeonInvalidArgument("Ciphertexts can not be multiplied because of the non-linear part! Please use relinearization operation!")
+        if a.rescale_required_ or b.rescale_required_:
+            raise HeonInvalidArgument("Ciphertexts can not be multiplied because of the noise! Please use rescale operation to get rid of additional noise!")
+        if a.depth_ != b.depth_:
+            raise HeonLogicError("Ciphertexts leveled are not equal")
+        c = self.context_
+        _check(lib.heon_ckks_multiply(c._h, _ptr(a.data), a.stride, _ptr(b.data), b.stride, _ptr(out.data), out.stride,
+                                      a.depth_, a.batch, _stream()))
+        out.depth_, out.cipher_size_ = a.depth_, 3
+        out.scale_ = a.scale_ * b.scale_
+        out.relinearization_required_ = True
+        out.rescale_required_ = True
+        return out
+
+    def relinearize_inplace(self, ct, relin_key):
+        if not ct.relinearization_required_:
+            raise HeonInvalidArgument("Ciphertexts can not use relinearization, since no non-linear part!")
+        c = self.context_
+        _check(lib.heon_ckks_relinearize(c._h, _ptr(ct.data), ct.stride, _ptr(relin_key.data), ct.depth_, ct.batch, _stream()))
+        ct.cipher_size_ = 2
+        ct.relinearization_required_ = False
+        return ct
+
+    def rescale_inplace(self, ct):
+        if not ct.rescale_required_ and False:
+            raise HeonInvalidArgument("Ciphertexts can not be rescaled")
+        c = self.context_
+        _check(lib.heon_ckks_rescale(c._h, _ptr(ct.data), ct.stride, ct.depth_, ct.batch, _stream()))
+        ct.scale_ = ct.scale_ / float(c.primes[c.Q_size - ct.depth_ - 1])
+        ct.depth_ += 1
+        ct.rescale_required_ = False
+        return ct
+
+    def mod_drop_inplace(self, ct):
+        c = self.context_
+        _check(lib.heon_ckks_mod_drop_inplace(c._h, _ptr(ct.data), ct.stride, ct.cipher_size_, ct.depth_, ct.batch, _stream()))
+        ct.depth_ += 1
+        return ct
+
+    # -- rotations (operator.cuh:1105-1270) --
+    def apply_galois(self, ct, out, galois_key, galois_elt):
+        c = self.context_
+        if galois_elt not in galois_key.device_location_:
+            raise HeonLogicError("Galois key not present!")
+        key = galois_key.device_location_[galois_elt]
+        _check(lib.heon_ckks_apply_galois(c._h, _ptr(ct.data), ct.stride, _ptr(out.data), out.stride, _ptr(key),
+                                          galois_elt, ct.depth_, ct.batch, _stream()))
+        out.depth_, out.cipher_size_, out.scale_ = ct.depth_, 2, ct.scale_
+        out.relinearization_required_ = ct.relinearization_required_
+        out.rescale_required_ = ct.rescale_required_
+        return out
+
+    def rotate_rows(self, ct, out, galois_key, shift):
+        elt = lib.heon_steps_to_galois_elt(shift, self.context_.n, galois_key.group_order_)
+        return self.apply_galois(ct, out, galois_key, elt)

@@ -1,0 +1,350 @@
+// extern "C" boundary: argument validation, exception -> status translation.
+#include <cstring>
+#include <memory>
+#include "../../include/heon_b200.h"
+#include "ops.hpp"
+
+using namespace heon;
+
+struct heon_context_s {
+    Context c;
+};
+
+namespace heon {
+std::atomic<long long> g_launches{0};
+}
+
+static thread_local std::string g_err;
+
+template <class F> static int guarded(F&& f)
+{
+    try
+    {
+        f();
+        return HEON_OK;
+    }
+    catch (const std::invalid_argument& e)
+    {
+        g_err = e.what();
+        return HEON_ERR_INVALID;
+    }
+    catch (const std::logic_error& e)
+    {
+        g_err = e.what();
+        return HEON_ERR_LOGIC;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return HEON_ERR_RUNTIME;
+    }
+}
+
+static void need_device(const Context& c)
+{
+    if (c.device < 0)
+        throw std::runtime_error("context was created host-only (device < 0): no CUDA path");
+    cudaError_t e = cudaSetDevice(c.device);
+    if (e != cudaSuccess)
+        throw std::runtime_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+}
+
+static void finish_context(Context& c, int device, int log_n, int n_q, int n_p)
+{
+    if (log_n < 12 || log_n > 16)
+        throw std::logic_error("Poly modulus degree is not supported");
+    if (n_p < 1)
+        throw std::logic_error("log_P_bases_bit_sizes cannot be empty!");
+    if (n_q < 1 || n_q + n_p > 128)
+        throw std::logic_error("invalid modulus count");
+    c.device = device;
+    c.scheme = SCHEME_CKKS;
+    c.logn = log_n;
+    c.n = 1 << log_n;
+    c.Q_size = n_q;
+    c.P_size = n_p;
+    c.Qp = n_q + n_p;
+    c.method = (n_p == 1) ? 1 : 2;
+    if (c.method == 2 && n_p > 15)
+        throw std::logic_error("P size above 15 is not supported");
+    build_host_tables(c);
+    if (device >= 0)
+        upload_tables(c);
+}
+
+extern "C" {
+
+const char* heon_last_error(void) { return g_err.c_str(); }
+const char* heon_version(void) { return "heon-b200 0.1 (sm_100a)"; }
+
+int heon_ckks_context_create(int device, int log_n, const int* q_bits, int n_q, const int* p_bits,
+                             int n_p, heon_context_t* out)
+{
+    return guarded([&] {
+        if (!out || !q_bits || !p_bits)
+            throw std::invalid_argument("null argument");
+        auto h = std::make_unique<heon_context_s>();
+        std::vector<int> bits(q_bits, q_bits + n_q);
+        bits.insert(bits.end(), p_bits, p_bits + n_p);
+        if (log_n < 12 || log_n > 16)
+            throw std::logic_error("Poly modulus degree is not supported");
+        for (u64 p : primes_for_bit_sizes(1ull << log_n, bits))
+            h->c.mod.push_back(make_mod(p));
+        finish_context(h->c, device, log_n, n_q, n_p);
+        *out = h.release();
+    });
+}
+
+int heon_ckks_context_create_values(int device, int log_n, const uint64_t* q, int n_q,
+                                    const uint64_t* p, int n_p, heon_context_t* out)
+{
+    return guarded([&] {
+        if (!out || !q || !p)
+            throw std::invalid_argument("null argument");
+        auto h = std::make_unique<heon_context_s>();
+        for (int i = 0; i < n_q; ++i)
+            h->c.mod.push_back(make_mod(q[i]));
+        for (int i = 0; i < n_p; ++i)
+            h->c.mod.push_back(make_mod(p[i]));
+        for (auto& m : h->c.mod)
+            if (m.bit > 61 || m.bit < 30 || !is_prime_u64(m.value) ||
+                (m.value - 1) % (2ull << log_n))
+                throw std::logic_error("invalid modulus");
+        finish_context(h->c, device, log_n, n_q, n_p);
+        *out = h.release();
+    });
+}
+
+void heon_context_destroy(heon_context_t ctx) { delete ctx; }
+
+int heon_context_info(heon_context_t ctx, heon_info* o)
+{
+    return guarded([&] {
+        if (!ctx || !o)
+            throw std::invalid_argument("null argument");
+        const Context& c = ctx->c;
+        *o = heon_info{c.scheme, c.n, c.logn, c.Q_size, c.P_size, c.method, c.device};
+    });
+}
+
+int heon_context_table(heon_context_t ctx, int which, int depth, uint64_t* h_out, size_t cap,
+                       size_t* count)
+{
+    return guarded([&] {
+        if (!ctx || !count)
+            throw std::invalid_argument("null argument");
+        const Context& c = ctx->c;
+        std::vector<u64> tmp;
+        const std::vector<u64>* src = nullptr;
+        auto lvl = [&]() -> const LevelTablesII& {
+            if (c.method != 2 || depth < 0 || depth >= (int) c.lvl2.size())
+                throw std::invalid_argument("no Method II table at this depth");
+            return c.lvl2[depth];
+        };
+        switch (which)
+        {
+            case HEON_TBL_MODULUS:
+                for (auto& m : c.mod)
+                {
+                    tmp.push_back(m.value);
+                    tmp.push_back(m.bit);
+                    tmp.push_back(m.mu);
+                }
+                src = &tmp;
+                break;
+            case HEON_TBL_PSI: src = &c.psi; break;
+            case HEON_TBL_NTT: src = &c.ntt_table; break;
+            case HEON_TBL_INTT: src = &c.intt_table; break;
+            case HEON_TBL_N_INVERSE: src = &c.n_inverse; break;
+            case HEON_TBL_LAST_Q_MODINV: src = &c.last_q_modinv; break;
+            case HEON_TBL_HALF: src = &c.half; break;
+            case HEON_TBL_HALF_MOD: src = &c.half_mod; break;
+            case HEON_TBL_FACTOR: src = &c.factor; break;
+            case HEON_TBL_RESCALED_LAST_Q_MODINV: src = &c.rescaled_last_q_modinv; break;
+            case HEON_TBL_RESCALED_HALF_MOD: src = &c.rescaled_half_mod; break;
+            case HEON_TBL_RESCALED_HALF: src = &c.rescaled_half; break;
+            case HEON_TBL_II_BASE_CHANGE: src = &lvl().base_change; break;
+            case HEON_TBL_II_MI_INV: src = &lvl().mi_inv; break;
+            case HEON_TBL_II_PROD: src = &lvl().prod; break;
+            case HEON_TBL_II_I_J:
+                for (int v : lvl().I_j)
+                    tmp.push_back((u64) v);
+                src = &tmp;
+                break;
+            case HEON_TBL_II_I_LOCATION:
+                for (int v : lvl().I_loc)
+                    tmp.push_back((u64) v);
+                src = &tmp;
+                break;
+            default: throw std::invalid_argument("unknown table");
+        }
+        *count = src->size();
+        if (h_out)
+        {
+            if (cap < src->size())
+                throw std::invalid_argument("output buffer too small");
+            std::memcpy(h_out, src->data(), src->size() * sizeof(u64));
+        }
+    });
+}
+
+int heon_steps_to_galois_elt(int steps, int n, int group_order)
+{
+    const int m = 2 * n;
+    if (steps == 0)
+        return m - 1;
+    const int pos = steps < 0 ? -steps : steps;
+    if (pos >= (n >> 1))
+        return 0;
+    int s = steps < 0 ? (n >> 1) - pos : pos;
+    int g = 1;
+    while (s-- > 0)
+        g = (int) (((long long) g * group_order) & (m - 1));
+    return g;
+}
+
+int heon_ntt(heon_context_t ctx, const uint64_t* in, uint64_t* out, long long n_polys,
+             const int* h_prime_index, int mod_count, int inverse, void* stream)
+{
+    return guarded([&] {
+        if (!ctx || !in || !out)
+            throw std::invalid_argument("null argument");
+        const Context& c = ctx->c;
+        need_device(c);
+        if (mod_count < 1 || mod_count > 128)
+            throw std::invalid_argument("invalid mod_count");
+        PrimeList pl;
+        pl.count = mod_count;
+        for (int i = 0; i < mod_count; ++i)
+        {
+            int v = h_prime_index ? h_prime_index[i] : i;
+            if (v < 0 || v >= c.Qp)
+                throw std::invalid_argument("prime index out of range");
+            pl.idx[i] = (unsigned char) v;
+        }
+        launch_ntt(c, in, out, n_polys, pl, inverse != 0, (cudaStream_t) stream);
+    });
+}
+
+int heon_ntt_poly_ordered(heon_context_t ctx, uint64_t* base, const long long* h_offsets,
+                          int n_polys, int prime_index, int inverse, void* stream)
+{
+    return guarded([&] {
+        if (!ctx || !base || !h_offsets)
+            throw std::invalid_argument("null argument");
+        const Context& c = ctx->c;
+        need_device(c);
+        if (prime_index < 0 || prime_index >= c.Qp)
+            throw std::invalid_argument("prime index out of range");
+        cudaStream_t st = (cudaStream_t) stream;
+        long long* d_off = nullptr;
+        if (cudaMallocAsync(&d_off, sizeof(long long) * n_polys, st) != cudaSuccess)
+            throw std::runtime_error("cudaMallocAsync failed");
+        cudaMemcpyAsync(d_off, h_offsets, sizeof(long long) * n_polys, cudaMemcpyHostToDevice, st);
+        launch_ntt_scattered(c, base, d_off, n_polys, prime_index, inverse != 0, st);
+        cudaFreeAsync(d_off, st);
+    });
+}
+
+#define HEON_OP_PROLOGUE                                                                           \
+    if (!ctx)                                                                                      \
+        throw std::invalid_argument("null context");                                               \
+    const Context& c = ctx->c;                                                                     \
+    need_device(c);                                                                                \
+    if (batch < 1)                                                                                 \
+        throw std::invalid_argument("batch must be positive");                                     \
+    cudaStream_t st = (cudaStream_t) stream;
+
+int heon_add(heon_context_t ctx, const uint64_t* a, long long as, const uint64_t* b, long long bs,
+             uint64_t* out, long long os, int comps, int depth, int batch, void* stream)
+{
+    return guarded([&] {
+        HEON_OP_PROLOGUE
+        op_add(c, a, as, b, bs, out, os, comps, depth, batch, 0, st);
+    });
+}
+int heon_sub(heon_context_t ctx, const uint64_t* a, long long as, const uint64_t* b, long long bs,
+             uint64_t* out, long long os, int comps, int depth, int batch, void* stream)
+{
+    return guarded([&] {
+        HEON_OP_PROLOGUE
+        op_add(c, a, as, b, bs, out, os, comps, depth, batch, 1, st);
+    });
+}
+int heon_negate(heon_context_t ctx, const uint64_t* a, long long as, uint64_t* out, long long os,
+                int comps, int depth, int batch, void* stream)
+{
+    return guarded([&] {
+        HEON_OP_PROLOGUE
+        op_add(c, a, as, a, as, out, os, comps, depth, batch, 2, st);
+    });
+}
+
+int heon_ckks_multiply(heon_context_t ctx, const uint64_t* a, long long as, const uint64_t* b,
+                       long long bs, uint64_t* out, long long os, int depth, int batch, void* stream)
+{
+    return guarded([&] {
+        HEON_OP_PROLOGUE
+        op_multiply(c, a, as, b, bs, out, os, depth, batch, st);
+    });
+}
+
+int heon_ckks_relinearize(heon_context_t ctx, uint64_t* ct, long long cs, const uint64_t* relin_key,
+                          int depth, int batch, void* stream)
+{
+    return guarded([&] {
+        HEON_OP_PROLOGUE
+        if (!ct || !relin_key)
+            throw std::invalid_argument("null argument");
+        op_relinearize(c, ct, cs, relin_key, depth, batch, st);
+    });
+}
+
+int heon_ckks_rescale(heon_context_t ctx, uint64_t* ct, long long cs, int depth, int batch,
+                      void* stream)
+{
+    return guarded([&] {
+        HEON_OP_PROLOGUE
+        op_rescale(c, ct, cs, depth, batch, st);
+    });
+}
+
+int heon_ckks_mod_drop_inplace(heon_context_t ctx, uint64_t* ct, long long cs, int comps, int depth,
+                               int batch, void* stream)
+{
+    return guarded([&] {
+        HEON_OP_PROLOGUE
+        op_mod_drop_inplace(c, ct, cs, comps, depth, batch, st);
+    });
+}
+
+int heon_ckks_mod_drop(heon_context_t ctx, const uint64_t* in, long long is, uint64_t* out,
+                       long long os, int depth, int batch, void* stream)
+{
+    return guarded([&] {
+        HEON_OP_PROLOGUE
+        op_mod_drop(c, in, is, out, os, depth, batch, st);
+    });
+}
+
+int heon_ckks_apply_galois(heon_context_t ctx, const uint64_t* in, long long is, uint64_t* out,
+                           long long os, const uint64_t* galois_key, uint32_t galois_elt, int depth,
+                           int batch, void* stream)
+{
+    return guarded([&] {
+        HEON_OP_PROLOGUE
+        if (!in || !out || !galois_key || in == out)
+            throw std::invalid_argument("invalid buffers");
+        op_apply_galois(c, in, is, out, os, galois_key, galois_elt, depth, batch, st);
+    });
+}
+
+long long heon_kernel_launches(int reset)
+{
+    long long v = g_launches.load();
+    if (reset)
+        g_launches.store(0);
+    return v;
+}
+
+} // extern "C"

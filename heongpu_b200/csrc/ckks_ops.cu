@@ -1,0 +1,560 @@
+// CKKS hot-path operators: tensor product, key-switch core (mod-up, inner
+// product, mod-down), relinearize, rescale, mod-drop, Galois automorphism,
+// element-wise add/sub/negate.  Batched: every ciphertext pointer comes with a
+// batch stride (in 64-bit words).
+//
+// Launch sequencing replaces src/lib/host/ckks/operator.cu:796-1720 of the
+// reference; kernels replace src/lib/kernel/{switchkey,multiplication,
+// addition}.cu (exact lines cited at each kernel).  All element-wise
+// arithmetic uses the reference's Barrett sequence (modarith.cuh), so stored
+// words are identical to the reference's.
+#include "modarith.cuh"
+#include "ops.hpp"
+
+namespace heon {
+
+// ---------------------------------------------------------------------------
+// element-wise kernels
+// ---------------------------------------------------------------------------
+
+// (c0,c1) x (d0,d1) -> (c0d0, c0d1+c1d0, c1d1) per limb.
+// reference: src/lib/kernel/multiplication.cu:102-126 (cross_multiplication)
+__global__ void __launch_bounds__(256)
+    k_cross_multiply(const u64* __restrict__ a, const u64* __restrict__ b, u64* __restrict__ out,
+                     long long a_bs, long long b_bs, long long o_bs, const Mod64* __restrict__ mods,
+                     int logn, int L)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    const long long bz = blockIdx.z;
+    const Mod64 m = mods[y];
+    const long long loc = idx + ((long long) y << logn);
+    const long long comp = (long long) L << logn;
+    const u64* pa = a + bz * a_bs;
+    const u64* pb = b + bz * b_bs;
+    u64* po = out + bz * o_bs;
+    u64 a0 = pa[loc], a1 = pa[loc + comp];
+    u64 b0 = pb[loc], b1 = pb[loc + comp];
+    u64 o0 = barrett_mul(a0, b0, m);
+    u64 o10 = barrett_mul(a0, b1, m);
+    u64 o11 = barrett_mul(a1, b0, m);
+    u64 o2 = barrett_mul(a1, b1, m);
+    po[loc] = o0;
+    po[loc + comp] = mod_add(o10, o11, m.value);
+    po[loc + 2 * comp] = o2;
+}
+
+// reference: src/lib/kernel/addition.cu:10-49 (addition / substraction / negation)
+template <int OP>
+__global__ void __launch_bounds__(256)
+    k_addsub(const u64* __restrict__ a, const u64* __restrict__ b, u64* __restrict__ out,
+             long long a_bs, long long b_bs, long long o_bs, const Mod64* __restrict__ mods, int logn,
+             int L, int comps)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    const long long bz = blockIdx.z / comps;
+    const int c = blockIdx.z % comps;
+    const u64 p = mods[y].value;
+    const long long loc = idx + ((long long) (c * L + y) << logn);
+    u64 x = a[bz * a_bs + loc];
+    u64 r;
+    if (OP == 0)
+        r = mod_add(x, b[bz * b_bs + loc], p);
+    else if (OP == 1)
+        r = mod_sub(x, b[bz * b_bs + loc], p);
+    else
+        r = mod_sub(0, x, p);
+    out[bz * o_bs + loc] = r;
+}
+
+// ---------------------------------------------------------------------------
+// key-switch inner product
+// ---------------------------------------------------------------------------
+
+// out[b][c][y] = sum_i in[b][i][y] * key[i][c][prime(y)]  (NTT domain).
+// Products are accumulated lazily in 128 bits and reduced once; the result is
+// the canonical residue, identical to the reference's per-term Barrett sum.
+// reference: src/lib/kernel/switchkey.cu:164-285 (Method I), 287-398 (Method II)
+__global__ void __launch_bounds__(256)
+    k_keyswitch_mac(const u64* __restrict__ in, const u64* __restrict__ key, u64* __restrict__ out,
+                    const PrimeConst* __restrict__ pcs, int logn, int d, int L, int Qpl, int Qp0,
+                    int depth)
+{
+    const int idx = (blockIdx.x * 256 + threadIdx.x) * 2;
+    const int y = blockIdx.y;
+    const long long bz = blockIdx.z;
+    const int prime = level_prime(y, L, depth);
+    const PrimeConst pc = pcs[prime];
+    const long long N = 1LL << logn;
+    const u64* pin = in + ((bz * d * Qpl + y) << logn) + idx;
+    const u64* pk = key + ((long long) prime << logn) + idx;
+    const long long in_step = (long long) Qpl << logn;
+    const long long key_c = (long long) Qp0 << logn;
+    const long long key_step = 2 * key_c;
+
+    u64 a0l = 0, a0h = 0, a1l = 0, a1h = 0; // coefficient idx
+    u64 b0l = 0, b0h = 0, b1l = 0, b1h = 0; // coefficient idx+1
+#pragma unroll 4
+    for (int i = 0; i < d; ++i)
+    {
+        const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(pin + i * in_step);
+        const ulonglong2 k0 = __ldg(reinterpret_cast<const ulonglong2*>(pk + i * key_step));
+        const ulonglong2 k1 = __ldg(reinterpret_cast<const ulonglong2*>(pk + i * key_step + key_c));
+        mac128(a0l, a0h, x.x, k0.x);
+        mac128(a1l, a1h, x.x, k1.x);
+        mac128(b0l, b0h, x.y, k0.y);
+        mac128(b1l, b1h, x.y, k1.y);
+    }
+    u64* po = out + ((bz * 2 * Qpl + y) << logn) + idx;
+    ulonglong2 r0, r1;
+    r0.x = reduce_u128(a0l, a0h, pc);
+    r0.y = reduce_u128(b0l, b0h, pc);
+    r1.x = reduce_u128(a1l, a1h, pc);
+    r1.y = reduce_u128(b1l, b1h, pc);
+    *reinterpret_cast<ulonglong2*>(po) = r0;
+    *reinterpret_cast<ulonglong2*>(po + ((long long) Qpl << logn)) = r1;
+    (void) N;
+}
+
+// ---------------------------------------------------------------------------
+// Method-II mod-up (HPS fast base conversion with the fp32 correction)
+// ---------------------------------------------------------------------------
+
+// reference: src/lib/kernel/switchkey.cu:985-1046
+// (base_conversion_DtoQtilde_relin_leveled_kernel).  The float sequence
+// (u64->f32 rn, IEEE divide, sequential adds, round half away) is reproduced
+// operation for operation.
+__global__ void __launch_bounds__(256)
+    k_modup2(const u64* __restrict__ coef, long long coef_bs, u64* __restrict__ out,
+             const Mod64* __restrict__ mods, const u64* __restrict__ base_change,
+             const u64* __restrict__ mi_inv, const u64* __restrict__ prod,
+             const int* __restrict__ I_j_, const int* __restrict__ I_loc_, int logn, int d, int Qpl,
+             int L, int depth)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int dg = blockIdx.y;
+    const long long bz = blockIdx.z;
+    const int I_j = I_j_[dg];
+    const int I_loc = I_loc_[dg];
+    const u64* pc = coef + bz * coef_bs + idx + ((long long) I_loc << logn);
+    u64* po = out + (((bz * d + dg) * Qpl) << logn) + idx;
+    const int matrix_index = I_loc * Qpl;
+
+    u64 partial[20];
+    float r = 0;
+    for (int i = 0; i < I_j; ++i)
+    {
+        u64 t = pc[(long long) i << logn];
+        partial[i] = barrett_mul(t, mi_inv[I_loc + i], mods[I_loc + i]);
+        float div = __ull2float_rn(partial[i]);
+        float mod = __ull2float_rn(mods[I_loc + i].value);
+        r = __fadd_rn(r, __fdiv_rn(div, mod));
+    }
+    r = roundf(r);
+    const u64 r_ = (u64) r;
+
+    for (int i = 0; i < Qpl; ++i)
+    {
+        const Mod64 m = mods[level_prime(i, L, depth)];
+        u64 t = 0;
+        for (int j = 0; j < I_j; ++j)
+        {
+            u64 mult = reduce_forced(partial[j], m);
+            mult = barrett_mul(mult, base_change[j + i * I_j + matrix_index], m);
+            t = mod_add(t, mult, m.value);
+        }
+        u64 r_mul = barrett_mul(r_, prod[i + dg * Qpl], m);
+        po[(long long) i << logn] = mod_sub(t, r_mul, m.value);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// mod-down
+// ---------------------------------------------------------------------------
+
+// Method I, stage two (NTT domain): ct[c][y] += (acc[c][y] - corr[c][y]) * P^-1.
+// reference: src/lib/kernel/switchkey.cu:707-736 (stage_two), 738-771
+// (switchkey variant: `add_mask` selects which components add the old ct).
+__global__ void __launch_bounds__(256)
+    k_moddown1_stage2(const u64* __restrict__ corr, const u64* __restrict__ acc,
+                      const u64* __restrict__ ct, long long ct_bs, u64* __restrict__ out,
+                      long long out_bs, const Mod64* __restrict__ mods,
+                      const u64* __restrict__ last_q_modinv, int logn, int L, int Qpl, int add_mask)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    const long long bz = blockIdx.z >> 1;
+    const int c = blockIdx.z & 1;
+    const Mod64 m = mods[y];
+    u64 last = corr[((bz * 2 + c) * L + y << logn) + idx];
+    u64 x = acc[((bz * 2 + c) * Qpl + y << logn) + idx];
+    x = mod_sub(x, last, m.value);
+    x = barrett_mul(x, last_q_modinv[y], m);
+    u64 cin = 0;
+    if ((add_mask >> c) & 1)
+        cin = ct[bz * ct_bs + ((long long) (c * L + y) << logn) + idx];
+    out[bz * out_bs + ((long long) (c * L + y) << logn) + idx] = mod_add(cin, x, m.value);
+}
+
+// Method II / Galois mod-down in the coefficient domain: peel the K special
+// primes one at a time (last first).  Optional fused epilogue for
+// apply_galois: add c0 to component 0 and scatter through the automorphism
+// i -> i*g mod 2N with sign flip (no zero check, as in the reference).
+// reference: src/lib/kernel/switchkey.cu:1222-1282
+// (divide_round_lastq_extended_leveled_kernel) and 1621-1718
+// (divide_round_lastq_permute_ckks_kernel).
+template <bool PERMUTE>
+__global__ void __launch_bounds__(256)
+    k_moddown_ext(const u64* __restrict__ in, u64* __restrict__ out, long long out_bs,
+                  const u64* __restrict__ c0coef, const Mod64* __restrict__ mods,
+                  const u64* __restrict__ half, const u64* __restrict__ half_mod,
+                  const u64* __restrict__ last_q_modinv, unsigned galois_elt, int logn, int Qpl, int L,
+                  int Qp0, int Q0, int K)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    const long long bz = blockIdx.z >> 1;
+    const int c = blockIdx.z & 1;
+    const u64* pin = in + (((bz * 2 + c) * Qpl) << logn) + idx;
+
+    u64 last_ct[15];
+    for (int i = 0; i < K; ++i)
+        last_ct[i] = pin[(long long) (L + i) << logn];
+    u64 x = pin[(long long) y << logn];
+    const Mod64 my = mods[y];
+
+    int loc = 0;
+    for (int i = 0; i < K; ++i)
+    {
+        u64 lh = mod_add(last_ct[K - 1 - i], half[i], mods[Qp0 - 1 - i].value);
+        for (int j = 0; j < K - 1 - i; ++j)
+        {
+            const Mod64 mj = mods[Q0 + j];
+            u64 t = reduce_forced(lh, mj);
+            t = mod_sub(t, half_mod[loc + Q0 + j], mj.value);
+            t = mod_sub(last_ct[j], t, mj.value);
+            last_ct[j] = barrett_mul(t, last_q_modinv[loc + Q0 + j], mj);
+        }
+        u64 t = reduce_forced(lh, my);
+        t = mod_sub(t, half_mod[loc + y], my.value);
+        t = mod_sub(x, t, my.value);
+        x = barrett_mul(t, last_q_modinv[loc + y], my);
+        loc += Qp0 - 1 - i;
+    }
+
+    if (!PERMUTE)
+    {
+        out[bz * out_bs + ((long long) (c * L + y) << logn) + idx] = x;
+    }
+    else
+    {
+        if (c == 0)
+        {
+            u64 cin = c0coef[((bz * 2 * L + y) << logn) + idx];
+            x = mod_add(cin, x, my.value);
+        }
+        const unsigned raw = (unsigned) idx * galois_elt; // low n+1 bits are all that matter
+        const unsigned dst = raw & ((1u << logn) - 1);
+        if ((raw >> logn) & 1)
+            x = my.value - x;
+        out[bz * out_bs + ((long long) (c * L + y) << logn) + dst] = x;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// rescale / mod-drop tails
+// ---------------------------------------------------------------------------
+
+// ct[c][y] = (ct[c][y] - corr[c][y]) * q_last^-1, compacted from [2][L] to
+// [2][L-1] in place.  One thread walks all limbs of a coefficient in
+// ascending order, so reads of slot c*L+y always precede the write that
+// reuses it (no staging copy needed).
+// reference: src/lib/kernel/switchkey.cu:776-815
+// (move_cipher_leveled_kernel + divide_round_lastq_rescale_kernel)
+__global__ void __launch_bounds__(256)
+    k_rescale_tail(const u64* __restrict__ corr, u64* __restrict__ ct, long long ct_bs,
+                   const Mod64* __restrict__ mods, const u64* __restrict__ inv, int logn, int L)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const long long bz = blockIdx.y;
+    u64* p = ct + bz * ct_bs + idx;
+    const int Lo = L - 1;
+    for (int c = 0; c < 2; ++c)
+        for (int y = 0; y < Lo; ++y)
+        {
+            const Mod64 m = mods[y];
+            u64 x = p[(long long) (c * L + y) << logn];
+            u64 last = corr[(((bz * 2 + c) * Lo + y) << logn) + idx];
+            x = mod_sub(x, last, m.value);
+            x = barrett_mul(x, inv[y], m);
+            p[(long long) (c * Lo + y) << logn] = x;
+        }
+}
+
+// [comps][L][N] -> [comps][L-1][N] in place (drop the last limb of each component).
+// reference: ckks/operator.cu:1246-1276 (mod_drop_ckks_leveled_inplace)
+__global__ void __launch_bounds__(256)
+    k_mod_drop_inplace(u64* __restrict__ ct, long long ct_bs, int logn, int L, int comps)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    u64* p = ct + (long long) blockIdx.y * ct_bs + idx;
+    for (int c = 1; c < comps; ++c)
+        for (int y = 0; y < L - 1; ++y)
+            p[(long long) (c * (L - 1) + y) << logn] = p[(long long) (c * L + y) << logn];
+}
+
+__global__ void __launch_bounds__(256)
+    k_mod_drop(const u64* __restrict__ in, long long in_bs, u64* __restrict__ out, long long out_bs,
+               int logn, int L)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    const long long bz = blockIdx.z >> 1;
+    const int c = blockIdx.z & 1;
+    out[bz * out_bs + ((long long) (c * (L - 1) + y) << logn) + idx] =
+        in[bz * in_bs + ((long long) (c * L + y) << logn) + idx];
+}
+
+// ---------------------------------------------------------------------------
+// workspace (stream-ordered, cached by the device's default memory pool)
+// ---------------------------------------------------------------------------
+
+struct Scratch {
+    void* p = nullptr;
+    cudaStream_t st;
+    Scratch(size_t bytes, cudaStream_t s) : st(s)
+    {
+        cudaError_t e = cudaMallocAsync(&p, bytes, s);
+        if (e != cudaSuccess)
+            throw std::runtime_error(std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+    }
+    ~Scratch()
+    {
+        if (p)
+            cudaFreeAsync(p, st);
+    }
+    u64* w() const { return (u64*) p; }
+};
+
+static void check_launch()
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        throw std::runtime_error(std::string("kernel launch: ") + cudaGetErrorString(e));
+}
+
+static void check_depth(const Context& c, int depth)
+{
+    if (depth < 0 || depth >= c.Q_size)
+        throw std::invalid_argument("invalid depth");
+}
+
+// ---------------------------------------------------------------------------
+// operators
+// ---------------------------------------------------------------------------
+
+void op_add(const Context& c, const u64* a, long long a_bs, const u64* b, long long b_bs, u64* out,
+            long long o_bs, int comps, int depth, int batch, int op, cudaStream_t st)
+{
+    check_depth(c, depth);
+    const int L = c.Q_size - depth;
+    dim3 g(c.n >> 8, L, batch * comps);
+    if (op == 0)
+        k_addsub<0><<<g, 256, 0, st>>>(a, b, out, a_bs, b_bs, o_bs, c.d_mod, c.logn, L, comps);
+    else if (op == 1)
+        k_addsub<1><<<g, 256, 0, st>>>(a, b, out, a_bs, b_bs, o_bs, c.d_mod, c.logn, L, comps);
+    else
+        k_addsub<2><<<g, 256, 0, st>>>(a, a, out, a_bs, a_bs, o_bs, c.d_mod, c.logn, L, comps);
+    check_launch();
+}
+
+void op_multiply(const Context& c, const u64* a, long long a_bs, const u64* b, long long b_bs,
+                 u64* out, long long o_bs, int depth, int batch, cudaStream_t st)
+{
+    check_depth(c, depth);
+    const int L = c.Q_size - depth;
+    dim3 g(c.n >> 8, L, batch);
+    k_cross_multiply<<<g, 256, 0, st>>>(a, b, out, a_bs, b_bs, o_bs, c.d_mod, c.logn, L);
+    check_launch();
+}
+
+// Key-switch core shared by relinearize / apply_galois / keyswitch:
+// takes the digit polynomial(s) in the coefficient domain and leaves
+// acc[b][2][Qpl][N] (NTT domain).  `tmp` must hold batch*d*Qpl*N words.
+static int keyswitch_core(const Context& c, const u64* coef, long long coef_bs, const u64* key,
+                          u64* tmp, u64* acc, int depth, int batch, cudaStream_t st)
+{
+    const int L = c.Q_size - depth, K = c.P_size, Qpl = L + K;
+    int d;
+    if (c.method == 1)
+    {
+        d = L;
+        launch_modup1_ntt(c, coef, coef_bs, tmp, L, depth, batch, st);
+    }
+    else
+    {
+        const LevelTablesII& t = c.lvl2[depth];
+        d = t.d;
+        dim3 g(c.n >> 8, d, batch);
+        k_modup2<<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_mod, t.d_base_change, t.d_mi_inv,
+                                     t.d_prod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth);
+        check_launch();
+        launch_ntt(c, tmp, tmp, (long long) batch * d * Qpl, level_primes(L, K, depth), false, st);
+    }
+    if (d > 64)
+        throw std::invalid_argument("too many key-switch digits");
+    dim3 g(c.n >> 9, Qpl, batch);
+    k_keyswitch_mac<<<g, 256, 0, st>>>(tmp, key, acc, c.d_pc, c.logn, d, L, Qpl, c.Qp, depth);
+    check_launch();
+    return d;
+}
+
+static size_t ks_tmp_words(const Context& c, int depth, int batch)
+{
+    const int L = c.Q_size - depth, Qpl = L + c.P_size;
+    const int d = (c.method == 1) ? L : c.lvl2[depth].d;
+    return (size_t) batch * d * Qpl * c.n;
+}
+
+// Mod-down of acc[b][2][Qpl][N] (NTT domain) and accumulation into ct.
+//  Method I : INTT the single P limb, stage one fused into the forward NTT of
+//             the corrections, stage two in the NTT domain.
+//  Method II: INTT everything, coefficient-domain peel, NTT, add.
+static void moddown_add(const Context& c, u64* acc, u64* tmp, const u64* ct_in, long long ct_bs,
+                        u64* out, long long out_bs, int depth, int batch, int add_mask,
+                        cudaStream_t st)
+{
+    const int L = c.Q_size - depth, K = c.P_size, Qpl = L + K;
+    const long long N = c.n;
+    if (c.method == 1)
+    {
+        // P limb of both components: acc + (b*2+c)*Qpl*N + L*N
+        launch_ntt_strided(c, acc + (long long) L * N, Qpl * N, 1, 0, (long long) batch * 2,
+                           range_primes(c.Q_size, 1), true, st);
+        launch_divround1_ntt(c, acc + (long long) L * N, 2 * Qpl * N, Qpl * N, tmp, L, c.half[0],
+                             c.mod[c.Q_size].value, c.d_half_mod, batch, st);
+        dim3 g(c.n >> 8, L, batch * 2);
+        k_moddown1_stage2<<<g, 256, 0, st>>>(tmp, acc, ct_in, ct_bs, out, out_bs, c.d_mod,
+                                              c.d_last_q_modinv, c.logn, L, Qpl, add_mask);
+        check_launch();
+    }
+    else
+    {
+        launch_ntt(c, acc, acc, (long long) batch * 2 * Qpl, level_primes(L, K, depth), true, st);
+        dim3 g(c.n >> 8, L, batch * 2);
+        k_moddown_ext<false><<<g, 256, 0, st>>>(acc, tmp, 2 * L * N, nullptr, c.d_mod, c.d_half,
+                                                c.d_half_mod, c.d_last_q_modinv, 0, c.logn, Qpl, L,
+                                                c.Qp, c.Q_size, K);
+        check_launch();
+        launch_ntt(c, tmp, tmp, (long long) batch * 2 * L, range_primes(0, L), false, st);
+        // out = tmp + ct (components selected by add_mask)
+        for (int comp = 0; comp < 2; ++comp)
+        {
+            dim3 g2(c.n >> 8, L, batch);
+            const u64* t = tmp + (long long) comp * L * N;
+            u64* o = out + (long long) comp * L * N;
+            if ((add_mask >> comp) & 1)
+                k_addsub<0><<<g2, 256, 0, st>>>(t, ct_in + (long long) comp * L * N, o, 2 * L * N,
+                                               ct_bs, out_bs, c.d_mod, c.logn, L, 1);
+            else
+                cudaMemcpy2DAsync(o, out_bs * 8, t, 2 * L * N * 8, L * N * 8, batch,
+                                  cudaMemcpyDeviceToDevice, st);
+            check_launch();
+        }
+    }
+}
+
+// ct: [b][3][L][N] NTT domain, in place; on return components 0,1 hold the
+// relinearized ciphertext and component 2 holds INTT(c2) (as in the reference).
+// reference: ckks/operator.cu:899-1023 (Method I), 1025-1154 (Method II)
+void op_relinearize(const Context& c, u64* ct, long long ct_bs, const u64* relin_key, int depth,
+                    int batch, cudaStream_t st)
+{
+    check_depth(c, depth);
+    const int L = c.Q_size - depth, K = c.P_size, Qpl = L + K;
+    const long long N = c.n;
+    // INTT c2 in place
+    launch_ntt_strided(c, ct, ct_bs, L, 2 * L, batch, range_primes(0, L), true, st);
+    Scratch tmp(ks_tmp_words(c, depth, batch) * 8, st);
+    Scratch acc((size_t) batch * 2 * Qpl * N * 8, st);
+    keyswitch_core(c, ct + 2LL * L * N, ct_bs, relin_key, tmp.w(), acc.w(), depth, batch, st);
+    moddown_add(c, acc.w(), tmp.w(), ct, ct_bs, ct, ct_bs, depth, batch, 3, st);
+}
+
+// ct: [b][2][L][N] -> [b][2][L-1][N] compacted in place.
+// reference: ckks/operator.cu:1156-1244 (rescale_inplace_ckks_leveled)
+void op_rescale(const Context& c, u64* ct, long long ct_bs, int depth, int batch, cudaStream_t st)
+{
+    check_depth(c, depth);
+    const int L = c.Q_size - depth;
+    if (L < 2)
+        throw std::logic_error("Ciphertext modulus can not be dropped!");
+    const long long N = c.n;
+    int location = 0;
+    for (int i = 0, cnt = c.Q_size - 1; i < depth; ++i, --cnt)
+        location += cnt;
+    // INTT the last limb of both components: ct + b*bs + (c*L + L-1)*N
+    // (two strided launches: component 0 and component 1)
+    for (int comp = 0; comp < 2; ++comp)
+        launch_ntt_strided(c, ct, ct_bs, 1, comp * L + L - 1, batch, range_primes(L - 1, 1), true,
+                           st);
+    Scratch tmp((size_t) batch * 2 * (L - 1) * N * 8, st);
+    launch_divround1_ntt(c, ct + (long long) (L - 1) * N, ct_bs, L * N, tmp.w(), L - 1,
+                         c.rescaled_half[depth], c.mod[L - 1].value,
+                         c.d_rescaled_half_mod + location, batch, st);
+    dim3 g(c.n >> 8, batch);
+    k_rescale_tail<<<g, 256, 0, st>>>(tmp.w(), ct, ct_bs, c.d_mod,
+                                       c.d_rescaled_last_q_modinv + location, c.logn, L);
+    check_launch();
+}
+
+void op_mod_drop_inplace(const Context& c, u64* ct, long long ct_bs, int comps, int depth, int batch,
+                         cudaStream_t st)
+{
+    check_depth(c, depth);
+    const int L = c.Q_size - depth;
+    if (L < 2)
+        throw std::logic_error("Ciphertext modulus can not be dropped!");
+    dim3 g(c.n >> 8, batch);
+    k_mod_drop_inplace<<<g, 256, 0, st>>>(ct, ct_bs, c.logn, L, comps);
+    check_launch();
+}
+
+void op_mod_drop(const Context& c, const u64* in, long long in_bs, u64* out, long long out_bs,
+                 int depth, int batch, cudaStream_t st)
+{
+    check_depth(c, depth);
+    const int L = c.Q_size - depth;
+    if (L < 2)
+        throw std::logic_error("Ciphertext modulus can not be dropped!");
+    dim3 g(c.n >> 8, L - 1, batch * 2);
+    k_mod_drop<<<g, 256, 0, st>>>(in, in_bs, out, out_bs, c.logn, L);
+    check_launch();
+}
+
+// out = automorphism_g(in) key-switched back to the original key.
+// reference: ckks/operator.cu:1422-1559 (Method I), 1561-1720 (Method II)
+void op_apply_galois(const Context& c, const u64* in, long long in_bs, u64* out, long long out_bs,
+                     const u64* galois_key, unsigned galois_elt, int depth, int batch,
+                     cudaStream_t st)
+{
+    check_depth(c, depth);
+    const int L = c.Q_size - depth, K = c.P_size, Qpl = L + K;
+    const long long N = c.n;
+    Scratch coef((size_t) batch * 2 * L * N * 8, st);
+    launch_ntt_strided_copy(c, in, in_bs, coef.w(), 2 * L, batch, range_primes(0, L), true, st);
+    Scratch tmp(ks_tmp_words(c, depth, batch) * 8, st);
+    Scratch acc((size_t) batch * 2 * Qpl * N * 8, st);
+    keyswitch_core(c, coef.w() + (long long) L * N, 2 * L * N, galois_key, tmp.w(), acc.w(), depth,
+                   batch, st);
+    launch_ntt(c, acc.w(), acc.w(), (long long) batch * 2 * Qpl, level_primes(L, K, depth), true, st);
+    dim3 g(c.n >> 8, L, batch * 2);
+    k_moddown_ext<true><<<g, 256, 0, st>>>(acc.w(), out, out_bs, coef.w(), c.d_mod, c.d_half,
+                                           c.d_half_mod, c.d_last_q_modinv, galois_elt, c.logn, Qpl,
+                                           L, c.Qp, c.Q_size, K);
+    check_launch();
+    launch_ntt_strided(c, out, out_bs, 2 * L, 0, batch, range_primes(0, L), false, st);
+}
+
+} // namespace heon

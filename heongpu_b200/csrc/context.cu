@@ -1,0 +1,232 @@
+// Context construction: prime chain, roots, NTT tables and every key-switch /
+// rescale constant the kernels consume.
+//
+// Table contents follow the reference bit for bit (all entries are exact
+// canonical residues, which is what the reference's host Barrett code yields):
+//   primes / psi / ntt tables     src/lib/util/util.cu:219-276,356-464
+//   last_q_modinv, half, half_mod src/lib/util/util.cu:700-767
+//   rescale tables                src/lib/host/ckks/context.cu:342-368
+//   Method-II level tables        src/lib/kernel/contextpool.cpp:11-66,193-438
+#include <cstring>
+#include "heon_internal.hpp"
+#include "modarith.cuh"
+
+namespace heon {
+
+#define HEON_CUDA(x)                                                                               \
+    do                                                                                             \
+    {                                                                                              \
+        cudaError_t e_ = (x);                                                                      \
+        if (e_ != cudaSuccess)                                                                     \
+            throw std::runtime_error(std::string("CUDA: ") + cudaGetErrorString(e_));              \
+    } while (0)
+
+template <class T> static T* upload(const std::vector<T>& h)
+{
+    if (h.empty())
+        return nullptr;
+    T* d = nullptr;
+    HEON_CUDA(cudaMalloc(&d, h.size() * sizeof(T)));
+    HEON_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+
+static std::vector<int> digit_sizes(int l, int m)
+{
+    std::vector<int> r;
+    while (l > 0)
+    {
+        r.push_back(l > m ? m : l);
+        l -= m;
+    }
+    return r;
+}
+
+void build_host_tables(Context& c)
+{
+    const int N = c.n, Qp = c.Qp, Q = c.Q_size, K = c.P_size;
+    c.psi.resize(Qp);
+    c.ntt_table.assign((size_t) Qp * N, 0);
+    c.intt_table.assign((size_t) Qp * N, 0);
+    c.n_inverse.resize(Qp);
+    std::vector<u64> pw(N);
+    for (int i = 0; i < Qp; ++i)
+    {
+        const u64 p = c.mod[i].value;
+        c.psi[i] = minimal_primitive_root(2 * (u64) N, p);
+        for (int pass = 0; pass < 2; ++pass)
+        {
+            const u64 root = pass ? invmod(c.psi[i], p) : c.psi[i];
+            pw[0] = 1;
+            for (int j = 1; j < N; ++j)
+                pw[j] = mulmod(pw[j - 1], root, p);
+            u64* dst = (pass ? c.intt_table.data() : c.ntt_table.data()) + (size_t) i * N;
+            for (int j = 0; j < N; ++j)
+                dst[j] = pw[bitrev(j, c.logn)];
+        }
+        c.n_inverse[i] = invmod(N, p);
+    }
+
+    // mod-down constants, one block per dropped P prime (last P first)
+    c.last_q_modinv.clear();
+    c.half.clear();
+    c.half_mod.clear();
+    c.factor.clear();
+    for (int i = 0; i < K; ++i)
+    {
+        const u64 last = c.mod[Qp - 1 - i].value;
+        c.half.push_back(last >> 1);
+        for (int j = 0; j < Qp - 1 - i; ++j)
+        {
+            const u64 pj = c.mod[j].value;
+            c.last_q_modinv.push_back(invmod(last % pj, pj));
+            c.half_mod.push_back((last >> 1) % pj);
+        }
+        for (int j = 0; j < Q; ++j)
+            c.factor.push_back(last % c.mod[j].value);
+    }
+
+    // rescale constants for every depth
+    c.rescaled_half.clear();
+    c.rescaled_half_mod.clear();
+    c.rescaled_last_q_modinv.clear();
+    for (int j = 0; j < Q - 1; ++j)
+    {
+        const int inner = Q - 1 - j;
+        const u64 ql = c.mod[inner].value;
+        c.rescaled_half.push_back(ql >> 1);
+        for (int i = 0; i < inner; ++i)
+        {
+            const u64 pi = c.mod[i].value;
+            c.rescaled_last_q_modinv.push_back(invmod(ql % pi, pi));
+            c.rescaled_half_mod.push_back((ql >> 1) % pi);
+        }
+    }
+
+    // Method II (hybrid key switching with K > 1): per-depth digit tables
+    c.lvl2.clear();
+    if (c.method == 2 && c.scheme == SCHEME_CKKS)
+    {
+        for (int depth = 0; depth < Q; ++depth)
+        {
+            const int L = Q - depth;
+            // limb set at this depth: q_0..q_{L-1}, p_0..p_{K-1}
+            std::vector<u64> base;
+            for (int y = 0; y < L + K; ++y)
+                base.push_back(c.mod[level_prime(y, L, depth)].value);
+            LevelTablesII t;
+            t.I_j = digit_sizes(L, K);
+            t.d = (int) t.I_j.size();
+            t.I_loc.assign(t.d, 0);
+            for (int l = 1; l < t.d; ++l)
+                t.I_loc[l] = t.I_loc[l - 1] + t.I_j[l - 1];
+            for (int l = 0; l < t.d; ++l)
+            {
+                const int lo = t.I_loc[l], sz = t.I_j[l];
+                for (int k = 0; k < L + K; ++k)
+                {
+                    const u64 tk = base[k];
+                    for (int i = 0; i < sz; ++i)
+                    {
+                        u64 prod = 1;
+                        for (int j = 0; j < sz; ++j)
+                            if (j != i)
+                                prod = mulmod(prod, base[lo + j] % tk, tk);
+                        t.base_change.push_back(prod);
+                    }
+                }
+                for (int i = 0; i < sz; ++i)
+                {
+                    const u64 qi = base[lo + i];
+                    u64 prod = 1;
+                    for (int j = 0; j < sz; ++j)
+                        if (j != i)
+                            prod = mulmod(prod, base[lo + j] % qi, qi);
+                    t.mi_inv.push_back(invmod(prod, qi));
+                }
+                for (int k = 0; k < L + K; ++k)
+                {
+                    const u64 tk = base[k];
+                    u64 prod = 1;
+                    for (int j = 0; j < sz; ++j)
+                        prod = mulmod(prod, base[lo + j] % tk, tk);
+                    t.prod.push_back(prod);
+                }
+            }
+            c.lvl2.push_back(std::move(t));
+        }
+    }
+}
+
+void upload_tables(Context& c)
+{
+    const int N = c.n, Qp = c.Qp;
+    HEON_CUDA(cudaSetDevice(c.device));
+    c.d_mod = upload(c.mod);
+    std::vector<PrimeConst> pcs(Qp);
+    std::vector<TwPair> fwd((size_t) Qp * N), inv((size_t) Qp * N), last(2 * (size_t) Qp);
+    for (int i = 0; i < Qp; ++i)
+    {
+        const u64 p = c.mod[i].value;
+        pcs[i].p = p;
+        pcs[i].inv64 = shoup(1, p);
+        pcs[i].r64 = (u64) ((((u128) 1) << 64) % p);
+        pcs[i].r64s = shoup(pcs[i].r64, p);
+        for (int j = 0; j < N; ++j)
+        {
+            const size_t o = (size_t) i * N + j;
+            fwd[o].w = c.ntt_table[o];
+            fwd[o].ws = shoup(c.ntt_table[o], p);
+            inv[o].w = c.intt_table[o];
+            inv[o].ws = shoup(c.intt_table[o], p);
+        }
+        const u64 ninv = c.n_inverse[i];
+        const u64 wn = mulmod(c.intt_table[(size_t) i * N + 1], ninv, p);
+        last[2 * i] = TwPair{ninv, shoup(ninv, p)};
+        last[2 * i + 1] = TwPair{wn, shoup(wn, p)};
+    }
+    c.d_pc = upload(pcs);
+    c.d_fwd = upload(fwd);
+    c.d_inv = upload(inv);
+    c.d_inv_last = upload(last);
+    c.d_last_q_modinv = upload(c.last_q_modinv);
+    c.d_half = upload(c.half);
+    c.d_half_mod = upload(c.half_mod);
+    c.d_rescaled_last_q_modinv = upload(c.rescaled_last_q_modinv);
+    c.d_rescaled_half_mod = upload(c.rescaled_half_mod);
+    c.d_rescaled_half = upload(c.rescaled_half);
+    for (auto& t : c.lvl2)
+    {
+        t.d_base_change = upload(t.base_change);
+        t.d_mi_inv = upload(t.mi_inv);
+        t.d_prod = upload(t.prod);
+        t.d_I_j = upload(t.I_j);
+        t.d_I_loc = upload(t.I_loc);
+    }
+}
+
+Context::~Context()
+{
+    cudaSetDevice(device);
+    cudaFree(d_mod);
+    cudaFree(d_pc);
+    cudaFree(d_fwd);
+    cudaFree(d_inv);
+    cudaFree(d_inv_last);
+    cudaFree(d_last_q_modinv);
+    cudaFree(d_half);
+    cudaFree(d_half_mod);
+    cudaFree(d_rescaled_last_q_modinv);
+    cudaFree(d_rescaled_half_mod);
+    cudaFree(d_rescaled_half);
+    for (auto& t : lvl2)
+    {
+        cudaFree(t.d_base_change);
+        cudaFree(t.d_mi_inv);
+        cudaFree(t.d_prod);
+        cudaFree(t.d_I_j);
+        cudaFree(t.d_I_loc);
+    }
+}
+
+} // namespace heon

@@ -1,0 +1,128 @@
+// Internal context of the B200 RNS engine (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "host_math.hpp"
+
+namespace heon {
+
+enum Scheme { SCHEME_BFV = 1, SCHEME_CKKS = 2 };
+
+// Shoup pair: multiplier w (< p) and floor(w * 2^64 / p).
+struct alignas(16) TwPair {
+    u64 w;
+    u64 ws;
+};
+
+// Per-prime constants used by the fused kernels.
+struct PrimeConst {
+    u64 p;
+    u64 inv64; // floor(2^64 / p): Shoup word of the multiplier 1
+    u64 r64; // 2^64 mod p
+    u64 r64s; // Shoup word of r64
+};
+
+// Method-II (hybrid, K > 1) level tables; one entry per depth.
+// Layouts follow src/lib/kernel/contextpool.cpp:193-438 of the reference.
+struct LevelTablesII {
+    int d = 0; // digit count at this depth
+    std::vector<u64> base_change; // [digit][k over Q'_l][i in digit]
+    std::vector<u64> mi_inv; // [I_location + i]
+    std::vector<u64> prod; // [digit][k over Q'_l]
+    std::vector<int> I_j; // digit sizes
+    std::vector<int> I_loc; // prefix sums
+    // device copies
+    u64* d_base_change = nullptr;
+    u64* d_mi_inv = nullptr;
+    u64* d_prod = nullptr;
+    int* d_I_j = nullptr;
+    int* d_I_loc = nullptr;
+};
+
+struct Context {
+    int device = 0;
+    int scheme = SCHEME_CKKS;
+    int n = 0, logn = 0;
+    int Q_size = 0, P_size = 0, Qp = 0;
+    int method = 1; // key-switching method: 1 (K == 1) or 2 (K > 1)
+    std::vector<Mod64> mod; // [q_0..q_{Q-1}, p_0..p_{K-1}]
+    std::vector<u64> psi; // minimal primitive 2N-th roots
+
+    // Reference-layout host tables (kept for introspection and parity tests).
+    std::vector<u64> ntt_table, intt_table, n_inverse;
+    std::vector<u64> last_q_modinv, half, half_mod, factor;
+    std::vector<u64> rescaled_last_q_modinv, rescaled_half_mod, rescaled_half;
+    std::vector<LevelTablesII> lvl2; // Method II only
+
+    // BFV plain modulus etc. (BFV contexts only)
+    u64 plain_modulus = 0;
+
+    // Device tables
+    Mod64* d_mod = nullptr; // [Qp]
+    PrimeConst* d_pc = nullptr; // [Qp]
+    TwPair* d_fwd = nullptr; // [Qp][N]  psi^bitrev(i) with Shoup word
+    TwPair* d_inv = nullptr; // [Qp][N]  psi^-bitrev(i) with Shoup word
+    TwPair* d_inv_last = nullptr; // [Qp][2] {n^-1, W_inv[1]*n^-1}
+    u64* d_last_q_modinv = nullptr;
+    u64* d_half = nullptr;
+    u64* d_half_mod = nullptr;
+    u64* d_rescaled_last_q_modinv = nullptr;
+    u64* d_rescaled_half_mod = nullptr;
+    u64* d_rescaled_half = nullptr;
+
+    std::string last_error;
+
+    ~Context();
+};
+
+// Prime index used by slot y of a levelled limb set {q_0..q_{L-1}, p_0..p_{K-1}}:
+// y < L -> y, else y + depth   (reference: ckks/operator.cu:24-39).
+__host__ __device__ inline int level_prime(int y, int L, int depth) { return y < L ? y : y + depth; }
+
+// Small by-value list of prime indices (one per limb slot of a limb set).
+struct PrimeList {
+    int count;
+    unsigned char idx[128];
+};
+
+inline PrimeList level_primes(int L, int K, int depth)
+{
+    PrimeList pl;
+    pl.count = L + K;
+    for (int y = 0; y < L + K; ++y)
+        pl.idx[y] = (unsigned char) level_prime(y, L, depth);
+    return pl;
+}
+inline PrimeList range_primes(int first, int count)
+{
+    PrimeList pl;
+    pl.count = count;
+    for (int y = 0; y < count; ++y)
+        pl.idx[y] = (unsigned char) (first + y);
+    return pl;
+}
+
+void build_host_tables(Context& c);
+void upload_tables(Context& c);
+
+// ---- NTT launchers (ntt.cu); all asynchronous on `st` ----
+void launch_ntt(const Context& c, const u64* src, u64* dst, long long n_polys, const PrimeList& pl,
+                bool inverse, cudaStream_t st);
+void launch_ntt_scattered(const Context& c, u64* base, const long long* d_offsets, int n_polys,
+                          int prime, bool inverse, cudaStream_t st);
+void launch_ntt_strided(const Context& c, u64* base, long long bstride, int per_batch, int first,
+                        long long batch, const PrimeList& pl, bool inverse, cudaStream_t st);
+void launch_ntt_strided_copy(const Context& c, const u64* src, long long src_bstride, u64* dst,
+                             int per_batch, long long batch, const PrimeList& pl, bool inverse,
+                             cudaStream_t st);
+void launch_modup1_ntt(const Context& c, const u64* coef, long long coef_bstride, u64* out, int L,
+                       int depth, long long batch, cudaStream_t st);
+void launch_divround1_ntt(const Context& c, const u64* src, long long bstride, long long cstride,
+                          u64* out, int Lout, u64 half, u64 plast, const u64* d_half_mod,
+                          long long batch, cudaStream_t st);
+
+} // namespace heon

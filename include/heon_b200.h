@@ -1,0 +1,164 @@
+/*
+ * heon_b200.h -- C ABI of the B200-native RNS-FHE arithmetic engine.
+ *
+ * Drop-in boundary for ONE hot path of Alisah-Ozcan/HEonGPU: batched
+ * negacyclic NTT/INTT over RNS limbs, RNS base conversion (mod-up, mod-down,
+ * rescale) and the key-switch inner product behind multiply -> relinearize
+ * (-> rescale) and rotate.  The reference exposes this path as a C++ class
+ * layer (no FFI); each entry point below names the reference host function
+ * (file:line under the reference tree) whose launch sequence it replaces.
+ * The `heongpu::` C++ classes in heongpu_b200/include/heongpu/ forward to
+ * these functions with batch = 1.
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers to 64-bit words unless the name
+ *    starts with h_.  Residues are canonical (0 <= x < p).
+ *  - Ciphertext layout is the reference's: [components][L][N] words with
+ *    L = Q_size - depth (src/lib/host/ckks/ciphertext.cu:20-31); CKKS
+ *    ciphertexts live in the NTT domain.
+ *  - Batched calls take a batch count and, per buffer, a batch stride in
+ *    words: element b of the batch starts at ptr + b*stride.
+ *  - Evaluation keys use the reference layout [digit][2][Q'_0][N]
+ *    (src/lib/kernel/keygeneration.cu:180-183), NTT domain.
+ *  - `stream` is a cudaStream_t passed as void*; everything is asynchronous
+ *    on it.  Scratch memory is stream-ordered (cudaMallocAsync).
+ *  - Every function returns HEON_OK (0) or a negative status; the message of
+ *    the last failure is available from heon_last_error().  No exceptions
+ *    cross the boundary.  (The reference throws std::invalid_argument /
+ *    std::logic_error / std::runtime_error; the class layer re-raises them.)
+ */
+#ifndef HEON_B200_H
+#define HEON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct heon_context_s* heon_context_t;
+
+enum {
+    HEON_OK = 0,
+    HEON_ERR_INVALID = -1, /* std::invalid_argument in the reference */
+    HEON_ERR_LOGIC = -2,   /* std::logic_error */
+    HEON_ERR_RUNTIME = -3, /* std::runtime_error / CUDA failure */
+    HEON_ERR_NO_DEVICE = -4
+};
+
+enum { HEON_SCHEME_BFV = 1, HEON_SCHEME_CKKS = 2 };
+
+/* table selectors for heon_context_table() (reference member names) */
+enum {
+    HEON_TBL_MODULUS = 0,       /* Modulus64 {value,bit,mu} x Q'           */
+    HEON_TBL_PSI = 1,           /* minimal primitive 2N-th roots x Q'     */
+    HEON_TBL_NTT = 2,           /* ntt_table_   [Q'][N]                    */
+    HEON_TBL_INTT = 3,          /* intt_table_  [Q'][N]                    */
+    HEON_TBL_N_INVERSE = 4,     /* n_inverse_   [Q']                       */
+    HEON_TBL_LAST_Q_MODINV = 5, /* last_q_modinv_                          */
+    HEON_TBL_HALF = 6,          /* half_p_                                 */
+    HEON_TBL_HALF_MOD = 7,      /* half_mod_                               */
+    HEON_TBL_FACTOR = 8,        /* factor_                                 */
+    HEON_TBL_RESCALED_LAST_Q_MODINV = 9,
+    HEON_TBL_RESCALED_HALF_MOD = 10,
+    HEON_TBL_RESCALED_HALF = 11,
+    HEON_TBL_II_BASE_CHANGE = 12, /* Method II, per depth (arg `depth`)    */
+    HEON_TBL_II_MI_INV = 13,
+    HEON_TBL_II_PROD = 14,
+    HEON_TBL_II_I_J = 15,      /* int32 widened to u64                     */
+    HEON_TBL_II_I_LOCATION = 16
+};
+
+typedef struct heon_info {
+    int scheme, n, log_n, q_size, p_size, keyswitch_method, device;
+} heon_info;
+
+const char* heon_last_error(void);
+const char* heon_version(void);
+
+/* ---- context: HEContext<Scheme::CKKS> ---------------------------------
+ * replaces HEContextImpl<CKKS>::set_poly_modulus_degree /
+ * set_coeff_modulus_bit_sizes / set_coeff_modulus_values / generate
+ * (src/lib/host/ckks/context.cu:26-260,267-539) and the table builders in
+ * src/lib/util/util.cu:219-276,356-464,700-767 and
+ * src/lib/kernel/contextpool.cpp:11-438.
+ * device < 0 builds the host tables only (no CUDA call is made). */
+int heon_ckks_context_create(int device, int log_n, const int* q_bits, int n_q, const int* p_bits,
+                             int n_p, heon_context_t* out);
+int heon_ckks_context_create_values(int device, int log_n, const uint64_t* q, int n_q,
+                                    const uint64_t* p, int n_p, heon_context_t* out);
+void heon_context_destroy(heon_context_t ctx);
+int heon_context_info(heon_context_t ctx, heon_info* out);
+/* Copies a host table into h_out (capacity `cap` words); *count receives the
+ * table length.  Pass h_out = NULL to query the length. */
+int heon_context_table(heon_context_t ctx, int which, int depth, uint64_t* h_out, size_t cap,
+                       size_t* count);
+/* steps_to_galois_elt (src/lib/kernel/keygeneration.cu:684-727); group_order 5 for CKKS, 3 for BFV */
+int heon_steps_to_galois_elt(int steps, int n, int group_order);
+
+/* ---- NTT: gpuntt::GPU_NTT / GPU_INTT and the *_Ordered variants --------
+ * (thirdparty/GPU-NTT/src/lib/ntt_merge/ntt.cu:2563-3103,3603-3783,4284-4466)
+ * n_polys polynomials of N words, polynomial z uses prime
+ * h_prime_index[z % mod_count] (an index into the context's Q' chain; this is
+ * `order[z % mod_count]` of GPU_NTT_Modulus_Ordered; pass NULL for the
+ * identity 0..mod_count-1 of plain GPU_NTT).  in == out is allowed. */
+int heon_ntt(heon_context_t ctx, const uint64_t* in, uint64_t* out, long long n_polys,
+             const int* h_prime_index, int mod_count, int inverse, void* stream);
+/* GPU_NTT_Poly_Ordered_Inplace: polynomials at word offsets h_offsets[z]
+ * from base, all with prime `prime_index`. */
+int heon_ntt_poly_ordered(heon_context_t ctx, uint64_t* base, const long long* h_offsets,
+                          int n_polys, int prime_index, int inverse, void* stream);
+
+/* ---- element-wise: HEOperator::add / sub / negate ----------------------
+ * (src/lib/host/ckks/operator.cu:66-140; kernels src/lib/kernel/addition.cu:10-49) */
+int heon_add(heon_context_t ctx, const uint64_t* a, long long a_stride, const uint64_t* b,
+             long long b_stride, uint64_t* out, long long out_stride, int components, int depth,
+             int batch, void* stream);
+int heon_sub(heon_context_t ctx, const uint64_t* a, long long a_stride, const uint64_t* b,
+             long long b_stride, uint64_t* out, long long out_stride, int components, int depth,
+             int batch, void* stream);
+int heon_negate(heon_context_t ctx, const uint64_t* a, long long a_stride, uint64_t* out,
+                long long out_stride, int components, int depth, int batch, void* stream);
+
+/* ---- HEOperator<CKKS>::multiply_ckks (operator.cu:796-837) -------------
+ * a, b: [2][L][N]; out: [3][L][N]. */
+int heon_ckks_multiply(heon_context_t ctx, const uint64_t* a, long long a_stride, const uint64_t* b,
+                       long long b_stride, uint64_t* out, long long out_stride, int depth, int batch,
+                       void* stream);
+
+/* ---- relinearize_seal_method_inplace_ckks (operator.cu:899-1023) and
+ *      relinearize_external_product_method2_inplace_ckks (:1025-1154);
+ * the method follows the context (P_size == 1 -> I, else II).
+ * ct: [3][L][N] in place; on return components 0 and 1 are the result and
+ * component 2 holds INTT(c2), exactly as the reference leaves it. */
+int heon_ckks_relinearize(heon_context_t ctx, uint64_t* ct, long long ct_stride,
+                          const uint64_t* relin_key, int depth, int batch, void* stream);
+
+/* ---- rescale_inplace_ckks_leveled (operator.cu:1156-1244) --------------
+ * ct: [2][L][N] -> [2][L-1][N] compacted in place. */
+int heon_ckks_rescale(heon_context_t ctx, uint64_t* ct, long long ct_stride, int depth, int batch,
+                      void* stream);
+
+/* ---- mod_drop_ckks_leveled[_inplace] (operator.cu:1246-1300) ----------- */
+int heon_ckks_mod_drop_inplace(heon_context_t ctx, uint64_t* ct, long long ct_stride, int components,
+                               int depth, int batch, void* stream);
+int heon_ckks_mod_drop(heon_context_t ctx, const uint64_t* in, long long in_stride, uint64_t* out,
+                       long long out_stride, int depth, int batch, void* stream);
+
+/* ---- apply_galois_ckks_method_I / _II (operator.cu:1422-1720) ----------
+ * in, out: [2][L][N] (distinct buffers); galois_key: the key for galois_elt
+ * ([digit][2][Q'_0][N]).  rotate_rows(shift) = apply_galois with
+ * galois_elt = heon_steps_to_galois_elt(shift, N, 5). */
+int heon_ckks_apply_galois(heon_context_t ctx, const uint64_t* in, long long in_stride,
+                           uint64_t* out, long long out_stride, const uint64_t* galois_key,
+                           uint32_t galois_elt, int depth, int batch, void* stream);
+
+/* Number of launches of this library's own kernels since the counter was
+ * last reset (bench.py reports it as gpu_launches). */
+long long heon_kernel_launches(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEON_B200_H */

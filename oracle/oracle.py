@@ -1,0 +1,191 @@
+"""ctypes/numpy wrapper of oracle/heon_oracle.c (the CPU restatement of the
+reference hot path).  TEST INFRASTRUCTURE ONLY -- see the header of
+heon_oracle.c for what each function restates and how the oracle is pinned."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libheon_oracle.so")
+u64p = C.POINTER(C.c_uint64)
+i32p = C.POINTER(C.c_int)
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "heon_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "oracle"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.oracle_mult.restype = C.c_uint64
+        L.oracle_mult.argtypes = [C.c_uint64] * 3
+        L.oracle_minimal_root.restype = C.c_uint64
+        L.oracle_minimal_root.argtypes = [C.c_uint64, C.c_uint64]
+        L.oracle_ctx_create.restype = C.c_void_p
+        L.oracle_ctx_create.argtypes = [C.c_int, u64p, C.c_int, C.c_int]
+        L.oracle_ctx_destroy.argtypes = [C.c_void_p]
+        L.oracle_digits.argtypes = [C.c_void_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(u64p)
+
+
+def _ip(a):
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(i32p)
+
+
+def make_mod(p):
+    out = (C.c_uint64 * 3)()
+    lib().oracle_make_mod(C.c_uint64(p), out)
+    return tuple(int(v) for v in out)
+
+
+def generate_primes(n, bits):
+    b = (C.c_int * len(bits))(*bits)
+    out = np.zeros(len(bits), dtype=np.uint64)
+    rc = lib().oracle_generate_primes(C.c_uint64(n), b, len(bits), _p(out))
+    if rc:
+        raise RuntimeError("failed to find enough qualifying primes")
+    return [int(v) for v in out]
+
+
+def ntt_tables(primes, n_power):
+    n = 1 << n_power
+    pr = np.array(primes, dtype=np.uint64)
+    psi = np.zeros(len(primes), dtype=np.uint64)
+    fwd = np.zeros(len(primes) * n, dtype=np.uint64)
+    inv = np.zeros(len(primes) * n, dtype=np.uint64)
+    ninv = np.zeros(len(primes), dtype=np.uint64)
+    lib().oracle_ntt_tables(_p(pr), len(primes), n_power, _p(psi), _p(fwd), _p(inv), _p(ninv))
+    return psi, fwd, inv, ninv
+
+
+def moddown_tables(primes, Q, K):
+    Qp = Q + K
+    pr = np.array(primes, dtype=np.uint64)
+    lqm = np.zeros(K * Qp, dtype=np.uint64)
+    half = np.zeros(K, dtype=np.uint64)
+    hm = np.zeros(K * Qp, dtype=np.uint64)
+    fac = np.zeros(K * Q, dtype=np.uint64)
+    w = lib().oracle_moddown_tables(_p(pr), Qp, K, Q, _p(lqm), _p(half), _p(hm), _p(fac))
+    return lqm[:w].copy(), half, hm[:w].copy(), fac
+
+
+def rescale_tables(primes, Q):
+    pr = np.array(primes, dtype=np.uint64)
+    a = np.zeros(Q * Q, dtype=np.uint64)
+    b = np.zeros(Q * Q, dtype=np.uint64)
+    h = np.zeros(max(Q - 1, 1), dtype=np.uint64)
+    w = lib().oracle_rescale_tables(_p(pr), Q, _p(a), _p(b), _p(h))
+    return a[:w].copy(), b[:w].copy(), h[: Q - 1].copy()
+
+
+def method2_tables(primes, Q, K, depth):
+    Qp = Q + K
+    pr = np.array(primes, dtype=np.uint64)
+    bc = np.zeros(Q * Qp * (K + 1), dtype=np.uint64)
+    mi = np.zeros(Q, dtype=np.uint64)
+    prod = np.zeros(Q * Qp, dtype=np.uint64)
+    ij = np.zeros(Q, dtype=np.int32)
+    il = np.zeros(Q, dtype=np.int32)
+    cnt = np.zeros(3, dtype=np.int32)
+    d = lib().oracle_method2_tables(_p(pr), Qp, K, depth, _p(bc), _p(mi), _p(prod), _ip(ij), _ip(il), _ip(cnt))
+    return dict(d=d, base_change=bc[: cnt[0]].copy(), mi_inv=mi[: cnt[1]].copy(), prod=prod[: cnt[2]].copy(),
+                I_j=ij[:d].copy(), I_location=il[:d].copy())
+
+
+class OracleContext:
+    """Bundle of tables + operator-level restatements (one ciphertext at a time)."""
+
+    def __init__(self, n_power, primes, Q, K):
+        self.n_power, self.n = n_power, 1 << n_power
+        self.Q, self.K, self.Qp = Q, K, Q + K
+        self.primes = [int(p) for p in primes]
+        self.method = 1 if K == 1 else 2
+        pr = np.array(self.primes, dtype=np.uint64)
+        self._h = C.c_void_p(lib().oracle_ctx_create(n_power, _p(pr), Q, K))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_ctx_destroy(self._h)
+            self._h = None
+
+    def level_primes(self, depth=0):
+        L = self.Q - depth
+        return list(range(L)) + [self.Q + j for j in range(self.K)]
+
+    def digits(self, depth=0):
+        return lib().oracle_digits(self._h, depth)
+
+    def ntt(self, data, order, inverse=False):
+        """data [..., N] uint64 (copied); poly z uses prime order[z % len(order)]."""
+        a = np.ascontiguousarray(data, dtype=np.uint64).copy()
+        o = np.array(order, dtype=np.int32)
+        lib().oracle_ntt_batch(self._h, _p(a), C.c_longlong(a.size // self.n), _ip(o), len(o), int(inverse))
+        return a
+
+    def multiply(self, a, b, depth=0):
+        L = self.Q - depth
+        out = np.zeros((3, L, self.n), dtype=np.uint64)
+        lib().oracle_cross_multiply(self._h, _p(np.ascontiguousarray(a)), _p(np.ascontiguousarray(b)), _p(out), depth)
+        return out
+
+    def addsub(self, a, b, op, depth=0):
+        a = np.ascontiguousarray(a)
+        b = np.ascontiguousarray(b)
+        out = np.zeros_like(a)
+        lib().oracle_addsub(self._h, _p(a), _p(b), _p(out), a.shape[0], depth, op)
+        return out
+
+    def relinearize(self, ct3, key, depth=0):
+        ct = np.ascontiguousarray(ct3, dtype=np.uint64).copy()
+        lib().oracle_relinearize(self._h, _p(ct), _p(np.ascontiguousarray(key)), depth)
+        return ct  # [3][L][N]: c0', c1', INTT(c2)
+
+    def rescale(self, ct2, depth=0):
+        L = self.Q - depth
+        ct = np.ascontiguousarray(ct2, dtype=np.uint64).copy()
+        lib().oracle_rescale(self._h, _p(ct), depth)
+        return ct.reshape(-1)[: 2 * (L - 1) * self.n].reshape(2, L - 1, self.n).copy()
+
+    def apply_galois(self, ct2, key, galois_elt, depth=0):
+        ct = np.ascontiguousarray(ct2, dtype=np.uint64)
+        out = np.zeros_like(ct)
+        lib().oracle_apply_galois(self._h, _p(ct), _p(out), _p(np.ascontiguousarray(key)), int(galois_elt), depth)
+        return out
+
+    def mod_drop(self, ct, depth=0):
+        ct = np.ascontiguousarray(ct, dtype=np.uint64)
+        comps, L = ct.shape[0], self.Q - depth
+        out = np.zeros((comps, L - 1, self.n), dtype=np.uint64)
+        lib().oracle_mod_drop(self._h, _p(ct), _p(out), comps, depth)
+        return out
+
+    def modup(self, coef, depth=0):
+        L = self.Q - depth
+        d = self.digits(depth)
+        out = np.zeros((d, L + self.K, self.n), dtype=np.uint64)
+        lib().oracle_modup(self._h, _p(np.ascontiguousarray(coef)), _p(out), depth)
+        return out
+
+    def keyswitch_core(self, coef, key, depth=0):
+        L = self.Q - depth
+        acc = np.zeros((2, L + self.K, self.n), dtype=np.uint64)
+        lib().oracle_keyswitch_core(self._h, _p(np.ascontiguousarray(coef)), _p(np.ascontiguousarray(key)), _p(acc), depth)
+        return acc
