@@ -39,6 +39,9 @@ SIGNATURES = {
     "heon_ckks_mod_drop_inplace": (ci, [vp, vp, ll, ci, ci, ci, vp]),
     "heon_ckks_mod_drop": (ci, [vp, vp, ll, vp, ll, ci, ci, vp]),
     "heon_ckks_apply_galois": (ci, [vp, vp, ll, vp, ll, vp, C.c_uint32, ci, ci, vp]),
+    "heon_profile_begin": (ci, []),
+    "heon_profile_end": (ci, [C.POINTER(C.c_double), i64p, ci]),
+    "heon_profile_class_name": (C.c_char_p, [ci]),
     "heon_kernel_launches": (ll, [ci]),
 }
 

@@ -1,6 +1,7 @@
 // extern "C" boundary: argument validation, exception -> status translation.
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include "../../include/heon_b200.h"
 #include "ops.hpp"
 
@@ -12,7 +13,63 @@ struct heon_context_s {
 
 namespace heon {
 std::atomic<long long> g_launches{0};
+
+static bool g_profiling = false;
+struct ProfRec {
+    int cls;
+    cudaEvent_t e0, e1;
+};
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+
+LaunchScope::LaunchScope(int c, cudaStream_t s) : cls(c), st(s)
+{
+    g_launches++;
+    if (g_profiling)
+    {
+        cudaEventCreate(&e0);
+        cudaEventRecord(e0, st);
+    }
 }
+LaunchScope::~LaunchScope()
+{
+    if (e0)
+    {
+        cudaEvent_t e1;
+        cudaEventCreate(&e1);
+        cudaEventRecord(e1, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.push_back(ProfRec{cls, e0, e1});
+    }
+}
+void profile_begin()
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.clear();
+    g_profiling = true;
+}
+void profile_end(double* ms, long long* launches)
+{
+    g_profiling = false;
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int i = 0; i < KC_COUNT; ++i)
+    {
+        ms[i] = 0;
+        launches[i] = 0;
+    }
+    for (auto& r : g_prof)
+    {
+        float t = 0;
+        cudaEventElapsedTime(&t, r.e0, r.e1);
+        ms[r.cls] += t;
+        launches[r.cls]++;
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+}
+} // namespace heon
 
 static thread_local std::string g_err;
 
@@ -337,6 +394,26 @@ int heon_ckks_apply_galois(heon_context_t ctx, const uint64_t* in, long long is,
             throw std::invalid_argument("invalid buffers");
         op_apply_galois(c, in, is, out, os, galois_key, galois_elt, depth, batch, st);
     });
+}
+
+int heon_profile_begin(void)
+{
+    profile_begin();
+    return HEON_OK;
+}
+int heon_profile_end(double* ms, long long* launches, int capacity)
+{
+    if (!ms || !launches || capacity < KC_COUNT)
+        return HEON_ERR_INVALID;
+    profile_end(ms, launches);
+    return KC_COUNT;
+}
+const char* heon_profile_class_name(int cls)
+{
+    static const char* names[KC_COUNT] = {"ntt_fwd_col_pass", "ntt_fwd_row_pass", "ntt_inv_row_pass",
+                                          "ntt_inv_col_pass", "keyswitch_mac",   "modup_method2",
+                                          "moddown",          "cross_multiply",  "elementwise"};
+    return (cls >= 0 && cls < KC_COUNT) ? names[cls] : "";
 }
 
 long long heon_kernel_launches(int reset)

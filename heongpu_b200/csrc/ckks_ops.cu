@@ -361,11 +361,20 @@ void op_add(const Context& c, const u64* a, long long a_bs, const u64* b, long l
     const int L = c.Q_size - depth;
     dim3 g(c.n >> 8, L, batch * comps);
     if (op == 0)
-        k_addsub<0><<<g, 256, 0, st>>>(a, b, out, a_bs, b_bs, o_bs, c.d_mod, c.logn, L, comps);
+        {
+            LaunchScope scope(KC_ELEMENTWISE, st);
+            k_addsub<0><<<g, 256, 0, st>>>(a, b, out, a_bs, b_bs, o_bs, c.d_mod, c.logn, L, comps);
+        }
     else if (op == 1)
-        k_addsub<1><<<g, 256, 0, st>>>(a, b, out, a_bs, b_bs, o_bs, c.d_mod, c.logn, L, comps);
+        {
+            LaunchScope scope(KC_ELEMENTWISE, st);
+            k_addsub<1><<<g, 256, 0, st>>>(a, b, out, a_bs, b_bs, o_bs, c.d_mod, c.logn, L, comps);
+        }
     else
-        k_addsub<2><<<g, 256, 0, st>>>(a, a, out, a_bs, a_bs, o_bs, c.d_mod, c.logn, L, comps);
+        {
+            LaunchScope scope(KC_ELEMENTWISE, st);
+            k_addsub<2><<<g, 256, 0, st>>>(a, a, out, a_bs, a_bs, o_bs, c.d_mod, c.logn, L, comps);
+        }
     check_launch();
 }
 
@@ -375,7 +384,10 @@ void op_multiply(const Context& c, const u64* a, long long a_bs, const u64* b, l
     check_depth(c, depth);
     const int L = c.Q_size - depth;
     dim3 g(c.n >> 8, L, batch);
-    k_cross_multiply<<<g, 256, 0, st>>>(a, b, out, a_bs, b_bs, o_bs, c.d_mod, c.logn, L);
+    {
+        LaunchScope scope(KC_CROSS_MULTIPLY, st);
+        k_cross_multiply<<<g, 256, 0, st>>>(a, b, out, a_bs, b_bs, o_bs, c.d_mod, c.logn, L);
+    }
     check_launch();
 }
 
@@ -397,15 +409,21 @@ static int keyswitch_core(const Context& c, const u64* coef, long long coef_bs, 
         const LevelTablesII& t = c.lvl2[depth];
         d = t.d;
         dim3 g(c.n >> 8, d, batch);
-        k_modup2<<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_mod, t.d_base_change, t.d_mi_inv,
+        {
+            LaunchScope scope(KC_MODUP2, st);
+            k_modup2<<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_mod, t.d_base_change, t.d_mi_inv,
                                      t.d_prod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth);
+        }
         check_launch();
         launch_ntt(c, tmp, tmp, (long long) batch * d * Qpl, level_primes(L, K, depth), false, st);
     }
     if (d > 64)
         throw std::invalid_argument("too many key-switch digits");
     dim3 g(c.n >> 9, Qpl, batch);
-    k_keyswitch_mac<<<g, 256, 0, st>>>(tmp, key, acc, c.d_pc, c.logn, d, L, Qpl, c.Qp, depth);
+    {
+        LaunchScope scope(KC_KEYSWITCH_MAC, st);
+        k_keyswitch_mac<<<g, 256, 0, st>>>(tmp, key, acc, c.d_pc, c.logn, d, L, Qpl, c.Qp, depth);
+    }
     check_launch();
     return d;
 }
@@ -435,17 +453,23 @@ static void moddown_add(const Context& c, u64* acc, u64* tmp, const u64* ct_in, 
         launch_divround1_ntt(c, acc + (long long) L * N, 2 * Qpl * N, Qpl * N, tmp, L, c.half[0],
                              c.mod[c.Q_size].value, c.d_half_mod, batch, st);
         dim3 g(c.n >> 8, L, batch * 2);
-        k_moddown1_stage2<<<g, 256, 0, st>>>(tmp, acc, ct_in, ct_bs, out, out_bs, c.d_mod,
+        {
+            LaunchScope scope(KC_MODDOWN, st);
+            k_moddown1_stage2<<<g, 256, 0, st>>>(tmp, acc, ct_in, ct_bs, out, out_bs, c.d_mod,
                                               c.d_last_q_modinv, c.logn, L, Qpl, add_mask);
+        }
         check_launch();
     }
     else
     {
         launch_ntt(c, acc, acc, (long long) batch * 2 * Qpl, level_primes(L, K, depth), true, st);
         dim3 g(c.n >> 8, L, batch * 2);
-        k_moddown_ext<false><<<g, 256, 0, st>>>(acc, tmp, 2 * L * N, nullptr, c.d_mod, c.d_half,
+        {
+            LaunchScope scope(KC_MODDOWN, st);
+            k_moddown_ext<false><<<g, 256, 0, st>>>(acc, tmp, 2 * L * N, nullptr, c.d_mod, c.d_half,
                                                 c.d_half_mod, c.d_last_q_modinv, 0, c.logn, Qpl, L,
                                                 c.Qp, c.Q_size, K);
+        }
         check_launch();
         launch_ntt(c, tmp, tmp, (long long) batch * 2 * L, range_primes(0, L), false, st);
         // out = tmp + ct (components selected by add_mask)
@@ -455,8 +479,11 @@ static void moddown_add(const Context& c, u64* acc, u64* tmp, const u64* ct_in, 
             const u64* t = tmp + (long long) comp * L * N;
             u64* o = out + (long long) comp * L * N;
             if ((add_mask >> comp) & 1)
-                k_addsub<0><<<g2, 256, 0, st>>>(t, ct_in + (long long) comp * L * N, o, 2 * L * N,
+                {
+                    LaunchScope scope(KC_ELEMENTWISE, st);
+                    k_addsub<0><<<g2, 256, 0, st>>>(t, ct_in + (long long) comp * L * N, o, 2 * L * N,
                                                ct_bs, out_bs, c.d_mod, c.logn, L, 1);
+                }
             else
                 cudaMemcpy2DAsync(o, out_bs * 8, t, 2 * L * N * 8, L * N * 8, batch,
                                   cudaMemcpyDeviceToDevice, st);
@@ -504,8 +531,11 @@ void op_rescale(const Context& c, u64* ct, long long ct_bs, int depth, int batch
                          c.rescaled_half[depth], c.mod[L - 1].value,
                          c.d_rescaled_half_mod + location, batch, st);
     dim3 g(c.n >> 8, batch);
-    k_rescale_tail<<<g, 256, 0, st>>>(tmp.w(), ct, ct_bs, c.d_mod,
+    {
+        LaunchScope scope(KC_MODDOWN, st);
+        k_rescale_tail<<<g, 256, 0, st>>>(tmp.w(), ct, ct_bs, c.d_mod,
                                        c.d_rescaled_last_q_modinv + location, c.logn, L);
+    }
     check_launch();
 }
 
@@ -517,7 +547,10 @@ void op_mod_drop_inplace(const Context& c, u64* ct, long long ct_bs, int comps, 
     if (L < 2)
         throw std::logic_error("Ciphertext modulus can not be dropped!");
     dim3 g(c.n >> 8, batch);
-    k_mod_drop_inplace<<<g, 256, 0, st>>>(ct, ct_bs, c.logn, L, comps);
+    {
+        LaunchScope scope(KC_ELEMENTWISE, st);
+        k_mod_drop_inplace<<<g, 256, 0, st>>>(ct, ct_bs, c.logn, L, comps);
+    }
     check_launch();
 }
 
@@ -529,7 +562,10 @@ void op_mod_drop(const Context& c, const u64* in, long long in_bs, u64* out, lon
     if (L < 2)
         throw std::logic_error("Ciphertext modulus can not be dropped!");
     dim3 g(c.n >> 8, L - 1, batch * 2);
-    k_mod_drop<<<g, 256, 0, st>>>(in, in_bs, out, out_bs, c.logn, L);
+    {
+        LaunchScope scope(KC_ELEMENTWISE, st);
+        k_mod_drop<<<g, 256, 0, st>>>(in, in_bs, out, out_bs, c.logn, L);
+    }
     check_launch();
 }
 
@@ -550,9 +586,12 @@ void op_apply_galois(const Context& c, const u64* in, long long in_bs, u64* out,
                    batch, st);
     launch_ntt(c, acc.w(), acc.w(), (long long) batch * 2 * Qpl, level_primes(L, K, depth), true, st);
     dim3 g(c.n >> 8, L, batch * 2);
-    k_moddown_ext<true><<<g, 256, 0, st>>>(acc.w(), out, out_bs, coef.w(), c.d_mod, c.d_half,
+    {
+        LaunchScope scope(KC_MODDOWN, st);
+        k_moddown_ext<true><<<g, 256, 0, st>>>(acc.w(), out, out_bs, coef.w(), c.d_mod, c.d_half,
                                            c.d_half_mod, c.d_last_q_modinv, galois_elt, c.logn, Qpl,
                                            L, c.Qp, c.Q_size, K);
+    }
     check_launch();
     launch_ntt_strided(c, out, out_bs, 2 * L, 0, batch, range_primes(0, L), false, st);
 }

@@ -17,6 +17,7 @@
 // final store, so results equal the reference's Barrett arithmetic bit for bit.
 #include "modarith.cuh"
 #include "ntt_core.cuh"
+#include "ops.hpp"
 
 namespace heon {
 
@@ -347,6 +348,7 @@ static void launch_col(const Context& c, const Map& m, long long n_polys, bool f
 {
     const int S = c.logn - 8;
     const unsigned grid = (unsigned) (n_polys * ((1 << S) / 16));
+    LaunchScope scope(INV ? KC_NTT_INV_COL : KC_NTT_FWD_COL, st);
 #define HEON_COL(SS)                                                                               \
     case SS:                                                                                       \
         ntt_col_pass<SS, INV, Map><<<grid, 256, 0, st>>>(m, INV ? c.d_inv : c.d_fwd, c.d_pc,       \
@@ -370,6 +372,7 @@ static void launch_row(const Context& c, const Map& m, long long n_polys, bool f
 {
     const int S = c.logn - 8;
     const unsigned grid = (unsigned) (n_polys * ((1 << S) / 16));
+    LaunchScope scope(INV ? KC_NTT_INV_ROW : KC_NTT_FWD_ROW, st);
     ntt_row_pass<INV, Map><<<grid, 256, 0, st>>>(m, INV ? c.d_inv : c.d_fwd, c.d_pc, c.logn, first);
 }
 

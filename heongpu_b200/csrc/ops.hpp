@@ -7,6 +7,32 @@ namespace heon {
 
 extern std::atomic<long long> g_launches;
 
+// Kernel classes for the launch counter / per-kernel CUDA-event profiler.
+enum KernelClass {
+    KC_NTT_FWD_COL = 0,
+    KC_NTT_FWD_ROW,
+    KC_NTT_INV_ROW,
+    KC_NTT_INV_COL,
+    KC_KEYSWITCH_MAC,
+    KC_MODUP2,
+    KC_MODDOWN,
+    KC_CROSS_MULTIPLY,
+    KC_ELEMENTWISE,
+    KC_COUNT
+};
+
+// RAII scope around one kernel launch: counts it and, when profiling is on,
+// brackets it with CUDA events on the launching stream.
+struct LaunchScope {
+    int cls;
+    cudaStream_t st;
+    cudaEvent_t e0 = nullptr;
+    LaunchScope(int cls, cudaStream_t st);
+    ~LaunchScope();
+};
+void profile_begin();
+void profile_end(double* ms, long long* launches);
+
 void op_add(const Context& c, const u64* a, long long a_bs, const u64* b, long long b_bs, u64* out,
             long long o_bs, int comps, int depth, int batch, int op, cudaStream_t st);
 void op_multiply(const Context& c, const u64* a, long long a_bs, const u64* b, long long b_bs,

@@ -154,6 +154,14 @@ int heon_ckks_apply_galois(heon_context_t ctx, const uint64_t* in, long long in_
                            uint64_t* out, long long out_stride, const uint64_t* galois_key,
                            uint32_t galois_elt, int depth, int batch, void* stream);
 
+/* Per-kernel-class CUDA-event profiler (used by bench.py for the roofline
+ * line): begin() arms it, end() synchronises the device and returns, per
+ * class, the summed device time in ms and the launch count; the return value
+ * is the number of classes.  heon_profile_class_name(i) names class i. */
+int heon_profile_begin(void);
+int heon_profile_end(double* h_ms, long long* h_launches, int capacity);
+const char* heon_profile_class_name(int cls);
+
 /* Number of launches of this library's own kernels since the counter was
  * last reset (bench.py reports it as gpu_launches). */
 long long heon_kernel_launches(int reset);
