@@ -4,7 +4,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libheon_b200.so")
+LIB_PATH = os.environ.get("HEON_B200_LIB") or os.path.join(_HERE, "lib", "libheon_b200.so")
 
 u64p = C.POINTER(C.c_uint64)
 i32p = C.POINTER(C.c_int)

@@ -1,4 +1,6 @@
 // extern "C" boundary: argument validation, exception -> status translation.
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -124,6 +126,10 @@ static void finish_context(Context& c, int device, int log_n, int n_q, int n_p)
     c.method = (n_p == 1) ? 1 : 2;
     if (c.method == 2 && n_p > 15)
         throw std::logic_error("P size above 15 is not supported");
+    if (const char* v = getenv("HEON_NTT_VARIANT"))
+        c.ntt_variant = atoi(v);
+    if (const char* v = getenv("HEON_NTT_TMA"))
+        c.use_tma = atoi(v);
     build_host_tables(c);
     if (device >= 0)
         upload_tables(c);
@@ -298,7 +304,14 @@ int heon_ntt_poly_ordered(heon_context_t ctx, uint64_t* base, const long long* h
         if (cudaMallocAsync(&d_off, sizeof(long long) * n_polys, st) != cudaSuccess)
             throw std::runtime_error("cudaMallocAsync failed");
         cudaMemcpyAsync(d_off, h_offsets, sizeof(long long) * n_polys, cudaMemcpyHostToDevice, st);
-        launch_ntt_scattered(c, base, d_off, n_polys, prime_index, inverse != 0, st);
+        long long ext = 0;
+        bool aligned = true;
+        for (int i = 0; i < n_polys; ++i)
+        {
+            ext = std::max(ext, h_offsets[i] + c.n);
+            aligned &= (h_offsets[i] & 15) == 0 && h_offsets[i] >= 0;
+        }
+        launch_ntt_scattered(c, base, d_off, n_polys, prime_index, inverse != 0, ext, aligned, st);
         cudaFreeAsync(d_off, st);
     });
 }

@@ -124,11 +124,68 @@ __global__ void __launch_bounds__(256)
 // reference: src/lib/kernel/switchkey.cu:985-1046
 // (base_conversion_DtoQtilde_relin_leveled_kernel).  The float sequence
 // (u64->f32 rn, IEEE divide, sequential adds, round half away) is reproduced
-// operation for operation.
+// operation for operation; the integer part is restructured:
+//   * partial_j = x_j * Mi_inv_j uses a Shoup product (canonical result),
+//   * sum_j partial_j * M_{j,k} is accumulated lazily in 128 bits and reduced
+//     once per output word,
+//   * r * prod_k comes from a small table of multiples,
+//   * output limbs that belong to the digit itself equal the input residue
+//     (M_{j,k} = 0 for j != k, partial_k * M_{k,k} = x_k, prod_k = 0) and are
+//     copied.
+// All of these are exact, so every output word equals the reference's.
+template <int IJ>
+__device__ __forceinline__ void modup2_body(const u64* __restrict__ pc_in, u64* __restrict__ po,
+                                            const PrimeConst* __restrict__ pcs,
+                                            const u64* __restrict__ base_change,
+                                            const TwPair* __restrict__ mi_inv,
+                                            const u64* __restrict__ rprod, int I_loc, int dg, int d,
+                                            int logn, int Qpl, int L, int depth)
+{
+    u64 x[IJ], partial[IJ];
+    float r = 0;
+#pragma unroll
+    for (int i = 0; i < IJ; ++i)
+    {
+        const PrimeConst pi = pcs[I_loc + i];
+        x[i] = pc_in[(long long) i << logn];
+        const TwPair mi = mi_inv[I_loc + i];
+        partial[i] = csub(shoup_mul_lazy(x[i], mi.w, mi.ws, pi.p), pi.p);
+        const float div = __ull2float_rn(partial[i]);
+        const float mod = __ull2float_rn(pi.p);
+        r = __fadd_rn(r, __fdiv_rn(div, mod));
+    }
+    r = roundf(r);
+    const unsigned r_ = (unsigned) r;
+    const int matrix_index = I_loc * Qpl;
+    const u64* rp = rprod + ((long long) r_ * d + dg) * Qpl;
+    for (int k = 0; k < Qpl; ++k)
+    {
+        u64 res;
+        if (k >= I_loc && k < I_loc + IJ)
+        {
+            res = 0;
+#pragma unroll
+            for (int i = 0; i < IJ; ++i)
+                if (k == I_loc + i)
+                    res = x[i];
+        }
+        else
+        {
+            const PrimeConst pk = pcs[level_prime(k, L, depth)];
+            u64 lo = 0, hi = 0;
+#pragma unroll
+            for (int j = 0; j < IJ; ++j)
+                mac128(lo, hi, partial[j], base_change[j + k * IJ + matrix_index]);
+            res = mod_sub(reduce_u128(lo, hi, pk), rp[k], pk.p);
+        }
+        po[(long long) k << logn] = res;
+    }
+}
+
 __global__ void __launch_bounds__(256)
     k_modup2(const u64* __restrict__ coef, long long coef_bs, u64* __restrict__ out,
-             const Mod64* __restrict__ mods, const u64* __restrict__ base_change,
-             const u64* __restrict__ mi_inv, const u64* __restrict__ prod,
+             const PrimeConst* __restrict__ pcs, const u64* __restrict__ base_change,
+             const TwPair* __restrict__ mi_inv, const u64* __restrict__ rprod,
              const int* __restrict__ I_j_, const int* __restrict__ I_loc_, int logn, int d, int Qpl,
              int L, int depth)
 {
@@ -137,36 +194,31 @@ __global__ void __launch_bounds__(256)
     const long long bz = blockIdx.z;
     const int I_j = I_j_[dg];
     const int I_loc = I_loc_[dg];
-    const u64* pc = coef + bz * coef_bs + idx + ((long long) I_loc << logn);
+    const u64* pin = coef + bz * coef_bs + idx + ((long long) I_loc << logn);
     u64* po = out + (((bz * d + dg) * Qpl) << logn) + idx;
-    const int matrix_index = I_loc * Qpl;
-
-    u64 partial[20];
-    float r = 0;
-    for (int i = 0; i < I_j; ++i)
+#define HEON_MU2(n)                                                                                \
+    case n:                                                                                        \
+        modup2_body<n>(pin, po, pcs, base_change, mi_inv, rprod, I_loc, dg, d, logn, Qpl, L, depth); \
+        break;
+    switch (I_j)
     {
-        u64 t = pc[(long long) i << logn];
-        partial[i] = barrett_mul(t, mi_inv[I_loc + i], mods[I_loc + i]);
-        float div = __ull2float_rn(partial[i]);
-        float mod = __ull2float_rn(mods[I_loc + i].value);
-        r = __fadd_rn(r, __fdiv_rn(div, mod));
+        HEON_MU2(1)
+        HEON_MU2(2)
+        HEON_MU2(3)
+        HEON_MU2(4)
+        HEON_MU2(5)
+        HEON_MU2(6)
+        HEON_MU2(7)
+        HEON_MU2(8)
+        HEON_MU2(9)
+        HEON_MU2(10)
+        HEON_MU2(11)
+        HEON_MU2(12)
+        HEON_MU2(13)
+        HEON_MU2(14)
+        HEON_MU2(15)
     }
-    r = roundf(r);
-    const u64 r_ = (u64) r;
-
-    for (int i = 0; i < Qpl; ++i)
-    {
-        const Mod64 m = mods[level_prime(i, L, depth)];
-        u64 t = 0;
-        for (int j = 0; j < I_j; ++j)
-        {
-            u64 mult = reduce_forced(partial[j], m);
-            mult = barrett_mul(mult, base_change[j + i * I_j + matrix_index], m);
-            t = mod_add(t, mult, m.value);
-        }
-        u64 r_mul = barrett_mul(r_, prod[i + dg * Qpl], m);
-        po[(long long) i << logn] = mod_sub(t, r_mul, m.value);
-    }
+#undef HEON_MU2
 }
 
 // ---------------------------------------------------------------------------
@@ -204,62 +256,108 @@ __global__ void __launch_bounds__(256)
 // reference: src/lib/kernel/switchkey.cu:1222-1282
 // (divide_round_lastq_extended_leveled_kernel) and 1621-1718
 // (divide_round_lastq_permute_ckks_kernel).
+// Restructured: one thread owns a coefficient of one component, runs the
+// P-limb chain once (the reference redoes it for every Q limb) and then walks
+// all Q limbs; x mod q uses an exact 64-bit reduction and the constant
+// multipliers use Shoup words.  Same exact values, so identical words.
+template <int K, bool PERMUTE>
+__device__ __forceinline__ void moddown_body(const u64* __restrict__ pin, u64* __restrict__ pout,
+                                             const u64* __restrict__ c0, const PrimeConst* __restrict__ pcs,
+                                             const u64* __restrict__ half, const u64* __restrict__ half_mod,
+                                             const TwPair* __restrict__ lqm, unsigned galois_elt, int idx,
+                                             int comp, int logn, int L, int Qp0, int Q0)
+{
+    u64 last_ct[K], lh[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+        last_ct[i] = pin[(long long) (L + i) << logn];
+    int loc = 0;
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+    {
+        lh[i] = mod_add(last_ct[K - 1 - i], half[i], pcs[Qp0 - 1 - i].p);
+#pragma unroll
+        for (int j = 0; j < K - 1 - i; ++j)
+        {
+            const PrimeConst pj = pcs[Q0 + j];
+            u64 t = reduce_u64(lh[i], pj);
+            t = mod_sub(t, half_mod[loc + Q0 + j], pj.p);
+            t = mod_sub(last_ct[j], t, pj.p);
+            const TwPair w = lqm[loc + Q0 + j];
+            last_ct[j] = csub(shoup_mul_lazy(t, w.w, w.ws, pj.p), pj.p);
+        }
+        loc += Qp0 - 1 - i;
+    }
+    for (int y = 0; y < L; ++y)
+    {
+        const PrimeConst py = pcs[y];
+        u64 x = pin[(long long) y << logn];
+        int l2 = 0;
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+        {
+            u64 t = reduce_u64(lh[i], py);
+            t = mod_sub(t, half_mod[l2 + y], py.p);
+            t = mod_sub(x, t, py.p);
+            const TwPair w = lqm[l2 + y];
+            x = csub(shoup_mul_lazy(t, w.w, w.ws, py.p), py.p);
+            l2 += Qp0 - 1 - i;
+        }
+        if (!PERMUTE)
+        {
+            pout[((long long) y << logn) + idx] = x;
+        }
+        else
+        {
+            if (comp == 0)
+                x = mod_add(c0[(long long) y << logn], x, py.p);
+            const unsigned raw = (unsigned) idx * galois_elt; // low n+1 bits are all that matter
+            const unsigned dst = raw & ((1u << logn) - 1);
+            if ((raw >> logn) & 1)
+                x = py.p - x;
+            pout[((long long) y << logn) + dst] = x;
+        }
+    }
+}
+
 template <bool PERMUTE>
 __global__ void __launch_bounds__(256)
     k_moddown_ext(const u64* __restrict__ in, u64* __restrict__ out, long long out_bs,
-                  const u64* __restrict__ c0coef, const Mod64* __restrict__ mods,
+                  const u64* __restrict__ c0coef, const PrimeConst* __restrict__ pcs,
                   const u64* __restrict__ half, const u64* __restrict__ half_mod,
-                  const u64* __restrict__ last_q_modinv, unsigned galois_elt, int logn, int Qpl, int L,
-                  int Qp0, int Q0, int K)
+                  const TwPair* __restrict__ lqm, unsigned galois_elt, int logn, int Qpl, int L, int Qp0,
+                  int Q0, int K)
 {
     const int idx = blockIdx.x * 256 + threadIdx.x;
-    const int y = blockIdx.y;
-    const long long bz = blockIdx.z >> 1;
-    const int c = blockIdx.z & 1;
+    const long long bz = blockIdx.y >> 1;
+    const int c = blockIdx.y & 1;
     const u64* pin = in + (((bz * 2 + c) * Qpl) << logn) + idx;
-
-    u64 last_ct[15];
-    for (int i = 0; i < K; ++i)
-        last_ct[i] = pin[(long long) (L + i) << logn];
-    u64 x = pin[(long long) y << logn];
-    const Mod64 my = mods[y];
-
-    int loc = 0;
-    for (int i = 0; i < K; ++i)
+    u64* pout = out + bz * out_bs + ((long long) (c * L) << logn);
+    const u64* c0 = PERMUTE ? c0coef + ((bz * 2 * L) << logn) + idx : nullptr;
+#define HEON_MD(n)                                                                                 \
+    case n:                                                                                        \
+        moddown_body<n, PERMUTE>(pin, pout, c0, pcs, half, half_mod, lqm, galois_elt, idx, c, logn, L, \
+                                 Qp0, Q0);                                                          \
+        break;
+    switch (K)
     {
-        u64 lh = mod_add(last_ct[K - 1 - i], half[i], mods[Qp0 - 1 - i].value);
-        for (int j = 0; j < K - 1 - i; ++j)
-        {
-            const Mod64 mj = mods[Q0 + j];
-            u64 t = reduce_forced(lh, mj);
-            t = mod_sub(t, half_mod[loc + Q0 + j], mj.value);
-            t = mod_sub(last_ct[j], t, mj.value);
-            last_ct[j] = barrett_mul(t, last_q_modinv[loc + Q0 + j], mj);
-        }
-        u64 t = reduce_forced(lh, my);
-        t = mod_sub(t, half_mod[loc + y], my.value);
-        t = mod_sub(x, t, my.value);
-        x = barrett_mul(t, last_q_modinv[loc + y], my);
-        loc += Qp0 - 1 - i;
+        HEON_MD(1)
+        HEON_MD(2)
+        HEON_MD(3)
+        HEON_MD(4)
+        HEON_MD(5)
+        HEON_MD(6)
+        HEON_MD(7)
+        HEON_MD(8)
+        HEON_MD(9)
+        HEON_MD(10)
+        HEON_MD(11)
+        HEON_MD(12)
+        HEON_MD(13)
+        HEON_MD(14)
+        HEON_MD(15)
     }
-
-    if (!PERMUTE)
-    {
-        out[bz * out_bs + ((long long) (c * L + y) << logn) + idx] = x;
-    }
-    else
-    {
-        if (c == 0)
-        {
-            u64 cin = c0coef[((bz * 2 * L + y) << logn) + idx];
-            x = mod_add(cin, x, my.value);
-        }
-        const unsigned raw = (unsigned) idx * galois_elt; // low n+1 bits are all that matter
-        const unsigned dst = raw & ((1u << logn) - 1);
-        if ((raw >> logn) & 1)
-            x = my.value - x;
-        out[bz * out_bs + ((long long) (c * L + y) << logn) + dst] = x;
-    }
+#undef HEON_MD
 }
 
 // ---------------------------------------------------------------------------
@@ -411,8 +509,8 @@ static int keyswitch_core(const Context& c, const u64* coef, long long coef_bs, 
         dim3 g(c.n >> 8, d, batch);
         {
             LaunchScope scope(KC_MODUP2, st);
-            k_modup2<<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_mod, t.d_base_change, t.d_mi_inv,
-                                     t.d_prod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth);
+            k_modup2<<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_pc, t.d_base_change, t.d_mi_inv_pair,
+                                     t.d_rprod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth);
         }
         check_launch();
         launch_ntt(c, tmp, tmp, (long long) batch * d * Qpl, level_primes(L, K, depth), false, st);
@@ -463,11 +561,11 @@ static void moddown_add(const Context& c, u64* acc, u64* tmp, const u64* ct_in, 
     else
     {
         launch_ntt(c, acc, acc, (long long) batch * 2 * Qpl, level_primes(L, K, depth), true, st);
-        dim3 g(c.n >> 8, L, batch * 2);
+        dim3 g(c.n >> 8, batch * 2);
         {
             LaunchScope scope(KC_MODDOWN, st);
-            k_moddown_ext<false><<<g, 256, 0, st>>>(acc, tmp, 2 * L * N, nullptr, c.d_mod, c.d_half,
-                                                c.d_half_mod, c.d_last_q_modinv, 0, c.logn, Qpl, L,
+            k_moddown_ext<false><<<g, 256, 0, st>>>(acc, tmp, 2 * L * N, nullptr, c.d_pc, c.d_half,
+                                                c.d_half_mod, c.d_lqm_pair, 0, c.logn, Qpl, L,
                                                 c.Qp, c.Q_size, K);
         }
         check_launch();
@@ -585,11 +683,11 @@ void op_apply_galois(const Context& c, const u64* in, long long in_bs, u64* out,
     keyswitch_core(c, coef.w() + (long long) L * N, 2 * L * N, galois_key, tmp.w(), acc.w(), depth,
                    batch, st);
     launch_ntt(c, acc.w(), acc.w(), (long long) batch * 2 * Qpl, level_primes(L, K, depth), true, st);
-    dim3 g(c.n >> 8, L, batch * 2);
+    dim3 g(c.n >> 8, batch * 2);
     {
         LaunchScope scope(KC_MODDOWN, st);
-        k_moddown_ext<true><<<g, 256, 0, st>>>(acc.w(), out, out_bs, coef.w(), c.d_mod, c.d_half,
-                                           c.d_half_mod, c.d_last_q_modinv, galois_elt, c.logn, Qpl,
+        k_moddown_ext<true><<<g, 256, 0, st>>>(acc.w(), out, out_bs, coef.w(), c.d_pc, c.d_half,
+                                           c.d_half_mod, c.d_lqm_pair, galois_elt, c.logn, Qpl,
                                            L, c.Qp, c.Q_size, K);
     }
     check_launch();

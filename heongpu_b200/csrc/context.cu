@@ -172,6 +172,10 @@ void upload_tables(Context& c)
         pcs[i].inv64 = shoup(1, p);
         pcs[i].r64 = (u64) ((((u128) 1) << 64) % p);
         pcs[i].r64s = shoup(pcs[i].r64, p);
+        pcs[i].bits = (unsigned) c.mod[i].bit;
+        pcs[i].fin_shift = pcs[i].bits - 25;
+        pcs[i].fin_m = (unsigned) ((((u128) 1) << (pcs[i].bits + 31)) / p);
+        pcs[i].nc_ok = pcs[i].bits <= 57 ? 1u : 0u;
         for (int j = 0; j < N; ++j)
         {
             const size_t o = (size_t) i * N + j;
@@ -185,11 +189,37 @@ void upload_tables(Context& c)
         last[2 * i] = TwPair{ninv, shoup(ninv, p)};
         last[2 * i + 1] = TwPair{wn, shoup(wn, p)};
     }
+    {
+        const int S1 = c.logn - 8, R = 1 << S1;
+        std::vector<TwPair> fb((size_t) Qp * R * 256), ib((size_t) Qp * R * 256);
+        for (int i = 0; i < Qp; ++i)
+            for (int r = 0; r < R; ++r)
+                for (int u = 4; u < 8; ++u)
+                    for (int g = 0; g < (1 << (u - 4)); ++g)
+                        for (int tt = 0; tt < 16; ++tt)
+                        {
+                            const size_t src = (size_t) i * N + (1u << (S1 + u)) + ((size_t) r << u) + (tt << (u - 4)) + g;
+                            const size_t dst = (((size_t) i * R + r) * 16 + ((1 << (u - 4)) - 1 + g)) * 16 + tt;
+                            fb[dst] = fwd[src];
+                            ib[dst] = inv[src];
+                        }
+        c.d_fwd_rowb = upload(fb);
+        c.d_inv_rowb = upload(ib);
+    }
     c.d_pc = upload(pcs);
     c.d_fwd = upload(fwd);
     c.d_inv = upload(inv);
     c.d_inv_last = upload(last);
     c.d_last_q_modinv = upload(c.last_q_modinv);
+    {
+        // block i of last_q_modinv holds entries for primes j = 0..Qp-2-i
+        std::vector<TwPair> pairs;
+        size_t o = 0;
+        for (int i = 0; i < c.P_size; ++i)
+            for (int j = 0; j < Qp - 1 - i; ++j, ++o)
+                pairs.push_back(TwPair{c.last_q_modinv[o], shoup(c.last_q_modinv[o], c.mod[j].value)});
+        c.d_lqm_pair = upload(pairs);
+    }
     c.d_half = upload(c.half);
     c.d_half_mod = upload(c.half_mod);
     c.d_rescaled_last_q_modinv = upload(c.rescaled_last_q_modinv);
@@ -200,6 +230,23 @@ void upload_tables(Context& c)
         t.d_base_change = upload(t.base_change);
         t.d_mi_inv = upload(t.mi_inv);
         t.d_prod = upload(t.prod);
+        {
+            const int depth = (int) (&t - &c.lvl2[0]);
+            const int L = c.Q_size - depth, K = c.P_size, Ql = L + K;
+            std::vector<TwPair> mp;
+            for (size_t i = 0; i < t.mi_inv.size(); ++i) // digit primes are q_i (same index at every depth)
+                mp.push_back(TwPair{t.mi_inv[i], shoup(t.mi_inv[i], c.mod[i].value)});
+            t.d_mi_inv_pair = upload(mp);
+            std::vector<u64> rp((size_t) (K + 1) * t.d * Ql);
+            for (int r = 0; r <= K; ++r)
+                for (int dg = 0; dg < t.d; ++dg)
+                    for (int k = 0; k < Ql; ++k)
+                    {
+                        const u64 tk = c.mod[level_prime(k, L, depth)].value;
+                        rp[((size_t) r * t.d + dg) * Ql + k] = mulmod((u64) r, t.prod[(size_t) dg * Ql + k], tk);
+                    }
+            t.d_rprod = upload(rp);
+        }
         t.d_I_j = upload(t.I_j);
         t.d_I_loc = upload(t.I_loc);
     }
@@ -213,7 +260,10 @@ Context::~Context()
     cudaFree(d_fwd);
     cudaFree(d_inv);
     cudaFree(d_inv_last);
+    cudaFree(d_fwd_rowb);
+    cudaFree(d_inv_rowb);
     cudaFree(d_last_q_modinv);
+    cudaFree(d_lqm_pair);
     cudaFree(d_half);
     cudaFree(d_half_mod);
     cudaFree(d_rescaled_last_q_modinv);
@@ -224,6 +274,8 @@ Context::~Context()
         cudaFree(t.d_base_change);
         cudaFree(t.d_mi_inv);
         cudaFree(t.d_prod);
+        cudaFree(t.d_mi_inv_pair);
+        cudaFree(t.d_rprod);
         cudaFree(t.d_I_j);
         cudaFree(t.d_I_loc);
     }

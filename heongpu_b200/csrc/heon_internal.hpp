@@ -24,6 +24,12 @@ struct PrimeConst {
     u64 inv64; // floor(2^64 / p): Shoup word of the multiplier 1
     u64 r64; // 2^64 mod p
     u64 r64s; // Shoup word of r64
+    // small-quotient reduction of a lazy word x < 128p:
+    //   q = ((x >> fin_shift) * fin_m) >> 56,  x - q*p in [0,2p)
+    unsigned fin_m; // floor(2^(bits+31) / p), fits 32 bits
+    unsigned fin_shift; // bits - 25
+    unsigned bits; // bit length of p
+    unsigned nc_ok; // 1 if p <= 57 bits: butterflies may skip every per-stage correction
 };
 
 // Method-II (hybrid, K > 1) level tables; one entry per depth.
@@ -39,6 +45,8 @@ struct LevelTablesII {
     u64* d_base_change = nullptr;
     u64* d_mi_inv = nullptr;
     u64* d_prod = nullptr;
+    TwPair* d_mi_inv_pair = nullptr; // mi_inv with Shoup words
+    u64* d_rprod = nullptr; // [r = 0..K][digit][k]: r * prod mod t_k
     int* d_I_j = nullptr;
     int* d_I_loc = nullptr;
 };
@@ -49,6 +57,7 @@ struct Context {
     int n = 0, logn = 0;
     int Q_size = 0, P_size = 0, Qp = 0;
     int method = 1; // key-switching method: 1 (K == 1) or 2 (K > 1)
+    int ntt_variant = 2; // butterfly variant (ntt_core.cuh); HEON_NTT_VARIANT overrides
     std::vector<Mod64> mod; // [q_0..q_{Q-1}, p_0..p_{K-1}]
     std::vector<u64> psi; // minimal primitive 2N-th roots
 
@@ -67,7 +76,13 @@ struct Context {
     TwPair* d_fwd = nullptr; // [Qp][N]  psi^bitrev(i) with Shoup word
     TwPair* d_inv = nullptr; // [Qp][N]  psi^-bitrev(i) with Shoup word
     TwPair* d_inv_last = nullptr; // [Qp][2] {n^-1, W_inv[1]*n^-1}
+    // lane-major copies of the last-four-stage twiddles of the row pass:
+    // [Qp][rows][16 entries][16 lanes] (ntt_core.cuh: ct_round_b_lm)
+    TwPair* d_fwd_rowb = nullptr;
+    TwPair* d_inv_rowb = nullptr;
+    int use_tma = 1; // row pass through TMA tensor maps (HEON_NTT_TMA=0 disables)
     u64* d_last_q_modinv = nullptr;
+    TwPair* d_lqm_pair = nullptr; // last_q_modinv with Shoup words
     u64* d_half = nullptr;
     u64* d_half_mod = nullptr;
     u64* d_rescaled_last_q_modinv = nullptr;
@@ -113,7 +128,7 @@ void upload_tables(Context& c);
 void launch_ntt(const Context& c, const u64* src, u64* dst, long long n_polys, const PrimeList& pl,
                 bool inverse, cudaStream_t st);
 void launch_ntt_scattered(const Context& c, u64* base, const long long* d_offsets, int n_polys,
-                          int prime, bool inverse, cudaStream_t st);
+                          int prime, bool inverse, long long extent_words, bool aligned, cudaStream_t st);
 void launch_ntt_strided(const Context& c, u64* base, long long bstride, int per_batch, int first,
                         long long batch, const PrimeList& pl, bool inverse, cudaStream_t st);
 void launch_ntt_strided_copy(const Context& c, const u64* src, long long src_bstride, u64* dst,

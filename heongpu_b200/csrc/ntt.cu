@@ -18,6 +18,11 @@
 #include "modarith.cuh"
 #include "ntt_core.cuh"
 #include "ops.hpp"
+#include "tma.cuh"
+
+#ifndef HEON_NTT_MINBLOCKS
+#define HEON_NTT_MINBLOCKS 3
+#endif
 
 namespace heon {
 
@@ -32,14 +37,15 @@ struct MapContig {
     u64* dst;
     PrimeList pl;
     int logn;
-    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& out, int& prime) const
+    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& out, int& prime, int& aux) const
     {
         in = src + (z << logn);
         out = dst + (z << logn);
         prime = pl.idx[z % pl.count];
+        aux = 0;
     }
     static constexpr bool kXform = false;
-    __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&) const { return x; }
+    __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&, int) const { return x; }
 };
 
 // polys at explicit word offsets, one prime, in place
@@ -47,13 +53,14 @@ struct MapScatter {
     u64* base;
     const long long* offs; // device array
     int prime;
-    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& out, int& pr) const
+    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& out, int& pr, int& aux) const
     {
         in = out = base + offs[z];
         pr = prime;
+        aux = 0;
     }
     static constexpr bool kXform = false;
-    __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&) const { return x; }
+    __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&, int) const { return x; }
 };
 
 // Strided polys: poly z = (b, j) with j < per_batch lives at
@@ -64,15 +71,16 @@ struct MapStrided {
     int per_batch, first;
     PrimeList pl;
     int logn;
-    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& out, int& prime) const
+    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& out, int& prime, int& aux) const
     {
         long long b = z / per_batch;
         int j = (int) (z % per_batch);
         in = out = base + b * bstride + ((long long) (first + j) << logn);
         prime = pl.idx[j % pl.count];
+        aux = 0;
     }
     static constexpr bool kXform = false;
-    __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&) const { return x; }
+    __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&, int) const { return x; }
 };
 
 // Out-of-place strided source -> contiguous destination (used by apply_galois
@@ -84,16 +92,17 @@ struct MapStridedCopy {
     int per_batch;
     PrimeList pl;
     int logn;
-    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& out, int& prime) const
+    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& out, int& prime, int& aux) const
     {
         long long b = z / per_batch;
         int j = (int) (z % per_batch);
         in = src + b * src_bstride + ((long long) j << logn);
         out = dst + (z << logn);
         prime = pl.idx[j % pl.count];
+        aux = 0;
     }
     static constexpr bool kXform = false;
-    __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&) const { return x; }
+    __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&, int) const { return x; }
 };
 
 // Method-I mod-up fused into the first pass: output poly z = (b, i, y) reads
@@ -105,7 +114,7 @@ struct MapModUpI {
     u64* out; // [b][L][Qpl][N]
     long long coef_bstride;
     int L, Qpl, depth, logn;
-    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& o, int& prime) const
+    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& o, int& prime, int& aux) const
     {
         int y = (int) (z % Qpl);
         long long t = z / Qpl;
@@ -114,12 +123,15 @@ struct MapModUpI {
         in = coef + b * coef_bstride + ((long long) i << logn);
         o = out + (z << logn);
         prime = level_prime(y, L, depth);
+        // The digit word x < 2^bits(q_i) is already a valid lazy NTT input (< 4p)
+        // when the digit prime is at most one bit longer than the target prime.
+        aux = pcs[i].bits > pcs[prime].bits + 1;
     }
     static constexpr bool kXform = true;
-    // x mod p, lazily in [0,2p): good enough as NTT input
-    __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst& pc) const
+    const PrimeConst* pcs;
+    __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst& pc, int need_reduce) const
     {
-        return shoup_mul_lazy(x, 1, pc.inv64, pc.p);
+        return need_reduce ? shoup_mul_lazy3(x, 1, pc.inv64, pc.p) : x; // [0,4p) either way
     }
 };
 
@@ -135,7 +147,7 @@ struct MapDivRoundOne {
     int Lout, logn;
     u64 half, plast; // floor(p_last/2), p_last
     const u64* half_mod; // [Lout]
-    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& o, int& prime) const
+    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& o, int& prime, int& aux) const
     {
         int i = (int) (z % Lout);
         long long t = z / Lout;
@@ -144,9 +156,10 @@ struct MapDivRoundOne {
         in = src + b * bstride + c * cstride;
         o = out + (z << logn);
         prime = i;
+        aux = 0;
     }
     static constexpr bool kXform = true;
-    __device__ __forceinline__ u64 xform(u64 x, int prime, const PrimeConst& pc) const
+    __device__ __forceinline__ u64 xform(u64 x, int prime, const PrimeConst& pc, int) const
     {
         x = mod_add(x, half, plast);
         x = reduce_u64(x, pc);
@@ -158,31 +171,17 @@ struct MapDivRoundOne {
 // kernels
 // ---------------------------------------------------------------------------
 
-// Column pass: S stages on columns (stride 256 words).  T = 2^S/16 threads
+// Column pass body: S stages on columns (stride 256 words).  T = 2^S/16 threads
 // cooperate on one column, C = 256/T adjacent columns per CTA.
-template <int S, bool INV, class Map>
-__global__ void __launch_bounds__(256) ntt_col_pass(Map map, const TwPair* __restrict__ tw_all,
-                                                    const PrimeConst* __restrict__ pcs,
-                                                    const TwPair* __restrict__ inv_last, int logn,
-                                                    bool first_pass)
+template <int S, bool INV, int VAR, class Map>
+__device__ __forceinline__ void col_pass_body(const Map& map, const u64* in, u64* out, int prime,
+                                              const PrimeConst& pc, const TwPair* __restrict__ tw,
+                                              const TwPair* __restrict__ inv_last, int tile,
+                                              bool first_pass, int aux, u64* sm)
 {
     constexpr int T = (1 << S) / 16;
     constexpr int C = 256 / T;
-    __shared__ u64 sm[(S > 4) ? (1 << S) * C : 1];
-
-    const int tiles = T; // 256 / C
-    long long z = blockIdx.x / tiles;
-    int tile = blockIdx.x % tiles;
-    const u64* in;
-    u64* out;
-    int prime;
-    map.get(z, in, out, prime);
-    if (!first_pass)
-        in = out;
-    const PrimeConst pc = pcs[prime];
-    const u64 p = pc.p, p2 = 2 * pc.p;
-    const TwPair* tw = tw_all + ((long long) prime << logn);
-
+    const BflyConst bc{pc.p, 2 * pc.p, 4 * pc.p, 0 - pc.p};
     const int c = threadIdx.x % C;
     const int tt = threadIdx.x / C;
     const int col = tile * C + c;
@@ -196,10 +195,10 @@ __global__ void __launch_bounds__(256) ntt_col_pass(Map map, const TwPair* __res
         {
             u64 x = in[(long long) (tt + T * k) * 256 + col];
             if (Map::kXform && first_pass)
-                x = map.xform(x, prime, pc);
+                x = map.xform(x, prime, pc, aux);
             v[k] = x;
         }
-        ct_round_a(v, tw, 0, 0, p, p2);
+        ct_round_a<VAR>(v, tw, 0, 0, bc);
         if constexpr (S > 4)
         {
 #pragma unroll
@@ -209,10 +208,10 @@ __global__ void __launch_bounds__(256) ntt_col_pass(Map map, const TwPair* __res
 #pragma unroll
             for (int k = 0; k < 16; ++k)
                 v[k] = sm[(16 * tt + k) * C + c];
-            ct_round_b<S>(v, tw, 0, 0, tt, p, p2);
+            ct_round_b<S, VAR>(v, tw, 0, 0, tt, bc);
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-                out[(long long) (16 * tt + k) * 256 + col] = v[k]; // lazy [0,4p)
+                out[(long long) (16 * tt + k) * 256 + col] = v[k]; // lazy, finished by the row pass
         }
         else
         {
@@ -230,7 +229,7 @@ __global__ void __launch_bounds__(256) ntt_col_pass(Map map, const TwPair* __res
 #pragma unroll
             for (int k = 0; k < 16; ++k)
                 v[k] = in[(long long) (16 * tt + k) * 256 + col];
-            gs_round_b<S>(v, tw, 0, 0, tt, p, p2);
+            gs_round_b<S, VAR>(v, tw, 0, 0, tt, bc);
 #pragma unroll
             for (int k = 0; k < 16; ++k)
                 sm[(16 * tt + k) * C + c] = v[k];
@@ -245,54 +244,58 @@ __global__ void __launch_bounds__(256) ntt_col_pass(Map map, const TwPair* __res
             for (int k = 0; k < 16; ++k)
                 v[k] = in[(long long) (tt + T * k) * 256 + col];
         }
-        gs_round_a_final(v, tw, p, p2, ninv, wninv);
+        gs_round_a_final<VAR>(v, tw, bc, ninv, wninv);
 #pragma unroll
         for (int k = 0; k < 16; ++k)
             out[(long long) (tt + T * k) * 256 + col] = v[k];
     }
 }
 
-// Row pass: the 8 stages that live inside one 256-word row.  16 threads per
-// row, 16 rows per CTA.  S1 = n - 8 is the number of column-pass stages.
-template <bool INV, class Map>
-__global__ void __launch_bounds__(256) ntt_row_pass(Map map, const TwPair* __restrict__ tw_all,
-                                                    const PrimeConst* __restrict__ pcs, int logn,
-                                                    bool first_pass)
+template <int S, bool INV, class Map>
+__global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS) ntt_col_pass(Map map, const TwPair* __restrict__ tw_all,
+                                                    const PrimeConst* __restrict__ pcs,
+                                                    const TwPair* __restrict__ inv_last, int logn,
+                                                    bool first_pass, int variant)
 {
-    constexpr int PITCH = 288; // 256 + 2 words of padding per 16
-    __shared__ __align__(16) u64 sm[16 * PITCH];
-    const int S1 = logn - 8;
-    const int tiles = (1 << S1) / 16;
+    constexpr int T = (1 << S) / 16;
+    constexpr int C = 256 / T;
+    __shared__ u64 sm[(S > 4) ? (1 << S) * C : 1];
+    const int tiles = T; // 256 / C
     long long z = blockIdx.x / tiles;
     int tile = blockIdx.x % tiles;
     const u64* in;
     u64* out;
-    int prime;
-    map.get(z, in, out, prime);
+    int prime, aux;
+    map.get(z, in, out, prime, aux);
     if (!first_pass)
         in = out;
     const PrimeConst pc = pcs[prime];
-    const u64 p = pc.p, p2 = 2 * pc.p;
     const TwPair* tw = tw_all + ((long long) prime << logn);
+    if (INV || variant == 1 || !pc.nc_ok)
+        col_pass_body<S, INV, 1>(map, in, out, prime, pc, tw, inv_last, tile, first_pass, aux, sm);
+    else
+        col_pass_body<S, INV, 2>(map, in, out, prime, pc, tw, inv_last, tile, first_pass, aux, sm);
+}
 
-    const int tt = threadIdx.x & 15;
-    const int rl = threadIdx.x >> 4;
-    const int r = tile * 16 + rl;
-    const u64* rin = in + (long long) r * 256;
-    u64* rout = out + (long long) r * 256;
-    u64* srow = sm + rl * PITCH;
+// Row pass: the 8 stages that live inside one 256-word row.  16 threads per
+// row, 16 rows per CTA.  S1 = n - 8 is the number of column-pass stages.
+template <bool INV, int VAR>
+__device__ __forceinline__ void row_pass_body(const u64* rin, u64* rout, const PrimeConst& pc,
+                                              const TwPair* __restrict__ tw, int S1, int r, int tt,
+                                              u64* srow)
+{
+    const BflyConst bc{pc.p, 2 * pc.p, 4 * pc.p, 0 - pc.p};
     u64 v[16];
-
     if constexpr (!INV)
     {
 #pragma unroll
         for (int k = 0; k < 16; ++k)
             v[k] = rin[tt + 16 * k];
-        ct_round_a(v, tw, S1, r, p, p2);
+        ct_round_a<VAR>(v, tw, S1, r, bc);
 #pragma unroll
         for (int k = 0; k < 16; ++k)
             srow[tt + 18 * k] = v[k];
-        __syncthreads();
+        __syncwarp(); // a row lives in one half-warp: the transpose is warp-local
 #pragma unroll
         for (int k = 0; k < 16; k += 2)
         {
@@ -300,13 +303,13 @@ __global__ void __launch_bounds__(256) ntt_row_pass(Map map, const TwPair* __res
             v[k] = t2.x;
             v[k + 1] = t2.y;
         }
-        ct_round_b<8>(v, tw, S1, r, tt, p, p2);
+        ct_round_b<8, VAR>(v, tw, S1, r, tt, bc);
 #pragma unroll
         for (int k = 0; k < 16; k += 2)
         {
             ulonglong2 t2;
-            t2.x = csub(csub(v[k], p2), p);
-            t2.y = csub(csub(v[k + 1], p2), p);
+            t2.x = ct_finish<VAR>(v[k], bc, pc);
+            t2.y = ct_finish<VAR>(v[k + 1], bc, pc);
             *reinterpret_cast<ulonglong2*>(rout + 16 * tt + k) = t2;
         }
     }
@@ -319,7 +322,7 @@ __global__ void __launch_bounds__(256) ntt_row_pass(Map map, const TwPair* __res
             v[k] = t2.x;
             v[k + 1] = t2.y;
         }
-        gs_round_b<8>(v, tw, S1, r, tt, p, p2);
+        gs_round_b<8, VAR>(v, tw, S1, r, tt, bc);
 #pragma unroll
         for (int k = 0; k < 16; k += 2)
         {
@@ -328,14 +331,193 @@ __global__ void __launch_bounds__(256) ntt_row_pass(Map map, const TwPair* __res
             t2.y = v[k + 1];
             *reinterpret_cast<ulonglong2*>(srow + 18 * tt + k) = t2;
         }
-        __syncthreads();
+        __syncwarp(); // a row lives in one half-warp: the transpose is warp-local
 #pragma unroll
         for (int k = 0; k < 16; ++k)
             v[k] = srow[tt + 18 * k];
-        gs_round_a(v, tw, S1, r, p, p2);
+        gs_round_a<VAR>(v, tw, S1, r, bc);
 #pragma unroll
         for (int k = 0; k < 16; ++k)
-            rout[tt + 16 * k] = v[k]; // lazy [0,2p), finished by the column pass
+            rout[tt + 16 * k] = v[k]; // lazy, finished by the column pass
+    }
+}
+
+template <bool INV, class Map>
+__global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS) ntt_row_pass(Map map, const TwPair* __restrict__ tw_all,
+                                                    const PrimeConst* __restrict__ pcs, int logn,
+                                                    bool first_pass, int variant)
+{
+    constexpr int PITCH = 288; // 256 + 2 words of padding per 16
+    __shared__ __align__(16) u64 sm[16 * PITCH];
+    const int S1 = logn - 8;
+    const int tiles = (1 << S1) / 16;
+    long long z = blockIdx.x / tiles;
+    int tile = blockIdx.x % tiles;
+    const u64* in;
+    u64* out;
+    int prime, aux;
+    map.get(z, in, out, prime, aux);
+    if (!first_pass)
+        in = out;
+    const PrimeConst pc = pcs[prime];
+    const TwPair* tw = tw_all + ((long long) prime << logn);
+    const int tt = threadIdx.x & 15;
+    const int rl = threadIdx.x >> 4;
+    const int r = tile * 16 + rl;
+    const u64* rin = in + (long long) r * 256;
+    u64* rout = out + (long long) r * 256;
+    u64* srow = sm + rl * PITCH;
+    if (INV || variant == 1 || !pc.nc_ok)
+        row_pass_body<INV, 1>(rin, rout, pc, tw, S1, r, tt, srow);
+    else
+        row_pass_body<INV, 2>(rin, rout, pc, tw, S1, r, tt, srow);
+}
+
+// ---------------------------------------------------------------------------
+// Row pass through TMA.  One CTA owns a tile of 16 rows (256 lines of 128 B,
+// 32 KiB).  A 2-D tensor map over "lines of sixteen 64-bit words" brings the
+// tile into shared memory with the 128-byte swizzle (UTMALDG), the threads
+// run the eight stages out of registers with ONE in-place, warp-local,
+// bank-conflict-free transpose, and the canonical result leaves through the
+// same swizzled buffer with a TMA store (UTMASTG).  The load/store unit only
+// sees shared-memory traffic and coalesced twiddle reads.
+//
+// Swizzled position of element e of line l of a row (row base 2 KiB aligned):
+//   byte = l*128 + ((e>>1) ^ (l&7))*16 + (e&1)*8
+// Round A (idx = tt + 16k) touches element tt of line k: a permutation inside
+// one 128-byte line -> conflict free.  Round B (idx = 16tt + k) touches the
+// eight 16-byte chunks of line tt at chunk positions c ^ (tt&7) -> the eight
+// lanes of a quarter warp hit eight different bank groups.
+// ---------------------------------------------------------------------------
+constexpr int kRowTileBytes = 16 * 2048;
+
+template <bool INV, int VAR>
+__device__ __forceinline__ void row_pass_tma_body(unsigned char* rowp, const PrimeConst& pc,
+                                                  const TwPair* __restrict__ tw,
+                                                  const TwPair* __restrict__ blk, int S1, int r, int tt)
+{
+    const BflyConst bc{pc.p, 2 * pc.p, 4 * pc.p, 0 - pc.p};
+    u64 v[16];
+    unsigned char* lineB = rowp + tt * 128;
+    const int sw = tt & 7;
+    if constexpr (!INV)
+    {
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            v[k] = *reinterpret_cast<const u64*>(rowp + k * 128 + ((((tt >> 1) ^ (k & 7)) << 4) | ((tt & 1) << 3)));
+        ct_round_a<VAR>(v, tw, S1, r, bc);
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            *reinterpret_cast<u64*>(rowp + k * 128 + ((((tt >> 1) ^ (k & 7)) << 4) | ((tt & 1) << 3))) = v[k];
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+        {
+            const ulonglong2 t2 = *reinterpret_cast<const ulonglong2*>(lineB + ((c ^ sw) << 4));
+            v[2 * c] = t2.x;
+            v[2 * c + 1] = t2.y;
+        }
+        ct_round_b_lm<VAR>(v, blk, tt, bc);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+        {
+            ulonglong2 t2;
+            t2.x = ct_finish<VAR>(v[2 * c], bc, pc);
+            t2.y = ct_finish<VAR>(v[2 * c + 1], bc, pc);
+            *reinterpret_cast<ulonglong2*>(lineB + ((c ^ sw) << 4)) = t2;
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+        {
+            const ulonglong2 t2 = *reinterpret_cast<const ulonglong2*>(lineB + ((c ^ sw) << 4));
+            v[2 * c] = t2.x;
+            v[2 * c + 1] = t2.y;
+        }
+        gs_round_b_lm<VAR>(v, blk, tt, bc);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+        {
+            ulonglong2 t2;
+            t2.x = v[2 * c];
+            t2.y = v[2 * c + 1];
+            *reinterpret_cast<ulonglong2*>(lineB + ((c ^ sw) << 4)) = t2;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            v[k] = *reinterpret_cast<const u64*>(rowp + k * 128 + ((((tt >> 1) ^ (k & 7)) << 4) | ((tt & 1) << 3)));
+        gs_round_a<VAR>(v, tw, S1, r, bc);
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            *reinterpret_cast<u64*>(rowp + k * 128 + ((((tt >> 1) ^ (k & 7)) << 4) | ((tt & 1) << 3))) = v[k]; // lazy
+    }
+}
+
+template <bool INV, class Map>
+__global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS)
+    ntt_row_pass_tma(Map map, const __grid_constant__ CUtensorMap tm_in,
+                     const __grid_constant__ CUtensorMap tm_out, const u64* in_base, const u64* out_base,
+                     const TwPair* __restrict__ tw_all, const TwPair* __restrict__ rowb_all,
+                     const PrimeConst* __restrict__ pcs, int logn, bool first_pass, int variant)
+{
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    // 1024-byte alignment for the 128B swizzle; plain offset arithmetic keeps the
+    // pointer in the shared address space (LDS/STS instead of generic LD/ST)
+    unsigned char* tile = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int S1 = logn - 8;
+    const int tiles = (1 << S1) / 16;
+    long long z = blockIdx.x / tiles;
+    int tile_idx = blockIdx.x % tiles;
+    const u64* in;
+    u64* out;
+    int prime, aux;
+    map.get(z, in, out, prime, aux);
+    if (!first_pass)
+    {
+        in = out;
+        in_base = out_base;
+    }
+    // tile position in 128-byte lines relative to the tensor-map bases
+    const int line_in = (int) ((in - in_base) >> 4) + tile_idx * 256;
+    const int line_out = (int) ((out - out_base) >> 4) + tile_idx * 256;
+    const CUtensorMap* tmi = first_pass ? &tm_in : &tm_out;
+
+    if (threadIdx.x == 0)
+    {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        mbar_arrive_expect_tx(&bar, kRowTileBytes);
+        tma_load_2d(tile, tmi, &bar, 0, line_in);
+    }
+    const PrimeConst pc = pcs[prime];
+    const TwPair* tw = tw_all + ((long long) prime << logn);
+    const int tt = threadIdx.x & 15;
+    const int rl = threadIdx.x >> 4;
+    const int r = tile_idx * 16 + rl;
+    const TwPair* blk = rowb_all + ((((long long) prime << S1) + r) << 8);
+    unsigned char* rowp = tile + rl * 2048;
+    mbar_wait(&bar, 0);
+
+    if (INV || variant == 1 || !pc.nc_ok)
+        row_pass_tma_body<INV, 1>(rowp, pc, tw, blk, S1, r, tt);
+    else
+        row_pass_tma_body<INV, 2>(rowp, pc, tw, blk, S1, r, tt);
+
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        tma_store_2d(&tm_out, tile, 0, line_out);
+        tma_store_commit();
+        tma_store_wait_read<0>();
     }
 }
 
@@ -352,7 +534,7 @@ static void launch_col(const Context& c, const Map& m, long long n_polys, bool f
 #define HEON_COL(SS)                                                                               \
     case SS:                                                                                       \
         ntt_col_pass<SS, INV, Map><<<grid, 256, 0, st>>>(m, INV ? c.d_inv : c.d_fwd, c.d_pc,       \
-                                                         c.d_inv_last, c.logn, first);             \
+                                                         c.d_inv_last, c.logn, first, c.ntt_variant);             \
         break;
     switch (S)
     {
@@ -373,22 +555,92 @@ static void launch_row(const Context& c, const Map& m, long long n_polys, bool f
     const int S = c.logn - 8;
     const unsigned grid = (unsigned) (n_polys * ((1 << S) / 16));
     LaunchScope scope(INV ? KC_NTT_INV_ROW : KC_NTT_FWD_ROW, st);
-    ntt_row_pass<INV, Map><<<grid, 256, 0, st>>>(m, INV ? c.d_inv : c.d_fwd, c.d_pc, c.logn, first);
+    ntt_row_pass<INV, Map><<<grid, 256, 0, st>>>(m, INV ? c.d_inv : c.d_fwd, c.d_pc, c.logn, first,
+                                                 c.ntt_variant);
+}
+
+// ---- tensor maps -----------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || !p)
+            throw std::runtime_error("cuTensorMapEncodeTiled is not available from this driver");
+        return (EncodeTiledFn) p;
+    }();
+    return fn;
+}
+
+// Buffer viewed as `lines` rows of sixteen 64-bit words (128 B); box = 256 lines (one 16-row tile).
+static CUtensorMap make_line_map(const u64* base, long long words)
+{
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {16, (cuuint64_t) (words >> 4)};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {16, 256};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult rc = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*) base, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS)
+        throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string((int) rc) + ")");
+    return m;
+}
+
+// extent of the buffers a map touches (for the tensor-map bounds)
+struct Extent {
+    const u64* in_base;
+    long long in_words;
+    const u64* out_base;
+    long long out_words;
+};
+
+template <bool INV, class Map>
+static void launch_row_tma(const Context& c, const Map& m, long long n_polys, bool first, const Extent& e,
+                           cudaStream_t st)
+{
+    const int S = c.logn - 8;
+    const unsigned grid = (unsigned) (n_polys * ((1 << S) / 16));
+    const CUtensorMap tm_out = make_line_map(e.out_base, e.out_words);
+    const CUtensorMap tm_in = first ? make_line_map(e.in_base, e.in_words) : tm_out;
+    static bool attr_set[2] = {false, false};
+    auto kfn = ntt_row_pass_tma<INV, Map>;
+    const int smem = kRowTileBytes + 1024;
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    (void) attr_set;
+    LaunchScope scope(INV ? KC_NTT_INV_ROW : KC_NTT_FWD_ROW, st);
+    kfn<<<grid, 256, smem, st>>>(m, tm_in, tm_out, e.in_base, e.out_base, INV ? c.d_inv : c.d_fwd,
+                                 INV ? c.d_inv_rowb : c.d_fwd_rowb, c.d_pc, c.logn, first, c.ntt_variant);
 }
 
 template <class Map>
-static void run_ntt(const Context& c, const Map& m, long long n_polys, bool inverse, cudaStream_t st)
+static void run_ntt(const Context& c, const Map& m, long long n_polys, bool inverse, const Extent& e,
+                    cudaStream_t st)
 {
     if (n_polys <= 0)
         return;
+    // TMA needs 16-byte aligned bases; fall back to the LSU row pass otherwise
+    const bool tma = c.use_tma && ((reinterpret_cast<uintptr_t>(e.in_base) | reinterpret_cast<uintptr_t>(e.out_base)) & 15) == 0;
     if (!inverse)
     {
         launch_col<false>(c, m, n_polys, true, st);
-        launch_row<false>(c, m, n_polys, false, st);
+        if (tma)
+            launch_row_tma<false>(c, m, n_polys, false, e, st);
+        else
+            launch_row<false>(c, m, n_polys, false, st);
     }
     else
     {
-        launch_row<true>(c, m, n_polys, true, st);
+        if (tma)
+            launch_row_tma<true>(c, m, n_polys, true, e, st);
+        else
+            launch_row<true>(c, m, n_polys, true, st);
         launch_col<true>(c, m, n_polys, false, st);
     }
 }
@@ -397,21 +649,26 @@ void launch_ntt(const Context& c, const u64* src, u64* dst, long long n_polys, c
                 bool inverse, cudaStream_t st)
 {
     MapContig m{src, dst, pl, c.logn};
-    run_ntt(c, m, n_polys, inverse, st);
+    const long long w = n_polys << c.logn;
+    run_ntt(c, m, n_polys, inverse, Extent{src, w, dst, w}, st);
 }
 
 void launch_ntt_scattered(const Context& c, u64* base, const long long* d_offsets, int n_polys,
-                          int prime, bool inverse, cudaStream_t st)
+                          int prime, bool inverse, long long extent_words, bool aligned, cudaStream_t st)
 {
     MapScatter m{base, d_offsets, prime};
-    run_ntt(c, m, n_polys, inverse, st);
+    // offsets that are not multiples of 16 words cannot be addressed in 128-byte lines
+    Extent e{aligned ? base : base + 1, extent_words, aligned ? base : base + 1, extent_words};
+    run_ntt(c, m, n_polys, inverse, e, st);
 }
 
 void launch_ntt_strided(const Context& c, u64* base, long long bstride, int per_batch, int first,
                         long long batch, const PrimeList& pl, bool inverse, cudaStream_t st)
 {
     MapStrided m{base, bstride, per_batch, first, pl, c.logn};
-    run_ntt(c, m, batch * per_batch, inverse, st);
+    const long long w = (batch - 1) * bstride + ((long long) (first + per_batch) << c.logn);
+    const u64* b0 = (bstride & 15) ? base + 1 : base; // odd strides: no line addressing -> LSU path
+    run_ntt(c, m, batch * per_batch, inverse, Extent{b0, w, b0, w}, st);
 }
 
 void launch_ntt_strided_copy(const Context& c, const u64* src, long long src_bstride, u64* dst,
@@ -419,15 +676,19 @@ void launch_ntt_strided_copy(const Context& c, const u64* src, long long src_bst
                              cudaStream_t st)
 {
     MapStridedCopy m{src, dst, src_bstride, per_batch, pl, c.logn};
-    run_ntt(c, m, batch * per_batch, inverse, st);
+    const long long wi = (batch - 1) * src_bstride + ((long long) per_batch << c.logn);
+    const long long wo = (batch * per_batch) << c.logn;
+    const u64* s0 = (src_bstride & 15) ? src + 1 : src;
+    run_ntt(c, m, batch * per_batch, inverse, Extent{s0, wi, dst, wo}, st);
 }
 
 void launch_modup1_ntt(const Context& c, const u64* coef, long long coef_bstride, u64* out, int L,
                        int depth, long long batch, cudaStream_t st)
 {
     const int Qpl = L + c.P_size;
-    MapModUpI m{coef, out, coef_bstride, L, Qpl, depth, c.logn};
-    run_ntt(c, m, batch * L * Qpl, false, st);
+    MapModUpI m{coef, out, coef_bstride, L, Qpl, depth, c.logn, c.d_pc};
+    const long long wo = (batch * L * Qpl) << c.logn;
+    run_ntt(c, m, batch * L * Qpl, false, Extent{out, wo, out, wo}, st);
 }
 
 void launch_divround1_ntt(const Context& c, const u64* src, long long bstride, long long cstride,
@@ -435,7 +696,8 @@ void launch_divround1_ntt(const Context& c, const u64* src, long long bstride, l
                           long long batch, cudaStream_t st)
 {
     MapDivRoundOne m{src, out, bstride, cstride, Lout, c.logn, half, plast, d_half_mod};
-    run_ntt(c, m, batch * 2 * Lout, false, st);
+    const long long wo = (batch * 2 * Lout) << c.logn;
+    run_ntt(c, m, batch * 2 * Lout, false, Extent{out, wo, out, wo}, st);
 }
 
 } // namespace heon

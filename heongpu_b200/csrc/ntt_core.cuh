@@ -6,6 +6,19 @@
 // coefficient index j.  Inside one pass of S stages that started after s0
 // stages on vector number q this becomes, for pass-stage u and vector index
 // idx:  table[2^(s0+u) + q*2^u + (idx >> (S-u))].
+//
+// Lazy-reduction variants of the forward (Cooley-Tukey) butterfly.  VAR 1/2
+// use the Shoup product T = Y*w - q*p with an APPROXIMATE quotient
+// q in [floor(Y*ws/2^64) - 2, floor(Y*ws/2^64)] (three 32x32->64 multiplies
+// instead of four), so T is in [0,4p):
+//   VAR 0  Harvey, exact quotient: values in [0,4p), one conditional
+//          subtraction of 2p per butterfly.
+//   VAR 1  values in [0,8p), one conditional subtraction of 4p per butterfly;
+//          valid for every p < 2^61.
+//   VAR 2  no per-stage correction at all: every stage adds at most 4p to the
+//          bound, 4p + 16*4p = 68p < 2^64 needs p <= 57 bits; the single
+//          final reduction uses a 32-bit quotient estimate (PrimeConst::fin_m).
+// Stored words are always canonical, so all variants give identical results.
 #pragma once
 #include "modarith.cuh"
 
@@ -20,112 +33,280 @@ __device__ __forceinline__ TwPair ld_tw(const TwPair* p)
     return r;
 }
 
-// Cooley-Tukey lazy butterfly: inputs in [0,4p), outputs in [0,4p).
-__device__ __forceinline__ void ct_bfly(u64& X, u64& Y, const TwPair& w, u64 p, u64 p2)
+// floor(a*b / 2^64) minus at most 2: drops the low x low partial product and
+// the carry out of the low halves of the two cross products.
+__device__ __forceinline__ u64 mulhi_approx(u64 a, u64 b)
 {
-    u64 x = csub(X, p2);
-    u64 t = shoup_mul_lazy(Y, w.w, w.ws, p);
-    X = x + t;
-    Y = x - t + p2;
+    const unsigned a0 = (unsigned) a, a1 = (unsigned) (a >> 32);
+    const unsigned b0 = (unsigned) b, b1 = (unsigned) (b >> 32);
+    const u64 m1 = (u64) a0 * b1;
+    const u64 m2 = (u64) a1 * b0;
+    return (u64) a1 * b1 + ((m1 >> 32) + (m2 >> 32));
 }
 
-// Gentleman-Sande lazy butterfly: inputs in [0,2p), outputs in [0,2p).
-__device__ __forceinline__ void gs_bfly(u64& X, u64& Y, const TwPair& w, u64 p, u64 p2)
+// x*w mod p, lazily in [0,4p), for ANY 64-bit x.
+__device__ __forceinline__ u64 shoup_mul_lazy3(u64 x, u64 w, u64 ws, u64 p)
 {
-    u64 s = csub(X + Y, p2);
-    u64 d = X - Y + p2;
-    X = s;
-    Y = shoup_mul_lazy(d, w.w, w.ws, p);
+    const u64 q = mulhi_approx(x, ws);
+    return x * w - q * p;
+}
+
+struct BflyConst {
+    u64 p, p2, p4;
+    u64 np; // 2^64 - p
+};
+
+// Hand-scheduled instruction selection for the hot butterflies.  ptxas, left
+// to itself, turns 64-bit additions into IMAD.WIDE (a*1+c) and so loads the
+// multiplier pipe -- the bottleneck of this kernel -- with work the integer
+// ALU can do.  Written with 32-bit carry-chain adds, the multiplier pipe only
+// sees the nine real multiplies of a Shoup product:
+//   q  ~ hi64(Y*ws)        2 x mul.hi.u32 + 1 x mul.wide.u32   (q >= exact - 2)
+//   T  = lo64(Y*w) + lo64(q*(2^64-p))   2 x mad.wide.u32 + 4 x mad.lo.u32
+// T is in [0,4p) for ANY 64-bit Y.
+__device__ __forceinline__ u64 shoup_lazy_ptx(u64 y, u64 w, u64 ws, u64 np)
+{
+#ifndef __CUDA_ARCH__
+    return y * w + mulhi_approx(y, ws) * np; // host emulation (tests/host_emul.cpp)
+#else
+    u64 t;
+    asm("{\n\t"
+        ".reg .u32 y0,y1,w0,w1,s0,s1,n0,n1,h1,h2,q0,q1,t0,t1;\n\t"
+        ".reg .u64 q, tt;\n\t"
+        "mov.b64 {y0,y1}, %1;\n\t"
+        "mov.b64 {w0,w1}, %2;\n\t"
+        "mov.b64 {s0,s1}, %3;\n\t"
+        "mov.b64 {n0,n1}, %4;\n\t"
+        "mul.hi.u32 h1, y0, s1;\n\t"
+        "mul.hi.u32 h2, y1, s0;\n\t"
+        "mul.wide.u32 q, y1, s1;\n\t"
+        "mov.b64 {q0,q1}, q;\n\t"
+        "add.cc.u32 q0, q0, h1;\n\t"
+        "addc.u32 q1, q1, 0;\n\t"
+        "add.cc.u32 q0, q0, h2;\n\t"
+        "addc.u32 q1, q1, 0;\n\t"
+        "mul.wide.u32 tt, y0, w0;\n\t"
+        "mad.wide.u32 tt, q0, n0, tt;\n\t"
+        "mov.b64 {t0,t1}, tt;\n\t"
+        "mad.lo.u32 t1, y0, w1, t1;\n\t"
+        "mad.lo.u32 t1, y1, w0, t1;\n\t"
+        "mad.lo.u32 t1, q0, n1, t1;\n\t"
+        "mad.lo.u32 t1, q1, n0, t1;\n\t"
+        "mov.b64 %0, {t0,t1};\n\t"
+        "}"
+        : "=l"(t)
+        : "l"(y), "l"(w), "l"(ws), "l"(np));
+    return t;
+#endif
+}
+
+// X' = X + T,  Y' = X + C - T   with 32-bit carry chains (integer ALU only)
+__device__ __forceinline__ void addsub_ptx(u64& X, u64& Y, u64 T, u64 C)
+{
+#ifndef __CUDA_ARCH__
+    const u64 x = X;
+    X = x + T;
+    Y = x + C - T;
+#else
+    u64 xo, yo;
+    asm("{\n\t"
+        ".reg .u32 x0,x1,t0,t1,c0,c1,a0,a1,b0,b1;\n\t"
+        "mov.b64 {x0,x1}, %2;\n\t"
+        "mov.b64 {t0,t1}, %3;\n\t"
+        "mov.b64 {c0,c1}, %4;\n\t"
+        "add.cc.u32 a0, x0, t0;\n\t"
+        "addc.u32 a1, x1, t1;\n\t"
+        "add.cc.u32 b0, x0, c0;\n\t"
+        "addc.u32 b1, x1, c1;\n\t"
+        "sub.cc.u32 b0, b0, t0;\n\t"
+        "subc.u32 b1, b1, t1;\n\t"
+        "mov.b64 %0, {a0,a1};\n\t"
+        "mov.b64 %1, {b0,b1};\n\t"
+        "}"
+        : "=l"(xo), "=l"(yo)
+        : "l"(X), "l"(T), "l"(C));
+    X = xo;
+    Y = yo;
+#endif
+}
+
+template <int VAR> __device__ __forceinline__ void ct_bfly(u64& X, u64& Y, const TwPair& w, const BflyConst& c)
+{
+    if (VAR == 0)
+    {
+        const u64 x = csub(X, c.p2);
+        const u64 t = shoup_mul_lazy(Y, w.w, w.ws, c.p);
+        X = x + t;
+        Y = x - t + c.p2;
+    }
+    else if (VAR == 1)
+    {
+        X = csub(X, c.p4);
+        const u64 t = shoup_lazy_ptx(Y, w.w, w.ws, c.np);
+        addsub_ptx(X, Y, t, c.p4);
+    }
+    else
+    {
+        const u64 t = shoup_lazy_ptx(Y, w.w, w.ws, c.np);
+        addsub_ptx(X, Y, t, c.p4);
+    }
+}
+
+// canonical value of a lazy forward word
+template <int VAR> __device__ __forceinline__ u64 ct_finish(u64 x, const BflyConst& c, const PrimeConst& pc)
+{
+    if (VAR == 0)
+        return csub(csub(x, c.p2), c.p);
+    if (VAR == 1)
+        return csub(csub(csub(x, c.p4), c.p2), c.p);
+    // x < 128p: 32-bit quotient estimate, remainder in [0,2p)
+    const unsigned xt = (unsigned) (x >> pc.fin_shift);
+    const unsigned q = (unsigned) (((u64) xt * pc.fin_m) >> 56);
+    return csub(x - (u64) q * c.p, c.p);
+}
+
+// Gentleman-Sande lazy butterfly.  GVAR 0: values in [0,2p), exact quotient.
+// GVAR 1: values in [0,4p), approximate quotient.
+template <int GVAR> __device__ __forceinline__ void gs_bfly(u64& X, u64& Y, const TwPair& w, const BflyConst& c)
+{
+    if (GVAR == 0)
+    {
+        const u64 s = csub(X + Y, c.p2);
+        const u64 d = X - Y + c.p2;
+        X = s;
+        Y = shoup_mul_lazy(d, w.w, w.ws, c.p);
+    }
+    else
+    {
+        u64 s = X, d = Y;
+        addsub_ptx(s, d, Y, c.p4); // s = X + Y, d = X + 4p - Y
+        X = csub(s, c.p4);
+        Y = shoup_lazy_ptx(d, w.w, w.ws, c.np);
+    }
 }
 
 // One stage on the 16 registers; butterflies pair k and k + 2^LS, the
 // twiddle changes every 2^(LS+1) registers.
-template <int LS, bool INV>
-__device__ __forceinline__ void stage16(u64 (&v)[16], const TwPair* __restrict__ tw, u64 p, u64 p2)
+template <int LS, bool INV, int VAR, int GSTRIDE = 1>
+__device__ __forceinline__ void stage16(u64 (&v)[16], const TwPair* __restrict__ tw, const BflyConst& c)
 {
 #pragma unroll
     for (int g = 0; g < (8 >> LS); ++g)
     {
-        const TwPair w = ld_tw(tw + g);
+        const TwPair w = ld_tw(tw + g * GSTRIDE);
 #pragma unroll
         for (int j = 0; j < (1 << LS); ++j)
         {
             const int k = g * (2 << LS) + j;
             if (INV)
-                gs_bfly(v[k], v[k + (1 << LS)], w, p, p2);
+                gs_bfly<VAR>(v[k], v[k + (1 << LS)], w, c);
             else
-                ct_bfly(v[k], v[k + (1 << LS)], w, p, p2);
+                ct_bfly<VAR>(v[k], v[k + (1 << LS)], w, c);
         }
     }
 }
 
 // Round A: the four stages with register strides 8,4,2,1 when the thread
 // holds idx = tt + T*k.  Twiddles do not depend on tt.
-__device__ __forceinline__ void ct_round_a(u64 (&v)[16], const TwPair* __restrict__ tw, int s0,
-                                           int q, u64 p, u64 p2)
+template <int VAR>
+__device__ __forceinline__ void ct_round_a(u64 (&v)[16], const TwPair* __restrict__ tw, int s0, int q,
+                                           const BflyConst& c)
 {
-    stage16<3, false>(v, tw + (1 << (s0 + 0)) + (q << 0), p, p2);
-    stage16<2, false>(v, tw + (1 << (s0 + 1)) + (q << 1), p, p2);
-    stage16<1, false>(v, tw + (1 << (s0 + 2)) + (q << 2), p, p2);
-    stage16<0, false>(v, tw + (1 << (s0 + 3)) + (q << 3), p, p2);
+    stage16<3, false, VAR>(v, tw + (1 << (s0 + 0)) + (q << 0), c);
+    stage16<2, false, VAR>(v, tw + (1 << (s0 + 1)) + (q << 1), c);
+    stage16<1, false, VAR>(v, tw + (1 << (s0 + 2)) + (q << 2), c);
+    stage16<0, false, VAR>(v, tw + (1 << (s0 + 3)) + (q << 3), c);
 }
 
-__device__ __forceinline__ void gs_round_a(u64 (&v)[16], const TwPair* __restrict__ tw, int s0,
-                                           int q, u64 p, u64 p2)
+template <int GVAR>
+__device__ __forceinline__ void gs_round_a(u64 (&v)[16], const TwPair* __restrict__ tw, int s0, int q,
+                                           const BflyConst& c)
 {
-    stage16<0, true>(v, tw + (1 << (s0 + 3)) + (q << 3), p, p2);
-    stage16<1, true>(v, tw + (1 << (s0 + 2)) + (q << 2), p, p2);
-    stage16<2, true>(v, tw + (1 << (s0 + 1)) + (q << 1), p, p2);
-    stage16<3, true>(v, tw + (1 << (s0 + 0)) + (q << 0), p, p2);
+    stage16<0, true, GVAR>(v, tw + (1 << (s0 + 3)) + (q << 3), c);
+    stage16<1, true, GVAR>(v, tw + (1 << (s0 + 2)) + (q << 2), c);
+    stage16<2, true, GVAR>(v, tw + (1 << (s0 + 1)) + (q << 1), c);
+    stage16<3, true, GVAR>(v, tw + (1 << (s0 + 0)) + (q << 0), c);
 }
 
 // Last round of the inverse transform (s0 = 0, q = 0): the final stage
 // multiplies both outputs by N^-1 (folded into the twiddle) and canonicalises.
-__device__ __forceinline__ void gs_round_a_final(u64 (&v)[16], const TwPair* __restrict__ tw, u64 p,
-                                                 u64 p2, const TwPair& ninv, const TwPair& wninv)
+template <int GVAR>
+__device__ __forceinline__ void gs_round_a_final(u64 (&v)[16], const TwPair* __restrict__ tw,
+                                                 const BflyConst& c, const TwPair& ninv,
+                                                 const TwPair& wninv)
 {
-    stage16<0, true>(v, tw + 8, p, p2);
-    stage16<1, true>(v, tw + 4, p, p2);
-    stage16<2, true>(v, tw + 2, p, p2);
+    stage16<0, true, GVAR>(v, tw + 8, c);
+    stage16<1, true, GVAR>(v, tw + 4, c);
+    stage16<2, true, GVAR>(v, tw + 2, c);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
     {
-        u64 s = v[k] + v[k + 8]; // < 4p
-        u64 d = v[k] - v[k + 8] + p2;
-        v[k] = csub(shoup_mul_lazy(s, ninv.w, ninv.ws, p), p);
-        v[k + 8] = csub(shoup_mul_lazy(d, wninv.w, wninv.ws, p), p);
+        const u64 s = v[k] + v[k + 8]; // < 8p
+        const u64 d = v[k] - v[k + 8] + c.p4;
+        if (GVAR == 0)
+        {
+            v[k] = csub(shoup_mul_lazy(s, ninv.w, ninv.ws, c.p), c.p);
+            v[k + 8] = csub(shoup_mul_lazy(d, wninv.w, wninv.ws, c.p), c.p);
+        }
+        else
+        {
+            v[k] = csub(csub(shoup_lazy_ptx(s, ninv.w, ninv.ws, c.np), c.p2), c.p);
+            v[k + 8] = csub(csub(shoup_lazy_ptx(d, wninv.w, wninv.ws, c.np), c.p2), c.p);
+        }
     }
 }
 
 // Round B: the S-4 stages with strides < 16 when the thread holds the 16
 // contiguous indices idx = 16*tt + k.
-template <int S>
-__device__ __forceinline__ void ct_round_b(u64 (&v)[16], const TwPair* __restrict__ tw, int s0,
-                                           int q, int tt, u64 p, u64 p2)
+template <int S, int VAR>
+__device__ __forceinline__ void ct_round_b(u64 (&v)[16], const TwPair* __restrict__ tw, int s0, int q,
+                                           int tt, const BflyConst& c)
 {
     // pass-stage u = 4..S-1, register stride 2^(S-1-u)
     if constexpr (S >= 5)
-        stage16<S - 5, false>(v, tw + (1 << (s0 + 4)) + (q << 4) + (tt << (8 - S)), p, p2);
+        stage16<S - 5, false, VAR>(v, tw + (1 << (s0 + 4)) + (q << 4) + (tt << (8 - S)), c);
     if constexpr (S >= 6)
-        stage16<S - 6, false>(v, tw + (1 << (s0 + 5)) + (q << 5) + (tt << (9 - S)), p, p2);
+        stage16<S - 6, false, VAR>(v, tw + (1 << (s0 + 5)) + (q << 5) + (tt << (9 - S)), c);
     if constexpr (S >= 7)
-        stage16<S - 7, false>(v, tw + (1 << (s0 + 6)) + (q << 6) + (tt << (10 - S)), p, p2);
+        stage16<S - 7, false, VAR>(v, tw + (1 << (s0 + 6)) + (q << 6) + (tt << (10 - S)), c);
     if constexpr (S >= 8)
-        stage16<S - 8, false>(v, tw + (1 << (s0 + 7)) + (q << 7) + (tt << (11 - S)), p, p2);
+        stage16<S - 8, false, VAR>(v, tw + (1 << (s0 + 7)) + (q << 7) + (tt << (11 - S)), c);
 }
 
-template <int S>
-__device__ __forceinline__ void gs_round_b(u64 (&v)[16], const TwPair* __restrict__ tw, int s0,
-                                           int q, int tt, u64 p, u64 p2)
+// Round B of the 256-point row transform with the lane-major twiddle block of
+// this (prime,row): entry e = 2^(u-4)-1+g of lane tt sits at blk[e*16 + tt], so
+// the 16 lanes of a row read 256 contiguous bytes per butterfly group.
+template <int VAR>
+__device__ __forceinline__ void ct_round_b_lm(u64 (&v)[16], const TwPair* __restrict__ blk, int tt,
+                                              const BflyConst& c)
+{
+    stage16<3, false, VAR, 16>(v, blk + 0 * 16 + tt, c);
+    stage16<2, false, VAR, 16>(v, blk + 1 * 16 + tt, c);
+    stage16<1, false, VAR, 16>(v, blk + 3 * 16 + tt, c);
+    stage16<0, false, VAR, 16>(v, blk + 7 * 16 + tt, c);
+}
+template <int GVAR>
+__device__ __forceinline__ void gs_round_b_lm(u64 (&v)[16], const TwPair* __restrict__ blk, int tt,
+                                              const BflyConst& c)
+{
+    stage16<0, true, GVAR, 16>(v, blk + 7 * 16 + tt, c);
+    stage16<1, true, GVAR, 16>(v, blk + 3 * 16 + tt, c);
+    stage16<2, true, GVAR, 16>(v, blk + 1 * 16 + tt, c);
+    stage16<3, true, GVAR, 16>(v, blk + 0 * 16 + tt, c);
+}
+
+template <int S, int GVAR>
+__device__ __forceinline__ void gs_round_b(u64 (&v)[16], const TwPair* __restrict__ tw, int s0, int q,
+                                           int tt, const BflyConst& c)
 {
     if constexpr (S >= 8)
-        stage16<S - 8, true>(v, tw + (1 << (s0 + 7)) + (q << 7) + (tt << (11 - S)), p, p2);
+        stage16<S - 8, true, GVAR>(v, tw + (1 << (s0 + 7)) + (q << 7) + (tt << (11 - S)), c);
     if constexpr (S >= 7)
-        stage16<S - 7, true>(v, tw + (1 << (s0 + 6)) + (q << 6) + (tt << (10 - S)), p, p2);
+        stage16<S - 7, true, GVAR>(v, tw + (1 << (s0 + 6)) + (q << 6) + (tt << (10 - S)), c);
     if constexpr (S >= 6)
-        stage16<S - 6, true>(v, tw + (1 << (s0 + 5)) + (q << 5) + (tt << (9 - S)), p, p2);
+        stage16<S - 6, true, GVAR>(v, tw + (1 << (s0 + 5)) + (q << 5) + (tt << (9 - S)), c);
     if constexpr (S >= 5)
-        stage16<S - 5, true>(v, tw + (1 << (s0 + 4)) + (q << 4) + (tt << (8 - S)), p, p2);
+        stage16<S - 5, true, GVAR>(v, tw + (1 << (s0 + 4)) + (q << 4) + (tt << (8 - S)), c);
 }
 
 } // namespace heon

@@ -1,0 +1,79 @@
+// Thin PTX wrappers for the Blackwell/Hopper async-copy machinery used by the
+// row-pass kernels: mbarrier, 2-D tensor-map TMA loads/stores (SASS UTMALDG /
+// UTMASTG) and the proxy fences that order generic shared-memory accesses
+// against the async proxy.
+#pragma once
+#include <cuda.h>
+#include <cstdint>
+
+namespace heon {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+// make the barrier initialisation visible to the async proxy
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    asm volatile("{\n\t"
+                 ".reg .pred P1;\n\t"
+                 "HEON_WAIT:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+                 "@P1 bra HEON_DONE;\n\t"
+                 "bra HEON_WAIT;\n\t"
+                 "HEON_DONE:\n\t"
+                 "}" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+
+// global -> shared tile load, completion signalled on `bar` (complete_tx::bytes)
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+// shared -> global tile store (bulk async group)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+
+// wait until the committed stores have finished READING shared memory
+template <int N> __device__ __forceinline__ void tma_store_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+// generic-proxy writes to shared memory -> visible to the async proxy (TMA store)
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+} // namespace heon

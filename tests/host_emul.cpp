@@ -1,0 +1,167 @@
+// Host emulation of the device butterfly code (ntt_core.cuh compiled for the
+// CPU with tiny shims): every lazy-reduction variant of the forward and
+// inverse transform must reproduce the textbook merged NTT / INTT exactly.
+// Built and run by tests/test_host_emulation.py (no GPU needed).
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+#include <cuda_runtime.h>
+static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b)
+{
+    return (unsigned long long) (((unsigned __int128) a * b) >> 64);
+}
+static inline ulonglong2 __ldg(const ulonglong2* p) { return *p; }
+#include "../heongpu_b200/csrc/ntt_core.cuh"
+using namespace heon;
+
+template <int VAR> static void fwd(std::vector<u64>& x, const std::vector<TwPair>& tw, const PrimeConst& pc)
+{
+    const BflyConst bc{pc.p, 2 * pc.p, 4 * pc.p, 0 - pc.p};
+    for (int col = 0; col < 256; ++col) // column pass, S = 4
+    {
+        u64 v[16];
+        for (int k = 0; k < 16; ++k) v[k] = x[k * 256 + col];
+        ct_round_a<VAR>(v, tw.data(), 0, 0, bc);
+        for (int k = 0; k < 16; ++k) x[k * 256 + col] = v[k];
+    }
+    for (int r = 0; r < 16; ++r) // row pass
+    {
+        u64 row[256];
+        for (int tt = 0; tt < 16; ++tt)
+        {
+            u64 v[16];
+            for (int k = 0; k < 16; ++k) v[k] = x[r * 256 + tt + 16 * k];
+            ct_round_a<VAR>(v, tw.data(), 4, r, bc);
+            for (int k = 0; k < 16; ++k) row[tt + 16 * k] = v[k];
+        }
+        for (int tt = 0; tt < 16; ++tt)
+        {
+            u64 v[16];
+            for (int k = 0; k < 16; ++k) v[k] = row[16 * tt + k];
+            ct_round_b<8, VAR>(v, tw.data(), 4, r, tt, bc);
+            for (int k = 0; k < 16; ++k) x[r * 256 + 16 * tt + k] = ct_finish<VAR>(v[k], bc, pc);
+        }
+    }
+}
+
+template <int GVAR>
+static void inv(std::vector<u64>& x, const std::vector<TwPair>& tw, const PrimeConst& pc, const TwPair& ninv,
+                const TwPair& wninv)
+{
+    const BflyConst bc{pc.p, 2 * pc.p, 4 * pc.p, 0 - pc.p};
+    for (int r = 0; r < 16; ++r) // row pass first
+    {
+        u64 row[256];
+        for (int tt = 0; tt < 16; ++tt)
+        {
+            u64 v[16];
+            for (int k = 0; k < 16; ++k) v[k] = x[r * 256 + 16 * tt + k];
+            gs_round_b<8, GVAR>(v, tw.data(), 4, r, tt, bc);
+            for (int k = 0; k < 16; ++k) row[16 * tt + k] = v[k];
+        }
+        for (int tt = 0; tt < 16; ++tt)
+        {
+            u64 v[16];
+            for (int k = 0; k < 16; ++k) v[k] = row[tt + 16 * k];
+            gs_round_a<GVAR>(v, tw.data(), 4, r, bc);
+            for (int k = 0; k < 16; ++k) x[r * 256 + tt + 16 * k] = v[k];
+        }
+    }
+    for (int col = 0; col < 256; ++col)
+    {
+        u64 v[16];
+        for (int k = 0; k < 16; ++k) v[k] = x[k * 256 + col];
+        gs_round_a_final<GVAR>(v, tw.data(), bc, ninv, wninv);
+        for (int k = 0; k < 16; ++k) x[k * 256 + col] = v[k];
+    }
+}
+
+int main()
+{
+    const int logn = 12, N = 1 << logn;
+    int failures = 0;
+    const int bitsizes[] = {30, 45, 50, 57, 58, 60, 61};
+    for (int bits : bitsizes)
+    {
+        const u64 p = bits == 61 ? 2305843009213554689ull : largest_ntt_primes(2 * N, bits, 1)[0];
+        const u64 psi = minimal_primitive_root(2 * N, p), ipsi = invmod(psi, p);
+        std::vector<TwPair> tw(N), itw(N);
+        std::vector<u64> pw(N), ipw(N);
+        pw[0] = ipw[0] = 1;
+        for (int j = 1; j < N; ++j)
+        {
+            pw[j] = mulmod(pw[j - 1], psi, p);
+            ipw[j] = mulmod(ipw[j - 1], ipsi, p);
+        }
+        for (int j = 0; j < N; ++j)
+        {
+            tw[j] = TwPair{pw[bitrev(j, logn)], shoup(pw[bitrev(j, logn)], p)};
+            itw[j] = TwPair{ipw[bitrev(j, logn)], shoup(ipw[bitrev(j, logn)], p)};
+        }
+        PrimeConst pc;
+        pc.p = p;
+        pc.inv64 = shoup(1, p);
+        pc.bits = bit_length(p);
+        pc.fin_shift = pc.bits - 25;
+        pc.fin_m = (unsigned) ((((u128) 1) << (pc.bits + 31)) / p);
+        pc.nc_ok = pc.bits <= 57;
+        const u64 ni = invmod(N, p), wn = mulmod(itw[1].w, ni, p);
+        const TwPair ninv{ni, shoup(ni, p)}, wninv{wn, shoup(wn, p)};
+        for (int pattern = 0; pattern < 3; ++pattern)
+        {
+            std::vector<u64> a(N), ref;
+            u64 s = 12345 + bits;
+            for (int i = 0; i < N; ++i)
+            {
+                s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+                a[i] = pattern == 0 ? (s >> 2) % p : pattern == 1 ? p - 1 : 0;
+            }
+            ref = a;
+            int t = N, m = 1;
+            while (m < N)
+            {
+                t >>= 1;
+                for (int i = 0; i < m; ++i)
+                    for (int j = 2 * i * t; j < 2 * i * t + t; ++j)
+                    {
+                        u64 U = ref[j], V = mulmod(ref[j + t], tw[m + i].w, p);
+                        ref[j] = addmod(U, V, p);
+                        ref[j + t] = submod(U, V, p);
+                    }
+                m <<= 1;
+            }
+            for (int var = 0; var < 3; ++var)
+            {
+                if (var == 2 && !pc.nc_ok)
+                    continue;
+                std::vector<u64> x = a;
+                // worst-case lazy input for the fused mod-up: words below 4p are legal inputs
+                if (var != 0 && pattern == 0)
+                    for (int i = 0; i < N; i += 3)
+                        x[i] += 3 * p;
+                var == 0 ? fwd<0>(x, tw, pc) : var == 1 ? fwd<1>(x, tw, pc) : fwd<2>(x, tw, pc);
+                int bad = 0;
+                for (int i = 0; i < N; ++i) bad += x[i] != ref[i];
+                if (bad)
+                {
+                    printf("FAIL fwd bits=%d var=%d pattern=%d mismatches=%d\n", bits, var, pattern, bad);
+                    ++failures;
+                }
+            }
+            for (int gvar = 0; gvar < 2; ++gvar)
+            {
+                std::vector<u64> x = ref;
+                gvar == 0 ? inv<0>(x, itw, pc, ninv, wninv) : inv<1>(x, itw, pc, ninv, wninv);
+                int bad = 0;
+                for (int i = 0; i < N; ++i) bad += x[i] != a[i];
+                if (bad)
+                {
+                    printf("FAIL inv bits=%d gvar=%d pattern=%d mismatches=%d\n", bits, gvar, pattern, bad);
+                    ++failures;
+                }
+            }
+        }
+    }
+    printf(failures ? "FAILED %d\n" : "OK\n", failures);
+    return failures != 0;
+}
