@@ -49,6 +49,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def traffic_per_launch_pair(limb_polys):
+    """DRAM bytes (read+write) of one forward-NTT launch pair, from the committed ncu --set full
+    capture (profiles/r1_traffic.json), scaled to the limb-polynomials one launch pair processes."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path))["fwd_ntt_dram_bytes_per_limb_poly"] * limb_polys
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -93,9 +102,7 @@ class ClockSampler:
 
 
 def dist_setup(n_gpus):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = env_rank_world()
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -105,19 +112,12 @@ def dist_setup(n_gpus):
     return rank, world, local
 
 
-def barrier(world):
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
+from heongpu_b200.sharding import barrier, env_rank_world  # noqa: E402
+from heongpu_b200 import sharding as _sh  # noqa: E402
 
 
 def max_over_ranks(x, world):
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-    return x
+    return _sh.max_over_ranks(x, world, device="cuda")
 
 
 def timed(fn, steps, world):
@@ -187,23 +187,57 @@ def run_ours(args, rank, world, local):
     clocks = sampler.stop() if rank == 0 else None
     value = B * args.steps * world / (ms * 1e-3)
 
-    # ---- e2e: pinned host buffers, H2D of both inputs + D2H of the result every step ----
+    # ---- e2e: pinned host buffers; every step copies both inputs H2D and the result D2H.
+    # The copies of neighbouring steps overlap the compute (three streams, two device
+    # buffer sets) -- all of it inside the timed region.
     ha, hb = inp["a"].cpu().pin_memory(), inp["b"].cpu().pin_memory()
-    hres = torch.empty(B, 2, L, n, dtype=torch.int64).pin_memory()
-    da, db = torch.empty_like(inp["a"]), torch.empty_like(inp["b"])
+    hres = [torch.empty(B, 2, L, n, dtype=torch.int64).pin_memory() for _ in range(2)]
+    da = [torch.empty_like(inp["a"]) for _ in range(2)]
+    db = [torch.empty_like(inp["b"]) for _ in range(2)]
+    outs = [out, torch.zeros_like(out)]
+    s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
 
-    def step_e2e():
-        da.copy_(ha, non_blocking=True)
-        db.copy_(hb, non_blocking=True)
-        Cc = api.Ciphertext(ctx, out)
-        op.multiply(api.Ciphertext(ctx, da), api.Ciphertext(ctx, db), Cc)
-        op.relinearize_inplace(Cc, rk)
-        hres.copy_(out[:, :2], non_blocking=True)
+    def run_e2e(steps):
+        ev_in = [None, None]
+        ev_cmp = [None, None]
+        ev_out = [None, None]
+        main = torch.cuda.current_stream()
+        for st in (s_in, s_cmp, s_out):
+            st.wait_stream(main)
+        for i in range(steps):
+            k = i & 1
+            with torch.cuda.stream(s_in):
+                if ev_cmp[k] is not None:
+                    s_in.wait_event(ev_cmp[k])  # inputs of step i-2 consumed
+                da[k].copy_(ha, non_blocking=True)
+                db[k].copy_(hb, non_blocking=True)
+                ev_in[k] = s_in.record_event()
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_in[k])
+                if ev_out[k] is not None:
+                    s_cmp.wait_event(ev_out[k])  # result buffer of step i-2 drained
+                Cc = api.Ciphertext(ctx, outs[k])
+                op.multiply(api.Ciphertext(ctx, da[k]), api.Ciphertext(ctx, db[k]), Cc)
+                op.relinearize_inplace(Cc, rk)
+                ev_cmp[k] = s_cmp.record_event()
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp[k])
+                hres[k].copy_(outs[k][:, :2], non_blocking=True)
+                ev_out[k] = s_out.record_event()
+        for st in (s_in, s_cmp, s_out):
+            main.wait_stream(st)
 
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    e2e_steps = max(2, args.steps // 2)
-    ms_e2e = timed(step_e2e, e2e_steps, world)
+    run_e2e(max(2, args.warmup))
+    e2e_steps = max(4, args.steps)
+    barrier(world)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_e2e(e2e_steps)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1), world)
     e2e_value = B * e2e_steps * world / (ms_e2e * 1e-3)
 
     # ---- per-kernel CUDA-event pass (separate, instrumented run of the same steps) ----
@@ -245,11 +279,11 @@ def run_ours(args, rank, world, local):
             achieved = polys["fwd"] * n * 16 / (fwd_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": "forward NTT (ntt_fwd_col_pass + ntt_fwd_row_pass)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "peak_source": peak_src, "traffic": None,
+                    "peak_source": peak_src, "traffic": traffic_per_launch_pair(polys["fwd"] * B),
                     "launches_per_step": fwd_launch,
                     "note": "algorithmic bytes = 16*N per limb-polynomial (SURVEY 8(d)); 64-bit modmul makes this kernel int-pipe bound"}
     res = dict(value=value, ms=ms, launches=launches, clocks=clocks, e2e=e2e_value,
-               h2d=int(ha.numel() * 8 * 2), d2h=int(hres.numel() * 8), kernels=kernels, roof=roof, inp=inp)
+               h2d=int(ha.numel() * 8 * 2), d2h=int(hres[0].numel() * 8), kernels=kernels, roof=roof, inp=inp)
     return res
 
 

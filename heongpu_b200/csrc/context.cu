@@ -162,6 +162,16 @@ void upload_tables(Context& c)
 {
     const int N = c.n, Qp = c.Qp;
     HEON_CUDA(cudaSetDevice(c.device));
+    {
+        // keep stream-ordered scratch cached in the pool across synchronisation points
+        // (the default release threshold of 0 hands it back to the OS at every sync)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess)
+        {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     c.d_mod = upload(c.mod);
     std::vector<PrimeConst> pcs(Qp);
     std::vector<TwPair> fwd((size_t) Qp * N), inv((size_t) Qp * N), last(2 * (size_t) Qp);

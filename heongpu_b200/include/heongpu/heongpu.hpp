@@ -1,0 +1,516 @@
+// heongpu.hpp -- source-level mirror of the HEonGPU class layer for the hot path,
+// implemented on top of the C ABI in include/heon_b200.h (libheon_b200.so).
+//
+// Mirrors, with the same names / argument meaning / exception types:
+//   heongpu::Scheme, sec_level_type, keyswitching_type, storage_type        src/include/heongpu/util/schemes.h:15-31
+//   heongpu::ExecutionOptions                                               src/include/heongpu/util/storagemanager.cuh:34-97
+//   heongpu::HEContext<S> / GenHEContext<S>(...)                            src/include/heongpu/host/ckks/context.cuh
+//   heongpu::Ciphertext<S>                                                  src/include/heongpu/host/ckks/ciphertext.cuh:77-209
+//   heongpu::Relinkey<S>, Galoiskey<S>                                      src/include/heongpu/host/ckks/evaluationkey.cuh
+//   heongpu::HEArithmeticOperator<S>::{add,sub,negate,multiply,multiply_inplace,
+//       relinearize_inplace,rescale_inplace,mod_drop_inplace,mod_drop,
+//       rotate_rows,rotate_rows_inplace,apply_galois,apply_galois_inplace}  src/include/heongpu/host/ckks/operator.cuh:95-1600
+//
+// Scope: the CKKS hot path.  Key generation, encoding and
+// encryption are client-side "next" rows: Relinkey / Galoiskey here are
+// containers in the reference layout that the caller fills (set_data), and
+// Ciphertext can be constructed from raw words.  Host-parsable (no CUDA
+// language extensions), like the reference's public headers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "../../../include/heon_b200.h"
+
+typedef std::uint64_t Data64;
+struct Modulus64 {
+    Data64 value, bit, mu;
+};
+
+namespace heongpu {
+
+enum class Scheme { BFV = 1, CKKS = 2, TFHE = 3 };
+enum class sec_level_type { none, sec128 = 128, sec192 = 192, sec256 = 256 };
+enum class keyswitching_type { NONE = 0, KEYSWITCHING_METHOD_I = 1, KEYSWITCHING_METHOD_II = 2 };
+enum class storage_type { HOST = 1, DEVICE = 2 };
+
+struct ExecutionOptions {
+    cudaStream_t stream_ = cudaStreamDefault;
+    storage_type storage_ = storage_type::DEVICE;
+    bool keep_initial_condition_ = true;
+    ExecutionOptions& set_stream(cudaStream_t s)
+    {
+        stream_ = s;
+        return *this;
+    }
+    ExecutionOptions& set_storage_type(storage_type s)
+    {
+        storage_ = s;
+        return *this;
+    }
+    ExecutionOptions& set_initial_location(bool k)
+    {
+        keep_initial_condition_ = k;
+        return *this;
+    }
+};
+
+namespace detail {
+inline void check(int status)
+{
+    if (status == HEON_OK)
+        return;
+    const std::string msg = heon_last_error();
+    if (status == HEON_ERR_INVALID)
+        throw std::invalid_argument(msg);
+    if (status == HEON_ERR_LOGIC)
+        throw std::logic_error(msg);
+    throw std::runtime_error(msg);
+}
+inline void cuda(cudaError_t e)
+{
+    if (e != cudaSuccess)
+        throw std::runtime_error(std::string("CUDA: ") + cudaGetErrorString(e));
+}
+} // namespace detail
+
+// Stream-ordered device buffer (the reference's DeviceVector is an
+// rmm::device_uvector over a process-wide pool; here cudaMallocAsync's pool).
+template <typename T> class DeviceVector {
+  public:
+    DeviceVector() = default;
+    explicit DeviceVector(size_t n, cudaStream_t st = cudaStreamDefault) { resize(n, st); }
+    DeviceVector(const std::vector<T>& h, cudaStream_t st = cudaStreamDefault)
+    {
+        resize(h.size(), st);
+        detail::cuda(cudaMemcpyAsync(ptr_, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+    DeviceVector(DeviceVector&& o) noexcept { swap(o); }
+    DeviceVector& operator=(DeviceVector&& o) noexcept
+    {
+        swap(o);
+        return *this;
+    }
+    DeviceVector(const DeviceVector&) = delete;
+    DeviceVector& operator=(const DeviceVector&) = delete;
+    ~DeviceVector()
+    {
+        if (ptr_)
+            cudaFreeAsync(ptr_, stream_);
+    }
+    void resize(size_t n, cudaStream_t st = cudaStreamDefault)
+    {
+        if (n == size_)
+            return;
+        T* p = nullptr;
+        if (n)
+            detail::cuda(cudaMallocAsync((void**) &p, n * sizeof(T), st));
+        if (ptr_ && p)
+            detail::cuda(cudaMemcpyAsync(p, ptr_, (n < size_ ? n : size_) * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        if (ptr_)
+            cudaFreeAsync(ptr_, st);
+        ptr_ = p;
+        size_ = n;
+        stream_ = st;
+    }
+    T* data() const { return ptr_; }
+    size_t size() const { return size_; }
+    void swap(DeviceVector& o)
+    {
+        std::swap(ptr_, o.ptr_);
+        std::swap(size_, o.size_);
+        std::swap(stream_, o.stream_);
+    }
+
+  private:
+    T* ptr_ = nullptr;
+    size_t size_ = 0;
+    cudaStream_t stream_ = cudaStreamDefault;
+};
+template <typename T> using HostVector = std::vector<T>;
+
+template <Scheme S> class HEContextImpl;
+template <Scheme S> using HEContext = std::shared_ptr<HEContextImpl<S>>;
+
+template <> class HEContextImpl<Scheme::CKKS> {
+  public:
+    explicit HEContextImpl(sec_level_type sec = sec_level_type::sec128, int device = 0) : sec_level_(sec), device_(device) {}
+    ~HEContextImpl()
+    {
+        if (h_)
+            heon_context_destroy(h_);
+    }
+    void set_poly_modulus_degree(size_t n)
+    {
+        if (coeff_modulus_specified_ || poly_modulus_degree_specified_)
+            throw std::logic_error("Poly modulus degree cannot be changed after the coeff_modulus is specified!");
+        if (n == 0 || (n & (n - 1)))
+            throw std::logic_error("Poly modulus degree have to be power of two");
+        if (n > 65536 || n < 4096)
+            throw std::logic_error("Poly modulus degree is not supported");
+        this->n = (int) n;
+        n_power = 0;
+        while ((size_t(1) << n_power) < n)
+            ++n_power;
+        poly_modulus_degree_specified_ = true;
+    }
+    void set_coeff_modulus_bit_sizes(const std::vector<int>& q_bits, const std::vector<int>& p_bits)
+    {
+        if (coeff_modulus_specified_ || context_generated_ || !poly_modulus_degree_specified_)
+            throw std::logic_error("Coeff_modulus cannot be changed after the context is generated!");
+        if (p_bits.empty())
+            throw std::logic_error("log_P_bases_bit_sizes cannot be empty!");
+        q_bits_ = q_bits;
+        p_bits_ = p_bits;
+        by_value_ = false;
+        coeff_modulus_specified_ = true;
+    }
+    void set_coeff_modulus_values(const std::vector<Data64>& q, const std::vector<Data64>& p)
+    {
+        if (coeff_modulus_specified_ || context_generated_ || !poly_modulus_degree_specified_)
+            throw std::logic_error("Coeff_modulus cannot be changed after the context is generated!");
+        if (p.empty())
+            throw std::logic_error("log_P_bases_bit_sizes cannot be empty!");
+        q_vals_ = q;
+        p_vals_ = p;
+        by_value_ = true;
+        coeff_modulus_specified_ = true;
+    }
+    void generate()
+    {
+        if (context_generated_ || !poly_modulus_degree_specified_ || !coeff_modulus_specified_)
+            throw std::runtime_error("Context is already generated!");
+        if (by_value_)
+            detail::check(heon_ckks_context_create_values(device_, n_power, q_vals_.data(), (int) q_vals_.size(),
+                                                          p_vals_.data(), (int) p_vals_.size(), &h_));
+        else
+            detail::check(heon_ckks_context_create(device_, n_power, q_bits_.data(), (int) q_bits_.size(),
+                                                   p_bits_.data(), (int) p_bits_.size(), &h_));
+        heon_info info;
+        detail::check(heon_context_info(h_, &info));
+        Q_size = info.q_size;
+        P_size = info.p_size;
+        Q_prime_size = Q_size + P_size;
+        keyswitching_type_ = info.keyswitch_method == 1 ? keyswitching_type::KEYSWITCHING_METHOD_I
+                                                        : keyswitching_type::KEYSWITCHING_METHOD_II;
+        size_t cnt = 0;
+        detail::check(heon_context_table(h_, HEON_TBL_MODULUS, 0, nullptr, 0, &cnt));
+        std::vector<Data64> raw(cnt);
+        detail::check(heon_context_table(h_, HEON_TBL_MODULUS, 0, raw.data(), cnt, &cnt));
+        prime_vector_.clear();
+        for (size_t i = 0; i < cnt; i += 3)
+            prime_vector_.push_back(Modulus64{raw[i], raw[i + 1], raw[i + 2]});
+        context_generated_ = true;
+    }
+    int digit_count(int depth) const
+    {
+        const int L = Q_size - depth;
+        return P_size == 1 ? L : (L + P_size - 1) / P_size;
+    }
+    heon_context_t handle() const { return h_; }
+    size_t get_poly_modulus_degree() const { return (size_t) n; }
+
+    int n = 0, n_power = 0;
+    int Q_size = 0, P_size = 0, Q_prime_size = 0;
+    keyswitching_type keyswitching_type_ = keyswitching_type::NONE;
+    std::vector<Modulus64> prime_vector_;
+    bool context_generated_ = false;
+
+  private:
+    sec_level_type sec_level_;
+    int device_;
+    heon_context_t h_ = nullptr;
+    std::vector<int> q_bits_, p_bits_;
+    std::vector<Data64> q_vals_, p_vals_;
+    bool by_value_ = false, poly_modulus_degree_specified_ = false, coeff_modulus_specified_ = false;
+};
+
+template <Scheme S> HEContext<S> GenHEContext(sec_level_type sec = sec_level_type::sec128, int device = 0)
+{
+    return std::make_shared<HEContextImpl<S>>(sec, device);
+}
+
+template <Scheme S> class Ciphertext;
+template <> class Ciphertext<Scheme::CKKS> {
+  public:
+    Ciphertext() = default;
+    // [cipher_size][L][N] words, NTT domain (ciphertext.cu:20-31)
+    Ciphertext(HEContext<Scheme::CKKS> ctx, const std::vector<Data64>& words, int cipher_size = 2, int depth = 0,
+               double scale = 1.0, const ExecutionOptions& opt = ExecutionOptions())
+        : context_(ctx), device_locations_(words, opt.stream_), cipher_size_(cipher_size), depth_(depth), scale_(scale)
+    {
+        ring_size_ = ctx->n;
+        coeff_modulus_count_ = ctx->Q_size;
+        if (words.size() < (size_t) cipher_size * (ctx->Q_size - depth) * ctx->n)
+            throw std::invalid_argument("Invalid Ciphertexts size!");
+        ciphertext_generated_ = true;
+    }
+    Data64* data() const { return device_locations_.data(); }
+    size_t memory_size() const { return device_locations_.size(); }
+    void memory_set(DeviceVector<Data64>&& v) { device_locations_ = std::move(v); }
+    void get_data(std::vector<Data64>& out, cudaStream_t st = cudaStreamDefault) const
+    {
+        out.resize((size_t) cipher_size_ * (coeff_modulus_count_ - depth_) * ring_size_);
+        detail::cuda(cudaMemcpyAsync(out.data(), data(), out.size() * sizeof(Data64), cudaMemcpyDeviceToHost, st));
+        detail::cuda(cudaStreamSynchronize(st));
+    }
+    int size() const { return cipher_size_; }
+    int depth() const { return depth_; }
+    double scale() const { return scale_; }
+    bool in_ntt_domain() const { return in_ntt_domain_; }
+    bool rescale_required() const { return rescale_required_; }
+    bool relinearization_required() const { return relinearization_required_; }
+
+    HEContext<Scheme::CKKS> context_;
+    DeviceVector<Data64> device_locations_;
+    int ring_size_ = 0, coeff_modulus_count_ = 0, cipher_size_ = 0, depth_ = 0;
+    double scale_ = 0;
+    bool in_ntt_domain_ = true, rescale_required_ = false, relinearization_required_ = false,
+         ciphertext_generated_ = false;
+};
+
+template <Scheme S> class Relinkey;
+template <> class Relinkey<Scheme::CKKS> {
+  public:
+    explicit Relinkey(HEContext<Scheme::CKKS> ctx) : context_(ctx), key_type(ctx->keyswitching_type_) {}
+    // [digit][2][Q'_0][N] NTT-domain words (keygeneration.cu:180-183)
+    void set_data(const std::vector<Data64>& words, cudaStream_t st = cudaStreamDefault)
+    {
+        const size_t need = (size_t) context_->digit_count(0) * 2 * context_->Q_prime_size * context_->n;
+        if (words.size() != need)
+            throw std::invalid_argument("Invalid relinearization key size!");
+        device_location_ = DeviceVector<Data64>(words, st);
+        relin_key_generated_ = true;
+    }
+    Data64* data() const { return device_location_.data(); }
+    HEContext<Scheme::CKKS> context_;
+    keyswitching_type key_type;
+    storage_type storage_type_ = storage_type::DEVICE;
+    DeviceVector<Data64> device_location_;
+    bool relin_key_generated_ = false;
+};
+
+template <Scheme S> class Galoiskey;
+template <> class Galoiskey<Scheme::CKKS> {
+  public:
+    explicit Galoiskey(HEContext<Scheme::CKKS> ctx) : context_(ctx), key_type(ctx->keyswitching_type_)
+    {
+        for (int i = 0; i < 8; ++i) // default keys for +-2^i, i < MAX_SHIFT (evaluationkey.cu:306-345)
+        {
+            galois_elt[1 << i] = heon_steps_to_galois_elt(1 << i, ctx->n, group_order_);
+            galois_elt[-(1 << i)] = heon_steps_to_galois_elt(-(1 << i), ctx->n, group_order_);
+        }
+    }
+    Galoiskey(HEContext<Scheme::CKKS> ctx, const std::vector<int>& shifts) : context_(ctx), key_type(ctx->keyswitching_type_)
+    {
+        customized = true;
+        for (int s : shifts)
+            galois_elt[s] = heon_steps_to_galois_elt(s, ctx->n, group_order_);
+    }
+    void set_key(int galois_element, const std::vector<Data64>& words, cudaStream_t st = cudaStreamDefault)
+    {
+        const size_t need = (size_t) context_->digit_count(0) * 2 * context_->Q_prime_size * context_->n;
+        if (words.size() != need)
+            throw std::invalid_argument("Invalid galois key size!");
+        device_location_[galois_element] = DeviceVector<Data64>(words, st);
+    }
+    HEContext<Scheme::CKKS> context_;
+    keyswitching_type key_type;
+    storage_type storage_type_ = storage_type::DEVICE;
+    int group_order_ = 5;
+    bool customized = false;
+    std::unordered_map<int, int> galois_elt; // shift -> galois element
+    std::unordered_map<int, DeviceVector<Data64>> device_location_; // galois element -> key
+};
+
+template <Scheme S> class HEEncoder; // client-side ("next" row); only named in the operator constructor
+template <Scheme S> class HEOperator;
+
+template <> class HEOperator<Scheme::CKKS> {
+  protected:
+    explicit HEOperator(HEContext<Scheme::CKKS> context)
+    {
+        if (!context || !context->context_generated_)
+            throw std::invalid_argument("HEContext is not generated!");
+        context_ = std::move(context);
+    }
+    HEContext<Scheme::CKKS> context_;
+    heon_context_t h() const { return context_->handle(); }
+    size_t words(int comps, int depth) const { return (size_t) comps * (context_->Q_size - depth) * context_->n; }
+    static void copy_meta(const Ciphertext<Scheme::CKKS>& a, Ciphertext<Scheme::CKKS>& o)
+    {
+        o.context_ = a.context_;
+        o.ring_size_ = a.ring_size_;
+        o.coeff_modulus_count_ = a.coeff_modulus_count_;
+        o.cipher_size_ = a.cipher_size_;
+        o.depth_ = a.depth_;
+        o.scale_ = a.scale_;
+        o.in_ntt_domain_ = a.in_ntt_domain_;
+        o.rescale_required_ = a.rescale_required_;
+        o.relinearization_required_ = a.relinearization_required_;
+        o.ciphertext_generated_ = true;
+    }
+
+  public:
+    void add(Ciphertext<Scheme::CKKS>& a, Ciphertext<Scheme::CKKS>& b, Ciphertext<Scheme::CKKS>& out,
+             const ExecutionOptions& opt = ExecutionOptions())
+    {
+        binary(a, b, out, opt, 0);
+    }
+    void sub(Ciphertext<Scheme::CKKS>& a, Ciphertext<Scheme::CKKS>& b, Ciphertext<Scheme::CKKS>& out,
+             const ExecutionOptions& opt = ExecutionOptions())
+    {
+        binary(a, b, out, opt, 1);
+    }
+    void negate(Ciphertext<Scheme::CKKS>& a, Ciphertext<Scheme::CKKS>& out, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        DeviceVector<Data64> mem(words(a.cipher_size_, a.depth_), opt.stream_);
+        detail::check(heon_negate(h(), a.data(), 0, mem.data(), 0, a.cipher_size_, a.depth_, 1, opt.stream_));
+        copy_meta(a, out);
+        out.memory_set(std::move(mem));
+    }
+
+    // operator.cuh:631-691 + multiply_ckks (operator.cu:796-837)
+    void multiply(Ciphertext<Scheme::CKKS>& a, Ciphertext<Scheme::CKKS>& b, Ciphertext<Scheme::CKKS>& out,
+                  const ExecutionOptions& opt = ExecutionOptions())
+    {
+        if (a.relinearization_required_ || b.relinearization_required_)
+            throw std::invalid_argument("Ciphertexts can not be multiplied because of the non-linear part! Please use relinearization operation!");
+        if (a.rescale_required_ || b.rescale_required_)
+            throw std::invalid_argument("Ciphertexts can not be multiplied because of the noise! Please use rescale operation to get rid of additional noise!");
+        if (a.depth_ != b.depth_)
+            throw std::logic_error("Ciphertexts leveled are not equal");
+        if (a.memory_size() < words(2, a.depth_) || b.memory_size() < words(2, a.depth_))
+            throw std::invalid_argument("Invalid Ciphertexts size!");
+        DeviceVector<Data64> mem(words(3, a.depth_), opt.stream_);
+        detail::check(heon_ckks_multiply(h(), a.data(), 0, b.data(), 0, mem.data(), 0, a.depth_, 1, opt.stream_));
+        const double scale = a.scale_ * b.scale_;
+        copy_meta(a, out);
+        out.memory_set(std::move(mem));
+        out.scale_ = scale;
+        out.cipher_size_ = 3;
+        out.relinearization_required_ = true;
+        out.rescale_required_ = true;
+    }
+    void multiply_inplace(Ciphertext<Scheme::CKKS>& a, Ciphertext<Scheme::CKKS>& b,
+                          const ExecutionOptions& opt = ExecutionOptions())
+    {
+        multiply(a, b, a, opt);
+    }
+
+    // operator.cuh:1053-1094
+    void relinearize_inplace(Ciphertext<Scheme::CKKS>& ct, Relinkey<Scheme::CKKS>& rk,
+                             const ExecutionOptions& opt = ExecutionOptions())
+    {
+        if (!ct.relinearization_required_)
+            throw std::invalid_argument("Ciphertexts can not use relinearization, since no non-linear part!");
+        if (!rk.relin_key_generated_)
+            throw std::invalid_argument("Relinkey is not generated!");
+        if (ct.memory_size() < words(3, ct.depth_))
+            throw std::invalid_argument("Invalid Ciphertexts size!");
+        detail::check(heon_ckks_relinearize(h(), ct.data(), 0, rk.data(), ct.depth_, 1, opt.stream_));
+        ct.relinearization_required_ = false;
+        ct.cipher_size_ = 2;
+    }
+
+    // operator.cuh:1423-1445
+    void rescale_inplace(Ciphertext<Scheme::CKKS>& ct, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        if (ct.depth_ >= context_->Q_size - 1)
+            throw std::invalid_argument("Ciphertexts can not be rescaled, level is too low!");
+        detail::check(heon_ckks_rescale(h(), ct.data(), 0, ct.depth_, 1, opt.stream_));
+        ct.scale_ /= (double) context_->prime_vector_[context_->Q_size - ct.depth_ - 1].value;
+        ct.depth_++;
+        ct.rescale_required_ = false;
+    }
+
+    // operator.cuh:1457-1600
+    void mod_drop_inplace(Ciphertext<Scheme::CKKS>& ct, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        detail::check(heon_ckks_mod_drop_inplace(h(), ct.data(), 0, ct.cipher_size_, ct.depth_, 1, opt.stream_));
+        ct.depth_++;
+    }
+    void mod_drop(Ciphertext<Scheme::CKKS>& in, Ciphertext<Scheme::CKKS>& out, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        DeviceVector<Data64> mem(words(2, in.depth_ + 1), opt.stream_);
+        detail::check(heon_ckks_mod_drop(h(), in.data(), 0, mem.data(), 0, in.depth_, 1, opt.stream_));
+        copy_meta(in, out);
+        out.memory_set(std::move(mem));
+        out.depth_ = in.depth_ + 1;
+    }
+
+    // operator.cuh:1105-1270
+    void apply_galois(Ciphertext<Scheme::CKKS>& in, Ciphertext<Scheme::CKKS>& out, Galoiskey<Scheme::CKKS>& gk,
+                      int galois_elt, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        if (in.rescale_required_ || in.relinearization_required_)
+            throw std::invalid_argument("Ciphertext can not be rotated because of the non-linear part or noise!");
+        auto it = gk.device_location_.find(galois_elt);
+        if (it == gk.device_location_.end())
+            throw std::logic_error("Galois key not present!");
+        DeviceVector<Data64> mem(words(2, in.depth_), opt.stream_);
+        detail::check(heon_ckks_apply_galois(h(), in.data(), 0, mem.data(), 0, it->second.data(),
+                                             (uint32_t) galois_elt, in.depth_, 1, opt.stream_));
+        copy_meta(in, out);
+        out.memory_set(std::move(mem));
+        out.cipher_size_ = 2;
+    }
+    void apply_galois_inplace(Ciphertext<Scheme::CKKS>& ct, Galoiskey<Scheme::CKKS>& gk, int galois_elt,
+                              const ExecutionOptions& opt = ExecutionOptions())
+    {
+        apply_galois(ct, ct, gk, galois_elt, opt);
+    }
+    void rotate_rows(Ciphertext<Scheme::CKKS>& in, Ciphertext<Scheme::CKKS>& out, Galoiskey<Scheme::CKKS>& gk, int shift,
+                     const ExecutionOptions& opt = ExecutionOptions())
+    {
+        if (shift == 0)
+        {
+            if (&in != &out)
+            {
+                DeviceVector<Data64> mem(words(2, in.depth_), opt.stream_);
+                detail::cuda(cudaMemcpyAsync(mem.data(), in.data(), mem.size() * sizeof(Data64), cudaMemcpyDeviceToDevice, opt.stream_));
+                copy_meta(in, out);
+                out.memory_set(std::move(mem));
+            }
+            return;
+        }
+        const int elt = heon_steps_to_galois_elt(shift, context_->n, gk.group_order_);
+        if (elt == 0)
+            throw std::invalid_argument("Galois Key can not be generated, Step count too large");
+        apply_galois(in, out, gk, elt, opt);
+    }
+    void rotate_rows_inplace(Ciphertext<Scheme::CKKS>& ct, Galoiskey<Scheme::CKKS>& gk, int shift,
+                             const ExecutionOptions& opt = ExecutionOptions())
+    {
+        rotate_rows(ct, ct, gk, shift, opt);
+    }
+
+  private:
+    void binary(Ciphertext<Scheme::CKKS>& a, Ciphertext<Scheme::CKKS>& b, Ciphertext<Scheme::CKKS>& out,
+                const ExecutionOptions& opt, int op)
+    {
+        if (a.depth_ != b.depth_)
+            throw std::logic_error("Ciphertexts leveled are not equal");
+        if (a.cipher_size_ != b.cipher_size_)
+            throw std::invalid_argument("Ciphertexts should have the same size!");
+        DeviceVector<Data64> mem(words(a.cipher_size_, a.depth_), opt.stream_);
+        detail::check((op == 0 ? heon_add : heon_sub)(h(), a.data(), 0, b.data(), 0, mem.data(), 0, a.cipher_size_,
+                                                      a.depth_, 1, opt.stream_));
+        copy_meta(a, out);
+        out.memory_set(std::move(mem));
+    }
+};
+
+template <Scheme S> class HEArithmeticOperator;
+template <> class HEArithmeticOperator<Scheme::CKKS> : public HEOperator<Scheme::CKKS> {
+  public:
+    explicit HEArithmeticOperator(HEContext<Scheme::CKKS> context) : HEOperator<Scheme::CKKS>(context) {}
+    // reference signature (ckks/operator.cu:6680); the encoder is not used by the hot path
+    HEArithmeticOperator(HEContext<Scheme::CKKS> context, HEEncoder<Scheme::CKKS>&) : HEOperator<Scheme::CKKS>(context) {}
+};
+
+} // namespace heongpu

@@ -1,0 +1,33 @@
+"""The heongpu:: C++ class layer compiles with a plain host compiler (like the
+reference's public headers) and, on a GPU, reproduces the C ABI word for word
+with the reference's exception behaviour."""
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build():
+    exe = os.path.join(tempfile.mkdtemp(), "class_layer_test")
+    lib = os.path.join(ROOT, "heongpu_b200", "lib")
+    subprocess.check_call([
+        "g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "heongpu_b200", "include"), "-I/usr/local/cuda/include",
+        os.path.join(ROOT, "tests", "cpp", "class_layer_test.cpp"), "-o", exe,
+        "-L", lib, "-lheon_b200", "-L/usr/local/cuda/lib64", "-lcudart", f"-Wl,-rpath,{lib}", "-Wl,-rpath,/usr/local/cuda/lib64"])
+    return exe
+
+
+def test_class_layer_compiles_and_links():
+    exe = _build()
+    out = subprocess.run([exe, "--no-gpu"], capture_output=True, text=True)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_class_layer_matches_c_abi_on_gpu():
+    exe = _build()
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
