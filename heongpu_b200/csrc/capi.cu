@@ -128,6 +128,10 @@ static void finish_context(Context& c, int device, int log_n, int n_q, int n_p)
         throw std::logic_error("P size above 15 is not supported");
     if (const char* v = getenv("HEON_NTT_VARIANT"))
         c.ntt_variant = atoi(v);
+    if (const char* v = getenv("HEON_NTT_PERSISTENT"))
+        c.ntt_persistent = atoi(v);
+    if (const char* v = getenv("HEON_NTT_FP64"))
+        c.use_fp64 = atoi(v);
     if (const char* v = getenv("HEON_NTT_TMA"))
         c.use_tma = atoi(v);
     build_host_tables(c);

@@ -162,6 +162,7 @@ void upload_tables(Context& c)
 {
     const int N = c.n, Qp = c.Qp;
     HEON_CUDA(cudaSetDevice(c.device));
+    HEON_CUDA(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, c.device));
     {
         // keep stream-ordered scratch cached in the pool across synchronisation points
         // (the default release threshold of 0 hands it back to the OS at every sync)
@@ -186,11 +187,23 @@ void upload_tables(Context& c)
         pcs[i].fin_shift = pcs[i].bits - 25;
         pcs[i].fin_m = (unsigned) ((((u128) 1) << (pcs[i].bits + 31)) / p);
         pcs[i].nc_ok = pcs[i].bits <= 57 ? 1u : 0u;
+        // measured on B200 (tools/microbench2.cu, SMSP cycles per warp-butterfly): integer VAR 2 30.9,
+        // FP64-quotient VAR 3 24.1, VAR 4 31.5 -> the FP64 pipe only pays off where no per-stage
+        // correction is needed (p <= 46 bits); HEON_NTT_FP64=2 also enables VAR 4 for 47..50 bits
+        pcs[i].fp_var = !c.use_fp64 ? 0u : pcs[i].bits <= 46 ? 3u : (c.use_fp64 >= 2 && pcs[i].bits <= 50) ? 4u : 0u;
+        pcs[i].pad_ = 0;
         for (int j = 0; j < N; ++j)
         {
             const size_t o = (size_t) i * N + j;
             fwd[o].w = c.ntt_table[o];
-            fwd[o].ws = shoup(c.ntt_table[o], p);
+            if (pcs[i].fp_var)
+            {
+                // RN(w/p): both operands are exact doubles (< 2^50), IEEE division rounds once
+                const double winv = (double) c.ntt_table[o] / (double) p;
+                std::memcpy(&fwd[o].ws, &winv, 8);
+            }
+            else
+                fwd[o].ws = shoup(c.ntt_table[o], p);
             inv[o].w = c.intt_table[o];
             inv[o].ws = shoup(c.intt_table[o], p);
         }

@@ -30,6 +30,8 @@ struct PrimeConst {
     unsigned fin_shift; // bits - 25
     unsigned bits; // bit length of p
     unsigned nc_ok; // 1 if p <= 57 bits: butterflies may skip every per-stage correction
+    unsigned fp_var; // 0: integer quotient; 3 / 4: forward twiddles carry RN(w/p), use VAR 3 / 4
+    unsigned pad_;
 };
 
 // Method-II (hybrid, K > 1) level tables; one entry per depth.
@@ -81,6 +83,9 @@ struct Context {
     TwPair* d_fwd_rowb = nullptr;
     TwPair* d_inv_rowb = nullptr;
     int use_tma = 1; // row pass through TMA tensor maps (HEON_NTT_TMA=0 disables)
+    int num_sms = 148;
+    int ntt_persistent = 0; // HEON_NTT_PERSISTENT=1: row-pass CTAs walk several tiles (double-buffered TMA)
+    int use_fp64 = 1; // FP64-pipe quotient for primes < 2^50 (HEON_NTT_FP64=0 disables)
     u64* d_last_q_modinv = nullptr;
     TwPair* d_lqm_pair = nullptr; // last_q_modinv with Shoup words
     u64* d_half = nullptr;

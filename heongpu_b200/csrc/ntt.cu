@@ -19,6 +19,7 @@
 #include "ntt_core.cuh"
 #include "ops.hpp"
 #include "tma.cuh"
+#include <algorithm>
 
 #ifndef HEON_NTT_MINBLOCKS
 #define HEON_NTT_MINBLOCKS 3
@@ -271,7 +272,11 @@ __global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS) ntt_col_pass(Map map,
         in = out;
     const PrimeConst pc = pcs[prime];
     const TwPair* tw = tw_all + ((long long) prime << logn);
-    if (INV || variant == 1 || !pc.nc_ok)
+    if (!INV && pc.fp_var == 3)
+        col_pass_body<S, INV, INV ? 1 : 3>(map, in, out, prime, pc, tw, inv_last, tile, first_pass, aux, sm);
+    else if (!INV && pc.fp_var == 4)
+        col_pass_body<S, INV, INV ? 1 : 4>(map, in, out, prime, pc, tw, inv_last, tile, first_pass, aux, sm);
+    else if (INV || variant == 1 || !pc.nc_ok)
         col_pass_body<S, INV, 1>(map, in, out, prime, pc, tw, inv_last, tile, first_pass, aux, sm);
     else
         col_pass_body<S, INV, 2>(map, in, out, prime, pc, tw, inv_last, tile, first_pass, aux, sm);
@@ -367,7 +372,11 @@ __global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS) ntt_row_pass(Map map,
     const u64* rin = in + (long long) r * 256;
     u64* rout = out + (long long) r * 256;
     u64* srow = sm + rl * PITCH;
-    if (INV || variant == 1 || !pc.nc_ok)
+    if (!INV && pc.fp_var == 3)
+        row_pass_body<INV, INV ? 1 : 3>(rin, rout, pc, tw, S1, r, tt, srow);
+    else if (!INV && pc.fp_var == 4)
+        row_pass_body<INV, INV ? 1 : 4>(rin, rout, pc, tw, S1, r, tt, srow);
+    else if (INV || variant == 1 || !pc.nc_ok)
         row_pass_body<INV, 1>(rin, rout, pc, tw, S1, r, tt, srow);
     else
         row_pass_body<INV, 2>(rin, rout, pc, tw, S1, r, tt, srow);
@@ -456,69 +465,106 @@ __device__ __forceinline__ void row_pass_tma_body(unsigned char* rowp, const Pri
     }
 }
 
+// Persistent form: the grid is a few CTAs per SM; each CTA walks tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ... with two shared-memory buffers, so the
+// TMA load of tile i+1 and the TMA store of tile i-1 overlap the arithmetic of
+// tile i (the pass is otherwise a load -> compute -> store chain whose memory
+// time and multiplier-pipe time add up instead of overlapping).
 template <bool INV, class Map>
 __global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS)
     ntt_row_pass_tma(Map map, const __grid_constant__ CUtensorMap tm_in,
                      const __grid_constant__ CUtensorMap tm_out, const u64* in_base, const u64* out_base,
                      const TwPair* __restrict__ tw_all, const TwPair* __restrict__ rowb_all,
-                     const PrimeConst* __restrict__ pcs, int logn, bool first_pass, int variant)
+                     const PrimeConst* __restrict__ pcs, int logn, bool first_pass, int variant,
+                     long long n_tiles)
 {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t bar[2];
     // 1024-byte alignment for the 128B swizzle; plain offset arithmetic keeps the
     // pointer in the shared address space (LDS/STS instead of generic LD/ST)
-    unsigned char* tile = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* buf0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int S1 = logn - 8;
     const int tiles = (1 << S1) / 16;
-    long long z = blockIdx.x / tiles;
-    int tile_idx = blockIdx.x % tiles;
-    const u64* in;
-    u64* out;
-    int prime, aux;
-    map.get(z, in, out, prime, aux);
-    if (!first_pass)
-    {
-        in = out;
-        in_base = out_base;
-    }
-    // tile position in 128-byte lines relative to the tensor-map bases
-    const int line_in = (int) ((in - in_base) >> 4) + tile_idx * 256;
-    const int line_out = (int) ((out - out_base) >> 4) + tile_idx * 256;
     const CUtensorMap* tmi = first_pass ? &tm_in : &tm_out;
+    if (!first_pass)
+        in_base = out_base;
+    const int tt = threadIdx.x & 15;
+    const int rl = threadIdx.x >> 4;
+
+    auto tile_lines = [&](long long t, int& line_in, int& line_out, int& prime, int& tile_idx) {
+        const long long z = t / tiles;
+        tile_idx = (int) (t % tiles);
+        const u64* in;
+        u64* out;
+        int aux;
+        map.get(z, in, out, prime, aux);
+        if (!first_pass)
+            in = out;
+        line_in = (int) ((in - in_base) >> 4) + tile_idx * 256;
+        line_out = (int) ((out - out_base) >> 4) + tile_idx * 256;
+    };
 
     if (threadIdx.x == 0)
     {
-        mbar_init(&bar, 1);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         fence_mbar_init();
     }
     __syncthreads();
-    if (threadIdx.x == 0)
+    long long t = blockIdx.x;
+    if (threadIdx.x == 0 && t < n_tiles)
     {
-        mbar_arrive_expect_tx(&bar, kRowTileBytes);
-        tma_load_2d(tile, tmi, &bar, 0, line_in);
+        int li, lo, pr, ti;
+        tile_lines(t, li, lo, pr, ti);
+        mbar_arrive_expect_tx(&bar[0], kRowTileBytes);
+        tma_load_2d(buf0, tmi, &bar[0], 0, li);
     }
-    const PrimeConst pc = pcs[prime];
-    const TwPair* tw = tw_all + ((long long) prime << logn);
-    const int tt = threadIdx.x & 15;
-    const int rl = threadIdx.x >> 4;
-    const int r = tile_idx * 16 + rl;
-    const TwPair* blk = rowb_all + ((((long long) prime << S1) + r) << 8);
-    unsigned char* rowp = tile + rl * 2048;
-    mbar_wait(&bar, 0);
-
-    if (INV || variant == 1 || !pc.nc_ok)
-        row_pass_tma_body<INV, 1>(rowp, pc, tw, blk, S1, r, tt);
-    else
-        row_pass_tma_body<INV, 2>(rowp, pc, tw, blk, S1, r, tt);
-
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (threadIdx.x == 0)
+    for (int it = 0; t < n_tiles; ++it, t += gridDim.x)
     {
-        tma_store_2d(&tm_out, tile, 0, line_out);
-        tma_store_commit();
+        const int b = it & 1;
+        unsigned char* tile = buf0 + b * kRowTileBytes;
+        if (threadIdx.x == 0)
+        {
+            // the other buffer was handed to a TMA store one iteration ago: wait until that
+            // store has finished reading it, then prefetch the next tile into it
+            tma_store_wait_read<0>();
+            const long long tn = t + gridDim.x;
+            if (tn < n_tiles)
+            {
+                int li, lo, pr, ti;
+                tile_lines(tn, li, lo, pr, ti);
+                mbar_arrive_expect_tx(&bar[b ^ 1], kRowTileBytes);
+                tma_load_2d(buf0 + (b ^ 1) * kRowTileBytes, tmi, &bar[b ^ 1], 0, li);
+            }
+        }
+        int line_in, line_out, prime, tile_idx;
+        tile_lines(t, line_in, line_out, prime, tile_idx);
+        const PrimeConst pc = pcs[prime];
+        const TwPair* tw = tw_all + ((long long) prime << logn);
+        const int r = tile_idx * 16 + rl;
+        const TwPair* blk = rowb_all + ((((long long) prime << S1) + r) << 8);
+        unsigned char* rowp = tile + rl * 2048;
+        mbar_wait(&bar[b], (it >> 1) & 1);
+
+        if (!INV && pc.fp_var == 3)
+            row_pass_tma_body<INV, INV ? 1 : 3>(rowp, pc, tw, blk, S1, r, tt);
+        else if (!INV && pc.fp_var == 4)
+            row_pass_tma_body<INV, INV ? 1 : 4>(rowp, pc, tw, blk, S1, r, tt);
+        else if (INV || variant == 1 || !pc.nc_ok)
+            row_pass_tma_body<INV, 1>(rowp, pc, tw, blk, S1, r, tt);
+        else
+            row_pass_tma_body<INV, 2>(rowp, pc, tw, blk, S1, r, tt);
+
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            tma_store_2d(&tm_out, tile, 0, line_out);
+            tma_store_commit();
+        }
+    }
+    if (threadIdx.x == 0)
         tma_store_wait_read<0>();
-    }
 }
 
 // ---------------------------------------------------------------------------
@@ -606,17 +652,22 @@ static void launch_row_tma(const Context& c, const Map& m, long long n_polys, bo
                            cudaStream_t st)
 {
     const int S = c.logn - 8;
-    const unsigned grid = (unsigned) (n_polys * ((1 << S) / 16));
+    const long long n_tiles = n_polys * ((1 << S) / 16);
+    // persistent (a few CTAs per SM walking tiles) or one tile per CTA
+    const unsigned grid = c.ntt_persistent
+                              ? (unsigned) std::min<long long>(n_tiles, (long long) c.num_sms * HEON_NTT_MINBLOCKS)
+                              : (unsigned) n_tiles;
     const CUtensorMap tm_out = make_line_map(e.out_base, e.out_words);
     const CUtensorMap tm_in = first ? make_line_map(e.in_base, e.in_words) : tm_out;
     static bool attr_set[2] = {false, false};
     auto kfn = ntt_row_pass_tma<INV, Map>;
-    const int smem = kRowTileBytes + 1024;
+    const int smem = 2 * kRowTileBytes + 1024;
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     (void) attr_set;
     LaunchScope scope(INV ? KC_NTT_INV_ROW : KC_NTT_FWD_ROW, st);
     kfn<<<grid, 256, smem, st>>>(m, tm_in, tm_out, e.in_base, e.out_base, INV ? c.d_inv : c.d_fwd,
-                                 INV ? c.d_inv_rowb : c.d_fwd_rowb, c.d_pc, c.logn, first, c.ntt_variant);
+                                 INV ? c.d_inv_rowb : c.d_fwd_rowb, c.d_pc, c.logn, first, c.ntt_variant,
+                                 n_tiles);
 }
 
 template <class Map>

@@ -18,6 +18,10 @@
 //   VAR 2  no per-stage correction at all: every stage adds at most 4p to the
 //          bound, 4p + 16*4p = 68p < 2^64 needs p <= 57 bits; the single
 //          final reduction uses a 32-bit quotient estimate (PrimeConst::fin_m).
+//   VAR 3  quotient from the FP64 pipe (fshoup, T in [0,2p)), no per-stage
+//          correction; values stay below 36p < 2^52: p <= 46 bits.
+//   VAR 4  quotient from the FP64 pipe, Harvey form [0,4p) < 2^52: p <= 50 bits.
+// For VAR 3/4 the second word of a twiddle pair holds the bits of RN(w/p).
 // Stored words are always canonical, so all variants give identical results.
 #pragma once
 #include "modarith.cuh"
@@ -130,6 +134,47 @@ __device__ __forceinline__ void addsub_ptx(u64& X, u64& Y, u64 T, u64 C)
 #endif
 }
 
+// Shoup product with the quotient taken from the FP64 pipe (primes below 2^50).
+// The multiplier pipe is the bottleneck of the integer butterfly; B200's FP64
+// pipe (64 lanes/clk/SM, idle otherwise) can produce the quotient instead:
+//   yd = (double) Y                    exact for Y < 2^52 (magic-number conversion)
+//   t  = fma(yd, winv, 2^52)           winv = RN(w/p); ONE rounding, to an integer
+//   qh = bits(t) - bits(2^52)          = rint(Y*winv),  |qh - Y*w/p| < 1/2 + Y*2^-53 < 1
+// hence qh is floor(Y*w/p) or that plus one, and
+//   T  = Y*w - (qh-1)*p  in [0,2p)     (two mad.wide.u32 + four mad.lo.u32, mod 2^64)
+// for ANY Y < 2^52.  Everything is exact integer arithmetic once qh is known,
+// so the canonical results are the same as on the integer path.
+__device__ __forceinline__ u64 fshoup(u64 y, u64 w, u64 winv_bits, u64 np)
+{
+    const double yd = __hiloint2double((int) (0x43300000u | (unsigned) (y >> 32)), (int) (unsigned) y) - 4503599627370496.0;
+    const double t = __fma_rn(yd, __longlong_as_double((long long) winv_bits), 4503599627370496.0);
+    const u64 q = (u64) __double_as_longlong(t) - 0x4330000000000001ull; // rint(Y*winv) - 1
+#ifndef __CUDA_ARCH__
+    return y * w + q * np;
+#else
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 y0,y1,w0,w1,n0,n1,q0,q1,t0,t1;\n\t"
+        ".reg .u64 tt;\n\t"
+        "mov.b64 {y0,y1}, %1;\n\t"
+        "mov.b64 {w0,w1}, %2;\n\t"
+        "mov.b64 {q0,q1}, %3;\n\t"
+        "mov.b64 {n0,n1}, %4;\n\t"
+        "mul.wide.u32 tt, y0, w0;\n\t"
+        "mad.wide.u32 tt, q0, n0, tt;\n\t"
+        "mov.b64 {t0,t1}, tt;\n\t"
+        "mad.lo.u32 t1, y0, w1, t1;\n\t"
+        "mad.lo.u32 t1, y1, w0, t1;\n\t"
+        "mad.lo.u32 t1, q0, n1, t1;\n\t"
+        "mad.lo.u32 t1, q1, n0, t1;\n\t"
+        "mov.b64 %0, {t0,t1};\n\t"
+        "}"
+        : "=l"(r)
+        : "l"(y), "l"(w), "l"(q), "l"(np));
+    return r;
+#endif
+}
+
 template <int VAR> __device__ __forceinline__ void ct_bfly(u64& X, u64& Y, const TwPair& w, const BflyConst& c)
 {
     if (VAR == 0)
@@ -145,17 +190,30 @@ template <int VAR> __device__ __forceinline__ void ct_bfly(u64& X, u64& Y, const
         const u64 t = shoup_lazy_ptx(Y, w.w, w.ws, c.np);
         addsub_ptx(X, Y, t, c.p4);
     }
-    else
+    else if (VAR == 2)
     {
         const u64 t = shoup_lazy_ptx(Y, w.w, w.ws, c.np);
         addsub_ptx(X, Y, t, c.p4);
+    }
+    else if (VAR == 3)
+    {
+        // FP64 quotient, no per-stage correction: +2p per stage, 4p + 16*2p = 36p < 2^52 for p <= 46 bits
+        const u64 t = fshoup(Y, w.w, w.ws, c.np);
+        addsub_ptx(X, Y, t, c.p2);
+    }
+    else
+    {
+        // FP64 quotient, Harvey form: values in [0,4p) < 2^52 for p < 2^50
+        X = csub(X, c.p2);
+        const u64 t = fshoup(Y, w.w, w.ws, c.np);
+        addsub_ptx(X, Y, t, c.p2);
     }
 }
 
 // canonical value of a lazy forward word
 template <int VAR> __device__ __forceinline__ u64 ct_finish(u64 x, const BflyConst& c, const PrimeConst& pc)
 {
-    if (VAR == 0)
+    if (VAR == 0 || VAR == 4)
         return csub(csub(x, c.p2), c.p);
     if (VAR == 1)
         return csub(csub(csub(x, c.p4), c.p2), c.p);
@@ -198,6 +256,12 @@ __device__ __forceinline__ void stage16(u64 (&v)[16], const TwPair* __restrict__
         for (int j = 0; j < (1 << LS); ++j)
         {
             const int k = g * (2 << LS) + j;
+#ifdef HEON_NTT_NULL
+            // diagnostic build: keep every load/store/transposition, drop the arithmetic
+            v[k] ^= w.w;
+            v[k + (1 << LS)] ^= w.ws;
+            continue;
+#endif
             if (INV)
                 gs_bfly<VAR>(v[k], v[k + (1 << LS)], w, c);
             else

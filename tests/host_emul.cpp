@@ -11,6 +11,28 @@ static inline unsigned long long __umul64hi(unsigned long long a, unsigned long 
     return (unsigned long long) (((unsigned __int128) a * b) >> 64);
 }
 static inline ulonglong2 __ldg(const ulonglong2* p) { return *p; }
+#include <cmath>
+#include <cstring>
+static inline double __hiloint2double(int hi, int lo)
+{
+    unsigned long long b = ((unsigned long long) (unsigned) hi << 32) | (unsigned) lo;
+    double d;
+    std::memcpy(&d, &b, 8);
+    return d;
+}
+static inline double __longlong_as_double(long long v)
+{
+    double d;
+    std::memcpy(&d, &v, 8);
+    return d;
+}
+static inline long long __double_as_longlong(double d)
+{
+    long long v;
+    std::memcpy(&v, &d, 8);
+    return v;
+}
+static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 #include "../heongpu_b200/csrc/ntt_core.cuh"
 using namespace heon;
 
@@ -80,12 +102,12 @@ int main()
 {
     const int logn = 12, N = 1 << logn;
     int failures = 0;
-    const int bitsizes[] = {30, 45, 50, 57, 58, 60, 61};
+    const int bitsizes[] = {30, 40, 45, 46, 47, 49, 50, 57, 58, 60, 61};
     for (int bits : bitsizes)
     {
         const u64 p = bits == 61 ? 2305843009213554689ull : largest_ntt_primes(2 * N, bits, 1)[0];
         const u64 psi = minimal_primitive_root(2 * N, p), ipsi = invmod(psi, p);
-        std::vector<TwPair> tw(N), itw(N);
+        std::vector<TwPair> tw(N), itw(N), twf(N);
         std::vector<u64> pw(N), ipw(N);
         pw[0] = ipw[0] = 1;
         for (int j = 1; j < N; ++j)
@@ -97,6 +119,9 @@ int main()
         {
             tw[j] = TwPair{pw[bitrev(j, logn)], shoup(pw[bitrev(j, logn)], p)};
             itw[j] = TwPair{ipw[bitrev(j, logn)], shoup(ipw[bitrev(j, logn)], p)};
+            const double winv = (double) tw[j].w / (double) p; // FP64-quotient table format
+            twf[j].w = tw[j].w;
+            std::memcpy(&twf[j].ws, &winv, 8);
         }
         PrimeConst pc;
         pc.p = p;
@@ -130,16 +155,22 @@ int main()
                     }
                 m <<= 1;
             }
-            for (int var = 0; var < 3; ++var)
+            for (int var = 0; var < 5; ++var)
             {
                 if (var == 2 && !pc.nc_ok)
+                    continue;
+                if ((var == 3 && pc.bits > 46) || (var == 4 && pc.bits > 50))
                     continue;
                 std::vector<u64> x = a;
                 // worst-case lazy input for the fused mod-up: words below 4p are legal inputs
                 if (var != 0 && pattern == 0)
                     for (int i = 0; i < N; i += 3)
                         x[i] += 3 * p;
-                var == 0 ? fwd<0>(x, tw, pc) : var == 1 ? fwd<1>(x, tw, pc) : fwd<2>(x, tw, pc);
+                var == 0   ? fwd<0>(x, tw, pc)
+                : var == 1 ? fwd<1>(x, tw, pc)
+                : var == 2 ? fwd<2>(x, tw, pc)
+                : var == 3 ? fwd<3>(x, twf, pc)
+                           : fwd<4>(x, twf, pc);
                 int bad = 0;
                 for (int i = 0; i < N; ++i) bad += x[i] != ref[i];
                 if (bad)
@@ -160,6 +191,34 @@ int main()
                     ++failures;
                 }
             }
+        }
+    }
+    // FP64-quotient Shoup product: exact for ANY Y < 2^52 (random and edge operands)
+    for (int bits : {30, 40, 46, 49, 50})
+    {
+        const u64 p = largest_ntt_primes(2 * N, bits, 1)[0];
+        u64 s = 777 + bits;
+        int bad = 0;
+        for (int it = 0; it < 400000; ++it)
+        {
+            s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+            u64 w = (it % 7 == 0) ? p - 1 : (it % 11 == 0) ? 1 : (s >> 4) % p;
+            s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+            u64 y = s >> 12; // < 2^52
+            if (it % 5 == 0) y = (y / p) * p + (it % 3) - 1 + (y < p ? p : 0); // multiples of p, +-1
+            if (it % 13 == 0) y = (1ull << 52) - 1 - (it & 7);
+            if (y >= (1ull << 52)) y = (1ull << 52) - 1;
+            const double winv = (double) w / (double) p;
+            u64 wb;
+            std::memcpy(&wb, &winv, 8);
+            const u64 tq = fshoup(y, w, wb, 0 - p);
+            if (!(tq < 2 * p) || tq % p != mulmod(y % p, w, p))
+                ++bad;
+        }
+        if (bad)
+        {
+            printf("FAIL fshoup bits=%d bad=%d\n", bits, bad);
+            ++failures;
         }
     }
     printf(failures ? "FAILED %d\n" : "OK\n", failures);

@@ -22,6 +22,8 @@ template <int OP> __global__ void __launch_bounds__(256) k(u64* out, u64 seed, i
             if (OP == 1) { ct_bfly<1>(v[0], v[1], tw, bc); ct_bfly<1>(v[2], v[3], tw, bc); ct_bfly<1>(v[4], v[5], tw, bc); ct_bfly<1>(v[6], v[7], tw, bc); }
             if (OP == 2) { ct_bfly<2>(v[0], v[1], tw, bc); ct_bfly<2>(v[2], v[3], tw, bc); ct_bfly<2>(v[4], v[5], tw, bc); ct_bfly<2>(v[6], v[7], tw, bc); }
             if (OP == 3) { gs_bfly<1>(v[0], v[1], tw, bc); gs_bfly<1>(v[2], v[3], tw, bc); gs_bfly<1>(v[4], v[5], tw, bc); gs_bfly<1>(v[6], v[7], tw, bc); }
+            if (OP == 6) { ct_bfly<3>(v[0], v[1], tw, bc); ct_bfly<3>(v[2], v[3], tw, bc); ct_bfly<3>(v[4], v[5], tw, bc); ct_bfly<3>(v[6], v[7], tw, bc); }
+            if (OP == 7) { ct_bfly<4>(v[0], v[1], tw, bc); ct_bfly<4>(v[2], v[3], tw, bc); ct_bfly<4>(v[4], v[5], tw, bc); ct_bfly<4>(v[6], v[7], tw, bc); }
             if (OP == 4) { a0 = __umulhi(a0, y) + a1; a1 = __umulhi(a1, y) + a2; a2 = __umulhi(a2, y) + a3; a3 = __umulhi(a3, y) + a0; }
             if (OP == 5) { v[0] = shoup_lazy_ptx(v[0], w, ws, bc.np); v[1] = shoup_lazy_ptx(v[1], w, ws, bc.np); v[2] = shoup_lazy_ptx(v[2], w, ws, bc.np); v[3] = shoup_lazy_ptx(v[3], w, ws, bc.np); }
         }
@@ -59,5 +61,7 @@ int main()
     run<3>("gs_bfly GVAR1 (ptx)");
     run<4>("mul.hi.u32 + add");
     run<5>("shoup_lazy_ptx only");
+    run<6>("ct_bfly VAR3 (fp64 quotient, nc)");
+    run<7>("ct_bfly VAR4 (fp64 quotient, csub)");
     return 0;
 }
