@@ -24,6 +24,9 @@ SIGNATURES = {
     "heon_version": (C.c_char_p, []),
     "heon_ckks_context_create": (ci, [ci, ci, i32p, ci, i32p, ci, C.POINTER(vp)]),
     "heon_ckks_context_create_values": (ci, [ci, ci, u64p, ci, u64p, ci, C.POINTER(vp)]),
+    "heon_bfv_context_create": (ci, [ci, ci, i32p, ci, i32p, ci, C.c_uint64, C.POINTER(vp)]),
+    "heon_bfv_multiply": (ci, [vp, vp, ll, vp, ll, vp, ll, ci, vp]),
+    "heon_bfv_relinearize": (ci, [vp, vp, ll, vp, ci, vp]),
     "heon_context_destroy": (None, [vp]),
     "heon_context_info": (ci, [vp, C.POINTER(heon_info)]),
     "heon_context_table": (ci, [vp, ci, ci, u64p, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -25,6 +25,9 @@ TBL = dict(
     modulus=0, psi=1, ntt=2, intt=3, n_inverse=4, last_q_modinv=5, half=6, half_mod=7, factor=8,
     rescaled_last_q_modinv=9, rescaled_half_mod=10, rescaled_half=11,
     ii_base_change=12, ii_mi_inv=13, ii_prod=14, ii_i_j=15, ii_i_location=16,
+    bfv_base_change_bsk=20, bfv_inv_punct_q=21, bfv_base_change_mtilde=22, bfv_inv_mtilde_mod_bsk=23,
+    bfv_prod_q_mod_bsk=24, bfv_inv_prod_q_mod_bsk=25, bfv_base_change_q=26, bfv_base_change_msk=27,
+    bfv_inv_punct_b=28, bfv_prod_b_mod_q=29, bfv_scalars=30,
 )
 
 _EXC = {-1: ValueError, -2: RuntimeError, -3: RuntimeError, -4: RuntimeError}
@@ -65,9 +68,15 @@ def _stream(stream=None):
 class HEContext:
     """HEContext<Scheme::CKKS> (reference: src/lib/host/ckks/context.cu:26-539)."""
 
-    def __init__(self, log_n, q_bits=None, p_bits=None, q_values=None, p_values=None, device=0):
+    def __init__(self, log_n, q_bits=None, p_bits=None, q_values=None, p_values=None, device=0,
+                 plain_modulus=None):
         h = C.c_void_p()
-        if q_values is not None:
+        self.scheme = "BFV" if plain_modulus else "CKKS"
+        if plain_modulus:  # HEContext<Scheme::BFV> (reference: src/lib/host/bfv/context.cu)
+            q = (C.c_int * len(q_bits))(*q_bits)
+            p = (C.c_int * len(p_bits))(*p_bits)
+            _check(lib.heon_bfv_context_create(device, log_n, q, len(q_bits), p, len(p_bits), int(plain_modulus), C.byref(h)))
+        elif q_values is not None:
             q = (C.c_uint64 * len(q_values))(*q_values)
             p = (C.c_uint64 * len(p_values))(*p_values)
             _check(lib.heon_ckks_context_create_values(device, log_n, q, len(q_values), p, len(p_values), C.byref(h)))
@@ -83,7 +92,10 @@ class HEContext:
         self.Q_prime_size = info.q_size + info.p_size
         self.keyswitch_method = info.keyswitch_method
         self.device = info.device
-        self.primes = [int(v) for v in self.table("modulus").reshape(-1, 3)[:, 0]]
+        allp = [int(v) for v in self.table("modulus").reshape(-1, 3)[:, 0]]
+        self.primes = allp[: self.Q_prime_size]
+        self.bsk_primes = allp[self.Q_prime_size:]  # BFV auxiliary base (empty for CKKS)
+        self.plain_modulus = int(plain_modulus) if plain_modulus else None
 
     def __del__(self):
         if getattr(self, "_h", None) and lib is not None:
@@ -246,6 +258,20 @@ class HEArithmeticOperator:
         ct.scale_ = ct.scale_ / float(c.primes[c.Q_size - ct.depth_ - 1])
         ct.depth_ += 1
         ct.rescale_required_ = False
+        return ct
+
+    # -- BFV (src/lib/host/bfv/operator.cu:336-430, 505-671); ciphertexts in the coefficient domain --
+    def multiply_bfv(self, a, b, out):
+        c = self.context_
+        _check(lib.heon_bfv_multiply(c._h, _ptr(a.data), a.stride, _ptr(b.data), b.stride, _ptr(out.data), out.stride,
+                                     a.batch, _stream()))
+        out.cipher_size_, out.relinearization_required_, out.in_ntt_domain_ = 3, True, False
+        return out
+
+    def relinearize_inplace_bfv(self, ct, relin_key):
+        c = self.context_
+        _check(lib.heon_bfv_relinearize(c._h, _ptr(ct.data), ct.stride, _ptr(relin_key.data), ct.batch, _stream()))
+        ct.cipher_size_, ct.relinearization_required_ = 2, False
         return ct
 
     def mod_drop_inplace(self, ct):

@@ -9,10 +9,10 @@ OBJ=${HEON_OBJDIR:-lib}
 mkdir -p $OBJ
 FLAGS="$HEON_EXTRA -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -cudart static"
 pids=()
-for f in ntt ckks_ops context capi; do
+for f in ntt ckks_ops bfv_ops context capi; do
   $NVCC $FLAGS -c csrc/$f.cu -o $OBJ/$f.o &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC $FLAGS -shared $OBJ/ntt.o $OBJ/ckks_ops.o $OBJ/context.o $OBJ/capi.o -o lib/$OUT
+$NVCC $FLAGS -shared $OBJ/ntt.o $OBJ/ckks_ops.o $OBJ/bfv_ops.o $OBJ/context.o $OBJ/capi.o -o lib/$OUT
 echo "built $(pwd)/lib/$OUT"

@@ -108,7 +108,7 @@ static void need_device(const Context& c)
         throw std::runtime_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
 }
 
-static void finish_context(Context& c, int device, int log_n, int n_q, int n_p)
+static void finish_context(Context& c, int device, int log_n, int n_q, int n_p, u64 plain_modulus = 0)
 {
     if (log_n < 12 || log_n > 16)
         throw std::logic_error("Poly modulus degree is not supported");
@@ -117,7 +117,8 @@ static void finish_context(Context& c, int device, int log_n, int n_q, int n_p)
     if (n_q < 1 || n_q + n_p > 128)
         throw std::logic_error("invalid modulus count");
     c.device = device;
-    c.scheme = SCHEME_CKKS;
+    c.scheme = plain_modulus ? SCHEME_BFV : SCHEME_CKKS;
+    c.plain_modulus = plain_modulus;
     c.logn = log_n;
     c.n = 1 << log_n;
     c.Q_size = n_q;
@@ -134,9 +135,31 @@ static void finish_context(Context& c, int device, int log_n, int n_q, int n_p)
         c.use_fp64 = atoi(v);
     if (const char* v = getenv("HEON_NTT_TMA"))
         c.use_tma = atoi(v);
+    if (c.scheme == SCHEME_BFV)
+    {
+        // auxiliary base Bsk: the largest 61-bit primes, one more than needed (the largest is the
+        // gamma prime of the decryptor and is not part of Bsk); bfv/context.cu:518-531, util.cu:278-310
+        int total_bits = 0;
+        for (int i = 0; i < n_q + n_p; ++i)
+            total_bits += (int) c.mod[i].bit;
+        c.bsk = n_q + n_p;
+        if (bit_length(plain_modulus) + total_bits + 32 >= 61 * n_q + 61)
+            c.bsk++;
+        std::vector<u64> big = largest_ntt_primes(2ull << log_n, 61, (size_t) c.bsk + 1);
+        for (int i = 0; i < c.bsk; ++i)
+            c.mod.push_back(make_mod(big[c.bsk - i])); // ascending; big[0] (largest) is gamma
+        if ((int) c.mod.size() > 128)
+            throw std::logic_error("invalid modulus count");
+    }
     build_host_tables(c);
+    if (c.scheme == SCHEME_BFV)
+        build_bfv_tables(c);
     if (device >= 0)
+    {
         upload_tables(c);
+        if (c.scheme == SCHEME_BFV)
+            upload_bfv_tables(c);
+    }
 }
 
 extern "C" {
@@ -179,6 +202,54 @@ int heon_ckks_context_create_values(int device, int log_n, const uint64_t* q, in
                 throw std::logic_error("invalid modulus");
         finish_context(h->c, device, log_n, n_q, n_p);
         *out = h.release();
+    });
+}
+
+int heon_bfv_context_create(int device, int log_n, const int* q_bits, int n_q, const int* p_bits, int n_p,
+                            uint64_t plain_modulus, heon_context_t* out)
+{
+    return guarded([&] {
+        if (!out || !q_bits || !p_bits)
+            throw std::invalid_argument("null argument");
+        if (plain_modulus < 2)
+            throw std::logic_error("invalid plain modulus");
+        auto h = std::make_unique<heon_context_s>();
+        std::vector<int> bits(q_bits, q_bits + n_q);
+        bits.insert(bits.end(), p_bits, p_bits + n_p);
+        if (log_n < 12 || log_n > 16)
+            throw std::logic_error("Poly modulus degree is not supported");
+        for (u64 p : primes_for_bit_sizes(1ull << log_n, bits))
+            h->c.mod.push_back(make_mod(p));
+        finish_context(h->c, device, log_n, n_q, n_p, plain_modulus);
+        *out = h.release();
+    });
+}
+
+int heon_bfv_multiply(heon_context_t ctx, const uint64_t* a, long long as, const uint64_t* b, long long bs,
+                      uint64_t* out, long long os, int batch, void* stream)
+{
+    return guarded([&] {
+        if (!ctx || !a || !b || !out)
+            throw std::invalid_argument("null argument");
+        const Context& c = ctx->c;
+        need_device(c);
+        if (batch < 1)
+            throw std::invalid_argument("batch must be positive");
+        op_bfv_multiply(c, a, as, b, bs, out, os, batch, (cudaStream_t) stream);
+    });
+}
+
+int heon_bfv_relinearize(heon_context_t ctx, uint64_t* ct, long long cs, const uint64_t* relin_key, int batch,
+                         void* stream)
+{
+    return guarded([&] {
+        if (!ctx || !ct || !relin_key)
+            throw std::invalid_argument("null argument");
+        const Context& c = ctx->c;
+        need_device(c);
+        if (batch < 1)
+            throw std::invalid_argument("batch must be positive");
+        op_bfv_relinearize(c, ct, cs, relin_key, batch, (cudaStream_t) stream);
     });
 }
 
@@ -241,6 +312,20 @@ int heon_context_table(heon_context_t ctx, int which, int depth, uint64_t* h_out
             case HEON_TBL_II_I_LOCATION:
                 for (int v : lvl().I_loc)
                     tmp.push_back((u64) v);
+                src = &tmp;
+                break;
+            case HEON_TBL_BFV_BASE_CHANGE_BSK: src = &c.bfv.base_change_matrix_Bsk; break;
+            case HEON_TBL_BFV_INV_PUNCT_Q: src = &c.bfv.inv_punctured_prod_mod_base_array; break;
+            case HEON_TBL_BFV_BASE_CHANGE_MTILDE: src = &c.bfv.base_change_matrix_m_tilde; break;
+            case HEON_TBL_BFV_INV_MTILDE_MOD_BSK: src = &c.bfv.inv_m_tilde_mod_Bsk; break;
+            case HEON_TBL_BFV_PROD_Q_MOD_BSK: src = &c.bfv.prod_q_mod_Bsk; break;
+            case HEON_TBL_BFV_INV_PROD_Q_MOD_BSK: src = &c.bfv.inv_prod_q_mod_Bsk; break;
+            case HEON_TBL_BFV_BASE_CHANGE_Q: src = &c.bfv.base_change_matrix_q; break;
+            case HEON_TBL_BFV_BASE_CHANGE_MSK: src = &c.bfv.base_change_matrix_msk; break;
+            case HEON_TBL_BFV_INV_PUNCT_B: src = &c.bfv.inv_punctured_prod_mod_B_array; break;
+            case HEON_TBL_BFV_PROD_B_MOD_Q: src = &c.bfv.prod_B_mod_q; break;
+            case HEON_TBL_BFV_SCALARS:
+                tmp = {c.bfv.inv_prod_q_mod_m_tilde, c.bfv.inv_prod_B_mod_m_sk, (u64) c.bsk, c.plain_modulus};
                 src = &tmp;
                 break;
             default: throw std::invalid_argument("unknown table");

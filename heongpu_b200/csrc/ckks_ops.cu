@@ -607,6 +607,39 @@ void op_relinearize(const Context& c, u64* ct, long long ct_bs, const u64* relin
     moddown_add(c, acc.w(), tmp.w(), ct, ct_bs, ct, ct_bs, depth, batch, 3, st);
 }
 
+// BFV relinearize: ct [b][3][Q][N] in the COEFFICIENT domain, in place.
+//   mod-up of c2 (Method I: exact reduction into every prime of Q', Method II: HPS base
+//   conversion) -> NTT -> inner product with the key -> INTT of all 2*Q' limbs ->
+//   coefficient-domain divide-and-round by P -> add to (c0, c1).
+// reference: bfv/operator.cu:505-590 (relinearize_seal_method_inplace),
+//            :592-671 (relinearize_external_product_method2_inplace)
+void op_bfv_relinearize(const Context& c, u64* ct, long long ct_bs, const u64* relin_key, int batch,
+                        cudaStream_t st)
+{
+    if (c.scheme != SCHEME_BFV)
+        throw std::invalid_argument("not a BFV context");
+    const int L = c.Q_size, K = c.P_size, Qpl = L + K;
+    const long long N = c.n;
+    Scratch tmp(ks_tmp_words(c, 0, batch) * 8, st);
+    Scratch acc((size_t) batch * 2 * Qpl * N * 8, st);
+    keyswitch_core(c, ct + 2LL * L * N, ct_bs, relin_key, tmp.w(), acc.w(), 0, batch, st);
+    launch_ntt(c, acc.w(), acc.w(), (long long) batch * 2 * Qpl, level_primes(L, K, 0), true, st);
+    dim3 g(c.n >> 8, batch * 2);
+    {
+        LaunchScope scope(KC_MODDOWN, st);
+        k_moddown_ext<false><<<g, 256, 0, st>>>(acc.w(), tmp.w(), 2 * L * N, nullptr, c.d_pc, c.d_half,
+                                                c.d_half_mod, c.d_lqm_pair, 0, c.logn, Qpl, L, c.Qp,
+                                                c.Q_size, K);
+    }
+    check_launch();
+    dim3 g2(c.n >> 8, L, batch * 2);
+    {
+        LaunchScope scope(KC_ELEMENTWISE, st);
+        k_addsub<0><<<g2, 256, 0, st>>>(tmp.w(), ct, ct, 2 * L * N, ct_bs, ct_bs, c.d_mod, c.logn, L, 2);
+    }
+    check_launch();
+}
+
 // ct: [b][2][L][N] -> [b][2][L-1][N] compacted in place.
 // reference: ckks/operator.cu:1156-1244 (rescale_inplace_ckks_leveled)
 void op_rescale(const Context& c, u64* ct, long long ct_bs, int depth, int batch, cudaStream_t st)

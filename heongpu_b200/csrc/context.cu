@@ -45,12 +45,13 @@ static std::vector<int> digit_sizes(int l, int m)
 void build_host_tables(Context& c)
 {
     const int N = c.n, Qp = c.Qp, Q = c.Q_size, K = c.P_size;
-    c.psi.resize(Qp);
-    c.ntt_table.assign((size_t) Qp * N, 0);
-    c.intt_table.assign((size_t) Qp * N, 0);
-    c.n_inverse.resize(Qp);
+    const int T = (int) c.mod.size(); // Q' chain followed by the BFV auxiliary base Bsk (if any)
+    c.psi.resize(T);
+    c.ntt_table.assign((size_t) T * N, 0);
+    c.intt_table.assign((size_t) T * N, 0);
+    c.n_inverse.resize(T);
     std::vector<u64> pw(N);
-    for (int i = 0; i < Qp; ++i)
+    for (int i = 0; i < T; ++i)
     {
         const u64 p = c.mod[i].value;
         c.psi[i] = minimal_primitive_root(2 * (u64) N, p);
@@ -105,9 +106,10 @@ void build_host_tables(Context& c)
 
     // Method II (hybrid key switching with K > 1): per-depth digit tables
     c.lvl2.clear();
-    if (c.method == 2 && c.scheme == SCHEME_CKKS)
+    if (c.method == 2)
     {
-        for (int depth = 0; depth < Q; ++depth)
+        // BFV has no levels: only the depth-0 tables (contextpool.cpp:160-191, 242-264, 361-394)
+        for (int depth = 0; depth < (c.scheme == SCHEME_CKKS ? Q : 1); ++depth)
         {
             const int L = Q - depth;
             // limb set at this depth: q_0..q_{L-1}, p_0..p_{K-1}
@@ -158,9 +160,117 @@ void build_host_tables(Context& c)
     }
 }
 
+// BFV (BEHZ) multiplication constants.  Every entry is the exact residue the
+// reference's host code produces (src/lib/host/bfv/context.cu:990-1290).
+// Prime chain layout: mod = [q_0..q_{Q-1}, p_0..p_{K-1}, B_0..B_{m-1}], the
+// auxiliary base Bsk = {B_0..B_{m-2}} U {m_sk = B_{m-1}}; m_tilde = 2^32.
+static u64 inv_mod_pow2_32(u64 a)
+{
+    // a odd; Newton iteration modulo 2^32
+    u64 x = a;
+    for (int i = 0; i < 6; ++i)
+        x = (x * (2 - a * x)) & 0xffffffffull;
+    return x & 0xffffffffull;
+}
+
+void build_bfv_tables(Context& c)
+{
+    const int Q = c.Q_size, m = c.bsk;
+    const u64 mt = 1ull << 32;
+    auto q = [&](int i) { return c.mod[i].value; };
+    auto B = [&](int i) { return c.mod[c.Qp + i].value; };
+    BfvTables& t = c.bfv;
+    t = BfvTables();
+    for (int k = 0; k < m; ++k) // generate_base_matrix_q_Bsk
+        for (int i = 0; i < Q; ++i)
+        {
+            u64 v = 1;
+            for (int j = 0; j < Q; ++j)
+                if (j != i)
+                    v = mulmod(v, q(j) % B(k), B(k));
+            t.base_change_matrix_Bsk.push_back(v);
+        }
+    for (int i = 0; i < Q; ++i) // calculate_Mi_inv(prime_vector_, Q_size)
+    {
+        u64 v = 1;
+        for (int j = 0; j < Q; ++j)
+            if (j != i)
+                v = mulmod(v, q(j) % q(i), q(i));
+        t.inv_punctured_prod_mod_base_array.push_back(invmod(v, q(i)));
+    }
+    u64 prod_mt = 1;
+    for (int i = 0; i < Q; ++i) // generate_base_change_matrix_m_tilde / inv_prod_q_mod_m_tilde
+    {
+        u64 v = 1;
+        for (int j = 0; j < Q; ++j)
+            if (j != i)
+                v = (v * (q(j) % mt)) % mt;
+        t.base_change_matrix_m_tilde.push_back(v);
+        prod_mt = (prod_mt * (q(i) % mt)) % mt;
+    }
+    t.inv_prod_q_mod_m_tilde = inv_mod_pow2_32(prod_mt);
+    for (int i = 0; i < m; ++i)
+    {
+        t.inv_m_tilde_mod_Bsk.push_back(invmod(mt % B(i), B(i)));
+        u64 v = 1;
+        for (int j = 0; j < Q; ++j)
+            v = mulmod(v, q(j) % B(i), B(i));
+        t.prod_q_mod_Bsk.push_back(v);
+        t.inv_prod_q_mod_Bsk.push_back(invmod(v, B(i)));
+    }
+    for (int k = 0; k < Q; ++k) // generate_base_matrix_Bsk_q
+        for (int i = 0; i < m - 1; ++i)
+        {
+            u64 v = 1;
+            for (int j = 0; j < m - 1; ++j)
+                if (j != i)
+                    v = mulmod(v, B(j) % q(k), q(k));
+            t.base_change_matrix_q.push_back(v);
+        }
+    const u64 msk = B(m - 1);
+    u64 prodB_msk = 1;
+    for (int i = 0; i < m - 1; ++i)
+    {
+        u64 v = 1, w = 1;
+        for (int j = 0; j < m - 1; ++j)
+            if (j != i)
+            {
+                v = mulmod(v, B(j) % msk, msk);
+                w = mulmod(w, B(j) % B(i), B(i));
+            }
+        t.base_change_matrix_msk.push_back(v);
+        t.inv_punctured_prod_mod_B_array.push_back(invmod(w, B(i)));
+        prodB_msk = mulmod(prodB_msk, B(i) % msk, msk);
+    }
+    t.inv_prod_B_mod_m_sk = invmod(prodB_msk, msk);
+    for (int i = 0; i < Q; ++i)
+    {
+        u64 v = 1;
+        for (int j = 0; j < m - 1; ++j)
+            v = mulmod(v, B(j) % q(i), q(i));
+        t.prod_B_mod_q.push_back(v);
+    }
+}
+
+void upload_bfv_tables(Context& c)
+{
+    BfvTables& t = c.bfv;
+    t.d_base_change_matrix_Bsk = upload(t.base_change_matrix_Bsk);
+    t.d_inv_punctured_prod_mod_base_array = upload(t.inv_punctured_prod_mod_base_array);
+    t.d_base_change_matrix_m_tilde = upload(t.base_change_matrix_m_tilde);
+    t.d_inv_m_tilde_mod_Bsk = upload(t.inv_m_tilde_mod_Bsk);
+    t.d_prod_q_mod_Bsk = upload(t.prod_q_mod_Bsk);
+    t.d_inv_prod_q_mod_Bsk = upload(t.inv_prod_q_mod_Bsk);
+    t.d_base_change_matrix_q = upload(t.base_change_matrix_q);
+    t.d_base_change_matrix_msk = upload(t.base_change_matrix_msk);
+    t.d_inv_punctured_prod_mod_B_array = upload(t.inv_punctured_prod_mod_B_array);
+    t.d_prod_B_mod_q = upload(t.prod_B_mod_q);
+}
+
 void upload_tables(Context& c)
 {
-    const int N = c.n, Qp = c.Qp;
+    const int N = c.n;
+    const int Qp = (int) c.mod.size(); // device NTT tables cover every prime (Q' chain + Bsk)
     HEON_CUDA(cudaSetDevice(c.device));
     HEON_CUDA(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, c.device));
     {
@@ -239,7 +349,7 @@ void upload_tables(Context& c)
         std::vector<TwPair> pairs;
         size_t o = 0;
         for (int i = 0; i < c.P_size; ++i)
-            for (int j = 0; j < Qp - 1 - i; ++j, ++o)
+            for (int j = 0; j < c.Qp - 1 - i; ++j, ++o)
                 pairs.push_back(TwPair{c.last_q_modinv[o], shoup(c.last_q_modinv[o], c.mod[j].value)});
         c.d_lqm_pair = upload(pairs);
     }
@@ -292,6 +402,16 @@ Context::~Context()
     cudaFree(d_rescaled_last_q_modinv);
     cudaFree(d_rescaled_half_mod);
     cudaFree(d_rescaled_half);
+    cudaFree(bfv.d_base_change_matrix_Bsk);
+    cudaFree(bfv.d_inv_punctured_prod_mod_base_array);
+    cudaFree(bfv.d_base_change_matrix_m_tilde);
+    cudaFree(bfv.d_inv_m_tilde_mod_Bsk);
+    cudaFree(bfv.d_prod_q_mod_Bsk);
+    cudaFree(bfv.d_inv_prod_q_mod_Bsk);
+    cudaFree(bfv.d_base_change_matrix_q);
+    cudaFree(bfv.d_base_change_matrix_msk);
+    cudaFree(bfv.d_inv_punctured_prod_mod_B_array);
+    cudaFree(bfv.d_prod_B_mod_q);
     for (auto& t : lvl2)
     {
         cudaFree(t.d_base_change);

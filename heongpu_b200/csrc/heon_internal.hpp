@@ -53,6 +53,18 @@ struct LevelTablesII {
     int* d_I_loc = nullptr;
 };
 
+// BFV BEHZ multiplication tables (reference member names, bfv/context.cu:543-660)
+struct BfvTables {
+    std::vector<u64> base_change_matrix_Bsk, inv_punctured_prod_mod_base_array, base_change_matrix_m_tilde,
+        inv_m_tilde_mod_Bsk, prod_q_mod_Bsk, inv_prod_q_mod_Bsk, base_change_matrix_q, base_change_matrix_msk,
+        inv_punctured_prod_mod_B_array, prod_B_mod_q;
+    u64 inv_prod_q_mod_m_tilde = 0, inv_prod_B_mod_m_sk = 0;
+    u64 *d_base_change_matrix_Bsk = nullptr, *d_inv_punctured_prod_mod_base_array = nullptr,
+        *d_base_change_matrix_m_tilde = nullptr, *d_inv_m_tilde_mod_Bsk = nullptr, *d_prod_q_mod_Bsk = nullptr,
+        *d_inv_prod_q_mod_Bsk = nullptr, *d_base_change_matrix_q = nullptr, *d_base_change_matrix_msk = nullptr,
+        *d_inv_punctured_prod_mod_B_array = nullptr, *d_prod_B_mod_q = nullptr;
+};
+
 struct Context {
     int device = 0;
     int scheme = SCHEME_CKKS;
@@ -69,8 +81,10 @@ struct Context {
     std::vector<u64> rescaled_last_q_modinv, rescaled_half_mod, rescaled_half;
     std::vector<LevelTablesII> lvl2; // Method II only
 
-    // BFV plain modulus etc. (BFV contexts only)
+    // BFV only: plain modulus, size of the auxiliary base Bsk (its primes follow the Q' chain in `mod`)
     u64 plain_modulus = 0;
+    int bsk = 0;
+    BfvTables bfv;
 
     // Device tables
     Mod64* d_mod = nullptr; // [Qp]
@@ -128,6 +142,8 @@ inline PrimeList range_primes(int first, int count)
 
 void build_host_tables(Context& c);
 void upload_tables(Context& c);
+void build_bfv_tables(Context& c);
+void upload_bfv_tables(Context& c);
 
 // ---- NTT launchers (ntt.cu); all asynchronous on `st` ----
 void launch_ntt(const Context& c, const u64* src, u64* dst, long long n_polys, const PrimeList& pl,

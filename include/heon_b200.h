@@ -67,7 +67,19 @@ enum {
     HEON_TBL_II_MI_INV = 13,
     HEON_TBL_II_PROD = 14,
     HEON_TBL_II_I_J = 15,      /* int32 widened to u64                     */
-    HEON_TBL_II_I_LOCATION = 16
+    HEON_TBL_II_I_LOCATION = 16,
+    /* BFV BEHZ tables (reference member names, src/lib/host/bfv/context.cu:543-660) */
+    HEON_TBL_BFV_BASE_CHANGE_BSK = 20,    /* base_change_matrix_Bsk_            [bsk][Q]   */
+    HEON_TBL_BFV_INV_PUNCT_Q = 21,        /* inv_punctured_prod_mod_base_array_ [Q]        */
+    HEON_TBL_BFV_BASE_CHANGE_MTILDE = 22, /* base_change_matrix_m_tilde_        [Q]        */
+    HEON_TBL_BFV_INV_MTILDE_MOD_BSK = 23, /* inv_m_tilde_mod_Bsk_               [bsk]      */
+    HEON_TBL_BFV_PROD_Q_MOD_BSK = 24,     /* prod_q_mod_Bsk_                    [bsk]      */
+    HEON_TBL_BFV_INV_PROD_Q_MOD_BSK = 25, /* inv_prod_q_mod_Bsk_                [bsk]      */
+    HEON_TBL_BFV_BASE_CHANGE_Q = 26,      /* base_change_matrix_q_              [Q][bsk-1] */
+    HEON_TBL_BFV_BASE_CHANGE_MSK = 27,    /* base_change_matrix_msk_            [bsk-1]    */
+    HEON_TBL_BFV_INV_PUNCT_B = 28,        /* inv_punctured_prod_mod_B_array_    [bsk-1]    */
+    HEON_TBL_BFV_PROD_B_MOD_Q = 29,       /* prod_B_mod_q_                      [Q]        */
+    HEON_TBL_BFV_SCALARS = 30 /* {inv_prod_q_mod_m_tilde_, inv_prod_B_mod_m_sk_, bsk_modulus, plain_modulus} */
 };
 
 typedef struct heon_info {
@@ -88,6 +100,13 @@ int heon_ckks_context_create(int device, int log_n, const int* q_bits, int n_q, 
                              int n_p, heon_context_t* out);
 int heon_ckks_context_create_values(int device, int log_n, const uint64_t* q, int n_q,
                                     const uint64_t* p, int n_p, heon_context_t* out);
+/* ---- context: HEContext<Scheme::BFV> ------------------------------------
+ * replaces HEContextImpl<BFV>::generate (src/lib/host/bfv/context.cu:397-700):
+ * the Q' chain as for CKKS, plus the BEHZ auxiliary base Bsk (61-bit internal
+ * primes, util.cu:278-310) with its NTT tables and conversion constants.
+ * HEON_TBL_MODULUS then lists Q' followed by the bsk_modulus Bsk primes. */
+int heon_bfv_context_create(int device, int log_n, const int* q_bits, int n_q, const int* p_bits, int n_p,
+                            uint64_t plain_modulus, heon_context_t* out);
 void heon_context_destroy(heon_context_t ctx);
 int heon_context_info(heon_context_t ctx, heon_info* out);
 /* Copies a host table into h_out (capacity `cap` words); *count receives the
@@ -153,6 +172,18 @@ int heon_ckks_mod_drop(heon_context_t ctx, const uint64_t* in, long long in_stri
 int heon_ckks_apply_galois(heon_context_t ctx, const uint64_t* in, long long in_stride,
                            uint64_t* out, long long out_stride, const uint64_t* galois_key,
                            uint32_t galois_elt, int depth, int batch, void* stream);
+
+/* ---- HEOperator<BFV>::multiply_bfv (src/lib/host/bfv/operator.cu:336-430) --
+ * BEHZ multiplication.  a, b: [2][Q][N], out: [3][Q][N], all in the
+ * COEFFICIENT domain (BFV ciphertexts are not kept in the NTT domain). */
+int heon_bfv_multiply(heon_context_t ctx, const uint64_t* a, long long a_stride, const uint64_t* b,
+                      long long b_stride, uint64_t* out, long long out_stride, int batch, void* stream);
+
+/* ---- relinearize_seal_method_inplace (bfv/operator.cu:505-590) and
+ *      relinearize_external_product_method2_inplace (:592-671).
+ * ct: [3][Q][N] coefficient domain, in place (components 0 and 1 updated). */
+int heon_bfv_relinearize(heon_context_t ctx, uint64_t* ct, long long ct_stride, const uint64_t* relin_key,
+                         int batch, void* stream);
 
 /* Per-kernel-class CUDA-event profiler (used by bench.py for the roofline
  * line): begin() arms it, end() synchronises the device and returns, per

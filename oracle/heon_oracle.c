@@ -837,3 +837,454 @@ void oracle_keyswitch_core(const octx* c, const u64* coef, const u64* key, u64* 
     o_keyswitch_core(c, coef, key, acc, depth);
 }
 int oracle_digits(const octx* c, int depth) { return c->method == 1 ? c->Q - depth : c->dcount[depth]; }
+
+/* ========================================================================== */
+/* BFV: BEHZ multiplication and un-levelled relinearization                    */
+/* ========================================================================== */
+
+/* generate_internal_primes: util.cu:278-310 -- (count) largest 61-bit primes,
+ * handed out from the back (ascending order in the result). */
+int oracle_internal_primes(u64 n, int count, u64* out)
+{
+    int bits[128];
+    for (int i = 0; i < count; i++)
+        bits[i] = 61;
+    /* oracle_generate_primes hands the list out from the back already */
+    u64 factor = 2 * n;
+    u64 value = ((((u64) 1) << 61) - 1) / factor * factor + 1, lower = ((u64) 1) << 60;
+    u64 list[128];
+    int found = 0;
+    while (found < count && value > lower) {
+        if (o_is_prime(value))
+            list[found++] = value;
+        value -= factor;
+    }
+    if (found < count)
+        return -1;
+    for (int i = 0; i < count; i++)
+        out[i] = list[count - 1 - i];
+    (void) bits;
+    return 0;
+}
+
+typedef struct {
+    int n, n_power, Q, K, Qp, m; /* m = bsk_modulus */
+    omod *q, *B;                 /* q: Q' chain, B: Bsk (m primes, last = m_sk) */
+    omod mt;                     /* m_tilde = 2^32 */
+    u64 t;                       /* plain modulus */
+    u64 *bcm_bsk, *inv_punct, *bcm_mt, *inv_mt_bsk, *prod_q_bsk, *inv_prod_q_bsk, *bcm_q, *bcm_msk, *inv_punct_B,
+        *prod_B_q;
+    u64 inv_prod_q_mt, inv_prod_B_msk;
+    u64 *fwd, *inv, *ninv; /* NTT tables over the merged base [q_0..q_{Q-1}, B_0..B_{m-1}] */
+    octx* ks;              /* key-switch tables over the Q' chain */
+} obfv;
+
+/* modInverse for the power-of-two modulus m_tilde (extended Euclid in the reference) */
+static u64 o_inv_pow2_32(u64 a)
+{
+    u64 x = 1;
+    for (int i = 0; i < 32; i++) /* bit-by-bit: x = a^-1 mod 2^(i+1) */
+        if (((a * x) >> i) & 1)
+            x |= ((u64) 1 << i);
+    return x & 0xffffffffull;
+}
+
+/* table generators: bfv/context.cu:990-1220 */
+obfv* oracle_bfv_create(int n_power, const u64* primes, int Q, int K, u64 plain_modulus)
+{
+    obfv* c = (obfv*) calloc(1, sizeof(obfv));
+    c->n_power = n_power;
+    c->n = 1 << n_power;
+    c->Q = Q;
+    c->K = K;
+    c->Qp = Q + K;
+    c->t = plain_modulus;
+    int total_bits = 0;
+    for (int i = 0; i < c->Qp; i++)
+        total_bits += (int) (log2((double) primes[i]) + 1);
+    c->m = c->Qp; /* bfv/context.cu:518-524 */
+    if ((int) (log2((double) plain_modulus) + 1) + total_bits + 32 >= 61 * Q + 61)
+        c->m++;
+    int m = c->m;
+    u64 bsk[128];
+    oracle_internal_primes((u64) c->n, m + 1, bsk); /* the extra (largest) one is gamma */
+    c->q = (omod*) malloc(sizeof(omod) * c->Qp);
+    c->B = (omod*) malloc(sizeof(omod) * m);
+    for (int i = 0; i < c->Qp; i++)
+        oracle_make_mod(primes[i], &c->q[i]);
+    for (int i = 0; i < m; i++)
+        oracle_make_mod(bsk[i], &c->B[i]);
+    oracle_make_mod((u64) 1 << 32, &c->mt);
+    c->ks = oracle_ctx_create(n_power, primes, Q, K);
+
+    c->bcm_bsk = (u64*) malloc(sizeof(u64) * m * Q);
+    for (int k = 0; k < m; k++) /* generate_base_matrix_q_Bsk */
+        for (int i = 0; i < Q; i++) {
+            u64 temp = 1;
+            for (int j = 0; j < Q; j++)
+                if (i != j)
+                    temp = o_mult(temp, c->q[j].value, &c->B[k]);
+            c->bcm_bsk[k * Q + i] = temp;
+        }
+    c->inv_punct = (u64*) malloc(sizeof(u64) * Q); /* calculate_Mi_inv (util.cu) */
+    c->bcm_mt = (u64*) malloc(sizeof(u64) * Q);
+    u64 prod_mt = 1;
+    for (int i = 0; i < Q; i++) {
+        u64 temp = 1, tm = 1;
+        for (int j = 0; j < Q; j++)
+            if (i != j) {
+                temp = o_mult(temp, c->q[j].value % c->q[i].value, &c->q[i]);
+                tm = o_mult(tm, c->q[j].value % c->mt.value, &c->mt);
+            }
+        c->inv_punct[i] = o_modinv(temp, &c->q[i]);
+        c->bcm_mt[i] = tm;
+        prod_mt = o_mult(prod_mt, c->q[i].value % c->mt.value, &c->mt);
+    }
+    c->inv_prod_q_mt = o_inv_pow2_32(prod_mt);
+    c->inv_mt_bsk = (u64*) malloc(sizeof(u64) * m);
+    c->prod_q_bsk = (u64*) malloc(sizeof(u64) * m);
+    c->inv_prod_q_bsk = (u64*) malloc(sizeof(u64) * m);
+    for (int i = 0; i < m; i++) {
+        c->inv_mt_bsk[i] = o_modinv(c->mt.value, &c->B[i]);
+        u64 temp = 1;
+        for (int j = 0; j < Q; j++)
+            temp = o_mult(temp, c->q[j].value, &c->B[i]);
+        c->prod_q_bsk[i] = temp;
+        c->inv_prod_q_bsk[i] = o_modinv(temp, &c->B[i]);
+    }
+    c->bcm_q = (u64*) malloc(sizeof(u64) * Q * (m - 1));
+    for (int k = 0; k < Q; k++) /* generate_base_matrix_Bsk_q */
+        for (int i = 0; i < m - 1; i++) {
+            u64 temp = 1;
+            for (int j = 0; j < m - 1; j++)
+                if (i != j)
+                    temp = o_mult(temp, c->B[j].value % c->q[k].value, &c->q[k]);
+            c->bcm_q[k * (m - 1) + i] = temp;
+        }
+    c->bcm_msk = (u64*) malloc(sizeof(u64) * (m - 1));
+    c->inv_punct_B = (u64*) malloc(sizeof(u64) * (m - 1));
+    u64 pb = 1;
+    for (int i = 0; i < m - 1; i++) {
+        u64 t1 = 1, t2 = 1;
+        for (int j = 0; j < m - 1; j++)
+            if (i != j) {
+                t1 = o_mult(t1, c->B[j].value, &c->B[m - 1]);
+                t2 = o_mult(t2, c->B[j].value, &c->B[i]);
+            }
+        c->bcm_msk[i] = t1;
+        c->inv_punct_B[i] = o_modinv(t2, &c->B[i]);
+        pb = o_mult(pb, c->B[i].value, &c->B[m - 1]);
+    }
+    c->inv_prod_B_msk = o_modinv(pb, &c->B[m - 1]);
+    c->prod_B_q = (u64*) malloc(sizeof(u64) * Q);
+    for (int i = 0; i < Q; i++) {
+        u64 temp = 1;
+        for (int j = 0; j < m - 1; j++)
+            temp = o_mult(temp, c->B[j].value % c->q[i].value, &c->q[i]);
+        c->prod_B_q[i] = temp;
+    }
+    /* merged NTT tables: generate_q_Bsk_merge_modulus / _root, bfv/context.cu:1222-1256 */
+    int W = Q + m;
+    u64* merged = (u64*) malloc(sizeof(u64) * W);
+    for (int i = 0; i < Q; i++)
+        merged[i] = primes[i];
+    for (int i = 0; i < m; i++)
+        merged[Q + i] = bsk[i];
+    c->fwd = (u64*) malloc(sizeof(u64) * (size_t) W * c->n);
+    c->inv = (u64*) malloc(sizeof(u64) * (size_t) W * c->n);
+    c->ninv = (u64*) malloc(sizeof(u64) * W);
+    u64* psi = (u64*) malloc(sizeof(u64) * W);
+    oracle_ntt_tables(merged, W, n_power, psi, c->fwd, c->inv, c->ninv);
+    free(psi);
+    free(merged);
+    return c;
+}
+
+void oracle_bfv_destroy(obfv* c)
+{
+    if (!c)
+        return;
+    free(c->q);
+    free(c->B);
+    free(c->bcm_bsk);
+    free(c->inv_punct);
+    free(c->bcm_mt);
+    free(c->inv_mt_bsk);
+    free(c->prod_q_bsk);
+    free(c->inv_prod_q_bsk);
+    free(c->bcm_q);
+    free(c->bcm_msk);
+    free(c->inv_punct_B);
+    free(c->prod_B_q);
+    free(c->fwd);
+    free(c->inv);
+    free(c->ninv);
+    oracle_ctx_destroy(c->ks);
+    free(c);
+}
+
+int oracle_bfv_bsk_count(const obfv* c) { return c->m; }
+void oracle_bfv_bsk_primes(const obfv* c, u64* out)
+{
+    for (int i = 0; i < c->m; i++)
+        out[i] = c->B[i].value;
+}
+/* which: same order as HEON_TBL_BFV_* (20..29); returns the count */
+int oracle_bfv_table(const obfv* c, int which, u64* out)
+{
+    int Q = c->Q, m = c->m, n = 0;
+    const u64* src = NULL;
+    switch (which) {
+    case 20: src = c->bcm_bsk; n = m * Q; break;
+    case 21: src = c->inv_punct; n = Q; break;
+    case 22: src = c->bcm_mt; n = Q; break;
+    case 23: src = c->inv_mt_bsk; n = m; break;
+    case 24: src = c->prod_q_bsk; n = m; break;
+    case 25: src = c->inv_prod_q_bsk; n = m; break;
+    case 26: src = c->bcm_q; n = Q * (m - 1); break;
+    case 27: src = c->bcm_msk; n = m - 1; break;
+    case 28: src = c->inv_punct_B; n = m - 1; break;
+    case 29: src = c->prod_B_q; n = Q; break;
+    case 30: out[0] = c->inv_prod_q_mt; out[1] = c->inv_prod_B_msk; out[2] = (u64) m; out[3] = c->t; return 4;
+    default: return -1;
+    }
+    memcpy(out, src, sizeof(u64) * n);
+    return n;
+}
+
+/* fast_convertion: multiplication.cu:10-100.  in1/in2: [2][Q][N]; out: [4][Q+m][N] */
+static void o_fast_convertion(const obfv* c, const u64* in1, const u64* in2, u64* out1)
+{
+    int n = c->n, Q = c->Q, m = c->m;
+#pragma omp parallel for
+    for (int idy = 0; idy < 4; idy++)
+        for (int idx = 0; idx < n; idx++) {
+            const u64* input = ((idy >> 1) == 0) ? in1 : in2;
+            size_t location = idx + (size_t) ((idy % 2) * Q) * n;
+            u64 temp[64], temp_[64], temp2[65];
+            for (int i = 0; i < Q; i++) {
+                temp_[i] = input[location + (size_t) i * n];
+                temp[i] = o_mult(temp_[i], c->mt.value, &c->q[i]);
+                temp[i] = o_mult(temp[i], c->inv_punct[i], &c->q[i]);
+            }
+            for (int i = 0; i < m; i++) {
+                temp2[i] = 0;
+                for (int j = 0; j < Q; j++) {
+                    u64 mult = o_mult(temp[j], c->bcm_bsk[j + i * Q], &c->B[i]);
+                    temp2[i] = o_add(temp2[i], mult, &c->B[i]);
+                }
+            }
+            temp2[m] = 0;
+            for (int j = 0; j < Q; j++) {
+                u64 temp_in = o_reduce_forced(temp[j], &c->mt);
+                u64 mult = o_mult(temp_in, c->bcm_mt[j], &c->mt);
+                temp2[m] = o_add(temp2[m], mult, &c->mt);
+            }
+            u64 m_tilde_div_2 = c->mt.value >> 1;
+            u64 r_m_tilde = o_mult(temp2[m], c->inv_prod_q_mt, &c->mt);
+            r_m_tilde = c->mt.value - r_m_tilde;
+            for (int i = 0; i < m; i++) {
+                u64 temp3 = r_m_tilde;
+                if (temp3 >= m_tilde_div_2) {
+                    temp3 = c->B[i].value - c->mt.value;
+                    temp3 = o_add(temp3, r_m_tilde, &c->B[i]);
+                }
+                temp3 = o_mult(temp3, c->prod_q_bsk[i], &c->B[i]);
+                temp3 = o_add(temp2[i], temp3, &c->B[i]);
+                temp2[i] = o_mult(temp3, c->inv_mt_bsk[i], &c->B[i]);
+            }
+            size_t location2 = idx + (size_t) (idy * (m + Q)) * n;
+            for (int i = 0; i < Q; i++)
+                out1[location2 + (size_t) i * n] = temp_[i];
+            for (int i = 0; i < m; i++)
+                out1[location2 + (size_t) (i + Q) * n] = temp2[i];
+        }
+}
+
+/* fast_floor: multiplication.cu:128-272.  in: [3][Q+m][N]; out: [3][Q][N] */
+static void o_fast_floor(const obfv* c, const u64* in, u64* out1)
+{
+    int n = c->n, Q = c->Q, m = c->m;
+    omod tmod;
+    oracle_make_mod(c->t, &tmod);
+#pragma omp parallel for
+    for (int idy = 0; idy < 3; idy++)
+        for (int idx = 0; idx < n; idx++) {
+            size_t location_q = idx + (size_t) (idy * (Q + m)) * n;
+            size_t location_Bsk = location_q + (size_t) Q * n;
+            u64 reg_q[64], reg_Bsk[64], temp[64], temp3[64], temp4[65];
+            for (int i = 0; i < Q; i++) {
+                reg_q[i] = o_mult(in[location_q + (size_t) i * n], tmod.value, &c->q[i]);
+                reg_q[i] = o_mult(reg_q[i], c->inv_punct[i], &c->q[i]);
+            }
+            for (int i = 0; i < m; i++)
+                reg_Bsk[i] = o_mult(in[location_Bsk + (size_t) i * n], tmod.value, &c->B[i]);
+            for (int i = 0; i < m; i++) {
+                temp[i] = 0;
+                for (int j = 0; j < Q; j++) {
+                    u64 mult = o_mult(reg_q[j], c->bcm_bsk[j + i * Q], &c->B[i]);
+                    temp[i] = o_add(temp[i], mult, &c->B[i]);
+                }
+            }
+            for (int i = 0; i < m; i++) {
+                u64 temp2 = o_sub(c->B[i].value, temp[i], &c->B[i]);
+                temp2 = o_add(temp2, reg_Bsk[i], &c->B[i]);
+                reg_Bsk[i] = o_mult(temp2, c->inv_prod_q_bsk[i], &c->B[i]);
+            }
+            for (int i = 0; i < m - 1; i++)
+                temp3[i] = o_mult(reg_Bsk[i], c->inv_punct_B[i], &c->B[i]);
+            for (int i = 0; i < Q; i++) {
+                temp4[i] = 0;
+                for (int j = 0; j < m - 1; j++) {
+                    u64 temp3_ = o_reduce_forced(temp3[j], &c->q[i]);
+                    u64 mult = o_mult(temp3_, c->bcm_q[j + i * (m - 1)], &c->q[i]);
+                    mult = o_reduce_forced(mult, &c->q[i]);
+                    temp4[i] = o_add(temp4[i], mult, &c->q[i]);
+                }
+            }
+            temp4[Q] = 0;
+            for (int j = 0; j < m - 1; j++) {
+                u64 mult = o_mult(temp3[j], c->bcm_msk[j], &c->B[m - 1]);
+                temp4[Q] = o_add(temp4[Q], mult, &c->B[m - 1]);
+            }
+            u64 alpha_sk = o_sub(c->B[m - 1].value, reg_Bsk[m - 1], &c->B[m - 1]);
+            alpha_sk = o_add(alpha_sk, temp4[Q], &c->B[m - 1]);
+            alpha_sk = o_mult(alpha_sk, c->inv_prod_B_msk, &c->B[m - 1]);
+            u64 m_sk_div_2 = c->B[m - 1].value >> 1;
+            for (int i = 0; i < Q; i++) {
+                u64 obase_ = o_reduce_forced(c->B[m - 1].value, &c->q[i]);
+                u64 temp4_ = o_reduce_forced(temp4[i], &c->q[i]);
+                u64 alpha_sk_ = o_reduce_forced(alpha_sk, &c->q[i]);
+                if (alpha_sk > m_sk_div_2) {
+                    u64 inner = o_sub(obase_, alpha_sk_, &c->q[i]);
+                    inner = o_mult(inner, c->prod_B_q[i], &c->q[i]);
+                    temp4[i] = o_add(temp4_, inner, &c->q[i]);
+                } else {
+                    u64 inner = o_sub(c->q[i].value, c->prod_B_q[i], &c->q[i]);
+                    inner = o_mult(inner, alpha_sk_, &c->q[i]);
+                    temp4[i] = o_add(temp4_, inner, &c->q[i]);
+                }
+            }
+            size_t location_out = idx + (size_t) (idy * Q) * n;
+            for (int i = 0; i < Q; i++)
+                out1[location_out + (size_t) i * n] = temp4[i];
+        }
+}
+
+/* multiply_bfv: bfv/operator.cu:336-430 */
+void oracle_bfv_multiply(const obfv* c, const u64* in1, const u64* in2, u64* out)
+{
+    int n = c->n, Q = c->Q, m = c->m, W = Q + m;
+    u64* temp1 = (u64*) malloc(sizeof(u64) * (size_t) 4 * W * n);
+    u64* temp2 = (u64*) malloc(sizeof(u64) * (size_t) 3 * W * n);
+    o_fast_convertion(c, in1, in2, temp1);
+#pragma omp parallel for schedule(dynamic)
+    for (int z = 0; z < 4 * W; z++) {
+        int pr = z % W;
+        const omod* md = pr < Q ? &c->q[pr] : &c->B[pr - Q];
+        oracle_ntt(temp1 + (size_t) z * n, c->fwd + (size_t) pr * n, md->value, c->n_power);
+    }
+    /* cross_multiplication over the merged base: multiplication.cu:102-126 */
+    size_t comp = (size_t) W * n;
+    const u64 *a = temp1, *b = temp1 + 2 * comp;
+    for (int y = 0; y < W; y++) {
+        const omod* md = y < Q ? &c->q[y] : &c->B[y - Q];
+        for (int idx = 0; idx < n; idx++) {
+            size_t loc = (size_t) y * n + idx;
+            u64 o0 = o_mult(a[loc], b[loc], md);
+            u64 o10 = o_mult(a[loc], b[loc + comp], md);
+            u64 o11 = o_mult(a[loc + comp], b[loc], md);
+            u64 o2 = o_mult(a[loc + comp], b[loc + comp], md);
+            temp2[loc] = o0;
+            temp2[loc + comp] = o_add(o10, o11, md);
+            temp2[loc + 2 * comp] = o2;
+        }
+    }
+#pragma omp parallel for schedule(dynamic)
+    for (int z = 0; z < 3 * W; z++) {
+        int pr = z % W;
+        const omod* md = pr < Q ? &c->q[pr] : &c->B[pr - Q];
+        oracle_intt(temp2 + (size_t) z * n, c->inv + (size_t) pr * n, md->value, c->n_power);
+    }
+    o_fast_floor(c, temp2, out);
+    free(temp1);
+    free(temp2);
+}
+
+/* relinearize_seal_method_inplace (bfv/operator.cu:505-590) and
+ * relinearize_external_product_method2_inplace (:592-671).  ct: [3][Q][N]
+ * coefficient domain, in place.  Kernels: cipher_broadcast_kernel
+ * (switchkey.cu:11-27), base_conversion_DtoQtilde_relin_kernel (:872-927),
+ * keyswitch_multiply_accumulate_kernel (:61-162), divide_round_lastq_kernel
+ * (:400-437), divide_round_lastq_extended_kernel (:480-543). */
+void oracle_bfv_relinearize(const obfv* c, u64* ct, const u64* key)
+{
+    const octx* k = c->ks;
+    int n = c->n, Q = c->Q, K = c->K, Qp = c->Qp;
+    int d = (K == 1) ? Q : k->dcount[0];
+    const u64* c2 = ct + (size_t) 2 * Q * n;
+    u64* temp1 = (u64*) malloc(sizeof(u64) * (size_t) d * Qp * n);
+    u64* temp2 = (u64*) malloc(sizeof(u64) * (size_t) 2 * Qp * n);
+    if (K == 1) {
+        for (int by = 0; by < Q; by++) /* cipher_broadcast_kernel: mult(1, x, modulus[i]) */
+            for (int idx = 0; idx < n; idx++) {
+                u64 v = c2[(size_t) by * n + idx];
+                for (int i = 0; i < Qp; i++)
+                    temp1[((size_t) by * Qp + i) * n + idx] = o_mult(1, v, &k->mod[i]);
+            }
+    } else {
+        /* the un-levelled tables equal the depth-0 levelled ones (contextpool.cpp:160-191 vs 193-236) */
+        const u64 *bc = k->bc[0], *mi = k->mi[0], *pr = k->pr[0];
+        const int *Ij = k->Ij[0], *Iloc = k->Iloc[0];
+        for (int by = 0; by < d; by++)
+            for (int idx = 0; idx < n; idx++) {
+                int I_j = Ij[by], I_location = Iloc[by], matrix_index = I_location * Qp;
+                u64 partial[20];
+                volatile float r = 0;
+                for (int i = 0; i < I_j; i++) {
+                    u64 temp = c2[(size_t) (I_location + i) * n + idx];
+                    partial[i] = o_mult(temp, mi[I_location + i], &k->mod[I_location + i]);
+                    volatile float div = (float) partial[i];
+                    volatile float mod = (float) k->mod[I_location + i].value;
+                    volatile float quo = div / mod;
+                    r = r + quo;
+                }
+                float rr = roundf(r);
+                u64 r_ = (u64) rr;
+                for (int i = 0; i < Qp; i++) {
+                    u64 temp = 0;
+                    for (int j = 0; j < I_j; j++) {
+                        u64 mult = o_mult(partial[j], bc[j + (i * I_j) + matrix_index], &k->mod[i]);
+                        temp = o_add(temp, mult, &k->mod[i]);
+                    }
+                    u64 r_mul = o_mult(r_, pr[i + by * Qp], &k->mod[i]);
+                    temp1[((size_t) by * Qp + i) * n + idx] = o_sub(temp, r_mul, &k->mod[i]);
+                }
+            }
+    }
+    oracle_ntt_batch(k, temp1, (long long) d * Qp, NULL, Qp, 0);
+    o_keyswitch_mac(k, temp1, key, temp2, d, 0);
+    oracle_ntt_batch(k, temp2, 2 * Qp, NULL, Qp, 1);
+    if (K == 1) {
+        for (int bz = 0; bz < 2; bz++) /* divide_round_lastq_kernel */
+            for (int by = 0; by < Q; by++)
+                for (int idx = 0; idx < n; idx++) {
+                    u64 last_ct = temp2[(size_t) Q * n + (size_t) (Q + 1) * n * bz + idx];
+                    last_ct = o_add(last_ct, k->half[0], &k->mod[Q]);
+                    last_ct = o_reduce_forced(last_ct, &k->mod[by]);
+                    last_ct = o_sub(last_ct, k->half_mod[by], &k->mod[by]);
+                    u64 input_ = temp2[(size_t) by * n + (size_t) (Q + 1) * n * bz + idx];
+                    input_ = o_sub(input_, last_ct, &k->mod[by]);
+                    input_ = o_mult(input_, k->last_q_modinv[by], &k->mod[by]);
+                    size_t o = (size_t) by * n + (size_t) Q * n * bz + idx;
+                    ct[o] = o_add(ct[o], input_, &k->mod[by]);
+                }
+    } else {
+        u64* t3 = (u64*) malloc(sizeof(u64) * (size_t) 2 * Q * n);
+        o_moddown_ext(k, temp2, t3, NULL, 0, 0); /* same recurrence as divide_round_lastq_extended_kernel */
+        oracle_addsub(k, t3, ct, ct, 2, 0, 0);
+        free(t3);
+    }
+    free(temp1);
+    free(temp2);
+}

@@ -189,3 +189,47 @@ class OracleContext:
         acc = np.zeros((2, L + self.K, self.n), dtype=np.uint64)
         lib().oracle_keyswitch_core(self._h, _p(np.ascontiguousarray(coef)), _p(np.ascontiguousarray(key)), _p(acc), depth)
         return acc
+
+
+class BfvOracle:
+    """BFV restatement: BEHZ multiply and un-levelled relinearize (heon_oracle.c, BFV section)."""
+
+    def __init__(self, n_power, primes, Q, K, plain_modulus):
+        L = lib()
+        L.oracle_bfv_create.restype = C.c_void_p
+        L.oracle_bfv_create.argtypes = [C.c_int, u64p, C.c_int, C.c_int, C.c_uint64]
+        L.oracle_bfv_destroy.argtypes = [C.c_void_p]
+        L.oracle_bfv_bsk_count.argtypes = [C.c_void_p]
+        self.n_power, self.n, self.Q, self.K, self.Qp = n_power, 1 << n_power, Q, K, Q + K
+        self.primes = [int(p) for p in primes]
+        self.t = int(plain_modulus)
+        self.method = 1 if K == 1 else 2
+        pr = np.array(self.primes, dtype=np.uint64)
+        self._h = C.c_void_p(L.oracle_bfv_create(n_power, _p(pr), Q, K, C.c_uint64(self.t)))
+        self.bsk = L.oracle_bfv_bsk_count(self._h)
+        b = np.zeros(self.bsk, dtype=np.uint64)
+        L.oracle_bfv_bsk_primes(self._h, _p(b))
+        self.bsk_primes = [int(v) for v in b]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_bfv_destroy(self._h)
+            self._h = None
+
+    def digits(self):
+        return self.Q if self.K == 1 else -(-self.Q // self.K)
+
+    def table(self, which):
+        out = np.zeros(64 * 64, dtype=np.uint64)
+        n = lib().oracle_bfv_table(self._h, which, _p(out))
+        return out[:n].copy()
+
+    def multiply(self, a, b):
+        out = np.zeros((3, self.Q, self.n), dtype=np.uint64)
+        lib().oracle_bfv_multiply(self._h, _p(np.ascontiguousarray(a)), _p(np.ascontiguousarray(b)), _p(out))
+        return out
+
+    def relinearize(self, ct3, key):
+        ct = np.ascontiguousarray(ct3, dtype=np.uint64).copy()
+        lib().oracle_bfv_relinearize(self._h, _p(ct), _p(np.ascontiguousarray(key)))
+        return ct

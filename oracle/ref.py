@@ -182,3 +182,43 @@ def tables_for_refgpu(n_power, primes, Q, K, use_ref_host=None):
         else:
             t["method2"] = [O.method2_tables(primes, Q, K, d) for d in range(Q)]
     return t
+
+
+class RefBfv:
+    """The reference's fast_convertion / fast_floor / cross_multiplication kernels and GPU-NTT,
+    replaying multiply_bfv (bfv/operator.cu:336-430).  BEHZ tables come from the oracle (the
+    reference builds them inside HEContextImpl<BFV>, which cannot be compiled offline); the
+    decrypt-level test pins those tables semantically."""
+
+    def __init__(self, ob):
+        from . import oracle as O
+        L = C.CDLL(GPU_SO)
+        L.refgpu_bfv_create.restype = C.c_void_p
+        self.L, self.ob = L, ob
+        Q, m, n_power = ob.Q, ob.bsk, ob.n_power
+        merged = ob.primes[:Q] + ob.bsk_primes
+        psi, fwd, inv, ninv = O.ntt_tables(merged, n_power)
+        t = [np.ascontiguousarray(ob.table(w)) for w in range(20, 31)]
+        sc = t[10]
+        q = np.array(ob.primes[:Q], dtype=np.uint64)
+        b = np.array(ob.bsk_primes, dtype=np.uint64)
+        L.refgpu_bfv_create.argtypes = [C.c_int, C.c_int, C.c_int, u64p, u64p, C.c_uint64] + [u64p] * 13 + [C.c_uint64, C.c_uint64]
+        self._h = C.c_void_p(L.refgpu_bfv_create(n_power, Q, m, _p(q), _p(b), C.c_uint64(ob.t), _p(fwd), _p(inv), _p(ninv),
+                                                 *[_p(x) for x in t[:10]], C.c_uint64(int(sc[0])), C.c_uint64(int(sc[1]))))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.L.refgpu_bfv_destroy(self._h)
+            self._h = None
+
+    def multiply(self, a, b, out, stream=None):
+        rc = self.L.refgpu_bfv_multiply(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()),
+                                        C.c_void_p(out.data_ptr()), RefGpu._s(stream))
+        if rc:
+            raise RuntimeError(f"reference kernel launch failed: cuda error {rc}")
+
+
+def bfv_relinearize(refgpu, ct, key, stream=None):
+    """relinearize_seal_method_inplace / _external_product_method2_inplace on a RefGpu handle."""
+    refgpu._chk(refgpu.L.refgpu_bfv_relinearize(refgpu._h, C.c_void_p(ct.data_ptr()), C.c_void_p(key.data_ptr()),
+                                                 RefGpu._s(stream)))

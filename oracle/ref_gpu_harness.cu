@@ -452,4 +452,158 @@ int refgpu_apply_galois(void* hv, Data64* in, Data64* out, Data64* galois_key, i
     return (int) cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// BFV: multiply_bfv (bfv/operator.cu:336-430) and relinearize (505-671)
+// ---------------------------------------------------------------------------
+struct RefBfv {
+    int n, n_power, Q, m;
+    Modulus64 *ibase, *obase, *merged;
+    Root64 *ntt, *intt;
+    Ninverse64* ninv;
+    Modulus64 m_tilde, plain;
+    Data64 inv_prod_q_mod_m_tilde, inv_prod_B_mod_m_sk;
+    Data64 *bcm_bsk, *inv_punct, *bcm_mt, *inv_mt_bsk, *prod_q_bsk, *inv_prod_q_bsk, *bcm_q, *bcm_msk, *inv_punct_B,
+        *prod_B_q;
+    Data64* temp;
+};
+
+void* refgpu_bfv_create(int n_power, int Q, int m, const Data64* q, const Data64* bsk, Data64 plain_modulus,
+                        const Data64* fwd, const Data64* inv, const Data64* ninv, const Data64* bcm_bsk,
+                        const Data64* inv_punct, const Data64* bcm_mt, const Data64* inv_mt_bsk,
+                        const Data64* prod_q_bsk, const Data64* inv_prod_q_bsk, const Data64* bcm_q,
+                        const Data64* bcm_msk, const Data64* inv_punct_B, const Data64* prod_B_q,
+                        Data64 inv_prod_q_mod_m_tilde, Data64 inv_prod_B_mod_m_sk)
+{
+    RefBfv* h = new RefBfv();
+    h->n_power = n_power;
+    h->n = 1 << n_power;
+    h->Q = Q;
+    h->m = m;
+    std::vector<Modulus64> ib, ob, mg;
+    for (int i = 0; i < Q; i++)
+        ib.push_back(Modulus64(q[i]));
+    for (int i = 0; i < m; i++)
+        ob.push_back(Modulus64(bsk[i]));
+    mg = ib;
+    mg.insert(mg.end(), ob.begin(), ob.end());
+    h->ibase = up(ib.data(), ib.size());
+    h->obase = up(ob.data(), ob.size());
+    h->merged = up(mg.data(), mg.size());
+    const int W = Q + m;
+    h->ntt = up(fwd, (size_t) W * h->n);
+    h->intt = up(inv, (size_t) W * h->n);
+    h->ninv = up(ninv, W);
+    h->m_tilde = Modulus64(1ULL << 32);
+    h->plain = Modulus64(plain_modulus);
+    h->inv_prod_q_mod_m_tilde = inv_prod_q_mod_m_tilde;
+    h->inv_prod_B_mod_m_sk = inv_prod_B_mod_m_sk;
+    h->bcm_bsk = up(bcm_bsk, (size_t) m * Q);
+    h->inv_punct = up(inv_punct, Q);
+    h->bcm_mt = up(bcm_mt, Q);
+    h->inv_mt_bsk = up(inv_mt_bsk, m);
+    h->prod_q_bsk = up(prod_q_bsk, m);
+    h->inv_prod_q_bsk = up(inv_prod_q_bsk, m);
+    h->bcm_q = up(bcm_q, (size_t) Q * (m - 1));
+    h->bcm_msk = up(bcm_msk, m - 1);
+    h->inv_punct_B = up(inv_punct_B, m - 1);
+    h->prod_B_q = up(prod_B_q, Q);
+    cudaMalloc(&h->temp, sizeof(Data64) * (size_t) 7 * W * h->n);
+    cudaDeviceSetLimit(cudaLimitStackSize, 2048); // bfv/context.cu sets this for the per-thread arrays
+    return h;
+}
+
+void refgpu_bfv_destroy(void* hv)
+{
+    RefBfv* h = (RefBfv*) hv;
+    cudaFree(h->ibase);
+    cudaFree(h->obase);
+    cudaFree(h->merged);
+    cudaFree(h->ntt);
+    cudaFree(h->intt);
+    cudaFree(h->ninv);
+    cudaFree(h->bcm_bsk);
+    cudaFree(h->inv_punct);
+    cudaFree(h->bcm_mt);
+    cudaFree(h->inv_mt_bsk);
+    cudaFree(h->prod_q_bsk);
+    cudaFree(h->inv_prod_q_bsk);
+    cudaFree(h->bcm_q);
+    cudaFree(h->bcm_msk);
+    cudaFree(h->inv_punct_B);
+    cudaFree(h->prod_B_q);
+    cudaFree(h->temp);
+    delete h;
+}
+
+int refgpu_bfv_multiply(void* hv, Data64* in1, Data64* in2, Data64* out, void* stream)
+{
+    RefBfv* h = (RefBfv*) hv;
+    cudaStream_t stream_ = (cudaStream_t) stream;
+    const int n = h->n, n_power = h->n_power, Q = h->Q, m = h->m, W = Q + m;
+    Data64* temp1_mul = h->temp;
+    Data64* temp2_mul = temp1_mul + ((size_t) 4 * n * W);
+    fast_convertion<<<dim3((n >> 8), 4, 1), 256, 0, stream_>>>(
+        in1, in2, temp1_mul, h->ibase, h->obase, h->m_tilde, h->inv_prod_q_mod_m_tilde, h->inv_mt_bsk,
+        h->prod_q_bsk, h->bcm_bsk, h->bcm_mt, h->inv_punct, n_power, Q, m);
+    gpuntt::ntt_rns_configuration<Data64> cfg_ntt = {.n_power = n_power,
+                                                    .ntt_type = gpuntt::FORWARD,
+                                                    .ntt_layout = gpuntt::PerPolynomial,
+                                                    .reduction_poly = gpuntt::ReductionPolynomial::X_N_plus,
+                                                    .zero_padding = false,
+                                                    .stream = stream_};
+    gpuntt::ntt_rns_configuration<Data64> cfg_intt = {.n_power = n_power,
+                                                     .ntt_type = gpuntt::INVERSE,
+                                                     .ntt_layout = gpuntt::PerPolynomial,
+                                                     .reduction_poly = gpuntt::ReductionPolynomial::X_N_plus,
+                                                     .zero_padding = false,
+                                                     .mod_inverse = h->ninv,
+                                                     .stream = stream_};
+    gpuntt::GPU_NTT_Inplace(temp1_mul, h->ntt, h->merged, cfg_ntt, W * 4, W);
+    cross_multiplication<<<dim3((n >> 8), W, 1), 256, 0, stream_>>>(temp1_mul, temp1_mul + ((size_t) W * 2 * n),
+                                                                   temp2_mul, h->merged, n_power, W);
+    gpuntt::GPU_INTT_Inplace(temp2_mul, h->intt, h->merged, cfg_intt, 3 * W, W);
+    fast_floor<<<dim3((n >> 8), 3, 1), 256, 0, stream_>>>(
+        temp2_mul, out, h->ibase, h->obase, h->plain, h->inv_punct, h->bcm_bsk, h->inv_prod_q_bsk, h->inv_punct_B,
+        h->bcm_q, h->bcm_msk, h->inv_prod_B_mod_m_sk, h->prod_B_q, n_power, Q, m);
+    return (int) cudaGetLastError();
+}
+
+// relinearize_seal_method_inplace / relinearize_external_product_method2_inplace on a RefGpu handle
+// (the Q' chain tables are the same objects as for CKKS; the un-levelled Method-II tables equal depth 0)
+int refgpu_bfv_relinearize(void* hv, Data64* ct, Data64* relin_key, void* stream)
+{
+    RefGpu* h = (RefGpu*) hv;
+    cudaStream_t stream_ = (cudaStream_t) stream;
+    const int n = h->n, n_power = h->n_power, Q = h->Q, Qp = h->Qp;
+    Data64* temp1_relin = h->temp;
+    Data64* temp2_relin = temp1_relin + ((size_t) n * Q * Qp);
+    auto cfg_ntt = cfg_of(h, false, nullptr, stream_);
+    auto cfg_intt = cfg_of(h, true, h->n_inverse, stream_);
+    int d;
+    if (h->method == 1)
+    {
+        d = Q;
+        cipher_broadcast_kernel<<<dim3((n >> 8), Q, 1), 256, 0, stream_>>>(ct + (Q << (n_power + 1)), temp1_relin,
+                                                                          h->modulus, n_power, Qp);
+    }
+    else
+    {
+        RefLevel2& l = h->lvl2[0];
+        d = l.d;
+        base_conversion_DtoQtilde_relin_kernel<<<dim3((n >> 8), d, 1), 256, 0, stream_>>>(
+            ct + (Q << (n_power + 1)), temp1_relin, h->modulus, l.bc, l.mi, l.pr, l.Ij, l.Iloc, n_power, Q, Qp, d);
+    }
+    gpuntt::GPU_NTT_Inplace(temp1_relin, h->ntt_table, h->modulus, cfg_ntt, d * Qp, Qp);
+    keyswitch_multiply_accumulate_kernel<<<dim3((n >> 8), Qp, 1), 256, 0, stream_>>>(
+        temp1_relin, relin_key, temp2_relin, h->modulus, n_power, Qp, d / 4, d % 4);
+    gpuntt::GPU_INTT_Inplace(temp2_relin, h->intt_table, h->modulus, cfg_intt, 2 * Qp, Qp);
+    if (h->method == 1)
+        divide_round_lastq_kernel<<<dim3((n >> 8), Q, 2), 256, 0, stream_>>>(
+            temp2_relin, ct, ct, h->modulus, h->half, h->half_mod, h->last_q_modinv, n_power, Q);
+    else
+        divide_round_lastq_extended_kernel<<<dim3((n >> 8), Q, 2), 256, 0, stream_>>>(
+            temp2_relin, ct, ct, h->modulus, h->half, h->half_mod, h->last_q_modinv, n_power, Qp, Q, h->K);
+    return (int) cudaGetLastError();
+}
+
 } // extern "C"
