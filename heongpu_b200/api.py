@@ -274,6 +274,22 @@ class HEArithmeticOperator:
         ct.cipher_size_, ct.relinearization_required_ = 2, False
         return ct
 
+    def apply_galois_bfv(self, ct, out, galois_key, galois_elt):
+        c = self.context_
+        if galois_elt not in galois_key.device_location_:
+            raise HeonLogicError("Galois key not present!")
+        key = galois_key.device_location_[galois_elt]
+        _check(lib.heon_bfv_apply_galois(c._h, _ptr(ct.data), ct.stride, _ptr(out.data), out.stride, _ptr(key),
+                                         galois_elt, ct.batch, _stream()))
+        out.cipher_size_ = 2
+        return out
+
+    def rotate_rows_bfv(self, ct, out, galois_key, shift):
+        return self.apply_galois_bfv(ct, out, galois_key, lib.heon_steps_to_galois_elt(shift, self.context_.n, 3))
+
+    def rotate_columns_bfv(self, ct, out, galois_key):
+        return self.apply_galois_bfv(ct, out, galois_key, 2 * self.context_.n - 1)
+
     def mod_drop_inplace(self, ct):
         c = self.context_
         _check(lib.heon_ckks_mod_drop_inplace(c._h, _ptr(ct.data), ct.stride, ct.cipher_size_, ct.depth_, ct.batch, _stream()))

@@ -253,6 +253,22 @@ int heon_bfv_relinearize(heon_context_t ctx, uint64_t* ct, long long cs, const u
     });
 }
 
+int heon_bfv_apply_galois(heon_context_t ctx, const uint64_t* in, long long is, uint64_t* out, long long os,
+                          const uint64_t* galois_key, uint32_t galois_elt, int batch, void* stream)
+{
+    return guarded([&] {
+        if (!ctx || !in || !out || !galois_key || in == out)
+            throw std::invalid_argument("invalid buffers");
+        const Context& c = ctx->c;
+        need_device(c);
+        if (c.scheme != SCHEME_BFV)
+            throw std::invalid_argument("not a BFV context");
+        if (batch < 1)
+            throw std::invalid_argument("batch must be positive");
+        op_apply_galois(c, in, is, out, os, galois_key, galois_elt, 0, batch, (cudaStream_t) stream);
+    });
+}
+
 void heon_context_destroy(heon_context_t ctx) { delete ctx; }
 
 int heon_context_info(heon_context_t ctx, heon_info* o)

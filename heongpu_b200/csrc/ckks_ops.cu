@@ -326,14 +326,14 @@ __global__ void __launch_bounds__(256)
                   const u64* __restrict__ c0coef, const PrimeConst* __restrict__ pcs,
                   const u64* __restrict__ half, const u64* __restrict__ half_mod,
                   const TwPair* __restrict__ lqm, unsigned galois_elt, int logn, int Qpl, int L, int Qp0,
-                  int Q0, int K)
+                  int Q0, int K, long long c0_bs)
 {
     const int idx = blockIdx.x * 256 + threadIdx.x;
     const long long bz = blockIdx.y >> 1;
     const int c = blockIdx.y & 1;
     const u64* pin = in + (((bz * 2 + c) * Qpl) << logn) + idx;
     u64* pout = out + bz * out_bs + ((long long) (c * L) << logn);
-    const u64* c0 = PERMUTE ? c0coef + ((bz * 2 * L) << logn) + idx : nullptr;
+    const u64* c0 = PERMUTE ? c0coef + bz * c0_bs + idx : nullptr;
 #define HEON_MD(n)                                                                                 \
     case n:                                                                                        \
         moddown_body<n, PERMUTE>(pin, pout, c0, pcs, half, half_mod, lqm, galois_elt, idx, c, logn, L, \
@@ -566,7 +566,7 @@ static void moddown_add(const Context& c, u64* acc, u64* tmp, const u64* ct_in, 
             LaunchScope scope(KC_MODDOWN, st);
             k_moddown_ext<false><<<g, 256, 0, st>>>(acc, tmp, 2 * L * N, nullptr, c.d_pc, c.d_half,
                                                 c.d_half_mod, c.d_lqm_pair, 0, c.logn, Qpl, L,
-                                                c.Qp, c.Q_size, K);
+                                                c.Qp, c.Q_size, K, 0);
         }
         check_launch();
         launch_ntt(c, tmp, tmp, (long long) batch * 2 * L, range_primes(0, L), false, st);
@@ -629,7 +629,7 @@ void op_bfv_relinearize(const Context& c, u64* ct, long long ct_bs, const u64* r
         LaunchScope scope(KC_MODDOWN, st);
         k_moddown_ext<false><<<g, 256, 0, st>>>(acc.w(), tmp.w(), 2 * L * N, nullptr, c.d_pc, c.d_half,
                                                 c.d_half_mod, c.d_lqm_pair, 0, c.logn, Qpl, L, c.Qp,
-                                                c.Q_size, K);
+                                                c.Q_size, K, 0);
     }
     check_launch();
     dim3 g2(c.n >> 8, L, batch * 2);
@@ -701,30 +701,42 @@ void op_mod_drop(const Context& c, const u64* in, long long in_bs, u64* out, lon
 }
 
 // out = automorphism_g(in) key-switched back to the original key.
-// reference: ckks/operator.cu:1422-1559 (Method I), 1561-1720 (Method II)
+// CKKS (ciphertexts in the NTT domain): ckks/operator.cu:1422-1559 (Method I), 1561-1720 (II).
+// BFV  (ciphertexts in the coefficient domain, depth 0): bfv/operator.cu:771-973
+//       -- the same pipeline without the leading INTT and the trailing NTT.
 void op_apply_galois(const Context& c, const u64* in, long long in_bs, u64* out, long long out_bs,
                      const u64* galois_key, unsigned galois_elt, int depth, int batch,
                      cudaStream_t st)
 {
     check_depth(c, depth);
+    const bool coeff = c.scheme == SCHEME_BFV;
+    if (coeff && depth != 0)
+        throw std::invalid_argument("BFV ciphertexts have no levels");
     const int L = c.Q_size - depth, K = c.P_size, Qpl = L + K;
     const long long N = c.n;
-    Scratch coef((size_t) batch * 2 * L * N * 8, st);
-    launch_ntt_strided_copy(c, in, in_bs, coef.w(), 2 * L, batch, range_primes(0, L), true, st);
+    Scratch coef(coeff ? 8 : (size_t) batch * 2 * L * N * 8, st);
+    const u64* cp = in;
+    long long cbs = in_bs;
+    if (!coeff)
+    {
+        launch_ntt_strided_copy(c, in, in_bs, coef.w(), 2 * L, batch, range_primes(0, L), true, st);
+        cp = coef.w();
+        cbs = 2 * L * N;
+    }
     Scratch tmp(ks_tmp_words(c, depth, batch) * 8, st);
     Scratch acc((size_t) batch * 2 * Qpl * N * 8, st);
-    keyswitch_core(c, coef.w() + (long long) L * N, 2 * L * N, galois_key, tmp.w(), acc.w(), depth,
-                   batch, st);
+    keyswitch_core(c, cp + (long long) L * N, cbs, galois_key, tmp.w(), acc.w(), depth, batch, st);
     launch_ntt(c, acc.w(), acc.w(), (long long) batch * 2 * Qpl, level_primes(L, K, depth), true, st);
     dim3 g(c.n >> 8, batch * 2);
     {
         LaunchScope scope(KC_MODDOWN, st);
-        k_moddown_ext<true><<<g, 256, 0, st>>>(acc.w(), out, out_bs, coef.w(), c.d_pc, c.d_half,
+        k_moddown_ext<true><<<g, 256, 0, st>>>(acc.w(), out, out_bs, cp, c.d_pc, c.d_half,
                                            c.d_half_mod, c.d_lqm_pair, galois_elt, c.logn, Qpl,
-                                           L, c.Qp, c.Q_size, K);
+                                           L, c.Qp, c.Q_size, K, cbs);
     }
     check_launch();
-    launch_ntt_strided(c, out, out_bs, 2 * L, 0, batch, range_primes(0, L), false, st);
+    if (!coeff)
+        launch_ntt_strided(c, out, out_bs, 2 * L, 0, batch, range_primes(0, L), false, st);
 }
 
 } // namespace heon

@@ -185,6 +185,13 @@ int heon_bfv_multiply(heon_context_t ctx, const uint64_t* a, long long a_stride,
 int heon_bfv_relinearize(heon_context_t ctx, uint64_t* ct, long long ct_stride, const uint64_t* relin_key,
                          int batch, void* stream);
 
+/* ---- HEOperator<BFV>::apply_galois_method_I / _II (bfv/operator.cu:771-973),
+ *      rotate_rows (galois element from heon_steps_to_galois_elt(shift, N, 3)) and
+ *      rotate_columns (galois element 2N-1).  in, out: [2][Q][N] coefficient domain. */
+int heon_bfv_apply_galois(heon_context_t ctx, const uint64_t* in, long long in_stride, uint64_t* out,
+                          long long out_stride, const uint64_t* galois_key, uint32_t galois_elt, int batch,
+                          void* stream);
+
 /* Per-kernel-class CUDA-event profiler (used by bench.py for the roofline
  * line): begin() arms it, end() synchronises the device and returns, per
  * class, the summed device time in ms and the launch count; the return value

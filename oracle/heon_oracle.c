@@ -1288,3 +1288,19 @@ void oracle_bfv_relinearize(const obfv* c, u64* ct, const u64* key)
     free(temp1);
     free(temp2);
 }
+
+/* apply_galois_method_I / _II for BFV: bfv/operator.cu:771-973.  Kernels:
+ * bfv_duplicate_kernel (switchkey.cu:1592-1619: c0 copied, c1 reduce_forced into every
+ * prime of Q') or base_conversion_DtoQtilde_relin_kernel, NTT, MAC, INTT,
+ * divide_round_lastq_permute_bfv_kernel (:1720-1813, the un-levelled twin of the CKKS
+ * kernel restated in o_moddown_ext).  in, out: [2][Q][N] coefficient domain. */
+void oracle_bfv_apply_galois(const obfv* c, const u64* in, u64* out, const u64* key, int galois_elt)
+{
+    const octx* k = c->ks;
+    int n = c->n, Q = c->Q, Qp = c->Qp;
+    u64* acc = (u64*) malloc(sizeof(u64) * (size_t) 2 * Qp * n);
+    o_keyswitch_core(k, in + (size_t) Q * n, key, acc, 0);
+    oracle_ntt_batch(k, acc, 2 * Qp, NULL, Qp, 1);
+    o_moddown_ext(k, acc, out, in, galois_elt, 0);
+    free(acc);
+}

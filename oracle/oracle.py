@@ -233,3 +233,9 @@ class BfvOracle:
         ct = np.ascontiguousarray(ct3, dtype=np.uint64).copy()
         lib().oracle_bfv_relinearize(self._h, _p(ct), _p(np.ascontiguousarray(key)))
         return ct
+
+    def apply_galois(self, ct2, key, galois_elt):
+        ct = np.ascontiguousarray(ct2, dtype=np.uint64)
+        out = np.zeros_like(ct)
+        lib().oracle_bfv_apply_galois(self._h, _p(ct), _p(out), _p(np.ascontiguousarray(key)), int(galois_elt))
+        return out

@@ -222,3 +222,9 @@ def bfv_relinearize(refgpu, ct, key, stream=None):
     """relinearize_seal_method_inplace / _external_product_method2_inplace on a RefGpu handle."""
     refgpu._chk(refgpu.L.refgpu_bfv_relinearize(refgpu._h, C.c_void_p(ct.data_ptr()), C.c_void_p(key.data_ptr()),
                                                  RefGpu._s(stream)))
+
+
+def bfv_apply_galois(refgpu, a, out, key, galois_elt, stream=None):
+    """apply_galois_method_I / _II of the BFV operator on a RefGpu handle."""
+    refgpu._chk(refgpu.L.refgpu_bfv_apply_galois(refgpu._h, C.c_void_p(a.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                  C.c_void_p(key.data_ptr()), int(galois_elt), RefGpu._s(stream)))

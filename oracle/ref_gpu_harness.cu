@@ -606,4 +606,40 @@ int refgpu_bfv_relinearize(void* hv, Data64* ct, Data64* relin_key, void* stream
     return (int) cudaGetLastError();
 }
 
+// apply_galois_method_I / _II (bfv/operator.cu:771-973) on a RefGpu handle
+int refgpu_bfv_apply_galois(void* hv, Data64* in, Data64* out, Data64* galois_key, int galois_elt, void* stream)
+{
+    RefGpu* h = (RefGpu*) hv;
+    cudaStream_t stream_ = (cudaStream_t) stream;
+    const int n = h->n, n_power = h->n_power, Q = h->Q, Qp = h->Qp;
+    Data64* temp0_rotation = h->temp;
+    Data64* temp1_rotation = temp0_rotation + ((size_t) 2 * n * Q);
+    Data64* temp2_rotation = temp1_rotation + ((size_t) n * Q * Qp);
+    auto cfg_ntt = cfg_of(h, false, nullptr, stream_);
+    auto cfg_intt = cfg_of(h, true, h->n_inverse, stream_);
+    int d;
+    if (h->method == 1)
+    {
+        d = Q;
+        bfv_duplicate_kernel<<<dim3((n >> 8), Q, 2), 256, 0, stream_>>>(in, temp0_rotation, temp1_rotation,
+                                                                       h->modulus, n_power, Qp);
+    }
+    else
+    {
+        RefLevel2& l = h->lvl2[0];
+        d = l.d;
+        global_memory_replace_kernel<<<dim3((n >> 8), Q, 1), 256, 0, stream_>>>(in, temp0_rotation, n_power);
+        base_conversion_DtoQtilde_relin_kernel<<<dim3((n >> 8), d, 1), 256, 0, stream_>>>(
+            in + (Q << n_power), temp1_rotation, h->modulus, l.bc, l.mi, l.pr, l.Ij, l.Iloc, n_power, Q, Qp, d);
+    }
+    gpuntt::GPU_NTT_Inplace(temp1_rotation, h->ntt_table, h->modulus, cfg_ntt, d * Qp, Qp);
+    keyswitch_multiply_accumulate_kernel<<<dim3((n >> 8), Qp, 1), 256, 0, stream_>>>(
+        temp1_rotation, galois_key, temp2_rotation, h->modulus, n_power, Qp, d / 4, d % 4);
+    gpuntt::GPU_INTT_Inplace(temp2_rotation, h->intt_table, h->modulus, cfg_intt, 2 * Qp, Qp);
+    divide_round_lastq_permute_bfv_kernel<<<dim3((n >> 8), Q, 2), 256, 0, stream_>>>(
+        temp2_rotation, temp0_rotation, out, h->modulus, h->half, h->half_mod, h->last_q_modinv, galois_elt,
+        n_power, Qp, Q, h->K);
+    return (int) cudaGetLastError();
+}
+
 } // extern "C"

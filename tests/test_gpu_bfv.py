@@ -76,3 +76,27 @@ def test_bfv_bit_exact_vs_reference_kernels(name):
     R.bfv_relinearize(rg, rc, dkey)
     torch.cuda.synchronize()
     assert torch.equal(Cc.data[0, :2], rc[:2]), "BFV relinearize differs from the reference kernels"
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["bfv_n12_I", "bfv_n12_II", "bfv_n15_II"])
+def test_bfv_rotate_vs_oracle_and_reference_kernels(name):
+    from heongpu_b200 import api
+    ob, oc, a, b, key = _inputs(name, 2)
+    ctx = bfv_gpu_ctx(name)
+    rb, rg = _ref_handles(name)
+    op = api.HEArithmeticOperator(ctx)
+    dkey = to_dev(key)
+    for elt in (api.lib.heon_steps_to_galois_elt(1, ob.n, 3), api.lib.heon_steps_to_galois_elt(-2, ob.n, 3), 2 * ob.n - 1):
+        gk = api.Galoiskey(ctx, {elt: dkey})
+        A = api.Ciphertext(ctx, to_dev(a))
+        out = api.Ciphertext(ctx, torch.zeros(2, 2, ob.Q, ob.n, dtype=torch.int64, device="cuda"))
+        op.apply_galois_bfv(A, out, gk, elt)
+        got = to_host(out.data)
+        if ob.n <= 8192:
+            for bi in range(2):
+                assert np.array_equal(got[bi], ob.apply_galois(a[bi], key, elt))
+        ra, ro = to_dev(a[0]), torch.zeros(2, ob.Q, ob.n, dtype=torch.int64, device="cuda")
+        R.bfv_apply_galois(rg, ra, ro, dkey, elt)
+        torch.cuda.synchronize()
+        assert torch.equal(out.data[0], ro), "BFV rotation differs from the reference kernels"
