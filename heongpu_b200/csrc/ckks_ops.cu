@@ -9,6 +9,7 @@
 // arithmetic uses the reference's Barrett sequence (modarith.cuh), so stored
 // words are identical to the reference's.
 #include "modarith.cuh"
+#include "ntt_core.cuh"
 #include "ops.hpp"
 
 namespace heon {
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(256)
 template <int IJ>
 __device__ __forceinline__ void modup2_body(const u64* __restrict__ pc_in, u64* __restrict__ po,
                                             const PrimeConst* __restrict__ pcs,
-                                            const u64* __restrict__ base_change,
+                                            const TwPair* __restrict__ base_change,
                                             const TwPair* __restrict__ mi_inv,
                                             const u64* __restrict__ rprod, int I_loc, int dg, int d,
                                             int logn, int Qpl, int L, int depth)
@@ -171,12 +172,19 @@ __device__ __forceinline__ void modup2_body(const u64* __restrict__ pc_in, u64* 
         }
         else
         {
+            // sum_j partial_j * M_{j,k}: one Shoup product per term (constant multiplier with
+            // its companion word, any 64-bit operand allowed), lazily in [0,4p)
             const PrimeConst pk = pcs[level_prime(k, L, depth)];
-            u64 lo = 0, hi = 0;
+            const u64 p4 = 4 * pk.p, np = 0 - pk.p;
+            u64 acc = 0;
 #pragma unroll
             for (int j = 0; j < IJ; ++j)
-                mac128(lo, hi, partial[j], base_change[j + k * IJ + matrix_index]);
-            res = mod_sub(reduce_u128(lo, hi, pk), rp[k], pk.p);
+            {
+                const TwPair m = ld_tw(base_change + j + k * IJ + matrix_index);
+                acc = csub(acc + shoup_lazy_ptx(partial[j], m.w, m.ws, np), p4);
+            }
+            acc = csub(csub(acc, 2 * pk.p), pk.p);
+            res = mod_sub(acc, rp[k], pk.p);
         }
         po[(long long) k << logn] = res;
     }
@@ -184,7 +192,7 @@ __device__ __forceinline__ void modup2_body(const u64* __restrict__ pc_in, u64* 
 
 __global__ void __launch_bounds__(256)
     k_modup2(const u64* __restrict__ coef, long long coef_bs, u64* __restrict__ out,
-             const PrimeConst* __restrict__ pcs, const u64* __restrict__ base_change,
+             const PrimeConst* __restrict__ pcs, const TwPair* __restrict__ base_change,
              const TwPair* __restrict__ mi_inv, const u64* __restrict__ rprod,
              const int* __restrict__ I_j_, const int* __restrict__ I_loc_, int logn, int d, int Qpl,
              int L, int depth)
@@ -509,7 +517,7 @@ static int keyswitch_core(const Context& c, const u64* coef, long long coef_bs, 
         dim3 g(c.n >> 8, d, batch);
         {
             LaunchScope scope(KC_MODUP2, st);
-            k_modup2<<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_pc, t.d_base_change, t.d_mi_inv_pair,
+            k_modup2<<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_pc, t.d_base_change_pair, t.d_mi_inv_pair,
                                      t.d_rprod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth);
         }
         check_launch();

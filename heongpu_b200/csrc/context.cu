@@ -370,6 +370,19 @@ void upload_tables(Context& c)
             for (size_t i = 0; i < t.mi_inv.size(); ++i) // digit primes are q_i (same index at every depth)
                 mp.push_back(TwPair{t.mi_inv[i], shoup(t.mi_inv[i], c.mod[i].value)});
             t.d_mi_inv_pair = upload(mp);
+            // base_change layout [digit][k over Q'_l][i in digit]: Shoup word for target prime t_k
+            std::vector<TwPair> bp;
+            {
+                size_t o = 0;
+                for (int l = 0; l < t.d; ++l)
+                    for (int k = 0; k < Ql; ++k)
+                    {
+                        const u64 tk = c.mod[level_prime(k, L, depth)].value;
+                        for (int i = 0; i < t.I_j[l]; ++i, ++o)
+                            bp.push_back(TwPair{t.base_change[o], shoup(t.base_change[o], tk)});
+                    }
+            }
+            t.d_base_change_pair = upload(bp);
             std::vector<u64> rp((size_t) (K + 1) * t.d * Ql);
             for (int r = 0; r <= K; ++r)
                 for (int dg = 0; dg < t.d; ++dg)
@@ -418,6 +431,7 @@ Context::~Context()
         cudaFree(t.d_mi_inv);
         cudaFree(t.d_prod);
         cudaFree(t.d_mi_inv_pair);
+        cudaFree(t.d_base_change_pair);
         cudaFree(t.d_rprod);
         cudaFree(t.d_I_j);
         cudaFree(t.d_I_loc);

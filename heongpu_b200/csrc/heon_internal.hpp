@@ -48,6 +48,7 @@ struct LevelTablesII {
     u64* d_mi_inv = nullptr;
     u64* d_prod = nullptr;
     TwPair* d_mi_inv_pair = nullptr; // mi_inv with Shoup words
+    TwPair* d_base_change_pair = nullptr; // base_change with Shoup words (for the target prime)
     u64* d_rprod = nullptr; // [r = 0..K][digit][k]: r * prod mod t_k
     int* d_I_j = nullptr;
     int* d_I_loc = nullptr;

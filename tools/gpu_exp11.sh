@@ -1,0 +1,6 @@
+#!/bin/bash
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python bench.py --workload C3_II --steps 10 --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('C3_II value',round(d['value'],1),'e2e',round(d['e2e']['value'],1))
+for k in d['kernels']: print('   %-18s ms/op %.4f share %.3f'%(k['kernel'],k['ms_per_op'],k['share']))"
