@@ -297,10 +297,10 @@ void upload_tables(Context& c)
         pcs[i].fin_shift = pcs[i].bits - 25;
         pcs[i].fin_m = (unsigned) ((((u128) 1) << (pcs[i].bits + 31)) / p);
         pcs[i].nc_ok = pcs[i].bits <= 57 ? 1u : 0u;
-        // measured on B200 (tools/microbench2.cu, SMSP cycles per warp-butterfly): integer VAR 2 30.9,
-        // FP64-quotient VAR 3 24.1, VAR 4 31.5 -> the FP64 pipe only pays off where no per-stage
-        // correction is needed (p <= 46 bits); HEON_NTT_FP64=2 also enables VAR 4 for 47..50 bits
-        pcs[i].fp_var = !c.use_fp64 ? 0u : pcs[i].bits <= 46 ? 3u : (c.use_fp64 >= 2 && pcs[i].bits <= 50) ? 4u : 0u;
+        // measured on B200 (tools/microbench2.cu, microbench3.cu; SMSP cycles per warp-butterfly):
+        // integer VAR 2 30.9, all-FP64 VAR 3 16.3, VAR 4 (X reduced every other stage) 19.4
+        pcs[i].fp_var = !c.use_fp64 ? 0u : pcs[i].bits <= 47 ? 3u : pcs[i].bits <= 50 ? 4u : 0u;
+        pcs[i].pinv = 1.0 / (double) p;
         pcs[i].pad_ = 0;
         for (int j = 0; j < N; ++j)
         {
@@ -308,8 +308,10 @@ void upload_tables(Context& c)
             fwd[o].w = c.ntt_table[o];
             if (pcs[i].fp_var)
             {
-                // RN(w/p): both operands are exact doubles (< 2^50), IEEE division rounds once
-                const double winv = (double) c.ntt_table[o] / (double) p;
+                // {w, RN(w/p)} as doubles: both operands are exact (< 2^50), IEEE division rounds once
+                const double wd = (double) c.ntt_table[o];
+                const double winv = wd / (double) p;
+                std::memcpy(&fwd[o].w, &wd, 8);
                 std::memcpy(&fwd[o].ws, &winv, 8);
             }
             else

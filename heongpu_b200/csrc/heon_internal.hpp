@@ -30,8 +30,9 @@ struct PrimeConst {
     unsigned fin_shift; // bits - 25
     unsigned bits; // bit length of p
     unsigned nc_ok; // 1 if p <= 57 bits: butterflies may skip every per-stage correction
-    unsigned fp_var; // 0: integer quotient; 3 / 4: forward twiddles carry RN(w/p), use VAR 3 / 4
+    unsigned fp_var; // 0: integer butterflies; 3 / 4: forward twiddles are doubles {w, RN(w/p)}, use VAR 3 / 4
     unsigned pad_;
+    double pinv; // RN(1/p) (FP64 variants)
 };
 
 // Method-II (hybrid, K > 1) level tables; one entry per depth.

@@ -46,6 +46,7 @@ struct MapContig {
         aux = 0;
     }
     static constexpr bool kXform = false;
+    static constexpr bool kLazyIn = false;
     __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&, int) const { return x; }
 };
 
@@ -61,6 +62,7 @@ struct MapScatter {
         aux = 0;
     }
     static constexpr bool kXform = false;
+    static constexpr bool kLazyIn = false;
     __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&, int) const { return x; }
 };
 
@@ -81,6 +83,7 @@ struct MapStrided {
         aux = 0;
     }
     static constexpr bool kXform = false;
+    static constexpr bool kLazyIn = false;
     __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&, int) const { return x; }
 };
 
@@ -103,6 +106,7 @@ struct MapStridedCopy {
         aux = 0;
     }
     static constexpr bool kXform = false;
+    static constexpr bool kLazyIn = false;
     __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&, int) const { return x; }
 };
 
@@ -129,6 +133,7 @@ struct MapModUpI {
         aux = pcs[i].bits > pcs[prime].bits + 1;
     }
     static constexpr bool kXform = true;
+    static constexpr bool kLazyIn = true; // words in [0,4p)
     const PrimeConst* pcs;
     __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst& pc, int need_reduce) const
     {
@@ -160,6 +165,7 @@ struct MapDivRoundOne {
         aux = 0;
     }
     static constexpr bool kXform = true;
+    static constexpr bool kLazyIn = false;
     __device__ __forceinline__ u64 xform(u64 x, int prime, const PrimeConst& pc, int) const
     {
         x = mod_add(x, half, plast);
@@ -182,7 +188,7 @@ __device__ __forceinline__ void col_pass_body(const Map& map, const u64* in, u64
 {
     constexpr int T = (1 << S) / 16;
     constexpr int C = 256 / T;
-    const BflyConst bc{pc.p, 2 * pc.p, 4 * pc.p, 0 - pc.p};
+    const BflyConst bc = make_bc(pc);
     const int c = threadIdx.x % C;
     const int tt = threadIdx.x / C;
     const int col = tile * C + c;
@@ -197,7 +203,7 @@ __device__ __forceinline__ void col_pass_body(const Map& map, const u64* in, u64
             u64 x = in[(long long) (tt + T * k) * 256 + col];
             if (Map::kXform && first_pass)
                 x = map.xform(x, prime, pc, aux);
-            v[k] = x;
+            v[k] = ct_prep<VAR>(x, bc, Map::kLazyIn);
         }
         ct_round_a<VAR>(v, tw, 0, 0, bc);
         if constexpr (S > 4)
@@ -289,14 +295,14 @@ __device__ __forceinline__ void row_pass_body(const u64* rin, u64* rout, const P
                                               const TwPair* __restrict__ tw, int S1, int r, int tt,
                                               u64* srow)
 {
-    const BflyConst bc{pc.p, 2 * pc.p, 4 * pc.p, 0 - pc.p};
+    const BflyConst bc = make_bc(pc);
     u64 v[16];
     if constexpr (!INV)
     {
 #pragma unroll
         for (int k = 0; k < 16; ++k)
             v[k] = rin[tt + 16 * k];
-        ct_round_a<VAR>(v, tw, S1, r, bc);
+        ct_round_a<VAR, 1>(v, tw, S1, r, bc);
 #pragma unroll
         for (int k = 0; k < 16; ++k)
             srow[tt + 18 * k] = v[k];
@@ -308,7 +314,7 @@ __device__ __forceinline__ void row_pass_body(const u64* rin, u64* rout, const P
             v[k] = t2.x;
             v[k + 1] = t2.y;
         }
-        ct_round_b<8, VAR>(v, tw, S1, r, tt, bc);
+        ct_round_b<8, VAR, 1>(v, tw, S1, r, tt, bc);
 #pragma unroll
         for (int k = 0; k < 16; k += 2)
         {
@@ -405,7 +411,7 @@ __device__ __forceinline__ void row_pass_tma_body(unsigned char* rowp, const Pri
                                                   const TwPair* __restrict__ tw,
                                                   const TwPair* __restrict__ blk, int S1, int r, int tt)
 {
-    const BflyConst bc{pc.p, 2 * pc.p, 4 * pc.p, 0 - pc.p};
+    const BflyConst bc = make_bc(pc);
     u64 v[16];
     unsigned char* lineB = rowp + tt * 128;
     const int sw = tt & 7;
@@ -414,7 +420,7 @@ __device__ __forceinline__ void row_pass_tma_body(unsigned char* rowp, const Pri
 #pragma unroll
         for (int k = 0; k < 16; ++k)
             v[k] = *reinterpret_cast<const u64*>(rowp + k * 128 + ((((tt >> 1) ^ (k & 7)) << 4) | ((tt & 1) << 3)));
-        ct_round_a<VAR>(v, tw, S1, r, bc);
+        ct_round_a<VAR, 1>(v, tw, S1, r, bc);
 #pragma unroll
         for (int k = 0; k < 16; ++k)
             *reinterpret_cast<u64*>(rowp + k * 128 + ((((tt >> 1) ^ (k & 7)) << 4) | ((tt & 1) << 3))) = v[k];
@@ -426,7 +432,7 @@ __device__ __forceinline__ void row_pass_tma_body(unsigned char* rowp, const Pri
             v[2 * c] = t2.x;
             v[2 * c + 1] = t2.y;
         }
-        ct_round_b_lm<VAR>(v, blk, tt, bc);
+        ct_round_b_lm<VAR, 1>(v, blk, tt, bc);
 #pragma unroll
         for (int c = 0; c < 8; ++c)
         {

@@ -18,10 +18,15 @@
 //   VAR 2  no per-stage correction at all: every stage adds at most 4p to the
 //          bound, 4p + 16*4p = 68p < 2^64 needs p <= 57 bits; the single
 //          final reduction uses a 32-bit quotient estimate (PrimeConst::fin_m).
-//   VAR 3  quotient from the FP64 pipe (fshoup, T in [0,2p)), no per-stage
-//          correction; values stay below 36p < 2^52: p <= 46 bits.
-//   VAR 4  quotient from the FP64 pipe, Harvey form [0,4p) < 2^52: p <= 50 bits.
-// For VAR 3/4 the second word of a twiddle pair holds the bits of RN(w/p).
+//   VAR 3  the whole butterfly on the FP64 pipe (fp_mulmod below): words are
+//          integer-valued doubles in balanced form, eight DFMA-class
+//          instructions per butterfly and no integer multiply at all; no
+//          per-stage correction, |v| grows by ~p/2 per stage and must stay
+//          below 2^51: p <= 47 bits.
+//   VAR 4  the same with X reduced on every other stage (three more FP64
+//          instructions), which keeps |v| < 1.7p < 2^51: p <= 50 bits.
+// For VAR 3/4 a twiddle pair holds the doubles {w, RN(w/p)}; the buffer
+// between the column pass and the row pass holds the doubles' bit patterns.
 // Stored words are always canonical, so all variants give identical results.
 #pragma once
 #include "modarith.cuh"
@@ -58,7 +63,21 @@ __device__ __forceinline__ u64 shoup_mul_lazy3(u64 x, u64 w, u64 ws, u64 p)
 struct BflyConst {
     u64 p, p2, p4;
     u64 np; // 2^64 - p
+    double dp, dnp, dpinv; // p, -p, RN(1/p) for the FP64 variants
 };
+
+__device__ __forceinline__ BflyConst make_bc(const PrimeConst& pc)
+{
+    BflyConst c;
+    c.p = pc.p;
+    c.p2 = 2 * pc.p;
+    c.p4 = 4 * pc.p;
+    c.np = 0 - pc.p;
+    c.dp = (double) pc.p;
+    c.dnp = -c.dp;
+    c.dpinv = pc.pinv;
+    return c;
+}
 
 // Hand-scheduled instruction selection for the hot butterflies.  ptxas, left
 // to itself, turns 64-bit additions into IMAD.WIDE (a*1+c) and so loads the
@@ -134,48 +153,63 @@ __device__ __forceinline__ void addsub_ptx(u64& X, u64& Y, u64 T, u64 C)
 #endif
 }
 
-// Shoup product with the quotient taken from the FP64 pipe (primes below 2^50).
-// The multiplier pipe is the bottleneck of the integer butterfly; B200's FP64
-// pipe (64 lanes/clk/SM, idle otherwise) can produce the quotient instead:
-//   yd = (double) Y                    exact for Y < 2^52 (magic-number conversion)
-//   t  = fma(yd, winv, 2^52)           winv = RN(w/p); ONE rounding, to an integer
-//   qh = bits(t) - bits(2^52)          = rint(Y*winv),  |qh - Y*w/p| < 1/2 + Y*2^-53 < 1
-// hence qh is floor(Y*w/p) or that plus one, and
-//   T  = Y*w - (qh-1)*p  in [0,2p)     (two mad.wide.u32 + four mad.lo.u32, mod 2^64)
-// for ANY Y < 2^52.  Everything is exact integer arithmetic once qh is known,
-// so the canonical results are the same as on the integer path.
-__device__ __forceinline__ u64 fshoup(u64 y, u64 w, u64 winv_bits, u64 np)
+// ---------------------------------------------------------------------------
+// FP64-pipe modular arithmetic (primes below 2^50).
+//
+// The multiplier pipe is the bottleneck of the integer butterfly (IMAD.WIDE
+// issues once per ~4 cycles per SM sub-partition on B200) while the FP64 pipe
+// (64 DFMA/clk/SM) idles.  Words are kept as integer-valued doubles in
+// balanced form; with Y, w integers, |Y| < 2^51, 0 <= w < p < 2^50:
+//   q  = rint(Y * RN(w/p))              fma against 1.5*2^52, one rounding
+//   h  = RN(Y*w),  l = fma(Y, w, -h)    l = Y*w - h exactly (error-free product)
+//   r  = fma(q, -p, h)                  h - q*p is an integer below 2^51: exact
+//   T  = r + l = Y*w - q*p              exact, |T| <= p*(1/2 + |Y|*2^-54)
+// Five FP64 instructions and no integer multiply; the butterfly adds two more
+// (X + T, X - T).  Every step is exact integer arithmetic once q is fixed, so
+// canonical results equal the integer path's bit for bit.
+// ---------------------------------------------------------------------------
+#define HEON_FP_MAGIC 6755399441055744.0 /* 1.5 * 2^52 */
+
+__device__ __forceinline__ double u2d(u64 x) { return __longlong_as_double((long long) x); }
+__device__ __forceinline__ u64 d2u(double x) { return (u64) __double_as_longlong(x); }
+
+__device__ __forceinline__ double fp_mulmod(double y, double w, double winv, double np)
 {
-    const double yd = __hiloint2double((int) (0x43300000u | (unsigned) (y >> 32)), (int) (unsigned) y) - 4503599627370496.0;
-    const double t = __fma_rn(yd, __longlong_as_double((long long) winv_bits), 4503599627370496.0);
-    const u64 q = (u64) __double_as_longlong(t) - 0x4330000000000001ull; // rint(Y*winv) - 1
-#ifndef __CUDA_ARCH__
-    return y * w + q * np;
-#else
-    u64 r;
-    asm("{\n\t"
-        ".reg .u32 y0,y1,w0,w1,n0,n1,q0,q1,t0,t1;\n\t"
-        ".reg .u64 tt;\n\t"
-        "mov.b64 {y0,y1}, %1;\n\t"
-        "mov.b64 {w0,w1}, %2;\n\t"
-        "mov.b64 {q0,q1}, %3;\n\t"
-        "mov.b64 {n0,n1}, %4;\n\t"
-        "mul.wide.u32 tt, y0, w0;\n\t"
-        "mad.wide.u32 tt, q0, n0, tt;\n\t"
-        "mov.b64 {t0,t1}, tt;\n\t"
-        "mad.lo.u32 t1, y0, w1, t1;\n\t"
-        "mad.lo.u32 t1, y1, w0, t1;\n\t"
-        "mad.lo.u32 t1, q0, n1, t1;\n\t"
-        "mad.lo.u32 t1, q1, n0, t1;\n\t"
-        "mov.b64 %0, {t0,t1};\n\t"
-        "}"
-        : "=l"(r)
-        : "l"(y), "l"(w), "l"(q), "l"(np));
-    return r;
-#endif
+    const double q = __dsub_rn(__fma_rn(y, winv, HEON_FP_MAGIC), HEON_FP_MAGIC);
+    const double h = __dmul_rn(y, w);
+    const double l = __fma_rn(y, w, -h);
+    const double r = __fma_rn(q, np, h);
+    return __dadd_rn(r, l);
 }
 
-template <int VAR> __device__ __forceinline__ void ct_bfly(u64& X, u64& Y, const TwPair& w, const BflyConst& c)
+// x - rint(x/p)*p: |result| <= p/2 (+1), exact for |x| < 2^52
+__device__ __forceinline__ double fp_reduce(double x, double pinv, double np)
+{
+    const double q = __dsub_rn(__fma_rn(x, pinv, HEON_FP_MAGIC), HEON_FP_MAGIC);
+    return __fma_rn(q, np, x);
+}
+
+// integer word x < 2^52 -> double (exact)
+__device__ __forceinline__ double fp_from_u64(u64 x)
+{
+    return __dsub_rn(__hiloint2double((int) (0x43300000u | (unsigned) (x >> 32)), (int) (unsigned) x),
+                     4503599627370496.0);
+}
+
+// Word as loaded (an integer below 4p) -> working representation of variant VAR.
+// `lazy`: the word may exceed p (fused mod-up); VAR 4 needs |v| <= p on entry.
+template <int VAR> __device__ __forceinline__ u64 ct_prep(u64 x, const BflyConst& c, bool lazy)
+{
+    if (VAR < 3)
+        return x;
+    double d = fp_from_u64(x);
+    if (VAR == 4 && lazy)
+        d = fp_reduce(d, c.dpinv, c.dnp);
+    return d2u(d);
+}
+
+template <int VAR, bool RED = false>
+__device__ __forceinline__ void ct_bfly(u64& X, u64& Y, const TwPair& w, const BflyConst& c)
 {
     if (VAR == 0)
     {
@@ -195,25 +229,30 @@ template <int VAR> __device__ __forceinline__ void ct_bfly(u64& X, u64& Y, const
         const u64 t = shoup_lazy_ptx(Y, w.w, w.ws, c.np);
         addsub_ptx(X, Y, t, c.p4);
     }
-    else if (VAR == 3)
-    {
-        // FP64 quotient, no per-stage correction: +2p per stage, 4p + 16*2p = 36p < 2^52 for p <= 46 bits
-        const u64 t = fshoup(Y, w.w, w.ws, c.np);
-        addsub_ptx(X, Y, t, c.p2);
-    }
     else
     {
-        // FP64 quotient, Harvey form: values in [0,4p) < 2^52 for p < 2^50
-        X = csub(X, c.p2);
-        const u64 t = fshoup(Y, w.w, w.ws, c.np);
-        addsub_ptx(X, Y, t, c.p2);
+        // VAR 3 / 4: FP64 pipe only (see fp_mulmod); VAR 4 reduces X on the stages marked RED
+        double x = u2d(X);
+        if (VAR == 4 && RED)
+            x = fp_reduce(x, c.dpinv, c.dnp);
+        const double t = fp_mulmod(u2d(Y), u2d(w.w), u2d(w.ws), c.dnp);
+        X = d2u(__dadd_rn(x, t));
+        Y = d2u(__dsub_rn(x, t));
     }
 }
 
 // canonical value of a lazy forward word
 template <int VAR> __device__ __forceinline__ u64 ct_finish(u64 x, const BflyConst& c, const PrimeConst& pc)
 {
-    if (VAR == 0 || VAR == 4)
+    if (VAR == 3 || VAR == 4)
+    {
+        double r = fp_reduce(u2d(x), c.dpinv, c.dnp); // [-p/2, p/2]
+        if (r < 0.0)
+            r = __dadd_rn(r, c.dp);
+        // r in [0,p), p < 2^50: the low 52 bits of r + 2^52 are the integer
+        return d2u(__dadd_rn(r, 4503599627370496.0)) & 0x000FFFFFFFFFFFFFull;
+    }
+    if (VAR == 0)
         return csub(csub(x, c.p2), c.p);
     if (VAR == 1)
         return csub(csub(csub(x, c.p4), c.p2), c.p);
@@ -245,7 +284,7 @@ template <int GVAR> __device__ __forceinline__ void gs_bfly(u64& X, u64& Y, cons
 
 // One stage on the 16 registers; butterflies pair k and k + 2^LS, the
 // twiddle changes every 2^(LS+1) registers.
-template <int LS, bool INV, int VAR, int GSTRIDE = 1>
+template <int LS, bool INV, int VAR, int GSTRIDE = 1, bool RED = false>
 __device__ __forceinline__ void stage16(u64 (&v)[16], const TwPair* __restrict__ tw, const BflyConst& c)
 {
 #pragma unroll
@@ -265,21 +304,24 @@ __device__ __forceinline__ void stage16(u64 (&v)[16], const TwPair* __restrict__
             if (INV)
                 gs_bfly<VAR>(v[k], v[k + (1 << LS)], w, c);
             else
-                ct_bfly<VAR>(v[k], v[k + (1 << LS)], w, c);
+                ct_bfly<VAR, RED>(v[k], v[k + (1 << LS)], w, c);
         }
     }
 }
 
 // Round A: the four stages with register strides 8,4,2,1 when the thread
 // holds idx = tt + T*k.  Twiddles do not depend on tt.
-template <int VAR>
+// PH: VAR 4 reduces X on every other stage; PH = 0 gives the pattern -,R,-,R (column pass, whose
+// input is canonical), PH = 1 gives R,-,R,- (row pass: its first stage follows an unreduced or
+// reduced column-pass stage alike).
+template <int VAR, int PH = 0>
 __device__ __forceinline__ void ct_round_a(u64 (&v)[16], const TwPair* __restrict__ tw, int s0, int q,
                                            const BflyConst& c)
 {
-    stage16<3, false, VAR>(v, tw + (1 << (s0 + 0)) + (q << 0), c);
-    stage16<2, false, VAR>(v, tw + (1 << (s0 + 1)) + (q << 1), c);
-    stage16<1, false, VAR>(v, tw + (1 << (s0 + 2)) + (q << 2), c);
-    stage16<0, false, VAR>(v, tw + (1 << (s0 + 3)) + (q << 3), c);
+    stage16<3, false, VAR, 1, PH == 1>(v, tw + (1 << (s0 + 0)) + (q << 0), c);
+    stage16<2, false, VAR, 1, PH == 0>(v, tw + (1 << (s0 + 1)) + (q << 1), c);
+    stage16<1, false, VAR, 1, PH == 1>(v, tw + (1 << (s0 + 2)) + (q << 2), c);
+    stage16<0, false, VAR, 1, PH == 0>(v, tw + (1 << (s0 + 3)) + (q << 3), c);
 }
 
 template <int GVAR>
@@ -322,32 +364,32 @@ __device__ __forceinline__ void gs_round_a_final(u64 (&v)[16], const TwPair* __r
 
 // Round B: the S-4 stages with strides < 16 when the thread holds the 16
 // contiguous indices idx = 16*tt + k.
-template <int S, int VAR>
+template <int S, int VAR, int PH = 0>
 __device__ __forceinline__ void ct_round_b(u64 (&v)[16], const TwPair* __restrict__ tw, int s0, int q,
                                            int tt, const BflyConst& c)
 {
     // pass-stage u = 4..S-1, register stride 2^(S-1-u)
     if constexpr (S >= 5)
-        stage16<S - 5, false, VAR>(v, tw + (1 << (s0 + 4)) + (q << 4) + (tt << (8 - S)), c);
+        stage16<S - 5, false, VAR, 1, PH == 1>(v, tw + (1 << (s0 + 4)) + (q << 4) + (tt << (8 - S)), c);
     if constexpr (S >= 6)
-        stage16<S - 6, false, VAR>(v, tw + (1 << (s0 + 5)) + (q << 5) + (tt << (9 - S)), c);
+        stage16<S - 6, false, VAR, 1, PH == 0>(v, tw + (1 << (s0 + 5)) + (q << 5) + (tt << (9 - S)), c);
     if constexpr (S >= 7)
-        stage16<S - 7, false, VAR>(v, tw + (1 << (s0 + 6)) + (q << 6) + (tt << (10 - S)), c);
+        stage16<S - 7, false, VAR, 1, PH == 1>(v, tw + (1 << (s0 + 6)) + (q << 6) + (tt << (10 - S)), c);
     if constexpr (S >= 8)
-        stage16<S - 8, false, VAR>(v, tw + (1 << (s0 + 7)) + (q << 7) + (tt << (11 - S)), c);
+        stage16<S - 8, false, VAR, 1, PH == 0>(v, tw + (1 << (s0 + 7)) + (q << 7) + (tt << (11 - S)), c);
 }
 
 // Round B of the 256-point row transform with the lane-major twiddle block of
 // this (prime,row): entry e = 2^(u-4)-1+g of lane tt sits at blk[e*16 + tt], so
 // the 16 lanes of a row read 256 contiguous bytes per butterfly group.
-template <int VAR>
+template <int VAR, int PH = 0>
 __device__ __forceinline__ void ct_round_b_lm(u64 (&v)[16], const TwPair* __restrict__ blk, int tt,
                                               const BflyConst& c)
 {
-    stage16<3, false, VAR, 16>(v, blk + 0 * 16 + tt, c);
-    stage16<2, false, VAR, 16>(v, blk + 1 * 16 + tt, c);
-    stage16<1, false, VAR, 16>(v, blk + 3 * 16 + tt, c);
-    stage16<0, false, VAR, 16>(v, blk + 7 * 16 + tt, c);
+    stage16<3, false, VAR, 16, PH == 1>(v, blk + 0 * 16 + tt, c);
+    stage16<2, false, VAR, 16, PH == 0>(v, blk + 1 * 16 + tt, c);
+    stage16<1, false, VAR, 16, PH == 1>(v, blk + 3 * 16 + tt, c);
+    stage16<0, false, VAR, 16, PH == 0>(v, blk + 7 * 16 + tt, c);
 }
 template <int GVAR>
 __device__ __forceinline__ void gs_round_b_lm(u64 (&v)[16], const TwPair* __restrict__ blk, int tt,

@@ -33,16 +33,19 @@ static inline long long __double_as_longlong(double d)
     return v;
 }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 #include "../heongpu_b200/csrc/ntt_core.cuh"
 using namespace heon;
 
 template <int VAR> static void fwd(std::vector<u64>& x, const std::vector<TwPair>& tw, const PrimeConst& pc)
 {
-    const BflyConst bc{pc.p, 2 * pc.p, 4 * pc.p, 0 - pc.p};
+    const BflyConst bc = make_bc(pc);
     for (int col = 0; col < 256; ++col) // column pass, S = 4
     {
         u64 v[16];
-        for (int k = 0; k < 16; ++k) v[k] = x[k * 256 + col];
+        for (int k = 0; k < 16; ++k) v[k] = ct_prep<VAR>(x[k * 256 + col], bc, true);
         ct_round_a<VAR>(v, tw.data(), 0, 0, bc);
         for (int k = 0; k < 16; ++k) x[k * 256 + col] = v[k];
     }
@@ -53,14 +56,14 @@ template <int VAR> static void fwd(std::vector<u64>& x, const std::vector<TwPair
         {
             u64 v[16];
             for (int k = 0; k < 16; ++k) v[k] = x[r * 256 + tt + 16 * k];
-            ct_round_a<VAR>(v, tw.data(), 4, r, bc);
+            ct_round_a<VAR, 1>(v, tw.data(), 4, r, bc);
             for (int k = 0; k < 16; ++k) row[tt + 16 * k] = v[k];
         }
         for (int tt = 0; tt < 16; ++tt)
         {
             u64 v[16];
             for (int k = 0; k < 16; ++k) v[k] = row[16 * tt + k];
-            ct_round_b<8, VAR>(v, tw.data(), 4, r, tt, bc);
+            ct_round_b<8, VAR, 1>(v, tw.data(), 4, r, tt, bc);
             for (int k = 0; k < 16; ++k) x[r * 256 + 16 * tt + k] = ct_finish<VAR>(v[k], bc, pc);
         }
     }
@@ -70,7 +73,7 @@ template <int GVAR>
 static void inv(std::vector<u64>& x, const std::vector<TwPair>& tw, const PrimeConst& pc, const TwPair& ninv,
                 const TwPair& wninv)
 {
-    const BflyConst bc{pc.p, 2 * pc.p, 4 * pc.p, 0 - pc.p};
+    const BflyConst bc = make_bc(pc);
     for (int r = 0; r < 16; ++r) // row pass first
     {
         u64 row[256];
@@ -119,8 +122,8 @@ int main()
         {
             tw[j] = TwPair{pw[bitrev(j, logn)], shoup(pw[bitrev(j, logn)], p)};
             itw[j] = TwPair{ipw[bitrev(j, logn)], shoup(ipw[bitrev(j, logn)], p)};
-            const double winv = (double) tw[j].w / (double) p; // FP64-quotient table format
-            twf[j].w = tw[j].w;
+            const double wd = (double) tw[j].w, winv = wd / (double) p; // FP64 table format {w, RN(w/p)}
+            std::memcpy(&twf[j].w, &wd, 8);
             std::memcpy(&twf[j].ws, &winv, 8);
         }
         PrimeConst pc;
@@ -130,6 +133,7 @@ int main()
         pc.fin_shift = pc.bits - 25;
         pc.fin_m = (unsigned) ((((u128) 1) << (pc.bits + 31)) / p);
         pc.nc_ok = pc.bits <= 57;
+        pc.pinv = 1.0 / (double) p;
         const u64 ni = invmod(N, p), wn = mulmod(itw[1].w, ni, p);
         const TwPair ninv{ni, shoup(ni, p)}, wninv{wn, shoup(wn, p)};
         for (int pattern = 0; pattern < 3; ++pattern)
@@ -159,7 +163,7 @@ int main()
             {
                 if (var == 2 && !pc.nc_ok)
                     continue;
-                if ((var == 3 && pc.bits > 46) || (var == 4 && pc.bits > 50))
+                if ((var == 3 && pc.bits > 47) || (var == 4 && pc.bits > 50))
                     continue;
                 std::vector<u64> x = a;
                 // worst-case lazy input for the fused mod-up: words below 4p are legal inputs
@@ -193,10 +197,11 @@ int main()
             }
         }
     }
-    // FP64-quotient Shoup product: exact for ANY Y < 2^52 (random and edge operands)
-    for (int bits : {30, 40, 46, 49, 50})
+    // FP64 modular product: exact for ANY integer |Y| < 2^51 (random and edge operands)
+    for (int bits : {30, 40, 46, 47, 49, 50})
     {
         const u64 p = largest_ntt_primes(2 * N, bits, 1)[0];
+        const double dp = (double) p;
         u64 s = 777 + bits;
         int bad = 0;
         for (int it = 0; it < 400000; ++it)
@@ -204,20 +209,26 @@ int main()
             s = s * 6364136223846793005ULL + 1442695040888963407ULL;
             u64 w = (it % 7 == 0) ? p - 1 : (it % 11 == 0) ? 1 : (s >> 4) % p;
             s = s * 6364136223846793005ULL + 1442695040888963407ULL;
-            u64 y = s >> 12; // < 2^52
+            u64 y = s >> 13; // < 2^51
             if (it % 5 == 0) y = (y / p) * p + (it % 3) - 1 + (y < p ? p : 0); // multiples of p, +-1
-            if (it % 13 == 0) y = (1ull << 52) - 1 - (it & 7);
-            if (y >= (1ull << 52)) y = (1ull << 52) - 1;
-            const double winv = (double) w / (double) p;
-            u64 wb;
-            std::memcpy(&wb, &winv, 8);
-            const u64 tq = fshoup(y, w, wb, 0 - p);
-            if (!(tq < 2 * p) || tq % p != mulmod(y % p, w, p))
+            if (it % 13 == 0) y = (1ull << 51) - 1 - (it & 7);
+            if (y >= (1ull << 51)) y = (1ull << 51) - 1;
+            const bool neg = (it & 1);
+            const double yd = neg ? -(double) y : (double) y;
+            const double wd = (double) w, winv = wd / dp;
+            const double t = fp_mulmod(yd, wd, winv, -dp);
+            // |T| <= p*(1/2 + |Y|*2^-54) and T == Y*w (mod p)
+            const double lim = dp * (0.5 + (double) y * 0x1p-54) + 1.0;
+            u64 want = mulmod(y % p, w, p);
+            if (neg && want) want = p - want;
+            long long ti = (long long) t;
+            u64 got = (u64) ((ti % (long long) p + (long long) p) % (long long) p);
+            if (!(t <= lim && t >= -lim) || (double) ti != t || got != want)
                 ++bad;
         }
         if (bad)
         {
-            printf("FAIL fshoup bits=%d bad=%d\n", bits, bad);
+            printf("FAIL fp_mulmod bits=%d bad=%d\n", bits, bad);
             ++failures;
         }
     }

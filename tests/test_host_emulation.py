@@ -11,6 +11,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def test_butterfly_variants_on_host():
     exe = os.path.join(tempfile.mkdtemp(), "host_emul")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-I/usr/local/cuda/include", "-D__forceinline__=inline",
-                           "-w", "-o", exe, os.path.join(HERE, "host_emul.cpp")])
+                           "-w", "-ffp-contract=off", "-o", exe, os.path.join(HERE, "host_emul.cpp")])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
