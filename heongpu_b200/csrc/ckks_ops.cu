@@ -77,17 +77,24 @@ __global__ void __launch_bounds__(256)
 // Products are accumulated lazily in 128 bits and reduced once; the result is
 // the canonical residue, identical to the reference's per-term Barrett sum.
 // reference: src/lib/kernel/switchkey.cu:164-285 (Method I), 287-398 (Method II)
+// One thread owns two adjacent coefficients of one limb of one ciphertext.  The key (larger
+// than L2 at the BASELINE sizes) should cross HBM once per batch, not once per ciphertext:
+//  * blockDim = (256/BY, BY): the BY warps-rows of a CTA work on BY ciphertexts of the batch
+//    and read the SAME key words, which the first reader leaves in L1;
+//  * the batch group is the fastest-varying block coordinate, so CTAs that are resident
+//    together share the key tile through L2.
 __global__ void __launch_bounds__(256)
     k_keyswitch_mac(const u64* __restrict__ in, const u64* __restrict__ key, u64* __restrict__ out,
                     const PrimeConst* __restrict__ pcs, int logn, int d, int L, int Qpl, int Qp0,
-                    int depth)
+                    int depth, int batch)
 {
-    const int idx = (blockIdx.x * 256 + threadIdx.x) * 2;
-    const int y = blockIdx.y;
-    const long long bz = blockIdx.z;
+    const int idx = (blockIdx.y * blockDim.x + threadIdx.x) * 2;
+    const int y = blockIdx.z;
+    const long long bz = (long long) blockIdx.x * blockDim.y + threadIdx.y;
+    if (bz >= batch)
+        return;
     const int prime = level_prime(y, L, depth);
     const PrimeConst pc = pcs[prime];
-    const long long N = 1LL << logn;
     const u64* pin = in + ((bz * d * Qpl + y) << logn) + idx;
     const u64* pk = key + ((long long) prime << logn) + idx;
     const long long in_step = (long long) Qpl << logn;
@@ -115,7 +122,6 @@ __global__ void __launch_bounds__(256)
     r1.y = reduce_u128(b1l, b1h, pc);
     *reinterpret_cast<ulonglong2*>(po) = r0;
     *reinterpret_cast<ulonglong2*>(po + ((long long) Qpl << logn)) = r1;
-    (void) N;
 }
 
 // ---------------------------------------------------------------------------
@@ -133,8 +139,14 @@ __global__ void __launch_bounds__(256)
 //   * output limbs that belong to the digit itself equal the input residue
 //     (M_{j,k} = 0 for j != k, partial_k * M_{k,k} = x_k, prod_k = 0) and are
 //     copied.
+//   * when the digit's primes and the target prime are below 2^50 the products run on the
+//     FP64 pipe (fp_mulmod, ntt_core.cuh): five DFMA-class instructions per term instead of
+//     nine integer multiplies; the table then holds the doubles {M, RN(M/t_k)}.
 // All of these are exact, so every output word equals the reference's.
-template <int IJ>
+// One thread converts CW adjacent coefficients (CW = 2: 16-byte loads and stores, the
+// per-target constants and table words are fetched once for both, and the two dependent
+// FP64 chains interleave).
+template <int IJ, int CW>
 __device__ __forceinline__ void modup2_body(const u64* __restrict__ pc_in, u64* __restrict__ po,
                                             const PrimeConst* __restrict__ pcs,
                                             const TwPair* __restrict__ base_change,
@@ -142,54 +154,131 @@ __device__ __forceinline__ void modup2_body(const u64* __restrict__ pc_in, u64* 
                                             const u64* __restrict__ rprod, int I_loc, int dg, int d,
                                             int logn, int Qpl, int L, int depth)
 {
-    u64 x[IJ], partial[IJ];
-    float r = 0;
+    u64 x[IJ][CW], partial[IJ][CW];
+    double pd[IJ][CW];
+    bool dfp = IJ <= 4; // every prime of the digit is FP64-capable (and the lazy sum stays below 2^52)
+    float r[CW];
+#pragma unroll
+    for (int e = 0; e < CW; ++e)
+        r[e] = 0;
 #pragma unroll
     for (int i = 0; i < IJ; ++i)
     {
         const PrimeConst pi = pcs[I_loc + i];
-        x[i] = pc_in[(long long) i << logn];
+        dfp = dfp && pi.fp_var != 0;
+        if (CW == 2)
+        {
+            const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(pc_in + ((long long) i << logn));
+            x[i][0] = t.x;
+            x[i][CW - 1] = t.y;
+        }
+        else
+            x[i][0] = pc_in[(long long) i << logn];
         const TwPair mi = mi_inv[I_loc + i];
-        partial[i] = csub(shoup_mul_lazy(x[i], mi.w, mi.ws, pi.p), pi.p);
-        const float div = __ull2float_rn(partial[i]);
         const float mod = __ull2float_rn(pi.p);
-        r = __fadd_rn(r, __fdiv_rn(div, mod));
+#pragma unroll
+        for (int e = 0; e < CW; ++e)
+        {
+            partial[i][e] = csub(shoup_mul_lazy(x[i][e], mi.w, mi.ws, pi.p), pi.p);
+            const float div = __ull2float_rn(partial[i][e]);
+            r[e] = __fadd_rn(r[e], __fdiv_rn(div, mod));
+        }
     }
-    r = roundf(r);
-    const unsigned r_ = (unsigned) r;
+    const u64* rp[CW];
+#pragma unroll
+    for (int e = 0; e < CW; ++e)
+    {
+        const unsigned r_ = (unsigned) roundf(r[e]);
+        rp[e] = rprod + ((long long) r_ * d + dg) * Qpl;
+    }
+    if (dfp)
+    {
+#pragma unroll
+        for (int i = 0; i < IJ; ++i)
+#pragma unroll
+            for (int e = 0; e < CW; ++e)
+                pd[i][e] = fp_from_u64(partial[i][e]);
+    }
     const int matrix_index = I_loc * Qpl;
-    const u64* rp = rprod + ((long long) r_ * d + dg) * Qpl;
+#pragma unroll 2
     for (int k = 0; k < Qpl; ++k)
     {
-        u64 res;
+        u64 res[CW];
         if (k >= I_loc && k < I_loc + IJ)
         {
-            res = 0;
+#pragma unroll
+            for (int e = 0; e < CW; ++e)
+                res[e] = 0;
 #pragma unroll
             for (int i = 0; i < IJ; ++i)
                 if (k == I_loc + i)
-                    res = x[i];
+                {
+#pragma unroll
+                    for (int e = 0; e < CW; ++e)
+                        res[e] = x[i][e];
+                }
         }
         else
         {
-            // sum_j partial_j * M_{j,k}: one Shoup product per term (constant multiplier with
-            // its companion word, any 64-bit operand allowed), lazily in [0,4p)
-            const PrimeConst pk = pcs[level_prime(k, L, depth)];
-            const u64 p4 = 4 * pk.p, np = 0 - pk.p;
-            u64 acc = 0;
-#pragma unroll
-            for (int j = 0; j < IJ; ++j)
+            const PrimeConst* ppk = pcs + level_prime(k, L, depth);
+            const u64 pkp = ppk->p;
+            if (dfp && ppk->fp_var != 0)
             {
-                const TwPair m = ld_tw(base_change + j + k * IJ + matrix_index);
-                acc = csub(acc + shoup_lazy_ptx(partial[j], m.w, m.ws, np), p4);
+                const double dp = fp_from_u64(pkp), dnp = -dp, dpinv = ppk->pinv;
+                double acc[CW]; // |acc| <= IJ * 0.6p, exact
+#pragma unroll
+                for (int e = 0; e < CW; ++e)
+                    acc[e] = 0.0;
+#pragma unroll
+                for (int j = 0; j < IJ; ++j)
+                {
+                    const TwPair m = ld_tw(base_change + j + k * IJ + matrix_index);
+#pragma unroll
+                    for (int e = 0; e < CW; ++e)
+                        acc[e] = __dadd_rn(acc[e], fp_mulmod(pd[j][e], u2d(m.w), u2d(m.ws), dnp));
+                }
+#pragma unroll
+                for (int e = 0; e < CW; ++e)
+                    res[e] = fp_canon(__dsub_rn(acc[e], fp_from_u64(rp[e][k])), dpinv, dnp, dp);
             }
-            acc = csub(csub(acc, 2 * pk.p), pk.p);
-            res = mod_sub(acc, rp[k], pk.p);
+            else
+            {
+                // sum_j partial_j * M_{j,k}: one Shoup product per term (constant multiplier with
+                // its companion word, any 64-bit operand allowed), lazily in [0,4p)
+                const u64 p4 = 4 * pkp, np = 0 - pkp;
+                u64 acc[CW];
+#pragma unroll
+                for (int e = 0; e < CW; ++e)
+                    acc[e] = 0;
+#pragma unroll
+                for (int j = 0; j < IJ; ++j)
+                {
+                    const TwPair m = ld_tw(base_change + j + k * IJ + matrix_index);
+#pragma unroll
+                    for (int e = 0; e < CW; ++e)
+                        acc[e] = csub(acc[e] + shoup_lazy_ptx(partial[j][e], m.w, m.ws, np), p4);
+                }
+#pragma unroll
+                for (int e = 0; e < CW; ++e)
+                {
+                    acc[e] = csub(csub(acc[e], 2 * pkp), pkp);
+                    res[e] = mod_sub(acc[e], rp[e][k], pkp);
+                }
+            }
         }
-        po[(long long) k << logn] = res;
+        if (CW == 2)
+        {
+            ulonglong2 t;
+            t.x = res[0];
+            t.y = res[CW - 1];
+            *reinterpret_cast<ulonglong2*>(po + ((long long) k << logn)) = t;
+        }
+        else
+            po[(long long) k << logn] = res[0];
     }
 }
 
+template <int CW>
 __global__ void __launch_bounds__(256)
     k_modup2(const u64* __restrict__ coef, long long coef_bs, u64* __restrict__ out,
              const PrimeConst* __restrict__ pcs, const TwPair* __restrict__ base_change,
@@ -197,7 +286,7 @@ __global__ void __launch_bounds__(256)
              const int* __restrict__ I_j_, const int* __restrict__ I_loc_, int logn, int d, int Qpl,
              int L, int depth)
 {
-    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int idx = (blockIdx.x * 256 + threadIdx.x) * CW;
     const int dg = blockIdx.y;
     const long long bz = blockIdx.z;
     const int I_j = I_j_[dg];
@@ -206,25 +295,38 @@ __global__ void __launch_bounds__(256)
     u64* po = out + (((bz * d + dg) * Qpl) << logn) + idx;
 #define HEON_MU2(n)                                                                                \
     case n:                                                                                        \
-        modup2_body<n>(pin, po, pcs, base_change, mi_inv, rprod, I_loc, dg, d, logn, Qpl, L, depth); \
+        modup2_body<n, CW>(pin, po, pcs, base_change, mi_inv, rprod, I_loc, dg, d, logn, Qpl, L, depth); \
         break;
-    switch (I_j)
+    if constexpr (CW == 2)
     {
-        HEON_MU2(1)
-        HEON_MU2(2)
-        HEON_MU2(3)
-        HEON_MU2(4)
-        HEON_MU2(5)
-        HEON_MU2(6)
-        HEON_MU2(7)
-        HEON_MU2(8)
-        HEON_MU2(9)
-        HEON_MU2(10)
-        HEON_MU2(11)
-        HEON_MU2(12)
-        HEON_MU2(13)
-        HEON_MU2(14)
-        HEON_MU2(15)
+        switch (I_j)
+        {
+            HEON_MU2(1)
+            HEON_MU2(2)
+            HEON_MU2(3)
+            HEON_MU2(4)
+        }
+    }
+    else
+    {
+        switch (I_j)
+        {
+            HEON_MU2(1)
+            HEON_MU2(2)
+            HEON_MU2(3)
+            HEON_MU2(4)
+            HEON_MU2(5)
+            HEON_MU2(6)
+            HEON_MU2(7)
+            HEON_MU2(8)
+            HEON_MU2(9)
+            HEON_MU2(10)
+            HEON_MU2(11)
+            HEON_MU2(12)
+            HEON_MU2(13)
+            HEON_MU2(14)
+            HEON_MU2(15)
+        }
     }
 #undef HEON_MU2
 }
@@ -514,21 +616,32 @@ static int keyswitch_core(const Context& c, const u64* coef, long long coef_bs, 
     {
         const LevelTablesII& t = c.lvl2[depth];
         d = t.d;
-        dim3 g(c.n >> 8, d, batch);
+        // two coefficients per thread when the digits are short and the buffers 16-byte aligned
+        const bool wide = K <= 4 && c.n >= 512 && (coef_bs & 1) == 0 &&
+                          ((reinterpret_cast<uintptr_t>(coef) | reinterpret_cast<uintptr_t>(tmp)) & 15) == 0;
+        dim3 g(wide ? c.n >> 9 : c.n >> 8, d, batch);
         {
             LaunchScope scope(KC_MODUP2, st);
-            k_modup2<<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_pc, t.d_base_change_pair, t.d_mi_inv_pair,
-                                     t.d_rprod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth);
+            if (wide)
+                k_modup2<2><<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_pc, t.d_base_change_pair, t.d_mi_inv_pair,
+                                            t.d_rprod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth);
+            else
+                k_modup2<1><<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_pc, t.d_base_change_pair, t.d_mi_inv_pair,
+                                            t.d_rprod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth);
         }
         check_launch();
         launch_ntt(c, tmp, tmp, (long long) batch * d * Qpl, level_primes(L, K, depth), false, st);
     }
     if (d > 64)
         throw std::invalid_argument("too many key-switch digits");
-    dim3 g(c.n >> 9, Qpl, batch);
     {
         LaunchScope scope(KC_KEYSWITCH_MAC, st);
-        k_keyswitch_mac<<<g, 256, 0, st>>>(tmp, key, acc, c.d_pc, c.logn, d, L, Qpl, c.Qp, depth);
+        int by = 1;
+        while (by < 8 && by * 2 <= batch && (c.n >> 1) >= 256 / by * 2)
+            by *= 2;
+        const int tx = 256 / by; // threads along the coefficient axis, two coefficients each
+        dim3 g((batch + by - 1) / by, (c.n >> 1) / tx, Qpl), blk(tx, by);
+        k_keyswitch_mac<<<g, blk, 0, st>>>(tmp, key, acc, c.d_pc, c.logn, d, L, Qpl, c.Qp, depth, batch);
     }
     check_launch();
     return d;

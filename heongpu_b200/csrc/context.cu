@@ -301,6 +301,11 @@ void upload_tables(Context& c)
         // integer VAR 2 30.9, all-FP64 VAR 3 16.3, VAR 4 (X reduced every other stage) 19.4
         pcs[i].fp_var = !c.use_fp64 ? 0u : pcs[i].bits <= 47 ? 3u : pcs[i].bits <= 50 ? 4u : 0u;
         pcs[i].pinv = 1.0 / (double) p;
+        {
+            // 1/p - pinv = (1 - p*pinv)/p; the residual 1 - p*pinv is exact in one fma
+            const double res = std::fma(-(double) p, pcs[i].pinv, 1.0);
+            pcs[i].pinv_lo = res / (double) p;
+        }
         pcs[i].pad_ = 0;
         for (int j = 0; j < N; ++j)
         {
@@ -340,6 +345,26 @@ void upload_tables(Context& c)
                         }
         c.d_fwd_rowb = upload(fb);
         c.d_inv_rowb = upload(ib);
+        // compact copy for the FP64 primes: bare doubles, round-A entries then the lane-major block
+        std::vector<double> rc((size_t) Qp * R * 256, 0.0);
+        for (int i = 0; i < Qp; ++i)
+        {
+            if (!pcs[i].fp_var)
+                continue;
+            for (int r = 0; r < R; ++r)
+            {
+                double* row = rc.data() + ((size_t) i * R + r) * 256;
+                for (int u = 0; u < 4; ++u)
+                    for (int g = 0; g < (1 << u); ++g)
+                        row[(1 << u) - 1 + g] = (double) c.ntt_table[(size_t) i * N + (1u << (S1 + u)) + ((size_t) r << u) + g];
+                for (int u = 4; u < 8; ++u)
+                    for (int g = 0; g < (1 << (u - 4)); ++g)
+                        for (int tt = 0; tt < 16; ++tt)
+                            row[16 + ((1 << (u - 4)) - 1 + g) * 16 + tt] =
+                                (double) c.ntt_table[(size_t) i * N + (1u << (S1 + u)) + ((size_t) r << u) + (tt << (u - 4)) + g];
+            }
+        }
+        c.d_fwd_rowc = upload(rc);
     }
     c.d_pc = upload(pcs);
     c.d_fwd = upload(fwd);
@@ -376,13 +401,31 @@ void upload_tables(Context& c)
             std::vector<TwPair> bp;
             {
                 size_t o = 0;
+                auto fp_ok = [&](int prime) { return c.use_fp64 && c.mod[prime].bit <= 50; };
                 for (int l = 0; l < t.d; ++l)
+                {
+                    bool dfp = t.I_j[l] <= 4; // k_modup2 uses the FP64 pipe when digit and target primes allow it
+                    for (int i = 0; i < t.I_j[l]; ++i)
+                        dfp = dfp && fp_ok(t.I_loc[l] + i);
                     for (int k = 0; k < Ql; ++k)
                     {
-                        const u64 tk = c.mod[level_prime(k, L, depth)].value;
+                        const int pk = level_prime(k, L, depth);
+                        const u64 tk = c.mod[pk].value;
                         for (int i = 0; i < t.I_j[l]; ++i, ++o)
-                            bp.push_back(TwPair{t.base_change[o], shoup(t.base_change[o], tk)});
+                        {
+                            if (dfp && fp_ok(pk))
+                            {
+                                const double md = (double) t.base_change[o], minv = md / (double) tk;
+                                TwPair tp;
+                                std::memcpy(&tp.w, &md, 8);
+                                std::memcpy(&tp.ws, &minv, 8);
+                                bp.push_back(tp);
+                            }
+                            else
+                                bp.push_back(TwPair{t.base_change[o], shoup(t.base_change[o], tk)});
+                        }
                     }
+                }
             }
             t.d_base_change_pair = upload(bp);
             std::vector<u64> rp((size_t) (K + 1) * t.d * Ql);
@@ -410,6 +453,7 @@ Context::~Context()
     cudaFree(d_inv_last);
     cudaFree(d_fwd_rowb);
     cudaFree(d_inv_rowb);
+    cudaFree(d_fwd_rowc);
     cudaFree(d_last_q_modinv);
     cudaFree(d_lqm_pair);
     cudaFree(d_half);

@@ -33,6 +33,7 @@ struct PrimeConst {
     unsigned fp_var; // 0: integer butterflies; 3 / 4: forward twiddles are doubles {w, RN(w/p)}, use VAR 3 / 4
     unsigned pad_;
     double pinv; // RN(1/p) (FP64 variants)
+    double pinv_lo; // RN(1/p - pinv): pinv + pinv_lo = 1/p to ~106 bits
 };
 
 // Method-II (hybrid, K > 1) level tables; one entry per depth.
@@ -98,6 +99,9 @@ struct Context {
     // [Qp][rows][16 entries][16 lanes] (ntt_core.cuh: ct_round_b_lm)
     TwPair* d_fwd_rowb = nullptr;
     TwPair* d_inv_rowb = nullptr;
+    // compact FP64 row-pass twiddles, bare doubles: [Qp][rows][256] (ntt_core.cuh: stage16_sm);
+    // a 16-row tile's twiddles are 32 KiB contiguous and travel by TMA next to the data tile
+    double* d_fwd_rowc = nullptr;
     int use_tma = 1; // row pass through TMA tensor maps (HEON_NTT_TMA=0 disables)
     int num_sms = 148;
     int ntt_persistent = 0; // HEON_NTT_PERSISTENT=1: row-pass CTAs walk several tiles (double-buffered TMA)

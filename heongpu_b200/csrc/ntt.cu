@@ -409,7 +409,8 @@ constexpr int kRowTileBytes = 16 * 2048;
 template <bool INV, int VAR>
 __device__ __forceinline__ void row_pass_tma_body(unsigned char* rowp, const PrimeConst& pc,
                                                   const TwPair* __restrict__ tw,
-                                                  const TwPair* __restrict__ blk, int S1, int r, int tt)
+                                                  const TwPair* __restrict__ blk, int S1, int r, int tt,
+                                                  const double* rowtw)
 {
     const BflyConst bc = make_bc(pc);
     u64 v[16];
@@ -420,7 +421,10 @@ __device__ __forceinline__ void row_pass_tma_body(unsigned char* rowp, const Pri
 #pragma unroll
         for (int k = 0; k < 16; ++k)
             v[k] = *reinterpret_cast<const u64*>(rowp + k * 128 + ((((tt >> 1) ^ (k & 7)) << 4) | ((tt & 1) << 3)));
-        ct_round_a<VAR, 1>(v, tw, S1, r, bc);
+        if ((VAR == 3 || VAR == 4) && rowtw)
+            ct_round_a_sm<VAR>(v, rowtw, bc);
+        else
+            ct_round_a<VAR, 1>(v, tw, S1, r, bc);
 #pragma unroll
         for (int k = 0; k < 16; ++k)
             *reinterpret_cast<u64*>(rowp + k * 128 + ((((tt >> 1) ^ (k & 7)) << 4) | ((tt & 1) << 3))) = v[k];
@@ -432,7 +436,10 @@ __device__ __forceinline__ void row_pass_tma_body(unsigned char* rowp, const Pri
             v[2 * c] = t2.x;
             v[2 * c + 1] = t2.y;
         }
-        ct_round_b_lm<VAR, 1>(v, blk, tt, bc);
+        if ((VAR == 3 || VAR == 4) && rowtw)
+            ct_round_b_sm<VAR>(v, rowtw, tt, bc);
+        else
+            ct_round_b_lm<VAR, 1>(v, blk, tt, bc);
 #pragma unroll
         for (int c = 0; c < 8; ++c)
         {
@@ -482,7 +489,7 @@ __global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS)
                      const __grid_constant__ CUtensorMap tm_out, const u64* in_base, const u64* out_base,
                      const TwPair* __restrict__ tw_all, const TwPair* __restrict__ rowb_all,
                      const PrimeConst* __restrict__ pcs, int logn, bool first_pass, int variant,
-                     long long n_tiles)
+                     long long n_tiles, const double* __restrict__ rowc_all)
 {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar[2];
@@ -518,12 +525,18 @@ __global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS)
     }
     __syncthreads();
     long long t = blockIdx.x;
+    // one tile per CTA (rowc_all != nullptr): the second buffer receives the tile's FP64
+    // twiddles (32 KiB, contiguous) through the same barrier
     if (threadIdx.x == 0 && t < n_tiles)
     {
         int li, lo, pr, ti;
         tile_lines(t, li, lo, pr, ti);
-        mbar_arrive_expect_tx(&bar[0], kRowTileBytes);
+        const bool twsm = !INV && rowc_all && pcs[pr].fp_var != 0;
+        mbar_arrive_expect_tx(&bar[0], twsm ? 2 * kRowTileBytes : kRowTileBytes);
         tma_load_2d(buf0, tmi, &bar[0], 0, li);
+        if (twsm)
+            tma_load_1d(buf0 + kRowTileBytes, rowc_all + ((((long long) pr << S1) + ti * 16) << 8), kRowTileBytes,
+                        &bar[0]);
     }
     for (int it = 0; t < n_tiles; ++it, t += gridDim.x)
     {
@@ -550,16 +563,18 @@ __global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS)
         const int r = tile_idx * 16 + rl;
         const TwPair* blk = rowb_all + ((((long long) prime << S1) + r) << 8);
         unsigned char* rowp = tile + rl * 2048;
+        const double* rowtw =
+            rowc_all ? reinterpret_cast<const double*>(buf0 + kRowTileBytes) + rl * 256 : nullptr;
         mbar_wait(&bar[b], (it >> 1) & 1);
 
         if (!INV && pc.fp_var == 3)
-            row_pass_tma_body<INV, INV ? 1 : 3>(rowp, pc, tw, blk, S1, r, tt);
+            row_pass_tma_body<INV, INV ? 1 : 3>(rowp, pc, tw, blk, S1, r, tt, rowtw);
         else if (!INV && pc.fp_var == 4)
-            row_pass_tma_body<INV, INV ? 1 : 4>(rowp, pc, tw, blk, S1, r, tt);
+            row_pass_tma_body<INV, INV ? 1 : 4>(rowp, pc, tw, blk, S1, r, tt, rowtw);
         else if (INV || variant == 1 || !pc.nc_ok)
-            row_pass_tma_body<INV, 1>(rowp, pc, tw, blk, S1, r, tt);
+            row_pass_tma_body<INV, 1>(rowp, pc, tw, blk, S1, r, tt, nullptr);
         else
-            row_pass_tma_body<INV, 2>(rowp, pc, tw, blk, S1, r, tt);
+            row_pass_tma_body<INV, 2>(rowp, pc, tw, blk, S1, r, tt, nullptr);
 
         fence_proxy_async_smem();
         __syncthreads();
@@ -673,7 +688,7 @@ static void launch_row_tma(const Context& c, const Map& m, long long n_polys, bo
     LaunchScope scope(INV ? KC_NTT_INV_ROW : KC_NTT_FWD_ROW, st);
     kfn<<<grid, 256, smem, st>>>(m, tm_in, tm_out, e.in_base, e.out_base, INV ? c.d_inv : c.d_fwd,
                                  INV ? c.d_inv_rowb : c.d_fwd_rowb, c.d_pc, c.logn, first, c.ntt_variant,
-                                 n_tiles);
+                                 n_tiles, (!INV && !c.ntt_persistent && c.use_fp64) ? c.d_fwd_rowc : nullptr);
 }
 
 template <class Map>

@@ -63,7 +63,7 @@ __device__ __forceinline__ u64 shoup_mul_lazy3(u64 x, u64 w, u64 ws, u64 p)
 struct BflyConst {
     u64 p, p2, p4;
     u64 np; // 2^64 - p
-    double dp, dnp, dpinv; // p, -p, RN(1/p) for the FP64 variants
+    double dp, dnp, dpinv, dpinv_lo; // p, -p, RN(1/p), RN(1/p - RN(1/p)) for the FP64 variants
 };
 
 __device__ __forceinline__ BflyConst make_bc(const PrimeConst& pc)
@@ -76,6 +76,7 @@ __device__ __forceinline__ BflyConst make_bc(const PrimeConst& pc)
     c.dp = (double) pc.p;
     c.dnp = -c.dp;
     c.dpinv = pc.pinv;
+    c.dpinv_lo = pc.pinv_lo;
     return c;
 }
 
@@ -196,6 +197,16 @@ __device__ __forceinline__ double fp_from_u64(u64 x)
                      4503599627370496.0);
 }
 
+// integer-valued double |v| < 2^52 -> canonical residue in [0,p), as an integer word
+__device__ __forceinline__ u64 fp_canon(double v, double pinv, double np, double dp)
+{
+    double r = fp_reduce(v, pinv, np); // [-p/2, p/2]
+    if (r < 0.0)
+        r = __dadd_rn(r, dp);
+    // r in [0,p), p < 2^50: the low 52 bits of r + 2^52 are the integer
+    return d2u(__dadd_rn(r, 4503599627370496.0)) & 0x000FFFFFFFFFFFFFull;
+}
+
 // Word as loaded (an integer below 4p) -> working representation of variant VAR.
 // `lazy`: the word may exceed p (fused mod-up); VAR 4 needs |v| <= p on entry.
 template <int VAR> __device__ __forceinline__ u64 ct_prep(u64 x, const BflyConst& c, bool lazy)
@@ -245,13 +256,7 @@ __device__ __forceinline__ void ct_bfly(u64& X, u64& Y, const TwPair& w, const B
 template <int VAR> __device__ __forceinline__ u64 ct_finish(u64 x, const BflyConst& c, const PrimeConst& pc)
 {
     if (VAR == 3 || VAR == 4)
-    {
-        double r = fp_reduce(u2d(x), c.dpinv, c.dnp); // [-p/2, p/2]
-        if (r < 0.0)
-            r = __dadd_rn(r, c.dp);
-        // r in [0,p), p < 2^50: the low 52 bits of r + 2^52 are the integer
-        return d2u(__dadd_rn(r, 4503599627370496.0)) & 0x000FFFFFFFFFFFFFull;
-    }
+        return fp_canon(u2d(x), c.dpinv, c.dnp, c.dp);
     if (VAR == 0)
         return csub(csub(x, c.p2), c.p);
     if (VAR == 1)
@@ -307,6 +312,47 @@ __device__ __forceinline__ void stage16(u64 (&v)[16], const TwPair* __restrict__
                 ct_bfly<VAR, RED>(v[k], v[k + (1 << LS)], w, c);
         }
     }
+}
+
+// FP64 row pass with the twiddles of the row staged in shared memory as bare doubles w
+// (8 bytes instead of a 16-byte pair: half the L2 traffic and half the shared memory).  The
+// quotient multiplier is rebuilt as winv = RN(RN(w*ph) + w*pl) with ph + pl = 1/p to 106 bits:
+// |winv - w/p| <= 2^-53, so |T| <= p*(1/2 + |Y|*2^-53) -- with X reduced on every other stage
+// (VAR 4, pattern R,-,R,-) values stay below 1.9p < 2^51 for p < 2^50; VAR 3 (p < 2^47) stays
+// below 14p.  Row layout: [0..14] round-A entries (stage u: 2^u - 1 + g), [15] pad,
+// [16 + e*16 + lane] round-B entries (lane-major, as ct_round_b_lm).
+template <int LS, int VAR, int GSTRIDE, bool RED>
+__device__ __forceinline__ void stage16_sm(u64 (&v)[16], const double* tws, const BflyConst& c)
+{
+#pragma unroll
+    for (int g = 0; g < (8 >> LS); ++g)
+    {
+        const double wd = tws[g * GSTRIDE];
+        TwPair w;
+        w.w = d2u(wd);
+        w.ws = d2u(__fma_rn(wd, c.dpinv_lo, __dmul_rn(wd, c.dpinv)));
+#pragma unroll
+        for (int j = 0; j < (1 << LS); ++j)
+        {
+            const int k = g * (2 << LS) + j;
+            ct_bfly<VAR, RED>(v[k], v[k + (1 << LS)], w, c);
+        }
+    }
+}
+template <int VAR> __device__ __forceinline__ void ct_round_a_sm(u64 (&v)[16], const double* rowtw, const BflyConst& c)
+{
+    stage16_sm<3, VAR, 1, true>(v, rowtw + 0, c);
+    stage16_sm<2, VAR, 1, false>(v, rowtw + 1, c);
+    stage16_sm<1, VAR, 1, true>(v, rowtw + 3, c);
+    stage16_sm<0, VAR, 1, false>(v, rowtw + 7, c);
+}
+template <int VAR>
+__device__ __forceinline__ void ct_round_b_sm(u64 (&v)[16], const double* rowtw, int tt, const BflyConst& c)
+{
+    stage16_sm<3, VAR, 16, true>(v, rowtw + 16 + 0 * 16 + tt, c);
+    stage16_sm<2, VAR, 16, false>(v, rowtw + 16 + 1 * 16 + tt, c);
+    stage16_sm<1, VAR, 16, true>(v, rowtw + 16 + 3 * 16 + tt, c);
+    stage16_sm<0, VAR, 16, false>(v, rowtw + 16 + 7 * 16 + tt, c);
 }
 
 // Round A: the four stages with register strides 8,4,2,1 when the thread

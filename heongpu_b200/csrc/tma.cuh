@@ -53,6 +53,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
                  : "memory");
 }
 
+// contiguous global -> shared bulk copy (bytes: multiple of 16), completion on `bar`
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // shared -> global tile store (bulk async group)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1)
 {
