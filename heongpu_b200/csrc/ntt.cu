@@ -588,6 +588,464 @@ __global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS)
         tma_store_wait_read<0>();
 }
 
+
+// ---------------------------------------------------------------------------
+// Fused forward transform: ONE persistent kernel runs the column tiles and the
+// row tiles of the whole batch.  CTAs draw tickets in order; the ticket stream
+// is  col(g0) col(g1) row(g0) col(g2) row(g1) ...  over groups of `G`
+// polynomials, so the column-pass output of a group (lazy words, written in
+// place into the destination) is still in L2 when its row tiles read it and
+// the transform costs one DRAM read and one DRAM write per word instead of
+// two of each.  A row tile waits on a per-polynomial counter of finished
+// column tiles (release/acquire at GPU scope); tickets are handed out in order
+// and column tickets of a group precede its row tickets, so every CTA a
+// waiter depends on is already running: no deadlock.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_gpu(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <int S, class Map>
+__global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS)
+    ntt_fwd_fused(Map map, const __grid_constant__ CUtensorMap tm_out, const u64* out_base,
+                  const TwPair* __restrict__ tw_all, const TwPair* __restrict__ rowb_all,
+                  const double* __restrict__ rowc_all, const PrimeConst* __restrict__ pcs,
+                  const TwPair* __restrict__ inv_last, int variant, long long n_polys, int G, int* sync)
+{
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ long long s_ticket;
+    constexpr int logn = S + 8;
+    constexpr int tiles = (1 << S) / 16; // tiles per polynomial, both passes
+    unsigned char* buf0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const long long seg = (long long) G * tiles; // tickets per segment
+    const long long n_groups = (n_polys + G - 1) / G;
+    const long long n_tickets = (2 * n_groups + 1) * seg; // col(0) + pairs {col(k), row(k-1)}, k = 1..n_groups
+    int* ticket = sync;
+    int* done = sync + 1;
+    const int tt = threadIdx.x & 15;
+    const int rl = threadIdx.x >> 4;
+    unsigned phase = 0;
+
+    if (threadIdx.x == 0)
+    {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    for (;;)
+    {
+        if (threadIdx.x == 0)
+        {
+            tma_store_wait_read<0>(); // the previous row tile has left shared memory
+            s_ticket = atomicAdd(ticket, 1);
+        }
+        __syncthreads();
+        const long long t = s_ticket;
+        __syncthreads();
+        if (t >= n_tickets)
+            break;
+        // segment s: 0 -> col(0); odd s -> col((s+1)/2); even s >= 2 -> row(s/2 - 1)
+        const long long sgm = t / seg;
+        const int w = (int) (t % seg);
+        const bool is_row = sgm >= 2 && (sgm & 1) == 0;
+        const long long g = sgm == 0 ? 0 : is_row ? sgm / 2 - 1 : (sgm + 1) / 2;
+        const long long z = g * G + w / tiles;
+        const int tile = w % tiles;
+        if (g >= n_groups || z >= n_polys)
+            continue;
+        const u64* in;
+        u64* out;
+        int prime, aux;
+        map.get(z, in, out, prime, aux);
+        const PrimeConst pc = pcs[prime];
+        const TwPair* tw = tw_all + ((long long) prime << logn);
+        if (!is_row)
+        {
+            u64* sm = reinterpret_cast<u64*>(buf0);
+            if (pc.fp_var == 3)
+                col_pass_body<S, false, 3>(map, in, out, prime, pc, tw, inv_last, tile, true, aux, sm);
+            else if (pc.fp_var == 4)
+                col_pass_body<S, false, 4>(map, in, out, prime, pc, tw, inv_last, tile, true, aux, sm);
+            else if (variant == 1 || !pc.nc_ok)
+                col_pass_body<S, false, 1>(map, in, out, prime, pc, tw, inv_last, tile, true, aux, sm);
+            else
+                col_pass_body<S, false, 2>(map, in, out, prime, pc, tw, inv_last, tile, true, aux, sm);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0)
+                atomicAdd(done + z, 1);
+        }
+        else
+        {
+            const bool twsm = rowc_all && pc.fp_var != 0;
+            if (threadIdx.x == 0)
+            {
+                while (ld_acquire_gpu(done + z) < tiles)
+                    __nanosleep(64);
+                fence_proxy_async_all(); // generic-proxy writes of other CTAs -> this CTA's TMA read
+                const int line = (int) ((out - out_base) >> 4) + tile * 256;
+                mbar_arrive_expect_tx(&bar, twsm ? 2 * kRowTileBytes : kRowTileBytes);
+                tma_load_2d(buf0, &tm_out, &bar, 0, line);
+                if (twsm)
+                    tma_load_1d(buf0 + kRowTileBytes, rowc_all + ((((long long) prime << S) + tile * 16) << 8),
+                                kRowTileBytes, &bar);
+            }
+            const int r = tile * 16 + rl;
+            const TwPair* blk = rowb_all + ((((long long) prime << S) + r) << 8);
+            unsigned char* rowp = buf0 + rl * 2048;
+            const double* rowtw = twsm ? reinterpret_cast<const double*>(buf0 + kRowTileBytes) + rl * 256 : nullptr;
+            mbar_wait(&bar, phase & 1);
+            ++phase;
+            if (pc.fp_var == 3)
+                row_pass_tma_body<false, 3>(rowp, pc, tw, blk, S, r, tt, rowtw);
+            else if (pc.fp_var == 4)
+                row_pass_tma_body<false, 4>(rowp, pc, tw, blk, S, r, tt, rowtw);
+            else if (variant == 1 || !pc.nc_ok)
+                row_pass_tma_body<false, 1>(rowp, pc, tw, blk, S, r, tt, nullptr);
+            else
+                row_pass_tma_body<false, 2>(rowp, pc, tw, blk, S, r, tt, nullptr);
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                const int line = (int) ((out - out_base) >> 4) + tile * 256;
+                tma_store_2d(&tm_out, buf0, 0, line);
+                tma_store_commit();
+            }
+        }
+    }
+    if (threadIdx.x == 0)
+        tma_store_wait_read<0>();
+}
+
+
+// ---------------------------------------------------------------------------
+// Pipelined fused forward transform for N = 2^16 (the BASELINE ring size).
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0  producer : walks the ticket stream, issues the TMA load of every tile into a ring
+//                      of kPipeStages 32 KiB shared-memory stages (full[] barriers);
+//   warp 1  storer   : waits until a stage has been computed (comp[]), issues its TMA store,
+//                      frees the stage (empty[]) and publishes finished column tiles;
+//   2 x 8 consumer warps: two groups of 256 threads, each transforming one tile at a time out
+//                      of registers, reading and writing the stage in place.
+// Loads, stores and arithmetic of different tiles overlap freely; nothing on the arithmetic
+// path waits for DRAM.  The ticket stream is  col(g0) col(g1) row(g0) col(g2) row(g1) ...  over
+// groups of G polynomials (tickets are dealt round-robin to the CTAs), so the column-pass output
+// of a group is still in L2 when its row tiles read it back: one DRAM read and one DRAM write
+// per word.  The producer holds a row tile back until the 16 column tiles of its polynomial have
+// been stored (per-polynomial counter, release/acquire at GPU scope).  The smallest unfinished
+// ticket only depends on smaller tickets, so the scheme cannot deadlock.
+//
+// Column tile: 16 columns x 256 rows through a 3-D tensor map {16 words, 16 lines, rows} with
+// box {16, 1, 256}; row tile: 16 rows = 256 consecutive 128-byte lines (2-D map); both land with
+// the 128-byte swizzle, element e of line l at  l*128 + ((e>>1) ^ (l&7))*16 + (e&1)*8.
+// ---------------------------------------------------------------------------
+constexpr int kPipeStages = 6;
+constexpr int kPipeGroups = 2;
+constexpr int kPipeThreads = 64 + 256 * kPipeGroups;
+
+template <int VAR, class Map>
+__device__ __forceinline__ void pipe_col_tile(unsigned char* tile, const Map& map, int prime, const PrimeConst& pc,
+                                              const TwPair* __restrict__ tw, int aux, int tid, int bar_id)
+{
+    const BflyConst bc = make_bc(pc);
+    const int c = tid & 15, tt = tid >> 4;
+    u64 v[16];
+    unsigned char* pa = tile + tt * 128 + ((((c >> 1) ^ (tt & 7)) << 4) | ((c & 1) << 3)); // rows tt + 16k
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+    {
+        u64 x = *reinterpret_cast<const u64*>(pa + k * 2048);
+        if (Map::kXform)
+            x = map.xform(x, prime, pc, aux);
+        v[k] = ct_prep<VAR>(x, bc, Map::kLazyIn);
+    }
+    ct_round_a<VAR>(v, tw, 0, 0, bc);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        *reinterpret_cast<u64*>(pa + k * 2048) = v[k];
+    named_bar_sync(bar_id, 256);
+    unsigned char* pb = tile + tt * 2048 + ((c & 1) << 3); // rows 16*tt + k
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        v[k] = *reinterpret_cast<const u64*>(pb + k * 128 + (((c >> 1) ^ (k & 7)) << 4));
+    ct_round_b<8, VAR>(v, tw, 0, 0, tt, bc);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        *reinterpret_cast<u64*>(pb + k * 128 + (((c >> 1) ^ (k & 7)) << 4)) = v[k]; // lazy, finished by the row tile
+}
+
+// FP64 row tile: the thread's 15 last-four-stage twiddles (bare doubles, compact table) are
+// requested before the first four stages run, so their L2 latency hides behind arithmetic.
+template <int VAR>
+__device__ __forceinline__ void pipe_row_tile_fp(unsigned char* rowp, const PrimeConst& pc,
+                                                 const double* __restrict__ rowc, int tt)
+{
+    const BflyConst bc = make_bc(pc);
+    double twb[15];
+#pragma unroll
+    for (int e = 0; e < 15; ++e)
+        twb[e] = __ldg(rowc + 16 + e * 16 + tt);
+    double twa[15];
+#pragma unroll
+    for (int e = 0; e < 15; ++e)
+        twa[e] = __ldg(rowc + e);
+    u64 v[16];
+    unsigned char* lineB = rowp + tt * 128;
+    const int sw = tt & 7;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        v[k] = *reinterpret_cast<const u64*>(rowp + k * 128 + ((((tt >> 1) ^ (k & 7)) << 4) | ((tt & 1) << 3)));
+    ct_round_a_sm<VAR>(v, twa, bc);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        *reinterpret_cast<u64*>(rowp + k * 128 + ((((tt >> 1) ^ (k & 7)) << 4) | ((tt & 1) << 3))) = v[k];
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+    {
+        const ulonglong2 t2 = *reinterpret_cast<const ulonglong2*>(lineB + ((c ^ sw) << 4));
+        v[2 * c] = t2.x;
+        v[2 * c + 1] = t2.y;
+    }
+    ct_round_a_sm<VAR>(v, twb, bc);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+    {
+        ulonglong2 t2;
+        t2.x = ct_finish<VAR>(v[2 * c], bc, pc);
+        t2.y = ct_finish<VAR>(v[2 * c + 1], bc, pc);
+        *reinterpret_cast<ulonglong2*>(lineB + ((c ^ sw) << 4)) = t2;
+    }
+}
+
+struct PipeTicket {
+    long long z;
+    int tile;
+    bool is_row, valid, end;
+};
+
+// ticket -> work item (segment s: 0 -> col(0); odd s -> col((s+1)/2); even s >= 2 -> row(s/2 - 1))
+__device__ __forceinline__ PipeTicket pipe_decode(long long t, long long n_polys, int G, long long n_groups)
+{
+    PipeTicket r;
+    const long long seg = (long long) G * 16;
+    r.end = t >= (2 * n_groups + 1) * seg;
+    const long long sgm = t / seg;
+    const int w = (int) (t % seg);
+    r.is_row = sgm >= 2 && (sgm & 1) == 0;
+    const long long g = sgm == 0 ? 0 : r.is_row ? sgm / 2 - 1 : (sgm + 1) / 2;
+    r.z = g * G + w / 16;
+    r.tile = w % 16;
+    r.valid = !r.end && g < n_groups && r.z < n_polys;
+    return r;
+}
+
+template <class Map>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+    ntt16_fwd_pipe(Map map, const __grid_constant__ CUtensorMap tm_in_col,
+                   const __grid_constant__ CUtensorMap tm_out_col,
+                   const __grid_constant__ CUtensorMap tm_out_row, const u64* in_base, const u64* out_base,
+                   const TwPair* __restrict__ tw_all, const TwPair* __restrict__ rowb_all,
+                   const double* __restrict__ rowc_all, const PrimeConst* __restrict__ pcs, int variant,
+                   long long n_polys, int G, int* done)
+{
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[kPipeStages], comp[kPipeStages], empty[kPipeStages];
+    __shared__ long long item[kPipeStages];
+    unsigned char* buf0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int logn = 16, S = 8;
+    const long long n_groups = (n_polys + G - 1) / G;
+    const int warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0)
+    {
+        for (int s = 0; s < kPipeStages; ++s)
+        {
+            mbar_init(&full[s], 1);
+            mbar_init(&comp[s], 256);
+            mbar_init(&empty[s], 1);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == 0)
+    {
+        // ---------------- producer ----------------
+        if (threadIdx.x != 0)
+            return;
+        long long t = blockIdx.x;
+        int sentinels = 0;
+        for (long long i = 0;; ++i)
+        {
+            const int s = (int) (i % kPipeStages);
+            if (i >= kPipeStages)
+                mbar_wait(&empty[s], (unsigned) ((i / kPipeStages - 1) & 1));
+            PipeTicket k = pipe_decode(t, n_polys, G, n_groups);
+            while (!k.end && !k.valid)
+            {
+                t += gridDim.x;
+                k = pipe_decode(t, n_polys, G, n_groups);
+            }
+            if (k.end)
+            {
+                item[s] = -1;
+                mbar_arrive(&full[s]);
+                if (++sentinels == kPipeGroups)
+                    break;
+                continue;
+            }
+            t += gridDim.x;
+            item[s] = (k.z << 8) | (k.tile << 1) | (k.is_row ? 1 : 0);
+            const u64* in;
+            u64* out;
+            int prime, aux;
+            map.get(k.z, in, out, prime, aux);
+            unsigned char* stage = buf0 + s * kRowTileBytes;
+            if (k.is_row)
+            {
+                while (ld_acquire_gpu(done + k.z) < 16)
+                    __nanosleep(32);
+                fence_proxy_async_all(); // other CTAs' tile stores -> this CTA's TMA read
+                mbar_arrive_expect_tx(&full[s], kRowTileBytes);
+                tma_load_2d(stage, &tm_out_row, &full[s], 0, (int) ((out - out_base) >> 4) + k.tile * 256);
+            }
+            else
+            {
+                mbar_arrive_expect_tx(&full[s], kRowTileBytes);
+                tma_load_3d(stage, &tm_in_col, &full[s], 0, k.tile, (int) ((in - in_base) >> 8));
+            }
+        }
+        return;
+    }
+    if (warp == 1)
+    {
+        // ---------------- storer ----------------
+        if (threadIdx.x != 32)
+            return;
+        long long pend[3] = {-1, -1, -1};
+        int sentinels = 0;
+        long long n_store = 0;
+        auto publish = [&](long long z) {
+            if (z >= 0)
+            {
+                fence_proxy_async_all();
+                __threadfence();
+                atomicAdd(done + z, 1);
+            }
+        };
+        for (long long i = 0;; ++i)
+        {
+            const int s = (int) (i % kPipeStages);
+            if (!mbar_test(&comp[s], (unsigned) ((i / kPipeStages) & 1)))
+            {
+                // nothing to store right now: finish the stores in flight and publish their column
+                // tiles (a row tile somewhere may be waiting for exactly these), then block
+                tma_store_wait_all<0>();
+                for (int j = 0; j < 3; ++j)
+                {
+                    publish(pend[j]);
+                    pend[j] = -1;
+                }
+                mbar_wait(&comp[s], (unsigned) ((i / kPipeStages) & 1));
+            }
+            const long long it = item[s];
+            if (it < 0)
+            {
+                if (++sentinels == kPipeGroups)
+                    break;
+                continue;
+            }
+            const long long z = it >> 8;
+            const int tile = (int) ((it >> 1) & 127);
+            const bool is_row = it & 1;
+            const u64* in;
+            u64* out;
+            int prime, aux;
+            map.get(z, in, out, prime, aux);
+            unsigned char* stage = buf0 + s * kRowTileBytes;
+            if (is_row)
+                tma_store_2d(&tm_out_row, stage, 0, (int) ((out - out_base) >> 4) + tile * 256);
+            else
+                tma_store_3d(&tm_out_col, stage, 0, tile, (int) ((out - out_base) >> 8));
+            tma_store_commit();
+            tma_store_wait_read<0>();
+            mbar_arrive(&empty[s]);
+            // stores older than the two most recent ones are complete: publish their column tiles
+            tma_store_wait_all<2>();
+            publish(pend[n_store % 3]);
+            pend[n_store % 3] = is_row ? -1 : z;
+            ++n_store;
+        }
+        tma_store_wait_all<0>();
+        for (int j = 0; j < 3; ++j)
+            publish(pend[j]);
+        return;
+    }
+    // ---------------- consumers ----------------
+    const int grp = (threadIdx.x - 64) >> 8;
+    const int tid = (threadIdx.x - 64) & 255;
+    for (long long i = grp;; i += kPipeGroups)
+    {
+        const int s = (int) (i % kPipeStages);
+        mbar_wait(&full[s], (unsigned) ((i / kPipeStages) & 1));
+        const long long it = item[s];
+        if (it < 0)
+        {
+            mbar_arrive(&comp[s]);
+            break;
+        }
+        const long long z = it >> 8;
+        const int tile = (int) ((it >> 1) & 127);
+        const bool is_row = it & 1;
+        const u64* in;
+        u64* out;
+        int prime, aux;
+        map.get(z, in, out, prime, aux);
+        const PrimeConst pc = pcs[prime];
+        const TwPair* tw = tw_all + ((long long) prime << logn);
+        unsigned char* stage = buf0 + s * kRowTileBytes;
+        if (!is_row)
+        {
+            if (pc.fp_var == 3)
+                pipe_col_tile<3>(stage, map, prime, pc, tw, aux, tid, 1 + grp);
+            else if (pc.fp_var == 4)
+                pipe_col_tile<4>(stage, map, prime, pc, tw, aux, tid, 1 + grp);
+            else if (variant == 1 || !pc.nc_ok)
+                pipe_col_tile<1>(stage, map, prime, pc, tw, aux, tid, 1 + grp);
+            else
+                pipe_col_tile<2>(stage, map, prime, pc, tw, aux, tid, 1 + grp);
+        }
+        else
+        {
+            const int tt = tid & 15, rl = tid >> 4;
+            const int r = tile * 16 + rl;
+            unsigned char* rowp = stage + rl * 2048;
+            if (pc.fp_var == 3)
+                pipe_row_tile_fp<3>(rowp, pc, rowc_all + ((((long long) prime << S) + r) << 8), tt);
+            else if (pc.fp_var == 4)
+                pipe_row_tile_fp<4>(rowp, pc, rowc_all + ((((long long) prime << S) + r) << 8), tt);
+            else
+            {
+                const TwPair* blk = rowb_all + ((((long long) prime << S) + r) << 8);
+                if (variant == 1 || !pc.nc_ok)
+                    row_pass_tma_body<false, 1>(rowp, pc, tw, blk, S, r, tt, nullptr);
+                else
+                    row_pass_tma_body<false, 2>(rowp, pc, tw, blk, S, r, tt, nullptr);
+            }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&comp[s]);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
@@ -666,6 +1124,10 @@ struct Extent {
     long long in_words;
     const u64* out_base;
     long long out_words;
+    // buffer read by the FIRST pass of a forward transform (column tiles by TMA); nullptr when
+    // its polynomials do not start on 2 KiB row boundaries relative to the base
+    const u64* col_in_base = nullptr;
+    long long col_in_words = 0;
 };
 
 template <bool INV, class Map>
@@ -691,6 +1153,101 @@ static void launch_row_tma(const Context& c, const Map& m, long long n_polys, bo
                                  n_tiles, (!INV && !c.ntt_persistent && c.use_fp64) ? c.d_fwd_rowc : nullptr);
 }
 
+
+// rows-of-2-KiB view for the column tiles: {16 words, 16 lines per row, rows}, box {16, 1, 256}
+static CUtensorMap make_col_map(const u64* base, long long words)
+{
+    CUtensorMap m;
+    const cuuint64_t dims[3] = {16, 16, (cuuint64_t) (words >> 8)};
+    const cuuint64_t strides[2] = {128, 2048};
+    const cuuint32_t box[3] = {16, 1, 256};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult rc = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void*) base, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS)
+        throw std::runtime_error("cuTensorMapEncodeTiled (column map) failed (" + std::to_string((int) rc) + ")");
+    return m;
+}
+
+// `ein`: extent of the buffer the FIRST pass reads (may differ from e.in_base, which describes
+// what the row pass reads); every polynomial must start a multiple of 256 words from the bases.
+template <class Map>
+static bool launch_fwd_pipe(const Context& c, const Map& m, long long n_polys, const u64* in_base,
+                            long long in_words, const Extent& e, cudaStream_t st)
+{
+    if (c.logn != 16 || !c.ntt_pipe || !c.use_fp64 || n_polys < 1)
+        return false;
+    if ((reinterpret_cast<uintptr_t>(in_base) | reinterpret_cast<uintptr_t>(e.out_base)) & 127)
+        return false;
+    const int G = std::max(1, c.ntt_group);
+    int* done = nullptr;
+    const size_t sync_bytes = (size_t) n_polys * sizeof(int);
+    if (cudaMallocAsync(&done, sync_bytes, st) != cudaSuccess)
+        return false;
+    cudaMemsetAsync(done, 0, sync_bytes, st);
+    const CUtensorMap tm_in_col = make_col_map(in_base, in_words);
+    const CUtensorMap tm_out_col = make_col_map(e.out_base, e.out_words);
+    const CUtensorMap tm_out_row = make_line_map(e.out_base, e.out_words);
+    const int smem = kPipeStages * kRowTileBytes + 1024;
+    const long long n_tiles = n_polys * 32;
+    const unsigned grid = (unsigned) std::min<long long>((n_tiles + 3) / 4, c.num_sms);
+    auto kfn = ntt16_fwd_pipe<Map>;
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    {
+        LaunchScope scope(KC_NTT_FWD_COL, st);
+        kfn<<<grid, kPipeThreads, smem, st>>>(m, tm_in_col, tm_out_col, tm_out_row, in_base, e.out_base, c.d_fwd,
+                                              c.d_fwd_rowb, c.d_fwd_rowc, c.d_pc, c.ntt_variant, n_polys, G, done);
+    }
+    cudaFreeAsync(done, st);
+    return true;
+}
+
+template <class Map>
+static bool launch_fwd_fused(const Context& c, const Map& m, long long n_polys, const Extent& e, cudaStream_t st)
+{
+    const int S = c.logn - 8;
+    if (S < 5 || !c.ntt_fused)
+        return false;
+    const int tiles = (1 << S) / 16;
+    // group = polynomials whose column-pass output waits in L2 for its row tiles (~8 MiB)
+    int G = (int) std::max<long long>(1, (8ll << 20) / (8ll << c.logn));
+    const long long n_groups = (n_polys + G - 1) / G;
+    const long long n_tickets = (2 * n_groups + 1) * (long long) G * tiles;
+    if (n_tickets + (long long) c.num_sms * 8 > 0x7fffffffll)
+        return false;
+    int* sync = nullptr;
+    const size_t sync_bytes = (size_t) (n_polys + 1) * sizeof(int);
+    if (cudaMallocAsync(&sync, sync_bytes, st) != cudaSuccess)
+        return false;
+    cudaMemsetAsync(sync, 0, sync_bytes, st);
+    const CUtensorMap tm_out = make_line_map(e.out_base, e.out_words);
+    const int smem = 2 * kRowTileBytes + 1024;
+    const unsigned grid = (unsigned) std::min<long long>(n_tickets, (long long) c.num_sms * HEON_NTT_MINBLOCKS);
+    {
+        LaunchScope scope(KC_NTT_FWD_COL, st);
+#define HEON_FUSED(SS)                                                                                      \
+    case SS: {                                                                                              \
+        auto kfn = ntt_fwd_fused<SS, Map>;                                                                  \
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                       \
+        kfn<<<grid, 256, smem, st>>>(m, tm_out, e.out_base, c.d_fwd, c.d_fwd_rowb,                          \
+                                     c.use_fp64 ? c.d_fwd_rowc : nullptr, c.d_pc, c.d_inv_last,             \
+                                     c.ntt_variant, n_polys, G, sync);                                      \
+        break;                                                                                              \
+    }
+        switch (S)
+        {
+            HEON_FUSED(5)
+            HEON_FUSED(6)
+            HEON_FUSED(7)
+            HEON_FUSED(8)
+        }
+#undef HEON_FUSED
+    }
+    cudaFreeAsync(sync, st);
+    return true;
+}
+
 template <class Map>
 static void run_ntt(const Context& c, const Map& m, long long n_polys, bool inverse, const Extent& e,
                     cudaStream_t st)
@@ -701,6 +1258,10 @@ static void run_ntt(const Context& c, const Map& m, long long n_polys, bool inve
     const bool tma = c.use_tma && ((reinterpret_cast<uintptr_t>(e.in_base) | reinterpret_cast<uintptr_t>(e.out_base)) & 15) == 0;
     if (!inverse)
     {
+        if (tma && e.col_in_base && launch_fwd_pipe(c, m, n_polys, e.col_in_base, e.col_in_words, e, st))
+            return;
+        if (tma && launch_fwd_fused(c, m, n_polys, e, st))
+            return;
         launch_col<false>(c, m, n_polys, true, st);
         if (tma)
             launch_row_tma<false>(c, m, n_polys, false, e, st);
@@ -722,7 +1283,7 @@ void launch_ntt(const Context& c, const u64* src, u64* dst, long long n_polys, c
 {
     MapContig m{src, dst, pl, c.logn};
     const long long w = n_polys << c.logn;
-    run_ntt(c, m, n_polys, inverse, Extent{src, w, dst, w}, st);
+    run_ntt(c, m, n_polys, inverse, Extent{src, w, dst, w, src, w}, st);
 }
 
 void launch_ntt_scattered(const Context& c, u64* base, const long long* d_offsets, int n_polys,
@@ -731,6 +1292,7 @@ void launch_ntt_scattered(const Context& c, u64* base, const long long* d_offset
     MapScatter m{base, d_offsets, prime};
     // offsets that are not multiples of 16 words cannot be addressed in 128-byte lines
     Extent e{aligned ? base : base + 1, extent_words, aligned ? base : base + 1, extent_words};
+    // arbitrary offsets: the column tiles need 2 KiB-aligned polynomials, not guaranteed here
     run_ntt(c, m, n_polys, inverse, e, st);
 }
 
@@ -740,7 +1302,13 @@ void launch_ntt_strided(const Context& c, u64* base, long long bstride, int per_
     MapStrided m{base, bstride, per_batch, first, pl, c.logn};
     const long long w = (batch - 1) * bstride + ((long long) (first + per_batch) << c.logn);
     const u64* b0 = (bstride & 15) ? base + 1 : base; // odd strides: no line addressing -> LSU path
-    run_ntt(c, m, batch * per_batch, inverse, Extent{b0, w, b0, w}, st);
+    Extent e{b0, w, b0, w};
+    if ((bstride & 255) == 0)
+    {
+        e.col_in_base = base;
+        e.col_in_words = w;
+    }
+    run_ntt(c, m, batch * per_batch, inverse, e, st);
 }
 
 void launch_ntt_strided_copy(const Context& c, const u64* src, long long src_bstride, u64* dst,
@@ -751,7 +1319,13 @@ void launch_ntt_strided_copy(const Context& c, const u64* src, long long src_bst
     const long long wi = (batch - 1) * src_bstride + ((long long) per_batch << c.logn);
     const long long wo = (batch * per_batch) << c.logn;
     const u64* s0 = (src_bstride & 15) ? src + 1 : src;
-    run_ntt(c, m, batch * per_batch, inverse, Extent{s0, wi, dst, wo}, st);
+    Extent e{s0, wi, dst, wo};
+    if ((src_bstride & 255) == 0)
+    {
+        e.col_in_base = src;
+        e.col_in_words = wi;
+    }
+    run_ntt(c, m, batch * per_batch, inverse, e, st);
 }
 
 void launch_modup1_ntt(const Context& c, const u64* coef, long long coef_bstride, u64* out, int L,
@@ -760,7 +1334,13 @@ void launch_modup1_ntt(const Context& c, const u64* coef, long long coef_bstride
     const int Qpl = L + c.P_size;
     MapModUpI m{coef, out, coef_bstride, L, Qpl, depth, c.logn, c.d_pc};
     const long long wo = (batch * L * Qpl) << c.logn;
-    run_ntt(c, m, batch * L * Qpl, false, Extent{out, wo, out, wo}, st);
+    Extent e{out, wo, out, wo};
+    if ((coef_bstride & 255) == 0)
+    {
+        e.col_in_base = coef;
+        e.col_in_words = (batch - 1) * coef_bstride + ((long long) L << c.logn);
+    }
+    run_ntt(c, m, batch * L * Qpl, false, e, st);
 }
 
 void launch_divround1_ntt(const Context& c, const u64* src, long long bstride, long long cstride,
@@ -769,7 +1349,13 @@ void launch_divround1_ntt(const Context& c, const u64* src, long long bstride, l
 {
     MapDivRoundOne m{src, out, bstride, cstride, Lout, c.logn, half, plast, d_half_mod};
     const long long wo = (batch * 2 * Lout) << c.logn;
-    run_ntt(c, m, batch * 2 * Lout, false, Extent{out, wo, out, wo}, st);
+    Extent e{out, wo, out, wo};
+    if ((bstride & 255) == 0 && (cstride & 255) == 0)
+    {
+        e.col_in_base = src;
+        e.col_in_words = (batch - 1) * bstride + cstride + (1ll << c.logn);
+    }
+    run_ntt(c, m, batch * 2 * Lout, false, e, st);
 }
 
 } // namespace heon

@@ -44,6 +44,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
                  : "memory");
 }
 
+// non-blocking probe of a barrier phase
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t"
+                 ".reg .pred P1;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, P1;\n\t"
+                 "}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+
 // global -> shared tile load, completion signalled on `bar` (complete_tx::bytes)
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1)
 {
@@ -60,6 +75,39 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, un
                      smem_u32(smem_dst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
+                                            int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// wait until all but the N most recent committed stores are COMPLETE (globally performed)
+template <int N> __device__ __forceinline__ void tma_store_wait_all()
+{
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 // shared -> global tile store (bulk async group)
