@@ -39,6 +39,11 @@ SIGNATURES = {
     "heon_negate": (ci, [vp, vp, ll, vp, ll, ci, ci, ci, vp]),
     "heon_ckks_multiply": (ci, [vp, vp, ll, vp, ll, vp, ll, ci, ci, vp]),
     "heon_ckks_relinearize": (ci, [vp, vp, ll, vp, ci, ci, vp]),
+    "heon_ckks_multiply_plain": (ci, [vp, vp, ll, vp, ll, vp, ll, ci, ci, ci, vp]),
+    "heon_ckks_add_plain": (ci, [vp, vp, ll, vp, ll, vp, ll, ci, ci, ci, vp]),
+    "heon_ckks_sub_plain": (ci, [vp, vp, ll, vp, ll, vp, ll, ci, ci, ci, vp]),
+    "heon_ckks_keyswitch": (ci, [vp, vp, ll, vp, ll, vp, ci, ci, vp]),
+    "heon_ckks_conjugate": (ci, [vp, vp, ll, vp, ll, vp, ci, ci, vp]),
     "heon_ckks_rescale": (ci, [vp, vp, ll, ci, ci, vp]),
     "heon_ckks_mod_drop_inplace": (ci, [vp, vp, ll, ci, ci, ci, vp]),
     "heon_ckks_mod_drop": (ci, [vp, vp, ll, vp, ll, ci, ci, vp]),

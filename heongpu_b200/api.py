@@ -179,15 +179,38 @@ class Relinkey(_EvalKey):
     (reference: src/lib/kernel/keygeneration.cu:180-183)."""
 
 
+class Switchkey(_EvalKey):
+    """Switchkey<Scheme::CKKS>: same layout as the Relinkey, re-encrypts under another secret key
+    (reference: src/lib/host/ckks/evaluationkey.cu)."""
+
+
+class Plaintext:
+    """Plaintext<Scheme::CKKS>: [L][N] words in the NTT domain (reference: ckks/plaintext.cu), optionally batched."""
+
+    def __init__(self, context, data, depth=0, scale=1.0):
+        self.context = context
+        if data.dim() == 2:
+            data = data.unsqueeze(0)
+        self.data = data
+        self.depth_ = depth
+        self.scale_ = scale
+
+    @property
+    def stride(self):
+        return self.data.stride(0) if self.data.shape[0] > 1 else 0
+
+
 class Galoiskey:
     """Galoiskey<Scheme::CKKS>: map galois_elt -> key of the Relinkey layout
     (reference: src/lib/host/ckks/evaluationkey.cu, device_location_)."""
 
     group_order_ = 5
 
-    def __init__(self, context, keys):
+    def __init__(self, context, keys, conjugate_key=None):
         self.context = context
         self.device_location_ = dict(keys)
+        self.galois_elt_zero = 2 * context.n - 1
+        self.zero_device_location_ = conjugate_key  # Galoiskey::c_data()
 
 
 class HEArithmeticOperator:
@@ -222,6 +245,46 @@ class HEArithmeticOperator:
         c = self.context_
         _check(lib.heon_negate(c._h, _ptr(a.data), a.stride, _ptr(out.data), out.stride, a.cipher_size_, a.depth_, a.batch, _stream()))
         out.depth_, out.cipher_size_ = a.depth_, a.cipher_size_
+        return out
+
+    # -- plaintext operands (operator.cuh:197-620,718-884) --
+    def _plain(self, fn, ct, pt, out, scale):
+        if ct.depth_ != pt.depth_:
+            raise HeonLogicError("Ciphertexts leveled are not equal")
+        c = self.context_
+        _check(fn(c._h, _ptr(ct.data), ct.stride, _ptr(pt.data), pt.stride, _ptr(out.data), out.stride,
+                  ct.cipher_size_, ct.depth_, ct.batch, _stream()))
+        out.depth_, out.cipher_size_, out.scale_ = ct.depth_, ct.cipher_size_, scale
+        out.relinearization_required_ = ct.relinearization_required_
+        out.rescale_required_ = ct.rescale_required_
+        return out
+
+    def multiply_plain(self, ct, pt, out):
+        out = self._plain(lib.heon_ckks_multiply_plain, ct, pt, out, ct.scale_ * pt.scale_)
+        out.rescale_required_ = True
+        return out
+
+    def add_plain(self, ct, pt, out):
+        return self._plain(lib.heon_ckks_add_plain, ct, pt, out, ct.scale_)
+
+    def sub_plain(self, ct, pt, out):
+        return self._plain(lib.heon_ckks_sub_plain, ct, pt, out, ct.scale_)
+
+    # -- keyswitch / conjugate (operator.cuh:1282-1420) --
+    def keyswitch(self, ct, out, switch_key):
+        c = self.context_
+        _check(lib.heon_ckks_keyswitch(c._h, _ptr(ct.data), ct.stride, _ptr(out.data), out.stride,
+                                       _ptr(switch_key.data), ct.depth_, ct.batch, _stream()))
+        out.depth_, out.cipher_size_, out.scale_ = ct.depth_, 2, ct.scale_
+        return out
+
+    def conjugate(self, ct, out, galois_key):
+        c = self.context_
+        if galois_key.zero_device_location_ is None:
+            raise HeonLogicError("Conjugation key not present!")
+        _check(lib.heon_ckks_conjugate(c._h, _ptr(ct.data), ct.stride, _ptr(out.data), out.stride,
+                                       _ptr(galois_key.zero_device_location_), ct.depth_, ct.batch, _stream()))
+        out.depth_, out.cipher_size_, out.scale_ = ct.depth_, 2, ct.scale_
         return out
 
     # -- multiply / relinearize / rescale (operator.cuh:631-707,1053-1094,1423-1445) --

@@ -470,6 +470,63 @@ int heon_ckks_multiply(heon_context_t ctx, const uint64_t* a, long long as, cons
     });
 }
 
+int heon_ckks_multiply_plain(heon_context_t ctx, const uint64_t* ct, long long cs, const uint64_t* pt,
+                             long long ps, uint64_t* out, long long os, int comps, int depth, int batch,
+                             void* stream)
+{
+    return guarded([&] {
+        HEON_OP_PROLOGUE
+        if (!ct || !pt || !out)
+            throw std::invalid_argument("null argument");
+        op_plain(c, ct, cs, pt, ps, out, os, comps, depth, batch, 0, st);
+    });
+}
+int heon_ckks_add_plain(heon_context_t ctx, const uint64_t* ct, long long cs, const uint64_t* pt, long long ps,
+                        uint64_t* out, long long os, int comps, int depth, int batch, void* stream)
+{
+    return guarded([&] {
+        HEON_OP_PROLOGUE
+        if (!ct || !pt || !out)
+            throw std::invalid_argument("null argument");
+        op_plain(c, ct, cs, pt, ps, out, os, comps, depth, batch, 1, st);
+    });
+}
+int heon_ckks_sub_plain(heon_context_t ctx, const uint64_t* ct, long long cs, const uint64_t* pt, long long ps,
+                        uint64_t* out, long long os, int comps, int depth, int batch, void* stream)
+{
+    return guarded([&] {
+        HEON_OP_PROLOGUE
+        if (!ct || !pt || !out)
+            throw std::invalid_argument("null argument");
+        op_plain(c, ct, cs, pt, ps, out, os, comps, depth, batch, 2, st);
+    });
+}
+
+int heon_ckks_keyswitch(heon_context_t ctx, const uint64_t* in, long long is, uint64_t* out, long long os,
+                        const uint64_t* switch_key, int depth, int batch, void* stream)
+{
+    return guarded([&] {
+        HEON_OP_PROLOGUE
+        if (!in || !out || !switch_key || in == out)
+            throw std::invalid_argument("keyswitch needs distinct, non-null buffers");
+        op_keyswitch(c, in, is, out, os, switch_key, depth, batch, st);
+    });
+}
+
+int heon_ckks_conjugate(heon_context_t ctx, const uint64_t* in, long long is, uint64_t* out, long long os,
+                        const uint64_t* conjugate_key, int depth, int batch, void* stream)
+{
+    return guarded([&] {
+        HEON_OP_PROLOGUE
+        if (!in || !out || !conjugate_key || in == out)
+            throw std::invalid_argument("conjugate needs distinct, non-null buffers");
+        if (c.scheme != SCHEME_CKKS)
+            throw std::invalid_argument("not a CKKS context");
+        // galois_elt_zero = 2N - 1 (ckks/evaluationkey.cu: conjugation key)
+        op_apply_galois(c, in, is, out, os, conjugate_key, (unsigned) (2 * c.n - 1), depth, batch, st);
+    });
+}
+
 int heon_ckks_relinearize(heon_context_t ctx, uint64_t* ct, long long cs, const uint64_t* relin_key,
                           int depth, int batch, void* stream)
 {

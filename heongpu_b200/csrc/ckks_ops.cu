@@ -69,6 +69,45 @@ __global__ void __launch_bounds__(256)
     out[bz * o_bs + loc] = r;
 }
 
+// ct (x) pt per limb, every component.
+// reference: src/lib/kernel/multiplication.cu:313-331 (cipherplain_multiplication_kernel)
+__global__ void __launch_bounds__(256)
+    k_multiply_plain(const u64* __restrict__ ct, const u64* __restrict__ pt, u64* __restrict__ out,
+                     long long ct_bs, long long pt_bs, long long o_bs, const Mod64* __restrict__ mods,
+                     int logn, int L, int comps)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    const long long bz = blockIdx.z / comps;
+    const int c = blockIdx.z % comps;
+    const long long loc = idx + ((long long) (c * L + y) << logn);
+    const u64 x = ct[bz * ct_bs + loc];
+    const u64 m = pt[bz * pt_bs + idx + ((long long) y << logn)];
+    out[bz * o_bs + loc] = barrett_mul(x, m, mods[y]);
+}
+
+// component 0 +/- pt, the other components copied.
+// reference: src/lib/kernel/addition.cu:175-217 (addition_plain_ckks_poly, substraction_plain_ckks_poly)
+template <int OP>
+__global__ void __launch_bounds__(256)
+    k_addsub_plain(const u64* __restrict__ ct, const u64* __restrict__ pt, u64* __restrict__ out,
+                   long long ct_bs, long long pt_bs, long long o_bs, const Mod64* __restrict__ mods,
+                   int logn, int L, int comps)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    const long long bz = blockIdx.z / comps;
+    const int c = blockIdx.z % comps;
+    const long long loc = idx + ((long long) (c * L + y) << logn);
+    u64 x = ct[bz * ct_bs + loc];
+    if (c == 0)
+    {
+        const u64 m = pt[bz * pt_bs + idx + ((long long) y << logn)];
+        x = OP == 0 ? mod_add(x, m, mods[y].value) : mod_sub(x, m, mods[y].value);
+    }
+    out[bz * o_bs + loc] = x;
+}
+
 // ---------------------------------------------------------------------------
 // key-switch inner product
 // ---------------------------------------------------------------------------
@@ -599,6 +638,28 @@ void op_multiply(const Context& c, const u64* a, long long a_bs, const u64* b, l
     check_launch();
 }
 
+// multiply_plain_ckks / add_plain_ckks / sub_plain_ckks (ckks/operator.cu:839-871, 302-345, 434-477):
+// op 0 multiply (every component), 1 add, 2 subtract (component 0 only, the rest copied).
+void op_plain(const Context& c, const u64* ct, long long ct_bs, const u64* pt, long long pt_bs, u64* out,
+              long long o_bs, int comps, int depth, int batch, int op, cudaStream_t st)
+{
+    check_depth(c, depth);
+    if (comps < 1 || comps > 3)
+        throw std::invalid_argument("Invalid Ciphertexts size!");
+    const int L = c.Q_size - depth;
+    dim3 g(c.n >> 8, L, batch * comps);
+    {
+        LaunchScope scope(KC_ELEMENTWISE, st);
+        if (op == 0)
+            k_multiply_plain<<<g, 256, 0, st>>>(ct, pt, out, ct_bs, pt_bs, o_bs, c.d_mod, c.logn, L, comps);
+        else if (op == 1)
+            k_addsub_plain<0><<<g, 256, 0, st>>>(ct, pt, out, ct_bs, pt_bs, o_bs, c.d_mod, c.logn, L, comps);
+        else
+            k_addsub_plain<1><<<g, 256, 0, st>>>(ct, pt, out, ct_bs, pt_bs, o_bs, c.d_mod, c.logn, L, comps);
+    }
+    check_launch();
+}
+
 // Key-switch core shared by relinearize / apply_galois / keyswitch:
 // takes the digit polynomial(s) in the coefficient domain and leaves
 // acc[b][2][Qpl][N] (NTT domain).  `tmp` must hold batch*d*Qpl*N words.
@@ -726,6 +787,26 @@ void op_relinearize(const Context& c, u64* ct, long long ct_bs, const u64* relin
     Scratch acc((size_t) batch * 2 * Qpl * N * 8, st);
     keyswitch_core(c, ct + 2LL * L * N, ct_bs, relin_key, tmp.w(), acc.w(), depth, batch, st);
     moddown_add(c, acc.w(), tmp.w(), ct, ct_bs, ct, ct_bs, depth, batch, 3, st);
+}
+
+// out = (c0, 0) + KeySwitch(c1): re-encrypts `in` under the key the switch key targets.
+// in, out: [b][2][L][N], NTT domain, distinct buffers.
+// reference: ckks/operator.cu:1722-1863 (switchkey_ckks_method_I), 1865-2025 (method_II)
+void op_keyswitch(const Context& c, const u64* in, long long in_bs, u64* out, long long out_bs,
+                  const u64* switch_key, int depth, int batch, cudaStream_t st)
+{
+    check_depth(c, depth);
+    if (c.scheme != SCHEME_CKKS)
+        throw std::invalid_argument("not a CKKS context");
+    const int L = c.Q_size - depth, K = c.P_size, Qpl = L + K;
+    const long long N = c.n;
+    // INTT(c1) into scratch (the input stays untouched)
+    Scratch coef((size_t) batch * L * N * 8, st);
+    launch_ntt_strided_copy(c, in + (long long) L * N, in_bs, coef.w(), L, batch, range_primes(0, L), true, st);
+    Scratch tmp(ks_tmp_words(c, depth, batch) * 8, st);
+    Scratch acc((size_t) batch * 2 * Qpl * N * 8, st);
+    keyswitch_core(c, coef.w(), L * N, switch_key, tmp.w(), acc.w(), depth, batch, st);
+    moddown_add(c, acc.w(), tmp.w(), in, in_bs, out, out_bs, depth, batch, 1, st);
 }
 
 // BFV relinearize: ct [b][3][Q][N] in the COEFFICIENT domain, in place.

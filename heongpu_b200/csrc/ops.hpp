@@ -35,6 +35,10 @@ void profile_end(double* ms, long long* launches);
 
 void op_add(const Context& c, const u64* a, long long a_bs, const u64* b, long long b_bs, u64* out,
             long long o_bs, int comps, int depth, int batch, int op, cudaStream_t st);
+void op_plain(const Context& c, const u64* ct, long long ct_bs, const u64* pt, long long pt_bs, u64* out,
+              long long o_bs, int comps, int depth, int batch, int op, cudaStream_t st);
+void op_keyswitch(const Context& c, const u64* in, long long in_bs, u64* out, long long out_bs,
+                  const u64* switch_key, int depth, int batch, cudaStream_t st);
 void op_multiply(const Context& c, const u64* a, long long a_bs, const u64* b, long long b_bs,
                  u64* out, long long o_bs, int depth, int batch, cudaStream_t st);
 void op_relinearize(const Context& c, u64* ct, long long ct_bs, const u64* relin_key, int depth,

@@ -7,11 +7,17 @@
 //   heongpu::HEContext<S> / GenHEContext<S>(...)                            src/include/heongpu/host/ckks/context.cuh
 //   heongpu::Ciphertext<S>                                                  src/include/heongpu/host/ckks/ciphertext.cuh:77-209
 //   heongpu::Relinkey<S>, Galoiskey<S>                                      src/include/heongpu/host/ckks/evaluationkey.cuh
+//   heongpu::Plaintext<S>, Switchkey<S>                                    src/include/heongpu/host/ckks/{plaintext,evaluationkey}.cuh
 //   heongpu::HEArithmeticOperator<S>::{add,sub,negate,multiply,multiply_inplace,
+//       multiply_plain,add_plain[_inplace],sub_plain[_inplace],
 //       relinearize_inplace,rescale_inplace,mod_drop_inplace,mod_drop,
-//       rotate_rows,rotate_rows_inplace,apply_galois,apply_galois_inplace}  src/include/heongpu/host/ckks/operator.cuh:95-1600
+//       rotate_rows,rotate_rows_inplace,apply_galois,apply_galois_inplace,
+//       keyswitch,conjugate}                                                src/include/heongpu/host/ckks/operator.cuh:95-1600
+//   the BFV twins (HEContext<BFV>, Ciphertext<BFV>, Relinkey<BFV>, Galoiskey<BFV>,
+//       HEArithmeticOperator<BFV>::{add,sub,negate,multiply,relinearize_inplace,
+//       rotate_rows,rotate_columns,apply_galois})                           src/include/heongpu/host/bfv/operator.cuh
 //
-// Scope: the CKKS hot path.  Key generation, encoding and
+// Scope: the CKKS and BFV hot path.  Key generation, encoding and
 // encryption are client-side "next" rows: Relinkey / Galoiskey here are
 // containers in the reference layout that the caller fills (set_data), and
 // Ciphertext can be constructed from raw words.  Host-parsable (no CUDA
@@ -318,13 +324,71 @@ template <> class Galoiskey<Scheme::CKKS> {
             throw std::invalid_argument("Invalid galois key size!");
         device_location_[galois_element] = DeviceVector<Data64>(words, st);
     }
+    // conjugation key (galois_elt_zero = 2N-1), Galoiskey::c_data() in the reference
+    void set_conjugate_key(const std::vector<Data64>& words, cudaStream_t st = cudaStreamDefault)
+    {
+        const size_t need = (size_t) context_->digit_count(0) * 2 * context_->Q_prime_size * context_->n;
+        if (words.size() != need)
+            throw std::invalid_argument("Invalid galois key size!");
+        zero_device_location_ = DeviceVector<Data64>(words, st);
+        galois_elt_zero = 2 * context_->n - 1;
+    }
+    Data64* c_data() const { return zero_device_location_.data(); }
     HEContext<Scheme::CKKS> context_;
     keyswitching_type key_type;
     storage_type storage_type_ = storage_type::DEVICE;
     int group_order_ = 5;
     bool customized = false;
+    int galois_elt_zero = 0;
     std::unordered_map<int, int> galois_elt; // shift -> galois element
     std::unordered_map<int, DeviceVector<Data64>> device_location_; // galois element -> key
+    DeviceVector<Data64> zero_device_location_;
+};
+
+template <Scheme S> class Plaintext;
+// Plaintext<CKKS>: [L][N] words in the NTT domain (ckks/plaintext.cu); encoding is a client-side
+// "next" row, so the caller supplies the encoded words.
+template <> class Plaintext<Scheme::CKKS> {
+  public:
+    Plaintext() = default;
+    Plaintext(HEContext<Scheme::CKKS> ctx, const std::vector<Data64>& words, int depth = 0, double scale = 1.0,
+              const ExecutionOptions& opt = ExecutionOptions())
+        : context_(ctx), device_locations_(words, opt.stream_), depth_(depth), scale_(scale)
+    {
+        if (words.size() < (size_t) (ctx->Q_size - depth) * ctx->n)
+            throw std::invalid_argument("Invalid Plaintext size!");
+        plain_size_ = (int) words.size();
+        plaintext_generated_ = true;
+    }
+    Data64* data() const { return device_locations_.data(); }
+    size_t size() const { return device_locations_.size(); }
+    int depth() const { return depth_; }
+    double scale() const { return scale_; }
+    HEContext<Scheme::CKKS> context_;
+    DeviceVector<Data64> device_locations_;
+    int plain_size_ = 0, depth_ = 0;
+    double scale_ = 0;
+    bool in_ntt_domain_ = true, plaintext_generated_ = false;
+};
+
+template <Scheme S> class Switchkey;
+template <> class Switchkey<Scheme::CKKS> {
+  public:
+    explicit Switchkey(HEContext<Scheme::CKKS> ctx) : context_(ctx), key_type(ctx->keyswitching_type_) {}
+    void set_data(const std::vector<Data64>& words, cudaStream_t st = cudaStreamDefault)
+    {
+        const size_t need = (size_t) context_->digit_count(0) * 2 * context_->Q_prime_size * context_->n;
+        if (words.size() != need)
+            throw std::invalid_argument("Invalid switch key size!");
+        device_location_ = DeviceVector<Data64>(words, st);
+        switch_key_generated_ = true;
+    }
+    Data64* data() const { return device_location_.data(); }
+    HEContext<Scheme::CKKS> context_;
+    keyswitching_type key_type;
+    storage_type storage_type_ = storage_type::DEVICE;
+    DeviceVector<Data64> device_location_;
+    bool switch_key_generated_ = false;
 };
 
 template <Scheme S> class HEEncoder; // client-side ("next" row); only named in the operator constructor
@@ -489,7 +553,79 @@ template <> class HEOperator<Scheme::CKKS> {
         rotate_rows(ct, ct, gk, shift, opt);
     }
 
+    // operator.cuh:718-884 + multiply_plain_ckks (operator.cu:839-871)
+    void multiply_plain(Ciphertext<Scheme::CKKS>& a, Plaintext<Scheme::CKKS>& p, Ciphertext<Scheme::CKKS>& out,
+                        const ExecutionOptions& opt = ExecutionOptions())
+    {
+        plain(a, p, out, opt, 0);
+        out.scale_ = a.scale_ * p.scale_;
+        out.rescale_required_ = true;
+    }
+    // operator.cuh:197-620 + add_plain_ckks / sub_plain_ckks (operator.cu:302-345, 434-477)
+    void add_plain(Ciphertext<Scheme::CKKS>& a, Plaintext<Scheme::CKKS>& p, Ciphertext<Scheme::CKKS>& out,
+                   const ExecutionOptions& opt = ExecutionOptions())
+    {
+        plain(a, p, out, opt, 1);
+    }
+    void add_plain_inplace(Ciphertext<Scheme::CKKS>& a, Plaintext<Scheme::CKKS>& p, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        plain(a, p, a, opt, 1);
+    }
+    void sub_plain(Ciphertext<Scheme::CKKS>& a, Plaintext<Scheme::CKKS>& p, Ciphertext<Scheme::CKKS>& out,
+                   const ExecutionOptions& opt = ExecutionOptions())
+    {
+        plain(a, p, out, opt, 2);
+    }
+    void sub_plain_inplace(Ciphertext<Scheme::CKKS>& a, Plaintext<Scheme::CKKS>& p, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        plain(a, p, a, opt, 2);
+    }
+
+    // operator.cuh:1282-1340 + switchkey_ckks_method_I/II (operator.cu:1722-2025)
+    void keyswitch(Ciphertext<Scheme::CKKS>& in, Ciphertext<Scheme::CKKS>& out, Switchkey<Scheme::CKKS>& sk,
+                   const ExecutionOptions& opt = ExecutionOptions())
+    {
+        if (in.rescale_required_ || in.relinearization_required_)
+            throw std::invalid_argument("Ciphertext can not be key-switched because of the non-linear part or noise!");
+        if (!sk.switch_key_generated_)
+            throw std::invalid_argument("Switchkey is not generated!");
+        DeviceVector<Data64> mem(words(2, in.depth_), opt.stream_);
+        detail::check(heon_ckks_keyswitch(h(), in.data(), 0, mem.data(), 0, sk.data(), in.depth_, 1, opt.stream_));
+        copy_meta(in, out);
+        out.memory_set(std::move(mem));
+        out.cipher_size_ = 2;
+    }
+    // operator.cuh:1354-1420 + conjugate_ckks_method_I/II (operator.cu:2027-2311)
+    void conjugate(Ciphertext<Scheme::CKKS>& in, Ciphertext<Scheme::CKKS>& out, Galoiskey<Scheme::CKKS>& gk,
+                   const ExecutionOptions& opt = ExecutionOptions())
+    {
+        if (in.rescale_required_ || in.relinearization_required_)
+            throw std::invalid_argument("Ciphertext can not be conjugated because of the non-linear part or noise!");
+        if (!gk.c_data())
+            throw std::logic_error("Conjugation key not present!");
+        DeviceVector<Data64> mem(words(2, in.depth_), opt.stream_);
+        detail::check(heon_ckks_conjugate(h(), in.data(), 0, mem.data(), 0, gk.c_data(), in.depth_, 1, opt.stream_));
+        copy_meta(in, out);
+        out.memory_set(std::move(mem));
+        out.cipher_size_ = 2;
+    }
+
   private:
+    void plain(Ciphertext<Scheme::CKKS>& a, Plaintext<Scheme::CKKS>& p, Ciphertext<Scheme::CKKS>& out,
+               const ExecutionOptions& opt, int op)
+    {
+        if (a.depth_ != p.depth_)
+            throw std::logic_error("Ciphertexts leveled are not equal");
+        if (a.memory_size() < words(a.cipher_size_, a.depth_))
+            throw std::invalid_argument("Invalid Ciphertexts size!");
+        if (p.size() < words(1, a.depth_))
+            throw std::invalid_argument("Invalid Plaintext size!");
+        DeviceVector<Data64> mem(words(a.cipher_size_, a.depth_), opt.stream_);
+        auto fn = op == 0 ? heon_ckks_multiply_plain : op == 1 ? heon_ckks_add_plain : heon_ckks_sub_plain;
+        detail::check(fn(h(), a.data(), 0, p.data(), 0, mem.data(), 0, a.cipher_size_, a.depth_, 1, opt.stream_));
+        copy_meta(a, out);
+        out.memory_set(std::move(mem));
+    }
     void binary(Ciphertext<Scheme::CKKS>& a, Ciphertext<Scheme::CKKS>& b, Ciphertext<Scheme::CKKS>& out,
                 const ExecutionOptions& opt, int op)
     {
@@ -511,6 +647,306 @@ template <> class HEArithmeticOperator<Scheme::CKKS> : public HEOperator<Scheme:
     explicit HEArithmeticOperator(HEContext<Scheme::CKKS> context) : HEOperator<Scheme::CKKS>(context) {}
     // reference signature (ckks/operator.cu:6680); the encoder is not used by the hot path
     HEArithmeticOperator(HEContext<Scheme::CKKS> context, HEEncoder<Scheme::CKKS>&) : HEOperator<Scheme::CKKS>(context) {}
+};
+
+// ---------------------------------------------------------------------------
+// BFV twins (src/include/heongpu/host/bfv/*.cuh).  Ciphertexts live in the
+// COEFFICIENT domain, there are no levels (depth 0 everywhere on this path).
+// ---------------------------------------------------------------------------
+template <> class HEContextImpl<Scheme::BFV> {
+  public:
+    explicit HEContextImpl(sec_level_type sec = sec_level_type::sec128, int device = 0) : sec_level_(sec), device_(device) {}
+    ~HEContextImpl()
+    {
+        if (h_)
+            heon_context_destroy(h_);
+    }
+    void set_poly_modulus_degree(size_t n)
+    {
+        if (coeff_modulus_specified_ || poly_modulus_degree_specified_)
+            throw std::logic_error("Poly modulus degree cannot be changed after the coeff_modulus is specified!");
+        if (n == 0 || (n & (n - 1)))
+            throw std::logic_error("Poly modulus degree have to be power of two");
+        if (n > 65536 || n < 4096)
+            throw std::logic_error("Poly modulus degree is not supported");
+        this->n = (int) n;
+        n_power = 0;
+        while ((size_t(1) << n_power) < n)
+            ++n_power;
+        poly_modulus_degree_specified_ = true;
+    }
+    void set_coeff_modulus_bit_sizes(const std::vector<int>& q_bits, const std::vector<int>& p_bits)
+    {
+        if (coeff_modulus_specified_ || context_generated_ || !poly_modulus_degree_specified_)
+            throw std::logic_error("Coeff_modulus cannot be changed after the context is generated!");
+        if (p_bits.empty())
+            throw std::logic_error("log_P_bases_bit_sizes cannot be empty!");
+        q_bits_ = q_bits;
+        p_bits_ = p_bits;
+        coeff_modulus_specified_ = true;
+    }
+    void set_plain_modulus(int t)
+    {
+        if (context_generated_)
+            throw std::logic_error("Plain modulus cannot be changed after the context is generated!");
+        plain_modulus_ = (Data64) t;
+        plain_modulus_specified_ = true;
+    }
+    void generate()
+    {
+        if (context_generated_ || !poly_modulus_degree_specified_ || !coeff_modulus_specified_ || !plain_modulus_specified_)
+            throw std::runtime_error("Context is already generated or not fully specified!");
+        detail::check(heon_bfv_context_create(device_, n_power, q_bits_.data(), (int) q_bits_.size(), p_bits_.data(),
+                                              (int) p_bits_.size(), plain_modulus_, &h_));
+        heon_info info;
+        detail::check(heon_context_info(h_, &info));
+        Q_size = info.q_size;
+        P_size = info.p_size;
+        Q_prime_size = Q_size + P_size;
+        keyswitching_type_ = info.keyswitch_method == 1 ? keyswitching_type::KEYSWITCHING_METHOD_I
+                                                        : keyswitching_type::KEYSWITCHING_METHOD_II;
+        size_t cnt = 0;
+        detail::check(heon_context_table(h_, HEON_TBL_MODULUS, 0, nullptr, 0, &cnt));
+        std::vector<Data64> raw(cnt);
+        detail::check(heon_context_table(h_, HEON_TBL_MODULUS, 0, raw.data(), cnt, &cnt));
+        prime_vector_.clear();
+        for (size_t i = 0; i < cnt && prime_vector_.size() < (size_t) Q_prime_size; i += 3)
+            prime_vector_.push_back(Modulus64{raw[i], raw[i + 1], raw[i + 2]});
+        context_generated_ = true;
+    }
+    int digit_count() const { return P_size == 1 ? Q_size : (Q_size + P_size - 1) / P_size; }
+    heon_context_t handle() const { return h_; }
+    size_t get_poly_modulus_degree() const { return (size_t) n; }
+
+    int n = 0, n_power = 0;
+    int Q_size = 0, P_size = 0, Q_prime_size = 0;
+    Data64 plain_modulus_ = 0;
+    keyswitching_type keyswitching_type_ = keyswitching_type::NONE;
+    std::vector<Modulus64> prime_vector_;
+    bool context_generated_ = false;
+
+  private:
+    sec_level_type sec_level_;
+    int device_;
+    heon_context_t h_ = nullptr;
+    std::vector<int> q_bits_, p_bits_;
+    bool poly_modulus_degree_specified_ = false, coeff_modulus_specified_ = false, plain_modulus_specified_ = false;
+};
+
+template <> class Ciphertext<Scheme::BFV> {
+  public:
+    Ciphertext() = default;
+    // [cipher_size][Q][N] words, coefficient domain (bfv/ciphertext.cu)
+    Ciphertext(HEContext<Scheme::BFV> ctx, const std::vector<Data64>& words, int cipher_size = 2,
+               const ExecutionOptions& opt = ExecutionOptions())
+        : context_(ctx), device_locations_(words, opt.stream_), cipher_size_(cipher_size)
+    {
+        ring_size_ = ctx->n;
+        coeff_modulus_count_ = ctx->Q_size;
+        if (words.size() < (size_t) cipher_size * ctx->Q_size * ctx->n)
+            throw std::invalid_argument("Invalid Ciphertexts size!");
+        ciphertext_generated_ = true;
+    }
+    Data64* data() const { return device_locations_.data(); }
+    size_t memory_size() const { return device_locations_.size(); }
+    void memory_set(DeviceVector<Data64>&& v) { device_locations_ = std::move(v); }
+    void get_data(std::vector<Data64>& out, cudaStream_t st = cudaStreamDefault) const
+    {
+        out.resize((size_t) cipher_size_ * coeff_modulus_count_ * ring_size_);
+        detail::cuda(cudaMemcpyAsync(out.data(), data(), out.size() * sizeof(Data64), cudaMemcpyDeviceToHost, st));
+        detail::cuda(cudaStreamSynchronize(st));
+    }
+    int size() const { return cipher_size_; }
+    bool in_ntt_domain() const { return in_ntt_domain_; }
+    bool relinearization_required() const { return relinearization_required_; }
+
+    HEContext<Scheme::BFV> context_;
+    DeviceVector<Data64> device_locations_;
+    int ring_size_ = 0, coeff_modulus_count_ = 0, cipher_size_ = 0;
+    bool in_ntt_domain_ = false, relinearization_required_ = false, ciphertext_generated_ = false;
+};
+
+template <> class Relinkey<Scheme::BFV> {
+  public:
+    explicit Relinkey(HEContext<Scheme::BFV> ctx) : context_(ctx), key_type(ctx->keyswitching_type_) {}
+    void set_data(const std::vector<Data64>& words, cudaStream_t st = cudaStreamDefault)
+    {
+        const size_t need = (size_t) context_->digit_count() * 2 * context_->Q_prime_size * context_->n;
+        if (words.size() != need)
+            throw std::invalid_argument("Invalid relinearization key size!");
+        device_location_ = DeviceVector<Data64>(words, st);
+        relin_key_generated_ = true;
+    }
+    Data64* data() const { return device_location_.data(); }
+    HEContext<Scheme::BFV> context_;
+    keyswitching_type key_type;
+    storage_type storage_type_ = storage_type::DEVICE;
+    DeviceVector<Data64> device_location_;
+    bool relin_key_generated_ = false;
+};
+
+template <> class Galoiskey<Scheme::BFV> {
+  public:
+    explicit Galoiskey(HEContext<Scheme::BFV> ctx) : context_(ctx), key_type(ctx->keyswitching_type_)
+    {
+        for (int i = 0; i < 8; ++i) // default keys for +-2^i, i < MAX_SHIFT (bfv/evaluationkey.cu:306-345)
+        {
+            galois_elt[1 << i] = heon_steps_to_galois_elt(1 << i, ctx->n, group_order_);
+            galois_elt[-(1 << i)] = heon_steps_to_galois_elt(-(1 << i), ctx->n, group_order_);
+        }
+        galois_elt_zero = 2 * ctx->n - 1;
+    }
+    Galoiskey(HEContext<Scheme::BFV> ctx, const std::vector<int>& shifts) : context_(ctx), key_type(ctx->keyswitching_type_)
+    {
+        customized = true;
+        for (int s : shifts)
+            galois_elt[s] = heon_steps_to_galois_elt(s, ctx->n, group_order_);
+        galois_elt_zero = 2 * ctx->n - 1;
+    }
+    void set_key(int galois_element, const std::vector<Data64>& words, cudaStream_t st = cudaStreamDefault)
+    {
+        const size_t need = (size_t) context_->digit_count() * 2 * context_->Q_prime_size * context_->n;
+        if (words.size() != need)
+            throw std::invalid_argument("Invalid galois key size!");
+        device_location_[galois_element] = DeviceVector<Data64>(words, st);
+    }
+    HEContext<Scheme::BFV> context_;
+    keyswitching_type key_type;
+    storage_type storage_type_ = storage_type::DEVICE;
+    int group_order_ = 3;
+    bool customized = false;
+    int galois_elt_zero = 0; // column rotation
+    std::unordered_map<int, int> galois_elt;
+    std::unordered_map<int, DeviceVector<Data64>> device_location_;
+};
+
+template <> class HEOperator<Scheme::BFV> {
+  protected:
+    explicit HEOperator(HEContext<Scheme::BFV> context)
+    {
+        if (!context || !context->context_generated_)
+            throw std::invalid_argument("HEContext is not generated!");
+        context_ = std::move(context);
+    }
+    HEContext<Scheme::BFV> context_;
+    heon_context_t h() const { return context_->handle(); }
+    size_t words(int comps) const { return (size_t) comps * context_->Q_size * context_->n; }
+    static void copy_meta(const Ciphertext<Scheme::BFV>& a, Ciphertext<Scheme::BFV>& o)
+    {
+        o.context_ = a.context_;
+        o.ring_size_ = a.ring_size_;
+        o.coeff_modulus_count_ = a.coeff_modulus_count_;
+        o.cipher_size_ = a.cipher_size_;
+        o.in_ntt_domain_ = a.in_ntt_domain_;
+        o.relinearization_required_ = a.relinearization_required_;
+        o.ciphertext_generated_ = true;
+    }
+
+  public:
+    void add(Ciphertext<Scheme::BFV>& a, Ciphertext<Scheme::BFV>& b, Ciphertext<Scheme::BFV>& out,
+             const ExecutionOptions& opt = ExecutionOptions())
+    {
+        binary(a, b, out, opt, 0);
+    }
+    void sub(Ciphertext<Scheme::BFV>& a, Ciphertext<Scheme::BFV>& b, Ciphertext<Scheme::BFV>& out,
+             const ExecutionOptions& opt = ExecutionOptions())
+    {
+        binary(a, b, out, opt, 1);
+    }
+    void negate(Ciphertext<Scheme::BFV>& a, Ciphertext<Scheme::BFV>& out, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        DeviceVector<Data64> mem(words(a.cipher_size_), opt.stream_);
+        detail::check(heon_negate(h(), a.data(), 0, mem.data(), 0, a.cipher_size_, 0, 1, opt.stream_));
+        copy_meta(a, out);
+        out.memory_set(std::move(mem));
+    }
+    // bfv/operator.cuh multiply + multiply_bfv (bfv/operator.cu:336-430)
+    void multiply(Ciphertext<Scheme::BFV>& a, Ciphertext<Scheme::BFV>& b, Ciphertext<Scheme::BFV>& out,
+                  const ExecutionOptions& opt = ExecutionOptions())
+    {
+        if (a.relinearization_required_ || b.relinearization_required_)
+            throw std::invalid_argument("Ciphertexts can not be multiplied because of the non-linear part! Please use relinearization operation!");
+        if (a.in_ntt_domain_ || b.in_ntt_domain_)
+            throw std::invalid_argument("Ciphertexts should be in the coefficient domain!");
+        if (a.memory_size() < words(2) || b.memory_size() < words(2))
+            throw std::invalid_argument("Invalid Ciphertexts size!");
+        DeviceVector<Data64> mem(words(3), opt.stream_);
+        detail::check(heon_bfv_multiply(h(), a.data(), 0, b.data(), 0, mem.data(), 0, 1, opt.stream_));
+        copy_meta(a, out);
+        out.memory_set(std::move(mem));
+        out.cipher_size_ = 3;
+        out.relinearization_required_ = true;
+    }
+    void multiply_inplace(Ciphertext<Scheme::BFV>& a, Ciphertext<Scheme::BFV>& b, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        multiply(a, b, a, opt);
+    }
+    // relinearize_seal_method_inplace / relinearize_external_product_method2_inplace (bfv/operator.cu:505-671)
+    void relinearize_inplace(Ciphertext<Scheme::BFV>& ct, Relinkey<Scheme::BFV>& rk, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        if (!ct.relinearization_required_)
+            throw std::invalid_argument("Ciphertexts can not use relinearization, since no non-linear part!");
+        if (!rk.relin_key_generated_)
+            throw std::invalid_argument("Relinkey is not generated!");
+        if (ct.memory_size() < words(3))
+            throw std::invalid_argument("Invalid Ciphertexts size!");
+        detail::check(heon_bfv_relinearize(h(), ct.data(), 0, rk.data(), 1, opt.stream_));
+        ct.relinearization_required_ = false;
+        ct.cipher_size_ = 2;
+    }
+    // apply_galois_method_I/II, rotate_rows, rotate_columns (bfv/operator.cu:771-973)
+    void apply_galois(Ciphertext<Scheme::BFV>& in, Ciphertext<Scheme::BFV>& out, Galoiskey<Scheme::BFV>& gk, int galois_elt,
+                      const ExecutionOptions& opt = ExecutionOptions())
+    {
+        if (in.relinearization_required_)
+            throw std::invalid_argument("Ciphertext can not be rotated because of the non-linear part!");
+        auto it = gk.device_location_.find(galois_elt);
+        if (it == gk.device_location_.end())
+            throw std::logic_error("Galois key not present!");
+        DeviceVector<Data64> mem(words(2), opt.stream_);
+        detail::check(heon_bfv_apply_galois(h(), in.data(), 0, mem.data(), 0, it->second.data(), (uint32_t) galois_elt, 1,
+                                            opt.stream_));
+        copy_meta(in, out);
+        out.memory_set(std::move(mem));
+        out.cipher_size_ = 2;
+    }
+    void rotate_rows(Ciphertext<Scheme::BFV>& in, Ciphertext<Scheme::BFV>& out, Galoiskey<Scheme::BFV>& gk, int shift,
+                     const ExecutionOptions& opt = ExecutionOptions())
+    {
+        const int elt = heon_steps_to_galois_elt(shift, context_->n, gk.group_order_);
+        if (elt == 0)
+            throw std::invalid_argument("Galois Key can not be generated, Step count too large");
+        apply_galois(in, out, gk, elt, opt);
+    }
+    void rotate_rows_inplace(Ciphertext<Scheme::BFV>& ct, Galoiskey<Scheme::BFV>& gk, int shift,
+                             const ExecutionOptions& opt = ExecutionOptions())
+    {
+        rotate_rows(ct, ct, gk, shift, opt);
+    }
+    void rotate_columns(Ciphertext<Scheme::BFV>& in, Ciphertext<Scheme::BFV>& out, Galoiskey<Scheme::BFV>& gk,
+                        const ExecutionOptions& opt = ExecutionOptions())
+    {
+        apply_galois(in, out, gk, gk.galois_elt_zero, opt);
+    }
+
+  private:
+    void binary(Ciphertext<Scheme::BFV>& a, Ciphertext<Scheme::BFV>& b, Ciphertext<Scheme::BFV>& out,
+                const ExecutionOptions& opt, int op)
+    {
+        if (a.cipher_size_ != b.cipher_size_)
+            throw std::invalid_argument("Ciphertexts should have the same size!");
+        DeviceVector<Data64> mem(words(a.cipher_size_), opt.stream_);
+        detail::check((op == 0 ? heon_add : heon_sub)(h(), a.data(), 0, b.data(), 0, mem.data(), 0, a.cipher_size_, 0, 1,
+                                                      opt.stream_));
+        copy_meta(a, out);
+        out.memory_set(std::move(mem));
+    }
+};
+
+template <> class HEArithmeticOperator<Scheme::BFV> : public HEOperator<Scheme::BFV> {
+  public:
+    explicit HEArithmeticOperator(HEContext<Scheme::BFV> context) : HEOperator<Scheme::BFV>(context) {}
+    HEArithmeticOperator(HEContext<Scheme::BFV> context, HEEncoder<Scheme::BFV>&) : HEOperator<Scheme::BFV>(context) {}
 };
 
 } // namespace heongpu

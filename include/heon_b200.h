@@ -146,6 +146,31 @@ int heon_ckks_multiply(heon_context_t ctx, const uint64_t* a, long long a_stride
                        long long b_stride, uint64_t* out, long long out_stride, int depth, int batch,
                        void* stream);
 
+/* ---- multiply_plain_ckks (operator.cu:839-871; kernel multiplication.cu:313-331),
+ *      add_plain_ckks (:302-345) / sub_plain_ckks (:434-477; kernels addition.cu:175-217).
+ * ct, out: [components][L][N]; pt: [L][N] (a CKKS Plaintext lives in the NTT domain).
+ * multiply scales every component; add/sub touch component 0 and copy the rest. */
+int heon_ckks_multiply_plain(heon_context_t ctx, const uint64_t* ct, long long ct_stride, const uint64_t* pt,
+                             long long pt_stride, uint64_t* out, long long out_stride, int components,
+                             int depth, int batch, void* stream);
+int heon_ckks_add_plain(heon_context_t ctx, const uint64_t* ct, long long ct_stride, const uint64_t* pt,
+                        long long pt_stride, uint64_t* out, long long out_stride, int components, int depth,
+                        int batch, void* stream);
+int heon_ckks_sub_plain(heon_context_t ctx, const uint64_t* ct, long long ct_stride, const uint64_t* pt,
+                        long long pt_stride, uint64_t* out, long long out_stride, int components, int depth,
+                        int batch, void* stream);
+
+/* ---- switchkey_ckks_method_I / _II (operator.cu:1722-2025): HEOperator::keyswitch.
+ * out = (c0, 0) + KeySwitch(c1) under `switch_key` ([digit][2][Q'_0][N]).
+ * in, out: [2][L][N], distinct buffers. */
+int heon_ckks_keyswitch(heon_context_t ctx, const uint64_t* in, long long in_stride, uint64_t* out,
+                        long long out_stride, const uint64_t* switch_key, int depth, int batch, void* stream);
+
+/* ---- conjugate_ckks_method_I / _II (operator.cu:2027-2311): HEOperator::conjugate.
+ * apply_galois with galois_elt_zero = 2N-1 and the key's conjugation entry (Galoiskey::c_data()). */
+int heon_ckks_conjugate(heon_context_t ctx, const uint64_t* in, long long in_stride, uint64_t* out,
+                        long long out_stride, const uint64_t* conjugate_key, int depth, int batch, void* stream);
+
 /* ---- relinearize_seal_method_inplace_ckks (operator.cu:899-1023) and
  *      relinearize_external_product_method2_inplace_ckks (:1025-1154);
  * the method follows the context (P_size == 1 -> I, else II).

@@ -814,6 +814,79 @@ void oracle_apply_galois(const octx* c, const u64* in, u64* out, const u64* key,
     free(temp0);
 }
 
+/* switchkey_ckks_method_I / _II: ckks/operator.cu:1722-1863 / 1865-2025 (HEOperator::keyswitch).
+ * in, out: [2][L][N] NTT domain.  The reference takes the whole ciphertext to the coefficient
+ * domain, key-switches c1, and brings c0 back with a forward NTT before the final addition. */
+void oracle_keyswitch(const octx* c, const u64* in, u64* out, const u64* key, int depth)
+{
+    int L = c->Q - depth, K = c->K, Ql = L + K, n = c->n;
+    u64* temp0 = (u64*) malloc(sizeof(u64) * (size_t) 2 * L * n);
+    memcpy(temp0, in, sizeof(u64) * (size_t) 2 * L * n);
+    oracle_ntt_batch(c, temp0, 2 * L, NULL, L, 1); /* GPU_INTT of both components */
+    u64* acc = (u64*) malloc(sizeof(u64) * (size_t) 2 * Ql * n);
+    u64* temp1 = (u64*) malloc(sizeof(u64) * (size_t) 2 * L * n);
+    /* cipher_broadcast_switchkey_leveled_kernel (switchkey.cu:1370-1411): c0 copied aside, c1 mod-up */
+    o_keyswitch_core(c, temp0 + (size_t) L * n, key, acc, depth);
+    int* order = (int*) malloc(sizeof(int) * Ql);
+    for (int y = 0; y < Ql; y++)
+        order[y] = lvl_prime(y, L, depth);
+    if (c->method == 1) {
+        for (int cc = 0; cc < 2; cc++)
+            oracle_intt(acc + ((size_t) cc * Ql + L) * n, c->inv + ((size_t) c->Q << c->n_power),
+                        c->mod[c->Q].value, c->n_power);
+        o_stage_one(c, acc, (size_t) Ql * n, L, temp1, c->half, c->half_mod, c->Q, L);
+        oracle_ntt_batch(c, temp1, 2 * L, NULL, L, 0);
+        oracle_ntt_batch(c, temp0, L, NULL, L, 0); /* c0 back to the NTT domain */
+        /* divide_round_lastq_leveled_stage_two_switchkey_kernel: switchkey.cu:738-771 */
+        for (int bz = 0; bz < 2; bz++)
+            for (int by = 0; by < L; by++)
+                for (int idx = 0; idx < n; idx++) {
+                    const omod* m = &c->mod[by];
+                    u64 last = temp1[((size_t) bz * L + by) * n + idx];
+                    u64 in_ = acc[((size_t) bz * Ql + by) * n + idx];
+                    in_ = o_sub(in_, last, m);
+                    in_ = o_mult(in_, c->last_q_modinv[by], m);
+                    u64 ct_in = bz == 0 ? temp0[((size_t) by) * n + idx] : 0;
+                    out[((size_t) bz * L + by) * n + idx] = o_add(ct_in, in_, m);
+                }
+    } else {
+        oracle_ntt_batch(c, acc, 2 * Ql, order, Ql, 1);
+        o_moddown_ext(c, acc, temp1, NULL, 0, depth);
+        oracle_ntt_batch(c, temp1, 2 * L, NULL, L, 0);
+        oracle_ntt_batch(c, temp0, L, NULL, L, 0);
+        /* addition_switchkey: out0 = ks0 + c0, out1 = ks1 */
+        for (int bz = 0; bz < 2; bz++)
+            for (int by = 0; by < L; by++)
+                for (int idx = 0; idx < n; idx++) {
+                    size_t o = ((size_t) bz * L + by) * n + idx;
+                    out[o] = bz == 0 ? o_add(temp1[o], temp0[o], &c->mod[by]) : temp1[o];
+                }
+    }
+    free(order);
+    free(acc);
+    free(temp0);
+    free(temp1);
+}
+
+/* multiply_plain_ckks (cipherplain_multiplication_kernel, multiplication.cu:313-331), add_plain_ckks /
+ * sub_plain_ckks (addition.cu:175-217).  op 0 multiply, 1 add, 2 subtract. */
+void oracle_plain(const octx* c, const u64* ct, const u64* pt, u64* out, int comps, int depth, int op)
+{
+    int L = c->Q - depth, n = c->n;
+    for (int z = 0; z < comps; z++)
+        for (int y = 0; y < L; y++)
+            for (int idx = 0; idx < n; idx++) {
+                size_t o = ((size_t) z * L + y) * n + idx;
+                u64 x = ct[o], m = pt[(size_t) y * n + idx];
+                if (op == 0)
+                    out[o] = o_mult(x, m, &c->mod[y]);
+                else if (z == 0)
+                    out[o] = op == 1 ? o_add(x, m, &c->mod[y]) : o_sub(x, m, &c->mod[y]);
+                else
+                    out[o] = x;
+            }
+}
+
 /* mod_drop_ckks_leveled_inplace: ckks/operator.cu:1246-1276 */
 void oracle_mod_drop(const octx* c, const u64* in, u64* out, int comps, int depth)
 {

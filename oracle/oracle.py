@@ -170,6 +170,24 @@ class OracleContext:
         lib().oracle_apply_galois(self._h, _p(ct), _p(out), _p(np.ascontiguousarray(key)), int(galois_elt), depth)
         return out
 
+    def keyswitch(self, ct2, key, depth=0):
+        ct = np.ascontiguousarray(ct2, dtype=np.uint64)
+        out = np.zeros_like(ct)
+        lib().oracle_keyswitch(self._h, _p(ct), _p(out), _p(np.ascontiguousarray(key)), depth)
+        return out
+
+    def conjugate(self, ct2, key, depth=0):
+        """conjugate_ckks_method_I/II (ckks/operator.cu:2027-2311): apply_galois with galois_elt_zero = 2N-1."""
+        return self.apply_galois(ct2, key, 2 * self.n - 1, depth)
+
+    def plain(self, ct, pt, op, depth=0):
+        """op 0 multiply_plain, 1 add_plain, 2 sub_plain; ct [comps][L][N], pt [L][N]."""
+        ct = np.ascontiguousarray(ct, dtype=np.uint64)
+        pt = np.ascontiguousarray(pt, dtype=np.uint64)
+        out = np.zeros_like(ct)
+        lib().oracle_plain(self._h, _p(ct), _p(pt), _p(out), ct.shape[0], depth, op)
+        return out
+
     def mod_drop(self, ct, depth=0):
         ct = np.ascontiguousarray(ct, dtype=np.uint64)
         comps, L = ct.shape[0], self.Q - depth

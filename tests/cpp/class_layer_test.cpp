@@ -86,6 +86,79 @@ int main(int argc, char** argv)
         threw = false;
         try { operators.rotate_rows(C1, R, galois_key, 5); } catch (const std::logic_error&) { threw = true; }
         if (!threw) { std::puts("FAIL: missing galois key must throw"); return 1; }
+
+        // plaintext operands, keyswitch, conjugate
+        auto pw = words(context->prime_vector_, 1, Q, n, 5);
+        Plaintext<S> P1(context, pw);
+        Ciphertext<S> M, Ad;
+        operators.multiply_plain(C1, P1, M);
+        operators.add_plain(C1, P1, Ad);
+        operators.sub_plain_inplace(Ad, P1); // (C1 + P) - P == C1
+        std::vector<Data64> m1, a1;
+        M.get_data(m1);
+        Ad.get_data(a1);
+        DeviceVector<Data64> dp(pw), dm((size_t) 2 * Q * n);
+        heon_ckks_multiply_plain(context->handle(), da.data(), 0, dp.data(), 0, dm.data(), 0, 2, 0, 1, nullptr);
+        std::vector<Data64> m2(m1.size());
+        cudaMemcpy(m2.data(), dm.data(), m2.size() * sizeof(Data64), cudaMemcpyDeviceToHost);
+        if (m1 != m2 || a1 != a) { std::puts("FAIL: plaintext operators"); return 1; }
+        Switchkey<S> swk(context);
+        swk.set_data(words(context->prime_vector_, context->digit_count(0) * 2, Qp, n, 6));
+        Ciphertext<S> K1, K2;
+        operators.keyswitch(C1, K1, swk);
+        galois_key.set_conjugate_key(words(context->prime_vector_, context->digit_count(0) * 2, Qp, n, 7));
+        operators.conjugate(C1, K2, galois_key);
+        std::vector<Data64> k1, k2, k3(2 * (size_t) Q * n);
+        K1.get_data(k1);
+        K2.get_data(k2);
+        heon_ckks_keyswitch(context->handle(), da.data(), 0, dr.data(), 0, swk.data(), 0, 1, nullptr);
+        cudaMemcpy(k3.data(), dr.data(), k3.size() * sizeof(Data64), cudaMemcpyDeviceToHost);
+        if (k1 != k3) { std::puts("FAIL: keyswitch differs from the C ABI"); return 1; }
+        heon_ckks_apply_galois(context->handle(), da.data(), 0, dr.data(), 0, galois_key.c_data(), (uint32_t) (2 * n - 1), 0, 1, nullptr);
+        cudaMemcpy(k3.data(), dr.data(), k3.size() * sizeof(Data64), cudaMemcpyDeviceToHost);
+        if (k2 != k3) { std::puts("FAIL: conjugate differs from apply_galois(2N-1)"); return 1; }
+    }
+    // BFV twins (test_bfv_multiplication.cpp parameters: N = 4096, {36,36}/{37}, t = 1032193)
+    {
+        constexpr Scheme B = Scheme::BFV;
+        HEContext<B> context = GenHEContext<B>(sec_level_type::none);
+        context->set_poly_modulus_degree(4096);
+        context->set_coeff_modulus_bit_sizes({36, 36}, {37});
+        context->set_plain_modulus(1032193);
+        context->generate();
+        const int n = context->n, Q = context->Q_size, Qp = context->Q_prime_size;
+        HEArithmeticOperator<B> operators(context);
+        auto a = words(context->prime_vector_, 2, Q, n, 11), b = words(context->prime_vector_, 2, Q, n, 12);
+        Ciphertext<B> C1(context, a), C2(context, b), C3;
+        Relinkey<B> relin_key(context);
+        relin_key.set_data(words(context->prime_vector_, context->digit_count() * 2, Qp, n, 13));
+        operators.multiply(C1, C2, C3);
+        operators.relinearize_inplace(C3, relin_key);
+        std::vector<Data64> got;
+        C3.get_data(got);
+        DeviceVector<Data64> da(a), db(b), dc((size_t) 3 * Q * n);
+        heon_bfv_multiply(context->handle(), da.data(), 0, db.data(), 0, dc.data(), 0, 1, nullptr);
+        heon_bfv_relinearize(context->handle(), dc.data(), 0, relin_key.data(), 1, nullptr);
+        std::vector<Data64> want(got.size());
+        cudaMemcpy(want.data(), dc.data(), want.size() * sizeof(Data64), cudaMemcpyDeviceToHost);
+        if (got != want || C3.size() != 2 || C3.relinearization_required()) { std::puts("FAIL: BFV multiply+relinearize"); return 1; }
+        Galoiskey<B> gk(context, std::vector<int>{1});
+        gk.set_key(gk.galois_elt[1], words(context->prime_vector_, context->digit_count() * 2, Qp, n, 14));
+        gk.set_key(gk.galois_elt_zero, words(context->prime_vector_, context->digit_count() * 2, Qp, n, 15));
+        Ciphertext<B> R1, R2, Sm;
+        operators.rotate_rows(C1, R1, gk, 1);
+        operators.rotate_columns(C1, R2, gk);
+        operators.add(R1, R2, Sm);
+        operators.sub(Sm, R2, Sm);
+        std::vector<Data64> r1, s1;
+        R1.get_data(r1);
+        Sm.get_data(s1);
+        DeviceVector<Data64> dr((size_t) 2 * Q * n);
+        heon_bfv_apply_galois(context->handle(), da.data(), 0, dr.data(), 0, gk.device_location_[gk.galois_elt[1]].data(),
+                              (uint32_t) gk.galois_elt[1], 1, nullptr);
+        std::vector<Data64> r2(r1.size());
+        cudaMemcpy(r2.data(), dr.data(), r2.size() * sizeof(Data64), cudaMemcpyDeviceToHost);
+        if (r1 != r2 || s1 != r1) { std::puts("FAIL: BFV rotate / add / sub"); return 1; }
     }
     std::puts("OK");
     return 0;

@@ -1,0 +1,141 @@
+"""keyswitch / conjugate / multiply_plain / add_plain / sub_plain (SURVEY 8(b) hot-path signatures).
+
+CPU: the oracle's restatements (switchkey_ckks_method_I/II ckks/operator.cu:1722-2025, conjugate :2027-2311,
+plain kernels addition.cu:175-217 / multiplication.cu:313-331) are pinned algebraically: a key switch
+under a real RLWE switching key decrypts to the same plaintext under the NEW secret, conjugation is
+the automorphism X -> X^(2N-1), plain ops match numpy big-int arithmetic.
+GPU: the CUDA path through the C ABI equals the oracle bit for bit (batched, depth 0 and 1)."""
+import numpy as np
+import pytest
+
+from tests.common import ciphertext, eval_key, oracle_ctx, residues
+from tests.test_decrypt_level import Scheme, _small_poly, _to_rns, _galois_key
+
+SMALL = ["n12_I", "n12_II", "n13_II", "mixed"]
+
+
+def _plain_ref(ct, pt, primes, op):
+    out = ct.copy()
+    for y in range(ct.shape[1]):
+        p = int(primes[y])
+        for z in range(ct.shape[0]):
+            a, m = ct[z, y].astype(object), pt[y].astype(object)
+            if op == 0:
+                out[z, y] = ((a * m) % p).astype(np.uint64)
+            elif z == 0:
+                out[z, y] = ((a + m) % p if op == 1 else (a - m) % p).astype(np.uint64)
+    return out
+
+
+@pytest.mark.parametrize("name", ["n12_I", "n13_II"])
+def test_oracle_plain_ops_match_bigint(name):
+    oc = oracle_ctx(name)
+    for depth in (0, 1):
+        L = oc.Q - depth
+        ct = ciphertext(80, oc.primes, L, oc.n, 3)
+        pt = residues(81, oc.primes[:L], oc.n)
+        for op in (0, 1, 2):
+            assert np.array_equal(oc.plain(ct, pt, op, depth), _plain_ref(ct, pt, oc.primes, op))
+
+
+@pytest.mark.parametrize("name", ["n12_I", "n12_II"])
+def test_oracle_keyswitch_and_conjugate_decrypt(name):
+    sc = Scheme(name)
+    oc, n, L = sc.oc, sc.n, sc.Q
+    m = _small_poly(2101, n, 1 << 14)
+    ct = sc.encrypt(m, 3101, L)
+    # switch from s to a fresh secret s2: the key encrypts P*s under s2
+    s2 = _small_poly(1777, n, 1)
+    s2_ntt = sc.ntt(_to_rns(s2, sc.primes))
+    swk = sc.switch_key(sc.s_ntt, s2_ntt, 6001)
+    out = oc.keyswitch(ct, swk)
+    sc_new = Scheme(name)
+    sc_new.s, sc_new.s_ntt = s2, s2_ntt
+    got, _ = sc_new.decrypt_coeffs(out, L, 64)
+    noise = max(abs(g - int(w)) for g, w in zip(got, m[:64]))
+    assert noise < 1 << 40, f"keyswitch noise too large: 2^{noise.bit_length()}"
+    # conjugation = automorphism with g = 2N-1
+    g = 2 * n - 1
+    conj = oc.conjugate(ct, _galois_key(sc, g))
+    got_c, _ = sc.decrypt_coeffs(conj, L, n)
+    exp = [0] * n
+    for i in range(n):
+        raw = (i * g) % (2 * n)
+        exp[raw % n] = -int(m[i]) if raw >= n else int(m[i])
+    assert max(abs(a - b) for a, b in zip(got_c[:256], exp[:256])) < 1 << 40
+
+
+# ------------------------------------------------------------------ GPU ---
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SMALL)
+@pytest.mark.parametrize("depth", [0, 1])
+def test_keyswitch_conjugate_vs_oracle_gpu(name, depth):
+    import torch
+    from heongpu_b200 import api
+    from tests.gpu_common import gpu_ctx, to_dev, to_host
+    ctx, oc = gpu_ctx(name), oracle_ctx(name)
+    batch, L, n = 3, oc.Q - depth, oc.n
+    a = ciphertext(90, oc.primes, L, n, 2, batch)
+    key = eval_key(91, oc.primes, oc.digits(0), n)
+    op = api.HEArithmeticOperator(ctx)
+    A = api.Ciphertext(ctx, to_dev(a), depth=depth)
+    out = api.Ciphertext(ctx, torch.zeros(batch, 2, L, n, dtype=torch.int64, device="cuda"), depth=depth)
+    op.keyswitch(A, out, api.Switchkey(ctx, to_dev(key)))
+    got = to_host(out.data).copy()
+    assert np.array_equal(to_host(A.data), a), "input must stay untouched"
+    for bi in range(batch):
+        assert np.array_equal(got[bi], oc.keyswitch(a[bi], key, depth)), "keyswitch"
+    gk = api.Galoiskey(ctx, {}, conjugate_key=to_dev(key))
+    op.conjugate(A, out, gk)
+    got = to_host(out.data).copy()
+    for bi in range(batch):
+        assert np.array_equal(got[bi], oc.conjugate(a[bi], key, depth)), "conjugate"
+    with pytest.raises(api.HeonError):
+        op.conjugate(A, out, api.Galoiskey(ctx, {}))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["n12_I", "n13_II", "n14_C2"])
+def test_plain_ops_vs_oracle_gpu(name):
+    import torch
+    from heongpu_b200 import api
+    from tests.gpu_common import gpu_ctx, to_dev, to_host
+    ctx, oc = gpu_ctx(name), oracle_ctx(name)
+    for depth, comps in ((0, 2), (1, 3)):
+        batch, L, n = 2, oc.Q - depth, oc.n
+        a = ciphertext(95, oc.primes, L, n, comps, batch)
+        pt = residues(96, oc.primes[:L], n)
+        op = api.HEArithmeticOperator(ctx)
+        A = api.Ciphertext(ctx, to_dev(a), depth=depth)
+        P = api.Plaintext(ctx, to_dev(pt), depth=depth)
+        out = api.Ciphertext(ctx, torch.zeros_like(A.data), depth=depth)
+        for fn, code in ((op.multiply_plain, 0), (op.add_plain, 1), (op.sub_plain, 2)):
+            fn(A, P, out)
+            got = to_host(out.data).copy()
+            for bi in range(batch):
+                assert np.array_equal(got[bi], oc.plain(a[bi], pt, code, depth)), (name, depth, code)
+        with pytest.raises(api.HeonError):
+            op.multiply_plain(A, api.Plaintext(ctx, to_dev(pt), depth=depth + 1), out)
+
+
+@pytest.mark.gpu
+def test_keyswitch_full_size_equals_identity_galois():
+    """At the BASELINE size (C3_II, Method II) the dedicated keyswitch path must agree with the
+    automorphism pipeline run with the identity element (which is pinned against the reference's
+    own kernels in test_gpu_parity.py): same arithmetic, different launch sequence."""
+    import torch
+    from heongpu_b200 import api
+    from tests.gpu_common import gpu_ctx, to_dev
+    for name in ("C3_II", "n16_I_small"):
+        ctx, oc = gpu_ctx(name), oracle_ctx(name)
+        L, n = oc.Q, oc.n
+        a = to_dev(ciphertext(97, oc.primes, L, n, 2, 2))
+        key = to_dev(eval_key(98, oc.primes, oc.digits(0), n))
+        op = api.HEArithmeticOperator(ctx)
+        A = api.Ciphertext(ctx, a)
+        o1 = api.Ciphertext(ctx, torch.zeros_like(a))
+        o2 = api.Ciphertext(ctx, torch.zeros_like(a))
+        op.keyswitch(A, o1, api.Switchkey(ctx, key))
+        op.apply_galois(A, o2, api.Galoiskey(ctx, {1: key}), 1)
+        torch.cuda.synchronize()
+        assert torch.equal(o1.data, o2.data)
