@@ -6,8 +6,12 @@ ciphertext pairs (B ops).  `value` = ops/s with inputs resident in HBM;
 `e2e` = the same through the public API with pinned HOST buffers (H2D of both
 inputs and D2H of the result inside the timed region).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3_II|C3_I|n14_C2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3_II|C3_I|n14_C2|M4_bfv_rot]
                     [--batch B] [--impl ours|reference]
+
+Workloads: C3_II (default, the configuration the BASELINE metric is quoted on) and C3_I are BASELINE
+config 3; n14_C2 is config 2 (CKKS N=2^14 L=4, batch 1024, multiply+relinearize+rescale); M4_bfv_rot
+is config 4 (BFV N=2^15, default 128-bit modulus, rotate_rows over the steps +-2^0..2^7).
 
 Multi-GPU: one process per GPU (torchrun), ciphertext batches are sharded, keys
 and tables replicated, no collective on the data path (weak scaling).
@@ -37,9 +41,14 @@ WORKLOADS = {
     # name: (params key, description)
     "C3_II": "CKKS N=2^16 {60,50x30}/{60,60,60} L=31 K=3 (Method II, bootstrapping params) mul+relin depth 0",
     "C3_I": "CKKS N=2^16 {59,45x36}/{59} L=37 K=1 (Method I) mul+relin depth 0",
-    "n14_C2": "CKKS N=2^14 {50,40,40,40}/{48} L=4 K=1 mul+relin depth 0",
+    "n14_C2": "CKKS N=2^14 {50,40,40,40}/{48} L=4 K=1 (logq~218) mul+relin+rescale depth 0 (BASELINE config 2)",
+    "M4_bfv_rot": "BFV N=2^15 default 128-bit modulus (14+1 primes, defaultmodulus.cpp:34-51) rotate_rows sweep over steps +-2^0..2^7 (BASELINE config 4)",
 }
-DEFAULT_BATCH = {"C3_II": 8, "C3_I": 4, "n14_C2": 256}
+DEFAULT_BATCH = {"C3_II": 8, "C3_I": 4, "n14_C2": 1024, "M4_bfv_rot": 64}
+# src/lib/util/defaultmodulus.cpp:34-51 (N = 32768, 128-bit security): the last prime is P
+BFV_32768_MODULUS = [0x2000000002b0001, 0x2000000003a0001, 0x2000000005b0001, 0x200000000640001, 0x400000000270001,
+                     0x400000000350001, 0x400000000360001, 0x4000000004d0001, 0x400000000570001, 0x400000000660001,
+                     0x4000000008a0001, 0x400000000920001, 0x400000000980001, 0x400000000990001, 0x400000000a40001]
 
 
 def peaks():
@@ -171,10 +180,14 @@ def run_ours(args, rank, world, local):
     out = torch.zeros(B, 3, L, n, dtype=torch.int64, device="cuda")
     rk = api.Relinkey(ctx, inp["key"])
 
+    with_rescale = args.workload == "n14_C2"
+
     def step():
         Cc = api.Ciphertext(ctx, out)
         op.multiply(A, Bc, Cc)
         op.relinearize_inplace(Cc, rk)
+        if with_rescale:
+            op.rescale_inplace(Cc)
 
     for _ in range(args.warmup):
         step()
@@ -219,6 +232,8 @@ def run_ours(args, rank, world, local):
                 Cc = api.Ciphertext(ctx, outs[k])
                 op.multiply(api.Ciphertext(ctx, da[k]), api.Ciphertext(ctx, db[k]), Cc)
                 op.relinearize_inplace(Cc, rk)
+                if with_rescale:
+                    op.rescale_inplace(Cc)
                 ev_cmp[k] = s_cmp.record_event()
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_cmp[k])
@@ -287,6 +302,117 @@ def run_ours(args, rank, world, local):
     return res
 
 
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 4: BFV N=2^15 Galois-rotate key-switch sweep (all power-of-2 steps)
+# ---------------------------------------------------------------------------------------------
+ROT_STEPS = [s * (1 << i) for i in range(8) for s in (1, -1)]  # +-2^0..2^7 (MAX_SHIFT = 8, bfv/evaluationkey.cu:306-345)
+
+
+def galois_elt(steps, n, group_order):
+    """steps_to_galois_elt (src/lib/kernel/keygeneration.cu:684-727)"""
+    m = 2 * n
+    pos = abs(steps)
+    s_ = (n >> 1) - pos if steps < 0 else pos
+    return pow(group_order, s_, m)
+
+
+def rot_inputs(batch, rank):
+    from tests.common import SEED0
+    primes, n = BFV_32768_MODULUS, 1 << 15
+    Q = len(primes) - 1
+
+    def dev_residues(buf, lead, plist):
+        g = torch.Generator(device="cuda")
+        g.manual_seed((SEED0 + buf + 1000 * rank) & 0x7FFFFFFFFFFFFFFF)
+        p = torch.tensor(plist, dtype=torch.int64, device="cuda").view(*([1] * len(lead)), len(plist), 1)
+        r = torch.randint(0, 1 << 62, (*lead, len(plist), n), dtype=torch.int64, device="cuda", generator=g)
+        return r % p
+    a = dev_residues(1, (batch, 2), primes[:Q])
+    keys = [dev_residues(10 + i, (Q, 2), primes) for i in range(len(ROT_STEPS))]  # d = Q digits (Method I)
+    return dict(n=n, Q=Q, primes=primes, a=a, keys=keys)
+
+
+def run_rot(args, rank, world, local, reference):
+    inp = rot_inputs(args.batch, rank)
+    B, Q, n = args.batch, inp["Q"], inp["n"]
+    out = torch.zeros(B, 2, Q, n, dtype=torch.int64, device="cuda")
+    if reference:
+        from oracle import ref as R
+        if not R.have_gpu():
+            return None
+        t = R.tables_for_refgpu(15, inp["primes"], Q, 1)
+        rg = R.RefGpu(15, inp["primes"], Q, 1, t)
+        elts = [galois_elt(s, n, 3) for s in ROT_STEPS]
+
+        def step():
+            for e, k in zip(elts, inp["keys"]):
+                for i in range(B):  # the reference has no batch dimension
+                    R.bfv_apply_galois(rg, inp["a"][i], out[i], k, e)
+        launches = None
+    else:
+        from heongpu_b200 import api
+        ctx = api.HEContext(15, q_values=inp["primes"][:Q], p_values=inp["primes"][Q:], plain_modulus=786433, device=local)
+        op = api.HEArithmeticOperator(ctx)
+        A = api.Ciphertext(ctx, inp["a"])
+        A.in_ntt_domain_ = False
+        elts = [api.lib.heon_steps_to_galois_elt(s, n, 3) for s in ROT_STEPS]
+        gk = api.Galoiskey(ctx, dict(zip(elts, inp["keys"])))
+        O_ = api.Ciphertext(ctx, out)
+
+        def step():
+            for s in ROT_STEPS:
+                op.rotate_rows_bfv(A, O_, gk, s)
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if not reference:
+        api.lib.heon_kernel_launches(1)
+    ms = timed(step, args.steps, world)
+    launches = None if reference else int(api.lib.heon_kernel_launches(0))
+    clocks = sampler.stop() if rank == 0 else None
+    ops = B * len(ROT_STEPS)
+    res = dict(value=ops * args.steps * world / (ms * 1e-3), ms=ms, launches=launches, clocks=clocks)
+    if reference:
+        return res
+    # e2e: inputs from pinned host memory, the sweep, the last rotation's result back to the host
+    ha = inp["a"].cpu().pin_memory()
+    hres = torch.empty(B, 2, Q, n, dtype=torch.int64).pin_memory()
+
+    def e2e_step():
+        inp["a"].copy_(ha, non_blocking=True)
+        step()
+        hres.copy_(out, non_blocking=True)
+    e2e_step()
+    ms_e = timed(e2e_step, max(2, args.steps // 2), world)
+    res.update(e2e=ops * max(2, args.steps // 2) * world / (ms_e * 1e-3), h2d=int(ha.numel() * 8), d2h=int(hres.numel() * 8))
+    # per-kernel CUDA-event pass
+    kernels = []
+    if rank == 0:
+        api.lib.heon_profile_begin()
+        step()
+        msv, cnt = (C.c_double * 16)(), (C.c_longlong * 16)()
+        ncls = api.lib.heon_profile_end(msv, cnt, 16)
+        tot = sum(msv[i] for i in range(ncls))
+        Qp = Q + 1
+        fwd_polys = Q * Qp  # per op: mod-up fused into the forward NTT of d*Q' limb-polynomials
+        for i in range(ncls):
+            if cnt[i]:
+                name = api.lib.heon_profile_class_name(i).decode()
+                kernels.append({"kernel": name, "launches_per_step": int(cnt[i]), "ms_per_op": msv[i] / ops,
+                                "share": msv[i] / tot if tot else None})
+        fwd_ms = sum(k["ms_per_op"] for k in kernels if k["kernel"].startswith("ntt_fwd"))
+        peak, peak_src = peaks()
+        if fwd_ms > 0:
+            achieved = fwd_polys * n * 16 / (fwd_ms * 1e-3) / 1e9
+            res["roof"] = {"bound": "hbm", "kernel": "forward NTT (mod-up fused)", "achieved": achieved, "peak": peak,
+                           "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                           "note": "58/59-bit primes: integer butterflies (the FP64 path needs p < 2^50)"}
+    res["kernels"] = kernels
+    return res
+
+
 def cpu_baseline(inp, workload):
     """The CPU oracle (port of the reference algorithm) on a bounded sample: one
     multiply+relinearize of the same workload with all host threads (OpenMP)."""
@@ -319,6 +445,8 @@ def run_reference(args, rank, world, local):
         for i in range(B):  # the reference has no batch dimension: B sequential ops on one stream
             rg.multiply(inp["a"][i], inp["b"][i], out[i], 0)
             rg.relinearize(out[i], inp["key"], 0)
+            if args.workload == "n14_C2":
+                rg.rescale(out[i], 0)
 
     for _ in range(args.warmup):
         step()
@@ -350,6 +478,35 @@ def main():
             "dtype": "u64", "data": "synthetic", "config": config}
     if args.workload == "n14_C2":
         base["metric"] = "CKKS N=2^14 mul+relin ops/sec"
+
+    if args.workload == "M4_bfv_rot":
+        base["metric"] = "BFV N=2^15 rotate_rows (Galois key-switch) ops/sec"
+        config["ops_per_step"] = args.batch * world * len(ROT_STEPS)
+        if args.impl == "reference":
+            if world > 1 and rank != 0:
+                return
+            r = run_rot(args, 0, 1, local, True)
+            if r is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_gpu.so not built"}))
+                return
+            line = dict(base)
+            line.update({"impl": "reference", "value": r["value"], "n_gpus": 1, "ms_per_step": r["ms"] / args.steps,
+                         "cpu_baseline": {"value": r["value"], "unit": "ops/s", "cores": 0, "kind": "reference",
+                                          "sample": "the reference's own CUDA kernels (sm_100a build) on one B200"},
+                         "e2e": {"value": r["value"], "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+            print(json.dumps(line))
+            return
+        r = run_rot(args, rank, world, local, False)
+        if rank != 0:
+            return
+        line = dict(base)
+        line.update({"value": r["value"], "ms_per_step": r["ms"] / args.steps, "gpu_launches": r["launches"],
+                     "clocks": r["clocks"], "roofline": r.get("roof"), "kernels": r["kernels"],
+                     "e2e": {"value": r["e2e"], "unit": "ops/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+                     "cpu_baseline": {"value": None, "unit": "ops/s", "cores": 0, "kind": "port",
+                                      "sample": "not timed for this workload (see the default workload's line)"}})
+        print(json.dumps(line))
+        return
 
     if args.impl == "reference":
         if world > 1 and rank != 0:

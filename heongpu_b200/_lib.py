@@ -25,6 +25,7 @@ SIGNATURES = {
     "heon_ckks_context_create": (ci, [ci, ci, i32p, ci, i32p, ci, C.POINTER(vp)]),
     "heon_ckks_context_create_values": (ci, [ci, ci, u64p, ci, u64p, ci, C.POINTER(vp)]),
     "heon_bfv_context_create": (ci, [ci, ci, i32p, ci, i32p, ci, C.c_uint64, C.POINTER(vp)]),
+    "heon_bfv_context_create_values": (ci, [ci, ci, u64p, ci, u64p, ci, C.c_uint64, C.POINTER(vp)]),
     "heon_bfv_multiply": (ci, [vp, vp, ll, vp, ll, vp, ll, ci, vp]),
     "heon_bfv_relinearize": (ci, [vp, vp, ll, vp, ci, vp]),
     "heon_bfv_apply_galois": (ci, [vp, vp, ll, vp, ll, vp, C.c_uint32, ci, vp]),

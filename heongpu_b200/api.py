@@ -72,7 +72,12 @@ class HEContext:
                  plain_modulus=None):
         h = C.c_void_p()
         self.scheme = "BFV" if plain_modulus else "CKKS"
-        if plain_modulus:  # HEContext<Scheme::BFV> (reference: src/lib/host/bfv/context.cu)
+        if plain_modulus and q_values is not None:  # set_coeff_modulus_values / default values (bfv/context.cu:223-300)
+            q = (C.c_uint64 * len(q_values))(*q_values)
+            p = (C.c_uint64 * len(p_values))(*p_values)
+            _check(lib.heon_bfv_context_create_values(device, log_n, q, len(q_values), p, len(p_values),
+                                                      int(plain_modulus), C.byref(h)))
+        elif plain_modulus:  # HEContext<Scheme::BFV> (reference: src/lib/host/bfv/context.cu)
             q = (C.c_int * len(q_bits))(*q_bits)
             p = (C.c_int * len(p_bits))(*p_bits)
             _check(lib.heon_bfv_context_create(device, log_n, q, len(q_bits), p, len(p_bits), int(plain_modulus), C.byref(h)))

@@ -231,6 +231,29 @@ int heon_bfv_context_create(int device, int log_n, const int* q_bits, int n_q, c
     });
 }
 
+int heon_bfv_context_create_values(int device, int log_n, const uint64_t* q, int n_q, const uint64_t* p, int n_p,
+                                   uint64_t plain_modulus, heon_context_t* out)
+{
+    return guarded([&] {
+        if (!out || !q || !p)
+            throw std::invalid_argument("null argument");
+        if (plain_modulus < 2)
+            throw std::logic_error("invalid plain modulus");
+        if (log_n < 12 || log_n > 16)
+            throw std::logic_error("Poly modulus degree is not supported");
+        auto h = std::make_unique<heon_context_s>();
+        for (int i = 0; i < n_q; ++i)
+            h->c.mod.push_back(make_mod(q[i]));
+        for (int i = 0; i < n_p; ++i)
+            h->c.mod.push_back(make_mod(p[i]));
+        for (auto& m : h->c.mod)
+            if (m.bit > 61 || m.bit < 30 || !is_prime_u64(m.value) || (m.value - 1) % (2ull << log_n))
+                throw std::logic_error("invalid modulus");
+        finish_context(h->c, device, log_n, n_q, n_p, plain_modulus);
+        *out = h.release();
+    });
+}
+
 int heon_bfv_multiply(heon_context_t ctx, const uint64_t* a, long long as, const uint64_t* b, long long bs,
                       uint64_t* out, long long os, int batch, void* stream)
 {

@@ -107,6 +107,10 @@ int heon_ckks_context_create_values(int device, int log_n, const uint64_t* q, in
  * HEON_TBL_MODULUS then lists Q' followed by the bsk_modulus Bsk primes. */
 int heon_bfv_context_create(int device, int log_n, const int* q_bits, int n_q, const int* p_bits, int n_p,
                             uint64_t plain_modulus, heon_context_t* out);
+/* set_coeff_modulus_values / set_coeff_modulus_default_values (bfv/context.cu:223-300): explicit
+ * primes, e.g. the default 128-bit-security chains of src/lib/util/defaultmodulus.cpp:12-90. */
+int heon_bfv_context_create_values(int device, int log_n, const uint64_t* q, int n_q, const uint64_t* p,
+                                   int n_p, uint64_t plain_modulus, heon_context_t* out);
 void heon_context_destroy(heon_context_t ctx);
 int heon_context_info(heon_context_t ctx, heon_info* out);
 /* Copies a host table into h_out (capacity `cap` words); *count receives the
