@@ -380,3 +380,18 @@ class HEArithmeticOperator:
     def rotate_rows(self, ct, out, galois_key, shift):
         elt = lib.heon_steps_to_galois_elt(shift, self.context_.n, galois_key.group_order_)
         return self.apply_galois(ct, out, galois_key, elt)
+
+    def rotate_rows_hoisted(self, ct, out_data, galois_key, shifts):
+        """The baby-step loop of the reference's BSGS product (fast_single_hoisting_rotation_ckks_method_I/II,
+        ckks/operator.cu:4674-5446): every shift of `shifts` applied to the same ciphertext(s), written to
+        out_data[r] ([R, B, 2, L, N]); mod-up and the forward NTTs are shared by all rotations."""
+        c = self.context_
+        elts = [lib.heon_steps_to_galois_elt(s, c.n, galois_key.group_order_) for s in shifts]
+        for e in elts:
+            if e not in galois_key.device_location_:
+                raise HeonLogicError("Galois key not present!")
+        keys = (C.c_void_p * len(elts))(*[galois_key.device_location_[e].data_ptr() for e in elts])
+        earr = (C.c_uint32 * len(elts))(*elts)
+        _check(lib.heon_ckks_rotate_hoisted(c._h, _ptr(ct.data), ct.stride, _ptr(out_data), out_data.stride(1),
+                                            out_data.stride(0), keys, earr, len(elts), ct.depth_, ct.batch, _stream()))
+        return out_data

@@ -550,6 +550,22 @@ int heon_ckks_conjugate(heon_context_t ctx, const uint64_t* in, long long is, ui
     });
 }
 
+int heon_ckks_rotate_hoisted(heon_context_t ctx, const uint64_t* in, long long is, uint64_t* out, long long os,
+                             long long out_rot_stride, const uint64_t* const* h_galois_keys,
+                             const uint32_t* h_galois_elts, int count, int depth, int batch, void* stream)
+{
+    return guarded([&] {
+        HEON_OP_PROLOGUE
+        if (!in || !out || !h_galois_keys || !h_galois_elts)
+            throw std::invalid_argument("null argument");
+        for (int r = 0; r < count; ++r)
+            if (!h_galois_keys[r])
+                throw std::logic_error("Galois key not present!");
+        op_rotate_hoisted(c, in, is, out, os, out_rot_stride, (const u64* const*) h_galois_keys, h_galois_elts, count,
+                          depth, batch, st);
+    });
+}
+
 int heon_ckks_relinearize(heon_context_t ctx, uint64_t* ct, long long cs, const uint64_t* relin_key,
                           int depth, int batch, void* stream)
 {

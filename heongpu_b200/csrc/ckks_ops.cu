@@ -663,8 +663,10 @@ void op_plain(const Context& c, const u64* ct, long long ct_bs, const u64* pt, l
 // Key-switch core shared by relinearize / apply_galois / keyswitch:
 // takes the digit polynomial(s) in the coefficient domain and leaves
 // acc[b][2][Qpl][N] (NTT domain).  `tmp` must hold batch*d*Qpl*N words.
-static int keyswitch_core(const Context& c, const u64* coef, long long coef_bs, const u64* key,
-                          u64* tmp, u64* acc, int depth, int batch, cudaStream_t st)
+// Part one: mod-up of the digits into every prime of Q'_l and forward NTT (tmp[b][d][Qpl][N]).
+// This half does not depend on the key: hoisted rotations run it once for many keys.
+static int keyswitch_modup_ntt(const Context& c, const u64* coef, long long coef_bs, u64* tmp, int depth,
+                               int batch, cudaStream_t st)
 {
     const int L = c.Q_size - depth, K = c.P_size, Qpl = L + K;
     int d;
@@ -695,6 +697,14 @@ static int keyswitch_core(const Context& c, const u64* coef, long long coef_bs, 
     }
     if (d > 64)
         throw std::invalid_argument("too many key-switch digits");
+    return d;
+}
+
+// Part two: inner product of the NTT-domain digits with the key.
+static void keyswitch_mac(const Context& c, const u64* tmp, const u64* key, u64* acc, int d, int depth,
+                          int batch, cudaStream_t st)
+{
+    const int L = c.Q_size - depth, K = c.P_size, Qpl = L + K;
     {
         LaunchScope scope(KC_KEYSWITCH_MAC, st);
         int by = 1;
@@ -705,6 +715,13 @@ static int keyswitch_core(const Context& c, const u64* coef, long long coef_bs, 
         k_keyswitch_mac<<<g, blk, 0, st>>>(tmp, key, acc, c.d_pc, c.logn, d, L, Qpl, c.Qp, depth, batch);
     }
     check_launch();
+}
+
+static int keyswitch_core(const Context& c, const u64* coef, long long coef_bs, const u64* key,
+                          u64* tmp, u64* acc, int depth, int batch, cudaStream_t st)
+{
+    const int d = keyswitch_modup_ntt(c, coef, coef_bs, tmp, depth, batch, st);
+    keyswitch_mac(c, tmp, key, acc, d, depth, batch, st);
     return d;
 }
 
@@ -939,6 +956,48 @@ void op_apply_galois(const Context& c, const u64* in, long long in_bs, u64* out,
     check_launch();
     if (!coeff)
         launch_ntt_strided(c, out, out_bs, 2 * L, 0, batch, range_primes(0, L), false, st);
+}
+
+// Hoisted rotations: `count` automorphisms of the SAME ciphertext(s).  INTT, mod-up and the
+// d*Q' forward NTTs -- more than half of a rotation -- run once; each rotation then costs one
+// inner product with its own key, the INTT of the 2*Q' accumulator limbs, the mod-down fused with
+// the permutation and the final NTT.  Rotation r is written to out + r*out_rs (+ b*out_bs) and is
+// bit-identical to apply_galois(in, key_r, elt_r): the automorphism is applied after the key
+// switch (as in the reference), so everything before the inner product is independent of it.
+// This is the baby-step loop of the reference's BSGS matrix-vector product
+// (fast_single_hoisting_rotation_ckks_method_I/II, ckks/operator.cu:4674-4954, 5092-5446), which
+// repeats the full pipeline for every shift.
+void op_rotate_hoisted(const Context& c, const u64* in, long long in_bs, u64* out, long long out_bs,
+                       long long out_rs, const u64* const* galois_keys, const unsigned* galois_elts, int count,
+                       int depth, int batch, cudaStream_t st)
+{
+    check_depth(c, depth);
+    if (c.scheme != SCHEME_CKKS)
+        throw std::invalid_argument("not a CKKS context");
+    if (count < 1)
+        throw std::invalid_argument("no rotations requested");
+    const int L = c.Q_size - depth, K = c.P_size, Qpl = L + K;
+    const long long N = c.n;
+    Scratch coef((size_t) batch * 2 * L * N * 8, st);
+    launch_ntt_strided_copy(c, in, in_bs, coef.w(), 2 * L, batch, range_primes(0, L), true, st);
+    Scratch tmp(ks_tmp_words(c, depth, batch) * 8, st);
+    Scratch acc((size_t) batch * 2 * Qpl * N * 8, st);
+    const int d = keyswitch_modup_ntt(c, coef.w() + (long long) L * N, 2 * L * N, tmp.w(), depth, batch, st);
+    for (int r = 0; r < count; ++r)
+    {
+        u64* o = out + (long long) r * out_rs;
+        keyswitch_mac(c, tmp.w(), galois_keys[r], acc.w(), d, depth, batch, st);
+        launch_ntt(c, acc.w(), acc.w(), (long long) batch * 2 * Qpl, level_primes(L, K, depth), true, st);
+        dim3 g(c.n >> 8, batch * 2);
+        {
+            LaunchScope scope(KC_MODDOWN, st);
+            k_moddown_ext<true><<<g, 256, 0, st>>>(acc.w(), o, out_bs, coef.w(), c.d_pc, c.d_half, c.d_half_mod,
+                                                   c.d_lqm_pair, galois_elts[r], c.logn, Qpl, L, c.Qp, c.Q_size, K,
+                                                   2 * L * N);
+        }
+        check_launch();
+        launch_ntt_strided(c, o, out_bs, 2 * L, 0, batch, range_primes(0, L), false, st);
+    }
 }
 
 } // namespace heon

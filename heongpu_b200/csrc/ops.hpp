@@ -37,6 +37,9 @@ void op_add(const Context& c, const u64* a, long long a_bs, const u64* b, long l
             long long o_bs, int comps, int depth, int batch, int op, cudaStream_t st);
 void op_plain(const Context& c, const u64* ct, long long ct_bs, const u64* pt, long long pt_bs, u64* out,
               long long o_bs, int comps, int depth, int batch, int op, cudaStream_t st);
+void op_rotate_hoisted(const Context& c, const u64* in, long long in_bs, u64* out, long long out_bs,
+                       long long out_rs, const u64* const* galois_keys, const unsigned* galois_elts, int count,
+                       int depth, int batch, cudaStream_t st);
 void op_keyswitch(const Context& c, const u64* in, long long in_bs, u64* out, long long out_bs,
                   const u64* switch_key, int depth, int batch, cudaStream_t st);
 void op_multiply(const Context& c, const u64* a, long long a_bs, const u64* b, long long b_bs,

@@ -202,6 +202,16 @@ int heon_ckks_apply_galois(heon_context_t ctx, const uint64_t* in, long long in_
                            uint64_t* out, long long out_stride, const uint64_t* galois_key,
                            uint32_t galois_elt, int depth, int batch, void* stream);
 
+/* ---- hoisted rotations: the baby-step loop of the BSGS matrix-vector product,
+ *      fast_single_hoisting_rotation_ckks_method_I / _II (operator.cu:4674-4954, 5092-5446).
+ * `count` automorphisms of the same ciphertext(s): h_galois_keys[r] (HOST array of DEVICE key
+ * pointers) with element h_galois_elts[r] (HOST array).  Rotation r of batch element b lands at
+ * out + r*out_rot_stride + b*out_stride, layout [2][L][N]; each equals heon_ckks_apply_galois
+ * with the same key bit for bit, but INTT, mod-up and the d*Q' forward NTTs run once. */
+int heon_ckks_rotate_hoisted(heon_context_t ctx, const uint64_t* in, long long in_stride, uint64_t* out,
+                             long long out_stride, long long out_rot_stride, const uint64_t* const* h_galois_keys,
+                             const uint32_t* h_galois_elts, int count, int depth, int batch, void* stream);
+
 /* ---- HEOperator<BFV>::multiply_bfv (src/lib/host/bfv/operator.cu:336-430) --
  * BEHZ multiplication.  a, b: [2][Q][N], out: [3][Q][N], all in the
  * COEFFICIENT domain (BFV ciphertexts are not kept in the NTT domain). */

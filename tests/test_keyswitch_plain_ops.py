@@ -139,3 +139,35 @@ def test_keyswitch_full_size_equals_identity_galois():
         op.apply_galois(A, o2, api.Galoiskey(ctx, {1: key}), 1)
         torch.cuda.synchronize()
         assert torch.equal(o1.data, o2.data)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,depth", [("n12_I", 0), ("n13_II", 1), ("n16_II_small", 0)])
+def test_hoisted_rotations_equal_individual_rotations_gpu(name, depth):
+    """SURVEY 8(f) rank 1: the BSGS baby-step rotations share INTT, mod-up and the forward NTTs;
+    every output must equal the stand-alone rotation (itself pinned against the oracle / the
+    reference kernels) bit for bit."""
+    import torch
+    from heongpu_b200 import api
+    from tests.gpu_common import gpu_ctx, to_dev, to_host
+    ctx, oc = gpu_ctx(name), oracle_ctx(name)
+    batch, L, n = 2, oc.Q - depth, oc.n
+    a = ciphertext(110, oc.primes, L, n, 2, batch)
+    shifts = [1, 2, -1, 5]
+    elts = [api.lib.heon_steps_to_galois_elt(s, n, 5) for s in shifts]
+    keys = {e: to_dev(eval_key(111 + i, oc.primes, oc.digits(0), n)) for i, e in enumerate(elts)}
+    gk = api.Galoiskey(ctx, keys)
+    op = api.HEArithmeticOperator(ctx)
+    A = api.Ciphertext(ctx, to_dev(a), depth=depth)
+    outs = torch.zeros(len(shifts), batch, 2, L, n, dtype=torch.int64, device="cuda")
+    op.rotate_rows_hoisted(A, outs, gk, shifts)
+    single = api.Ciphertext(ctx, torch.zeros(batch, 2, L, n, dtype=torch.int64, device="cuda"), depth=depth)
+    for r, s in enumerate(shifts):
+        op.rotate_rows(A, single, gk, s)
+        torch.cuda.synchronize()
+        assert torch.equal(outs[r], single.data), f"hoisted rotation {s} differs"
+    if n <= 8192:  # and against the oracle where it is quick
+        key0 = to_host(keys[elts[0]])
+        assert np.array_equal(to_host(outs[0, 0]), oc.apply_galois(a[0], key0, elts[0], depth))
+    with pytest.raises(api.HeonError):
+        op.rotate_rows_hoisted(A, outs, gk, [7])
