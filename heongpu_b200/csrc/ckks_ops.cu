@@ -509,6 +509,117 @@ __global__ void __launch_bounds__(256)
 #undef HEON_MD
 }
 
+// Method-II mod-down without leaving the NTT domain for the Q limbs.
+// The reference's coefficient-domain peel (divide_round_lastq_extended_leveled_kernel,
+// switchkey.cu:1222-1282) computes, for every Q limb y,
+//     x' = (((x - t_0) m_0 - t_1) m_1 ... - t_{K-1}) m_{K-1}  (mod q_y),
+// where the t_i depend only on the K special-prime limbs.  That is x' = x*M_y + c_y with
+// M_y = prod m_i and c_y = the same chain started from x = 0 -- exact arithmetic mod q_y, and the
+// NTT is linear, so NTT(x') = NTT(x)*M_y + NTT(c_y).  NTT(x) is what the inner product produced:
+// only the 2K special limbs go through the inverse NTT (instead of all 2Q'), the correction c_y
+// costs the 2L forward NTTs the old path spent on x', and the final combination also adds the
+// old ciphertext.  Every word equals the reference's.
+template <int K>
+__device__ __forceinline__ void moddown2_corr_body(const u64* __restrict__ pin, u64* __restrict__ pout,
+                                                   const PrimeConst* __restrict__ pcs,
+                                                   const u64* __restrict__ half, const u64* __restrict__ half_mod,
+                                                   const TwPair* __restrict__ lqm, int logn, int L, int Qp0, int Q0)
+{
+    u64 last_ct[K], lh[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+        last_ct[i] = pin[(long long) i << logn];
+    int loc = 0;
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+    {
+        lh[i] = mod_add(last_ct[K - 1 - i], half[i], pcs[Qp0 - 1 - i].p);
+#pragma unroll
+        for (int j = 0; j < K - 1 - i; ++j)
+        {
+            const PrimeConst pj = pcs[Q0 + j];
+            u64 t = reduce_u64(lh[i], pj);
+            t = mod_sub(t, half_mod[loc + Q0 + j], pj.p);
+            t = mod_sub(last_ct[j], t, pj.p);
+            const TwPair w = lqm[loc + Q0 + j];
+            last_ct[j] = csub(shoup_mul_lazy(t, w.w, w.ws, pj.p), pj.p);
+        }
+        loc += Qp0 - 1 - i;
+    }
+    for (int y = 0; y < L; ++y)
+    {
+        const PrimeConst py = pcs[y];
+        u64 x = 0;
+        int l2 = 0;
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+        {
+            u64 t = reduce_u64(lh[i], py);
+            t = mod_sub(t, half_mod[l2 + y], py.p);
+            t = mod_sub(x, t, py.p);
+            const TwPair w = lqm[l2 + y];
+            x = csub(shoup_mul_lazy(t, w.w, w.ws, py.p), py.p);
+            l2 += Qp0 - 1 - i;
+        }
+        pout[(long long) y << logn] = x;
+    }
+}
+
+// in: acc[b][2][Qpl][N] whose P limbs are in the coefficient domain; out: corr[b][2][L][N]
+__global__ void __launch_bounds__(256)
+    k_moddown2_corr(const u64* __restrict__ acc, u64* __restrict__ corr, const PrimeConst* __restrict__ pcs,
+                    const u64* __restrict__ half, const u64* __restrict__ half_mod,
+                    const TwPair* __restrict__ lqm, int logn, int Qpl, int L, int Qp0, int Q0, int K)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const long long bc = blockIdx.y; // b*2 + c
+    const u64* pin = acc + ((bc * Qpl + L) << logn) + idx;
+    u64* pout = corr + ((bc * L) << logn) + idx;
+#define HEON_MD2(n)                                                                                \
+    case n:                                                                                        \
+        moddown2_corr_body<n>(pin, pout, pcs, half, half_mod, lqm, logn, L, Qp0, Q0);              \
+        break;
+    switch (K)
+    {
+        HEON_MD2(1)
+        HEON_MD2(2)
+        HEON_MD2(3)
+        HEON_MD2(4)
+        HEON_MD2(5)
+        HEON_MD2(6)
+        HEON_MD2(7)
+        HEON_MD2(8)
+    }
+#undef HEON_MD2
+}
+
+// out[c][y] = (ct[c][y] if selected) + acc[c][y]*M_y + corr[c][y]   (all NTT domain)
+__global__ void __launch_bounds__(256)
+    k_moddown2_final(const u64* __restrict__ acc, const u64* __restrict__ corr, const u64* __restrict__ ct,
+                     long long ct_bs, u64* __restrict__ out, long long out_bs, const PrimeConst* __restrict__ pcs,
+                     const TwPair* __restrict__ mprod, int logn, int L, int Qpl, int add_mask)
+{
+    const int idx = (blockIdx.x * 256 + threadIdx.x) * 2;
+    const int y = blockIdx.y;
+    const long long bz = blockIdx.z >> 1;
+    const int c = blockIdx.z & 1;
+    const u64 p = pcs[y].p;
+    const TwPair m = mprod[y];
+    const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(acc + (((bz * 2 + c) * Qpl + y) << logn) + idx);
+    const ulonglong2 k = *reinterpret_cast<const ulonglong2*>(corr + (((bz * 2 + c) * L + y) << logn) + idx);
+    ulonglong2 r;
+    r.x = mod_add(csub(shoup_mul_lazy(x.x, m.w, m.ws, p), p), k.x, p);
+    r.y = mod_add(csub(shoup_mul_lazy(x.y, m.w, m.ws, p), p), k.y, p);
+    const long long o = ((long long) (c * L + y) << logn) + idx;
+    if ((add_mask >> c) & 1)
+    {
+        const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(ct + bz * ct_bs + o);
+        r.x = mod_add(t.x, r.x, p);
+        r.y = mod_add(t.y, r.y, p);
+    }
+    *reinterpret_cast<ulonglong2*>(out + bz * out_bs + o) = r;
+}
+
 // ---------------------------------------------------------------------------
 // rescale / mod-drop tails
 // ---------------------------------------------------------------------------
@@ -759,6 +870,31 @@ static void moddown_add(const Context& c, u64* acc, u64* tmp, const u64* ct_in, 
     }
     else
     {
+        const bool aligned = ((reinterpret_cast<uintptr_t>(acc) | reinterpret_cast<uintptr_t>(tmp) |
+                               reinterpret_cast<uintptr_t>(ct_in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+                             ((ct_bs | out_bs) & 1) == 0;
+        if (K <= 8 && aligned && c.n >= 512)
+        {
+            // inverse NTT of the K special limbs of both components only
+            launch_ntt_strided(c, acc + (long long) L * N, Qpl * N, K, 0, (long long) batch * 2,
+                               range_primes(c.Q_size, K), true, st);
+            {
+                dim3 g(c.n >> 8, batch * 2);
+                LaunchScope scope(KC_MODDOWN, st);
+                k_moddown2_corr<<<g, 256, 0, st>>>(acc, tmp, c.d_pc, c.d_half, c.d_half_mod, c.d_lqm_pair, c.logn, Qpl,
+                                                L, c.Qp, c.Q_size, K);
+            }
+            check_launch();
+            launch_ntt(c, tmp, tmp, (long long) batch * 2 * L, range_primes(0, L), false, st);
+            {
+                dim3 g(c.n >> 9, L, batch * 2);
+                LaunchScope scope(KC_MODDOWN, st);
+                k_moddown2_final<<<g, 256, 0, st>>>(acc, tmp, ct_in, ct_bs, out, out_bs, c.d_pc, c.d_md2_M, c.logn, L,
+                                                 Qpl, add_mask);
+            }
+            check_launch();
+            return;
+        }
         launch_ntt(c, acc, acc, (long long) batch * 2 * Qpl, level_primes(L, K, depth), true, st);
         dim3 g(c.n >> 8, batch * 2);
         {

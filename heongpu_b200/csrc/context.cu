@@ -379,6 +379,21 @@ void upload_tables(Context& c)
             for (int j = 0; j < c.Qp - 1 - i; ++j, ++o)
                 pairs.push_back(TwPair{c.last_q_modinv[o], shoup(c.last_q_modinv[o], c.mod[j].value)});
         c.d_lqm_pair = upload(pairs);
+        // product over the K blocks, per Q prime: the factor the NTT-domain mod-down multiplies by
+        std::vector<TwPair> mprod;
+        for (int y = 0; y < c.Q_size; ++y)
+        {
+            const u64 q = c.mod[y].value;
+            u64 m = 1;
+            size_t l2 = 0;
+            for (int i = 0; i < c.P_size; ++i)
+            {
+                m = mulmod(m, c.last_q_modinv[l2 + y], q);
+                l2 += c.Qp - 1 - i;
+            }
+            mprod.push_back(TwPair{m, shoup(m, q)});
+        }
+        c.d_md2_M = upload(mprod);
     }
     c.d_half = upload(c.half);
     c.d_half_mod = upload(c.half_mod);
@@ -456,6 +471,7 @@ Context::~Context()
     cudaFree(d_fwd_rowc);
     cudaFree(d_last_q_modinv);
     cudaFree(d_lqm_pair);
+    cudaFree(d_md2_M);
     cudaFree(d_half);
     cudaFree(d_half_mod);
     cudaFree(d_rescaled_last_q_modinv);

@@ -111,6 +111,7 @@ struct Context {
     int use_fp64 = 1; // FP64-pipe quotient for primes < 2^50 (HEON_NTT_FP64=0 disables)
     u64* d_last_q_modinv = nullptr;
     TwPair* d_lqm_pair = nullptr; // last_q_modinv with Shoup words
+    TwPair* d_md2_M = nullptr; // [Q]: prod_i last_q_modinv[block i][y] = (p_0..p_{K-1})^-1 mod q_y, Shoup pair
     u64* d_half = nullptr;
     u64* d_half_mod = nullptr;
     u64* d_rescaled_last_q_modinv = nullptr;
