@@ -519,11 +519,15 @@ __global__ void __launch_bounds__(256)
 // only the 2K special limbs go through the inverse NTT (instead of all 2Q'), the correction c_y
 // costs the 2L forward NTTs the old path spent on x', and the final combination also adds the
 // old ciphertext.  Every word equals the reference's.
+// For Q primes below 2^50 the chain is evaluated on the FP64 pipe in its expanded form
+//   c_y = Cst_y - sum_i lh_i * B_{i,y}  (mod q_y),   lh_i = hi_i*2^30 + lo_i  (lh_i < 2^61),
+// two fp_mulmod per special prime with operands below 2^31 (ntt_core.cuh); exact, same residue.
 template <int K>
 __device__ __forceinline__ void moddown2_corr_body(const u64* __restrict__ pin, u64* __restrict__ pout,
                                                    const PrimeConst* __restrict__ pcs,
                                                    const u64* __restrict__ half, const u64* __restrict__ half_mod,
-                                                   const TwPair* __restrict__ lqm, int logn, int L, int Qp0, int Q0)
+                                                   const TwPair* __restrict__ lqm, const TwPair* __restrict__ btab,
+                                                   const u64* __restrict__ cst, int logn, int L, int Qp0, int Q0)
 {
     u64 last_ct[K], lh[K];
 #pragma unroll
@@ -546,20 +550,48 @@ __device__ __forceinline__ void moddown2_corr_body(const u64* __restrict__ pin, 
         }
         loc += Qp0 - 1 - i;
     }
+    double dh[K], dl[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+    {
+        dh[i] = fp_from_u64(lh[i] >> 30);
+        dl[i] = fp_from_u64(lh[i] & 0x3FFFFFFFull);
+    }
+#pragma unroll 2
     for (int y = 0; y < L; ++y)
     {
-        const PrimeConst py = pcs[y];
-        u64 x = 0;
-        int l2 = 0;
-#pragma unroll
-        for (int i = 0; i < K; ++i)
+        const PrimeConst* ppy = pcs + y;
+        const u64 q = ppy->p;
+        u64 x;
+        if (ppy->fp_var != 0 && K <= 8)
         {
-            u64 t = reduce_u64(lh[i], py);
-            t = mod_sub(t, half_mod[l2 + y], py.p);
-            t = mod_sub(x, t, py.p);
-            const TwPair w = lqm[l2 + y];
-            x = csub(shoup_mul_lazy(t, w.w, w.ws, py.p), py.p);
-            l2 += Qp0 - 1 - i;
+            const double dp = fp_from_u64(q), dnp = -dp;
+            double acc = 0.0; // |acc| <= 2K * 0.51 q
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+            {
+                const TwPair b0 = ld_tw(btab + ((long long) y * K + i) * 2);
+                const TwPair b1 = ld_tw(btab + ((long long) y * K + i) * 2 + 1);
+                acc = __dadd_rn(acc, fp_mulmod(dh[i], u2d(b0.w), u2d(b0.ws), dnp));
+                acc = __dadd_rn(acc, fp_mulmod(dl[i], u2d(b1.w), u2d(b1.ws), dnp));
+            }
+            x = fp_canon(__dsub_rn(fp_from_u64(cst[y]), acc), ppy->pinv, dnp, dp);
+        }
+        else
+        {
+            const PrimeConst py = *ppy;
+            x = 0;
+            int l2 = 0;
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+            {
+                u64 t = reduce_u64(lh[i], py);
+                t = mod_sub(t, half_mod[l2 + y], py.p);
+                t = mod_sub(x, t, py.p);
+                const TwPair w = lqm[l2 + y];
+                x = csub(shoup_mul_lazy(t, w.w, w.ws, py.p), py.p);
+                l2 += Qp0 - 1 - i;
+            }
         }
         pout[(long long) y << logn] = x;
     }
@@ -569,7 +601,8 @@ __device__ __forceinline__ void moddown2_corr_body(const u64* __restrict__ pin, 
 __global__ void __launch_bounds__(256)
     k_moddown2_corr(const u64* __restrict__ acc, u64* __restrict__ corr, const PrimeConst* __restrict__ pcs,
                     const u64* __restrict__ half, const u64* __restrict__ half_mod,
-                    const TwPair* __restrict__ lqm, int logn, int Qpl, int L, int Qp0, int Q0, int K)
+                    const TwPair* __restrict__ lqm, const TwPair* __restrict__ btab, const u64* __restrict__ cst,
+                    int logn, int Qpl, int L, int Qp0, int Q0, int K)
 {
     const int idx = blockIdx.x * 256 + threadIdx.x;
     const long long bc = blockIdx.y; // b*2 + c
@@ -577,7 +610,7 @@ __global__ void __launch_bounds__(256)
     u64* pout = corr + ((bc * L) << logn) + idx;
 #define HEON_MD2(n)                                                                                \
     case n:                                                                                        \
-        moddown2_corr_body<n>(pin, pout, pcs, half, half_mod, lqm, logn, L, Qp0, Q0);              \
+        moddown2_corr_body<n>(pin, pout, pcs, half, half_mod, lqm, btab, cst, logn, L, Qp0, Q0);   \
         break;
     switch (K)
     {
@@ -881,8 +914,8 @@ static void moddown_add(const Context& c, u64* acc, u64* tmp, const u64* ct_in, 
             {
                 dim3 g(c.n >> 8, batch * 2);
                 LaunchScope scope(KC_MODDOWN, st);
-                k_moddown2_corr<<<g, 256, 0, st>>>(acc, tmp, c.d_pc, c.d_half, c.d_half_mod, c.d_lqm_pair, c.logn, Qpl,
-                                                L, c.Qp, c.Q_size, K);
+                k_moddown2_corr<<<g, 256, 0, st>>>(acc, tmp, c.d_pc, c.d_half, c.d_half_mod, c.d_lqm_pair, c.d_md2_B,
+                                                c.d_md2_cst, c.logn, Qpl, L, c.Qp, c.Q_size, K);
             }
             check_launch();
             launch_ntt(c, tmp, tmp, (long long) batch * 2 * L, range_primes(0, L), false, st);

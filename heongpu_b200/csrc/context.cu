@@ -394,6 +394,46 @@ void upload_tables(Context& c)
             mprod.push_back(TwPair{m, shoup(m, q)});
         }
         c.d_md2_M = upload(mprod);
+        // FP64 tables of the correction chain (only meaningful for primes the FP64 path handles)
+        const int K = c.P_size;
+        std::vector<TwPair> btab((size_t) c.Q_size * K * 2);
+        std::vector<u64> cst(c.Q_size);
+        for (int y = 0; y < c.Q_size; ++y)
+        {
+            const u64 q = c.mod[y].value;
+            std::vector<u64> m(K), hm(K), B(K);
+            size_t l2 = 0;
+            for (int i = 0; i < K; ++i)
+            {
+                m[i] = c.last_q_modinv[l2 + y];
+                hm[i] = c.half_mod[l2 + y];
+                l2 += c.Qp - 1 - i;
+            }
+            u64 suffix = 1, acc = 0;
+            for (int i = K - 1; i >= 0; --i)
+            {
+                suffix = mulmod(suffix, m[i], q);
+                B[i] = suffix;
+            }
+            for (int i = 0; i < K; ++i)
+                acc = (u64) (((u128) acc + mulmod(hm[i] % q, B[i], q)) % q);
+            cst[y] = acc;
+            for (int i = 0; i < K; ++i)
+            {
+                const u64 b30 = mulmod(B[i], (u64) ((1ull << 30) % q), q);
+                const double w0 = (double) b30, w1 = (double) B[i];
+                const double i0 = w0 / (double) q, i1 = w1 / (double) q;
+                TwPair t0, t1;
+                std::memcpy(&t0.w, &w0, 8);
+                std::memcpy(&t0.ws, &i0, 8);
+                std::memcpy(&t1.w, &w1, 8);
+                std::memcpy(&t1.ws, &i1, 8);
+                btab[((size_t) y * K + i) * 2] = t0;
+                btab[((size_t) y * K + i) * 2 + 1] = t1;
+            }
+        }
+        c.d_md2_B = upload(btab);
+        c.d_md2_cst = upload(cst);
     }
     c.d_half = upload(c.half);
     c.d_half_mod = upload(c.half_mod);
@@ -472,6 +512,8 @@ Context::~Context()
     cudaFree(d_last_q_modinv);
     cudaFree(d_lqm_pair);
     cudaFree(d_md2_M);
+    cudaFree(d_md2_B);
+    cudaFree(d_md2_cst);
     cudaFree(d_half);
     cudaFree(d_half_mod);
     cudaFree(d_rescaled_last_q_modinv);

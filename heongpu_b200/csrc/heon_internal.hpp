@@ -111,6 +111,11 @@ struct Context {
     int use_fp64 = 1; // FP64-pipe quotient for primes < 2^50 (HEON_NTT_FP64=0 disables)
     u64* d_last_q_modinv = nullptr;
     TwPair* d_lqm_pair = nullptr; // last_q_modinv with Shoup words
+    // FP64 form of the correction chain for Q primes below 2^50 (k_moddown2_corr):
+    //   c_y = Cst_y - sum_i (hi_i * (2^30 B_{i,y}) + lo_i * B_{i,y}),  B_{i,y} = prod_{j>=i} m_{j,y}
+    // [Q][K][2] double pairs {w, RN(w/q_y)} for {2^30*B mod q, B}, and Cst_y = sum_i half_mod_i * B_i mod q_y
+    TwPair* d_md2_B = nullptr;
+    u64* d_md2_cst = nullptr;
     TwPair* d_md2_M = nullptr; // [Q]: prod_i last_q_modinv[block i][y] = (p_0..p_{K-1})^-1 mod q_y, Shoup pair
     u64* d_half = nullptr;
     u64* d_half_mod = nullptr;
