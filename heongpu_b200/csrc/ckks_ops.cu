@@ -317,6 +317,147 @@ __device__ __forceinline__ void modup2_body(const u64* __restrict__ pc_in, u64* 
     }
 }
 
+// Fast form for short digits (I_j <= 4) and Q'_l <= 128: the per-target constants of this digit
+// (prime, 1/p, the I_j conversion factors, whether the FP64 path applies, which input limb a
+// digit-own target copies) and the r*prod table are staged in shared memory once per CTA, so the
+// 34-target loop of the BASELINE parameters runs without global loads or 64-bit address arithmetic.
+struct __align__(16) Mu2Rec {
+    TwPair m[4];
+    u64 p;
+    double dp, pinv;
+    int fp, self, pad0, pad1;
+};
+constexpr int kMu2MaxQ = 128;
+
+template <int IJ>
+__device__ __forceinline__ void modup2_fast_body(const u64* __restrict__ pc_in, u64* __restrict__ po,
+                                                 const PrimeConst* __restrict__ pcs,
+                                                 const TwPair* __restrict__ mi_inv, const Mu2Rec* rec,
+                                                 const u64* srp, int I_loc, int logn, int Qpl)
+{
+    u64 x[IJ][2], partial[IJ][2];
+    double pd[IJ][2];
+    bool dfp = true;
+    float r[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < IJ; ++i)
+    {
+        const PrimeConst pi = pcs[I_loc + i];
+        dfp = dfp && pi.fp_var != 0;
+        const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(pc_in + ((long long) i << logn));
+        x[i][0] = t.x;
+        x[i][1] = t.y;
+        const TwPair mi = mi_inv[I_loc + i];
+        const float mod = __ull2float_rn(pi.p);
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+        {
+            partial[i][e] = csub(shoup_mul_lazy(x[i][e], mi.w, mi.ws, pi.p), pi.p);
+            const float div = __ull2float_rn(partial[i][e]);
+            r[e] = __fadd_rn(r[e], __fdiv_rn(div, mod));
+        }
+    }
+    const u64* rp0 = srp + (unsigned) roundf(r[0]) * Qpl;
+    const u64* rp1 = srp + (unsigned) roundf(r[1]) * Qpl;
+    if (dfp)
+    {
+#pragma unroll
+        for (int i = 0; i < IJ; ++i)
+        {
+            pd[i][0] = fp_from_u64(partial[i][0]);
+            pd[i][1] = fp_from_u64(partial[i][1]);
+        }
+    }
+    const long long lstep = 1ll << logn;
+#pragma unroll 2
+    for (int k = 0; k < Qpl; ++k, po += lstep)
+    {
+        const Mu2Rec& rc = rec[k];
+        ulonglong2 res;
+        if (rc.self >= 0)
+        {
+            res.x = res.y = 0;
+#pragma unroll
+            for (int i = 0; i < IJ; ++i)
+                if (rc.self == i)
+                {
+                    res.x = x[i][0];
+                    res.y = x[i][1];
+                }
+        }
+        else if (dfp && rc.fp)
+        {
+            const double dnp = -rc.dp;
+            double a0 = 0.0, a1 = 0.0; // |acc| <= IJ * 0.6p, exact
+#pragma unroll
+            for (int j = 0; j < IJ; ++j)
+            {
+                const double w = u2d(rc.m[j].w), wi = u2d(rc.m[j].ws);
+                a0 = __dadd_rn(a0, fp_mulmod(pd[j][0], w, wi, dnp));
+                a1 = __dadd_rn(a1, fp_mulmod(pd[j][1], w, wi, dnp));
+            }
+            res.x = fp_canon(__dsub_rn(a0, fp_from_u64(rp0[k])), rc.pinv, dnp, rc.dp);
+            res.y = fp_canon(__dsub_rn(a1, fp_from_u64(rp1[k])), rc.pinv, dnp, rc.dp);
+        }
+        else
+        {
+            const u64 pkp = rc.p, p4 = 4 * pkp, np = 0 - pkp;
+            u64 a0 = 0, a1 = 0;
+#pragma unroll
+            for (int j = 0; j < IJ; ++j)
+            {
+                a0 = csub(a0 + shoup_lazy_ptx(partial[j][0], rc.m[j].w, rc.m[j].ws, np), p4);
+                a1 = csub(a1 + shoup_lazy_ptx(partial[j][1], rc.m[j].w, rc.m[j].ws, np), p4);
+            }
+            res.x = mod_sub(csub(csub(a0, 2 * pkp), pkp), rp0[k], pkp);
+            res.y = mod_sub(csub(csub(a1, 2 * pkp), pkp), rp1[k], pkp);
+        }
+        *reinterpret_cast<ulonglong2*>(po) = res;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    k_modup2_fast(const u64* __restrict__ coef, long long coef_bs, u64* __restrict__ out,
+                  const PrimeConst* __restrict__ pcs, const TwPair* __restrict__ base_change,
+                  const TwPair* __restrict__ mi_inv, const u64* __restrict__ rprod,
+                  const int* __restrict__ I_j_, const int* __restrict__ I_loc_, int logn, int d, int Qpl,
+                  int L, int depth, int K)
+{
+    __shared__ Mu2Rec rec[kMu2MaxQ];
+    __shared__ u64 srp[kMu2MaxQ * 5];
+    const int idx = (blockIdx.x * 256 + threadIdx.x) * 2;
+    const int dg = blockIdx.y;
+    const long long bz = blockIdx.z;
+    const int I_j = I_j_[dg];
+    const int I_loc = I_loc_[dg];
+    for (int k = threadIdx.x; k < Qpl; k += 256)
+    {
+        const PrimeConst pk = pcs[level_prime(k, L, depth)];
+        Mu2Rec rc;
+        for (int j = 0; j < 4; ++j)
+            rc.m[j] = j < I_j ? base_change[j + k * I_j + I_loc * Qpl] : TwPair{0, 0};
+        rc.p = pk.p;
+        rc.dp = (double) pk.p;
+        rc.pinv = pk.pinv;
+        rc.fp = pk.fp_var != 0;
+        rc.self = (k >= I_loc && k < I_loc + I_j) ? k - I_loc : -1;
+        rc.pad0 = rc.pad1 = 0;
+        rec[k] = rc;
+    }
+    for (int t = threadIdx.x; t < (K + 1) * Qpl; t += 256)
+        srp[t] = rprod[((long long) (t / Qpl) * d + dg) * Qpl + (t % Qpl)];
+    __syncthreads();
+    const u64* pin = coef + bz * coef_bs + idx + ((long long) I_loc << logn);
+    u64* po = out + (((bz * d + dg) * Qpl) << logn) + idx;
+    switch (I_j)
+    {
+        case 1: modup2_fast_body<1>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl); break;
+        case 2: modup2_fast_body<2>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl); break;
+        case 3: modup2_fast_body<3>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl); break;
+        case 4: modup2_fast_body<4>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl); break;
+    }
+}
+
 template <int CW>
 __global__ void __launch_bounds__(256)
     k_modup2(const u64* __restrict__ coef, long long coef_bs, u64* __restrict__ out,
@@ -829,7 +970,10 @@ static int keyswitch_modup_ntt(const Context& c, const u64* coef, long long coef
         dim3 g(wide ? c.n >> 9 : c.n >> 8, d, batch);
         {
             LaunchScope scope(KC_MODUP2, st);
-            if (wide)
+            if (wide && Qpl <= kMu2MaxQ && K <= 4)
+                k_modup2_fast<<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_pc, t.d_base_change_pair, t.d_mi_inv_pair,
+                                              t.d_rprod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth, K);
+            else if (wide)
                 k_modup2<2><<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_pc, t.d_base_change_pair, t.d_mi_inv_pair,
                                             t.d_rprod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth);
             else
