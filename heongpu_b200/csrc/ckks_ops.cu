@@ -8,6 +8,7 @@
 // addition}.cu (exact lines cited at each kernel).  All element-wise
 // arithmetic uses the reference's Barrett sequence (modarith.cuh), so stored
 // words are identical to the reference's.
+#include <cstdlib>
 #include "modarith.cuh"
 #include "ntt_core.cuh"
 #include "ops.hpp"
@@ -118,8 +119,8 @@ __global__ void __launch_bounds__(256)
 // reference: src/lib/kernel/switchkey.cu:164-285 (Method I), 287-398 (Method II)
 // One thread owns two adjacent coefficients of one limb of one ciphertext.  The key (larger
 // than L2 at the BASELINE sizes) should cross HBM once per batch, not once per ciphertext:
-//  * blockDim = (256/BY, BY): the BY warps-rows of a CTA work on BY ciphertexts of the batch
-//    and read the SAME key words, which the first reader leaves in L1;
+//  * blockDim = (256/BY, BY): the BY warp-rows of a CTA work on BY ciphertexts of the batch
+//    and read the SAME key words, which the first reader leaves in L1 (HEON_MAC_BY, default 1);
 //  * the batch group is the fastest-varying block coordinate, so CTAs that are resident
 //    together share the key tile through L2.
 __global__ void __launch_bounds__(256)
@@ -995,8 +996,12 @@ static void keyswitch_mac(const Context& c, const u64* tmp, const u64* key, u64*
     const int L = c.Q_size - depth, K = c.P_size, Qpl = L + K;
     {
         LaunchScope scope(KC_KEYSWITCH_MAC, st);
+        static const int by_max = [] {
+            const char* v = getenv("HEON_MAC_BY");
+            return v ? atoi(v) : 1; // measured on B200: sharing through L2 alone is as fast (71.7 vs 73.3 us/op)
+        }();
         int by = 1;
-        while (by < 8 && by * 2 <= batch && (c.n >> 1) >= 256 / by * 2)
+        while (by < by_max && by * 2 <= batch && (c.n >> 1) >= 256 / by * 2)
             by *= 2;
         const int tx = 256 / by; // threads along the coefficient axis, two coefficients each
         dim3 g((batch + by - 1) / by, (c.n >> 1) / tx, Qpl), blk(tx, by);
