@@ -24,6 +24,9 @@
 #ifndef HEON_NTT_MINBLOCKS
 #define HEON_NTT_MINBLOCKS 3
 #endif
+#ifndef HEON_COL_MINBLOCKS
+#define HEON_COL_MINBLOCKS HEON_NTT_MINBLOCKS
+#endif
 
 namespace heon {
 
@@ -259,7 +262,7 @@ __device__ __forceinline__ void col_pass_body(const Map& map, const u64* in, u64
 }
 
 template <int S, bool INV, class Map>
-__global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS) ntt_col_pass(Map map, const TwPair* __restrict__ tw_all,
+__global__ void __launch_bounds__(256, HEON_COL_MINBLOCKS) ntt_col_pass(Map map, const TwPair* __restrict__ tw_all,
                                                     const PrimeConst* __restrict__ pcs,
                                                     const TwPair* __restrict__ inv_last, int logn,
                                                     bool first_pass, int variant)

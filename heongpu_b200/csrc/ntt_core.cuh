@@ -176,6 +176,9 @@ __device__ __forceinline__ u64 d2u(double x) { return (u64) __double_as_longlong
 
 __device__ __forceinline__ double fp_mulmod(double y, double w, double winv, double np)
 {
+#ifdef HEON_FP_TRACK
+    heon_fp_track(y); // host emulation only: records max |Y| to check the 2^51 operand bound
+#endif
     const double q = __dsub_rn(__fma_rn(y, winv, HEON_FP_MAGIC), HEON_FP_MAGIC);
     const double h = __dmul_rn(y, w);
     const double l = __fma_rn(y, w, -h);

@@ -36,6 +36,9 @@ static inline double __fma_rn(double a, double b, double c) { return std::fma(a,
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+static double g_fp_max = 0.0; // largest |Y| ever multiplied on the FP64 path
+static inline void heon_fp_track(double y) { if (std::fabs(y) > g_fp_max) g_fp_max = std::fabs(y); }
+#define HEON_FP_TRACK
 #include "../heongpu_b200/csrc/ntt_core.cuh"
 using namespace heon;
 
@@ -64,6 +67,49 @@ template <int VAR> static void fwd(std::vector<u64>& x, const std::vector<TwPair
             u64 v[16];
             for (int k = 0; k < 16; ++k) v[k] = row[16 * tt + k];
             ct_round_b<8, VAR, 1>(v, tw.data(), 4, r, tt, bc);
+            for (int k = 0; k < 16; ++k) x[r * 256 + 16 * tt + k] = ct_finish<VAR>(v[k], bc, pc);
+        }
+    }
+}
+
+// forward transform with the row pass of the TMA kernels: bare-double twiddles per row
+// (stage16_sm: winv rebuilt from w with the two-word 1/p)
+template <int VAR> static void fwd_sm(std::vector<u64>& x, const std::vector<TwPair>& twf, const std::vector<TwPair>& tw_int,
+                                      const PrimeConst& pc)
+{
+    const BflyConst bc = make_bc(pc);
+    const int S1 = 4;
+    for (int col = 0; col < 256; ++col)
+    {
+        u64 v[16];
+        for (int k = 0; k < 16; ++k) v[k] = ct_prep<VAR>(x[k * 256 + col], bc, true);
+        ct_round_a<VAR>(v, twf.data(), 0, 0, bc);
+        for (int k = 0; k < 16; ++k) x[k * 256 + col] = v[k];
+    }
+    for (int r = 0; r < 16; ++r)
+    {
+        double rowtw[256] = {0};
+        for (int u = 0; u < 4; ++u)
+            for (int g = 0; g < (1 << u); ++g)
+                rowtw[(1 << u) - 1 + g] = (double) tw_int[(1u << (S1 + u)) + ((size_t) r << u) + g].w;
+        for (int u = 4; u < 8; ++u)
+            for (int g = 0; g < (1 << (u - 4)); ++g)
+                for (int tt = 0; tt < 16; ++tt)
+                    rowtw[16 + ((1 << (u - 4)) - 1 + g) * 16 + tt] =
+                        (double) tw_int[(1u << (S1 + u)) + ((size_t) r << u) + (tt << (u - 4)) + g].w;
+        u64 row[256];
+        for (int tt = 0; tt < 16; ++tt)
+        {
+            u64 v[16];
+            for (int k = 0; k < 16; ++k) v[k] = x[r * 256 + tt + 16 * k];
+            ct_round_a_sm<VAR>(v, rowtw, bc);
+            for (int k = 0; k < 16; ++k) row[tt + 16 * k] = v[k];
+        }
+        for (int tt = 0; tt < 16; ++tt)
+        {
+            u64 v[16];
+            for (int k = 0; k < 16; ++k) v[k] = row[16 * tt + k];
+            ct_round_b_sm<VAR>(v, rowtw, tt, bc);
             for (int k = 0; k < 16; ++k) x[r * 256 + 16 * tt + k] = ct_finish<VAR>(v[k], bc, pc);
         }
     }
@@ -134,6 +180,7 @@ int main()
         pc.fin_m = (unsigned) ((((u128) 1) << (pc.bits + 31)) / p);
         pc.nc_ok = pc.bits <= 57;
         pc.pinv = 1.0 / (double) p;
+        pc.pinv_lo = std::fma(-(double) p, pc.pinv, 1.0) / (double) p;
         const u64 ni = invmod(N, p), wn = mulmod(itw[1].w, ni, p);
         const TwPair ninv{ni, shoup(ni, p)}, wninv{wn, shoup(wn, p)};
         for (int pattern = 0; pattern < 3; ++pattern)
@@ -183,6 +230,23 @@ int main()
                     ++failures;
                 }
             }
+            for (int var = 3; var < 5; ++var) // shared-memory twiddle form of the row pass
+            {
+                if ((var == 3 && pc.bits > 47) || (var == 4 && pc.bits > 50))
+                    continue;
+                std::vector<u64> x = a;
+                if (pattern == 0)
+                    for (int i = 0; i < N; i += 3)
+                        x[i] += 3 * p;
+                var == 3 ? fwd_sm<3>(x, twf, tw, pc) : fwd_sm<4>(x, twf, tw, pc);
+                int bad = 0;
+                for (int i = 0; i < N; ++i) bad += x[i] != ref[i];
+                if (bad)
+                {
+                    printf("FAIL fwd_sm bits=%d var=%d pattern=%d mismatches=%d\n", bits, var, pattern, bad);
+                    ++failures;
+                }
+            }
             for (int gvar = 0; gvar < 2; ++gvar)
             {
                 std::vector<u64> x = ref;
@@ -197,6 +261,7 @@ int main()
             }
         }
     }
+    const double ntt_fp_max = g_fp_max; // operands seen inside the transforms (incl. worst-case lazy inputs)
     // FP64 modular product: exact for ANY integer |Y| < 2^51 (random and edge operands)
     for (int bits : {30, 40, 46, 47, 49, 50})
     {
@@ -231,6 +296,13 @@ int main()
             printf("FAIL fp_mulmod bits=%d bad=%d\n", bits, bad);
             ++failures;
         }
+    }
+    // the FP64 butterflies are exact only while every multiplied operand stays below 2^51
+    printf("max |Y| inside the FP64 transforms: 2^%.2f\n", std::log2(ntt_fp_max));
+    if (!(ntt_fp_max < 0x1p51))
+    {
+        printf("FAIL: FP64 operand bound exceeded\n");
+        ++failures;
     }
     printf(failures ? "FAILED %d\n" : "OK\n", failures);
     return failures != 0;

@@ -1,5 +1,5 @@
 """CPU: compile the device butterfly header for the host and check every
-lazy-reduction variant (forward VAR 0/1/2, inverse GVAR 0/1) against the
+lazy-reduction variant (forward VAR 0/1/2 integer, VAR 3/4 all-FP64 incl. the shared-memory-twiddle row pass, inverse GVAR 0/1) against the
 textbook merged NTT for prime sizes 30..61 bits, incl. worst-case lazy inputs."""
 import os
 import subprocess
