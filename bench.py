@@ -44,7 +44,7 @@ WORKLOADS = {
     "n14_C2": "CKKS N=2^14 {50,40,40,40}/{48} L=4 K=1 (logq~218) mul+relin+rescale depth 0 (BASELINE config 2)",
     "M4_bfv_rot": "BFV N=2^15 default 128-bit modulus (14+1 primes, defaultmodulus.cpp:34-51) rotate_rows sweep over steps +-2^0..2^7 (BASELINE config 4)",
 }
-DEFAULT_BATCH = {"C3_II": 8, "C3_I": 4, "n14_C2": 1024, "M4_bfv_rot": 64}
+DEFAULT_BATCH = {"C3_II": 16, "C3_I": 8, "n14_C2": 1024, "M4_bfv_rot": 64}
 # src/lib/util/defaultmodulus.cpp:34-51 (N = 32768, 128-bit security): the last prime is P
 BFV_32768_MODULUS = [0x2000000002b0001, 0x2000000003a0001, 0x2000000005b0001, 0x200000000640001, 0x400000000270001,
                      0x400000000350001, 0x400000000360001, 0x4000000004d0001, 0x400000000570001, 0x400000000660001,
