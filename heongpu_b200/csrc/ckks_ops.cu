@@ -849,6 +849,30 @@ __global__ void __launch_bounds__(256)
         in[bz * in_bs + ((long long) (c * L + y) << logn) + idx];
 }
 
+// Galois automorphism X -> X^g applied IN THE NTT DOMAIN: a pure index permutation, no sign flips.
+// With the reference's bit-reversed layout out[i] = a(psi^(2*brev(i)+1)), sigma_g(a) evaluated at the
+// same point is a(psi^((2*brev(i)+1)*g)), i.e. word i' of the input with
+//     2*brev(i') + 1 = (2*brev(i) + 1) * g  (mod 2N).
+// Equal, word for word, to permuting in the coefficient domain and transforming afterwards
+// (divide_round_lastq_permute_ckks_kernel + GPU_NTT, switchkey.cu:1621-1718) for canonical data.
+// In natural order the map is k -> g*k + (g-1)/2 (mod N); the 32 lanes of a warp differ only in the
+// top five bits of k, so their sources are a permutation of ONE aligned 256-byte block: the gather is
+// fully coalesced.
+__global__ void __launch_bounds__(256)
+    k_galois_permute_ntt(const u64* __restrict__ in, long long in_bs, u64* __restrict__ out, long long out_bs,
+                         int logn, int L, unsigned galois_elt)
+{
+    const unsigned idx = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    const long long bz = blockIdx.z >> 1;
+    const int c = blockIdx.z & 1;
+    const unsigned k = __brev(idx) >> (32 - logn);
+    const unsigned f = (((2u * k + 1u) * galois_elt) & ((2u << logn) - 1u)) >> 1;
+    const unsigned src = __brev(f) >> (32 - logn);
+    const long long limb = (long long) (c * L + y) << logn;
+    out[bz * out_bs + limb + idx] = in[bz * in_bs + limb + src];
+}
+
 // ---------------------------------------------------------------------------
 // workspace (stream-ordered, cached by the device's default memory pool)
 // ---------------------------------------------------------------------------
@@ -1251,6 +1275,20 @@ void op_apply_galois(const Context& c, const u64* in, long long in_bs, u64* out,
         throw std::invalid_argument("BFV ciphertexts have no levels");
     const int L = c.Q_size - depth, K = c.P_size, Qpl = L + K;
     const long long N = c.n;
+    if (!coeff && c.galois_ntt)
+    {
+        // CKKS: key switch entirely in the NTT domain (only c1 and the 2K special limbs ever leave it),
+        // then the automorphism as an index permutation of the NTT words
+        Scratch ks((size_t) batch * 2 * L * N * 8, st);
+        op_keyswitch(c, in, in_bs, ks.w(), 2 * L * N, galois_key, depth, batch, st);
+        dim3 g(c.n >> 8, L, batch * 2);
+        {
+            LaunchScope scope(KC_ELEMENTWISE, st);
+            k_galois_permute_ntt<<<g, 256, 0, st>>>(ks.w(), 2 * L * N, out, out_bs, c.logn, L, galois_elt);
+        }
+        check_launch();
+        return;
+    }
     Scratch coef(coeff ? 8 : (size_t) batch * 2 * L * N * 8, st);
     const u64* cp = in;
     long long cbs = in_bs;
@@ -1296,6 +1334,31 @@ void op_rotate_hoisted(const Context& c, const u64* in, long long in_bs, u64* ou
         throw std::invalid_argument("no rotations requested");
     const int L = c.Q_size - depth, K = c.P_size, Qpl = L + K;
     const long long N = c.n;
+    if (c.galois_ntt)
+    {
+        // NTT-domain form: only c1 is taken to the coefficient domain (once); per rotation the inner
+        // product, the NTT-domain mod-down (+ c0) and the index permutation
+        Scratch coef1((size_t) batch * L * N * 8, st);
+        launch_ntt_strided_copy(c, in + (long long) L * N, in_bs, coef1.w(), L, batch, range_primes(0, L), true, st);
+        Scratch tmp(ks_tmp_words(c, depth, batch) * 8, st);
+        Scratch acc((size_t) batch * 2 * Qpl * N * 8, st);
+        Scratch corr((size_t) batch * 2 * L * N * 8, st);
+        Scratch ks((size_t) batch * 2 * L * N * 8, st);
+        const int d = keyswitch_modup_ntt(c, coef1.w(), L * N, tmp.w(), depth, batch, st);
+        for (int r = 0; r < count; ++r)
+        {
+            keyswitch_mac(c, tmp.w(), galois_keys[r], acc.w(), d, depth, batch, st);
+            moddown_add(c, acc.w(), corr.w(), in, in_bs, ks.w(), 2 * L * N, depth, batch, 1, st);
+            dim3 g(c.n >> 8, L, batch * 2);
+            {
+                LaunchScope scope(KC_ELEMENTWISE, st);
+                k_galois_permute_ntt<<<g, 256, 0, st>>>(ks.w(), 2 * L * N, out + (long long) r * out_rs, out_bs, c.logn,
+                                                     L, galois_elts[r]);
+            }
+            check_launch();
+        }
+        return;
+    }
     Scratch coef((size_t) batch * 2 * L * N * 8, st);
     launch_ntt_strided_copy(c, in, in_bs, coef.w(), 2 * L, batch, range_primes(0, L), true, st);
     Scratch tmp(ks_tmp_words(c, depth, batch) * 8, st);

@@ -107,6 +107,7 @@ struct Context {
     int ntt_persistent = 0; // HEON_NTT_PERSISTENT=1: row-pass CTAs walk several tiles (double-buffered TMA)
     int ntt_pipe = 0; // N = 2^16: warp-specialised pipelined fused forward transform (HEON_NTT_PIPE=1 enables; needs all CTAs co-resident, i.e. an otherwise idle GPU)
     int ntt_group = 48; // polynomials per L2-resident group of the fused transform (HEON_NTT_GROUP)
+    int galois_ntt = 1; // CKKS automorphisms as NTT-domain permutations after an NTT-domain key switch (HEON_GALOIS_NTT=0: coefficient-domain path)
     int ntt_fused = 0; // forward transform as one ticket-ordered kernel, pass-to-pass data in L2 (HEON_NTT_FUSED=1 enables; superseded by the pipelined kernel)
     int use_fp64 = 1; // FP64-pipe quotient for primes < 2^50 (HEON_NTT_FP64=0 disables)
     u64* d_last_q_modinv = nullptr;
