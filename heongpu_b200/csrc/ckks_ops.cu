@@ -123,7 +123,13 @@ __global__ void __launch_bounds__(256)
 //    and read the SAME key words, which the first reader leaves in L1 (HEON_MAC_BY, default 1);
 //  * the batch group is the fastest-varying block coordinate, so CTAs that are resident
 //    together share the key tile through L2.
-__global__ void __launch_bounds__(256)
+#ifndef HEON_MAC_MINBLOCKS
+#define HEON_MAC_MINBLOCKS 4
+#endif
+#ifndef HEON_MAC_UNROLL
+#define HEON_MAC_UNROLL 4
+#endif
+__global__ void __launch_bounds__(256, HEON_MAC_MINBLOCKS)
     k_keyswitch_mac(const u64* __restrict__ in, const u64* __restrict__ key, u64* __restrict__ out,
                     const PrimeConst* __restrict__ pcs, int logn, int d, int L, int Qpl, int Qp0,
                     int depth, int batch)
@@ -143,7 +149,8 @@ __global__ void __launch_bounds__(256)
 
     u64 a0l = 0, a0h = 0, a1l = 0, a1h = 0; // coefficient idx
     u64 b0l = 0, b0h = 0, b1l = 0, b1h = 0; // coefficient idx+1
-#pragma unroll 4
+    constexpr int kUnroll = HEON_MAC_UNROLL;
+#pragma unroll kUnroll
     for (int i = 0; i < d; ++i)
     {
         const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(pin + i * in_step);

@@ -553,6 +553,44 @@ template <> class HEOperator<Scheme::CKKS> {
         rotate_rows(ct, ct, gk, shift, opt);
     }
 
+    // Baby-step loop of the BSGS matrix-vector product: every shift of `shifts` applied to the same
+    // ciphertext (fast_single_hoisting_rotation_ckks_method_I/II, operator.cu:4674-5446; protected in the
+    // reference, public here).  Mod-up and the forward NTTs are shared by all rotations; result r is
+    // bit-identical to rotate_rows(in, out[r], gk, shifts[r]).
+    std::vector<Ciphertext<Scheme::CKKS>> rotate_rows_hoisted(Ciphertext<Scheme::CKKS>& in, Galoiskey<Scheme::CKKS>& gk,
+                                                              const std::vector<int>& shifts,
+                                                              const ExecutionOptions& opt = ExecutionOptions())
+    {
+        if (in.rescale_required_ || in.relinearization_required_)
+            throw std::invalid_argument("Ciphertext can not be rotated because of the non-linear part or noise!");
+        std::vector<const uint64_t*> keys;
+        std::vector<uint32_t> elts;
+        for (int s : shifts)
+        {
+            const int elt = heon_steps_to_galois_elt(s, context_->n, gk.group_order_);
+            auto it = gk.device_location_.find(elt);
+            if (elt == 0 || it == gk.device_location_.end())
+                throw std::logic_error("Galois key not present!");
+            keys.push_back(it->second.data());
+            elts.push_back((uint32_t) elt);
+        }
+        const size_t w = words(2, in.depth_);
+        DeviceVector<Data64> mem(w * shifts.size(), opt.stream_);
+        detail::check(heon_ckks_rotate_hoisted(h(), in.data(), 0, mem.data(), 0, (long long) w, keys.data(), elts.data(),
+                                               (int) shifts.size(), in.depth_, 1, opt.stream_));
+        std::vector<Ciphertext<Scheme::CKKS>> out(shifts.size());
+        for (size_t r = 0; r < shifts.size(); ++r)
+        {
+            DeviceVector<Data64> one(w, opt.stream_);
+            detail::cuda(cudaMemcpyAsync(one.data(), mem.data() + r * w, w * sizeof(Data64), cudaMemcpyDeviceToDevice,
+                                         opt.stream_));
+            copy_meta(in, out[r]);
+            out[r].memory_set(std::move(one));
+            out[r].cipher_size_ = 2;
+        }
+        return out;
+    }
+
     // operator.cuh:718-884 + multiply_plain_ckks (operator.cu:839-871)
     void multiply_plain(Ciphertext<Scheme::CKKS>& a, Plaintext<Scheme::CKKS>& p, Ciphertext<Scheme::CKKS>& out,
                         const ExecutionOptions& opt = ExecutionOptions())

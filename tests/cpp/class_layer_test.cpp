@@ -87,6 +87,25 @@ int main(int argc, char** argv)
         try { operators.rotate_rows(C1, R, galois_key, 5); } catch (const std::logic_error&) { threw = true; }
         if (!threw) { std::puts("FAIL: missing galois key must throw"); return 1; }
 
+        // hoisted rotations == stand-alone rotations
+        {
+            Galoiskey<S> gk2(context, std::vector<int>{1, 2, -1});
+            int seed = 20;
+            for (auto& kv : gk2.galois_elt)
+                gk2.set_key(kv.second, words(context->prime_vector_, context->digit_count(0) * 2, Qp, n, seed++));
+            std::vector<int> shifts{2, -1, 1};
+            auto hs = operators.rotate_rows_hoisted(C1, gk2, shifts);
+            for (size_t r = 0; r < shifts.size(); ++r)
+            {
+                Ciphertext<S> one;
+                operators.rotate_rows(C1, one, gk2, shifts[r]);
+                std::vector<Data64> x1, x2;
+                hs[r].get_data(x1);
+                one.get_data(x2);
+                if (x1 != x2) { std::puts("FAIL: hoisted rotation differs from rotate_rows"); return 1; }
+            }
+        }
+
         // plaintext operands, keyswitch, conjugate
         auto pw = words(context->prime_vector_, 1, Q, n, 5);
         Plaintext<S> P1(context, pw);

@@ -264,3 +264,65 @@ def test_rotate_bit_exact_vs_reference_kernels(name, depth):
     assert torch.equal(out.data[0], ro)
 
 
+
+
+# ------------------------------------------- alternate code paths (opt-in) --
+def _ctx_with_env(name, **env):
+    """A fresh context created under the given HEON_* switches (read once, at context creation)."""
+    import os
+    api = _api()
+    log_n, qb, pb = PARAMS[name]
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return api.HEContext(log_n, qb, pb, device=0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("env", [{"HEON_NTT_PIPE": 1}, {"HEON_NTT_FUSED": 1}, {"HEON_NTT_FP64": 0}, {"HEON_NTT_TMA": 0}])
+def test_alternate_ntt_paths_agree(env):
+    """The opt-in transforms (warp-specialised pipelined kernel, ticket-ordered fused kernel), the
+    integer-only butterflies and the LSU row pass must give the default path's words."""
+    name = "n16_II_small"
+    ctx, alt, oc = gpu_ctx(name), _ctx_with_env(name, **env), oracle_ctx(name)
+    order = ctx.level_primes(0)
+    x = residues(130, [oc.primes[i] for i in order], oc.n, (3,))  # 3 polys per prime
+    a, b = to_dev(x), to_dev(x)
+    ctx.ntt(a, order)
+    alt.ntt(b, order)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b), env
+    ctx.ntt(a, order, inverse=True)
+    alt.ntt(b, order, inverse=True)
+    assert torch.equal(a, b) and np.array_equal(to_host(a), x), env
+
+
+@pytest.mark.parametrize("name,env", [("n16_II_small", {"HEON_NTT_PIPE": 1}), ("n13_II", {"HEON_GALOIS_NTT": 0}),
+                                      ("n16_I_small", {"HEON_GALOIS_NTT": 0}), ("n13_II", {"HEON_NTT_FP64": 0})])
+def test_alternate_operator_paths_agree(name, env):
+    """multiply + relinearize + rotation through the alternate paths equal the default path."""
+    api = _api()
+    ctx, alt, oc = gpu_ctx(name), _ctx_with_env(name, **env), oracle_ctx(name)
+    batch, L, n = 2, oc.Q, oc.n
+    a = ciphertext(131, oc.primes, L, n, 2, batch)
+    b = ciphertext(132, oc.primes, L, n, 2, batch)
+    key = to_dev(eval_key(133, oc.primes, oc.digits(0), n))
+    elt = api.lib.heon_steps_to_galois_elt(3, n, 5)
+    res = []
+    for c in (ctx, alt):
+        op = api.HEArithmeticOperator(c)
+        A, B = api.Ciphertext(c, to_dev(a)), api.Ciphertext(c, to_dev(b))
+        Cc = api.Ciphertext(c, torch.zeros(batch, 3, L, n, dtype=torch.int64, device="cuda"))
+        op.multiply(A, B, Cc)
+        op.relinearize_inplace(Cc, api.Relinkey(c, key))
+        R_ = api.Ciphertext(c, torch.zeros(batch, 2, L, n, dtype=torch.int64, device="cuda"))
+        op.apply_galois(A, R_, api.Galoiskey(c, {elt: key}), elt)
+        torch.cuda.synchronize()
+        res.append((Cc.data.clone(), R_.data.clone()))
+    assert torch.equal(res[0][0], res[1][0]), ("relinearize", env)
+    assert torch.equal(res[0][1], res[1][1]), ("apply_galois", env)
