@@ -21,22 +21,37 @@ namespace heon {
 
 // (c0,c1) x (d0,d1) -> (c0d0, c0d1+c1d0, c1d1) per limb.
 // reference: src/lib/kernel/multiplication.cu:102-126 (cross_multiplication)
+// For primes below 2^50 the four products run on the FP64 pipe (fp_mulmod with the quotient
+// multiplier rebuilt as b*RN(1/p): |T| <= p(1/2 + 3/16)); same canonical residues.
 __global__ void __launch_bounds__(256)
     k_cross_multiply(const u64* __restrict__ a, const u64* __restrict__ b, u64* __restrict__ out,
                      long long a_bs, long long b_bs, long long o_bs, const Mod64* __restrict__ mods,
-                     int logn, int L)
+                     const PrimeConst* __restrict__ pcs, int logn, int L)
 {
     const int idx = blockIdx.x * 256 + threadIdx.x;
     const int y = blockIdx.y;
     const long long bz = blockIdx.z;
-    const Mod64 m = mods[y];
     const long long loc = idx + ((long long) y << logn);
     const long long comp = (long long) L << logn;
     const u64* pa = a + bz * a_bs;
     const u64* pb = b + bz * b_bs;
     u64* po = out + bz * o_bs;
-    u64 a0 = pa[loc], a1 = pa[loc + comp];
-    u64 b0 = pb[loc], b1 = pb[loc + comp];
+    const u64 a0 = pa[loc], a1 = pa[loc + comp];
+    const u64 b0 = pb[loc], b1 = pb[loc + comp];
+    const PrimeConst* pc = pcs + y;
+    if (pc->fp_var != 0 && ((a0 | a1 | b0 | b1) >> 50) == 0)
+    {
+        const double dp = fp_from_u64(pc->p), dnp = -dp, pinv = pc->pinv;
+        const double x0 = fp_from_u64(a0), x1 = fp_from_u64(a1), y0 = fp_from_u64(b0), y1 = fp_from_u64(b1);
+        const double i0 = __dmul_rn(y0, pinv), i1 = __dmul_rn(y1, pinv);
+        const double t00 = fp_mulmod(x0, y0, i0, dnp), t01 = fp_mulmod(x0, y1, i1, dnp);
+        const double t10 = fp_mulmod(x1, y0, i0, dnp), t11 = fp_mulmod(x1, y1, i1, dnp);
+        po[loc] = fp_canon(t00, pinv, dnp, dp);
+        po[loc + comp] = fp_canon(__dadd_rn(t01, t10), pinv, dnp, dp);
+        po[loc + 2 * comp] = fp_canon(t11, pinv, dnp, dp);
+        return;
+    }
+    const Mod64 m = mods[y];
     u64 o0 = barrett_mul(a0, b0, m);
     u64 o10 = barrett_mul(a0, b1, m);
     u64 o11 = barrett_mul(a1, b0, m);
@@ -775,6 +790,149 @@ __global__ void __launch_bounds__(256)
 #undef HEON_MD2
 }
 
+// Fast form (K <= 4, L <= 128): per-limb constants staged in shared memory, two coefficients per thread.
+struct __align__(16) Md2Rec {
+    TwPair b[8]; // {2^30*B_i, B_i} pairs, i < K
+    u64 p;
+    double dp, pinv, cst;
+    int fp, pad0;
+};
+
+template <int K>
+__device__ __forceinline__ void moddown2_corr_fast_body(const u64* __restrict__ pin, u64* __restrict__ pout,
+                                                        const PrimeConst* __restrict__ pcs,
+                                                        const u64* __restrict__ half, const u64* __restrict__ half_mod,
+                                                        const TwPair* __restrict__ lqm, const Md2Rec* rec, int logn, int L,
+                                                        int Qp0, int Q0)
+{
+    u64 lh[K][2];
+    {
+        u64 last_ct[K][2];
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+        {
+            const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(pin + ((long long) i << logn));
+            last_ct[i][0] = t.x;
+            last_ct[i][1] = t.y;
+        }
+        int loc = 0;
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+        {
+            const u64 pp = pcs[Qp0 - 1 - i].p;
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                lh[i][e] = mod_add(last_ct[K - 1 - i][e], half[i], pp);
+#pragma unroll
+            for (int j = 0; j < K - 1 - i; ++j)
+            {
+                const PrimeConst pj = pcs[Q0 + j];
+                const TwPair w = lqm[loc + Q0 + j];
+                const u64 hm = half_mod[loc + Q0 + j];
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                {
+                    u64 t = reduce_u64(lh[i][e], pj);
+                    t = mod_sub(t, hm, pj.p);
+                    t = mod_sub(last_ct[j][e], t, pj.p);
+                    last_ct[j][e] = csub(shoup_mul_lazy(t, w.w, w.ws, pj.p), pj.p);
+                }
+            }
+            loc += Qp0 - 1 - i;
+        }
+    }
+    double dh[K][2], dl[K][2];
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+        {
+            dh[i][e] = fp_from_u64(lh[i][e] >> 30);
+            dl[i][e] = fp_from_u64(lh[i][e] & 0x3FFFFFFFull);
+        }
+    const long long lstep = 1ll << logn;
+#pragma unroll 2
+    for (int y = 0; y < L; ++y, pout += lstep)
+    {
+        const Md2Rec& rc = rec[y];
+        ulonglong2 res;
+        if (rc.fp)
+        {
+            const double dnp = -rc.dp;
+            double a0 = 0.0, a1 = 0.0; // |acc| <= 2K * 0.51 q
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+            {
+                const double w0 = u2d(rc.b[2 * i].w), i0 = u2d(rc.b[2 * i].ws);
+                const double w1 = u2d(rc.b[2 * i + 1].w), i1 = u2d(rc.b[2 * i + 1].ws);
+                a0 = __dadd_rn(a0, __dadd_rn(fp_mulmod(dh[i][0], w0, i0, dnp), fp_mulmod(dl[i][0], w1, i1, dnp)));
+                a1 = __dadd_rn(a1, __dadd_rn(fp_mulmod(dh[i][1], w0, i0, dnp), fp_mulmod(dl[i][1], w1, i1, dnp)));
+            }
+            res.x = fp_canon(__dsub_rn(rc.cst, a0), rc.pinv, dnp, rc.dp);
+            res.y = fp_canon(__dsub_rn(rc.cst, a1), rc.pinv, dnp, rc.dp);
+        }
+        else
+        {
+            const PrimeConst py = pcs[y];
+            u64 x[2] = {0, 0};
+            int l2 = 0;
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+            {
+                const TwPair w = lqm[l2 + y];
+                const u64 hm = half_mod[l2 + y];
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                {
+                    u64 t = reduce_u64(lh[i][e], py);
+                    t = mod_sub(t, hm, py.p);
+                    t = mod_sub(x[e], t, py.p);
+                    x[e] = csub(shoup_mul_lazy(t, w.w, w.ws, py.p), py.p);
+                }
+                l2 += Qp0 - 1 - i;
+            }
+            res.x = x[0];
+            res.y = x[1];
+        }
+        *reinterpret_cast<ulonglong2*>(pout) = res;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    k_moddown2_corr_fast(const u64* __restrict__ acc, u64* __restrict__ corr, const PrimeConst* __restrict__ pcs,
+                         const u64* __restrict__ half, const u64* __restrict__ half_mod,
+                         const TwPair* __restrict__ lqm, const TwPair* __restrict__ btab,
+                         const u64* __restrict__ cst, int logn, int Qpl, int L, int Qp0, int Q0, int K)
+{
+    __shared__ Md2Rec rec[128];
+    for (int y = threadIdx.x; y < L; y += 256)
+    {
+        const PrimeConst py = pcs[y];
+        Md2Rec rc;
+        for (int i = 0; i < 8; ++i)
+            rc.b[i] = i < 2 * K ? btab[(long long) y * K * 2 + i] : TwPair{0, 0};
+        rc.p = py.p;
+        rc.dp = (double) py.p;
+        rc.pinv = py.pinv;
+        rc.cst = (double) cst[y];
+        rc.fp = py.fp_var != 0;
+        rc.pad0 = 0;
+        rec[y] = rc;
+    }
+    __syncthreads();
+    const int idx = (blockIdx.x * 256 + threadIdx.x) * 2;
+    const long long bc = blockIdx.y; // b*2 + c
+    const u64* pin = acc + ((bc * Qpl + L) << logn) + idx;
+    u64* pout = corr + ((bc * L) << logn) + idx;
+    switch (K)
+    {
+        case 1: moddown2_corr_fast_body<1>(pin, pout, pcs, half, half_mod, lqm, rec, logn, L, Qp0, Q0); break;
+        case 2: moddown2_corr_fast_body<2>(pin, pout, pcs, half, half_mod, lqm, rec, logn, L, Qp0, Q0); break;
+        case 3: moddown2_corr_fast_body<3>(pin, pout, pcs, half, half_mod, lqm, rec, logn, L, Qp0, Q0); break;
+        case 4: moddown2_corr_fast_body<4>(pin, pout, pcs, half, half_mod, lqm, rec, logn, L, Qp0, Q0); break;
+    }
+}
+
 // out[c][y] = (ct[c][y] if selected) + acc[c][y]*M_y + corr[c][y]   (all NTT domain)
 __global__ void __launch_bounds__(256)
     k_moddown2_final(const u64* __restrict__ acc, const u64* __restrict__ corr, const u64* __restrict__ ct,
@@ -950,7 +1108,7 @@ void op_multiply(const Context& c, const u64* a, long long a_bs, const u64* b, l
     dim3 g(c.n >> 8, L, batch);
     {
         LaunchScope scope(KC_CROSS_MULTIPLY, st);
-        k_cross_multiply<<<g, 256, 0, st>>>(a, b, out, a_bs, b_bs, o_bs, c.d_mod, c.logn, L);
+        k_cross_multiply<<<g, 256, 0, st>>>(a, b, out, a_bs, b_bs, o_bs, c.d_mod, c.d_pc, c.logn, L);
     }
     check_launch();
 }
@@ -1092,10 +1250,19 @@ static void moddown_add(const Context& c, u64* acc, u64* tmp, const u64* ct_in, 
             launch_ntt_strided(c, acc + (long long) L * N, Qpl * N, K, 0, (long long) batch * 2,
                                range_primes(c.Q_size, K), true, st);
             {
-                dim3 g(c.n >> 8, batch * 2);
                 LaunchScope scope(KC_MODDOWN, st);
-                k_moddown2_corr<<<g, 256, 0, st>>>(acc, tmp, c.d_pc, c.d_half, c.d_half_mod, c.d_lqm_pair, c.d_md2_B,
-                                                c.d_md2_cst, c.logn, Qpl, L, c.Qp, c.Q_size, K);
+                if (K <= 4 && L <= 128)
+                {
+                    dim3 g(c.n >> 9, batch * 2);
+                    k_moddown2_corr_fast<<<g, 256, 0, st>>>(acc, tmp, c.d_pc, c.d_half, c.d_half_mod, c.d_lqm_pair,
+                                                         c.d_md2_B, c.d_md2_cst, c.logn, Qpl, L, c.Qp, c.Q_size, K);
+                }
+                else
+                {
+                    dim3 g(c.n >> 8, batch * 2);
+                    k_moddown2_corr<<<g, 256, 0, st>>>(acc, tmp, c.d_pc, c.d_half, c.d_half_mod, c.d_lqm_pair, c.d_md2_B,
+                                                    c.d_md2_cst, c.logn, Qpl, L, c.Qp, c.Q_size, K);
+                }
             }
             check_launch();
             launch_ntt(c, tmp, tmp, (long long) batch * 2 * L, range_primes(0, L), false, st);
