@@ -267,8 +267,13 @@ def run_ours(args, rank, world, local):
         cnt = (C.c_longlong * 16)()
         ncls = api.lib.heon_profile_end(msv, cnt, 16)
         Qp = inp["Q"] + inp["K"]
+        K = inp["K"]
         polys = {  # limb-polynomials transformed per op by each NTT class
-            "fwd": inp["d"] * Qp + 2 * L, "inv": L + (2 if inp["K"] == 1 else 2 * Qp)}
+            # Method I: d*Q' mod-up digits + 2L corrections; Method II: the digits' own limbs are not
+            # transformed (they are the input's NTT words), the mod-down corrections add 2L
+            "fwd": inp["d"] * Qp + 2 * L - (0 if K == 1 else L),
+            # INTT: c2 (L) + the 2K special limbs of the accumulator (NTT-domain mod-down)
+            "inv": L + 2 * K}
         tot = sum(msv[i] for i in range(ncls))
         for i in range(ncls):
             if cnt[i] == 0:

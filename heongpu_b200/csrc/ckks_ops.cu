@@ -356,7 +356,7 @@ template <int IJ>
 __device__ __forceinline__ void modup2_fast_body(const u64* __restrict__ pc_in, u64* __restrict__ po,
                                                  const PrimeConst* __restrict__ pcs,
                                                  const TwPair* __restrict__ mi_inv, const Mu2Rec* rec,
-                                                 const u64* srp, int I_loc, int logn, int Qpl)
+                                                 const u64* srp, int I_loc, int logn, int Qpl, bool skip_own)
 {
     u64 x[IJ][2], partial[IJ][2];
     double pd[IJ][2];
@@ -399,6 +399,8 @@ __device__ __forceinline__ void modup2_fast_body(const u64* __restrict__ pc_in, 
         ulonglong2 res;
         if (rc.self >= 0)
         {
+            if (skip_own)
+                continue; // the slot already holds the original NTT-domain words
             res.x = res.y = 0;
 #pragma unroll
             for (int i = 0; i < IJ; ++i)
@@ -444,7 +446,7 @@ __global__ void __launch_bounds__(256)
                   const PrimeConst* __restrict__ pcs, const TwPair* __restrict__ base_change,
                   const TwPair* __restrict__ mi_inv, const u64* __restrict__ rprod,
                   const int* __restrict__ I_j_, const int* __restrict__ I_loc_, int logn, int d, int Qpl,
-                  int L, int depth, int K)
+                  int L, int depth, int K, int skip_own)
 {
     __shared__ Mu2Rec rec[kMu2MaxQ];
     __shared__ u64 srp[kMu2MaxQ * 5];
@@ -474,10 +476,10 @@ __global__ void __launch_bounds__(256)
     u64* po = out + (((bz * d + dg) * Qpl) << logn) + idx;
     switch (I_j)
     {
-        case 1: modup2_fast_body<1>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl); break;
-        case 2: modup2_fast_body<2>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl); break;
-        case 3: modup2_fast_body<3>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl); break;
-        case 4: modup2_fast_body<4>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl); break;
+        case 1: modup2_fast_body<1>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, skip_own != 0); break;
+        case 2: modup2_fast_body<2>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, skip_own != 0); break;
+        case 3: modup2_fast_body<3>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, skip_own != 0); break;
+        case 4: modup2_fast_body<4>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, skip_own != 0); break;
     }
 }
 
@@ -1135,13 +1137,53 @@ void op_plain(const Context& c, const u64* ct, long long ct_bs, const u64* pt, l
     check_launch();
 }
 
+// tmp[b][digit(y)][y] = src[b][y] for every Q limb y: the digit's own limbs of the mod-up output,
+// NTT domain, taken from the ciphertext component BEFORE it is brought to the coefficient domain.
+__global__ void __launch_bounds__(256)
+    k_stash_own_limbs(const u64* __restrict__ src, long long src_bs, u64* __restrict__ tmp,
+                      const int* __restrict__ I_j_, const int* __restrict__ I_loc_, int logn, int d, int Qpl)
+{
+    const int idx = (blockIdx.x * 256 + threadIdx.x) * 2;
+    const int y = blockIdx.y;
+    const long long bz = blockIdx.z;
+    int i = 0;
+    while (i + 1 < d && y >= I_loc_[i] + I_j_[i])
+        ++i;
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(src + bz * src_bs + ((long long) y << logn) + idx);
+    *reinterpret_cast<ulonglong2*>(tmp + (((bz * d + i) * Qpl + y) << logn) + idx) = v;
+}
+
+// Method II with the fast mod-up: true when the own-limb shortcut applies (see keyswitch_stash_own)
+static bool own_limb_shortcut(const Context& c, int depth)
+{
+    const int L = c.Q_size - depth, K = c.P_size, Qpl = L + K;
+    return c.method == 2 && c.skip_own && K <= 4 && Qpl <= kMu2MaxQ && c.n >= 512 && c.lvl2[depth].d <= 64;
+}
+
+// `src`: the key-switched component in the NTT domain, [b][L][N] with batch stride src_bs.
+static bool keyswitch_stash_own(const Context& c, const u64* src, long long src_bs, u64* tmp, int depth, int batch,
+                                cudaStream_t st)
+{
+    if (!own_limb_shortcut(c, depth) || (src_bs & 1) || ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(tmp)) & 15))
+        return false;
+    const int L = c.Q_size - depth, Qpl = L + c.P_size;
+    const LevelTablesII& t = c.lvl2[depth];
+    dim3 g(c.n >> 9, L, batch);
+    {
+        LaunchScope scope(KC_ELEMENTWISE, st);
+        k_stash_own_limbs<<<g, 256, 0, st>>>(src, src_bs, tmp, t.d_I_j, t.d_I_loc, c.logn, t.d, Qpl);
+    }
+    check_launch();
+    return true;
+}
+
 // Key-switch core shared by relinearize / apply_galois / keyswitch:
 // takes the digit polynomial(s) in the coefficient domain and leaves
 // acc[b][2][Qpl][N] (NTT domain).  `tmp` must hold batch*d*Qpl*N words.
 // Part one: mod-up of the digits into every prime of Q'_l and forward NTT (tmp[b][d][Qpl][N]).
 // This half does not depend on the key: hoisted rotations run it once for many keys.
 static int keyswitch_modup_ntt(const Context& c, const u64* coef, long long coef_bs, u64* tmp, int depth,
-                               int batch, cudaStream_t st)
+                               int batch, cudaStream_t st, bool own_stashed = false)
 {
     const int L = c.Q_size - depth, K = c.P_size, Qpl = L + K;
     int d;
@@ -1160,9 +1202,12 @@ static int keyswitch_modup_ntt(const Context& c, const u64* coef, long long coef
         dim3 g(wide ? c.n >> 9 : c.n >> 8, d, batch);
         {
             LaunchScope scope(KC_MODUP2, st);
+            if (own_stashed && !(wide && Qpl <= kMu2MaxQ && K <= 4))
+                throw std::logic_error("own-limb shortcut needs the fast mod-up");
             if (wide && Qpl <= kMu2MaxQ && K <= 4)
                 k_modup2_fast<<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_pc, t.d_base_change_pair, t.d_mi_inv_pair,
-                                              t.d_rprod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth, K);
+                                              t.d_rprod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth, K,
+                                              own_stashed ? 1 : 0);
             else if (wide)
                 k_modup2<2><<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_pc, t.d_base_change_pair, t.d_mi_inv_pair,
                                             t.d_rprod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth);
@@ -1171,7 +1216,10 @@ static int keyswitch_modup_ntt(const Context& c, const u64* coef, long long coef
                                             t.d_rprod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth);
         }
         check_launch();
-        launch_ntt(c, tmp, tmp, (long long) batch * d * Qpl, level_primes(L, K, depth), false, st);
+        if (own_stashed)
+            launch_ntt_digit_skip(c, tmp, d, t.I_loc.data(), t.I_j.data(), L, depth, batch, st);
+        else
+            launch_ntt(c, tmp, tmp, (long long) batch * d * Qpl, level_primes(L, K, depth), false, st);
     }
     if (d > 64)
         throw std::invalid_argument("too many key-switch digits");
@@ -1200,9 +1248,9 @@ static void keyswitch_mac(const Context& c, const u64* tmp, const u64* key, u64*
 }
 
 static int keyswitch_core(const Context& c, const u64* coef, long long coef_bs, const u64* key,
-                          u64* tmp, u64* acc, int depth, int batch, cudaStream_t st)
+                          u64* tmp, u64* acc, int depth, int batch, cudaStream_t st, bool own_stashed = false)
 {
-    const int d = keyswitch_modup_ntt(c, coef, coef_bs, tmp, depth, batch, st);
+    const int d = keyswitch_modup_ntt(c, coef, coef_bs, tmp, depth, batch, st, own_stashed);
     keyswitch_mac(c, tmp, key, acc, d, depth, batch, st);
     return d;
 }
@@ -1314,11 +1362,13 @@ void op_relinearize(const Context& c, u64* ct, long long ct_bs, const u64* relin
     check_depth(c, depth);
     const int L = c.Q_size - depth, K = c.P_size, Qpl = L + K;
     const long long N = c.n;
-    // INTT c2 in place
-    launch_ntt_strided(c, ct, ct_bs, L, 2 * L, batch, range_primes(0, L), true, st);
     Scratch tmp(ks_tmp_words(c, depth, batch) * 8, st);
     Scratch acc((size_t) batch * 2 * Qpl * N * 8, st);
-    keyswitch_core(c, ct + 2LL * L * N, ct_bs, relin_key, tmp.w(), acc.w(), depth, batch, st);
+    // the digits' own limbs of the mod-up output are c2 itself (NTT domain): keep them before the INTT
+    const bool own = keyswitch_stash_own(c, ct + 2LL * L * N, ct_bs, tmp.w(), depth, batch, st);
+    // INTT c2 in place
+    launch_ntt_strided(c, ct, ct_bs, L, 2 * L, batch, range_primes(0, L), true, st);
+    keyswitch_core(c, ct + 2LL * L * N, ct_bs, relin_key, tmp.w(), acc.w(), depth, batch, st, own);
     moddown_add(c, acc.w(), tmp.w(), ct, ct_bs, ct, ct_bs, depth, batch, 3, st);
 }
 
@@ -1338,7 +1388,8 @@ void op_keyswitch(const Context& c, const u64* in, long long in_bs, u64* out, lo
     launch_ntt_strided_copy(c, in + (long long) L * N, in_bs, coef.w(), L, batch, range_primes(0, L), true, st);
     Scratch tmp(ks_tmp_words(c, depth, batch) * 8, st);
     Scratch acc((size_t) batch * 2 * Qpl * N * 8, st);
-    keyswitch_core(c, coef.w(), L * N, switch_key, tmp.w(), acc.w(), depth, batch, st);
+    const bool own = keyswitch_stash_own(c, in + (long long) L * N, in_bs, tmp.w(), depth, batch, st);
+    keyswitch_core(c, coef.w(), L * N, switch_key, tmp.w(), acc.w(), depth, batch, st, own);
     moddown_add(c, acc.w(), tmp.w(), in, in_bs, out, out_bs, depth, batch, 1, st);
 }
 
@@ -1518,7 +1569,8 @@ void op_rotate_hoisted(const Context& c, const u64* in, long long in_bs, u64* ou
         Scratch acc((size_t) batch * 2 * Qpl * N * 8, st);
         Scratch corr((size_t) batch * 2 * L * N * 8, st);
         Scratch ks((size_t) batch * 2 * L * N * 8, st);
-        const int d = keyswitch_modup_ntt(c, coef1.w(), L * N, tmp.w(), depth, batch, st);
+        const bool own = keyswitch_stash_own(c, in + (long long) L * N, in_bs, tmp.w(), depth, batch, st);
+        const int d = keyswitch_modup_ntt(c, coef1.w(), L * N, tmp.w(), depth, batch, st, own);
         for (int r = 0; r < count; ++r)
         {
             keyswitch_mac(c, tmp.w(), galois_keys[r], acc.w(), d, depth, batch, st);

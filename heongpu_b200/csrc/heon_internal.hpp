@@ -107,6 +107,7 @@ struct Context {
     int ntt_persistent = 0; // HEON_NTT_PERSISTENT=1: row-pass CTAs walk several tiles (double-buffered TMA)
     int ntt_pipe = 0; // N = 2^16: warp-specialised pipelined fused forward transform (HEON_NTT_PIPE=1 enables; needs all CTAs co-resident, i.e. an otherwise idle GPU)
     int ntt_group = 48; // polynomials per L2-resident group of the fused transform (HEON_NTT_GROUP)
+    int skip_own = 1; // Method II: the digits' own limbs skip mod-up and forward NTT (HEON_SKIP_OWN=0 disables)
     int galois_ntt = 1; // CKKS automorphisms as NTT-domain permutations after an NTT-domain key switch (HEON_GALOIS_NTT=0: coefficient-domain path)
     int ntt_fused = 0; // forward transform as one ticket-ordered kernel, pass-to-pass data in L2 (HEON_NTT_FUSED=1 enables; superseded by the pipelined kernel)
     int use_fp64 = 1; // FP64-pipe quotient for primes < 2^50 (HEON_NTT_FP64=0 disables)
@@ -164,6 +165,8 @@ void upload_bfv_tables(Context& c);
 // ---- NTT launchers (ntt.cu); all asynchronous on `st` ----
 void launch_ntt(const Context& c, const u64* src, u64* dst, long long n_polys, const PrimeList& pl,
                 bool inverse, cudaStream_t st);
+void launch_ntt_digit_skip(const Context& c, u64* tmp, int d, const int* I_loc, const int* I_j, int L, int depth,
+                           long long batch, cudaStream_t st);
 void launch_ntt_scattered(const Context& c, u64* base, const long long* d_offsets, int n_polys,
                           int prime, bool inverse, long long extent_words, bool aligned, cudaStream_t st);
 void launch_ntt_strided(const Context& c, u64* base, long long bstride, int per_batch, int first,

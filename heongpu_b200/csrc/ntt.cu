@@ -113,6 +113,32 @@ struct MapStridedCopy {
     __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&, int) const { return x; }
 };
 
+// Method-II key-switch buffer tmp[b][digit][Q'_l][N] WITHOUT the digits' own limbs (those hold the
+// original NTT-domain words already: NTT(INTT(x)) = x).  Poly z = (b, i, y') enumerates, per digit i,
+// the Q'_l - I_j[i] limbs outside [I_loc[i], I_loc[i] + I_j[i]).  In place.
+struct MapDigitSkip {
+    u64* base;
+    int d, Qpl, L, depth, logn, per_b;
+    short prefix[66], I_loc[65], I_j[65];
+    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& out, int& prime, int& aux) const
+    {
+        const long long b = z / per_b;
+        const int zl = (int) (z % per_b);
+        int i = 0;
+        while (i + 1 < d && zl >= prefix[i + 1])
+            ++i;
+        int y = zl - prefix[i];
+        if (y >= I_loc[i])
+            y += I_j[i];
+        in = out = base + (((b * d + i) * Qpl + y) << logn);
+        prime = level_prime(y, L, depth);
+        aux = 0;
+    }
+    static constexpr bool kXform = false;
+    static constexpr bool kLazyIn = false;
+    __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&, int) const { return x; }
+};
+
 // Method-I mod-up fused into the first pass: output poly z = (b, i, y) reads
 // digit i of ciphertext b (coefficient domain) and reduces it into prime y.
 // Replaces cipher_broadcast_leveled_kernel / ckks_duplicate_kernel
@@ -1287,6 +1313,33 @@ void launch_ntt(const Context& c, const u64* src, u64* dst, long long n_polys, c
     MapContig m{src, dst, pl, c.logn};
     const long long w = n_polys << c.logn;
     run_ntt(c, m, n_polys, inverse, Extent{src, w, dst, w, src, w}, st);
+}
+
+void launch_ntt_digit_skip(const Context& c, u64* tmp, int d, const int* I_loc, const int* I_j, int L, int depth,
+                           long long batch, cudaStream_t st)
+{
+    const int Qpl = L + c.P_size;
+    if (d > 64)
+        throw std::invalid_argument("too many key-switch digits");
+    MapDigitSkip m;
+    m.base = tmp;
+    m.d = d;
+    m.Qpl = Qpl;
+    m.L = L;
+    m.depth = depth;
+    m.logn = c.logn;
+    int acc = 0;
+    for (int i = 0; i < d; ++i)
+    {
+        m.prefix[i] = (short) acc;
+        m.I_loc[i] = (short) I_loc[i];
+        m.I_j[i] = (short) I_j[i];
+        acc += Qpl - I_j[i];
+    }
+    m.prefix[d] = (short) acc;
+    m.per_b = acc;
+    const long long w = (batch * d * Qpl) << c.logn;
+    run_ntt(c, m, batch * acc, false, Extent{tmp, w, tmp, w}, st);
 }
 
 void launch_ntt_scattered(const Context& c, u64* base, const long long* d_offsets, int n_polys,
