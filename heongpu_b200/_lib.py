@@ -29,6 +29,7 @@ SIGNATURES = {
     "heon_bfv_multiply": (ci, [vp, vp, ll, vp, ll, vp, ll, ci, vp]),
     "heon_bfv_relinearize": (ci, [vp, vp, ll, vp, ci, vp]),
     "heon_bfv_apply_galois": (ci, [vp, vp, ll, vp, ll, vp, C.c_uint32, ci, vp]),
+    "heon_bfv_keyswitch": (ci, [vp, vp, ll, vp, ll, vp, ci, vp]),
     "heon_context_destroy": (None, [vp]),
     "heon_context_info": (ci, [vp, C.POINTER(heon_info)]),
     "heon_context_table": (ci, [vp, ci, ci, u64p, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -352,6 +352,13 @@ class HEArithmeticOperator:
         out.cipher_size_ = 2
         return out
 
+    def keyswitch_bfv(self, ct, out, switch_key):
+        c = self.context_
+        _check(lib.heon_bfv_keyswitch(c._h, _ptr(ct.data), ct.stride, _ptr(out.data), out.stride, _ptr(switch_key.data),
+                                      ct.batch, _stream()))
+        out.cipher_size_ = 2
+        return out
+
     def rotate_rows_bfv(self, ct, out, galois_key, shift):
         return self.apply_galois_bfv(ct, out, galois_key, lib.heon_steps_to_galois_elt(shift, self.context_.n, 3))
 

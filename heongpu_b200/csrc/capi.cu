@@ -302,6 +302,23 @@ int heon_bfv_apply_galois(heon_context_t ctx, const uint64_t* in, long long is, 
     });
 }
 
+int heon_bfv_keyswitch(heon_context_t ctx, const uint64_t* in, long long is, uint64_t* out, long long os,
+                       const uint64_t* switch_key, int batch, void* stream)
+{
+    return guarded([&] {
+        if (!ctx || !in || !out || !switch_key || in == out)
+            throw std::invalid_argument("invalid buffers");
+        const Context& c = ctx->c;
+        need_device(c);
+        if (c.scheme != SCHEME_BFV)
+            throw std::invalid_argument("not a BFV context");
+        if (batch < 1)
+            throw std::invalid_argument("batch must be positive");
+        // the automorphism pipeline with the identity element: (c0, 0) + KeySwitch(c1), coefficient domain
+        op_apply_galois(c, in, is, out, os, switch_key, 1u, 0, batch, (cudaStream_t) stream);
+    });
+}
+
 void heon_context_destroy(heon_context_t ctx) { delete ctx; }
 
 int heon_context_info(heon_context_t ctx, heon_info* o)

@@ -823,6 +823,25 @@ template <> class Relinkey<Scheme::BFV> {
     bool relin_key_generated_ = false;
 };
 
+template <> class Switchkey<Scheme::BFV> {
+  public:
+    explicit Switchkey(HEContext<Scheme::BFV> ctx) : context_(ctx), key_type(ctx->keyswitching_type_) {}
+    void set_data(const std::vector<Data64>& words, cudaStream_t st = cudaStreamDefault)
+    {
+        const size_t need = (size_t) context_->digit_count() * 2 * context_->Q_prime_size * context_->n;
+        if (words.size() != need)
+            throw std::invalid_argument("Invalid switch key size!");
+        device_location_ = DeviceVector<Data64>(words, st);
+        switch_key_generated_ = true;
+    }
+    Data64* data() const { return device_location_.data(); }
+    HEContext<Scheme::BFV> context_;
+    keyswitching_type key_type;
+    storage_type storage_type_ = storage_type::DEVICE;
+    DeviceVector<Data64> device_location_;
+    bool switch_key_generated_ = false;
+};
+
 template <> class Galoiskey<Scheme::BFV> {
   public:
     explicit Galoiskey(HEContext<Scheme::BFV> ctx) : context_(ctx), key_type(ctx->keyswitching_type_)
@@ -960,6 +979,20 @@ template <> class HEOperator<Scheme::BFV> {
                              const ExecutionOptions& opt = ExecutionOptions())
     {
         rotate_rows(ct, ct, gk, shift, opt);
+    }
+    // switchkey_method_I/II (bfv/operator.cu:975-1372)
+    void keyswitch(Ciphertext<Scheme::BFV>& in, Ciphertext<Scheme::BFV>& out, Switchkey<Scheme::BFV>& sk,
+                   const ExecutionOptions& opt = ExecutionOptions())
+    {
+        if (in.relinearization_required_)
+            throw std::invalid_argument("Ciphertext can not be key-switched because of the non-linear part!");
+        if (!sk.switch_key_generated_)
+            throw std::invalid_argument("Switchkey is not generated!");
+        DeviceVector<Data64> mem(words(2), opt.stream_);
+        detail::check(heon_bfv_keyswitch(h(), in.data(), 0, mem.data(), 0, sk.data(), 1, opt.stream_));
+        copy_meta(in, out);
+        out.memory_set(std::move(mem));
+        out.cipher_size_ = 2;
     }
     void rotate_columns(Ciphertext<Scheme::BFV>& in, Ciphertext<Scheme::BFV>& out, Galoiskey<Scheme::BFV>& gk,
                         const ExecutionOptions& opt = ExecutionOptions())

@@ -231,6 +231,11 @@ int heon_bfv_apply_galois(heon_context_t ctx, const uint64_t* in, long long in_s
                           long long out_stride, const uint64_t* galois_key, uint32_t galois_elt, int batch,
                           void* stream);
 
+/* ---- HEOperator<BFV>::switchkey_method_I / _II (bfv/operator.cu:975-1372, HEOperator::keyswitch):
+ *      out = (c0, 0) + KeySwitch(c1) under `switch_key`; in, out: [2][Q][N] coefficient domain. */
+int heon_bfv_keyswitch(heon_context_t ctx, const uint64_t* in, long long in_stride, uint64_t* out,
+                       long long out_stride, const uint64_t* switch_key, int batch, void* stream);
+
 /* Per-kernel-class CUDA-event profiler (used by bench.py for the roofline
  * line): begin() arms it, end() synchronises the device and returns, per
  * class, the summed device time in ms and the launch count; the return value

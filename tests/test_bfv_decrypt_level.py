@@ -172,3 +172,57 @@ def _gpu_backend_for(name):
 @pytest.mark.parametrize("name", ["bfv_n12_I", "bfv_n12_II", "bfv_n13_I"])
 def test_bfv_decrypt_level_gpu(name):
     _run(name, _gpu_backend_for(name))
+
+
+# ---- BFV keyswitch (switchkey_method_I/II, bfv/operator.cu:975-1372): re-encryption under a new secret ----
+def _switch_key(sc, s_new_ntt, seed):
+    """key that takes a ciphertext part under sc.s to the secret s_new: rk0 = -(a*s_new + e) + [own limb] P*s."""
+    d = sc.ob.digits()
+    key = np.zeros((d, 2, sc.Qp, sc.n), dtype=np.uint64)
+    allp = list(range(sc.Qp))
+    for i in range(d):
+        a = np.stack([splitmix64(seed + 100 * i + y, sc.n) % np.uint64(p) for y, p in enumerate(sc.primes)])
+        e = sc.oc.ntt(_rns(_small(seed + 100 * i + 55, sc.n, 4), sc.primes), allp)
+        for y, p in enumerate(sc.primes):
+            v = (-(a[y].astype(object) * s_new_ntt[y].astype(object) + e[y].astype(object))) % p
+            in_digit = y < sc.Q and ((y == i) if sc.K == 1 else (y // sc.K == i))
+            if in_digit:
+                v = (v + (sc.Pprod % p) * sc.s_ntt[y].astype(object)) % p
+            key[i, 0, y] = v.astype(np.uint64)
+            key[i, 1, y] = a[y]
+    return key
+
+
+def _run_keyswitch(name, backend):
+    sc = Bfv(name)
+    n, t = sc.n, sc.t
+    m = (splitmix64(7, n) % np.uint64(t)).astype(np.int64)
+    ct = sc.encrypt(m, 5000)
+    s_new = _small(4242, n, 1)
+    s_new_ntt = sc.oc.ntt(_rns(s_new, sc.primes), list(range(sc.Qp)))
+    out = backend(sc, ct, _switch_key(sc, s_new_ntt, 6000))
+    sc.s_ntt = s_new_ntt  # decrypt under the NEW secret
+    assert sc.decrypt(out, 32) == [int(v) for v in m[:32]], "key-switched ciphertext does not decrypt under the new secret"
+
+
+@pytest.mark.parametrize("name", ["bfv_n12_I", "bfv_n12_II"])
+def test_bfv_keyswitch_decrypts_oracle(name):
+    _run_keyswitch(name, lambda sc, ct, key: sc.ob.apply_galois(ct, key, 1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["bfv_n12_I", "bfv_n12_II", "bfv_n13_I"])
+def test_bfv_keyswitch_decrypts_gpu(name):
+    def backend(sc, ct, key):
+        import torch
+        from heongpu_b200 import api
+        from tests.gpu_common import to_dev, to_host
+        ctx = bfv_gpu_ctx(name)
+        op = api.HEArithmeticOperator(ctx)
+        A = api.Ciphertext(ctx, to_dev(ct))
+        out = api.Ciphertext(ctx, torch.zeros(1, 2, sc.Q, sc.n, dtype=torch.int64, device="cuda"))
+        op.keyswitch_bfv(A, out, api.Switchkey(ctx, to_dev(key)))
+        got = to_host(out.data)[0].copy()
+        assert np.array_equal(got, sc.ob.apply_galois(ct, key, 1)), "BFV keyswitch differs from the oracle"
+        return got
+    _run_keyswitch(name, backend)
