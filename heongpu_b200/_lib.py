@@ -29,6 +29,9 @@ SIGNATURES = {
     "heon_bfv_multiply": (ci, [vp, vp, ll, vp, ll, vp, ll, ci, vp]),
     "heon_bfv_relinearize": (ci, [vp, vp, ll, vp, ci, vp]),
     "heon_bfv_apply_galois": (ci, [vp, vp, ll, vp, ll, vp, C.c_uint32, ci, vp]),
+    "heon_bfv_add_plain": (ci, [vp, vp, ll, vp, ll, vp, ll, ci, ci, vp]),
+    "heon_bfv_sub_plain": (ci, [vp, vp, ll, vp, ll, vp, ll, ci, ci, vp]),
+    "heon_bfv_multiply_plain": (ci, [vp, vp, ll, vp, ll, vp, ll, ci, vp]),
     "heon_bfv_keyswitch": (ci, [vp, vp, ll, vp, ll, vp, ci, vp]),
     "heon_context_destroy": (None, [vp]),
     "heon_context_info": (ci, [vp, C.POINTER(heon_info)]),

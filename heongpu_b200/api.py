@@ -194,7 +194,7 @@ class Plaintext:
 
     def __init__(self, context, data, depth=0, scale=1.0):
         self.context = context
-        if data.dim() == 2:
+        if data.dim() <= 2:  # CKKS [L][N] / BFV [N] -> a batch of one
             data = data.unsqueeze(0)
         self.data = data
         self.depth_ = depth
@@ -349,6 +349,27 @@ class HEArithmeticOperator:
         key = galois_key.device_location_[galois_elt]
         _check(lib.heon_bfv_apply_galois(c._h, _ptr(ct.data), ct.stride, _ptr(out.data), out.stride, _ptr(key),
                                          galois_elt, ct.batch, _stream()))
+        out.cipher_size_ = 2
+        return out
+
+    def add_plain_bfv(self, ct, pt, out):
+        c = self.context_
+        _check(lib.heon_bfv_add_plain(c._h, _ptr(ct.data), ct.stride, _ptr(pt.data), pt.stride, _ptr(out.data), out.stride,
+                                      ct.cipher_size_, ct.batch, _stream()))
+        out.cipher_size_ = ct.cipher_size_
+        return out
+
+    def sub_plain_bfv(self, ct, pt, out):
+        c = self.context_
+        _check(lib.heon_bfv_sub_plain(c._h, _ptr(ct.data), ct.stride, _ptr(pt.data), pt.stride, _ptr(out.data), out.stride,
+                                      ct.cipher_size_, ct.batch, _stream()))
+        out.cipher_size_ = ct.cipher_size_
+        return out
+
+    def multiply_plain_bfv(self, ct, pt, out):
+        c = self.context_
+        _check(lib.heon_bfv_multiply_plain(c._h, _ptr(ct.data), ct.stride, _ptr(pt.data), pt.stride, _ptr(out.data),
+                                           out.stride, ct.batch, _stream()))
         out.cipher_size_ = 2
         return out
 

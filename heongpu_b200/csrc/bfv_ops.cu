@@ -221,4 +221,111 @@ void op_bfv_multiply(const Context& c, const u64* a, long long a_bs, const u64* 
     check_launch_bfv();
 }
 
+// ---------------------------------------------------------------------------
+// BFV plaintext operands (coefficient-domain ciphertexts, plaintext = [N] values below t)
+// ---------------------------------------------------------------------------
+
+// component 0 +/- (m * floor(Q/t) + round-fix), the other components copied.
+// reference: src/lib/kernel/addition.cu:50-173 (addition_plain_bfv_poly, substraction_plain_bfv_poly)
+template <int OP>
+__global__ void __launch_bounds__(256)
+    k_bfv_addsub_plain(const u64* __restrict__ ct, long long ct_bs, const u64* __restrict__ pt, long long pt_bs,
+                       u64* __restrict__ out, long long o_bs, const Mod64* __restrict__ mods, u64 plain_mod,
+                       u64 Q_mod_t, u64 upper_threshold, const u64* __restrict__ coeff_div, int logn, int Q, int comps)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    const long long bz = blockIdx.z / comps;
+    const int c = blockIdx.z % comps;
+    const long long loc = idx + ((long long) (c * Q + y) << logn);
+    u64 x = ct[bz * ct_bs + loc];
+    if (c == 0)
+    {
+        const Mod64 m = mods[y];
+        const u64 message = pt[bz * pt_bs + idx];
+        u64 fix = message * Q_mod_t + upper_threshold;
+        fix = (u64) (long long) (int) (fix / plain_mod); // `int(fix / plain_mod.value)` in the reference kernel
+        u64 r = barrett_mul(message, coeff_div[y], m);
+        r = mod_add(r, fix, m.value);
+        x = OP == 0 ? mod_add(r, x, m.value) : mod_sub(x, r, m.value);
+    }
+    out[bz * o_bs + loc] = x;
+}
+
+// centred lift of the plaintext into every q_i: m >= (t+1)/2 -> m + (q_i - t)
+// reference: src/lib/kernel/multiplication.cu:274-296 (threshold_kernel)
+__global__ void __launch_bounds__(256)
+    k_bfv_threshold(const u64* __restrict__ pt, long long pt_bs, u64* __restrict__ out, const Mod64* __restrict__ mods,
+                    const u64* __restrict__ upper_inc, u64 upper_threshold, int logn, int Q)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    const long long bz = blockIdx.z;
+    const u64 v = pt[bz * pt_bs + idx];
+    out[((bz * Q + y) << logn) + idx] = v >= upper_threshold ? mod_add(v, upper_inc[y], mods[y].value) : v;
+}
+
+// reference: src/lib/kernel/multiplication.cu:298-311 (cipherplain_kernel), in place on the NTT-domain copy
+__global__ void __launch_bounds__(256)
+    k_bfv_cipherplain(u64* __restrict__ ct, const u64* __restrict__ pt, const Mod64* __restrict__ mods, int logn, int Q)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    const long long bz = blockIdx.z >> 1;
+    const int c = blockIdx.z & 1;
+    const long long o = (((bz * 2 + c) * Q + y) << logn) + idx;
+    ct[o] = barrett_mul(ct[o], pt[((bz * Q + y) << logn) + idx], mods[y]);
+}
+
+// add_plain_bfv / sub_plain_bfv (bfv/operator.cu:216-340): op 1 add, 2 subtract
+void op_bfv_addsub_plain(const Context& c, const u64* ct, long long ct_bs, const u64* pt, long long pt_bs, u64* out,
+                         long long o_bs, int comps, int batch, int op, cudaStream_t st)
+{
+    if (c.scheme != SCHEME_BFV)
+        throw std::invalid_argument("not a BFV context");
+    if (comps < 2 || comps > 3)
+        throw std::invalid_argument("Invalid Ciphertexts size!");
+    const BfvTables& t = c.bfv;
+    dim3 g(c.n >> 8, c.Q_size, batch * comps);
+    {
+        LaunchScope scope(KC_ELEMENTWISE, st);
+        if (op == 1)
+            k_bfv_addsub_plain<0><<<g, 256, 0, st>>>(ct, ct_bs, pt, pt_bs, out, o_bs, c.d_mod, c.plain_modulus, t.Q_mod_t,
+                                                   t.upper_threshold, t.d_coeff_div_plainmod, c.logn, c.Q_size, comps);
+        else
+            k_bfv_addsub_plain<1><<<g, 256, 0, st>>>(ct, ct_bs, pt, pt_bs, out, o_bs, c.d_mod, c.plain_modulus, t.Q_mod_t,
+                                                   t.upper_threshold, t.d_coeff_div_plainmod, c.logn, c.Q_size, comps);
+    }
+    check_launch_bfv();
+}
+
+// multiply_plain_bfv (bfv/operator.cu:432-503), coefficient-domain ciphertext: lift the plaintext,
+// NTT both, multiply, INTT.  out: [b][2][Q][N] contiguous.
+void op_bfv_multiply_plain(const Context& c, const u64* ct, long long ct_bs, const u64* pt, long long pt_bs, u64* out,
+                           long long o_bs, int batch, cudaStream_t st)
+{
+    if (c.scheme != SCHEME_BFV)
+        throw std::invalid_argument("not a BFV context");
+    const int Q = c.Q_size;
+    const long long N = c.n;
+    if (o_bs != 2 * Q * N && batch > 1)
+        throw std::invalid_argument("multiply_plain needs a contiguous output batch");
+    const BfvTables& t = c.bfv;
+    ScratchB tp((size_t) batch * Q * N * 8, st);
+    {
+        LaunchScope scope(KC_ELEMENTWISE, st);
+        k_bfv_threshold<<<dim3(c.n >> 8, Q, batch), 256, 0, st>>>(pt, pt_bs, tp.w(), c.d_mod, t.d_upper_halfincrement,
+                                                               t.upper_threshold, c.logn, Q);
+    }
+    check_launch_bfv();
+    launch_ntt(c, tp.w(), tp.w(), (long long) batch * Q, range_primes(0, Q), false, st);
+    launch_ntt_strided_copy(c, ct, ct_bs, out, 2 * Q, batch, range_primes(0, Q), false, st);
+    {
+        LaunchScope scope(KC_ELEMENTWISE, st);
+        k_bfv_cipherplain<<<dim3(c.n >> 8, Q, batch * 2), 256, 0, st>>>(out, tp.w(), c.d_mod, c.logn, Q);
+    }
+    check_launch_bfv();
+    launch_ntt(c, out, out, (long long) batch * 2 * Q, range_primes(0, Q), true, st);
+}
+
 } // namespace heon

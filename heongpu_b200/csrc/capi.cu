@@ -302,6 +302,46 @@ int heon_bfv_apply_galois(heon_context_t ctx, const uint64_t* in, long long is, 
     });
 }
 
+int heon_bfv_add_plain(heon_context_t ctx, const uint64_t* ct, long long cs, const uint64_t* pt, long long ps,
+                       uint64_t* out, long long os, int comps, int batch, void* stream)
+{
+    return guarded([&] {
+        if (!ctx || !ct || !pt || !out)
+            throw std::invalid_argument("null argument");
+        const Context& c = ctx->c;
+        need_device(c);
+        if (batch < 1)
+            throw std::invalid_argument("batch must be positive");
+        op_bfv_addsub_plain(c, ct, cs, pt, ps, out, os, comps, batch, 1, (cudaStream_t) stream);
+    });
+}
+int heon_bfv_sub_plain(heon_context_t ctx, const uint64_t* ct, long long cs, const uint64_t* pt, long long ps,
+                       uint64_t* out, long long os, int comps, int batch, void* stream)
+{
+    return guarded([&] {
+        if (!ctx || !ct || !pt || !out)
+            throw std::invalid_argument("null argument");
+        const Context& c = ctx->c;
+        need_device(c);
+        if (batch < 1)
+            throw std::invalid_argument("batch must be positive");
+        op_bfv_addsub_plain(c, ct, cs, pt, ps, out, os, comps, batch, 2, (cudaStream_t) stream);
+    });
+}
+int heon_bfv_multiply_plain(heon_context_t ctx, const uint64_t* ct, long long cs, const uint64_t* pt, long long ps,
+                            uint64_t* out, long long os, int batch, void* stream)
+{
+    return guarded([&] {
+        if (!ctx || !ct || !pt || !out || ct == out)
+            throw std::invalid_argument("invalid buffers");
+        const Context& c = ctx->c;
+        need_device(c);
+        if (batch < 1)
+            throw std::invalid_argument("batch must be positive");
+        op_bfv_multiply_plain(c, ct, cs, pt, ps, out, os, batch, (cudaStream_t) stream);
+    });
+}
+
 int heon_bfv_keyswitch(heon_context_t ctx, const uint64_t* in, long long is, uint64_t* out, long long os,
                        const uint64_t* switch_key, int batch, void* stream)
 {

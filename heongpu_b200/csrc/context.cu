@@ -255,6 +255,27 @@ void build_bfv_tables(Context& c)
 void upload_bfv_tables(Context& c)
 {
     BfvTables& t = c.bfv;
+    {
+        // plaintext-operand constants; floor(Q/t) mod q_i = -(Q mod t) * t^-1 mod q_i because
+        // Q - (Q mod t) is divisible by t and Q = 0 (mod q_i)  (reference: GMP, bfv/context.cu:953-984)
+        const u64 tt = c.plain_modulus;
+        u64 r = 1;
+        for (int i = 0; i < c.Q_size; ++i)
+            r = mulmod(r, c.mod[i].value % tt, tt);
+        t.Q_mod_t = r;
+        t.upper_threshold = (tt + 1) >> 1;
+        t.coeff_div_plainmod.clear();
+        t.upper_halfincrement.clear();
+        for (int i = 0; i < c.Q_size; ++i)
+        {
+            const u64 q = c.mod[i].value;
+            const u64 rq = r % q;
+            t.coeff_div_plainmod.push_back(rq == 0 ? 0 : mulmod(q - rq, invmod(tt % q, q), q));
+            t.upper_halfincrement.push_back(q - tt);
+        }
+        t.d_coeff_div_plainmod = upload(t.coeff_div_plainmod);
+        t.d_upper_halfincrement = upload(t.upper_halfincrement);
+    }
     t.d_base_change_matrix_Bsk = upload(t.base_change_matrix_Bsk);
     t.d_inv_punctured_prod_mod_base_array = upload(t.inv_punctured_prod_mod_base_array);
     t.d_base_change_matrix_m_tilde = upload(t.base_change_matrix_m_tilde);
@@ -529,6 +550,8 @@ Context::~Context()
     cudaFree(bfv.d_base_change_matrix_msk);
     cudaFree(bfv.d_inv_punctured_prod_mod_B_array);
     cudaFree(bfv.d_prod_B_mod_q);
+    cudaFree(bfv.d_coeff_div_plainmod);
+    cudaFree(bfv.d_upper_halfincrement);
     for (auto& t : lvl2)
     {
         cudaFree(t.d_base_change);

@@ -62,6 +62,10 @@ struct BfvTables {
         inv_m_tilde_mod_Bsk, prod_q_mod_Bsk, inv_prod_q_mod_Bsk, base_change_matrix_q, base_change_matrix_msk,
         inv_punctured_prod_mod_B_array, prod_B_mod_q;
     u64 inv_prod_q_mod_m_tilde = 0, inv_prod_B_mod_m_sk = 0;
+    // plaintext operands (bfv/context.cu:501-516, 936-984): Q mod t, floor(Q/t) mod q_i, (t+1)>>1, q_i - t
+    u64 Q_mod_t = 0, upper_threshold = 0;
+    std::vector<u64> coeff_div_plainmod, upper_halfincrement;
+    u64 *d_coeff_div_plainmod = nullptr, *d_upper_halfincrement = nullptr;
     u64 *d_base_change_matrix_Bsk = nullptr, *d_inv_punctured_prod_mod_base_array = nullptr,
         *d_base_change_matrix_m_tilde = nullptr, *d_inv_m_tilde_mod_Bsk = nullptr, *d_prod_q_mod_Bsk = nullptr,
         *d_inv_prod_q_mod_Bsk = nullptr, *d_base_change_matrix_q = nullptr, *d_base_change_matrix_msk = nullptr,

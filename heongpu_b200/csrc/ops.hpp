@@ -53,6 +53,10 @@ void op_mod_drop(const Context& c, const u64* in, long long in_bs, u64* out, lon
                  int depth, int batch, cudaStream_t st);
 void op_bfv_multiply(const Context& c, const u64* a, long long a_bs, const u64* b, long long b_bs, u64* out,
                      long long o_bs, int batch, cudaStream_t st);
+void op_bfv_addsub_plain(const Context& c, const u64* ct, long long ct_bs, const u64* pt, long long pt_bs, u64* out,
+                         long long o_bs, int comps, int batch, int op, cudaStream_t st);
+void op_bfv_multiply_plain(const Context& c, const u64* ct, long long ct_bs, const u64* pt, long long pt_bs, u64* out,
+                           long long o_bs, int batch, cudaStream_t st);
 void op_bfv_relinearize(const Context& c, u64* ct, long long ct_bs, const u64* relin_key, int batch,
                         cudaStream_t st);
 void op_apply_galois(const Context& c, const u64* in, long long in_bs, u64* out, long long out_bs,

@@ -804,6 +804,26 @@ template <> class Ciphertext<Scheme::BFV> {
     bool in_ntt_domain_ = false, relinearization_required_ = false, ciphertext_generated_ = false;
 };
 
+// Plaintext<BFV>: [N] values below the plain modulus (bfv/plaintext.cu); batching encode is a client-side row.
+template <> class Plaintext<Scheme::BFV> {
+  public:
+    Plaintext() = default;
+    Plaintext(HEContext<Scheme::BFV> ctx, const std::vector<Data64>& words, const ExecutionOptions& opt = ExecutionOptions())
+        : context_(ctx), device_locations_(words, opt.stream_)
+    {
+        if (words.size() < (size_t) ctx->n)
+            throw std::invalid_argument("Invalid Plaintext size!");
+        plain_size_ = (int) words.size();
+        plaintext_generated_ = true;
+    }
+    Data64* data() const { return device_locations_.data(); }
+    size_t size() const { return device_locations_.size(); }
+    HEContext<Scheme::BFV> context_;
+    DeviceVector<Data64> device_locations_;
+    int plain_size_ = 0;
+    bool in_ntt_domain_ = false, plaintext_generated_ = false;
+};
+
 template <> class Relinkey<Scheme::BFV> {
   public:
     explicit Relinkey(HEContext<Scheme::BFV> ctx) : context_(ctx), key_type(ctx->keyswitching_type_) {}
@@ -980,6 +1000,32 @@ template <> class HEOperator<Scheme::BFV> {
     {
         rotate_rows(ct, ct, gk, shift, opt);
     }
+    // add_plain_bfv / sub_plain_bfv / multiply_plain_bfv (bfv/operator.cu:216-340, 432-503)
+    void add_plain(Ciphertext<Scheme::BFV>& a, Plaintext<Scheme::BFV>& p, Ciphertext<Scheme::BFV>& out,
+                   const ExecutionOptions& opt = ExecutionOptions())
+    {
+        plain(a, p, out, opt, 1);
+    }
+    void add_plain_inplace(Ciphertext<Scheme::BFV>& a, Plaintext<Scheme::BFV>& p, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        plain(a, p, a, opt, 1);
+    }
+    void sub_plain(Ciphertext<Scheme::BFV>& a, Plaintext<Scheme::BFV>& p, Ciphertext<Scheme::BFV>& out,
+                   const ExecutionOptions& opt = ExecutionOptions())
+    {
+        plain(a, p, out, opt, 2);
+    }
+    void sub_plain_inplace(Ciphertext<Scheme::BFV>& a, Plaintext<Scheme::BFV>& p, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        plain(a, p, a, opt, 2);
+    }
+    void multiply_plain(Ciphertext<Scheme::BFV>& a, Plaintext<Scheme::BFV>& p, Ciphertext<Scheme::BFV>& out,
+                        const ExecutionOptions& opt = ExecutionOptions())
+    {
+        if (a.relinearization_required_)
+            throw std::invalid_argument("Ciphertexts can not be multiplied because of the non-linear part! Please use relinearization operation!");
+        plain(a, p, out, opt, 0);
+    }
     // switchkey_method_I/II (bfv/operator.cu:975-1372)
     void keyswitch(Ciphertext<Scheme::BFV>& in, Ciphertext<Scheme::BFV>& out, Switchkey<Scheme::BFV>& sk,
                    const ExecutionOptions& opt = ExecutionOptions())
@@ -1001,6 +1047,24 @@ template <> class HEOperator<Scheme::BFV> {
     }
 
   private:
+    void plain(Ciphertext<Scheme::BFV>& a, Plaintext<Scheme::BFV>& p, Ciphertext<Scheme::BFV>& out,
+               const ExecutionOptions& opt, int op)
+    {
+        const int comps = op == 0 ? 2 : (a.relinearization_required_ ? 3 : 2);
+        if (a.memory_size() < words(comps))
+            throw std::invalid_argument("Invalid Ciphertexts size!");
+        if (p.size() < (size_t) context_->n)
+            throw std::invalid_argument("Invalid Plaintext size!");
+        DeviceVector<Data64> mem(words(comps), opt.stream_);
+        if (op == 0)
+            detail::check(heon_bfv_multiply_plain(h(), a.data(), 0, p.data(), 0, mem.data(), 0, 1, opt.stream_));
+        else
+            detail::check((op == 1 ? heon_bfv_add_plain : heon_bfv_sub_plain)(h(), a.data(), 0, p.data(), 0, mem.data(), 0,
+                                                                             comps, 1, opt.stream_));
+        copy_meta(a, out);
+        out.memory_set(std::move(mem));
+        out.cipher_size_ = comps;
+    }
     void binary(Ciphertext<Scheme::BFV>& a, Ciphertext<Scheme::BFV>& b, Ciphertext<Scheme::BFV>& out,
                 const ExecutionOptions& opt, int op)
     {

@@ -231,6 +231,19 @@ int heon_bfv_apply_galois(heon_context_t ctx, const uint64_t* in, long long in_s
                           long long out_stride, const uint64_t* galois_key, uint32_t galois_elt, int batch,
                           void* stream);
 
+/* ---- add_plain_bfv / sub_plain_bfv (bfv/operator.cu:216-340; kernels addition.cu:50-173) and
+ *      multiply_plain_bfv (bfv/operator.cu:432-503; threshold_kernel + cipherplain_kernel).
+ * ct, out: [components][Q][N] coefficient domain; pt: [N] values below the plain modulus
+ * (pt_stride 0 shares one plaintext across the batch).  multiply: 2 components, out != ct. */
+int heon_bfv_add_plain(heon_context_t ctx, const uint64_t* ct, long long ct_stride, const uint64_t* pt,
+                       long long pt_stride, uint64_t* out, long long out_stride, int components, int batch,
+                       void* stream);
+int heon_bfv_sub_plain(heon_context_t ctx, const uint64_t* ct, long long ct_stride, const uint64_t* pt,
+                       long long pt_stride, uint64_t* out, long long out_stride, int components, int batch,
+                       void* stream);
+int heon_bfv_multiply_plain(heon_context_t ctx, const uint64_t* ct, long long ct_stride, const uint64_t* pt,
+                            long long pt_stride, uint64_t* out, long long out_stride, int batch, void* stream);
+
 /* ---- HEOperator<BFV>::switchkey_method_I / _II (bfv/operator.cu:975-1372, HEOperator::keyswitch):
  *      out = (c0, 0) + KeySwitch(c1) under `switch_key`; in, out: [2][Q][N] coefficient domain. */
 int heon_bfv_keyswitch(heon_context_t ctx, const uint64_t* in, long long in_stride, uint64_t* out,

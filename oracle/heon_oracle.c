@@ -1377,3 +1377,70 @@ void oracle_bfv_apply_galois(const obfv* c, const u64* in, u64* out, const u64* 
     o_moddown_ext(k, acc, out, in, galois_elt, 0);
     free(acc);
 }
+
+/* ---- BFV plaintext operands -------------------------------------------------------------
+ * add_plain_bfv / sub_plain_bfv (bfv/operator.cu:216-340; kernels addition.cu:50-173) and
+ * multiply_plain_bfv (bfv/operator.cu:432-503; threshold_kernel + cipherplain_kernel,
+ * multiplication.cu:274-311).  Constants as in bfv/context.cu:501-516, 936-984:
+ *   Q_mod_t = prod q_i mod t;  coeff_div[i] = floor(Q/t) mod q_i = -(Q mod t) * t^-1 mod q_i
+ *   (Q - (Q mod t) is divisible by t and Q = 0 mod q_i);  upper_threshold = (t+1)>>1;
+ *   upper_half_increment[i] = q_i - t.
+ * ct, out: [comps][Q][N] coefficient domain; pt: [N] values below t.  op 0 multiply (comps = 2),
+ * 1 add, 2 subtract. */
+void oracle_bfv_plain(const obfv* c, const u64* ct, const u64* pt, u64* out, int comps, int op)
+{
+    int Q = c->Q, n = c->n;
+    u64 t = c->t;
+    omod tm;
+    oracle_make_mod(t, &tm);
+    u64 Q_mod_t = 1;
+    for (int i = 0; i < Q; i++)
+        Q_mod_t = (u64) (((u128) Q_mod_t * (c->q[i].value % t)) % t);
+    u64 upper_threshold = (t + 1) >> 1;
+    if (op != 0) {
+        for (int z = 0; z < comps; z++)
+            for (int y = 0; y < Q; y++) {
+                const omod* m = &c->q[y];
+                u64 tinv = o_modinv(t % m->value, m);
+                u64 coeff_div = o_mult(m->value - (Q_mod_t % m->value), tinv, m);
+                if (Q_mod_t % m->value == 0)
+                    coeff_div = 0;
+                for (int idx = 0; idx < n; idx++) {
+                    size_t o = ((size_t) z * Q + y) * n + idx;
+                    if (z != 0) {
+                        out[o] = ct[o];
+                        continue;
+                    }
+                    u64 message = pt[idx];
+                    u64 fix = message * Q_mod_t;
+                    fix = fix + upper_threshold;
+                    fix = (u64) (long long) (int) (fix / t); /* `int(fix / plain_mod.value)` in the kernel */
+                    u64 r = o_mult(message, coeff_div, m);
+                    r = o_add(r, fix, m);
+                    out[o] = op == 1 ? o_add(r, ct[o], m) : o_sub(ct[o], r, m);
+                }
+            }
+        return;
+    }
+    /* multiply: lift the plaintext (threshold_kernel), NTT both, multiply, INTT */
+    u64* tp = (u64*) malloc(sizeof(u64) * (size_t) Q * n);
+    for (int y = 0; y < Q; y++) {
+        const omod* m = &c->q[y];
+        for (int idx = 0; idx < n; idx++) {
+            u64 v = pt[idx];
+            tp[(size_t) y * n + idx] = v >= upper_threshold ? o_add(v, m->value - t, m) : v;
+        }
+        oracle_ntt(tp + (size_t) y * n, c->fwd + ((size_t) y << c->n_power), m->value, c->n_power);
+    }
+    memcpy(out, ct, sizeof(u64) * (size_t) 2 * Q * n);
+    for (int z = 0; z < 2; z++)
+        for (int y = 0; y < Q; y++) {
+            const omod* m = &c->q[y];
+            u64* po = out + ((size_t) z * Q + y) * n;
+            oracle_ntt(po, c->fwd + ((size_t) y << c->n_power), m->value, c->n_power);
+            for (int idx = 0; idx < n; idx++)
+                po[idx] = o_mult(po[idx], tp[(size_t) y * n + idx], m);
+            oracle_intt(po, c->inv + ((size_t) y << c->n_power), m->value, c->n_power); /* incl. n^-1 */
+        }
+    free(tp);
+}

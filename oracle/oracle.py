@@ -252,6 +252,14 @@ class BfvOracle:
         lib().oracle_bfv_relinearize(self._h, _p(ct), _p(np.ascontiguousarray(key)))
         return ct
 
+    def plain(self, ct, pt, op):
+        """op 0 multiply_plain_bfv, 1 add_plain_bfv, 2 sub_plain_bfv; ct [comps][Q][N] (coefficient domain), pt [N] < t."""
+        ct = np.ascontiguousarray(ct, dtype=np.uint64)
+        pt = np.ascontiguousarray(pt, dtype=np.uint64)
+        out = np.zeros_like(ct)
+        lib().oracle_bfv_plain(self._h, _p(ct), _p(pt), _p(out), ct.shape[0], op)
+        return out
+
     def apply_galois(self, ct2, key, galois_elt):
         ct = np.ascontiguousarray(ct2, dtype=np.uint64)
         out = np.zeros_like(ct)

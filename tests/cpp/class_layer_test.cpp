@@ -178,6 +178,30 @@ int main(int argc, char** argv)
         std::vector<Data64> r2(r1.size());
         cudaMemcpy(r2.data(), dr.data(), r2.size() * sizeof(Data64), cudaMemcpyDeviceToHost);
         if (r1 != r2 || s1 != r1) { std::puts("FAIL: BFV rotate / add / sub"); return 1; }
+        // plaintext operands and keyswitch
+        std::vector<Data64> pw(n);
+        for (int i = 0; i < n; ++i) pw[i] = (Data64) ((i * 7919u + 13u) % 1032193u);
+        Plaintext<B> P1(context, pw);
+        Ciphertext<B> Ap, Mp, Kp;
+        operators.add_plain(C1, P1, Ap);
+        operators.sub_plain_inplace(Ap, P1); // (C1 + P) - P == C1
+        operators.multiply_plain(C1, P1, Mp);
+        std::vector<Data64> a1, m1;
+        Ap.get_data(a1);
+        Mp.get_data(m1);
+        DeviceVector<Data64> dp(pw), dm((size_t) 2 * Q * n);
+        heon_bfv_multiply_plain(context->handle(), da.data(), 0, dp.data(), 0, dm.data(), 0, 1, nullptr);
+        std::vector<Data64> m2(m1.size());
+        cudaMemcpy(m2.data(), dm.data(), m2.size() * sizeof(Data64), cudaMemcpyDeviceToHost);
+        if (a1 != a || m1 != m2) { std::puts("FAIL: BFV plaintext operators"); return 1; }
+        Switchkey<B> swk(context);
+        swk.set_data(words(context->prime_vector_, context->digit_count() * 2, Qp, n, 16));
+        operators.keyswitch(C1, Kp, swk);
+        std::vector<Data64> k1, k2(2 * (size_t) Q * n);
+        Kp.get_data(k1);
+        heon_bfv_keyswitch(context->handle(), da.data(), 0, dr.data(), 0, swk.data(), 1, nullptr);
+        cudaMemcpy(k2.data(), dr.data(), k2.size() * sizeof(Data64), cudaMemcpyDeviceToHost);
+        if (k1 != k2) { std::puts("FAIL: BFV keyswitch"); return 1; }
     }
     std::puts("OK");
     return 0;

@@ -226,3 +226,50 @@ def test_bfv_keyswitch_decrypts_gpu(name):
         assert np.array_equal(got, sc.ob.apply_galois(ct, key, 1)), "BFV keyswitch differs from the oracle"
         return got
     _run_keyswitch(name, backend)
+
+
+# ---- BFV plaintext operands (add_plain_bfv / sub_plain_bfv / multiply_plain_bfv) ----
+def _run_plain(name, backend):
+    sc = Bfv(name)
+    n, t = sc.n, sc.t
+    m1 = (splitmix64(21, n) % np.uint64(t)).astype(np.int64)
+    m2 = (splitmix64(22, n) % np.uint64(t)).astype(np.int64)
+    ct = sc.encrypt(m1, 7000)
+    pt = m2.astype(np.uint64)
+    add, sub, mul = backend(sc, ct, pt)
+    count = 24
+    assert sc.decrypt(add, count) == [int((a + b) % t) for a, b in zip(m1[:count], m2[:count])], "add_plain"
+    assert sc.decrypt(sub, count) == [int((a - b) % t) for a, b in zip(m1[:count], m2[:count])], "sub_plain"
+    assert sc.decrypt(mul, count) == _negacyclic_mod_t(m1, m2, n, t, count), "multiply_plain"
+
+
+@pytest.mark.parametrize("name", ["bfv_n12_I", "bfv_n12_II"])
+def test_bfv_plain_ops_decrypt_oracle(name):
+    _run_plain(name, lambda sc, ct, pt: (sc.ob.plain(ct, pt, 1), sc.ob.plain(ct, pt, 2), sc.ob.plain(ct, pt, 0)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["bfv_n12_I", "bfv_n12_II", "bfv_n13_I"])
+def test_bfv_plain_ops_gpu(name):
+    def backend(sc, ct, pt):
+        import torch
+        from heongpu_b200 import api
+        from tests.gpu_common import to_dev, to_host
+        ctx = bfv_gpu_ctx(name)
+        op = api.HEArithmeticOperator(ctx)
+        batch = 2
+        cts = np.stack([ct, ct])
+        A = api.Ciphertext(ctx, to_dev(cts))
+        P = api.Plaintext(ctx, to_dev(pt))
+        res = []
+        for fn, code in ((op.add_plain_bfv, 1), (op.sub_plain_bfv, 2), (op.multiply_plain_bfv, 0)):
+            out = api.Ciphertext(ctx, torch.zeros(batch, 2, sc.Q, sc.n, dtype=torch.int64, device="cuda"))
+            fn(A, P, out)
+            got = to_host(out.data).copy()
+            want = sc.ob.plain(ct, pt, code)
+            for bi in range(batch):
+                assert np.array_equal(got[bi], want), f"BFV plain op {code} differs from the oracle"
+            res.append(got[0])
+        assert np.array_equal(to_host(A.data), cts), "input must stay untouched"
+        return res
+    _run_plain(name, backend)
