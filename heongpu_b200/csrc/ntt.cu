@@ -512,8 +512,9 @@ __device__ __forceinline__ void row_pass_tma_body(unsigned char* rowp, const Pri
 // TMA load of tile i+1 and the TMA store of tile i-1 overlap the arithmetic of
 // tile i (the pass is otherwise a load -> compute -> store chain whose memory
 // time and multiplier-pipe time add up instead of overlapping).
-template <bool INV, class Map>
-__global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS)
+// ROWS rows per CTA (16 threads each): 16 -> 32 KiB tiles, 3 CTAs/SM; 8 -> 16 KiB tiles, 6 CTAs/SM.
+template <bool INV, class Map, int ROWS>
+__global__ void __launch_bounds__(ROWS * 16, HEON_NTT_MINBLOCKS * 16 / ROWS)
     ntt_row_pass_tma(Map map, const __grid_constant__ CUtensorMap tm_in,
                      const __grid_constant__ CUtensorMap tm_out, const u64* in_base, const u64* out_base,
                      const TwPair* __restrict__ tw_all, const TwPair* __restrict__ rowb_all,
@@ -526,7 +527,8 @@ __global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS)
     // pointer in the shared address space (LDS/STS instead of generic LD/ST)
     unsigned char* buf0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int S1 = logn - 8;
-    const int tiles = (1 << S1) / 16;
+    const int tiles = (1 << S1) / ROWS;
+    constexpr int kTileBytes = ROWS * 2048;
     const CUtensorMap* tmi = first_pass ? &tm_in : &tm_out;
     if (!first_pass)
         in_base = out_base;
@@ -542,8 +544,8 @@ __global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS)
         map.get(z, in, out, prime, aux);
         if (!first_pass)
             in = out;
-        line_in = (int) ((in - in_base) >> 4) + tile_idx * 256;
-        line_out = (int) ((out - out_base) >> 4) + tile_idx * 256;
+        line_in = (int) ((in - in_base) >> 4) + tile_idx * (ROWS * 16);
+        line_out = (int) ((out - out_base) >> 4) + tile_idx * (ROWS * 16);
     };
 
     if (threadIdx.x == 0)
@@ -561,16 +563,16 @@ __global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS)
         int li, lo, pr, ti;
         tile_lines(t, li, lo, pr, ti);
         const bool twsm = !INV && rowc_all && pcs[pr].fp_var != 0;
-        mbar_arrive_expect_tx(&bar[0], twsm ? 2 * kRowTileBytes : kRowTileBytes);
+        mbar_arrive_expect_tx(&bar[0], twsm ? 2 * kTileBytes : kTileBytes);
         tma_load_2d(buf0, tmi, &bar[0], 0, li);
         if (twsm)
-            tma_load_1d(buf0 + kRowTileBytes, rowc_all + ((((long long) pr << S1) + ti * 16) << 8), kRowTileBytes,
+            tma_load_1d(buf0 + kTileBytes, rowc_all + ((((long long) pr << S1) + ti * ROWS) << 8), kTileBytes,
                         &bar[0]);
     }
     for (int it = 0; t < n_tiles; ++it, t += gridDim.x)
     {
         const int b = it & 1;
-        unsigned char* tile = buf0 + b * kRowTileBytes;
+        unsigned char* tile = buf0 + b * kTileBytes;
         if (threadIdx.x == 0)
         {
             // the other buffer was handed to a TMA store one iteration ago: wait until that
@@ -581,19 +583,19 @@ __global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS)
             {
                 int li, lo, pr, ti;
                 tile_lines(tn, li, lo, pr, ti);
-                mbar_arrive_expect_tx(&bar[b ^ 1], kRowTileBytes);
-                tma_load_2d(buf0 + (b ^ 1) * kRowTileBytes, tmi, &bar[b ^ 1], 0, li);
+                mbar_arrive_expect_tx(&bar[b ^ 1], kTileBytes);
+                tma_load_2d(buf0 + (b ^ 1) * kTileBytes, tmi, &bar[b ^ 1], 0, li);
             }
         }
         int line_in, line_out, prime, tile_idx;
         tile_lines(t, line_in, line_out, prime, tile_idx);
         const PrimeConst pc = pcs[prime];
         const TwPair* tw = tw_all + ((long long) prime << logn);
-        const int r = tile_idx * 16 + rl;
+        const int r = tile_idx * ROWS + rl;
         const TwPair* blk = rowb_all + ((((long long) prime << S1) + r) << 8);
         unsigned char* rowp = tile + rl * 2048;
         const double* rowtw =
-            rowc_all ? reinterpret_cast<const double*>(buf0 + kRowTileBytes) + rl * 256 : nullptr;
+            rowc_all ? reinterpret_cast<const double*>(buf0 + kTileBytes) + rl * 256 : nullptr;
         mbar_wait(&bar[b], (it >> 1) & 1);
 
         if (!INV && pc.fp_var == 3)
@@ -1132,12 +1134,12 @@ static EncodeTiledFn encode_tiled()
 }
 
 // Buffer viewed as `lines` rows of sixteen 64-bit words (128 B); box = 256 lines (one 16-row tile).
-static CUtensorMap make_line_map(const u64* base, long long words)
+static CUtensorMap make_line_map(const u64* base, long long words, int box_lines = 256)
 {
     CUtensorMap m;
     const cuuint64_t dims[2] = {16, (cuuint64_t) (words >> 4)};
     const cuuint64_t strides[1] = {128};
-    const cuuint32_t box[2] = {16, 256};
+    const cuuint32_t box[2] = {16, (cuuint32_t) box_lines};
     const cuuint32_t estr[2] = {1, 1};
     CUresult rc = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*) base, dims, strides, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1159,27 +1161,37 @@ struct Extent {
     long long col_in_words = 0;
 };
 
-template <bool INV, class Map>
-static void launch_row_tma(const Context& c, const Map& m, long long n_polys, bool first, const Extent& e,
-                           cudaStream_t st)
+template <bool INV, class Map, int ROWS>
+static void launch_row_tma_rows(const Context& c, const Map& m, long long n_polys, bool first, const Extent& e,
+                                cudaStream_t st)
 {
     const int S = c.logn - 8;
-    const long long n_tiles = n_polys * ((1 << S) / 16);
+    const long long n_tiles = n_polys * ((1 << S) / ROWS);
     // persistent (a few CTAs per SM walking tiles) or one tile per CTA
     const unsigned grid = c.ntt_persistent
                               ? (unsigned) std::min<long long>(n_tiles, (long long) c.num_sms * HEON_NTT_MINBLOCKS)
                               : (unsigned) n_tiles;
-    const CUtensorMap tm_out = make_line_map(e.out_base, e.out_words);
-    const CUtensorMap tm_in = first ? make_line_map(e.in_base, e.in_words) : tm_out;
-    static bool attr_set[2] = {false, false};
-    auto kfn = ntt_row_pass_tma<INV, Map>;
-    const int smem = 2 * kRowTileBytes + 1024;
+    const CUtensorMap tm_out = make_line_map(e.out_base, e.out_words, ROWS * 16);
+    const CUtensorMap tm_in = first ? make_line_map(e.in_base, e.in_words, ROWS * 16) : tm_out;
+    auto kfn = ntt_row_pass_tma<INV, Map, ROWS>;
+    const int smem = 2 * ROWS * 2048 + 1024;
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    (void) attr_set;
     LaunchScope scope(INV ? KC_NTT_INV_ROW : KC_NTT_FWD_ROW, st);
-    kfn<<<grid, 256, smem, st>>>(m, tm_in, tm_out, e.in_base, e.out_base, INV ? c.d_inv : c.d_fwd,
-                                 INV ? c.d_inv_rowb : c.d_fwd_rowb, c.d_pc, c.logn, first, c.ntt_variant,
-                                 n_tiles, (!INV && !c.ntt_persistent && c.use_fp64) ? c.d_fwd_rowc : nullptr);
+    kfn<<<grid, ROWS * 16, smem, st>>>(m, tm_in, tm_out, e.in_base, e.out_base, INV ? c.d_inv : c.d_fwd,
+                                       INV ? c.d_inv_rowb : c.d_fwd_rowb, c.d_pc, c.logn, first, c.ntt_variant,
+                                       n_tiles, (!INV && !c.ntt_persistent && c.use_fp64) ? c.d_fwd_rowc : nullptr);
+}
+
+template <bool INV, class Map>
+static void launch_row_tma(const Context& c, const Map& m, long long n_polys, bool first, const Extent& e,
+                           cudaStream_t st)
+{
+    if (c.row_tile == 4 && !c.ntt_persistent)
+        launch_row_tma_rows<INV, Map, 4>(c, m, n_polys, first, e, st);
+    else if (c.row_tile == 8 && !c.ntt_persistent)
+        launch_row_tma_rows<INV, Map, 8>(c, m, n_polys, first, e, st);
+    else
+        launch_row_tma_rows<INV, Map, 16>(c, m, n_polys, first, e, st);
 }
 
 
