@@ -133,6 +133,8 @@ static void finish_context(Context& c, int device, int log_n, int n_q, int n_p, 
         c.ntt_persistent = atoi(v);
     if (const char* v = getenv("HEON_NTT_FP64"))
         c.use_fp64 = atoi(v);
+    if (const char* v = getenv("HEON_COL_THREADS"))
+        c.col_threads = atoi(v);
     if (const char* v = getenv("HEON_ROW_TILE"))
         c.row_tile = atoi(v);
     if (const char* v = getenv("HEON_SKIP_OWN"))

@@ -111,6 +111,7 @@ struct Context {
     int ntt_persistent = 0; // HEON_NTT_PERSISTENT=1: row-pass CTAs walk several tiles (double-buffered TMA)
     int ntt_pipe = 0; // N = 2^16: warp-specialised pipelined fused forward transform (HEON_NTT_PIPE=1 enables; needs all CTAs co-resident, i.e. an otherwise idle GPU)
     int ntt_group = 48; // polynomials per L2-resident group of the fused transform (HEON_NTT_GROUP)
+    int col_threads = 0; // threads per CTA of the column pass at N = 2^16: 256, 128, or 0 = per map (HEON_COL_THREADS)
     int row_tile = 8; // rows per CTA of the TMA row pass: 16 (32 KiB tiles, 3 CTAs/SM), 8 (6 CTAs/SM, default: +3..7 % measured) or 4 (HEON_ROW_TILE)
     int skip_own = 1; // Method II: the digits' own limbs skip mod-up and forward NTT (HEON_SKIP_OWN=0 disables)
     int galois_ntt = 1; // CKKS automorphisms as NTT-domain permutations after an NTT-domain key switch (HEON_GALOIS_NTT=0: coefficient-domain path)
