@@ -343,12 +343,27 @@ void upload_tables(Context& c)
             else
                 fwd[o].ws = shoup(c.ntt_table[o], p);
             inv[o].w = c.intt_table[o];
-            inv[o].ws = shoup(c.intt_table[o], p);
+            if (pcs[i].fp_var)
+            {
+                const double wd = (double) c.intt_table[o];
+                const double winv = wd / (double) p;
+                std::memcpy(&inv[o].w, &wd, 8);
+                std::memcpy(&inv[o].ws, &winv, 8);
+            }
+            else
+                inv[o].ws = shoup(c.intt_table[o], p);
         }
         const u64 ninv = c.n_inverse[i];
         const u64 wn = mulmod(c.intt_table[(size_t) i * N + 1], ninv, p);
         last[2 * i] = TwPair{ninv, shoup(ninv, p)};
         last[2 * i + 1] = TwPair{wn, shoup(wn, p)};
+        if (pcs[i].fp_var)
+            for (int e = 0; e < 2; ++e)
+            {
+                const double wd = (double) last[2 * i + e].w, winv = wd / (double) p;
+                std::memcpy(&last[2 * i + e].w, &wd, 8);
+                std::memcpy(&last[2 * i + e].ws, &winv, 8);
+            }
     }
     {
         const int S1 = c.logn - 8, R = 1 << S1;

@@ -308,10 +308,10 @@ __global__ void __launch_bounds__(NT, HEON_COL_MINBLOCKS * 256 / NT) ntt_col_pas
         in = out;
     const PrimeConst pc = pcs[prime];
     const TwPair* tw = tw_all + ((long long) prime << logn);
-    if (!INV && pc.fp_var == 3)
-        col_pass_body<S, INV, INV ? 1 : 3, Map, NT>(map, in, out, prime, pc, tw, inv_last, tile, first_pass, aux, sm);
-    else if (!INV && pc.fp_var == 4)
-        col_pass_body<S, INV, INV ? 1 : 4, Map, NT>(map, in, out, prime, pc, tw, inv_last, tile, first_pass, aux, sm);
+    if (pc.fp_var == 3)
+        col_pass_body<S, INV, 3, Map, NT>(map, in, out, prime, pc, tw, inv_last, tile, first_pass, aux, sm);
+    else if (pc.fp_var == 4)
+        col_pass_body<S, INV, 4, Map, NT>(map, in, out, prime, pc, tw, inv_last, tile, first_pass, aux, sm);
     else if (INV || variant == 1 || !pc.nc_ok)
         col_pass_body<S, INV, 1, Map, NT>(map, in, out, prime, pc, tw, inv_last, tile, first_pass, aux, sm);
     else
@@ -360,8 +360,8 @@ __device__ __forceinline__ void row_pass_body(const u64* rin, u64* rout, const P
         for (int k = 0; k < 16; k += 2)
         {
             ulonglong2 t2 = *reinterpret_cast<const ulonglong2*>(rin + 16 * tt + k);
-            v[k] = t2.x;
-            v[k + 1] = t2.y;
+            v[k] = gs_prep<VAR>(t2.x);
+            v[k + 1] = gs_prep<VAR>(t2.y);
         }
         gs_round_b<8, VAR>(v, tw, S1, r, tt, bc);
 #pragma unroll
@@ -408,10 +408,10 @@ __global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS) ntt_row_pass(Map map,
     const u64* rin = in + (long long) r * 256;
     u64* rout = out + (long long) r * 256;
     u64* srow = sm + rl * PITCH;
-    if (!INV && pc.fp_var == 3)
-        row_pass_body<INV, INV ? 1 : 3>(rin, rout, pc, tw, S1, r, tt, srow);
-    else if (!INV && pc.fp_var == 4)
-        row_pass_body<INV, INV ? 1 : 4>(rin, rout, pc, tw, S1, r, tt, srow);
+    if (pc.fp_var == 3)
+        row_pass_body<INV, 3>(rin, rout, pc, tw, S1, r, tt, srow);
+    else if (pc.fp_var == 4)
+        row_pass_body<INV, 4>(rin, rout, pc, tw, S1, r, tt, srow);
     else if (INV || variant == 1 || !pc.nc_ok)
         row_pass_body<INV, 1>(rin, rout, pc, tw, S1, r, tt, srow);
     else
@@ -485,8 +485,8 @@ __device__ __forceinline__ void row_pass_tma_body(unsigned char* rowp, const Pri
         for (int c = 0; c < 8; ++c)
         {
             const ulonglong2 t2 = *reinterpret_cast<const ulonglong2*>(lineB + ((c ^ sw) << 4));
-            v[2 * c] = t2.x;
-            v[2 * c + 1] = t2.y;
+            v[2 * c] = gs_prep<VAR>(t2.x);
+            v[2 * c + 1] = gs_prep<VAR>(t2.y);
         }
         gs_round_b_lm<VAR>(v, blk, tt, bc);
 #pragma unroll
@@ -599,10 +599,10 @@ __global__ void __launch_bounds__(ROWS * 16, HEON_NTT_MINBLOCKS * 16 / ROWS)
             rowc_all ? reinterpret_cast<const double*>(buf0 + kTileBytes) + rl * 256 : nullptr;
         mbar_wait(&bar[b], (it >> 1) & 1);
 
-        if (!INV && pc.fp_var == 3)
-            row_pass_tma_body<INV, INV ? 1 : 3>(rowp, pc, tw, blk, S1, r, tt, rowtw);
-        else if (!INV && pc.fp_var == 4)
-            row_pass_tma_body<INV, INV ? 1 : 4>(rowp, pc, tw, blk, S1, r, tt, rowtw);
+        if (pc.fp_var == 3)
+            row_pass_tma_body<INV, 3>(rowp, pc, tw, blk, S1, r, tt, rowtw);
+        else if (pc.fp_var == 4)
+            row_pass_tma_body<INV, 4>(rowp, pc, tw, blk, S1, r, tt, rowtw);
         else if (INV || variant == 1 || !pc.nc_ok)
             row_pass_tma_body<INV, 1>(rowp, pc, tw, blk, S1, r, tt, nullptr);
         else

@@ -255,6 +255,12 @@ __device__ __forceinline__ void ct_bfly(u64& X, u64& Y, const TwPair& w, const B
     }
 }
 
+// canonical word loaded by the first pass of the inverse transform -> working representation
+template <int GVAR> __device__ __forceinline__ u64 gs_prep(u64 x)
+{
+    return GVAR >= 3 ? d2u(fp_from_u64(x)) : x;
+}
+
 // canonical value of a lazy forward word
 template <int VAR> __device__ __forceinline__ u64 ct_finish(u64 x, const BflyConst& c, const PrimeConst& pc)
 {
@@ -272,9 +278,24 @@ template <int VAR> __device__ __forceinline__ u64 ct_finish(u64 x, const BflyCon
 
 // Gentleman-Sande lazy butterfly.  GVAR 0: values in [0,2p), exact quotient.
 // GVAR 1: values in [0,4p), approximate quotient.
-template <int GVAR> __device__ __forceinline__ void gs_bfly(u64& X, u64& Y, const TwPair& w, const BflyConst& c)
+// GVAR 3 / 4: the FP64 pipe (words are integer-valued doubles, twiddle pairs {w, RN(w/p)}):
+//   S = X + Y (reduced when RED), D = X - Y, Y' = D*w mod p by fp_mulmod.  The sum branch doubles
+//   per stage, so it is reduced on every stage for p < 2^50 (GVAR 4: all words stay below 0.58p,
+//   |D| < 1.2p < 2^51) and on every other stage for p < 2^47 (GVAR 3).
+template <int GVAR, bool RED = true>
+__device__ __forceinline__ void gs_bfly(u64& X, u64& Y, const TwPair& w, const BflyConst& c)
 {
-    if (GVAR == 0)
+    if (GVAR >= 3)
+    {
+        const double x = u2d(X), y = u2d(Y);
+        double s = __dadd_rn(x, y);
+        const double d = __dsub_rn(x, y);
+        if (GVAR == 4 || RED)
+            s = fp_reduce(s, c.dpinv, c.dnp);
+        X = d2u(s);
+        Y = d2u(fp_mulmod(d, u2d(w.w), u2d(w.ws), c.dnp));
+    }
+    else if (GVAR == 0)
     {
         const u64 s = csub(X + Y, c.p2);
         const u64 d = X - Y + c.p2;
@@ -310,7 +331,7 @@ __device__ __forceinline__ void stage16(u64 (&v)[16], const TwPair* __restrict__
             continue;
 #endif
             if (INV)
-                gs_bfly<VAR>(v[k], v[k + (1 << LS)], w, c);
+                gs_bfly<VAR, RED>(v[k], v[k + (1 << LS)], w, c);
             else
                 ct_bfly<VAR, RED>(v[k], v[k + (1 << LS)], w, c);
         }
@@ -377,10 +398,11 @@ template <int GVAR>
 __device__ __forceinline__ void gs_round_a(u64 (&v)[16], const TwPair* __restrict__ tw, int s0, int q,
                                            const BflyConst& c)
 {
-    stage16<0, true, GVAR>(v, tw + (1 << (s0 + 3)) + (q << 3), c);
-    stage16<1, true, GVAR>(v, tw + (1 << (s0 + 2)) + (q << 2), c);
-    stage16<2, true, GVAR>(v, tw + (1 << (s0 + 1)) + (q << 1), c);
-    stage16<3, true, GVAR>(v, tw + (1 << (s0 + 0)) + (q << 0), c);
+    // RED (FP64 variants only): the sum branch is reduced on alternate stages (GVAR 4: on every stage)
+    stage16<0, true, GVAR, 1, true>(v, tw + (1 << (s0 + 3)) + (q << 3), c);
+    stage16<1, true, GVAR, 1, false>(v, tw + (1 << (s0 + 2)) + (q << 2), c);
+    stage16<2, true, GVAR, 1, true>(v, tw + (1 << (s0 + 1)) + (q << 1), c);
+    stage16<3, true, GVAR, 1, false>(v, tw + (1 << (s0 + 0)) + (q << 0), c);
 }
 
 // Last round of the inverse transform (s0 = 0, q = 0): the final stage
@@ -390,9 +412,21 @@ __device__ __forceinline__ void gs_round_a_final(u64 (&v)[16], const TwPair* __r
                                                  const BflyConst& c, const TwPair& ninv,
                                                  const TwPair& wninv)
 {
-    stage16<0, true, GVAR>(v, tw + 8, c);
-    stage16<1, true, GVAR>(v, tw + 4, c);
-    stage16<2, true, GVAR>(v, tw + 2, c);
+    stage16<0, true, GVAR, 1, true>(v, tw + 8, c);
+    stage16<1, true, GVAR, 1, false>(v, tw + 4, c);
+    stage16<2, true, GVAR, 1, true>(v, tw + 2, c);
+    if (GVAR >= 3)
+    {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+        {
+            const double x = u2d(v[k]), y = u2d(v[k + 8]);
+            const double sd = __dadd_rn(x, y), dd = __dsub_rn(x, y); // |.| < 2.4p
+            v[k] = fp_canon(fp_mulmod(sd, u2d(ninv.w), u2d(ninv.ws), c.dnp), c.dpinv, c.dnp, c.dp);
+            v[k + 8] = fp_canon(fp_mulmod(dd, u2d(wninv.w), u2d(wninv.ws), c.dnp), c.dpinv, c.dnp, c.dp);
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k)
     {
@@ -444,10 +478,10 @@ template <int GVAR>
 __device__ __forceinline__ void gs_round_b_lm(u64 (&v)[16], const TwPair* __restrict__ blk, int tt,
                                               const BflyConst& c)
 {
-    stage16<0, true, GVAR, 16>(v, blk + 7 * 16 + tt, c);
-    stage16<1, true, GVAR, 16>(v, blk + 3 * 16 + tt, c);
-    stage16<2, true, GVAR, 16>(v, blk + 1 * 16 + tt, c);
-    stage16<3, true, GVAR, 16>(v, blk + 0 * 16 + tt, c);
+    stage16<0, true, GVAR, 16, true>(v, blk + 7 * 16 + tt, c);
+    stage16<1, true, GVAR, 16, false>(v, blk + 3 * 16 + tt, c);
+    stage16<2, true, GVAR, 16, true>(v, blk + 1 * 16 + tt, c);
+    stage16<3, true, GVAR, 16, false>(v, blk + 0 * 16 + tt, c);
 }
 
 template <int S, int GVAR>
@@ -455,13 +489,13 @@ __device__ __forceinline__ void gs_round_b(u64 (&v)[16], const TwPair* __restric
                                            int tt, const BflyConst& c)
 {
     if constexpr (S >= 8)
-        stage16<S - 8, true, GVAR>(v, tw + (1 << (s0 + 7)) + (q << 7) + (tt << (11 - S)), c);
+        stage16<S - 8, true, GVAR, 1, true>(v, tw + (1 << (s0 + 7)) + (q << 7) + (tt << (11 - S)), c);
     if constexpr (S >= 7)
-        stage16<S - 7, true, GVAR>(v, tw + (1 << (s0 + 6)) + (q << 6) + (tt << (10 - S)), c);
+        stage16<S - 7, true, GVAR, 1, false>(v, tw + (1 << (s0 + 6)) + (q << 6) + (tt << (10 - S)), c);
     if constexpr (S >= 6)
-        stage16<S - 6, true, GVAR>(v, tw + (1 << (s0 + 5)) + (q << 5) + (tt << (9 - S)), c);
+        stage16<S - 6, true, GVAR, 1, true>(v, tw + (1 << (s0 + 5)) + (q << 5) + (tt << (9 - S)), c);
     if constexpr (S >= 5)
-        stage16<S - 5, true, GVAR>(v, tw + (1 << (s0 + 4)) + (q << 4) + (tt << (8 - S)), c);
+        stage16<S - 5, true, GVAR, 1, false>(v, tw + (1 << (s0 + 4)) + (q << 4) + (tt << (8 - S)), c);
 }
 
 } // namespace heon

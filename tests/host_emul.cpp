@@ -126,7 +126,7 @@ static void inv(std::vector<u64>& x, const std::vector<TwPair>& tw, const PrimeC
         for (int tt = 0; tt < 16; ++tt)
         {
             u64 v[16];
-            for (int k = 0; k < 16; ++k) v[k] = x[r * 256 + 16 * tt + k];
+            for (int k = 0; k < 16; ++k) v[k] = gs_prep<GVAR>(x[r * 256 + 16 * tt + k]);
             gs_round_b<8, GVAR>(v, tw.data(), 4, r, tt, bc);
             for (int k = 0; k < 16; ++k) row[16 * tt + k] = v[k];
         }
@@ -156,7 +156,7 @@ int main()
     {
         const u64 p = bits == 61 ? 2305843009213554689ull : largest_ntt_primes(2 * N, bits, 1)[0];
         const u64 psi = minimal_primitive_root(2 * N, p), ipsi = invmod(psi, p);
-        std::vector<TwPair> tw(N), itw(N), twf(N);
+        std::vector<TwPair> tw(N), itw(N), twf(N), itwf(N);
         std::vector<u64> pw(N), ipw(N);
         pw[0] = ipw[0] = 1;
         for (int j = 1; j < N; ++j)
@@ -171,6 +171,9 @@ int main()
             const double wd = (double) tw[j].w, winv = wd / (double) p; // FP64 table format {w, RN(w/p)}
             std::memcpy(&twf[j].w, &wd, 8);
             std::memcpy(&twf[j].ws, &winv, 8);
+            const double iwd = (double) itw[j].w, iwinv = iwd / (double) p;
+            std::memcpy(&itwf[j].w, &iwd, 8);
+            std::memcpy(&itwf[j].ws, &iwinv, 8);
         }
         PrimeConst pc;
         pc.p = p;
@@ -247,10 +250,22 @@ int main()
                     ++failures;
                 }
             }
-            for (int gvar = 0; gvar < 2; ++gvar)
+            for (int gvar = 0; gvar < 5; ++gvar)
             {
+                if (gvar == 2 || (gvar == 3 && pc.bits > 47) || (gvar == 4 && pc.bits > 50))
+                    continue;
                 std::vector<u64> x = ref;
-                gvar == 0 ? inv<0>(x, itw, pc, ninv, wninv) : inv<1>(x, itw, pc, ninv, wninv);
+                auto dpair = [&](u64 w) {
+                    const double wd = (double) w, wi = wd / (double) p;
+                    TwPair t;
+                    std::memcpy(&t.w, &wd, 8);
+                    std::memcpy(&t.ws, &wi, 8);
+                    return t;
+                };
+                gvar == 0   ? inv<0>(x, itw, pc, ninv, wninv)
+                : gvar == 1 ? inv<1>(x, itw, pc, ninv, wninv)
+                : gvar == 3 ? inv<3>(x, itwf, pc, dpair(ni), dpair(wn))
+                            : inv<4>(x, itwf, pc, dpair(ni), dpair(wn));
                 int bad = 0;
                 for (int i = 0; i < N; ++i) bad += x[i] != a[i];
                 if (bad)
