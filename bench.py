@@ -475,7 +475,16 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.batch <= 0:
         args.batch = DEFAULT_BATCH[args.workload]
-    rank, world, local = dist_setup(args.gpus)
+    if args.impl == "reference":
+        # the reference is single-GPU: under torchrun rank 0 alone runs it (no process group is
+        # created, so the other ranks can leave at once without a collective to wait for)
+        rank, world, local = env_rank_world()
+        if rank != 0:
+            return
+        torch.cuda.set_device(local)
+        rank, world = 0, 1
+    else:
+        rank, world, local = dist_setup(args.gpus)
 
     config = {"workload": WORKLOADS[args.workload], "workload_key": args.workload,
               "batch_per_gpu": args.batch, "ops_per_step": args.batch * world,
