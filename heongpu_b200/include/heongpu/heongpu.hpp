@@ -438,6 +438,17 @@ template <> class HEOperator<Scheme::CKKS> {
         out.memory_set(std::move(mem));
     }
 
+    // in-place forms (operator.cuh:130-190, 260-300): the result replaces the first operand
+    void add_inplace(Ciphertext<Scheme::CKKS>& a, Ciphertext<Scheme::CKKS>& b, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        add(a, b, a, opt);
+    }
+    void sub_inplace(Ciphertext<Scheme::CKKS>& a, Ciphertext<Scheme::CKKS>& b, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        sub(a, b, a, opt);
+    }
+    void negate_inplace(Ciphertext<Scheme::CKKS>& a, const ExecutionOptions& opt = ExecutionOptions()) { negate(a, a, opt); }
+
     // operator.cuh:631-691 + multiply_ckks (operator.cu:796-837)
     void multiply(Ciphertext<Scheme::CKKS>& a, Ciphertext<Scheme::CKKS>& b, Ciphertext<Scheme::CKKS>& out,
                   const ExecutionOptions& opt = ExecutionOptions())
@@ -599,6 +610,11 @@ template <> class HEOperator<Scheme::CKKS> {
         out.scale_ = a.scale_ * p.scale_;
         out.rescale_required_ = true;
     }
+    void multiply_plain_inplace(Ciphertext<Scheme::CKKS>& a, Plaintext<Scheme::CKKS>& p,
+                                const ExecutionOptions& opt = ExecutionOptions())
+    {
+        multiply_plain(a, p, a, opt);
+    }
     // operator.cuh:197-620 + add_plain_ckks / sub_plain_ckks (operator.cu:302-345, 434-477)
     void add_plain(Ciphertext<Scheme::CKKS>& a, Plaintext<Scheme::CKKS>& p, Ciphertext<Scheme::CKKS>& out,
                    const ExecutionOptions& opt = ExecutionOptions())
@@ -633,6 +649,10 @@ template <> class HEOperator<Scheme::CKKS> {
         out.memory_set(std::move(mem));
         out.cipher_size_ = 2;
     }
+    void keyswitch_inplace(Ciphertext<Scheme::CKKS>& ct, Switchkey<Scheme::CKKS>& sk, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        keyswitch(ct, ct, sk, opt);
+    }
     // operator.cuh:1354-1420 + conjugate_ckks_method_I/II (operator.cu:2027-2311)
     void conjugate(Ciphertext<Scheme::CKKS>& in, Ciphertext<Scheme::CKKS>& out, Galoiskey<Scheme::CKKS>& gk,
                    const ExecutionOptions& opt = ExecutionOptions())
@@ -646,6 +666,11 @@ template <> class HEOperator<Scheme::CKKS> {
         copy_meta(in, out);
         out.memory_set(std::move(mem));
         out.cipher_size_ = 2;
+    }
+
+    void conjugate_inplace(Ciphertext<Scheme::CKKS>& ct, Galoiskey<Scheme::CKKS>& gk, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        conjugate(ct, ct, gk, opt);
     }
 
   private:
@@ -937,6 +962,15 @@ template <> class HEOperator<Scheme::BFV> {
         copy_meta(a, out);
         out.memory_set(std::move(mem));
     }
+    void add_inplace(Ciphertext<Scheme::BFV>& a, Ciphertext<Scheme::BFV>& b, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        add(a, b, a, opt);
+    }
+    void sub_inplace(Ciphertext<Scheme::BFV>& a, Ciphertext<Scheme::BFV>& b, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        sub(a, b, a, opt);
+    }
+    void negate_inplace(Ciphertext<Scheme::BFV>& a, const ExecutionOptions& opt = ExecutionOptions()) { negate(a, a, opt); }
     // bfv/operator.cuh multiply + multiply_bfv (bfv/operator.cu:336-430)
     void multiply(Ciphertext<Scheme::BFV>& a, Ciphertext<Scheme::BFV>& b, Ciphertext<Scheme::BFV>& out,
                   const ExecutionOptions& opt = ExecutionOptions())
@@ -1044,6 +1078,23 @@ template <> class HEOperator<Scheme::BFV> {
                         const ExecutionOptions& opt = ExecutionOptions())
     {
         apply_galois(in, out, gk, gk.galois_elt_zero, opt);
+    }
+    void rotate_columns_inplace(Ciphertext<Scheme::BFV>& ct, Galoiskey<Scheme::BFV>& gk, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        rotate_columns(ct, ct, gk, opt);
+    }
+    void apply_galois_inplace(Ciphertext<Scheme::BFV>& ct, Galoiskey<Scheme::BFV>& gk, int galois_elt,
+                              const ExecutionOptions& opt = ExecutionOptions())
+    {
+        apply_galois(ct, ct, gk, galois_elt, opt);
+    }
+    void keyswitch_inplace(Ciphertext<Scheme::BFV>& ct, Switchkey<Scheme::BFV>& sk, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        keyswitch(ct, ct, sk, opt);
+    }
+    void multiply_plain_inplace(Ciphertext<Scheme::BFV>& a, Plaintext<Scheme::BFV>& p, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        multiply_plain(a, p, a, opt);
     }
 
   private:

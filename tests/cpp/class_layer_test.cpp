@@ -87,6 +87,18 @@ int main(int argc, char** argv)
         try { operators.rotate_rows(C1, R, galois_key, 5); } catch (const std::logic_error&) { threw = true; }
         if (!threw) { std::puts("FAIL: missing galois key must throw"); return 1; }
 
+        // in-place forms: (C1 + C2) - C2 == C1, -(-C1) == C1
+        {
+            Ciphertext<S> T1(context, a);
+            operators.add_inplace(T1, C2);
+            operators.sub_inplace(T1, C2);
+            operators.negate_inplace(T1);
+            operators.negate_inplace(T1);
+            std::vector<Data64> t1;
+            T1.get_data(t1);
+            if (t1 != a) { std::puts("FAIL: in-place add/sub/negate"); return 1; }
+        }
+
         // hoisted rotations == stand-alone rotations
         {
             Galoiskey<S> gk2(context, std::vector<int>{1, 2, -1});

@@ -284,7 +284,9 @@ def _ctx_with_env(name, **env):
                 os.environ[k] = v
 
 
-@pytest.mark.parametrize("env", [{"HEON_NTT_PIPE": 1}, {"HEON_NTT_FUSED": 1}, {"HEON_NTT_FP64": 0}, {"HEON_NTT_TMA": 0}])
+@pytest.mark.parametrize("env", [{"HEON_NTT_PIPE": 1}, {"HEON_NTT_FUSED": 1}, {"HEON_NTT_FP64": 0}, {"HEON_NTT_TMA": 0},
+                                 {"HEON_ROW_TILE": 16}, {"HEON_ROW_TILE": 4}, {"HEON_COL_THREADS": 256},
+                                 {"HEON_COL_THREADS": 128}, {"HEON_NTT_PERSISTENT": 1}])
 def test_alternate_ntt_paths_agree(env):
     """The opt-in transforms (warp-specialised pipelined kernel, ticket-ordered fused kernel), the
     integer-only butterflies and the LSU row pass must give the default path's words."""
@@ -303,7 +305,8 @@ def test_alternate_ntt_paths_agree(env):
 
 
 @pytest.mark.parametrize("name,env", [("n16_II_small", {"HEON_NTT_PIPE": 1}), ("n13_II", {"HEON_GALOIS_NTT": 0}),
-                                      ("n16_I_small", {"HEON_GALOIS_NTT": 0}), ("n13_II", {"HEON_NTT_FP64": 0})])
+                                      ("n16_I_small", {"HEON_GALOIS_NTT": 0}), ("n13_II", {"HEON_NTT_FP64": 0}),
+                                      ("n16_II_small", {"HEON_SKIP_OWN": 0}), ("n16_II_small", {"HEON_MAC_BY": 8})])
 def test_alternate_operator_paths_agree(name, env):
     """multiply + relinearize + rotation through the alternate paths equal the default path."""
     api = _api()
