@@ -171,3 +171,30 @@ def test_hoisted_rotations_equal_individual_rotations_gpu(name, depth):
         assert np.array_equal(to_host(outs[0, 0]), oc.apply_galois(a[0], key0, elts[0], depth))
     with pytest.raises(api.HeonError):
         op.rotate_rows_hoisted(A, outs, gk, [7])
+
+
+@pytest.mark.parametrize("g", [5, 25, 3, -1])
+def test_ntt_domain_automorphism_index_map(g):
+    """The index map k_galois_permute_ntt applies (2*brev(i')+1 = (2*brev(i)+1)*g mod 2N) equals the
+    coefficient-domain automorphism X -> X^g followed by the forward NTT, for the reference's
+    bit-reversed layout (CPU: oracle NTT)."""
+    oc = oracle_ctx("n12_I")
+    n, logn, p = oc.n, oc.n_power, oc.primes[0]
+    g = g % (2 * n)
+    x = residues(140, [p], n)[0]
+    y = np.zeros(n, dtype=np.uint64)
+    for i in range(n):
+        raw = (i * g) % (2 * n)
+        v = int(x[i])
+        y[raw % n] = (p - v) % p if raw >= n else v
+    want = oc.ntt(y[None, :], [0])[0]
+    X = oc.ntt(x[None, :], [0])[0]
+
+    def brev(v):
+        return int(format(v, f"0{logn}b")[::-1], 2)
+    got = np.array([X[brev((((2 * brev(i) + 1) * g) % (2 * n) - 1) // 2)] for i in range(n)], dtype=np.uint64)
+    assert np.array_equal(got, want)
+    # lanes of a warp (32 consecutive i) read one aligned block of 32 words
+    for base in (0, 32 * 7):
+        srcs = [brev((((2 * brev(i) + 1) * g) % (2 * n) - 1) // 2) for i in range(base, base + 32)]
+        assert len({s // 32 for s in srcs}) == 1 and len(set(srcs)) == 32
