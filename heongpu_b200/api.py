@@ -27,7 +27,7 @@ TBL = dict(
     ii_base_change=12, ii_mi_inv=13, ii_prod=14, ii_i_j=15, ii_i_location=16,
     bfv_base_change_bsk=20, bfv_inv_punct_q=21, bfv_base_change_mtilde=22, bfv_inv_mtilde_mod_bsk=23,
     bfv_prod_q_mod_bsk=24, bfv_inv_prod_q_mod_bsk=25, bfv_base_change_q=26, bfv_base_change_msk=27,
-    bfv_inv_punct_b=28, bfv_prod_b_mod_q=29, bfv_scalars=30,
+    bfv_inv_punct_b=28, bfv_prod_b_mod_q=29, bfv_scalars=30, bfv_plain=31,
 )
 
 _EXC = {-1: ValueError, -2: RuntimeError, -3: RuntimeError, -4: RuntimeError}

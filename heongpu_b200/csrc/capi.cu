@@ -438,6 +438,13 @@ int heon_context_table(heon_context_t ctx, int which, int depth, uint64_t* h_out
                 tmp = {c.bfv.inv_prod_q_mod_m_tilde, c.bfv.inv_prod_B_mod_m_sk, (u64) c.bsk, c.plain_modulus};
                 src = &tmp;
                 break;
+            case HEON_TBL_BFV_PLAIN:
+                tmp = c.bfv.coeff_div_plainmod;
+                tmp.insert(tmp.end(), c.bfv.upper_halfincrement.begin(), c.bfv.upper_halfincrement.end());
+                tmp.push_back(c.bfv.Q_mod_t);
+                tmp.push_back(c.bfv.upper_threshold);
+                src = &tmp;
+                break;
             default: throw std::invalid_argument("unknown table");
         }
         *count = src->size();

@@ -173,6 +173,28 @@ static u64 inv_mod_pow2_32(u64 a)
     return x & 0xffffffffull;
 }
 
+// plaintext-operand constants (bfv/context.cu:501-516, 936-984); floor(Q/t) mod q_i = -(Q mod t) * t^-1 mod q_i
+// because Q - (Q mod t) is divisible by t and Q = 0 (mod q_i)  (the reference divides the big integer with GMP)
+static void build_bfv_plain_constants(Context& c)
+{
+    BfvTables& t = c.bfv;
+    const u64 tt = c.plain_modulus;
+    u64 r = 1;
+    for (int i = 0; i < c.Q_size; ++i)
+        r = mulmod(r, c.mod[i].value % tt, tt);
+    t.Q_mod_t = r;
+    t.upper_threshold = (tt + 1) >> 1;
+    t.coeff_div_plainmod.clear();
+    t.upper_halfincrement.clear();
+    for (int i = 0; i < c.Q_size; ++i)
+    {
+        const u64 q = c.mod[i].value;
+        const u64 rq = r % q;
+        t.coeff_div_plainmod.push_back(rq == 0 ? 0 : mulmod(q - rq, invmod(tt % q, q), q));
+        t.upper_halfincrement.push_back(q - tt);
+    }
+}
+
 void build_bfv_tables(Context& c)
 {
     const int Q = c.Q_size, m = c.bsk;
@@ -250,29 +272,13 @@ void build_bfv_tables(Context& c)
             v = mulmod(v, B(j) % q(i), q(i));
         t.prod_B_mod_q.push_back(v);
     }
+    build_bfv_plain_constants(c);
 }
 
 void upload_bfv_tables(Context& c)
 {
     BfvTables& t = c.bfv;
     {
-        // plaintext-operand constants; floor(Q/t) mod q_i = -(Q mod t) * t^-1 mod q_i because
-        // Q - (Q mod t) is divisible by t and Q = 0 (mod q_i)  (reference: GMP, bfv/context.cu:953-984)
-        const u64 tt = c.plain_modulus;
-        u64 r = 1;
-        for (int i = 0; i < c.Q_size; ++i)
-            r = mulmod(r, c.mod[i].value % tt, tt);
-        t.Q_mod_t = r;
-        t.upper_threshold = (tt + 1) >> 1;
-        t.coeff_div_plainmod.clear();
-        t.upper_halfincrement.clear();
-        for (int i = 0; i < c.Q_size; ++i)
-        {
-            const u64 q = c.mod[i].value;
-            const u64 rq = r % q;
-            t.coeff_div_plainmod.push_back(rq == 0 ? 0 : mulmod(q - rq, invmod(tt % q, q), q));
-            t.upper_halfincrement.push_back(q - tt);
-        }
         t.d_coeff_div_plainmod = upload(t.coeff_div_plainmod);
         t.d_upper_halfincrement = upload(t.upper_halfincrement);
     }

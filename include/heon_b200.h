@@ -79,7 +79,9 @@ enum {
     HEON_TBL_BFV_BASE_CHANGE_MSK = 27,    /* base_change_matrix_msk_            [bsk-1]    */
     HEON_TBL_BFV_INV_PUNCT_B = 28,        /* inv_punctured_prod_mod_B_array_    [bsk-1]    */
     HEON_TBL_BFV_PROD_B_MOD_Q = 29,       /* prod_B_mod_q_                      [Q]        */
-    HEON_TBL_BFV_SCALARS = 30 /* {inv_prod_q_mod_m_tilde_, inv_prod_B_mod_m_sk_, bsk_modulus, plain_modulus} */
+    HEON_TBL_BFV_SCALARS = 30, /* {inv_prod_q_mod_m_tilde_, inv_prod_B_mod_m_sk_, bsk_modulus, plain_modulus} */
+    /* plaintext-operand constants: coeeff_div_plainmod_ [Q], upper_halfincrement_ [Q], Q_mod_t_, upper_threshold_ */
+    HEON_TBL_BFV_PLAIN = 31
 };
 
 typedef struct heon_info {

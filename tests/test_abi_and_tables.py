@@ -84,3 +84,20 @@ def test_steps_to_galois_elt():
     assert api.lib.heon_steps_to_galois_elt(3, n, 5) == pow(5, 3, 2 * n)
     assert api.lib.heon_steps_to_galois_elt(-1, n, 5) == pow(5, n // 2 - 1, 2 * n)
     assert api.lib.heon_steps_to_galois_elt(n // 2, n, 5) == 0
+
+
+@pytest.mark.parametrize("log_n,qb,pb,t", [(12, [36, 36], [37], 1032193), (13, [40, 40, 40, 40], [45, 45], 786433)])
+def test_bfv_plain_constants_equal_big_integer_arithmetic(log_n, qb, pb, t):
+    """coeeff_div_plainmod_ = floor(Q/t) mod q_i (the reference divides the big integer with GMP,
+    bfv/context.cu:953-984); the engine uses -(Q mod t) * t^-1 mod q_i.  Checked against Python integers."""
+    from heongpu_b200 import api
+    ctx = api.HEContext(log_n, qb, pb, device=-1, plain_modulus=t)
+    Q = len(qb)
+    tab = [int(v) for v in ctx.table("bfv_plain")]
+    primes = ctx.primes[:Q]
+    bigQ = 1
+    for q in primes:
+        bigQ *= q
+    assert tab[:Q] == [(bigQ // t) % q for q in primes]
+    assert tab[Q:2 * Q] == [q - t for q in primes]
+    assert tab[2 * Q] == bigQ % t and tab[2 * Q + 1] == (t + 1) >> 1
