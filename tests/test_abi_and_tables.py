@@ -101,3 +101,18 @@ def test_bfv_plain_constants_equal_big_integer_arithmetic(log_n, qb, pb, t):
     assert tab[:Q] == [(bigQ // t) % q for q in primes]
     assert tab[Q:2 * Q] == [q - t for q in primes]
     assert tab[2 * Q] == bigQ % t and tab[2 * Q + 1] == (t + 1) >> 1
+
+
+def test_bench_galois_elt_matches_the_abi():
+    """bench.py's reference arm computes Galois elements itself (so that arm does not touch this
+    library): same values as heon_steps_to_galois_elt (keygeneration.cu:684-727)."""
+    import importlib.util
+    from heongpu_b200 import _lib
+    lib = _lib.load()
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for n in (4096, 32768, 65536):
+        for order in (3, 5):
+            for steps in bench.ROT_STEPS + [3, -5, 100]:
+                assert bench.galois_elt(steps, n, order) == lib.heon_steps_to_galois_elt(steps, n, order), (n, order, steps)
