@@ -143,12 +143,15 @@ def timed(fn, steps, world):
     return max_over_ranks(e0.elapsed_time(e1), world)
 
 
-def make_inputs(name, batch, rank):
-    from tests.common import PARAMS, SEED0, oracle_ctx  # parameter sets + seeded generator only
-    from oracle import oracle as O
+def make_inputs(name, batch, rank, primes=None):
+    """Synthetic ciphertexts and key.  `primes`: the modulus chain of the engine under test (our arm
+    passes its own context's primes; only the reference arm asks the oracle for the chain)."""
+    from tests.common import PARAMS, SEED0  # parameter sets + the documented seed only
     log_n, qb, pb = PARAMS[name]
     n, Q, K = 1 << log_n, len(qb), len(pb)
-    primes = O.generate_primes(n, qb + pb)  # prime search only (table parity is tested elsewhere)
+    if primes is None:
+        from oracle import oracle as O  # reference arm
+        primes = O.generate_primes(n, qb + pb)
     # uniform canonical residues generated ON DEVICE from a counter-based mix of the documented seed
     def dev_residues(buf, shape_lead, plist):
         g = torch.Generator(device="cuda")
@@ -171,10 +174,11 @@ def algorithmic_bytes_per_op(inp):
 
 def run_ours(args, rank, world, local):
     from heongpu_b200 import api
-    inp = make_inputs(args.workload, args.batch, rank)
+    from tests.common import PARAMS
+    log_n, qb, pb = PARAMS[args.workload]
+    ctx = api.HEContext(log_n, qb, pb, device=local)
+    inp = make_inputs(args.workload, args.batch, rank, primes=ctx.primes)
     B, L, n = args.batch, inp["Q"], inp["n"]
-    ctx = api.HEContext(inp["log_n"], inp["qb"], inp["pb"], device=local)
-    assert ctx.primes == inp["primes"]
     op = api.HEArithmeticOperator(ctx)
     A, Bc = api.Ciphertext(ctx, inp["a"]), api.Ciphertext(ctx, inp["b"])
     out = torch.zeros(B, 3, L, n, dtype=torch.int64, device="cuda")
