@@ -116,7 +116,10 @@ class HEContext:
 
     def digits(self, depth=0):
         L = self.Q_size - depth
-        return L if self.keyswitch_method == 1 else -(-L // self.P_size)
+        if self.keyswitch_method == 1:
+            return L
+        # Method II digit size: |P| for CKKS, always 2 for BFV (contextpool.hpp:29, contextpool.cpp:78-104)
+        return -(-L // (self.P_size if self.scheme == "CKKS" else 2))
 
     # ---- NTT (gpuntt::GPU_NTT / GPU_INTT / *_Modulus_Ordered) ----
     def ntt(self, data, prime_index=None, inverse=False, out=None, stream=None):

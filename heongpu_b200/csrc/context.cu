@@ -117,41 +117,52 @@ void build_host_tables(Context& c)
             for (int y = 0; y < L + K; ++y)
                 base.push_back(c.mod[level_prime(y, L, depth)].value);
             LevelTablesII t;
-            t.I_j = digit_sizes(L, K);
+            // digit size: |P| for CKKS (contextpool.cpp:104); the reference's BFV branch never sets it and
+            // keeps the member default m = 2 (contextpool.hpp:29, contextpool.cpp:78-92)
+            t.I_j = digit_sizes(L, c.scheme == SCHEME_CKKS ? K : 2);
             t.d = (int) t.I_j.size();
             t.I_loc.assign(t.d, 0);
             for (int l = 1; l < t.d; ++l)
                 t.I_loc[l] = t.I_loc[l - 1] + t.I_j[l - 1];
+            // Generators follow contextpool.cpp:160-191 / 193-236 (base change), 242-264 / 266-308 (Mi_inv),
+            // 361-394 / 396-438 (prod) with the reference's host Barrett product and its UNREDUCED prime
+            // operand: the words equal the reference's even where that leaves a non-canonical representative.
+            std::vector<Mod64> bm;
+            for (u64 b : base)
+                bm.push_back(make_mod(b));
             for (int l = 0; l < t.d; ++l)
             {
                 const int lo = t.I_loc[l], sz = t.I_j[l];
                 for (int k = 0; k < L + K; ++k)
-                {
-                    const u64 tk = base[k];
                     for (int i = 0; i < sz; ++i)
                     {
                         u64 prod = 1;
                         for (int j = 0; j < sz; ++j)
                             if (j != i)
-                                prod = mulmod(prod, base[lo + j] % tk, tk);
+                                prod = barrett_mult_host(prod, base[lo + j], bm[k]);
                         t.base_change.push_back(prod);
                     }
-                }
+            }
+            for (int l = 0; l < t.d; ++l)
+            {
+                const int lo = t.I_loc[l], sz = t.I_j[l];
                 for (int i = 0; i < sz; ++i)
                 {
-                    const u64 qi = base[lo + i];
                     u64 prod = 1;
                     for (int j = 0; j < sz; ++j)
                         if (j != i)
-                            prod = mulmod(prod, base[lo + j] % qi, qi);
-                    t.mi_inv.push_back(invmod(prod, qi));
+                            prod = barrett_mult_host(prod, base[lo + j], bm[lo + i]);
+                    t.mi_inv.push_back(barrett_modinv_host(prod, bm[lo + i]));
                 }
+            }
+            for (int l = 0; l < t.d; ++l)
+            {
+                const int lo = t.I_loc[l], sz = t.I_j[l];
                 for (int k = 0; k < L + K; ++k)
                 {
-                    const u64 tk = base[k];
                     u64 prod = 1;
                     for (int j = 0; j < sz; ++j)
-                        prod = mulmod(prod, base[lo + j] % tk, tk);
+                        prod = barrett_mult_host(prod, base[lo + j], bm[k]);
                     t.prod.push_back(prod);
                 }
             }
@@ -492,7 +503,7 @@ void upload_tables(Context& c)
             const int L = c.Q_size - depth, K = c.P_size, Ql = L + K;
             std::vector<TwPair> mp;
             for (size_t i = 0; i < t.mi_inv.size(); ++i) // digit primes are q_i (same index at every depth)
-                mp.push_back(TwPair{t.mi_inv[i], shoup(t.mi_inv[i], c.mod[i].value)});
+                mp.push_back(TwPair{t.mi_inv[i] % c.mod[i].value, shoup(t.mi_inv[i] % c.mod[i].value, c.mod[i].value)});
             t.d_mi_inv_pair = upload(mp);
             // base_change layout [digit][k over Q'_l][i in digit]: Shoup word for target prime t_k
             std::vector<TwPair> bp;
@@ -510,16 +521,17 @@ void upload_tables(Context& c)
                         const u64 tk = c.mod[pk].value;
                         for (int i = 0; i < t.I_j[l]; ++i, ++o)
                         {
+                            const u64 bcw = t.base_change[o] % tk; // canonical residue of the exported word
                             if (dfp && fp_ok(pk))
                             {
-                                const double md = (double) t.base_change[o], minv = md / (double) tk;
+                                const double md = (double) bcw, minv = md / (double) tk;
                                 TwPair tp;
                                 std::memcpy(&tp.w, &md, 8);
                                 std::memcpy(&tp.ws, &minv, 8);
                                 bp.push_back(tp);
                             }
                             else
-                                bp.push_back(TwPair{t.base_change[o], shoup(t.base_change[o], tk)});
+                                bp.push_back(TwPair{bcw, shoup(bcw, tk)});
                         }
                     }
                 }
@@ -531,7 +543,7 @@ void upload_tables(Context& c)
                     for (int k = 0; k < Ql; ++k)
                     {
                         const u64 tk = c.mod[level_prime(k, L, depth)].value;
-                        rp[((size_t) r * t.d + dg) * Ql + k] = mulmod((u64) r, t.prod[(size_t) dg * Ql + k], tk);
+                        rp[((size_t) r * t.d + dg) * Ql + k] = mulmod((u64) r, t.prod[(size_t) dg * Ql + k] % tk, tk);
                     }
             t.d_rprod = upload(rp);
         }

@@ -35,6 +35,43 @@ inline Mod64 make_mod(u64 p)
 }
 
 inline u64 mulmod(u64 a, u64 b, u64 p) { return (u64) (((u128) a * b) % p); }
+
+// The reference's HOST Barrett product, operation for operation
+// (gpuntt/common/modular_arith.cuh:90-107, OPERATOR<Data64>::mult): all intermediates in 128 bits, ONE
+// conditional subtraction.  For operands below the modulus it is the exact residue; the Method-II table
+// generators (contextpool.cpp:160-191, 193-236, 361-438) call it with an UNREDUCED prime as one operand,
+// and then the word it leaves can be a non-canonical representative.  Those generators are reproduced with
+// this function so that every exported table word equals the reference's on every modulus chain.
+inline u64 barrett_mult_host(u64 a, u64 b, const Mod64& m)
+{
+    u128 mult = (u128) a * (u128) b;
+    u128 r = mult >> (m.bit - 2);
+    r = r * (u128) m.mu;
+    r = r >> (m.bit + 3);
+    r = r * (u128) m.value;
+    mult = mult - r;
+    const u64 res = (u64) mult;
+    return res >= m.value ? res - m.value : res;
+}
+// OPERATOR<Data64>::exp / modinv of the reference (modular_arith.cuh:111-136): square-and-multiply over
+// the host Barrett product, bit count from log2() of the exponent as a double.  Equal to the exact inverse
+// for a canonical base; reproduced so that a non-canonical base gives the reference's word.
+inline u64 barrett_exp_host(u64 base, u64 exponent, const Mod64& m)
+{
+    u64 result = 1;
+    if (exponent == 0)
+        return result;
+    const int exponent_bit = (int) (__builtin_log2((double) exponent) + 1);
+    for (int i = exponent_bit - 1; i >= 0; --i)
+    {
+        result = barrett_mult_host(result, result, m);
+        if (i < 64 && ((exponent >> i) & 1))
+            result = barrett_mult_host(result, base, m);
+    }
+    return result;
+}
+inline u64 barrett_modinv_host(u64 a, const Mod64& m) { return barrett_exp_host(a, m.value - 2, m); }
+
 inline u64 addmod(u64 a, u64 b, u64 p)
 {
     u64 s = a + b;

@@ -777,7 +777,8 @@ template <> class HEContextImpl<Scheme::BFV> {
             prime_vector_.push_back(Modulus64{raw[i], raw[i + 1], raw[i + 2]});
         context_generated_ = true;
     }
-    int digit_count() const { return P_size == 1 ? Q_size : (Q_size + P_size - 1) / P_size; }
+    // Method II digits have size 2 in the reference's BFV context whatever |P| is (contextpool.hpp:29)
+    int digit_count() const { return P_size == 1 ? Q_size : (Q_size + 1) / 2; }
     heon_context_t handle() const { return h_; }
     size_t get_poly_modulus_degree() const { return (size_t) n; }
 

@@ -64,6 +64,32 @@ static inline u64 o_mult(u64 a, u64 b, const omod* m)
     u64 res = (u64) mult;
     return (res >= m->value) ? (res - m->value) : res;
 }
+/* HOST variant of mult (modular_arith.cuh:90-107): every intermediate stays in 128 bits.  Equal to
+ * o_mult for operands below the modulus; the Method-II table generators call it with an unreduced
+ * prime as one operand (contextpool.cpp:176-181 ff.) and then the two variants can differ. */
+static inline u64 o_mult_host(u64 a, u64 b, const omod* m)
+{
+    u128 mult = (u128) a * (u128) b;
+    u128 r = mult >> (m->bit - 2);
+    r = r * (u128) m->mu;
+    r = r >> (m->bit + 3);
+    r = r * (u128) m->value;
+    mult = mult - r;
+    u64 res = (u64) mult;
+    return (res >= m->value) ? (res - m->value) : res;
+}
+/* exp / modinv on the host (modular_arith.cuh:111-136) */
+static inline u64 o_modinv_host(u64 a, const omod* m)
+{
+    u64 e = m->value - 2, result = 1;
+    int ebit = (int) (log2((double) e) + 1);
+    for (int i = ebit - 1; i >= 0; i--) {
+        result = o_mult_host(result, result, m);
+        if (i < 64 && ((e >> i) & 1))
+            result = o_mult_host(result, a, m);
+    }
+    return result;
+}
 /* reduce: modular_arith.cuh:343-369 */
 static inline u64 o_reduce(u64 a, const omod* m)
 {
@@ -289,8 +315,17 @@ int oracle_rescale_tables(const u64* primes, int Q, u64* modinv, u64* half_mod, 
  * 193-236 (level_base_change_matrix_D_to_Qtilda), 266-308
  * (level_Mi_inv_D_to_Qtilda), 396-438 (level_prod_D_to_Qtilda).  At depth l
  * the top l Q primes are erased from both bases. */
+/* `m` = digit size: |P| for CKKS (contextpool.cpp:104 `m = P_size`); the BFV constructor branch
+ * (contextpool.cpp:78-92) leaves the member's default `m = 2` (contextpool.hpp:29) whatever |P| is. */
+int oracle_method2_tables_m(const u64* primes, int Qp, int K, int depth, int m, u64* base_change, u64* mi_inv,
+                            u64* prod, int* I_j, int* I_loc, int* counts);
 int oracle_method2_tables(const u64* primes, int Qp, int K, int depth, u64* base_change, u64* mi_inv,
                           u64* prod, int* I_j, int* I_loc, int* counts)
+{
+    return oracle_method2_tables_m(primes, Qp, K, depth, K, base_change, mi_inv, prod, I_j, I_loc, counts);
+}
+int oracle_method2_tables_m(const u64* primes, int Qp, int K, int depth, int m, u64* base_change, u64* mi_inv,
+                            u64* prod, int* I_j, int* I_loc, int* counts)
 {
     int Q = Qp - K, L = Q - depth, Ql = L + K;
     u64* base = (u64*) malloc(sizeof(u64) * Ql);
@@ -300,9 +335,9 @@ int oracle_method2_tables(const u64* primes, int Qp, int K, int depth, u64* base
         base[L + i] = primes[Q + i];
     int d = 0, l_ = L;
     while (l_ > 0) {
-        if (l_ > K) {
-            I_j[d++] = K;
-            l_ -= K;
+        if (l_ > m) {
+            I_j[d++] = m;
+            l_ -= m;
         } else {
             I_j[d++] = l_;
             break;
@@ -320,7 +355,7 @@ int oracle_method2_tables(const u64* primes, int Qp, int K, int depth, u64* base
                 u64 temp = 1;
                 for (int j = 0; j < I_j[l]; j++)
                     if (i != j)
-                        temp = o_mult(temp, base[j + index] % base[k], &ok);
+                        temp = o_mult_host(temp, base[j + index], &ok); /* unreduced operand, as the reference */
                 base_change[nb++] = temp;
             }
         }
@@ -334,8 +369,8 @@ int oracle_method2_tables(const u64* primes, int Qp, int K, int depth, u64* base
             u64 temp = 1;
             for (int j = 0; j < I_j[l]; j++)
                 if (i != j)
-                    temp = o_mult(temp, base[j + index] % base[i + index], &mi);
-            mi_inv[nm++] = o_modinv(temp, &mi);
+                    temp = o_mult_host(temp, base[j + index], &mi);
+            mi_inv[nm++] = o_modinv_host(temp, &mi);
         }
         index += I_j[l];
     }
@@ -345,7 +380,7 @@ int oracle_method2_tables(const u64* primes, int Qp, int K, int depth, u64* base
             oracle_make_mod(base[i], &oi);
             u64 temp = 1;
             for (int j = 0; j < I_j[l]; j++)
-                temp = o_mult(temp, base[j + I_loc[l]] % base[i], &oi);
+                temp = o_mult_host(temp, base[j + I_loc[l]], &oi);
             prod[np++] = temp;
         }
     counts[0] = nb;
@@ -417,7 +452,12 @@ typedef struct {
     int **Ij, **Iloc, *dcount;
 } octx;
 
+octx* oracle_ctx_create_m(int n_power, const u64* primes, int Q, int K, int digit_m);
 octx* oracle_ctx_create(int n_power, const u64* primes, int Q, int K)
+{
+    return oracle_ctx_create_m(n_power, primes, Q, K, K); /* CKKS: digits of |P| primes */
+}
+octx* oracle_ctx_create_m(int n_power, const u64* primes, int Q, int K, int digit_m)
 {
     octx* c = (octx*) calloc(1, sizeof(octx));
     c->n_power = n_power;
@@ -454,14 +494,14 @@ octx* oracle_ctx_create(int n_power, const u64* primes, int Q, int K)
         c->dcount = (int*) calloc(Q, sizeof(int));
         for (int dep = 0; dep < Q; dep++) {
             int Ql = Qp - dep;
-            c->bc[dep] = (u64*) malloc(sizeof(u64) * (size_t) Q * Ql * (K + 1));
+            c->bc[dep] = (u64*) malloc(sizeof(u64) * (size_t) Q * Ql * (digit_m + 1));
             c->mi[dep] = (u64*) malloc(sizeof(u64) * Q);
             c->pr[dep] = (u64*) malloc(sizeof(u64) * (size_t) Q * Ql);
             c->Ij[dep] = (int*) malloc(sizeof(int) * Q);
             c->Iloc[dep] = (int*) malloc(sizeof(int) * Q);
             int counts[3];
-            c->dcount[dep] = oracle_method2_tables(primes, Qp, K, dep, c->bc[dep], c->mi[dep],
-                                                   c->pr[dep], c->Ij[dep], c->Iloc[dep], counts);
+            c->dcount[dep] = oracle_method2_tables_m(primes, Qp, K, dep, digit_m, c->bc[dep], c->mi[dep],
+                                                     c->pr[dep], c->Ij[dep], c->Iloc[dep], counts);
         }
     }
     return c;
@@ -988,7 +1028,7 @@ obfv* oracle_bfv_create(int n_power, const u64* primes, int Q, int K, u64 plain_
     for (int i = 0; i < m; i++)
         oracle_make_mod(bsk[i], &c->B[i]);
     oracle_make_mod((u64) 1 << 32, &c->mt);
-    c->ks = oracle_ctx_create(n_power, primes, Q, K);
+    c->ks = oracle_ctx_create_m(n_power, primes, Q, K, 2); /* BFV digits: m = 2 (contextpool.hpp:29) */
 
     c->bcm_bsk = (u64*) malloc(sizeof(u64) * m * Q);
     for (int k = 0; k < m; k++) /* generate_base_matrix_q_Bsk */
@@ -1306,7 +1346,7 @@ void oracle_bfv_relinearize(const obfv* c, u64* ct, const u64* key)
                     temp1[((size_t) by * Qp + i) * n + idx] = o_mult(1, v, &k->mod[i]);
             }
     } else {
-        /* the un-levelled tables equal the depth-0 levelled ones (contextpool.cpp:160-191 vs 193-236) */
+        /* un-levelled tables (contextpool.cpp:160-191, 242-264, 361-394): the depth-0 construction with digit size m = 2 */
         const u64 *bc = k->bc[0], *mi = k->mi[0], *pr = k->pr[0];
         const int *Ij = k->Ij[0], *Iloc = k->Iloc[0];
         for (int by = 0; by < d; by++)

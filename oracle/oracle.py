@@ -96,16 +96,18 @@ def rescale_tables(primes, Q):
     return a[:w].copy(), b[:w].copy(), h[: Q - 1].copy()
 
 
-def method2_tables(primes, Q, K, depth):
+def method2_tables(primes, Q, K, depth, digit_m=None):
+    """digit_m: digit size (default |P|, the CKKS rule; the reference's BFV context always uses 2)."""
     Qp = Q + K
+    m = K if digit_m is None else digit_m
     pr = np.array(primes, dtype=np.uint64)
-    bc = np.zeros(Q * Qp * (K + 1), dtype=np.uint64)
+    bc = np.zeros(Q * Qp * (m + 1), dtype=np.uint64)
     mi = np.zeros(Q, dtype=np.uint64)
     prod = np.zeros(Q * Qp, dtype=np.uint64)
     ij = np.zeros(Q, dtype=np.int32)
     il = np.zeros(Q, dtype=np.int32)
     cnt = np.zeros(3, dtype=np.int32)
-    d = lib().oracle_method2_tables(_p(pr), Qp, K, depth, _p(bc), _p(mi), _p(prod), _ip(ij), _ip(il), _ip(cnt))
+    d = lib().oracle_method2_tables_m(_p(pr), Qp, K, depth, m, _p(bc), _p(mi), _p(prod), _ip(ij), _ip(il), _ip(cnt))
     return dict(d=d, base_change=bc[: cnt[0]].copy(), mi_inv=mi[: cnt[1]].copy(), prod=prod[: cnt[2]].copy(),
                 I_j=ij[:d].copy(), I_location=il[:d].copy())
 
@@ -235,7 +237,8 @@ class BfvOracle:
             self._h = None
 
     def digits(self):
-        return self.Q if self.K == 1 else -(-self.Q // self.K)
+        # Method II digits have size 2 in the reference's BFV context whatever |P| is (contextpool.hpp:29)
+        return self.Q if self.K == 1 else -(-self.Q // 2)
 
     def table(self, which):
         out = np.zeros(64 * 64, dtype=np.uint64)

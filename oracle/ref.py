@@ -161,10 +161,12 @@ class RefGpu:
         self._chk(self.L.refgpu_apply_galois(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(key.data_ptr()), int(galois_elt), depth, self._s(stream)))
 
 
-def tables_for_refgpu(n_power, primes, Q, K, use_ref_host=None):
+def tables_for_refgpu(n_power, primes, Q, K, use_ref_host=None, scheme="CKKS", plain_modulus=786433):
     """Build the table bundle RefGpu needs, from the reference's own host code
     when libref_host.so is present, else from the CPU oracle (identical values,
-    see tests/test_oracle_vs_ref_host.py)."""
+    see tests/test_oracle_vs_ref_host.py).  scheme="BFV": the Method-II tables are the UN-LEVELLED
+    ones of the reference's BFV context (digit size 2, contextpool.cpp:160-191 ff.), read from the
+    reference's own HEContextImpl<BFV> (libref_ctx.so) when it was built."""
     from . import oracle as O
     if use_ref_host is None:
         use_ref_host = have_host()
@@ -176,7 +178,16 @@ def tables_for_refgpu(n_power, primes, Q, K, use_ref_host=None):
              r_modinv=r_modinv if len(r_modinv) else np.zeros(1, dtype=np.uint64),
              r_half_mod=r_half_mod if len(r_half_mod) else np.zeros(1, dtype=np.uint64),
              r_half=r_half if len(r_half) else np.zeros(1, dtype=np.uint64))
-    if K > 1:
+    if K > 1 and scheme == "BFV":
+        if use_ref_host and have_ctx():
+            rc = RefContext("BFV", 1 << n_power, primes[:Q], primes[Q:], plain_modulus=plain_modulus)
+            m = dict(base_change=rc.table(12), mi_inv=rc.table(13), prod=rc.table(14),
+                     I_j=rc.table(15).astype(np.int32), I_location=rc.table(16).astype(np.int32))
+            m["d"] = len(m["I_j"])
+        else:
+            m = O.method2_tables(primes, Q, K, 0, digit_m=2)
+        t["method2"] = [m] * Q
+    elif K > 1:
         if use_ref_host:
             t["method2"] = [method2_tables(1 << n_power, primes, Q, K, d) for d in range(Q)]
         else:
@@ -228,3 +239,56 @@ def bfv_apply_galois(refgpu, a, out, key, galois_elt, stream=None):
     """apply_galois_method_I / _II of the BFV operator on a RefGpu handle."""
     refgpu._chk(refgpu.L.refgpu_bfv_apply_galois(refgpu._h, C.c_void_p(a.data_ptr()), C.c_void_p(out.data_ptr()),
                                                   C.c_void_p(key.data_ptr()), int(galois_elt), RefGpu._s(stream)))
+
+
+# ---------------------------------------------------------------------------------------------
+# libref_ctx.so: the reference's OWN HEContextImpl<BFV> / HEContextImpl<CKKS> (bfv/context.cu,
+# ckks/context.cu compiled unmodified on host-only infrastructure shims, oracle/ref_ctx_harness.cu)
+# ---------------------------------------------------------------------------------------------
+CTX_SO = os.path.join(_HERE, "_ref", "libref_ctx.so")
+
+
+def have_ctx():
+    return os.path.exists(CTX_SO)
+
+
+class RefContext:
+    """Tables of a reference context, addressed by the HEON_TBL_* codes of include/heon_b200.h
+    (BFV extras: 40..43 merged q||Bsk modulus / NTT / INTT / n^-1, 44 {m, l, l_tilda, d})."""
+
+    def __init__(self, scheme, n, q_values=None, p_values=None, plain_modulus=None, default_p_size=None):
+        L = C.CDLL(CTX_SO)
+        for f in ("refctx_bfv_create", "refctx_bfv_create_default", "refctx_ckks_create"):
+            getattr(L, f).restype = C.c_void_p
+        L.refctx_bfv_table.restype = C.c_longlong
+        L.refctx_ckks_table.restype = C.c_longlong
+        self.L, self.scheme = L, scheme
+        if default_p_size is not None:
+            h = L.refctx_bfv_create_default(n, default_p_size, int(plain_modulus))
+        else:
+            q = np.array(q_values, dtype=np.uint64)
+            p = np.array(p_values, dtype=np.uint64)
+            if scheme == "BFV":
+                h = L.refctx_bfv_create(n, _p(q), len(q), _p(p), len(p), int(plain_modulus))
+            else:
+                h = L.refctx_ckks_create(n, _p(q), len(q), _p(p), len(p))
+        if not h:
+            raise RuntimeError("reference context construction failed")
+        self._h = C.c_void_p(h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            (self.L.refctx_bfv_destroy if self.scheme == "BFV" else self.L.refctx_ckks_destroy)(self._h)
+            self._h = None
+
+    def table(self, which, depth=0):
+        if self.scheme == "BFV":
+            call = lambda out, cap: self.L.refctx_bfv_table(self._h, which, out, C.c_longlong(cap))
+        else:
+            call = lambda out, cap: self.L.refctx_ckks_table(self._h, which, depth, out, C.c_longlong(cap))
+        n = call(None, 0)
+        if n < 0:
+            raise KeyError(which)
+        out = np.zeros(max(n, 1), dtype=np.uint64)
+        call(_p(out), n)
+        return out[:n]

@@ -51,7 +51,7 @@ def test_bfv_multiply_relinearize_vs_oracle(name):
 @functools.lru_cache(maxsize=2)
 def _ref_handles(name):
     ob, oc = bfv_oracle(name)
-    t = R.tables_for_refgpu(ob.n_power, ob.primes, ob.Q, ob.K)
+    t = R.tables_for_refgpu(ob.n_power, ob.primes, ob.Q, ob.K, scheme="BFV", plain_modulus=ob.t)
     return R.RefBfv(ob), R.RefGpu(ob.n_power, ob.primes, ob.Q, ob.K, t)
 
 
