@@ -322,8 +322,6 @@ class HEArithmeticOperator:
         return ct
 
     def rescale_inplace(self, ct):
-        if not ct.rescale_required_ and False:
-            raise HeonInvalidArgument("Ciphertexts can not be rescaled")
         c = self.context_
         _check(lib.heon_ckks_rescale(c._h, _ptr(ct.data), ct.stride, ct.depth_, ct.batch, _stream()))
         ct.scale_ = ct.scale_ / float(c.primes[c.Q_size - ct.depth_ - 1])
@@ -384,7 +382,18 @@ class HEArithmeticOperator:
         return out
 
     def rotate_rows_bfv(self, ct, out, galois_key, shift):
+        if shift == 0:  # the reference returns the input unchanged (bfv/operator.cuh:591-595)
+            return self._identity(ct, out)
         return self.apply_galois_bfv(ct, out, galois_key, lib.heon_steps_to_galois_elt(shift, self.context_.n, 3))
+
+    @staticmethod
+    def _identity(ct, out):
+        if out is not ct:
+            out.data.copy_(ct.data)
+            for k in ("depth_", "cipher_size_", "scale_", "relinearization_required_", "rescale_required_", "in_ntt_domain_"):
+                if hasattr(ct, k):
+                    setattr(out, k, getattr(ct, k))
+        return out
 
     def rotate_columns_bfv(self, ct, out, galois_key):
         return self.apply_galois_bfv(ct, out, galois_key, 2 * self.context_.n - 1)
@@ -409,6 +418,8 @@ class HEArithmeticOperator:
         return out
 
     def rotate_rows(self, ct, out, galois_key, shift):
+        if shift == 0:  # the reference returns the input unchanged (ckks/operator.cuh:1123)
+            return self._identity(ct, out)
         elt = lib.heon_steps_to_galois_elt(shift, self.context_.n, galois_key.group_order_)
         return self.apply_galois(ct, out, galois_key, elt)
 
@@ -417,6 +428,16 @@ class HEArithmeticOperator:
         ckks/operator.cu:4674-5446): every shift of `shifts` applied to the same ciphertext(s), written to
         out_data[r] ([R, B, 2, L, N]); mod-up and the forward NTTs are shared by all rotations."""
         c = self.context_
+        if 0 in shifts:  # shift 0 is the identity (ckks/operator.cuh:1123), not the conjugation element 2N-1
+            nz = [i for i, s in enumerate(shifts) if s != 0]
+            if nz:
+                sub = torch.empty((len(nz),) + tuple(out_data.shape[1:]), dtype=out_data.dtype, device=out_data.device)
+                self.rotate_rows_hoisted(ct, sub, galois_key, [shifts[i] for i in nz])
+                out_data[nz] = sub
+            for i, s in enumerate(shifts):
+                if s == 0:
+                    out_data[i].copy_(ct.data)
+            return out_data
         elts = [lib.heon_steps_to_galois_elt(s, c.n, galois_key.group_order_) for s in shifts]
         for e in elts:
             if e not in galois_key.device_location_:

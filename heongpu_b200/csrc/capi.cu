@@ -99,14 +99,33 @@ template <class F> static int guarded(F&& f)
     }
 }
 
-static void need_device(const Context& c)
-{
-    if (c.device < 0)
-        throw std::runtime_error("context was created host-only (device < 0): no CUDA path");
-    cudaError_t e = cudaSetDevice(c.device);
-    if (e != cudaSuccess)
-        throw std::runtime_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
-}
+// Makes the context's device current for the duration of one ABI call and restores the caller's
+// device afterwards; also drops any stale error a previous, unrelated CUDA call left on this thread, so
+// that the launch checks of this call (cudaGetLastError) only ever report this call's own launches.
+struct DeviceGuard {
+    int prev = -1, dev = -1;
+    explicit DeviceGuard(const Context& c)
+    {
+        if (c.device < 0)
+            throw std::runtime_error("context was created host-only (device < 0): no CUDA path");
+        dev = c.device;
+        cudaGetDevice(&prev);
+        if (prev != dev)
+        {
+            cudaError_t e = cudaSetDevice(dev);
+            if (e != cudaSuccess)
+                throw std::runtime_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+        }
+        (void) cudaGetLastError();
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0 && prev != dev)
+            cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 static void finish_context(Context& c, int device, int log_n, int n_q, int n_p, u64 plain_modulus = 0)
 {
@@ -205,6 +224,8 @@ int heon_ckks_context_create_values(int device, int log_n, const uint64_t* q, in
     return guarded([&] {
         if (!out || !q || !p)
             throw std::invalid_argument("null argument");
+        if (log_n < 12 || log_n > 16)
+            throw std::logic_error("Poly modulus degree is not supported");
         auto h = std::make_unique<heon_context_s>();
         for (int i = 0; i < n_q; ++i)
             h->c.mod.push_back(make_mod(q[i]));
@@ -269,7 +290,7 @@ int heon_bfv_multiply(heon_context_t ctx, const uint64_t* a, long long as, const
         if (!ctx || !a || !b || !out)
             throw std::invalid_argument("null argument");
         const Context& c = ctx->c;
-        need_device(c);
+        DeviceGuard dev_guard(c);
         if (batch < 1)
             throw std::invalid_argument("batch must be positive");
         op_bfv_multiply(c, a, as, b, bs, out, os, batch, (cudaStream_t) stream);
@@ -283,7 +304,7 @@ int heon_bfv_relinearize(heon_context_t ctx, uint64_t* ct, long long cs, const u
         if (!ctx || !ct || !relin_key)
             throw std::invalid_argument("null argument");
         const Context& c = ctx->c;
-        need_device(c);
+        DeviceGuard dev_guard(c);
         if (batch < 1)
             throw std::invalid_argument("batch must be positive");
         op_bfv_relinearize(c, ct, cs, relin_key, batch, (cudaStream_t) stream);
@@ -297,7 +318,7 @@ int heon_bfv_apply_galois(heon_context_t ctx, const uint64_t* in, long long is, 
         if (!ctx || !in || !out || !galois_key || in == out)
             throw std::invalid_argument("invalid buffers");
         const Context& c = ctx->c;
-        need_device(c);
+        DeviceGuard dev_guard(c);
         if (c.scheme != SCHEME_BFV)
             throw std::invalid_argument("not a BFV context");
         if (batch < 1)
@@ -313,7 +334,7 @@ int heon_bfv_add_plain(heon_context_t ctx, const uint64_t* ct, long long cs, con
         if (!ctx || !ct || !pt || !out)
             throw std::invalid_argument("null argument");
         const Context& c = ctx->c;
-        need_device(c);
+        DeviceGuard dev_guard(c);
         if (batch < 1)
             throw std::invalid_argument("batch must be positive");
         op_bfv_addsub_plain(c, ct, cs, pt, ps, out, os, comps, batch, 1, (cudaStream_t) stream);
@@ -326,7 +347,7 @@ int heon_bfv_sub_plain(heon_context_t ctx, const uint64_t* ct, long long cs, con
         if (!ctx || !ct || !pt || !out)
             throw std::invalid_argument("null argument");
         const Context& c = ctx->c;
-        need_device(c);
+        DeviceGuard dev_guard(c);
         if (batch < 1)
             throw std::invalid_argument("batch must be positive");
         op_bfv_addsub_plain(c, ct, cs, pt, ps, out, os, comps, batch, 2, (cudaStream_t) stream);
@@ -339,7 +360,7 @@ int heon_bfv_multiply_plain(heon_context_t ctx, const uint64_t* ct, long long cs
         if (!ctx || !ct || !pt || !out || ct == out)
             throw std::invalid_argument("invalid buffers");
         const Context& c = ctx->c;
-        need_device(c);
+        DeviceGuard dev_guard(c);
         if (batch < 1)
             throw std::invalid_argument("batch must be positive");
         op_bfv_multiply_plain(c, ct, cs, pt, ps, out, os, batch, (cudaStream_t) stream);
@@ -353,7 +374,7 @@ int heon_bfv_keyswitch(heon_context_t ctx, const uint64_t* in, long long is, uin
         if (!ctx || !in || !out || !switch_key || in == out)
             throw std::invalid_argument("invalid buffers");
         const Context& c = ctx->c;
-        need_device(c);
+        DeviceGuard dev_guard(c);
         if (c.scheme != SCHEME_BFV)
             throw std::invalid_argument("not a BFV context");
         if (batch < 1)
@@ -479,7 +500,7 @@ int heon_ntt(heon_context_t ctx, const uint64_t* in, uint64_t* out, long long n_
         if (!ctx || !in || !out)
             throw std::invalid_argument("null argument");
         const Context& c = ctx->c;
-        need_device(c);
+        DeviceGuard dev_guard(c);
         if (mod_count < 1 || mod_count > 128)
             throw std::invalid_argument("invalid mod_count");
         PrimeList pl;
@@ -502,7 +523,7 @@ int heon_ntt_poly_ordered(heon_context_t ctx, uint64_t* base, const long long* h
         if (!ctx || !base || !h_offsets)
             throw std::invalid_argument("null argument");
         const Context& c = ctx->c;
-        need_device(c);
+        DeviceGuard dev_guard(c);
         if (prime_index < 0 || prime_index >= c.Qp)
             throw std::invalid_argument("prime index out of range");
         cudaStream_t st = (cudaStream_t) stream;
@@ -526,7 +547,7 @@ int heon_ntt_poly_ordered(heon_context_t ctx, uint64_t* base, const long long* h
     if (!ctx)                                                                                      \
         throw std::invalid_argument("null context");                                               \
     const Context& c = ctx->c;                                                                     \
-    need_device(c);                                                                                \
+    DeviceGuard dev_guard(c);                                                                                \
     if (batch < 1)                                                                                 \
         throw std::invalid_argument("batch must be positive");                                     \
     cudaStream_t st = (cudaStream_t) stream;
@@ -536,6 +557,10 @@ int heon_add(heon_context_t ctx, const uint64_t* a, long long as, const uint64_t
 {
     return guarded([&] {
         HEON_OP_PROLOGUE
+        if (!a || !b || !out)
+            throw std::invalid_argument("null argument");
+        if (comps < 1 || comps > 3)
+            throw std::invalid_argument("Invalid Ciphertexts size!");
         op_add(c, a, as, b, bs, out, os, comps, depth, batch, 0, st);
     });
 }
@@ -544,6 +569,10 @@ int heon_sub(heon_context_t ctx, const uint64_t* a, long long as, const uint64_t
 {
     return guarded([&] {
         HEON_OP_PROLOGUE
+        if (!a || !b || !out)
+            throw std::invalid_argument("null argument");
+        if (comps < 1 || comps > 3)
+            throw std::invalid_argument("Invalid Ciphertexts size!");
         op_add(c, a, as, b, bs, out, os, comps, depth, batch, 1, st);
     });
 }
@@ -552,6 +581,10 @@ int heon_negate(heon_context_t ctx, const uint64_t* a, long long as, uint64_t* o
 {
     return guarded([&] {
         HEON_OP_PROLOGUE
+        if (!a || !out)
+            throw std::invalid_argument("null argument");
+        if (comps < 1 || comps > 3)
+            throw std::invalid_argument("Invalid Ciphertexts size!");
         op_add(c, a, as, a, as, out, os, comps, depth, batch, 2, st);
     });
 }
@@ -561,6 +594,8 @@ int heon_ckks_multiply(heon_context_t ctx, const uint64_t* a, long long as, cons
 {
     return guarded([&] {
         HEON_OP_PROLOGUE
+        if (!a || !b || !out)
+            throw std::invalid_argument("null argument");
         op_multiply(c, a, as, b, bs, out, os, depth, batch, st);
     });
 }
@@ -654,6 +689,8 @@ int heon_ckks_rescale(heon_context_t ctx, uint64_t* ct, long long cs, int depth,
 {
     return guarded([&] {
         HEON_OP_PROLOGUE
+        if (!ct)
+            throw std::invalid_argument("null argument");
         op_rescale(c, ct, cs, depth, batch, st);
     });
 }
@@ -663,6 +700,10 @@ int heon_ckks_mod_drop_inplace(heon_context_t ctx, uint64_t* ct, long long cs, i
 {
     return guarded([&] {
         HEON_OP_PROLOGUE
+        if (!ct)
+            throw std::invalid_argument("null argument");
+        if (comps < 1 || comps > 3)
+            throw std::invalid_argument("Invalid Ciphertexts size!");
         op_mod_drop_inplace(c, ct, cs, comps, depth, batch, st);
     });
 }
@@ -672,6 +713,8 @@ int heon_ckks_mod_drop(heon_context_t ctx, const uint64_t* in, long long is, uin
 {
     return guarded([&] {
         HEON_OP_PROLOGUE
+        if (!in || !out)
+            throw std::invalid_argument("null argument");
         op_mod_drop(c, in, is, out, os, depth, batch, st);
     });
 }

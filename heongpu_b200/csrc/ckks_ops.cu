@@ -1190,12 +1190,16 @@ static int keyswitch_modup_ntt(const Context& c, const u64* coef, long long coef
     if (c.method == 1)
     {
         d = L;
+        if (d > 64)
+            throw std::invalid_argument("too many key-switch digits");
         launch_modup1_ntt(c, coef, coef_bs, tmp, L, depth, batch, st);
     }
     else
     {
         const LevelTablesII& t = c.lvl2[depth];
         d = t.d;
+        if (d > 64)
+            throw std::invalid_argument("too many key-switch digits");
         // two coefficients per thread when the digits are short and the buffers 16-byte aligned
         const bool wide = K <= 4 && c.n >= 512 && (coef_bs & 1) == 0 &&
                           ((reinterpret_cast<uintptr_t>(coef) | reinterpret_cast<uintptr_t>(tmp)) & 15) == 0;
@@ -1221,8 +1225,6 @@ static int keyswitch_modup_ntt(const Context& c, const u64* coef, long long coef
         else
             launch_ntt(c, tmp, tmp, (long long) batch * d * Qpl, level_primes(L, K, depth), false, st);
     }
-    if (d > 64)
-        throw std::invalid_argument("too many key-switch digits");
     return d;
 }
 

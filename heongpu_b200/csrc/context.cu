@@ -309,6 +309,16 @@ void upload_tables(Context& c)
 {
     const int N = c.n;
     const int Qp = (int) c.mod.size(); // device NTT tables cover every prime (Q' chain + Bsk)
+    int prev_device = -1;
+    cudaGetDevice(&prev_device);
+    struct Restore {
+        int prev, dev;
+        ~Restore()
+        {
+            if (prev >= 0 && prev != dev)
+                cudaSetDevice(prev);
+        }
+    } restore{prev_device, c.device};
     HEON_CUDA(cudaSetDevice(c.device));
     HEON_CUDA(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, c.device));
     {
@@ -554,7 +564,20 @@ void upload_tables(Context& c)
 
 Context::~Context()
 {
-    cudaSetDevice(device);
+    if (device < 0)
+        return; // host-only context: nothing was uploaded, and no CUDA call may touch this thread's error state
+    int prev_device = -1;
+    cudaGetDevice(&prev_device);
+    struct Restore {
+        int prev, dev;
+        ~Restore()
+        {
+            if (prev >= 0 && prev != dev)
+                cudaSetDevice(prev);
+        }
+    } restore{prev_device, device};
+    if (prev_device != device)
+        cudaSetDevice(device);
     cudaFree(d_mod);
     cudaFree(d_pc);
     cudaFree(d_fwd);

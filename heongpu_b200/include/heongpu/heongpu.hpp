@@ -578,6 +578,8 @@ template <> class HEOperator<Scheme::CKKS> {
         std::vector<uint32_t> elts;
         for (int s : shifts)
         {
+            if (s == 0)
+                throw std::invalid_argument("rotate_rows_hoisted: shift 0 is the identity, use the input itself");
             const int elt = heon_steps_to_galois_elt(s, context_->n, gk.group_order_);
             auto it = gk.device_location_.find(elt);
             if (elt == 0 || it == gk.device_location_.end())
@@ -1025,6 +1027,19 @@ template <> class HEOperator<Scheme::BFV> {
     void rotate_rows(Ciphertext<Scheme::BFV>& in, Ciphertext<Scheme::BFV>& out, Galoiskey<Scheme::BFV>& gk, int shift,
                      const ExecutionOptions& opt = ExecutionOptions())
     {
+        if (shift == 0)
+        {
+            // the reference returns the input unchanged (bfv/operator.cuh:591-595); steps_to_galois_elt(0) is the
+            // column-rotation element 2N-1 and must not be applied here
+            if (&in != &out)
+            {
+                DeviceVector<Data64> mem(words(2), opt.stream_);
+                detail::cuda(cudaMemcpyAsync(mem.data(), in.data(), mem.size() * sizeof(Data64), cudaMemcpyDeviceToDevice, opt.stream_));
+                copy_meta(in, out);
+                out.memory_set(std::move(mem));
+            }
+            return;
+        }
         const int elt = heon_steps_to_galois_elt(shift, context_->n, gk.group_order_);
         if (elt == 0)
             throw std::invalid_argument("Galois Key can not be generated, Step count too large");
