@@ -158,6 +158,10 @@ static void finish_context(Context& c, int device, int log_n, int n_q, int n_p, 
         c.row_tile = atoi(v);
     if (const char* v = getenv("HEON_SKIP_OWN"))
         c.skip_own = atoi(v);
+    if (const char* v = getenv("HEON_ROW_MAC"))
+        c.row_mac = atoi(v);
+    if (const char* v = getenv("HEON_ROW_MAC_ROWS"))
+        c.row_mac_rows = atoi(v);
     if (const char* v = getenv("HEON_GALOIS_NTT"))
         c.galois_ntt = atoi(v);
     if (const char* v = getenv("HEON_NTT_PIPE"))
@@ -747,7 +751,7 @@ const char* heon_profile_class_name(int cls)
 {
     static const char* names[KC_COUNT] = {"ntt_fwd_col_pass", "ntt_fwd_row_pass", "ntt_inv_row_pass",
                                           "ntt_inv_col_pass", "keyswitch_mac",   "modup_method2",
-                                          "moddown",          "cross_multiply",  "elementwise"};
+                                          "moddown",          "cross_multiply",  "elementwise", "keyswitch_row_mac"};
     return (cls >= 0 && cls < KC_COUNT) ? names[cls] : "";
 }
 

@@ -1183,7 +1183,7 @@ static bool keyswitch_stash_own(const Context& c, const u64* src, long long src_
 // Part one: mod-up of the digits into every prime of Q'_l and forward NTT (tmp[b][d][Qpl][N]).
 // This half does not depend on the key: hoisted rotations run it once for many keys.
 static int keyswitch_modup_ntt(const Context& c, const u64* coef, long long coef_bs, u64* tmp, int depth,
-                               int batch, cudaStream_t st, bool own_stashed = false)
+                               int batch, cudaStream_t st, bool own_stashed = false, bool col_only = false)
 {
     const int L = c.Q_size - depth, K = c.P_size, Qpl = L + K;
     int d;
@@ -1192,7 +1192,7 @@ static int keyswitch_modup_ntt(const Context& c, const u64* coef, long long coef
         d = L;
         if (d > 64)
             throw std::invalid_argument("too many key-switch digits");
-        launch_modup1_ntt(c, coef, coef_bs, tmp, L, depth, batch, st);
+        launch_modup1_ntt(c, coef, coef_bs, tmp, L, depth, batch, st, col_only);
     }
     else
     {
@@ -1221,9 +1221,9 @@ static int keyswitch_modup_ntt(const Context& c, const u64* coef, long long coef
         }
         check_launch();
         if (own_stashed)
-            launch_ntt_digit_skip(c, tmp, d, t.I_loc.data(), t.I_j.data(), L, depth, batch, st);
+            launch_ntt_digit_skip(c, tmp, d, t.I_loc.data(), t.I_j.data(), L, depth, batch, st, col_only);
         else
-            launch_ntt(c, tmp, tmp, (long long) batch * d * Qpl, level_primes(L, K, depth), false, st);
+            launch_ntt(c, tmp, tmp, (long long) batch * d * Qpl, level_primes(L, K, depth), false, st, col_only);
     }
     return d;
 }
@@ -1252,6 +1252,19 @@ static void keyswitch_mac(const Context& c, const u64* tmp, const u64* key, u64*
 static int keyswitch_core(const Context& c, const u64* coef, long long coef_bs, const u64* key,
                           u64* tmp, u64* acc, int depth, int batch, cudaStream_t st, bool own_stashed = false)
 {
+    const int L = c.Q_size - depth;
+    const int d0 = (c.method == 1) ? L : c.lvl2[depth].d;
+    if (row_mac_available(c, tmp, key, acc, d0))
+    {
+        // column stages only; the row stages run inside the inner-product kernel and the transformed
+        // digits never travel through HBM
+        const int d = keyswitch_modup_ntt(c, coef, coef_bs, tmp, depth, batch, st, own_stashed, true);
+        const LevelTablesII* t = c.method == 2 ? &c.lvl2[depth] : nullptr;
+        launch_row_mac(c, tmp, key, acc, d, depth, batch, own_stashed, t ? t->I_loc.data() : nullptr,
+                       t ? t->I_j.data() : nullptr, st);
+        check_launch();
+        return d;
+    }
     const int d = keyswitch_modup_ntt(c, coef, coef_bs, tmp, depth, batch, st, own_stashed);
     keyswitch_mac(c, tmp, key, acc, d, depth, batch, st);
     return d;

@@ -117,6 +117,8 @@ struct Context {
     int galois_ntt = 1; // CKKS automorphisms as NTT-domain permutations after an NTT-domain key switch (HEON_GALOIS_NTT=0: coefficient-domain path)
     int ntt_fused = 0; // forward transform as one ticket-ordered kernel, pass-to-pass data in L2 (HEON_NTT_FUSED=1 enables; superseded by the pipelined kernel)
     int use_fp64 = 1; // FP64-pipe quotient for primes < 2^50 (HEON_NTT_FP64=0 disables)
+    int row_mac = 1; // key switch: forward row pass fused with the inner product (HEON_ROW_MAC=0: separate kernels)
+    int row_mac_rows = 8; // rows per CTA of the fused kernel: 8 or 4 (HEON_ROW_MAC_ROWS)
     u64* d_last_q_modinv = nullptr;
     TwPair* d_lqm_pair = nullptr; // last_q_modinv with Shoup words
     // FP64 form of the correction chain for Q primes below 2^50 (k_moddown2_corr):
@@ -169,10 +171,14 @@ void build_bfv_tables(Context& c);
 void upload_bfv_tables(Context& c);
 
 // ---- NTT launchers (ntt.cu); all asynchronous on `st` ----
+// col_only: run only the first n-8 (column) stages; the row stages follow inside launch_row_mac
 void launch_ntt(const Context& c, const u64* src, u64* dst, long long n_polys, const PrimeList& pl,
-                bool inverse, cudaStream_t st);
+                bool inverse, cudaStream_t st, bool col_only = false);
 void launch_ntt_digit_skip(const Context& c, u64* tmp, int d, const int* I_loc, const int* I_j, int L, int depth,
-                           long long batch, cudaStream_t st);
+                           long long batch, cudaStream_t st, bool col_only = false);
+bool row_mac_available(const Context& c, const u64* tmp, const u64* key, const u64* acc, int d);
+void launch_row_mac(const Context& c, const u64* tmp, const u64* key, u64* acc, int d, int depth, int batch,
+                    bool own_stashed, const int* I_loc, const int* I_j, cudaStream_t st);
 void launch_ntt_scattered(const Context& c, u64* base, const long long* d_offsets, int n_polys,
                           int prime, bool inverse, long long extent_words, bool aligned, cudaStream_t st);
 void launch_ntt_strided(const Context& c, u64* base, long long bstride, int per_batch, int first,
@@ -181,7 +187,7 @@ void launch_ntt_strided_copy(const Context& c, const u64* src, long long src_bst
                              int per_batch, long long batch, const PrimeList& pl, bool inverse,
                              cudaStream_t st);
 void launch_modup1_ntt(const Context& c, const u64* coef, long long coef_bstride, u64* out, int L,
-                       int depth, long long batch, cudaStream_t st);
+                       int depth, long long batch, cudaStream_t st, bool col_only = false);
 void launch_divround1_ntt(const Context& c, const u64* src, long long bstride, long long cstride,
                           u64* out, int Lout, u64 half, u64 plast, const u64* d_half_mod,
                           long long batch, cudaStream_t st);

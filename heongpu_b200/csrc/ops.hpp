@@ -18,6 +18,7 @@ enum KernelClass {
     KC_MODDOWN,
     KC_CROSS_MULTIPLY,
     KC_ELEMENTWISE,
+    KC_ROW_MAC,
     KC_COUNT
 };
 
