@@ -447,3 +447,165 @@ class HEArithmeticOperator:
         _check(lib.heon_ckks_rotate_hoisted(c._h, _ptr(ct.data), ct.stride, _ptr(out_data), out_data.stride(1),
                                             out_data.stride(0), keys, earr, len(elts), ct.depth_, ct.batch, _stream()))
         return out_data
+
+
+# ---------------------------------------------------------------------------------------------
+# client side: key generation, encryption, decryption, encoding
+# ---------------------------------------------------------------------------------------------
+class Secretkey:
+    """Secretkey<S>: [Q'][N] NTT-domain words (src/lib/host/ckks/secretkey.cu)."""
+
+    def __init__(self, context, hamming_weight=None):
+        self.context = context
+        self.hamming_weight_ = hamming_weight if hamming_weight is not None else context.n // 2
+        self.data = None
+        self.secret_key_generated_ = False
+
+
+class Publickey:
+    """Publickey<S>: [2][Q'][N] NTT-domain words (src/lib/host/ckks/publickey.cu)."""
+
+    def __init__(self, context):
+        self.context = context
+        self.data = None
+        self.public_key_generated_ = False
+
+
+class HEKeyGenerator:
+    """HEKeyGenerator<S> (src/lib/host/ckks/keygenerator.cu:28-1200, bfv twin): keys in the reference
+    layouts from a caller-supplied seed (reproducible)."""
+
+    def __init__(self, context, seed=0x48454F4E):
+        self.context_ = context
+        self.seed_ = seed
+        self._n = 0
+
+    def _next(self):
+        self._n += 1
+        return (self.seed_ * 0x9E3779B97F4A7C15 + self._n) & 0xFFFFFFFFFFFFFFFF
+
+    def _buf(self, *shape):
+        return torch.zeros(*shape, dtype=torch.int64, device="cuda")
+
+    def generate_secret_key(self, sk):
+        if sk.secret_key_generated_:
+            raise HeonLogicError("Secretkey is already generated!")
+        c = self.context_
+        sk.data = self._buf(c.Q_prime_size, c.n)
+        _check(lib.heon_keygen_secret(c._h, self._next(), sk.hamming_weight_, _ptr(sk.data), _stream()))
+        sk.secret_key_generated_ = True
+        return sk
+
+    def generate_public_key(self, pk, sk):
+        if not sk.secret_key_generated_:
+            raise HeonLogicError("Secretkey is not generated!")
+        c = self.context_
+        pk.data = self._buf(2, c.Q_prime_size, c.n)
+        _check(lib.heon_keygen_public(c._h, _ptr(sk.data), self._next(), _ptr(pk.data), _stream()))
+        pk.public_key_generated_ = True
+        return pk
+
+    def generate_relin_key(self, sk):
+        c = self.context_
+        key = self._buf(c.digits(0), 2, c.Q_prime_size, c.n)
+        _check(lib.heon_keygen_relin(c._h, _ptr(sk.data), self._next(), _ptr(key), _stream()))
+        return Relinkey(c, key)
+
+    def generate_galois_key(self, sk, shifts=None, galois_elts=None, group_order=None):
+        """Keys for rotate_rows by `shifts` (default +-2^i, i < 8: MAX_SHIFT, evaluationkey.cu:306-345) plus the
+        conjugation / column-rotation key (galois element 2N-1)."""
+        c = self.context_
+        order = group_order or (5 if c.scheme == "CKKS" else 3)
+        if galois_elts is None:
+            if shifts is None:
+                shifts = [s * (1 << i) for i in range(8) for s in (1, -1)]
+            galois_elts = [lib.heon_steps_to_galois_elt(s, c.n, order) for s in shifts]
+        keys = {}
+        for e in list(galois_elts) + [2 * c.n - 1]:
+            if e in keys:
+                continue
+            k = self._buf(c.digits(0), 2, c.Q_prime_size, c.n)
+            _check(lib.heon_keygen_galois(c._h, _ptr(sk.data), e, self._next(), _ptr(k), _stream()))
+            keys[e] = k
+        gk = Galoiskey(c, keys, conjugate_key=keys[2 * c.n - 1])
+        gk.group_order_ = order
+        return gk
+
+    def generate_switch_key(self, new_sk, old_sk):
+        c = self.context_
+        key = self._buf(c.digits(0), 2, c.Q_prime_size, c.n)
+        _check(lib.heon_keygen_switch(c._h, _ptr(new_sk.data), _ptr(old_sk.data), self._next(), _ptr(key), _stream()))
+        return Switchkey(c, key)
+
+
+class HEEncoder:
+    """HEEncoder<CKKS> / HEEncoder<BFV> (src/lib/host/{ckks,bfv}/encoder.cu)."""
+
+    def __init__(self, context):
+        self.context_ = context
+        self.slot_count_ = context.n // 2 if context.scheme == "CKKS" else context.n
+
+    def encode(self, message, scale=None, depth=0):
+        c = self.context_
+        if c.scheme == "CKKS":
+            z = np.ascontiguousarray(np.asarray(message, dtype=np.complex128))
+            L = c.Q_size - depth
+            data = torch.zeros(L, c.n, dtype=torch.int64, device="cuda")
+            _check(lib.heon_ckks_encode(c._h, z.view(np.float64).ctypes.data_as(C.POINTER(C.c_double)), len(z), float(scale),
+                                        depth, _ptr(data), _stream()))
+            return Plaintext(c, data, depth=depth, scale=float(scale))
+        m = np.ascontiguousarray(np.asarray(message, dtype=np.int64) % c.plain_modulus).astype(np.uint64)
+        data = torch.zeros(c.n, dtype=torch.int64, device="cuda")
+        _check(lib.heon_bfv_encode(c._h, m.ctypes.data_as(_lib.u64p), len(m), _ptr(data), _stream()))
+        return Plaintext(c, data)
+
+    def decode(self, pt, count=None):
+        c = self.context_
+        if c.scheme == "CKKS":
+            count = self.slot_count_ if count is None else count
+            out = np.zeros(count, dtype=np.complex128)
+            _check(lib.heon_ckks_decode(c._h, _ptr(pt.data), pt.depth_, float(pt.scale_),
+                                        out.view(np.float64).ctypes.data_as(C.POINTER(C.c_double)), count, _stream()))
+            return out
+        count = self.slot_count_ if count is None else count
+        out = np.zeros(count, dtype=np.uint64)
+        _check(lib.heon_bfv_decode(c._h, _ptr(pt.data), out.ctypes.data_as(_lib.u64p), count, _stream()))
+        return out
+
+
+class HEEncryptor:
+    """HEEncryptor<S>(context, public_key) (src/lib/host/{ckks,bfv}/encryptor.cu)."""
+
+    def __init__(self, context, public_key, seed=0x454E43):
+        self.context_, self.public_key_, self.seed_, self._n = context, public_key, seed, 0
+
+    def encrypt(self, pt):
+        c = self.context_
+        self._n += 1
+        data = torch.zeros(1, 2, c.Q_size, c.n, dtype=torch.int64, device="cuda")
+        _check(lib.heon_encrypt(c._h, _ptr(self.public_key_.data), _ptr(pt.data), (self.seed_ << 20) + self._n, _ptr(data),
+                                _stream()))
+        ct = Ciphertext(c, data, depth=0, scale=getattr(pt, "scale_", 1.0))
+        ct.in_ntt_domain_ = c.scheme == "CKKS"
+        return ct
+
+
+class HEDecryptor:
+    """HEDecryptor<S>(context, secret_key) (src/lib/host/{ckks,bfv}/decryptor.cu)."""
+
+    def __init__(self, context, secret_key):
+        self.context_, self.secret_key_ = context, secret_key
+
+    def decrypt(self, ct, index=0):
+        c = self.context_
+        words = ct.words()[index]
+        if c.scheme == "CKKS":
+            L = ct.level_count()
+            data = torch.zeros(L, c.n, dtype=torch.int64, device="cuda")
+            _check(lib.heon_ckks_decrypt(c._h, _ptr(self.secret_key_.data), _ptr(words.contiguous()), ct.cipher_size_, ct.depth_,
+                                         _ptr(data), _stream()))
+            return Plaintext(c, data, depth=ct.depth_, scale=ct.scale_)
+        data = torch.zeros(c.n, dtype=torch.int64, device="cuda")
+        _check(lib.heon_bfv_decrypt(c._h, _ptr(self.secret_key_.data), _ptr(words.contiguous()), ct.cipher_size_, _ptr(data),
+                                    _stream()))
+        return Plaintext(c, data)

@@ -9,10 +9,12 @@ OBJ=${HEON_OBJDIR:-lib}
 mkdir -p $OBJ
 FLAGS="$HEON_EXTRA -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -cudart static"
 pids=()
-for f in ntt ckks_ops bfv_ops context capi; do
+SRCS="ntt ntt_maps ntt_skip ntt_modup1 ntt_modup2 ntt_divround rowmac ckks_ops bfv_ops client context capi"
+for f in $SRCS; do
   $NVCC $FLAGS -c csrc/$f.cu -o $OBJ/$f.o &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC $FLAGS -shared $OBJ/ntt.o $OBJ/ckks_ops.o $OBJ/bfv_ops.o $OBJ/context.o $OBJ/capi.o -o lib/$OUT
+OBJS=""; for f in $SRCS; do OBJS="$OBJS $OBJ/$f.o"; done
+$NVCC $FLAGS -shared $OBJS -o lib/$OUT
 echo "built $(pwd)/lib/$OUT"

@@ -160,6 +160,8 @@ static void finish_context(Context& c, int device, int log_n, int n_q, int n_p, 
         c.skip_own = atoi(v);
     if (const char* v = getenv("HEON_ROW_MAC"))
         c.row_mac = atoi(v);
+    if (const char* v = getenv("HEON_MODUP_FUSED"))
+        c.modup_fused = atoi(v);
     if (const char* v = getenv("HEON_ROW_MAC_ROWS"))
         c.row_mac_rows = atoi(v);
     if (const char* v = getenv("HEON_GALOIS_NTT"))
@@ -198,6 +200,22 @@ static void finish_context(Context& c, int device, int log_n, int n_q, int n_p, 
             upload_bfv_tables(c);
     }
 }
+
+// ---- client side (client.cu) ----
+namespace heon {
+void client_keygen_secret(const Context& c, u64 seed, int hamming_weight, u64* sk, cudaStream_t st);
+void client_keygen_public(const Context& c, const u64* sk, u64 seed, u64* pk, cudaStream_t st);
+void client_keygen_evk(const Context& c, const u64* under, const u64* target, u64 seed, u64* key, cudaStream_t st);
+void client_keygen_relin(const Context& c, const u64* sk, u64 seed, u64* key, cudaStream_t st);
+void client_keygen_galois(const Context& c, const u64* sk, unsigned galois_elt, u64 seed, u64* key, cudaStream_t st);
+void client_encrypt(const Context& c, const u64* pk, const u64* pt, u64 seed, u64* ct, cudaStream_t st);
+void client_decrypt_ckks(const Context& c, const u64* sk, const u64* ct, int comps, int depth, u64* pt, cudaStream_t st);
+void client_decrypt_bfv(const Context& c, const u64* sk, const u64* ct, int comps, u64* pt, cudaStream_t st);
+void client_ckks_encode(const Context& c, const double* values, int count, double scale, int depth, u64* pt, cudaStream_t st);
+void client_ckks_decode(const Context& c, const u64* pt, int depth, double scale, double* out, int count, cudaStream_t st);
+void client_bfv_encode(const Context& c, const u64* msg, int count, u64* pt, cudaStream_t st);
+void client_bfv_decode(const Context& c, const u64* pt, u64* msg, int count, cudaStream_t st);
+} // namespace heon
 
 extern "C" {
 
@@ -732,6 +750,138 @@ int heon_ckks_apply_galois(heon_context_t ctx, const uint64_t* in, long long is,
         if (!in || !out || !galois_key || in == out)
             throw std::invalid_argument("invalid buffers");
         op_apply_galois(c, in, is, out, os, galois_key, galois_elt, depth, batch, st);
+    });
+}
+
+// ---- client side (client.cu) ----
+
+#define HEON_CLIENT_PROLOGUE                                                                       \
+    if (!ctx)                                                                                      \
+        throw std::invalid_argument("null context");                                               \
+    const Context& c = ctx->c;                                                                     \
+    DeviceGuard dev_guard(c);                                                                      \
+    cudaStream_t st = (cudaStream_t) stream;
+
+int heon_keygen_secret(heon_context_t ctx, uint64_t seed, int hamming_weight, uint64_t* sk, void* stream)
+{
+    return guarded([&] {
+        HEON_CLIENT_PROLOGUE
+        if (!sk)
+            throw std::invalid_argument("null argument");
+        client_keygen_secret(c, seed, hamming_weight, sk, st);
+    });
+}
+int heon_keygen_public(heon_context_t ctx, const uint64_t* sk, uint64_t seed, uint64_t* pk, void* stream)
+{
+    return guarded([&] {
+        HEON_CLIENT_PROLOGUE
+        if (!sk || !pk)
+            throw std::invalid_argument("null argument");
+        client_keygen_public(c, sk, seed, pk, st);
+    });
+}
+int heon_keygen_relin(heon_context_t ctx, const uint64_t* sk, uint64_t seed, uint64_t* key, void* stream)
+{
+    return guarded([&] {
+        HEON_CLIENT_PROLOGUE
+        if (!sk || !key)
+            throw std::invalid_argument("null argument");
+        client_keygen_relin(c, sk, seed, key, st);
+    });
+}
+int heon_keygen_galois(heon_context_t ctx, const uint64_t* sk, uint32_t galois_elt, uint64_t seed, uint64_t* key,
+                       void* stream)
+{
+    return guarded([&] {
+        HEON_CLIENT_PROLOGUE
+        if (!sk || !key)
+            throw std::invalid_argument("null argument");
+        client_keygen_galois(c, sk, galois_elt, seed, key, st);
+    });
+}
+int heon_keygen_switch(heon_context_t ctx, const uint64_t* new_sk, const uint64_t* old_sk, uint64_t seed,
+                       uint64_t* key, void* stream)
+{
+    return guarded([&] {
+        HEON_CLIENT_PROLOGUE
+        if (!new_sk || !old_sk || !key)
+            throw std::invalid_argument("null argument");
+        client_keygen_evk(c, new_sk, old_sk, seed, key, st);
+    });
+}
+int heon_encrypt(heon_context_t ctx, const uint64_t* pk, const uint64_t* pt, uint64_t seed, uint64_t* ct, void* stream)
+{
+    return guarded([&] {
+        HEON_CLIENT_PROLOGUE
+        if (!pk || !ct)
+            throw std::invalid_argument("null argument");
+        client_encrypt(c, pk, pt, seed, ct, st);
+    });
+}
+int heon_ckks_decrypt(heon_context_t ctx, const uint64_t* sk, const uint64_t* ct, int components, int depth,
+                      uint64_t* pt, void* stream)
+{
+    return guarded([&] {
+        HEON_CLIENT_PROLOGUE
+        if (!sk || !ct || !pt)
+            throw std::invalid_argument("null argument");
+        if (c.scheme != SCHEME_CKKS)
+            throw std::invalid_argument("not a CKKS context");
+        client_decrypt_ckks(c, sk, ct, components, depth, pt, st);
+    });
+}
+int heon_bfv_decrypt(heon_context_t ctx, const uint64_t* sk, const uint64_t* ct, int components, uint64_t* pt,
+                     void* stream)
+{
+    return guarded([&] {
+        HEON_CLIENT_PROLOGUE
+        if (!sk || !ct || !pt)
+            throw std::invalid_argument("null argument");
+        if (c.scheme != SCHEME_BFV)
+            throw std::invalid_argument("not a BFV context");
+        client_decrypt_bfv(c, sk, ct, components, pt, st);
+    });
+}
+int heon_ckks_encode(heon_context_t ctx, const double* h_values, int count, double scale, int depth, uint64_t* pt,
+                     void* stream)
+{
+    return guarded([&] {
+        HEON_CLIENT_PROLOGUE
+        if (!pt || (count > 0 && !h_values))
+            throw std::invalid_argument("null argument");
+        if (c.scheme != SCHEME_CKKS)
+            throw std::invalid_argument("not a CKKS context");
+        client_ckks_encode(c, h_values, count, scale, depth, pt, st);
+    });
+}
+int heon_ckks_decode(heon_context_t ctx, const uint64_t* pt, int depth, double scale, double* h_out, int count,
+                     void* stream)
+{
+    return guarded([&] {
+        HEON_CLIENT_PROLOGUE
+        if (!pt || !h_out)
+            throw std::invalid_argument("null argument");
+        if (c.scheme != SCHEME_CKKS)
+            throw std::invalid_argument("not a CKKS context");
+        client_ckks_decode(c, pt, depth, scale, h_out, count, st);
+    });
+}
+int heon_bfv_encode(heon_context_t ctx, const uint64_t* h_message, int count, uint64_t* pt, void* stream)
+{
+    return guarded([&] {
+        HEON_CLIENT_PROLOGUE
+        if (!pt || (count > 0 && !h_message))
+            throw std::invalid_argument("null argument");
+        client_bfv_encode(c, h_message, count, pt, st);
+    });
+}
+int heon_bfv_decode(heon_context_t ctx, const uint64_t* pt, uint64_t* h_message, int count, void* stream)
+{
+    return guarded([&] {
+        HEON_CLIENT_PROLOGUE
+        if (!pt || !h_message)
+            throw std::invalid_argument("null argument");
+        client_bfv_decode(c, pt, h_message, count, st);
     });
 }
 

@@ -1200,6 +1200,15 @@ static int keyswitch_modup_ntt(const Context& c, const u64* coef, long long coef
         d = t.d;
         if (d > 64)
             throw std::invalid_argument("too many key-switch digits");
+        if (modup2_fused_available(c, depth, coef, coef_bs))
+        {
+            // the conversion runs inside the column-pass load: the converted digits are never stored
+            Scratch part((size_t) batch * L * c.n * 8, st);
+            Scratch rq((size_t) batch * d * c.n, st);
+            launch_modup2_ntt(c, coef, coef_bs, tmp, part.w(), (unsigned char*) rq.p, depth, batch, own_stashed, col_only, st);
+            check_launch();
+            return d;
+        }
         // two coefficients per thread when the digits are short and the buffers 16-byte aligned
         const bool wide = K <= 4 && c.n >= 512 && (coef_bs & 1) == 0 &&
                           ((reinterpret_cast<uintptr_t>(coef) | reinterpret_cast<uintptr_t>(tmp)) & 15) == 0;
@@ -1366,6 +1375,20 @@ static void moddown_add(const Context& c, u64* acc, u64* tmp, const u64* ct_in, 
             check_launch();
         }
     }
+}
+
+// Coefficient-domain divide-and-round by every special prime of acc-shaped input [b][2][Q'][N] -> [b][2][Q][N]
+// (depth 0).  Used by public-key encryption (enc_div_lastq_*_kernel, encryption.cu:30-210).
+void op_moddown_coeff(const Context& c, const u64* in, u64* out, long long out_bs, int batch, cudaStream_t st)
+{
+    const int L = c.Q_size, K = c.P_size, Qpl = L + K;
+    dim3 g(c.n >> 8, batch * 2);
+    {
+        LaunchScope scope(KC_MODDOWN, st);
+        k_moddown_ext<false><<<g, 256, 0, st>>>(in, out, out_bs, nullptr, c.d_pc, c.d_half, c.d_half_mod, c.d_lqm_pair, 0, c.logn,
+                                                Qpl, L, c.Qp, c.Q_size, K, 0);
+    }
+    check_launch();
 }
 
 // ct: [b][3][L][N] NTT domain, in place; on return components 0,1 hold the

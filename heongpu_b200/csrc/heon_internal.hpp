@@ -118,7 +118,8 @@ struct Context {
     int ntt_fused = 0; // forward transform as one ticket-ordered kernel, pass-to-pass data in L2 (HEON_NTT_FUSED=1 enables; superseded by the pipelined kernel)
     int use_fp64 = 1; // FP64-pipe quotient for primes < 2^50 (HEON_NTT_FP64=0 disables)
     int row_mac = 1; // key switch: forward row pass fused with the inner product (HEON_ROW_MAC=0: separate kernels)
-    int row_mac_rows = 8; // rows per CTA of the fused kernel: 8 or 4 (HEON_ROW_MAC_ROWS)
+    int modup_fused = 0; // HEON_MODUP_FUSED=1: Method-II mod-up computed inside the column-pass load (no converted-digit buffer; measured slower than the separate FP64 kernel on B200, kept opt-in)
+    int row_mac_rows = 4; // rows per CTA of the fused kernel: 4 (default, 6 CTAs/SM: +2 % measured) or 8 (HEON_ROW_MAC_ROWS)
     u64* d_last_q_modinv = nullptr;
     TwPair* d_lqm_pair = nullptr; // last_q_modinv with Shoup words
     // FP64 form of the correction chain for Q primes below 2^50 (k_moddown2_corr):
@@ -176,6 +177,9 @@ void launch_ntt(const Context& c, const u64* src, u64* dst, long long n_polys, c
                 bool inverse, cudaStream_t st, bool col_only = false);
 void launch_ntt_digit_skip(const Context& c, u64* tmp, int d, const int* I_loc, const int* I_j, int L, int depth,
                            long long batch, cudaStream_t st, bool col_only = false);
+bool modup2_fused_available(const Context& c, int depth, const u64* coef, long long coef_bs);
+void launch_modup2_ntt(const Context& c, const u64* coef, long long coef_bs, u64* tmp, u64* part, unsigned char* rq,
+                       int depth, long long batch, bool own_stashed, bool col_only, cudaStream_t st);
 bool row_mac_available(const Context& c, const u64* tmp, const u64* key, const u64* acc, int d);
 void launch_row_mac(const Context& c, const u64* tmp, const u64* key, u64* acc, int d, int depth, int batch,
                     bool own_stashed, const int* I_loc, const int* I_j, cudaStream_t st);

@@ -1,1589 +1,7 @@
-// Batched negacyclic NTT / INTT over RNS limbs for sm_100a.
-//
-// Replaces gpuntt::GPU_NTT / GPU_INTT / *_Modulus_Ordered / *_Poly_Ordered
-// (reference: thirdparty/GPU-NTT/src/lib/ntt_merge/ntt.cu:596-763,1204-1320,
-// 3106-3255,3405-3502,3785-3935,4085-4182; host dispatch 2563-3103,3603-3783,
-// 4284-4466).  Same transform: psi-merged Cooley-Tukey forward (natural in,
-// bit-reversed out), Gentleman-Sande inverse with the final N^-1, twiddles
-// psi^bitrev(i) (reference table layout util.cu:398-451).
-//
-// Structure: N = 2^n is viewed as a (2^(n-8) x 256) matrix.  The forward
-// transform is a column pass (first n-8 stages, stride >= 256) followed by a
-// row pass (last 8 stages inside 2 KiB rows); the inverse runs the row pass
-// first.  Each thread keeps 16 coefficients in registers and performs four
-// radix-2 stages per round; rounds are separated by one shared-memory
-// transpose.  Butterflies are Harvey/Shoup lazy butterflies (values kept in
-// [0,4p) forward, [0,2p) inverse); every word is canonicalised before the
-// final store, so results equal the reference's Barrett arithmetic bit for bit.
-#include "modarith.cuh"
-#include "ntt_core.cuh"
-#include "ops.hpp"
-#include "tma.cuh"
-#include <algorithm>
-
-#ifndef HEON_NTT_MINBLOCKS
-#define HEON_NTT_MINBLOCKS 3
-#endif
-#ifndef HEON_COL_MINBLOCKS
-#define HEON_COL_MINBLOCKS HEON_NTT_MINBLOCKS
-#endif
+// Batched negacyclic NTT / INTT: contiguous polynomials (gpuntt::GPU_NTT / GPU_INTT / *_Modulus_Ordered).
+#include "ntt_impl.cuh"
 
 namespace heon {
-
-// ---------------------------------------------------------------------------
-// poly -> (input pointer, output pointer, prime) maps
-// ---------------------------------------------------------------------------
-
-// contiguous polys; prime = list[z % count].  `src` may differ from `dst`
-// (out-of-place transform), both are [n_polys][N].
-struct MapContig {
-    const u64* src;
-    u64* dst;
-    PrimeList pl;
-    int logn;
-    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& out, int& prime, int& aux) const
-    {
-        in = src + (z << logn);
-        out = dst + (z << logn);
-        prime = pl.idx[z % pl.count];
-        aux = 0;
-    }
-    static constexpr bool kXform = false;
-    static constexpr bool kLazyIn = false;
-    __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&, int) const { return x; }
-};
-
-// polys at explicit word offsets, one prime, in place
-struct MapScatter {
-    u64* base;
-    const long long* offs; // device array
-    int prime;
-    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& out, int& pr, int& aux) const
-    {
-        in = out = base + offs[z];
-        pr = prime;
-        aux = 0;
-    }
-    static constexpr bool kXform = false;
-    static constexpr bool kLazyIn = false;
-    __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&, int) const { return x; }
-};
-
-// Strided polys: poly z = (b, j) with j < per_batch lives at
-// base + b*bstride + (first + j)*N; prime = list[j % count].  In place.
-struct MapStrided {
-    u64* base;
-    long long bstride;
-    int per_batch, first;
-    PrimeList pl;
-    int logn;
-    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& out, int& prime, int& aux) const
-    {
-        long long b = z / per_batch;
-        int j = (int) (z % per_batch);
-        in = out = base + b * bstride + ((long long) (first + j) << logn);
-        prime = pl.idx[j % pl.count];
-        aux = 0;
-    }
-    static constexpr bool kXform = false;
-    static constexpr bool kLazyIn = false;
-    __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&, int) const { return x; }
-};
-
-// Out-of-place strided source -> contiguous destination (used by apply_galois
-// to leave the input ciphertext untouched).
-struct MapStridedCopy {
-    const u64* src;
-    u64* dst;
-    long long src_bstride;
-    int per_batch;
-    PrimeList pl;
-    int logn;
-    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& out, int& prime, int& aux) const
-    {
-        long long b = z / per_batch;
-        int j = (int) (z % per_batch);
-        in = src + b * src_bstride + ((long long) j << logn);
-        out = dst + (z << logn);
-        prime = pl.idx[j % pl.count];
-        aux = 0;
-    }
-    static constexpr bool kXform = false;
-    static constexpr bool kLazyIn = false;
-    __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&, int) const { return x; }
-};
-
-// Method-II key-switch buffer tmp[b][digit][Q'_l][N] WITHOUT the digits' own limbs (those hold the
-// original NTT-domain words already: NTT(INTT(x)) = x).  Poly z = (b, i, y') enumerates, per digit i,
-// the Q'_l - I_j[i] limbs outside [I_loc[i], I_loc[i] + I_j[i]).  In place.
-struct MapDigitSkip {
-    u64* base;
-    int d, Qpl, L, depth, logn, per_b;
-    short prefix[66], I_loc[65], I_j[65];
-    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& out, int& prime, int& aux) const
-    {
-        const long long b = z / per_b;
-        const int zl = (int) (z % per_b);
-        int i = 0;
-        while (i + 1 < d && zl >= prefix[i + 1])
-            ++i;
-        int y = zl - prefix[i];
-        if (y >= I_loc[i])
-            y += I_j[i];
-        in = out = base + (((b * d + i) * Qpl + y) << logn);
-        prime = level_prime(y, L, depth);
-        aux = 0;
-    }
-    static constexpr bool kXform = false;
-    static constexpr bool kLazyIn = false;
-    __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst&, int) const { return x; }
-};
-
-// Method-I mod-up fused into the first pass: output poly z = (b, i, y) reads
-// digit i of ciphertext b (coefficient domain) and reduces it into prime y.
-// Replaces cipher_broadcast_leveled_kernel / ckks_duplicate_kernel
-// (reference: src/lib/kernel/switchkey.cu:29-59, 1558-1590).
-struct MapModUpI {
-    const u64* coef; // digits (coefficient domain): coef + b*bstride + i*N
-    u64* out; // [b][L][Qpl][N]
-    long long coef_bstride;
-    int L, Qpl, depth, logn;
-    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& o, int& prime, int& aux) const
-    {
-        int y = (int) (z % Qpl);
-        long long t = z / Qpl;
-        int i = (int) (t % L);
-        long long b = t / L;
-        in = coef + b * coef_bstride + ((long long) i << logn);
-        o = out + (z << logn);
-        prime = level_prime(y, L, depth);
-        // The digit word x < 2^bits(q_i) is already a valid lazy NTT input (< 4p)
-        // when the digit prime is at most one bit longer than the target prime.
-        aux = pcs[i].bits > pcs[prime].bits + 1;
-    }
-    static constexpr bool kXform = true;
-    static constexpr bool kLazyIn = true; // words in [0,4p)
-    const PrimeConst* pcs;
-    __device__ __forceinline__ u64 xform(u64 x, int, const PrimeConst& pc, int need_reduce) const
-    {
-        return need_reduce ? shoup_mul_lazy3(x, 1, pc.inv64, pc.p) : x; // [0,4p) either way
-    }
-};
-
-// Divide-and-round stage one fused into the first pass: output poly
-// z = (b, c, i) reads the dropped limb of component c (coefficient domain),
-// adds half, reduces into q_i and subtracts half mod q_i.
-// Replaces divide_round_lastq_leveled_stage_one_kernel
-// (reference: src/lib/kernel/switchkey.cu:678-705).
-struct MapDivRoundOne {
-    const u64* src; // dropped limb of comp c: src + b*bstride + c*cstride
-    u64* out; // [b][2][Lout][N]
-    long long bstride, cstride;
-    int Lout, logn;
-    u64 half, plast; // floor(p_last/2), p_last
-    const u64* half_mod; // [Lout]
-    __device__ __forceinline__ void get(long long z, const u64*& in, u64*& o, int& prime, int& aux) const
-    {
-        int i = (int) (z % Lout);
-        long long t = z / Lout;
-        int c = (int) (t & 1);
-        long long b = t >> 1;
-        in = src + b * bstride + c * cstride;
-        o = out + (z << logn);
-        prime = i;
-        aux = 0;
-    }
-    static constexpr bool kXform = true;
-    static constexpr bool kLazyIn = false;
-    __device__ __forceinline__ u64 xform(u64 x, int prime, const PrimeConst& pc, int) const
-    {
-        x = mod_add(x, half, plast);
-        x = reduce_u64(x, pc);
-        return mod_sub(x, half_mod[prime], pc.p);
-    }
-};
-
-// ---------------------------------------------------------------------------
-// kernels
-// ---------------------------------------------------------------------------
-
-// Column pass body: S stages on columns (stride 256 words).  T = 2^S/16 threads
-// cooperate on one column, C = 256/T adjacent columns per CTA.
-template <int S, bool INV, int VAR, class Map, int NT = 256>
-__device__ __forceinline__ void col_pass_body(const Map& map, const u64* in, u64* out, int prime,
-                                              const PrimeConst& pc, const TwPair* __restrict__ tw,
-                                              const TwPair* __restrict__ inv_last, int tile,
-                                              bool first_pass, int aux, u64* sm)
-{
-    constexpr int T = (1 << S) / 16;
-    constexpr int C = NT / T; // columns per CTA
-    const BflyConst bc = make_bc(pc);
-    const int c = threadIdx.x % C;
-    const int tt = threadIdx.x / C;
-    const int col = tile * C + c;
-    u64 v[16];
-
-    if constexpr (!INV)
-    {
-        // forward: first pass of the transform
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-        {
-            u64 x = in[(long long) (tt + T * k) * 256 + col];
-            if (Map::kXform && first_pass)
-                x = map.xform(x, prime, pc, aux);
-            v[k] = ct_prep<VAR>(x, bc, Map::kLazyIn);
-        }
-        ct_round_a<VAR>(v, tw, 0, 0, bc);
-        if constexpr (S > 4)
-        {
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                sm[(tt + T * k) * C + c] = v[k];
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                v[k] = sm[(16 * tt + k) * C + c];
-            ct_round_b<S, VAR>(v, tw, 0, 0, tt, bc);
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                out[(long long) (16 * tt + k) * 256 + col] = v[k]; // lazy, finished by the row pass
-        }
-        else
-        {
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                out[(long long) (tt + T * k) * 256 + col] = v[k];
-        }
-    }
-    else
-    {
-        // inverse: last pass of the transform, folds N^-1 into the last stage
-        const TwPair ninv = inv_last[2 * prime], wninv = inv_last[2 * prime + 1];
-        if constexpr (S > 4)
-        {
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                v[k] = in[(long long) (16 * tt + k) * 256 + col];
-            gs_round_b<S, VAR>(v, tw, 0, 0, tt, bc);
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                sm[(16 * tt + k) * C + c] = v[k];
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                v[k] = sm[(tt + T * k) * C + c];
-        }
-        else
-        {
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                v[k] = in[(long long) (tt + T * k) * 256 + col];
-        }
-        gs_round_a_final<VAR>(v, tw, bc, ninv, wninv);
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            out[(long long) (tt + T * k) * 256 + col] = v[k];
-    }
-}
-
-// NT threads per CTA: 256 (16 columns at N = 2^16, 32 KiB of transposition space) or 128 (8 columns).
-template <int S, bool INV, class Map, int NT = 256>
-__global__ void __launch_bounds__(NT, HEON_COL_MINBLOCKS * 256 / NT) ntt_col_pass(Map map, const TwPair* __restrict__ tw_all,
-                                                    const PrimeConst* __restrict__ pcs,
-                                                    const TwPair* __restrict__ inv_last, int logn,
-                                                    bool first_pass, int variant)
-{
-    constexpr int T = (1 << S) / 16;
-    constexpr int C = NT / T;
-    __shared__ u64 sm[(S > 4) ? (1 << S) * C : 1];
-    const int tiles = 256 / C;
-    long long z = blockIdx.x / tiles;
-    int tile = blockIdx.x % tiles;
-    const u64* in;
-    u64* out;
-    int prime, aux;
-    map.get(z, in, out, prime, aux);
-    if (!first_pass)
-        in = out;
-    const PrimeConst pc = pcs[prime];
-    const TwPair* tw = tw_all + ((long long) prime << logn);
-    if (pc.fp_var == 3)
-        col_pass_body<S, INV, 3, Map, NT>(map, in, out, prime, pc, tw, inv_last, tile, first_pass, aux, sm);
-    else if (pc.fp_var == 4)
-        col_pass_body<S, INV, 4, Map, NT>(map, in, out, prime, pc, tw, inv_last, tile, first_pass, aux, sm);
-    else if (INV || variant == 1 || !pc.nc_ok)
-        col_pass_body<S, INV, 1, Map, NT>(map, in, out, prime, pc, tw, inv_last, tile, first_pass, aux, sm);
-    else
-        col_pass_body<S, INV, 2, Map, NT>(map, in, out, prime, pc, tw, inv_last, tile, first_pass, aux, sm);
-}
-
-// Row pass: the 8 stages that live inside one 256-word row.  16 threads per
-// row, 16 rows per CTA.  S1 = n - 8 is the number of column-pass stages.
-template <bool INV, int VAR>
-__device__ __forceinline__ void row_pass_body(const u64* rin, u64* rout, const PrimeConst& pc,
-                                              const TwPair* __restrict__ tw, int S1, int r, int tt,
-                                              u64* srow)
-{
-    const BflyConst bc = make_bc(pc);
-    u64 v[16];
-    if constexpr (!INV)
-    {
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            v[k] = rin[tt + 16 * k];
-        ct_round_a<VAR, 1>(v, tw, S1, r, bc);
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            srow[tt + 18 * k] = v[k];
-        __syncwarp(); // a row lives in one half-warp: the transpose is warp-local
-#pragma unroll
-        for (int k = 0; k < 16; k += 2)
-        {
-            ulonglong2 t2 = *reinterpret_cast<const ulonglong2*>(srow + 18 * tt + k);
-            v[k] = t2.x;
-            v[k + 1] = t2.y;
-        }
-        ct_round_b<8, VAR, 1>(v, tw, S1, r, tt, bc);
-#pragma unroll
-        for (int k = 0; k < 16; k += 2)
-        {
-            ulonglong2 t2;
-            t2.x = ct_finish<VAR>(v[k], bc, pc);
-            t2.y = ct_finish<VAR>(v[k + 1], bc, pc);
-            *reinterpret_cast<ulonglong2*>(rout + 16 * tt + k) = t2;
-        }
-    }
-    else
-    {
-#pragma unroll
-        for (int k = 0; k < 16; k += 2)
-        {
-            ulonglong2 t2 = *reinterpret_cast<const ulonglong2*>(rin + 16 * tt + k);
-            v[k] = gs_prep<VAR>(t2.x);
-            v[k + 1] = gs_prep<VAR>(t2.y);
-        }
-        gs_round_b<8, VAR>(v, tw, S1, r, tt, bc);
-#pragma unroll
-        for (int k = 0; k < 16; k += 2)
-        {
-            ulonglong2 t2;
-            t2.x = v[k];
-            t2.y = v[k + 1];
-            *reinterpret_cast<ulonglong2*>(srow + 18 * tt + k) = t2;
-        }
-        __syncwarp(); // a row lives in one half-warp: the transpose is warp-local
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            v[k] = srow[tt + 18 * k];
-        gs_round_a<VAR>(v, tw, S1, r, bc);
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            rout[tt + 16 * k] = v[k]; // lazy, finished by the column pass
-    }
-}
-
-template <bool INV, class Map>
-__global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS) ntt_row_pass(Map map, const TwPair* __restrict__ tw_all,
-                                                    const PrimeConst* __restrict__ pcs, int logn,
-                                                    bool first_pass, int variant)
-{
-    constexpr int PITCH = 288; // 256 + 2 words of padding per 16
-    __shared__ __align__(16) u64 sm[16 * PITCH];
-    const int S1 = logn - 8;
-    const int tiles = (1 << S1) / 16;
-    long long z = blockIdx.x / tiles;
-    int tile = blockIdx.x % tiles;
-    const u64* in;
-    u64* out;
-    int prime, aux;
-    map.get(z, in, out, prime, aux);
-    if (!first_pass)
-        in = out;
-    const PrimeConst pc = pcs[prime];
-    const TwPair* tw = tw_all + ((long long) prime << logn);
-    const int tt = threadIdx.x & 15;
-    const int rl = threadIdx.x >> 4;
-    const int r = tile * 16 + rl;
-    const u64* rin = in + (long long) r * 256;
-    u64* rout = out + (long long) r * 256;
-    u64* srow = sm + rl * PITCH;
-    if (pc.fp_var == 3)
-        row_pass_body<INV, 3>(rin, rout, pc, tw, S1, r, tt, srow);
-    else if (pc.fp_var == 4)
-        row_pass_body<INV, 4>(rin, rout, pc, tw, S1, r, tt, srow);
-    else if (INV || variant == 1 || !pc.nc_ok)
-        row_pass_body<INV, 1>(rin, rout, pc, tw, S1, r, tt, srow);
-    else
-        row_pass_body<INV, 2>(rin, rout, pc, tw, S1, r, tt, srow);
-}
-
-// ---------------------------------------------------------------------------
-// Row pass through TMA.  One CTA owns a tile of 16 rows (256 lines of 128 B,
-// 32 KiB).  A 2-D tensor map over "lines of sixteen 64-bit words" brings the
-// tile into shared memory with the 128-byte swizzle (UTMALDG), the threads
-// run the eight stages out of registers with ONE in-place, warp-local,
-// bank-conflict-free transpose, and the canonical result leaves through the
-// same swizzled buffer with a TMA store (UTMASTG).  The load/store unit only
-// sees shared-memory traffic and coalesced twiddle reads.
-//
-// Swizzled position of element e of line l of a row (row base 2 KiB aligned):
-//   byte = l*128 + ((e>>1) ^ (l&7))*16 + (e&1)*8
-// Round A (idx = tt + 16k) touches element tt of line k: a permutation inside
-// one 128-byte line -> conflict free.  Round B (idx = 16tt + k) touches the
-// eight 16-byte chunks of line tt at chunk positions c ^ (tt&7) -> the eight
-// lanes of a quarter warp hit eight different bank groups.
-// ---------------------------------------------------------------------------
-constexpr int kRowTileBytes = 16 * 2048;
-
-// Forward row stages on one swizzled row: loads the thread's 16 words in the round-A layout, runs the
-// eight stages with the in-place warp-local transpose, and leaves the LAZY results in registers in the
-// round-B layout (v[2c], v[2c+1] = 16-byte chunk c of line tt).
-template <int VAR>
-__device__ __forceinline__ void row_fwd_stages(unsigned char* rowp, const BflyConst& bc, const TwPair* __restrict__ tw,
-                                               const TwPair* __restrict__ blk, int S1, int r, int tt,
-                                               const double* rowtw, u64 (&v)[16])
-{
-    unsigned char* lineB = rowp + tt * 128;
-    const int sw = tt & 7;
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        v[k] = *reinterpret_cast<const u64*>(rowp + k * 128 + ((((tt >> 1) ^ (k & 7)) << 4) | ((tt & 1) << 3)));
-    if ((VAR == 3 || VAR == 4) && rowtw)
-        ct_round_a_sm<VAR>(v, rowtw, bc);
-    else
-        ct_round_a<VAR, 1>(v, tw, S1, r, bc);
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        *reinterpret_cast<u64*>(rowp + k * 128 + ((((tt >> 1) ^ (k & 7)) << 4) | ((tt & 1) << 3))) = v[k];
-    __syncwarp();
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-    {
-        const ulonglong2 t2 = *reinterpret_cast<const ulonglong2*>(lineB + ((c ^ sw) << 4));
-        v[2 * c] = t2.x;
-        v[2 * c + 1] = t2.y;
-    }
-    if ((VAR == 3 || VAR == 4) && rowtw)
-        ct_round_b_sm<VAR>(v, rowtw, tt, bc);
-    else
-        ct_round_b_lm<VAR, 1>(v, blk, tt, bc);
-}
-
-template <bool INV, int VAR>
-__device__ __forceinline__ void row_pass_tma_body(unsigned char* rowp, const PrimeConst& pc,
-                                                  const TwPair* __restrict__ tw,
-                                                  const TwPair* __restrict__ blk, int S1, int r, int tt,
-                                                  const double* rowtw)
-{
-    const BflyConst bc = make_bc(pc);
-    u64 v[16];
-    unsigned char* lineB = rowp + tt * 128;
-    const int sw = tt & 7;
-    if constexpr (!INV)
-    {
-        row_fwd_stages<VAR>(rowp, bc, tw, blk, S1, r, tt, rowtw, v);
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-        {
-            ulonglong2 t2;
-            t2.x = ct_finish<VAR>(v[2 * c], bc, pc);
-            t2.y = ct_finish<VAR>(v[2 * c + 1], bc, pc);
-            *reinterpret_cast<ulonglong2*>(lineB + ((c ^ sw) << 4)) = t2;
-        }
-    }
-    else
-    {
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-        {
-            const ulonglong2 t2 = *reinterpret_cast<const ulonglong2*>(lineB + ((c ^ sw) << 4));
-            v[2 * c] = gs_prep<VAR>(t2.x);
-            v[2 * c + 1] = gs_prep<VAR>(t2.y);
-        }
-        gs_round_b_lm<VAR>(v, blk, tt, bc);
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-        {
-            ulonglong2 t2;
-            t2.x = v[2 * c];
-            t2.y = v[2 * c + 1];
-            *reinterpret_cast<ulonglong2*>(lineB + ((c ^ sw) << 4)) = t2;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            v[k] = *reinterpret_cast<const u64*>(rowp + k * 128 + ((((tt >> 1) ^ (k & 7)) << 4) | ((tt & 1) << 3)));
-        gs_round_a<VAR>(v, tw, S1, r, bc);
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            *reinterpret_cast<u64*>(rowp + k * 128 + ((((tt >> 1) ^ (k & 7)) << 4) | ((tt & 1) << 3))) = v[k]; // lazy
-    }
-}
-
-// Persistent form: the grid is a few CTAs per SM; each CTA walks tiles
-// blockIdx.x, blockIdx.x + gridDim.x, ... with two shared-memory buffers, so the
-// TMA load of tile i+1 and the TMA store of tile i-1 overlap the arithmetic of
-// tile i (the pass is otherwise a load -> compute -> store chain whose memory
-// time and multiplier-pipe time add up instead of overlapping).
-// ROWS rows per CTA (16 threads each): 16 -> 32 KiB tiles, 3 CTAs/SM; 8 -> 16 KiB tiles, 6 CTAs/SM.
-template <bool INV, class Map, int ROWS>
-__global__ void __launch_bounds__(ROWS * 16, HEON_NTT_MINBLOCKS * 16 / ROWS)
-    ntt_row_pass_tma(Map map, const __grid_constant__ CUtensorMap tm_in,
-                     const __grid_constant__ CUtensorMap tm_out, const u64* in_base, const u64* out_base,
-                     const TwPair* __restrict__ tw_all, const TwPair* __restrict__ rowb_all,
-                     const PrimeConst* __restrict__ pcs, int logn, bool first_pass, int variant,
-                     long long n_tiles, const double* __restrict__ rowc_all)
-{
-    extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar[2];
-    // 1024-byte alignment for the 128B swizzle; plain offset arithmetic keeps the
-    // pointer in the shared address space (LDS/STS instead of generic LD/ST)
-    unsigned char* buf0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int S1 = logn - 8;
-    const int tiles = (1 << S1) / ROWS;
-    constexpr int kTileBytes = ROWS * 2048;
-    const CUtensorMap* tmi = first_pass ? &tm_in : &tm_out;
-    if (!first_pass)
-        in_base = out_base;
-    const int tt = threadIdx.x & 15;
-    const int rl = threadIdx.x >> 4;
-
-    auto tile_lines = [&](long long t, int& line_in, int& line_out, int& prime, int& tile_idx) {
-        const long long z = t / tiles;
-        tile_idx = (int) (t % tiles);
-        const u64* in;
-        u64* out;
-        int aux;
-        map.get(z, in, out, prime, aux);
-        if (!first_pass)
-            in = out;
-        line_in = (int) ((in - in_base) >> 4) + tile_idx * (ROWS * 16);
-        line_out = (int) ((out - out_base) >> 4) + tile_idx * (ROWS * 16);
-    };
-
-    if (threadIdx.x == 0)
-    {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    long long t = blockIdx.x;
-    // one tile per CTA (rowc_all != nullptr): the second buffer receives the tile's FP64
-    // twiddles (32 KiB, contiguous) through the same barrier
-    if (threadIdx.x == 0 && t < n_tiles)
-    {
-        int li, lo, pr, ti;
-        tile_lines(t, li, lo, pr, ti);
-        const bool twsm = !INV && rowc_all && pcs[pr].fp_var != 0;
-        mbar_arrive_expect_tx(&bar[0], twsm ? 2 * kTileBytes : kTileBytes);
-        tma_load_2d(buf0, tmi, &bar[0], 0, li);
-        if (twsm)
-            tma_load_1d(buf0 + kTileBytes, rowc_all + ((((long long) pr << S1) + ti * ROWS) << 8), kTileBytes,
-                        &bar[0]);
-    }
-    for (int it = 0; t < n_tiles; ++it, t += gridDim.x)
-    {
-        const int b = it & 1;
-        unsigned char* tile = buf0 + b * kTileBytes;
-        if (threadIdx.x == 0)
-        {
-            // the other buffer was handed to a TMA store one iteration ago: wait until that
-            // store has finished reading it, then prefetch the next tile into it
-            tma_store_wait_read<0>();
-            const long long tn = t + gridDim.x;
-            if (tn < n_tiles)
-            {
-                int li, lo, pr, ti;
-                tile_lines(tn, li, lo, pr, ti);
-                mbar_arrive_expect_tx(&bar[b ^ 1], kTileBytes);
-                tma_load_2d(buf0 + (b ^ 1) * kTileBytes, tmi, &bar[b ^ 1], 0, li);
-            }
-        }
-        int line_in, line_out, prime, tile_idx;
-        tile_lines(t, line_in, line_out, prime, tile_idx);
-        const PrimeConst pc = pcs[prime];
-        const TwPair* tw = tw_all + ((long long) prime << logn);
-        const int r = tile_idx * ROWS + rl;
-        const TwPair* blk = rowb_all + ((((long long) prime << S1) + r) << 8);
-        unsigned char* rowp = tile + rl * 2048;
-        const double* rowtw =
-            rowc_all ? reinterpret_cast<const double*>(buf0 + kTileBytes) + rl * 256 : nullptr;
-        mbar_wait(&bar[b], (it >> 1) & 1);
-
-        if (pc.fp_var == 3)
-            row_pass_tma_body<INV, 3>(rowp, pc, tw, blk, S1, r, tt, rowtw);
-        else if (pc.fp_var == 4)
-            row_pass_tma_body<INV, 4>(rowp, pc, tw, blk, S1, r, tt, rowtw);
-        else if (INV || variant == 1 || !pc.nc_ok)
-            row_pass_tma_body<INV, 1>(rowp, pc, tw, blk, S1, r, tt, nullptr);
-        else
-            row_pass_tma_body<INV, 2>(rowp, pc, tw, blk, S1, r, tt, nullptr);
-
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (threadIdx.x == 0)
-        {
-            tma_store_2d(&tm_out, tile, 0, line_out);
-            tma_store_commit();
-        }
-    }
-    if (threadIdx.x == 0)
-        tma_store_wait_read<0>();
-}
-
-
-// ---------------------------------------------------------------------------
-// Fused forward transform: ONE persistent kernel runs the column tiles and the
-// row tiles of the whole batch.  CTAs draw tickets in order; the ticket stream
-// is  col(g0) col(g1) row(g0) col(g2) row(g1) ...  over groups of `G`
-// polynomials, so the column-pass output of a group (lazy words, written in
-// place into the destination) is still in L2 when its row tiles read it and
-// the transform costs one DRAM read and one DRAM write per word instead of
-// two of each.  A row tile waits on a per-polynomial counter of finished
-// column tiles (release/acquire at GPU scope); tickets are handed out in order
-// and column tickets of a group precede its row tickets, so every CTA a
-// waiter depends on is already running: no deadlock.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ int ld_acquire_gpu(const int* p)
-{
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-template <int S, class Map>
-__global__ void __launch_bounds__(256, HEON_NTT_MINBLOCKS)
-    ntt_fwd_fused(Map map, const __grid_constant__ CUtensorMap tm_out, const u64* out_base,
-                  const TwPair* __restrict__ tw_all, const TwPair* __restrict__ rowb_all,
-                  const double* __restrict__ rowc_all, const PrimeConst* __restrict__ pcs,
-                  const TwPair* __restrict__ inv_last, int variant, long long n_polys, int G, int* sync)
-{
-    extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ long long s_ticket;
-    constexpr int logn = S + 8;
-    constexpr int tiles = (1 << S) / 16; // tiles per polynomial, both passes
-    unsigned char* buf0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const long long seg = (long long) G * tiles; // tickets per segment
-    const long long n_groups = (n_polys + G - 1) / G;
-    const long long n_tickets = (2 * n_groups + 1) * seg; // col(0) + pairs {col(k), row(k-1)}, k = 1..n_groups
-    int* ticket = sync;
-    int* done = sync + 1;
-    const int tt = threadIdx.x & 15;
-    const int rl = threadIdx.x >> 4;
-    unsigned phase = 0;
-
-    if (threadIdx.x == 0)
-    {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    for (;;)
-    {
-        if (threadIdx.x == 0)
-        {
-            tma_store_wait_read<0>(); // the previous row tile has left shared memory
-            s_ticket = atomicAdd(ticket, 1);
-        }
-        __syncthreads();
-        const long long t = s_ticket;
-        __syncthreads();
-        if (t >= n_tickets)
-            break;
-        // segment s: 0 -> col(0); odd s -> col((s+1)/2); even s >= 2 -> row(s/2 - 1)
-        const long long sgm = t / seg;
-        const int w = (int) (t % seg);
-        const bool is_row = sgm >= 2 && (sgm & 1) == 0;
-        const long long g = sgm == 0 ? 0 : is_row ? sgm / 2 - 1 : (sgm + 1) / 2;
-        const long long z = g * G + w / tiles;
-        const int tile = w % tiles;
-        if (g >= n_groups || z >= n_polys)
-            continue;
-        const u64* in;
-        u64* out;
-        int prime, aux;
-        map.get(z, in, out, prime, aux);
-        const PrimeConst pc = pcs[prime];
-        const TwPair* tw = tw_all + ((long long) prime << logn);
-        if (!is_row)
-        {
-            u64* sm = reinterpret_cast<u64*>(buf0);
-            if (pc.fp_var == 3)
-                col_pass_body<S, false, 3>(map, in, out, prime, pc, tw, inv_last, tile, true, aux, sm);
-            else if (pc.fp_var == 4)
-                col_pass_body<S, false, 4>(map, in, out, prime, pc, tw, inv_last, tile, true, aux, sm);
-            else if (variant == 1 || !pc.nc_ok)
-                col_pass_body<S, false, 1>(map, in, out, prime, pc, tw, inv_last, tile, true, aux, sm);
-            else
-                col_pass_body<S, false, 2>(map, in, out, prime, pc, tw, inv_last, tile, true, aux, sm);
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0)
-                atomicAdd(done + z, 1);
-        }
-        else
-        {
-            const bool twsm = rowc_all && pc.fp_var != 0;
-            if (threadIdx.x == 0)
-            {
-                while (ld_acquire_gpu(done + z) < tiles)
-                    __nanosleep(64);
-                fence_proxy_async_all(); // generic-proxy writes of other CTAs -> this CTA's TMA read
-                const int line = (int) ((out - out_base) >> 4) + tile * 256;
-                mbar_arrive_expect_tx(&bar, twsm ? 2 * kRowTileBytes : kRowTileBytes);
-                tma_load_2d(buf0, &tm_out, &bar, 0, line);
-                if (twsm)
-                    tma_load_1d(buf0 + kRowTileBytes, rowc_all + ((((long long) prime << S) + tile * 16) << 8),
-                                kRowTileBytes, &bar);
-            }
-            const int r = tile * 16 + rl;
-            const TwPair* blk = rowb_all + ((((long long) prime << S) + r) << 8);
-            unsigned char* rowp = buf0 + rl * 2048;
-            const double* rowtw = twsm ? reinterpret_cast<const double*>(buf0 + kRowTileBytes) + rl * 256 : nullptr;
-            mbar_wait(&bar, phase & 1);
-            ++phase;
-            if (pc.fp_var == 3)
-                row_pass_tma_body<false, 3>(rowp, pc, tw, blk, S, r, tt, rowtw);
-            else if (pc.fp_var == 4)
-                row_pass_tma_body<false, 4>(rowp, pc, tw, blk, S, r, tt, rowtw);
-            else if (variant == 1 || !pc.nc_ok)
-                row_pass_tma_body<false, 1>(rowp, pc, tw, blk, S, r, tt, nullptr);
-            else
-                row_pass_tma_body<false, 2>(rowp, pc, tw, blk, S, r, tt, nullptr);
-            fence_proxy_async_smem();
-            __syncthreads();
-            if (threadIdx.x == 0)
-            {
-                const int line = (int) ((out - out_base) >> 4) + tile * 256;
-                tma_store_2d(&tm_out, buf0, 0, line);
-                tma_store_commit();
-            }
-        }
-    }
-    if (threadIdx.x == 0)
-        tma_store_wait_read<0>();
-}
-
-
-// ---------------------------------------------------------------------------
-// Pipelined fused forward transform for N = 2^16 (the BASELINE ring size).
-//
-// One persistent CTA per SM, warp-specialised:
-//   warp 0  producer : walks the ticket stream, issues the TMA load of every tile into a ring
-//                      of kPipeStages 32 KiB shared-memory stages (full[] barriers);
-//   warp 1  storer   : waits until a stage has been computed (comp[]), issues its TMA store,
-//                      frees the stage (empty[]) and publishes finished column tiles;
-//   2 x 8 consumer warps: two groups of 256 threads, each transforming one tile at a time out
-//                      of registers, reading and writing the stage in place.
-// Loads, stores and arithmetic of different tiles overlap freely; nothing on the arithmetic
-// path waits for DRAM.  The ticket stream is  col(g0) col(g1) row(g0) col(g2) row(g1) ...  over
-// groups of G polynomials (tickets are dealt round-robin to the CTAs), so the column-pass output
-// of a group is still in L2 when its row tiles read it back: one DRAM read and one DRAM write
-// per word.  The producer holds a row tile back until the 16 column tiles of its polynomial have
-// been stored (per-polynomial counter, release/acquire at GPU scope).  The smallest unfinished
-// ticket only depends on smaller tickets, so the scheme cannot deadlock.
-//
-// Column tile: 16 columns x 256 rows through a 3-D tensor map {16 words, 16 lines, rows} with
-// box {16, 1, 256}; row tile: 16 rows = 256 consecutive 128-byte lines (2-D map); both land with
-// the 128-byte swizzle, element e of line l at  l*128 + ((e>>1) ^ (l&7))*16 + (e&1)*8.
-// ---------------------------------------------------------------------------
-constexpr int kPipeStages = 6;
-constexpr int kPipeGroups = 2;
-constexpr int kPipeThreads = 64 + 256 * kPipeGroups;
-
-template <int VAR, class Map>
-__device__ __forceinline__ void pipe_col_tile(unsigned char* tile, const Map& map, int prime, const PrimeConst& pc,
-                                              const TwPair* __restrict__ tw, int aux, int tid, int bar_id)
-{
-    const BflyConst bc = make_bc(pc);
-    const int c = tid & 15, tt = tid >> 4;
-    u64 v[16];
-    unsigned char* pa = tile + tt * 128 + ((((c >> 1) ^ (tt & 7)) << 4) | ((c & 1) << 3)); // rows tt + 16k
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-    {
-        u64 x = *reinterpret_cast<const u64*>(pa + k * 2048);
-        if (Map::kXform)
-            x = map.xform(x, prime, pc, aux);
-        v[k] = ct_prep<VAR>(x, bc, Map::kLazyIn);
-    }
-    ct_round_a<VAR>(v, tw, 0, 0, bc);
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        *reinterpret_cast<u64*>(pa + k * 2048) = v[k];
-    named_bar_sync(bar_id, 256);
-    unsigned char* pb = tile + tt * 2048 + ((c & 1) << 3); // rows 16*tt + k
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        v[k] = *reinterpret_cast<const u64*>(pb + k * 128 + (((c >> 1) ^ (k & 7)) << 4));
-    ct_round_b<8, VAR>(v, tw, 0, 0, tt, bc);
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        *reinterpret_cast<u64*>(pb + k * 128 + (((c >> 1) ^ (k & 7)) << 4)) = v[k]; // lazy, finished by the row tile
-}
-
-// FP64 row tile: the thread's 15 last-four-stage twiddles (bare doubles, compact table) are
-// requested before the first four stages run, so their L2 latency hides behind arithmetic.
-template <int VAR>
-__device__ __forceinline__ void pipe_row_tile_fp(unsigned char* rowp, const PrimeConst& pc,
-                                                 const double* __restrict__ rowc, int tt)
-{
-    const BflyConst bc = make_bc(pc);
-    double twb[15];
-#pragma unroll
-    for (int e = 0; e < 15; ++e)
-        twb[e] = __ldg(rowc + 16 + e * 16 + tt);
-    double twa[15];
-#pragma unroll
-    for (int e = 0; e < 15; ++e)
-        twa[e] = __ldg(rowc + e);
-    u64 v[16];
-    unsigned char* lineB = rowp + tt * 128;
-    const int sw = tt & 7;
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        v[k] = *reinterpret_cast<const u64*>(rowp + k * 128 + ((((tt >> 1) ^ (k & 7)) << 4) | ((tt & 1) << 3)));
-    ct_round_a_sm<VAR>(v, twa, bc);
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        *reinterpret_cast<u64*>(rowp + k * 128 + ((((tt >> 1) ^ (k & 7)) << 4) | ((tt & 1) << 3))) = v[k];
-    __syncwarp();
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-    {
-        const ulonglong2 t2 = *reinterpret_cast<const ulonglong2*>(lineB + ((c ^ sw) << 4));
-        v[2 * c] = t2.x;
-        v[2 * c + 1] = t2.y;
-    }
-    ct_round_a_sm<VAR>(v, twb, bc);
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-    {
-        ulonglong2 t2;
-        t2.x = ct_finish<VAR>(v[2 * c], bc, pc);
-        t2.y = ct_finish<VAR>(v[2 * c + 1], bc, pc);
-        *reinterpret_cast<ulonglong2*>(lineB + ((c ^ sw) << 4)) = t2;
-    }
-}
-
-struct PipeTicket {
-    long long z;
-    int tile;
-    bool is_row, valid, end;
-};
-
-// ticket -> work item (segment s: 0 -> col(0); odd s -> col((s+1)/2); even s >= 2 -> row(s/2 - 1))
-__device__ __forceinline__ PipeTicket pipe_decode(long long t, long long n_polys, int G, long long n_groups)
-{
-    PipeTicket r;
-    const long long seg = (long long) G * 16;
-    r.end = t >= (2 * n_groups + 1) * seg;
-    const long long sgm = t / seg;
-    const int w = (int) (t % seg);
-    r.is_row = sgm >= 2 && (sgm & 1) == 0;
-    const long long g = sgm == 0 ? 0 : r.is_row ? sgm / 2 - 1 : (sgm + 1) / 2;
-    r.z = g * G + w / 16;
-    r.tile = w % 16;
-    r.valid = !r.end && g < n_groups && r.z < n_polys;
-    return r;
-}
-
-template <class Map>
-__global__ void __launch_bounds__(kPipeThreads, 1)
-    ntt16_fwd_pipe(Map map, const __grid_constant__ CUtensorMap tm_in_col,
-                   const __grid_constant__ CUtensorMap tm_out_col,
-                   const __grid_constant__ CUtensorMap tm_out_row, const u64* in_base, const u64* out_base,
-                   const TwPair* __restrict__ tw_all, const TwPair* __restrict__ rowb_all,
-                   const double* __restrict__ rowc_all, const PrimeConst* __restrict__ pcs, int variant,
-                   long long n_polys, int G, int* done)
-{
-    extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full[kPipeStages], comp[kPipeStages], empty[kPipeStages];
-    __shared__ long long item[kPipeStages];
-    unsigned char* buf0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    constexpr int logn = 16, S = 8;
-    const long long n_groups = (n_polys + G - 1) / G;
-    const int warp = threadIdx.x >> 5;
-
-    if (threadIdx.x == 0)
-    {
-        for (int s = 0; s < kPipeStages; ++s)
-        {
-            mbar_init(&full[s], 1);
-            mbar_init(&comp[s], 256);
-            mbar_init(&empty[s], 1);
-        }
-        fence_mbar_init();
-    }
-    __syncthreads();
-
-    if (warp == 0)
-    {
-        // ---------------- producer ----------------
-        if (threadIdx.x != 0)
-            return;
-        long long t = blockIdx.x;
-        int sentinels = 0;
-        for (long long i = 0;; ++i)
-        {
-            const int s = (int) (i % kPipeStages);
-            if (i >= kPipeStages)
-                mbar_wait(&empty[s], (unsigned) ((i / kPipeStages - 1) & 1));
-            PipeTicket k = pipe_decode(t, n_polys, G, n_groups);
-            while (!k.end && !k.valid)
-            {
-                t += gridDim.x;
-                k = pipe_decode(t, n_polys, G, n_groups);
-            }
-            if (k.end)
-            {
-                item[s] = -1;
-                mbar_arrive(&full[s]);
-                if (++sentinels == kPipeGroups)
-                    break;
-                continue;
-            }
-            t += gridDim.x;
-            item[s] = (k.z << 8) | (k.tile << 1) | (k.is_row ? 1 : 0);
-            const u64* in;
-            u64* out;
-            int prime, aux;
-            map.get(k.z, in, out, prime, aux);
-            unsigned char* stage = buf0 + s * kRowTileBytes;
-            if (k.is_row)
-            {
-                while (ld_acquire_gpu(done + k.z) < 16)
-                    __nanosleep(32);
-                fence_proxy_async_all(); // other CTAs' tile stores -> this CTA's TMA read
-                mbar_arrive_expect_tx(&full[s], kRowTileBytes);
-                tma_load_2d(stage, &tm_out_row, &full[s], 0, (int) ((out - out_base) >> 4) + k.tile * 256);
-            }
-            else
-            {
-                mbar_arrive_expect_tx(&full[s], kRowTileBytes);
-                tma_load_3d(stage, &tm_in_col, &full[s], 0, k.tile, (int) ((in - in_base) >> 8));
-            }
-        }
-        return;
-    }
-    if (warp == 1)
-    {
-        // ---------------- storer ----------------
-        if (threadIdx.x != 32)
-            return;
-        long long pend[3] = {-1, -1, -1};
-        int sentinels = 0;
-        long long n_store = 0;
-        auto publish = [&](long long z) {
-            if (z >= 0)
-            {
-                fence_proxy_async_all();
-                __threadfence();
-                atomicAdd(done + z, 1);
-            }
-        };
-        for (long long i = 0;; ++i)
-        {
-            const int s = (int) (i % kPipeStages);
-            if (!mbar_test(&comp[s], (unsigned) ((i / kPipeStages) & 1)))
-            {
-                // nothing to store right now: finish the stores in flight and publish their column
-                // tiles (a row tile somewhere may be waiting for exactly these), then block
-                tma_store_wait_all<0>();
-                for (int j = 0; j < 3; ++j)
-                {
-                    publish(pend[j]);
-                    pend[j] = -1;
-                }
-                mbar_wait(&comp[s], (unsigned) ((i / kPipeStages) & 1));
-            }
-            const long long it = item[s];
-            if (it < 0)
-            {
-                if (++sentinels == kPipeGroups)
-                    break;
-                continue;
-            }
-            const long long z = it >> 8;
-            const int tile = (int) ((it >> 1) & 127);
-            const bool is_row = it & 1;
-            const u64* in;
-            u64* out;
-            int prime, aux;
-            map.get(z, in, out, prime, aux);
-            unsigned char* stage = buf0 + s * kRowTileBytes;
-            if (is_row)
-                tma_store_2d(&tm_out_row, stage, 0, (int) ((out - out_base) >> 4) + tile * 256);
-            else
-                tma_store_3d(&tm_out_col, stage, 0, tile, (int) ((out - out_base) >> 8));
-            tma_store_commit();
-            tma_store_wait_read<0>();
-            mbar_arrive(&empty[s]);
-            // stores older than the two most recent ones are complete: publish their column tiles
-            tma_store_wait_all<2>();
-            publish(pend[n_store % 3]);
-            pend[n_store % 3] = is_row ? -1 : z;
-            ++n_store;
-        }
-        tma_store_wait_all<0>();
-        for (int j = 0; j < 3; ++j)
-            publish(pend[j]);
-        return;
-    }
-    // ---------------- consumers ----------------
-    const int grp = (threadIdx.x - 64) >> 8;
-    const int tid = (threadIdx.x - 64) & 255;
-    for (long long i = grp;; i += kPipeGroups)
-    {
-        const int s = (int) (i % kPipeStages);
-        mbar_wait(&full[s], (unsigned) ((i / kPipeStages) & 1));
-        const long long it = item[s];
-        if (it < 0)
-        {
-            mbar_arrive(&comp[s]);
-            break;
-        }
-        const long long z = it >> 8;
-        const int tile = (int) ((it >> 1) & 127);
-        const bool is_row = it & 1;
-        const u64* in;
-        u64* out;
-        int prime, aux;
-        map.get(z, in, out, prime, aux);
-        const PrimeConst pc = pcs[prime];
-        const TwPair* tw = tw_all + ((long long) prime << logn);
-        unsigned char* stage = buf0 + s * kRowTileBytes;
-        if (!is_row)
-        {
-            if (pc.fp_var == 3)
-                pipe_col_tile<3>(stage, map, prime, pc, tw, aux, tid, 1 + grp);
-            else if (pc.fp_var == 4)
-                pipe_col_tile<4>(stage, map, prime, pc, tw, aux, tid, 1 + grp);
-            else if (variant == 1 || !pc.nc_ok)
-                pipe_col_tile<1>(stage, map, prime, pc, tw, aux, tid, 1 + grp);
-            else
-                pipe_col_tile<2>(stage, map, prime, pc, tw, aux, tid, 1 + grp);
-        }
-        else
-        {
-            const int tt = tid & 15, rl = tid >> 4;
-            const int r = tile * 16 + rl;
-            unsigned char* rowp = stage + rl * 2048;
-            if (pc.fp_var == 3)
-                pipe_row_tile_fp<3>(rowp, pc, rowc_all + ((((long long) prime << S) + r) << 8), tt);
-            else if (pc.fp_var == 4)
-                pipe_row_tile_fp<4>(rowp, pc, rowc_all + ((((long long) prime << S) + r) << 8), tt);
-            else
-            {
-                const TwPair* blk = rowb_all + ((((long long) prime << S) + r) << 8);
-                if (variant == 1 || !pc.nc_ok)
-                    row_pass_tma_body<false, 1>(rowp, pc, tw, blk, S, r, tt, nullptr);
-                else
-                    row_pass_tma_body<false, 2>(rowp, pc, tw, blk, S, r, tt, nullptr);
-            }
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(&comp[s]);
-    }
-}
-
-// ---------------------------------------------------------------------------
-// Key-switch inner product fused behind the forward row pass.
-//
-//   acc[b][c][y] = sum_i NTT(tmp[b][i][y]) (.) key[i][c][prime(y)]        (c = 0, 1)
-//
-// replaces  ntt_row_pass_tma (last eight stages of d*Q' transforms)  +  k_keyswitch_mac
-// (reference: the trailing kernel of GPU_NTT_Modulus_Ordered_Inplace, ntt.cu:3106-3255, followed by
-// keyswitch_multiply_accumulate_leveled[_method_II]_kernel, switchkey.cu:164-398).  One CTA owns
-// (ciphertext b, limb y, a tile of ROWS rows) and walks the d digits: the column-pass words of digit i
-// arrive by TMA (2-D tensor map, 128-byte swizzle), the eight row stages run out of registers, and the
-// finished words are multiplied into the two key tiles (brought in by TMA with the same swizzle, so the
-// register layout of the transform is also the conflict-free layout of the key read) and accumulated
-// in registers.  Only the two accumulator tiles are stored.  The transformed digits -- d*Q'*N words,
-// the largest buffer of the operator -- are never written back and never read again.
-//
-// Arithmetic (FP = true, primes below 2^50): the transform leaves integer-valued doubles x, |x| < 2^51;
-// a key word k < p becomes a double exactly, T = x*k mod p comes from fp_mulmod with the quotient
-// multiplier RN(k * RN(1/p)) (|T| <= p), and the terms are summed in one double per (coefficient,
-// component): exact while |sum| < 2^53, so the sum is reduced every `red_period` digits.  The final
-// word is canonical and equals the reference's per-term Barrett sum.  FP = false (58..61-bit primes):
-// canonical words, 128-bit lazy integer accumulation, one reduction per output.
-// The batch index is the fastest block coordinate: the CTAs that need the same key tiles run together
-// and share them through L2 (the key crosses HBM once per batch).
-// Digit-own limbs (Method II, see MapDigitSkip) hold canonical NTT-domain words already and skip the
-// stages.
-// ---------------------------------------------------------------------------
-struct OwnLimbs {
-    int d, own;
-    short I_loc[65], I_j[65];
-};
-struct LimbList {
-    unsigned char y[128];
-};
-
-template <bool FP, int ROWS>
-__global__ void __launch_bounds__(ROWS * 16, FP ? 24 / ROWS : 16 / ROWS)
-    k_row_mac(const __grid_constant__ CUtensorMap tm_tmp, const __grid_constant__ CUtensorMap tm_key,
-              const __grid_constant__ CUtensorMap tm_out, const TwPair* __restrict__ tw_all,
-              const TwPair* __restrict__ rowb_all, const double* __restrict__ rowc_all,
-              const PrimeConst* __restrict__ pcs, const LimbList limb_list, int logn, int L,
-              int Qpl, int Qp0, int depth, int variant, int red_period_lo, int red_period_hi, OwnLimbs own)
-{
-    extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar[2];
-    constexpr int T = ROWS * 2048;
-    unsigned char* buf0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char* sdata = buf0;
-    unsigned char* skey0 = buf0 + T;
-    unsigned char* skey1 = buf0 + 2 * T;
-    unsigned char* stw = buf0 + 3 * T;
-    const int S1 = logn - 8;
-    const int lpp = 1 << (logn - 4); // 128-byte lines per polynomial
-    const long long b = blockIdx.x;
-    const int tile_idx = blockIdx.y;
-    const int y = limb_list.y[blockIdx.z];
-    const int prime = level_prime(y, L, depth);
-    const PrimeConst pc = pcs[prime];
-    const BflyConst bc = make_bc(pc);
-    const int d = own.d;
-    const int tt = threadIdx.x & 15, rl = threadIdx.x >> 4;
-    const int r = tile_idx * ROWS + rl;
-    const int line0 = tile_idx * ROWS * 16;
-    auto dline = [&](int i) { return (int) (((b * d + i) * Qpl + y) * lpp) + line0; };
-    auto kline = [&](int i, int c) { return (int) ((((long long) i * 2 + c) * Qp0 + prime) * lpp) + line0; };
-
-    if (threadIdx.x == 0)
-    {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        mbar_arrive_expect_tx(&bar[0], FP ? 2 * T : T);
-        tma_load_2d(sdata, &tm_tmp, &bar[0], 0, dline(0));
-        if (FP)
-            tma_load_1d(stw, rowc_all + ((((long long) prime << S1) + tile_idx * ROWS) << 8), T, &bar[0]);
-        mbar_arrive_expect_tx(&bar[1], 2 * T);
-        tma_load_2d(skey0, &tm_key, &bar[1], 0, kline(0, 0));
-        tma_load_2d(skey1, &tm_key, &bar[1], 0, kline(0, 1));
-    }
-    const TwPair* tw = tw_all + ((long long) prime << logn);
-    const TwPair* blk = rowb_all + ((((long long) prime << S1) + r) << 8);
-    const double* rowtw = reinterpret_cast<const double*>(stw) + rl * 256;
-    unsigned char* rowp = sdata + rl * 2048;
-    const int sw = tt & 7;
-    const unsigned lineoff = rl * 2048 + tt * 128;
-
-    // accumulators: FP -> one double per (coefficient, component); integer -> 128 bits each
-    double fa0[FP ? 16 : 1], fa1[FP ? 16 : 1];
-    u64 il0[FP ? 1 : 16], ih0[FP ? 1 : 16], il1[FP ? 1 : 16], ih1[FP ? 1 : 16];
-    if constexpr (FP)
-    {
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            fa0[k] = fa1[k] = 0.0;
-    }
-    else
-    {
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            il0[k] = ih0[k] = il1[k] = ih1[k] = 0;
-    }
-    const int red_period = pc.fp_var == 3 ? red_period_lo : red_period_hi;
-    int since_red = 0;
-
-    for (int i = 0; i < d; ++i)
-    {
-        u64 v[16];
-        mbar_wait(&bar[0], i & 1);
-        const bool own_i = own.own && y < L && y >= own.I_loc[i] && y < own.I_loc[i] + own.I_j[i];
-        if (own_i)
-        {
-            // canonical NTT-domain words (stashed from the input): no stages
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-            {
-                const ulonglong2 t2 = *reinterpret_cast<const ulonglong2*>(sdata + lineoff + ((c ^ sw) << 4));
-                v[2 * c] = FP ? d2u(fp_from_u64(t2.x)) : t2.x;
-                v[2 * c + 1] = FP ? d2u(fp_from_u64(t2.y)) : t2.y;
-            }
-        }
-        else if constexpr (FP)
-        {
-            if (pc.fp_var == 3)
-                row_fwd_stages<3>(rowp, bc, tw, blk, S1, r, tt, rowtw, v);
-            else
-                row_fwd_stages<4>(rowp, bc, tw, blk, S1, r, tt, rowtw, v);
-        }
-        else
-        {
-            if (variant == 1 || !pc.nc_ok)
-            {
-                row_fwd_stages<1>(rowp, bc, tw, blk, S1, r, tt, nullptr, v);
-#pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    v[k] = ct_finish<1>(v[k], bc, pc);
-            }
-            else
-            {
-                row_fwd_stages<2>(rowp, bc, tw, blk, S1, r, tt, nullptr, v);
-#pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    v[k] = ct_finish<2>(v[k], bc, pc);
-            }
-        }
-        // every warp holds its words in registers: the data tile can take the next digit
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (threadIdx.x == 0 && i + 1 < d)
-        {
-            mbar_arrive_expect_tx(&bar[0], T);
-            tma_load_2d(sdata, &tm_tmp, &bar[0], 0, dline(i + 1));
-        }
-        mbar_wait(&bar[1], i & 1);
-        if constexpr (FP)
-        {
-            const double pinv = bc.dpinv, dnp = bc.dnp;
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-            {
-                const ulonglong2 k0 = *reinterpret_cast<const ulonglong2*>(skey0 + lineoff + ((c ^ sw) << 4));
-                const ulonglong2 k1 = *reinterpret_cast<const ulonglong2*>(skey1 + lineoff + ((c ^ sw) << 4));
-                const double x0 = u2d(v[2 * c]), x1 = u2d(v[2 * c + 1]);
-                const double a0 = fp_from_u64(k0.x), a1 = fp_from_u64(k0.y);
-                const double b0 = fp_from_u64(k1.x), b1 = fp_from_u64(k1.y);
-                fa0[2 * c] = __dadd_rn(fa0[2 * c], fp_mulmod(x0, a0, __dmul_rn(a0, pinv), dnp));
-                fa0[2 * c + 1] = __dadd_rn(fa0[2 * c + 1], fp_mulmod(x1, a1, __dmul_rn(a1, pinv), dnp));
-                fa1[2 * c] = __dadd_rn(fa1[2 * c], fp_mulmod(x0, b0, __dmul_rn(b0, pinv), dnp));
-                fa1[2 * c + 1] = __dadd_rn(fa1[2 * c + 1], fp_mulmod(x1, b1, __dmul_rn(b1, pinv), dnp));
-            }
-            if (++since_red >= red_period && i + 1 < d)
-            {
-                since_red = 0;
-#pragma unroll
-                for (int k = 0; k < 16; ++k)
-                {
-                    fa0[k] = fp_reduce(fa0[k], pinv, dnp);
-                    fa1[k] = fp_reduce(fa1[k], pinv, dnp);
-                }
-            }
-        }
-        else
-        {
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-            {
-                const ulonglong2 k0 = *reinterpret_cast<const ulonglong2*>(skey0 + lineoff + ((c ^ sw) << 4));
-                const ulonglong2 k1 = *reinterpret_cast<const ulonglong2*>(skey1 + lineoff + ((c ^ sw) << 4));
-                mac128(il0[2 * c], ih0[2 * c], v[2 * c], k0.x);
-                mac128(il0[2 * c + 1], ih0[2 * c + 1], v[2 * c + 1], k0.y);
-                mac128(il1[2 * c], ih1[2 * c], v[2 * c], k1.x);
-                mac128(il1[2 * c + 1], ih1[2 * c + 1], v[2 * c + 1], k1.y);
-            }
-        }
-        __syncthreads(); // the key tiles have been consumed
-        if (threadIdx.x == 0 && i + 1 < d)
-        {
-            mbar_arrive_expect_tx(&bar[1], 2 * T);
-            tma_load_2d(skey0, &tm_key, &bar[1], 0, kline(i + 1, 0));
-            tma_load_2d(skey1, &tm_key, &bar[1], 0, kline(i + 1, 1));
-        }
-    }
-    // canonical results leave through the two (now idle) key buffers
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-    {
-        ulonglong2 r0, r1;
-        if constexpr (FP)
-        {
-            r0.x = fp_canon(fa0[2 * c], bc.dpinv, bc.dnp, bc.dp);
-            r0.y = fp_canon(fa0[2 * c + 1], bc.dpinv, bc.dnp, bc.dp);
-            r1.x = fp_canon(fa1[2 * c], bc.dpinv, bc.dnp, bc.dp);
-            r1.y = fp_canon(fa1[2 * c + 1], bc.dpinv, bc.dnp, bc.dp);
-        }
-        else
-        {
-            r0.x = reduce_u128(il0[2 * c], ih0[2 * c], pc);
-            r0.y = reduce_u128(il0[2 * c + 1], ih0[2 * c + 1], pc);
-            r1.x = reduce_u128(il1[2 * c], ih1[2 * c], pc);
-            r1.y = reduce_u128(il1[2 * c + 1], ih1[2 * c + 1], pc);
-        }
-        *reinterpret_cast<ulonglong2*>(skey0 + lineoff + ((c ^ sw) << 4)) = r0;
-        *reinterpret_cast<ulonglong2*>(skey1 + lineoff + ((c ^ sw) << 4)) = r1;
-    }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        tma_store_2d(&tm_out, skey0, 0, (int) (((b * 2 + 0) * Qpl + y) * lpp) + line0);
-        tma_store_2d(&tm_out, skey1, 0, (int) (((b * 2 + 1) * Qpl + y) * lpp) + line0);
-        tma_store_commit();
-        tma_store_wait_read<0>();
-    }
-}
-
-// ---------------------------------------------------------------------------
-// host launchers
-// ---------------------------------------------------------------------------
-
-template <bool INV, class Map>
-static void launch_col(const Context& c, const Map& m, long long n_polys, bool first, cudaStream_t st)
-{
-    const int S = c.logn - 8;
-    const unsigned grid = (unsigned) (n_polys * ((1 << S) / 16));
-    LaunchScope scope(INV ? KC_NTT_INV_COL : KC_NTT_FWD_COL, st);
-    // measured on B200: +5.5 % for the in-place maps, -1.4 % for the fused mod-up map (64-byte chunks of a
-    // source that 38 output limbs share) -> narrow CTAs only where the map does not transform its input
-    if (S == 8 && (c.col_threads == 128 || (c.col_threads == 0 && !Map::kXform)))
-    {
-        // 8 columns per CTA: twice as many, half as large CTAs (finer-grained overlap of load / compute / store)
-        ntt_col_pass<8, INV, Map, 128><<<grid * 2, 128, 0, st>>>(m, INV ? c.d_inv : c.d_fwd, c.d_pc, c.d_inv_last, c.logn,
-                                                               first, c.ntt_variant);
-        return;
-    }
-#define HEON_COL(SS)                                                                               \
-    case SS:                                                                                       \
-        ntt_col_pass<SS, INV, Map><<<grid, 256, 0, st>>>(m, INV ? c.d_inv : c.d_fwd, c.d_pc,       \
-                                                         c.d_inv_last, c.logn, first, c.ntt_variant);             \
-        break;
-    switch (S)
-    {
-        HEON_COL(4)
-        HEON_COL(5)
-        HEON_COL(6)
-        HEON_COL(7)
-        HEON_COL(8)
-        default:
-            throw std::invalid_argument("unsupported ring size");
-    }
-#undef HEON_COL
-}
-
-template <bool INV, class Map>
-static void launch_row(const Context& c, const Map& m, long long n_polys, bool first, cudaStream_t st)
-{
-    const int S = c.logn - 8;
-    const unsigned grid = (unsigned) (n_polys * ((1 << S) / 16));
-    LaunchScope scope(INV ? KC_NTT_INV_ROW : KC_NTT_FWD_ROW, st);
-    ntt_row_pass<INV, Map><<<grid, 256, 0, st>>>(m, INV ? c.d_inv : c.d_fwd, c.d_pc, c.logn, first,
-                                                 c.ntt_variant);
-}
-
-// ---- tensor maps -----------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled()
-{
-    static EncodeTiledFn fn = [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qr;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || !p)
-            throw std::runtime_error("cuTensorMapEncodeTiled is not available from this driver");
-        return (EncodeTiledFn) p;
-    }();
-    return fn;
-}
-
-// Buffer viewed as `lines` rows of sixteen 64-bit words (128 B); box = 256 lines (one 16-row tile).
-static CUtensorMap make_line_map(const u64* base, long long words, int box_lines = 256)
-{
-    CUtensorMap m;
-    const cuuint64_t dims[2] = {16, (cuuint64_t) (words >> 4)};
-    const cuuint64_t strides[1] = {128};
-    const cuuint32_t box[2] = {16, (cuuint32_t) box_lines};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult rc = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*) base, dims, strides, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS)
-        throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string((int) rc) + ")");
-    return m;
-}
-
-// extent of the buffers a map touches (for the tensor-map bounds)
-struct Extent {
-    const u64* in_base;
-    long long in_words;
-    const u64* out_base;
-    long long out_words;
-    // buffer read by the FIRST pass of a forward transform (column tiles by TMA); nullptr when
-    // its polynomials do not start on 2 KiB row boundaries relative to the base
-    const u64* col_in_base = nullptr;
-    long long col_in_words = 0;
-};
-
-template <bool INV, class Map, int ROWS>
-static void launch_row_tma_rows(const Context& c, const Map& m, long long n_polys, bool first, const Extent& e,
-                                cudaStream_t st)
-{
-    const int S = c.logn - 8;
-    const long long n_tiles = n_polys * ((1 << S) / ROWS);
-    // persistent (a few CTAs per SM walking tiles) or one tile per CTA
-    const unsigned grid = c.ntt_persistent
-                              ? (unsigned) std::min<long long>(n_tiles, (long long) c.num_sms * HEON_NTT_MINBLOCKS)
-                              : (unsigned) n_tiles;
-    const CUtensorMap tm_out = make_line_map(e.out_base, e.out_words, ROWS * 16);
-    const CUtensorMap tm_in = first ? make_line_map(e.in_base, e.in_words, ROWS * 16) : tm_out;
-    auto kfn = ntt_row_pass_tma<INV, Map, ROWS>;
-    const int smem = 2 * ROWS * 2048 + 1024;
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    LaunchScope scope(INV ? KC_NTT_INV_ROW : KC_NTT_FWD_ROW, st);
-    kfn<<<grid, ROWS * 16, smem, st>>>(m, tm_in, tm_out, e.in_base, e.out_base, INV ? c.d_inv : c.d_fwd,
-                                       INV ? c.d_inv_rowb : c.d_fwd_rowb, c.d_pc, c.logn, first, c.ntt_variant,
-                                       n_tiles, (!INV && !c.ntt_persistent && c.use_fp64) ? c.d_fwd_rowc : nullptr);
-}
-
-template <bool INV, class Map>
-static void launch_row_tma(const Context& c, const Map& m, long long n_polys, bool first, const Extent& e,
-                           cudaStream_t st)
-{
-    if (c.row_tile == 4 && !c.ntt_persistent)
-        launch_row_tma_rows<INV, Map, 4>(c, m, n_polys, first, e, st);
-    else if (c.row_tile == 8 && !c.ntt_persistent)
-        launch_row_tma_rows<INV, Map, 8>(c, m, n_polys, first, e, st);
-    else
-        launch_row_tma_rows<INV, Map, 16>(c, m, n_polys, first, e, st);
-}
-
-
-// rows-of-2-KiB view for the column tiles: {16 words, 16 lines per row, rows}, box {16, 1, 256}
-static CUtensorMap make_col_map(const u64* base, long long words)
-{
-    CUtensorMap m;
-    const cuuint64_t dims[3] = {16, 16, (cuuint64_t) (words >> 8)};
-    const cuuint64_t strides[2] = {128, 2048};
-    const cuuint32_t box[3] = {16, 1, 256};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult rc = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void*) base, dims, strides, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS)
-        throw std::runtime_error("cuTensorMapEncodeTiled (column map) failed (" + std::to_string((int) rc) + ")");
-    return m;
-}
-
-// `ein`: extent of the buffer the FIRST pass reads (may differ from e.in_base, which describes
-// what the row pass reads); every polynomial must start a multiple of 256 words from the bases.
-template <class Map>
-static bool launch_fwd_pipe(const Context& c, const Map& m, long long n_polys, const u64* in_base,
-                            long long in_words, const Extent& e, cudaStream_t st)
-{
-    if (c.logn != 16 || !c.ntt_pipe || !c.use_fp64 || n_polys < 1)
-        return false;
-    if ((reinterpret_cast<uintptr_t>(in_base) | reinterpret_cast<uintptr_t>(e.out_base)) & 127)
-        return false;
-    const int G = std::max(1, c.ntt_group);
-    int* done = nullptr;
-    const size_t sync_bytes = (size_t) n_polys * sizeof(int);
-    if (cudaMallocAsync(&done, sync_bytes, st) != cudaSuccess)
-        return false;
-    cudaMemsetAsync(done, 0, sync_bytes, st);
-    const CUtensorMap tm_in_col = make_col_map(in_base, in_words);
-    const CUtensorMap tm_out_col = make_col_map(e.out_base, e.out_words);
-    const CUtensorMap tm_out_row = make_line_map(e.out_base, e.out_words);
-    const int smem = kPipeStages * kRowTileBytes + 1024;
-    const long long n_tiles = n_polys * 32;
-    const unsigned grid = (unsigned) std::min<long long>((n_tiles + 3) / 4, c.num_sms);
-    auto kfn = ntt16_fwd_pipe<Map>;
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    {
-        LaunchScope scope(KC_NTT_FWD_COL, st);
-        kfn<<<grid, kPipeThreads, smem, st>>>(m, tm_in_col, tm_out_col, tm_out_row, in_base, e.out_base, c.d_fwd,
-                                              c.d_fwd_rowb, c.d_fwd_rowc, c.d_pc, c.ntt_variant, n_polys, G, done);
-    }
-    cudaFreeAsync(done, st);
-    return true;
-}
-
-template <class Map>
-static bool launch_fwd_fused(const Context& c, const Map& m, long long n_polys, const Extent& e, cudaStream_t st)
-{
-    const int S = c.logn - 8;
-    if (S < 5 || !c.ntt_fused)
-        return false;
-    const int tiles = (1 << S) / 16;
-    // group = polynomials whose column-pass output waits in L2 for its row tiles (~8 MiB)
-    int G = (int) std::max<long long>(1, (8ll << 20) / (8ll << c.logn));
-    const long long n_groups = (n_polys + G - 1) / G;
-    const long long n_tickets = (2 * n_groups + 1) * (long long) G * tiles;
-    if (n_tickets + (long long) c.num_sms * 8 > 0x7fffffffll)
-        return false;
-    int* sync = nullptr;
-    const size_t sync_bytes = (size_t) (n_polys + 1) * sizeof(int);
-    if (cudaMallocAsync(&sync, sync_bytes, st) != cudaSuccess)
-        return false;
-    cudaMemsetAsync(sync, 0, sync_bytes, st);
-    const CUtensorMap tm_out = make_line_map(e.out_base, e.out_words);
-    const int smem = 2 * kRowTileBytes + 1024;
-    const unsigned grid = (unsigned) std::min<long long>(n_tickets, (long long) c.num_sms * HEON_NTT_MINBLOCKS);
-    {
-        LaunchScope scope(KC_NTT_FWD_COL, st);
-#define HEON_FUSED(SS)                                                                                      \
-    case SS: {                                                                                              \
-        auto kfn = ntt_fwd_fused<SS, Map>;                                                                  \
-        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                       \
-        kfn<<<grid, 256, smem, st>>>(m, tm_out, e.out_base, c.d_fwd, c.d_fwd_rowb,                          \
-                                     c.use_fp64 ? c.d_fwd_rowc : nullptr, c.d_pc, c.d_inv_last,             \
-                                     c.ntt_variant, n_polys, G, sync);                                      \
-        break;                                                                                              \
-    }
-        switch (S)
-        {
-            HEON_FUSED(5)
-            HEON_FUSED(6)
-            HEON_FUSED(7)
-            HEON_FUSED(8)
-        }
-#undef HEON_FUSED
-    }
-    cudaFreeAsync(sync, st);
-    return true;
-}
-
-template <class Map>
-static void run_ntt(const Context& c, const Map& m, long long n_polys, bool inverse, const Extent& e,
-                    cudaStream_t st, bool col_only = false)
-{
-    if (n_polys <= 0)
-        return;
-    if (col_only)
-    {
-        // first n-8 stages only: the row stages run inside the fused inner-product kernel (k_row_mac)
-        launch_col<false>(c, m, n_polys, true, st);
-        return;
-    }
-    // TMA needs 16-byte aligned bases; fall back to the LSU row pass otherwise
-    const bool tma = c.use_tma && ((reinterpret_cast<uintptr_t>(e.in_base) | reinterpret_cast<uintptr_t>(e.out_base)) & 15) == 0;
-    if (!inverse)
-    {
-        if (tma && e.col_in_base && launch_fwd_pipe(c, m, n_polys, e.col_in_base, e.col_in_words, e, st))
-            return;
-        if (tma && launch_fwd_fused(c, m, n_polys, e, st))
-            return;
-        launch_col<false>(c, m, n_polys, true, st);
-        if (tma)
-            launch_row_tma<false>(c, m, n_polys, false, e, st);
-        else
-            launch_row<false>(c, m, n_polys, false, st);
-    }
-    else
-    {
-        if (tma)
-            launch_row_tma<true>(c, m, n_polys, true, e, st);
-        else
-            launch_row<true>(c, m, n_polys, true, st);
-        launch_col<true>(c, m, n_polys, false, st);
-    }
-}
 
 void launch_ntt(const Context& c, const u64* src, u64* dst, long long n_polys, const PrimeList& pl,
                 bool inverse, cudaStream_t st, bool col_only)
@@ -1591,167 +9,6 @@ void launch_ntt(const Context& c, const u64* src, u64* dst, long long n_polys, c
     MapContig m{src, dst, pl, c.logn};
     const long long w = n_polys << c.logn;
     run_ntt(c, m, n_polys, inverse, Extent{src, w, dst, w, src, w}, st, col_only);
-}
-
-// true when the fused row-pass + inner-product kernel can serve this key switch
-bool row_mac_available(const Context& c, const u64* tmp, const u64* key, const u64* acc, int d)
-{
-    return c.use_tma && c.row_mac && c.logn >= 12 && d >= 1 && d <= 64 &&
-           ((reinterpret_cast<uintptr_t>(tmp) | reinterpret_cast<uintptr_t>(key) | reinterpret_cast<uintptr_t>(acc)) & 15) == 0;
-}
-
-// acc[b][2][Qpl][N] = sum_i rowpass(tmp[b][i][y]) (.) key[i][c][prime(y)]; tmp holds column-pass output
-// (lazy words), digit-own limbs (own_stashed) hold canonical NTT-domain words.
-void launch_row_mac(const Context& c, const u64* tmp, const u64* key, u64* acc, int d, int depth, int batch,
-                    bool own_stashed, const int* I_loc, const int* I_j, cudaStream_t st)
-{
-    const int L = c.Q_size - depth, K = c.P_size, Qpl = L + K;
-    OwnLimbs own;
-    own.d = d;
-    own.own = own_stashed ? 1 : 0;
-    for (int i = 0; i < d && i < 65; ++i)
-    {
-        own.I_loc[i] = (short) (own_stashed ? I_loc[i] : 0);
-        own.I_j[i] = (short) (own_stashed ? I_j[i] : 0);
-    }
-    // limb slots by arithmetic: FP64 primes / integer primes (two launches, different register budgets)
-    LimbList lfp, lint;
-    int nfp = 0, nint = 0;
-    for (int y = 0; y < Qpl; ++y)
-    {
-        const bool fp = c.use_fp64 && c.mod[level_prime(y, L, depth)].bit <= 50;
-        if (fp)
-            lfp.y[nfp++] = (unsigned char) y;
-        else
-            lint.y[nint++] = (unsigned char) y;
-    }
-    const long long wt = ((long long) batch * d * Qpl) << c.logn;
-    const long long wk = ((long long) d * 2 * c.Qp) << c.logn;
-    const long long wa = ((long long) batch * 2 * Qpl) << c.logn;
-    const int rows = (c.row_mac_rows == 4) ? 4 : 8;
-    const CUtensorMap tm_tmp = make_line_map(tmp, wt, rows * 16);
-    const CUtensorMap tm_key = make_line_map(key, wk, rows * 16);
-    const CUtensorMap tm_out = make_line_map(acc, wa, rows * 16);
-    const int tiles = (1 << (c.logn - 8)) / rows;
-    // |T| <= p per term: the double accumulator stays exact while (terms + 1/2) * p < 2^53
-    const int red_lo = 60, red_hi = 7;
-    auto go = [&](auto kfn, int nl, const LimbList& list, int smem) {
-        if (nl == 0)
-            return;
-        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        LaunchScope scope(KC_ROW_MAC, st);
-        kfn<<<dim3(batch, tiles, nl), rows * 16, smem, st>>>(tm_tmp, tm_key, tm_out, c.d_fwd, c.d_fwd_rowb, c.d_fwd_rowc, c.d_pc,
-                                                        list, c.logn, L, Qpl, c.Qp, depth, c.ntt_variant, red_lo, red_hi, own);
-    };
-    if (rows == 8)
-    {
-        go(k_row_mac<true, 8>, nfp, lfp, 4 * 8 * 2048 + 1024);
-        go(k_row_mac<false, 8>, nint, lint, 3 * 8 * 2048 + 1024);
-    }
-    else
-    {
-        go(k_row_mac<true, 4>, nfp, lfp, 4 * 4 * 2048 + 1024);
-        go(k_row_mac<false, 4>, nint, lint, 3 * 4 * 2048 + 1024);
-    }
-}
-
-void launch_ntt_digit_skip(const Context& c, u64* tmp, int d, const int* I_loc, const int* I_j, int L, int depth,
-                           long long batch, cudaStream_t st, bool col_only)
-{
-    const int Qpl = L + c.P_size;
-    if (d > 64)
-        throw std::invalid_argument("too many key-switch digits");
-    MapDigitSkip m;
-    m.base = tmp;
-    m.d = d;
-    m.Qpl = Qpl;
-    m.L = L;
-    m.depth = depth;
-    m.logn = c.logn;
-    int acc = 0;
-    for (int i = 0; i < d; ++i)
-    {
-        m.prefix[i] = (short) acc;
-        m.I_loc[i] = (short) I_loc[i];
-        m.I_j[i] = (short) I_j[i];
-        acc += Qpl - I_j[i];
-    }
-    m.prefix[d] = (short) acc;
-    m.per_b = acc;
-    const long long w = (batch * d * Qpl) << c.logn;
-    run_ntt(c, m, batch * acc, false, Extent{tmp, w, tmp, w}, st, col_only);
-}
-
-void launch_ntt_scattered(const Context& c, u64* base, const long long* d_offsets, int n_polys,
-                          int prime, bool inverse, long long extent_words, bool aligned, cudaStream_t st)
-{
-    MapScatter m{base, d_offsets, prime};
-    // offsets that are not multiples of 16 words cannot be addressed in 128-byte lines
-    Extent e{aligned ? base : base + 1, extent_words, aligned ? base : base + 1, extent_words};
-    // arbitrary offsets: the column tiles need 2 KiB-aligned polynomials, not guaranteed here
-    run_ntt(c, m, n_polys, inverse, e, st);
-}
-
-void launch_ntt_strided(const Context& c, u64* base, long long bstride, int per_batch, int first,
-                        long long batch, const PrimeList& pl, bool inverse, cudaStream_t st)
-{
-    MapStrided m{base, bstride, per_batch, first, pl, c.logn};
-    const long long w = (batch - 1) * bstride + ((long long) (first + per_batch) << c.logn);
-    const u64* b0 = (bstride & 15) ? base + 1 : base; // odd strides: no line addressing -> LSU path
-    Extent e{b0, w, b0, w};
-    if ((bstride & 255) == 0)
-    {
-        e.col_in_base = base;
-        e.col_in_words = w;
-    }
-    run_ntt(c, m, batch * per_batch, inverse, e, st);
-}
-
-void launch_ntt_strided_copy(const Context& c, const u64* src, long long src_bstride, u64* dst,
-                             int per_batch, long long batch, const PrimeList& pl, bool inverse,
-                             cudaStream_t st)
-{
-    MapStridedCopy m{src, dst, src_bstride, per_batch, pl, c.logn};
-    const long long wi = (batch - 1) * src_bstride + ((long long) per_batch << c.logn);
-    const long long wo = (batch * per_batch) << c.logn;
-    const u64* s0 = (src_bstride & 15) ? src + 1 : src;
-    Extent e{s0, wi, dst, wo};
-    if ((src_bstride & 255) == 0)
-    {
-        e.col_in_base = src;
-        e.col_in_words = wi;
-    }
-    run_ntt(c, m, batch * per_batch, inverse, e, st);
-}
-
-void launch_modup1_ntt(const Context& c, const u64* coef, long long coef_bstride, u64* out, int L,
-                       int depth, long long batch, cudaStream_t st, bool col_only)
-{
-    const int Qpl = L + c.P_size;
-    MapModUpI m{coef, out, coef_bstride, L, Qpl, depth, c.logn, c.d_pc};
-    const long long wo = (batch * L * Qpl) << c.logn;
-    Extent e{out, wo, out, wo};
-    if ((coef_bstride & 255) == 0)
-    {
-        e.col_in_base = coef;
-        e.col_in_words = (batch - 1) * coef_bstride + ((long long) L << c.logn);
-    }
-    run_ntt(c, m, batch * L * Qpl, false, e, st, col_only);
-}
-
-void launch_divround1_ntt(const Context& c, const u64* src, long long bstride, long long cstride,
-                          u64* out, int Lout, u64 half, u64 plast, const u64* d_half_mod,
-                          long long batch, cudaStream_t st)
-{
-    MapDivRoundOne m{src, out, bstride, cstride, Lout, c.logn, half, plast, d_half_mod};
-    const long long wo = (batch * 2 * Lout) << c.logn;
-    Extent e{out, wo, out, wo};
-    if ((bstride & 255) == 0 && (cstride & 255) == 0)
-    {
-        e.col_in_base = src;
-        e.col_in_words = (batch - 1) * bstride + cstride + (1ll << c.logn);
-    }
-    run_ntt(c, m, batch * 2 * Lout, false, e, st);
 }
 
 } // namespace heon

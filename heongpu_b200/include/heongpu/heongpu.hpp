@@ -24,6 +24,7 @@
 // language extensions), like the reference's public headers.
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdint>
 #include <memory>
 #include <stdexcept>
@@ -33,8 +34,43 @@
 #include "../../../include/heon_b200.h"
 
 typedef std::uint64_t Data64;
+// Modulus<Data64> {value, bit, mu} with mu = floor(2^(2*bit+1) / value) and the host Barrett product of
+// OPERATOR<Data64> (thirdparty/GPU-NTT/src/include/gpuntt/common/modular_arith.cuh:28-60, 90-107); both
+// live at global namespace in the reference and its tests use them directly
+// (test/test_bfv_multiplication.cpp:50-58).
 struct Modulus64 {
-    Data64 value, bit, mu;
+    Data64 value = 0, bit = 0, mu = 0;
+    Modulus64() = default;
+    Modulus64(Data64 v, Data64 b, Data64 m) : value(v), bit(b), mu(m) {}
+    Modulus64(Data64 v) : value(v)
+    {
+        for (Data64 t = v; t; t >>= 1)
+            ++bit;
+        mu = (Data64) ((((unsigned __int128) 1) << (2 * bit + 1)) / v);
+    }
+};
+struct OPERATOR64 {
+    static Data64 mult(const Data64& a, const Data64& b, const Modulus64& m)
+    {
+        unsigned __int128 z = (unsigned __int128) a * b;
+        unsigned __int128 r = z >> (m.bit - 2);
+        r = r * (unsigned __int128) m.mu;
+        r = r >> (m.bit + 3);
+        r = r * (unsigned __int128) m.value;
+        z = z - r;
+        const Data64 res = (Data64) z;
+        return res >= m.value ? res - m.value : res;
+    }
+    static Data64 add(const Data64& a, const Data64& b, const Modulus64& m)
+    {
+        const Data64 s = a + b;
+        return s >= m.value ? s - m.value : s;
+    }
+    static Data64 sub(const Data64& a, const Data64& b, const Modulus64& m)
+    {
+        const Data64 d = a + m.value - b;
+        return d >= m.value ? d - m.value : d;
+    }
 };
 
 namespace heongpu {
@@ -139,6 +175,202 @@ template <typename T> class DeviceVector {
 };
 template <typename T> using HostVector = std::vector<T>;
 
+// Pinned host buffer (the reference's HostVector is an rmm pinned-pool vector, hostvector.cuh).
+template <typename T> class PinnedVector {
+  public:
+    PinnedVector() = default;
+    PinnedVector(PinnedVector&& o) noexcept { swap(o); }
+    PinnedVector& operator=(PinnedVector&& o) noexcept
+    {
+        swap(o);
+        return *this;
+    }
+    PinnedVector(const PinnedVector&) = delete;
+    PinnedVector& operator=(const PinnedVector&) = delete;
+    ~PinnedVector() { clear(); }
+    void resize(size_t n)
+    {
+        if (n == size_)
+            return;
+        clear();
+        if (n)
+            detail::cuda(cudaMallocHost((void**) &ptr_, n * sizeof(T)));
+        size_ = n;
+    }
+    void clear()
+    {
+        if (ptr_)
+            cudaFreeHost(ptr_);
+        ptr_ = nullptr;
+        size_ = 0;
+    }
+    T* data() const { return ptr_; }
+    size_t size() const { return size_; }
+    void swap(PinnedVector& o)
+    {
+        std::swap(ptr_, o.ptr_);
+        std::swap(size_, o.size_);
+    }
+
+  private:
+    T* ptr_ = nullptr;
+    size_t size_ = 0;
+};
+
+namespace detail {
+// Where an object's words live and how they move: store_in_host / store_in_device / copy_to_device /
+// remove_from_host / remove_from_device / is_on_device of the reference's Ciphertext, Plaintext and key
+// classes (ckks/ciphertext.cuh:120-209).
+class Storable {
+  public:
+    Data64* data() const { return device_locations_.data(); }
+    Data64* host_data() const { return host_locations_.data(); }
+    bool is_on_device() const { return storage_type_ == storage_type::DEVICE; }
+    void store_in_device(cudaStream_t st = cudaStreamDefault)
+    {
+        if (storage_type_ == storage_type::DEVICE)
+            return;
+        copy_to_device(st);
+        detail::cuda(cudaStreamSynchronize(st)); // the pinned source is released next
+        host_locations_.clear();
+    }
+    void store_in_host(cudaStream_t st = cudaStreamDefault)
+    {
+        if (storage_type_ == storage_type::HOST)
+            return;
+        host_locations_.resize(device_locations_.size());
+        detail::cuda(cudaMemcpyAsync(host_locations_.data(), device_locations_.data(), device_locations_.size() * sizeof(Data64),
+                                     cudaMemcpyDeviceToHost, st));
+        detail::cuda(cudaStreamSynchronize(st));
+        device_locations_ = DeviceVector<Data64>();
+        storage_type_ = storage_type::HOST;
+    }
+    // device copy next to the host copy (the host words stay valid)
+    void copy_to_device(cudaStream_t st = cudaStreamDefault)
+    {
+        if (storage_type_ == storage_type::DEVICE)
+            return;
+        DeviceVector<Data64> d(host_locations_.size(), st);
+        detail::cuda(cudaMemcpyAsync(d.data(), host_locations_.data(), host_locations_.size() * sizeof(Data64),
+                                     cudaMemcpyHostToDevice, st));
+        device_locations_ = std::move(d);
+        storage_type_ = storage_type::DEVICE;
+    }
+    void remove_from_device(cudaStream_t st = cudaStreamDefault)
+    {
+        // back to the host state kept by copy_to_device (the words did not change)
+        if (host_locations_.size() == 0)
+        {
+            store_in_host(st);
+            return;
+        }
+        device_locations_ = DeviceVector<Data64>();
+        storage_type_ = storage_type::HOST;
+    }
+    void remove_from_host() { host_locations_.clear(); }
+    size_t memory_size() const { return is_on_device() ? device_locations_.size() : host_locations_.size(); }
+    void memory_set(DeviceVector<Data64>&& v)
+    {
+        device_locations_ = std::move(v);
+        host_locations_.clear();
+        storage_type_ = storage_type::DEVICE;
+    }
+
+    DeviceVector<Data64> device_locations_;
+    PinnedVector<Data64> host_locations_;
+    storage_type storage_type_ = storage_type::DEVICE;
+};
+
+// input_storage_manager (storagemanager.cuh:113-167): brings an operand to the device for the call and,
+// when the call ends, leaves it where ExecutionOptions says (truth table: README.md:349-366).
+template <class T> struct InputGuard {
+    T& o;
+    ExecutionOptions opt;
+    storage_type initial;
+    bool same;
+    InputGuard(T& obj, const ExecutionOptions& op, bool is_input_output_same = false)
+        : o(obj), opt(op), initial(obj.storage_type_), same(is_input_output_same)
+    {
+        if (!o.is_on_device())
+        {
+            if (opt.keep_initial_condition_ && !same)
+                o.copy_to_device(opt.stream_);
+            else
+                o.store_in_device(opt.stream_);
+        }
+    }
+    ~InputGuard() noexcept(false)
+    {
+        if (same)
+            return; // the result's location is set by output_storage
+        if (opt.keep_initial_condition_)
+        {
+            if (initial == storage_type::HOST)
+                o.remove_from_device(opt.stream_);
+        }
+        else if (opt.storage_ == storage_type::HOST)
+            o.store_in_host(opt.stream_);
+        else
+            o.store_in_device(opt.stream_);
+    }
+};
+// output_storage_manager: the result goes where set_storage_type says
+template <class T> void output_storage(T& out, const ExecutionOptions& opt)
+{
+    if (opt.storage_ == storage_type::HOST)
+        out.store_in_host(opt.stream_);
+}
+} // namespace detail
+
+
+namespace detail {
+// heongpu_{128,192,256}bit_std_parms (src/include/heongpu/util/secstdparams.h:24-76): the largest total
+// coefficient-modulus bit count a ring degree supports at a security level
+inline int max_total_bits(sec_level_type sec, size_t n)
+{
+    static const int tab[3][5] = {{109, 218, 438, 881, 1761}, {74, 149, 300, 605, 1212}, {57, 115, 232, 465, 930}};
+    const int row = sec == sec_level_type::sec128 ? 0 : sec == sec_level_type::sec192 ? 1 : 2;
+    const int col = n == 4096 ? 0 : n == 8192 ? 1 : n == 16384 ? 2 : n == 32768 ? 3 : n == 65536 ? 4 : -1;
+    return col < 0 ? 0 : tab[row][col];
+}
+inline int bit_size(Data64 v)
+{
+    int b = 0;
+    while (v)
+    {
+        ++b;
+        v >>= 1;
+    }
+    return b;
+}
+// set_coeff_modulus_*: "Parameters do not align with the security recommendations" (ckks/context.cu:113,
+// bfv/context.cu:113,223) unless the level is sec_level_type::none
+inline void check_security(sec_level_type sec, size_t n, int total_bits)
+{
+    if (sec == sec_level_type::none)
+        return;
+    if (total_bits > max_total_bits(sec, n))
+        throw std::runtime_error("Parameters do not align with the security recommendations.");
+}
+// default 128-bit-security coefficient moduli (src/lib/util/defaultmodulus.cpp:12-90; the SEAL defaults)
+inline std::vector<Data64> default_modulus_128(size_t n)
+{
+    switch (n)
+    {
+        case 4096: return {0x800004001, 0x800008001, 0x1000002001};
+        case 8192: return {0x40000084001, 0x400000b0001, 0x8000002c001, 0x80000050001, 0x80000064001};
+        case 16384:
+            return {0x800000020001,  0x8000001a8001,  0x8000001e8001,  0x10000000d8001, 0x1000000168001,
+                    0x10000001a0001, 0x10000001e0001, 0x10000002b8001, 0x10000002e8001};
+        case 32768:
+            return {0x2000000002b0001, 0x2000000003a0001, 0x2000000005b0001, 0x200000000640001, 0x400000000270001,
+                    0x400000000350001, 0x400000000360001, 0x4000000004d0001, 0x400000000570001, 0x400000000660001,
+                    0x4000000008a0001, 0x400000000920001, 0x400000000980001, 0x400000000990001, 0x400000000a40001};
+    }
+    throw std::logic_error("no default modulus for this poly_modulus_degree");
+}
+} // namespace detail
+
 template <Scheme S> class HEContextImpl;
 template <Scheme S> using HEContext = std::shared_ptr<HEContextImpl<S>>;
 
@@ -170,6 +402,12 @@ template <> class HEContextImpl<Scheme::CKKS> {
             throw std::logic_error("Coeff_modulus cannot be changed after the context is generated!");
         if (p_bits.empty())
             throw std::logic_error("log_P_bases_bit_sizes cannot be empty!");
+        int total = 0;
+        for (int b : q_bits)
+            total += b;
+        for (int b : p_bits)
+            total += b;
+        detail::check_security(sec_level_, (size_t) n, total);
         q_bits_ = q_bits;
         p_bits_ = p_bits;
         by_value_ = false;
@@ -181,6 +419,12 @@ template <> class HEContextImpl<Scheme::CKKS> {
             throw std::logic_error("Coeff_modulus cannot be changed after the context is generated!");
         if (p.empty())
             throw std::logic_error("log_P_bases_bit_sizes cannot be empty!");
+        int total = 0;
+        for (Data64 v : q)
+            total += detail::bit_size(v);
+        for (Data64 v : p)
+            total += detail::bit_size(v);
+        detail::check_security(sec_level_, (size_t) n, total);
         q_vals_ = q;
         p_vals_ = p;
         by_value_ = true;
@@ -241,29 +485,41 @@ template <Scheme S> HEContext<S> GenHEContext(sec_level_type sec = sec_level_typ
 }
 
 template <Scheme S> class Ciphertext;
-template <> class Ciphertext<Scheme::CKKS> {
+template <> class Ciphertext<Scheme::CKKS> : public detail::Storable {
   public:
     Ciphertext() = default;
+    // empty ciphertext bound to a context (ckks/ciphertext.cu:8-31); filled by the encryptor / operators
+    explicit Ciphertext(HEContext<Scheme::CKKS> ctx, const ExecutionOptions& = ExecutionOptions()) : context_(ctx)
+    {
+        ring_size_ = ctx->n;
+        coeff_modulus_count_ = ctx->Q_size;
+        cipher_size_ = 2;
+        scale_ = 0;
+    }
     // [cipher_size][L][N] words, NTT domain (ciphertext.cu:20-31)
     Ciphertext(HEContext<Scheme::CKKS> ctx, const std::vector<Data64>& words, int cipher_size = 2, int depth = 0,
                double scale = 1.0, const ExecutionOptions& opt = ExecutionOptions())
-        : context_(ctx), device_locations_(words, opt.stream_), cipher_size_(cipher_size), depth_(depth), scale_(scale)
+        : context_(ctx), cipher_size_(cipher_size), depth_(depth), scale_(scale)
     {
+        device_locations_ = DeviceVector<Data64>(words, opt.stream_);
         ring_size_ = ctx->n;
         coeff_modulus_count_ = ctx->Q_size;
         if (words.size() < (size_t) cipher_size * (ctx->Q_size - depth) * ctx->n)
             throw std::invalid_argument("Invalid Ciphertexts size!");
         ciphertext_generated_ = true;
     }
-    Data64* data() const { return device_locations_.data(); }
-    size_t memory_size() const { return device_locations_.size(); }
-    void memory_set(DeviceVector<Data64>&& v) { device_locations_ = std::move(v); }
     void get_data(std::vector<Data64>& out, cudaStream_t st = cudaStreamDefault) const
     {
         out.resize((size_t) cipher_size_ * (coeff_modulus_count_ - depth_) * ring_size_);
+        if (!is_on_device())
+        {
+            std::copy(host_data(), host_data() + out.size(), out.begin());
+            return;
+        }
         detail::cuda(cudaMemcpyAsync(out.data(), data(), out.size() * sizeof(Data64), cudaMemcpyDeviceToHost, st));
         detail::cuda(cudaStreamSynchronize(st));
     }
+    int level() const { return coeff_modulus_count_ - depth_; }
     int size() const { return cipher_size_; }
     int depth() const { return depth_; }
     double scale() const { return scale_; }
@@ -272,7 +528,6 @@ template <> class Ciphertext<Scheme::CKKS> {
     bool relinearization_required() const { return relinearization_required_; }
 
     HEContext<Scheme::CKKS> context_;
-    DeviceVector<Data64> device_locations_;
     int ring_size_ = 0, coeff_modulus_count_ = 0, cipher_size_ = 0, depth_ = 0;
     double scale_ = 0;
     bool in_ntt_domain_ = true, rescale_required_ = false, relinearization_required_ = false,
@@ -334,6 +589,19 @@ template <> class Galoiskey<Scheme::CKKS> {
         galois_elt_zero = 2 * context_->n - 1;
     }
     Data64* c_data() const { return zero_device_location_.data(); }
+    // keys by explicit Galois element (evaluationkey.cu: Galoiskey(context, std::vector<uint32_t>))
+    Galoiskey(HEContext<Scheme::CKKS> ctx, const std::vector<uint32_t>& elts)
+        : context_(ctx), key_type(ctx->keyswitching_type_), custom_galois_elt(elts)
+    {
+        customized = true;
+    }
+    void set_zero_key(int elt, DeviceVector<Data64>&& key)
+    {
+        zero_device_location_ = std::move(key);
+        galois_elt_zero = elt;
+    }
+    std::vector<uint32_t> custom_galois_elt;
+    bool galois_key_generated_ = false;
     HEContext<Scheme::CKKS> context_;
     keyswitching_type key_type;
     storage_type storage_type_ = storage_type::DEVICE;
@@ -348,24 +616,24 @@ template <> class Galoiskey<Scheme::CKKS> {
 template <Scheme S> class Plaintext;
 // Plaintext<CKKS>: [L][N] words in the NTT domain (ckks/plaintext.cu); encoding is a client-side
 // "next" row, so the caller supplies the encoded words.
-template <> class Plaintext<Scheme::CKKS> {
+template <> class Plaintext<Scheme::CKKS> : public detail::Storable {
   public:
     Plaintext() = default;
+    explicit Plaintext(HEContext<Scheme::CKKS> ctx, const ExecutionOptions& = ExecutionOptions()) : context_(ctx) {}
     Plaintext(HEContext<Scheme::CKKS> ctx, const std::vector<Data64>& words, int depth = 0, double scale = 1.0,
               const ExecutionOptions& opt = ExecutionOptions())
-        : context_(ctx), device_locations_(words, opt.stream_), depth_(depth), scale_(scale)
+        : context_(ctx), depth_(depth), scale_(scale)
     {
+        device_locations_ = DeviceVector<Data64>(words, opt.stream_);
         if (words.size() < (size_t) (ctx->Q_size - depth) * ctx->n)
             throw std::invalid_argument("Invalid Plaintext size!");
         plain_size_ = (int) words.size();
         plaintext_generated_ = true;
     }
-    Data64* data() const { return device_locations_.data(); }
-    size_t size() const { return device_locations_.size(); }
+    size_t size() const { return memory_size(); }
     int depth() const { return depth_; }
     double scale() const { return scale_; }
     HEContext<Scheme::CKKS> context_;
-    DeviceVector<Data64> device_locations_;
     int plain_size_ = 0, depth_ = 0;
     double scale_ = 0;
     bool in_ntt_domain_ = true, plaintext_generated_ = false;
@@ -436,6 +704,7 @@ template <> class HEOperator<Scheme::CKKS> {
         detail::check(heon_negate(h(), a.data(), 0, mem.data(), 0, a.cipher_size_, a.depth_, 1, opt.stream_));
         copy_meta(a, out);
         out.memory_set(std::move(mem));
+        detail::output_storage(out, opt);
     }
 
     // in-place forms (operator.cuh:130-190, 260-300): the result replaces the first operand
@@ -461,6 +730,7 @@ template <> class HEOperator<Scheme::CKKS> {
             throw std::logic_error("Ciphertexts leveled are not equal");
         if (a.memory_size() < words(2, a.depth_) || b.memory_size() < words(2, a.depth_))
             throw std::invalid_argument("Invalid Ciphertexts size!");
+        detail::InputGuard<Ciphertext<Scheme::CKKS>> ga(a, opt, &a == &out), gb(b, opt, &b == &out);
         DeviceVector<Data64> mem(words(3, a.depth_), opt.stream_);
         detail::check(heon_ckks_multiply(h(), a.data(), 0, b.data(), 0, mem.data(), 0, a.depth_, 1, opt.stream_));
         const double scale = a.scale_ * b.scale_;
@@ -468,6 +738,7 @@ template <> class HEOperator<Scheme::CKKS> {
         out.memory_set(std::move(mem));
         out.scale_ = scale;
         out.cipher_size_ = 3;
+        detail::output_storage(out, opt);
         out.relinearization_required_ = true;
         out.rescale_required_ = true;
     }
@@ -487,9 +758,11 @@ template <> class HEOperator<Scheme::CKKS> {
             throw std::invalid_argument("Relinkey is not generated!");
         if (ct.memory_size() < words(3, ct.depth_))
             throw std::invalid_argument("Invalid Ciphertexts size!");
+        detail::InputGuard<Ciphertext<Scheme::CKKS>> g(ct, opt, true);
         detail::check(heon_ckks_relinearize(h(), ct.data(), 0, rk.data(), ct.depth_, 1, opt.stream_));
         ct.relinearization_required_ = false;
         ct.cipher_size_ = 2;
+        detail::output_storage(ct, opt);
     }
 
     // operator.cuh:1423-1445
@@ -497,17 +770,21 @@ template <> class HEOperator<Scheme::CKKS> {
     {
         if (ct.depth_ >= context_->Q_size - 1)
             throw std::invalid_argument("Ciphertexts can not be rescaled, level is too low!");
+        detail::InputGuard<Ciphertext<Scheme::CKKS>> g(ct, opt, true);
         detail::check(heon_ckks_rescale(h(), ct.data(), 0, ct.depth_, 1, opt.stream_));
         ct.scale_ /= (double) context_->prime_vector_[context_->Q_size - ct.depth_ - 1].value;
         ct.depth_++;
         ct.rescale_required_ = false;
+        detail::output_storage(ct, opt);
     }
 
     // operator.cuh:1457-1600
     void mod_drop_inplace(Ciphertext<Scheme::CKKS>& ct, const ExecutionOptions& opt = ExecutionOptions())
     {
+        detail::InputGuard<Ciphertext<Scheme::CKKS>> g(ct, opt, true);
         detail::check(heon_ckks_mod_drop_inplace(h(), ct.data(), 0, ct.cipher_size_, ct.depth_, 1, opt.stream_));
         ct.depth_++;
+        detail::output_storage(ct, opt);
     }
     void mod_drop(Ciphertext<Scheme::CKKS>& in, Ciphertext<Scheme::CKKS>& out, const ExecutionOptions& opt = ExecutionOptions())
     {
@@ -527,12 +804,14 @@ template <> class HEOperator<Scheme::CKKS> {
         auto it = gk.device_location_.find(galois_elt);
         if (it == gk.device_location_.end())
             throw std::logic_error("Galois key not present!");
+        detail::InputGuard<Ciphertext<Scheme::CKKS>> g(in, opt, &in == &out);
         DeviceVector<Data64> mem(words(2, in.depth_), opt.stream_);
         detail::check(heon_ckks_apply_galois(h(), in.data(), 0, mem.data(), 0, it->second.data(),
                                              (uint32_t) galois_elt, in.depth_, 1, opt.stream_));
         copy_meta(in, out);
         out.memory_set(std::move(mem));
         out.cipher_size_ = 2;
+        detail::output_storage(out, opt);
     }
     void apply_galois_inplace(Ciphertext<Scheme::CKKS>& ct, Galoiskey<Scheme::CKKS>& gk, int galois_elt,
                               const ExecutionOptions& opt = ExecutionOptions())
@@ -679,6 +958,8 @@ template <> class HEOperator<Scheme::CKKS> {
     void plain(Ciphertext<Scheme::CKKS>& a, Plaintext<Scheme::CKKS>& p, Ciphertext<Scheme::CKKS>& out,
                const ExecutionOptions& opt, int op)
     {
+        detail::InputGuard<Ciphertext<Scheme::CKKS>> ga(a, opt, &a == &out);
+        detail::InputGuard<Plaintext<Scheme::CKKS>> gp(p, opt, false);
         if (a.depth_ != p.depth_)
             throw std::logic_error("Ciphertexts leveled are not equal");
         if (a.memory_size() < words(a.cipher_size_, a.depth_))
@@ -690,10 +971,12 @@ template <> class HEOperator<Scheme::CKKS> {
         detail::check(fn(h(), a.data(), 0, p.data(), 0, mem.data(), 0, a.cipher_size_, a.depth_, 1, opt.stream_));
         copy_meta(a, out);
         out.memory_set(std::move(mem));
+        detail::output_storage(out, opt);
     }
     void binary(Ciphertext<Scheme::CKKS>& a, Ciphertext<Scheme::CKKS>& b, Ciphertext<Scheme::CKKS>& out,
                 const ExecutionOptions& opt, int op)
     {
+        detail::InputGuard<Ciphertext<Scheme::CKKS>> ga(a, opt, &a == &out), gb(b, opt, &b == &out);
         if (a.depth_ != b.depth_)
             throw std::logic_error("Ciphertexts leveled are not equal");
         if (a.cipher_size_ != b.cipher_size_)
@@ -703,6 +986,7 @@ template <> class HEOperator<Scheme::CKKS> {
                                                       a.depth_, 1, opt.stream_));
         copy_meta(a, out);
         out.memory_set(std::move(mem));
+        detail::output_storage(out, opt);
     }
 };
 
@@ -746,8 +1030,47 @@ template <> class HEContextImpl<Scheme::BFV> {
             throw std::logic_error("Coeff_modulus cannot be changed after the context is generated!");
         if (p_bits.empty())
             throw std::logic_error("log_P_bases_bit_sizes cannot be empty!");
+        int total = 0;
+        for (int b : q_bits)
+            total += b;
+        for (int b : p_bits)
+            total += b;
+        detail::check_security(sec_level_, (size_t) n, total);
         q_bits_ = q_bits;
         p_bits_ = p_bits;
+        coeff_modulus_specified_ = true;
+    }
+    // bfv/context.cu:135-220
+    void set_coeff_modulus_values(const std::vector<Data64>& q, const std::vector<Data64>& p)
+    {
+        if (coeff_modulus_specified_ || context_generated_ || !poly_modulus_degree_specified_)
+            throw std::logic_error("Coeff_modulus cannot be changed after the context is generated!");
+        if (p.empty())
+            throw std::logic_error("log_P_bases_bit_sizes cannot be empty!");
+        int total = 0;
+        for (Data64 v : q)
+            total += detail::bit_size(v);
+        for (Data64 v : p)
+            total += detail::bit_size(v);
+        detail::check_security(sec_level_, (size_t) n, total);
+        q_vals_ = q;
+        p_vals_ = p;
+        by_value_ = true;
+        coeff_modulus_specified_ = true;
+    }
+    // bfv/context.cu:223-300: the last P_modulus_size primes of the default chain are the special primes
+    void set_coeff_modulus_default_values(int P_modulus_size)
+    {
+        if (coeff_modulus_specified_ || context_generated_ || !poly_modulus_degree_specified_)
+            throw std::logic_error("Coeff_modulus cannot be changed after the context is generated!");
+        if (sec_level_ != sec_level_type::sec128)
+            throw std::runtime_error("default moduli are tabulated for 128-bit security only");
+        const std::vector<Data64> all = detail::default_modulus_128((size_t) n);
+        if (P_modulus_size < 1 || (size_t) P_modulus_size >= all.size())
+            throw std::logic_error("P_modulus_size is not valid!");
+        q_vals_.assign(all.begin(), all.end() - P_modulus_size);
+        p_vals_.assign(all.end() - P_modulus_size, all.end());
+        by_value_ = true;
         coeff_modulus_specified_ = true;
     }
     void set_plain_modulus(int t)
@@ -761,8 +1084,12 @@ template <> class HEContextImpl<Scheme::BFV> {
     {
         if (context_generated_ || !poly_modulus_degree_specified_ || !coeff_modulus_specified_ || !plain_modulus_specified_)
             throw std::runtime_error("Context is already generated or not fully specified!");
-        detail::check(heon_bfv_context_create(device_, n_power, q_bits_.data(), (int) q_bits_.size(), p_bits_.data(),
-                                              (int) p_bits_.size(), plain_modulus_, &h_));
+        if (by_value_)
+            detail::check(heon_bfv_context_create_values(device_, n_power, q_vals_.data(), (int) q_vals_.size(), p_vals_.data(),
+                                                         (int) p_vals_.size(), plain_modulus_, &h_));
+        else
+            detail::check(heon_bfv_context_create(device_, n_power, q_bits_.data(), (int) q_bits_.size(), p_bits_.data(),
+                                                  (int) p_bits_.size(), plain_modulus_, &h_));
         heon_info info;
         detail::check(heon_context_info(h_, &info));
         Q_size = info.q_size;
@@ -796,29 +1123,40 @@ template <> class HEContextImpl<Scheme::BFV> {
     int device_;
     heon_context_t h_ = nullptr;
     std::vector<int> q_bits_, p_bits_;
+    std::vector<Data64> q_vals_, p_vals_;
+    bool by_value_ = false;
     bool poly_modulus_degree_specified_ = false, coeff_modulus_specified_ = false, plain_modulus_specified_ = false;
 };
 
-template <> class Ciphertext<Scheme::BFV> {
+template <> class Ciphertext<Scheme::BFV> : public detail::Storable {
   public:
     Ciphertext() = default;
+    explicit Ciphertext(HEContext<Scheme::BFV> ctx, const ExecutionOptions& = ExecutionOptions()) : context_(ctx)
+    {
+        ring_size_ = ctx->n;
+        coeff_modulus_count_ = ctx->Q_size;
+        cipher_size_ = 2;
+    }
     // [cipher_size][Q][N] words, coefficient domain (bfv/ciphertext.cu)
     Ciphertext(HEContext<Scheme::BFV> ctx, const std::vector<Data64>& words, int cipher_size = 2,
                const ExecutionOptions& opt = ExecutionOptions())
-        : context_(ctx), device_locations_(words, opt.stream_), cipher_size_(cipher_size)
+        : context_(ctx), cipher_size_(cipher_size)
     {
+        device_locations_ = DeviceVector<Data64>(words, opt.stream_);
         ring_size_ = ctx->n;
         coeff_modulus_count_ = ctx->Q_size;
         if (words.size() < (size_t) cipher_size * ctx->Q_size * ctx->n)
             throw std::invalid_argument("Invalid Ciphertexts size!");
         ciphertext_generated_ = true;
     }
-    Data64* data() const { return device_locations_.data(); }
-    size_t memory_size() const { return device_locations_.size(); }
-    void memory_set(DeviceVector<Data64>&& v) { device_locations_ = std::move(v); }
     void get_data(std::vector<Data64>& out, cudaStream_t st = cudaStreamDefault) const
     {
         out.resize((size_t) cipher_size_ * coeff_modulus_count_ * ring_size_);
+        if (!is_on_device())
+        {
+            std::copy(host_data(), host_data() + out.size(), out.begin());
+            return;
+        }
         detail::cuda(cudaMemcpyAsync(out.data(), data(), out.size() * sizeof(Data64), cudaMemcpyDeviceToHost, st));
         detail::cuda(cudaStreamSynchronize(st));
     }
@@ -827,27 +1165,26 @@ template <> class Ciphertext<Scheme::BFV> {
     bool relinearization_required() const { return relinearization_required_; }
 
     HEContext<Scheme::BFV> context_;
-    DeviceVector<Data64> device_locations_;
     int ring_size_ = 0, coeff_modulus_count_ = 0, cipher_size_ = 0;
     bool in_ntt_domain_ = false, relinearization_required_ = false, ciphertext_generated_ = false;
 };
 
 // Plaintext<BFV>: [N] values below the plain modulus (bfv/plaintext.cu); batching encode is a client-side row.
-template <> class Plaintext<Scheme::BFV> {
+template <> class Plaintext<Scheme::BFV> : public detail::Storable {
   public:
     Plaintext() = default;
+    explicit Plaintext(HEContext<Scheme::BFV> ctx, const ExecutionOptions& = ExecutionOptions()) : context_(ctx) {}
     Plaintext(HEContext<Scheme::BFV> ctx, const std::vector<Data64>& words, const ExecutionOptions& opt = ExecutionOptions())
-        : context_(ctx), device_locations_(words, opt.stream_)
+        : context_(ctx)
     {
+        device_locations_ = DeviceVector<Data64>(words, opt.stream_);
         if (words.size() < (size_t) ctx->n)
             throw std::invalid_argument("Invalid Plaintext size!");
         plain_size_ = (int) words.size();
         plaintext_generated_ = true;
     }
-    Data64* data() const { return device_locations_.data(); }
-    size_t size() const { return device_locations_.size(); }
+    size_t size() const { return memory_size(); }
     HEContext<Scheme::BFV> context_;
-    DeviceVector<Data64> device_locations_;
     int plain_size_ = 0;
     bool in_ntt_domain_ = false, plaintext_generated_ = false;
 };
@@ -915,6 +1252,20 @@ template <> class Galoiskey<Scheme::BFV> {
             throw std::invalid_argument("Invalid galois key size!");
         device_location_[galois_element] = DeviceVector<Data64>(words, st);
     }
+    Galoiskey(HEContext<Scheme::BFV> ctx, const std::vector<uint32_t>& elts)
+        : context_(ctx), key_type(ctx->keyswitching_type_), custom_galois_elt(elts)
+    {
+        customized = true;
+        galois_elt_zero = 2 * ctx->n - 1;
+    }
+    // the column-rotation key (element 2N-1) lives in the same map (bfv/evaluationkey.cu)
+    void set_zero_key(int elt, DeviceVector<Data64>&& key)
+    {
+        device_location_[elt] = std::move(key);
+        galois_elt_zero = elt;
+    }
+    std::vector<uint32_t> custom_galois_elt;
+    bool galois_key_generated_ = false;
     HEContext<Scheme::BFV> context_;
     keyswitching_type key_type;
     storage_type storage_type_ = storage_type::DEVICE;
@@ -964,6 +1315,7 @@ template <> class HEOperator<Scheme::BFV> {
         detail::check(heon_negate(h(), a.data(), 0, mem.data(), 0, a.cipher_size_, 0, 1, opt.stream_));
         copy_meta(a, out);
         out.memory_set(std::move(mem));
+        detail::output_storage(out, opt);
     }
     void add_inplace(Ciphertext<Scheme::BFV>& a, Ciphertext<Scheme::BFV>& b, const ExecutionOptions& opt = ExecutionOptions())
     {
@@ -984,12 +1336,14 @@ template <> class HEOperator<Scheme::BFV> {
             throw std::invalid_argument("Ciphertexts should be in the coefficient domain!");
         if (a.memory_size() < words(2) || b.memory_size() < words(2))
             throw std::invalid_argument("Invalid Ciphertexts size!");
+        detail::InputGuard<Ciphertext<Scheme::BFV>> ga(a, opt, &a == &out), gb(b, opt, &b == &out);
         DeviceVector<Data64> mem(words(3), opt.stream_);
         detail::check(heon_bfv_multiply(h(), a.data(), 0, b.data(), 0, mem.data(), 0, 1, opt.stream_));
         copy_meta(a, out);
         out.memory_set(std::move(mem));
         out.cipher_size_ = 3;
         out.relinearization_required_ = true;
+        detail::output_storage(out, opt);
     }
     void multiply_inplace(Ciphertext<Scheme::BFV>& a, Ciphertext<Scheme::BFV>& b, const ExecutionOptions& opt = ExecutionOptions())
     {
@@ -1004,9 +1358,11 @@ template <> class HEOperator<Scheme::BFV> {
             throw std::invalid_argument("Relinkey is not generated!");
         if (ct.memory_size() < words(3))
             throw std::invalid_argument("Invalid Ciphertexts size!");
+        detail::InputGuard<Ciphertext<Scheme::BFV>> g(ct, opt, true);
         detail::check(heon_bfv_relinearize(h(), ct.data(), 0, rk.data(), 1, opt.stream_));
         ct.relinearization_required_ = false;
         ct.cipher_size_ = 2;
+        detail::output_storage(ct, opt);
     }
     // apply_galois_method_I/II, rotate_rows, rotate_columns (bfv/operator.cu:771-973)
     void apply_galois(Ciphertext<Scheme::BFV>& in, Ciphertext<Scheme::BFV>& out, Galoiskey<Scheme::BFV>& gk, int galois_elt,
@@ -1017,12 +1373,14 @@ template <> class HEOperator<Scheme::BFV> {
         auto it = gk.device_location_.find(galois_elt);
         if (it == gk.device_location_.end())
             throw std::logic_error("Galois key not present!");
+        detail::InputGuard<Ciphertext<Scheme::BFV>> g(in, opt, &in == &out);
         DeviceVector<Data64> mem(words(2), opt.stream_);
         detail::check(heon_bfv_apply_galois(h(), in.data(), 0, mem.data(), 0, it->second.data(), (uint32_t) galois_elt, 1,
                                             opt.stream_));
         copy_meta(in, out);
         out.memory_set(std::move(mem));
         out.cipher_size_ = 2;
+        detail::output_storage(out, opt);
     }
     void rotate_rows(Ciphertext<Scheme::BFV>& in, Ciphertext<Scheme::BFV>& out, Galoiskey<Scheme::BFV>& gk, int shift,
                      const ExecutionOptions& opt = ExecutionOptions())
@@ -1117,6 +1475,8 @@ template <> class HEOperator<Scheme::BFV> {
     void plain(Ciphertext<Scheme::BFV>& a, Plaintext<Scheme::BFV>& p, Ciphertext<Scheme::BFV>& out,
                const ExecutionOptions& opt, int op)
     {
+        detail::InputGuard<Ciphertext<Scheme::BFV>> ga(a, opt, &a == &out);
+        detail::InputGuard<Plaintext<Scheme::BFV>> gp(p, opt, false);
         const int comps = op == 0 ? 2 : (a.relinearization_required_ ? 3 : 2);
         if (a.memory_size() < words(comps))
             throw std::invalid_argument("Invalid Ciphertexts size!");
@@ -1135,6 +1495,7 @@ template <> class HEOperator<Scheme::BFV> {
     void binary(Ciphertext<Scheme::BFV>& a, Ciphertext<Scheme::BFV>& b, Ciphertext<Scheme::BFV>& out,
                 const ExecutionOptions& opt, int op)
     {
+        detail::InputGuard<Ciphertext<Scheme::BFV>> ga(a, opt, &a == &out), gb(b, opt, &b == &out);
         if (a.cipher_size_ != b.cipher_size_)
             throw std::invalid_argument("Ciphertexts should have the same size!");
         DeviceVector<Data64> mem(words(a.cipher_size_), opt.stream_);
@@ -1142,6 +1503,7 @@ template <> class HEOperator<Scheme::BFV> {
                                                       opt.stream_));
         copy_meta(a, out);
         out.memory_set(std::move(mem));
+        detail::output_storage(out, opt);
     }
 };
 
@@ -1152,3 +1514,5 @@ template <> class HEArithmeticOperator<Scheme::BFV> : public HEOperator<Scheme::
 };
 
 } // namespace heongpu
+
+#include "heongpu_client.hpp"

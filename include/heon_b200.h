@@ -251,6 +251,52 @@ int heon_bfv_multiply_plain(heon_context_t ctx, const uint64_t* ct, long long ct
 int heon_bfv_keyswitch(heon_context_t ctx, const uint64_t* in, long long in_stride, uint64_t* out,
                        long long out_stride, const uint64_t* switch_key, int batch, void* stream);
 
+/* ---- client side: key generation, encryption, decryption, encoding ------------
+ * Secret / public / evaluation keys in the reference's layouts, so they interoperate with every operator
+ * above.  Randomness is a counter-based generator seeded by the caller (reproducible); the reference draws
+ * from RNGonGPU's AES-CTR DRBG, so key WORDS differ by construction and parity here is decrypt-level.
+ *
+ * heon_keygen_secret: HEKeyGenerator::generate_secret_key (ckks/keygenerator.cu:28-82; kernels
+ *   keygeneration.cu:13-91).  sk: [Q'][N] NTT domain, ternary with `hamming_weight` non-zeros.
+ * heon_keygen_public: generate_public_key (ckks/keygenerator.cu:167-243, publickey_gen_kernel :93-116).
+ *   pk: [2][Q'][N] = (-(a*s + e), a).
+ * heon_keygen_relin: generate_relin_key Method I / II (ckks/keygenerator.cu:245-415; relinkey_gen_kernel
+ *   keygeneration.cu:145-185, relinkey_gen_II_kernel :584-629).  key: [d][2][Q'][N].
+ * heon_keygen_galois: generate_galois_key (ckks/keygenerator.cu:416-995; galoiskey_gen_kernel :757-860):
+ *   the key for apply_galois(galois_elt); heon_keygen_switch: generate_switch_key (:996-1200,
+ *   switchkey_gen_kernel :896-1030): re-encrypts a ciphertext under old_sk to new_sk. */
+int heon_keygen_secret(heon_context_t ctx, uint64_t seed, int hamming_weight, uint64_t* sk, void* stream);
+int heon_keygen_public(heon_context_t ctx, const uint64_t* sk, uint64_t seed, uint64_t* pk, void* stream);
+int heon_keygen_relin(heon_context_t ctx, const uint64_t* sk, uint64_t seed, uint64_t* key, void* stream);
+int heon_keygen_galois(heon_context_t ctx, const uint64_t* sk, uint32_t galois_elt, uint64_t seed, uint64_t* key,
+                       void* stream);
+int heon_keygen_switch(heon_context_t ctx, const uint64_t* new_sk, const uint64_t* old_sk, uint64_t seed,
+                       uint64_t* key, void* stream);
+/* HEEncryptor::encrypt (host/{ckks,bfv}/encryptor.cu; kernels encryption.cu): ct = round((pk*u + e)/P) + pt.
+ * CKKS: pt [Q][N] NTT domain, ct [2][Q][N] NTT domain.  BFV: pt [N] below the plain modulus, ct
+ * [2][Q][N] coefficient domain.  pt == NULL encrypts zero. */
+int heon_encrypt(heon_context_t ctx, const uint64_t* pk, const uint64_t* pt, uint64_t seed, uint64_t* ct,
+                 void* stream);
+/* HEDecryptor::decrypt (host/ckks/decryptor.cu; sk_multiplication_ckks decryption.cu:349-370):
+ * pt [L][N] NTT domain = c0 + c1*s (+ c2*s^2) at `depth`. */
+int heon_ckks_decrypt(heon_context_t ctx, const uint64_t* sk, const uint64_t* ct, int components, int depth,
+                      uint64_t* pt, void* stream);
+/* HEDecryptor<BFV>::decrypt (host/bfv/decryptor.cu): pt [N] = round(t/Q * [c0 + c1*s]_Q) mod t.  The
+ * final scaling runs on the host (exact CRT fraction); the call synchronises the stream. */
+int heon_bfv_decrypt(heon_context_t ctx, const uint64_t* sk, const uint64_t* ct, int components, uint64_t* pt,
+                     void* stream);
+/* HEEncoder<CKKS>::encode / decode (host/ckks/encoder.cu; kernels encoding.cu:43-400): canonical
+ * embedding with the 5^j slot order.  h_values / h_out: `count` complex slots as (re, im) pairs on the
+ * HOST; pt: [L][N] NTT domain on the device.  The FFT and the CRT composition run on the host. */
+int heon_ckks_encode(heon_context_t ctx, const double* h_values, int count, double scale, int depth, uint64_t* pt,
+                     void* stream);
+int heon_ckks_decode(heon_context_t ctx, const uint64_t* pt, int depth, double scale, double* h_out, int count,
+                     void* stream);
+/* HEEncoder<BFV>::encode / decode (host/bfv/encoder.cu; encode_kernel_bfv / decode_kernel_bfv
+ * encoding.cu:11-41): batching with generator 3 and the negacyclic transform modulo t. */
+int heon_bfv_encode(heon_context_t ctx, const uint64_t* h_message, int count, uint64_t* pt, void* stream);
+int heon_bfv_decode(heon_context_t ctx, const uint64_t* pt, uint64_t* h_message, int count, void* stream);
+
 /* Per-kernel-class CUDA-event profiler (used by bench.py for the roofline
  * line): begin() arms it, end() synchronises the device and returns, per
  * class, the summed device time in ms and the launch count; the return value

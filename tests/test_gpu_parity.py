@@ -306,7 +306,14 @@ def test_alternate_ntt_paths_agree(env):
 
 @pytest.mark.parametrize("name,env", [("n16_II_small", {"HEON_NTT_PIPE": 1}), ("n13_II", {"HEON_GALOIS_NTT": 0}),
                                       ("n16_I_small", {"HEON_GALOIS_NTT": 0}), ("n13_II", {"HEON_NTT_FP64": 0}),
-                                      ("n16_II_small", {"HEON_SKIP_OWN": 0}), ("n16_II_small", {"HEON_MAC_BY": 8})])
+                                      ("n16_II_small", {"HEON_SKIP_OWN": 0}), ("n16_II_small", {"HEON_MAC_BY": 8}),
+                                      # round 2: the fused row-pass + inner-product kernel against the separate kernels,
+                                      # its 4-row tiling, and the mod-up fused into the column-pass load
+                                      ("n16_II_small", {"HEON_ROW_MAC": 0}), ("n16_I_small", {"HEON_ROW_MAC": 0}),
+                                      ("n13_II", {"HEON_ROW_MAC": 0}), ("n16_II_small", {"HEON_ROW_MAC_ROWS": 4}),
+                                      ("n16_II_small", {"HEON_MODUP_FUSED": 1}), ("n13_II", {"HEON_MODUP_FUSED": 1}),
+                                      ("n16_II_small", {"HEON_MODUP_FUSED": 1, "HEON_SKIP_OWN": 0}),
+                                      ("n15_II", {"HEON_MODUP_FUSED": 1, "HEON_ROW_MAC": 0})])
 def test_alternate_operator_paths_agree(name, env):
     """multiply + relinearize + rotation through the alternate paths equal the default path."""
     api = _api()

@@ -1,0 +1,27 @@
+"""GPU: the reference's OWN test sources (/root/reference/test/test_{ckks,bfv}_*.cpp) compiled UNMODIFIED
+against this repository's class layer (heongpu.hpp + libheon_b200.so) by tests/cpp/build_reference_tests.sh
+in the build container; the binaries travel to the GPU box.  Each must exit 0 (every EXPECT of the
+reference test holds): the north-star's literal acceptance test for the class layer -- context, key
+generation, encoding, encryption, every operator of the hot path, decryption, decoding."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "_bin")
+NAMES = ["test_ckks_encoding", "test_ckks_encryption", "test_ckks_addition", "test_ckks_multiplication",
+         "test_ckks_relinearization", "test_ckks_rotation_method_1", "test_ckks_rotation_method_2",
+         "test_bfv_encoding", "test_bfv_encryption", "test_bfv_addition", "test_bfv_multiplication",
+         "test_bfv_relinearization", "test_bfv_rotation_method_1", "test_bfv_rotation_method_2"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_reference_test_source_passes_against_this_class_layer(name):
+    exe = os.path.join(BIN, name)
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/_bin not built (needs /root/reference at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0, tail
+    assert " 0 failed" in r.stdout, tail
