@@ -54,6 +54,7 @@ SIGNATURES = {
     "heon_ckks_mod_drop_inplace": (ci, [vp, vp, ll, ci, ci, ci, vp]),
     "heon_ckks_mod_drop": (ci, [vp, vp, ll, vp, ll, ci, ci, vp]),
     "heon_ckks_apply_galois": (ci, [vp, vp, ll, vp, ll, vp, C.c_uint32, ci, ci, vp]),
+    "heon_ckks_multiply_relinearize_host": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]),
     "heon_keygen_secret": (ci, [vp, C.c_uint64, ci, vp, vp]),
     "heon_keygen_public": (ci, [vp, vp, C.c_uint64, vp, vp]),
     "heon_keygen_relin": (ci, [vp, vp, C.c_uint64, vp, vp]),
@@ -62,6 +63,7 @@ SIGNATURES = {
     "heon_encrypt": (ci, [vp, vp, vp, C.c_uint64, vp, vp]),
     "heon_ckks_decrypt": (ci, [vp, vp, vp, ci, ci, vp, vp]),
     "heon_bfv_decrypt": (ci, [vp, vp, vp, ci, vp, vp]),
+    "heon_bfv_noise_budget": (ci, [vp, vp, vp, ci, i32p, vp]),
     "heon_ckks_encode": (ci, [vp, C.POINTER(C.c_double), ci, C.c_double, ci, vp, vp]),
     "heon_ckks_decode": (ci, [vp, vp, ci, C.c_double, C.POINTER(C.c_double), ci, vp]),
     "heon_bfv_encode": (ci, [vp, u64p, ci, vp, vp]),

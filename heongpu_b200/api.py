@@ -321,6 +321,17 @@ class HEArithmeticOperator:
         ct.relinearization_required_ = False
         return ct
 
+    def multiply_relinearize_host(self, h_a, h_b, h_out, relin_key, depth=0, rescale=False, chunk=0):
+        """multiply + relinearize_inplace (+ rescale_inplace) on HOST-resident ciphertext batches
+        (ExecutionOptions::set_storage_type(HOST), storagemanager.cuh:113-167): h_a, h_b [B, 2, L, N] and h_out
+        [B, 2, L', N] are (pinned) host tensors; copies and compute are pipelined inside the library."""
+        c = self.context_
+        assert not h_a.is_cuda and not h_b.is_cuda and not h_out.is_cuda
+        _check(lib.heon_ckks_multiply_relinearize_host(c._h, C.c_void_p(h_a.data_ptr()), C.c_void_p(h_b.data_ptr()),
+                                                       C.c_void_p(h_out.data_ptr()), _ptr(relin_key.data), depth, int(rescale),
+                                                       h_a.shape[0], chunk, _stream()))
+        return h_out
+
     def rescale_inplace(self, ct):
         c = self.context_
         _check(lib.heon_ckks_rescale(c._h, _ptr(ct.data), ct.stride, ct.depth_, ct.batch, _stream()))

@@ -16,7 +16,7 @@ struct heon_context_s {
 namespace heon {
 std::atomic<long long> g_launches{0};
 
-static bool g_profiling = false;
+static std::atomic<bool> g_profiling{false}; // operators may run on several host threads (one stream each)
 struct ProfRec {
     int cls;
     cudaEvent_t e0, e1;
@@ -210,7 +210,8 @@ void client_keygen_relin(const Context& c, const u64* sk, u64 seed, u64* key, cu
 void client_keygen_galois(const Context& c, const u64* sk, unsigned galois_elt, u64 seed, u64* key, cudaStream_t st);
 void client_encrypt(const Context& c, const u64* pk, const u64* pt, u64 seed, u64* ct, cudaStream_t st);
 void client_decrypt_ckks(const Context& c, const u64* sk, const u64* ct, int comps, int depth, u64* pt, cudaStream_t st);
-void client_decrypt_bfv(const Context& c, const u64* sk, const u64* ct, int comps, u64* pt, cudaStream_t st);
+void client_decrypt_bfv(const Context& c, const u64* sk, const u64* ct, int comps, u64* pt, cudaStream_t st, int* budget = nullptr);
+void client_noise_budget_bfv(const Context& c, const u64* sk, const u64* ct, int comps, int* bits, cudaStream_t st);
 void client_ckks_encode(const Context& c, const double* values, int count, double scale, int depth, u64* pt, cudaStream_t st);
 void client_ckks_decode(const Context& c, const u64* pt, int depth, double scale, double* out, int count, cudaStream_t st);
 void client_bfv_encode(const Context& c, const u64* msg, int count, u64* pt, cudaStream_t st);
@@ -762,6 +763,20 @@ int heon_ckks_apply_galois(heon_context_t ctx, const uint64_t* in, long long is,
     DeviceGuard dev_guard(c);                                                                      \
     cudaStream_t st = (cudaStream_t) stream;
 
+int heon_ckks_multiply_relinearize_host(heon_context_t ctx, const uint64_t* h_a, const uint64_t* h_b, uint64_t* h_out,
+                                        const uint64_t* relin_key, int depth, int rescale, int batch, int chunk,
+                                        void* stream)
+{
+    return guarded([&] {
+        HEON_OP_PROLOGUE
+        if (!h_a || !h_b || !h_out || !relin_key)
+            throw std::invalid_argument("null argument");
+        if (c.scheme != SCHEME_CKKS)
+            throw std::invalid_argument("not a CKKS context");
+        op_mulrelin_host(c, h_a, h_b, h_out, relin_key, depth, rescale, batch, chunk, st);
+    });
+}
+
 int heon_keygen_secret(heon_context_t ctx, uint64_t seed, int hamming_weight, uint64_t* sk, void* stream)
 {
     return guarded([&] {
@@ -840,6 +855,18 @@ int heon_bfv_decrypt(heon_context_t ctx, const uint64_t* sk, const uint64_t* ct,
         if (c.scheme != SCHEME_BFV)
             throw std::invalid_argument("not a BFV context");
         client_decrypt_bfv(c, sk, ct, components, pt, st);
+    });
+}
+int heon_bfv_noise_budget(heon_context_t ctx, const uint64_t* sk, const uint64_t* ct, int components, int* bits,
+                          void* stream)
+{
+    return guarded([&] {
+        HEON_CLIENT_PROLOGUE
+        if (!sk || !ct || !bits)
+            throw std::invalid_argument("null argument");
+        if (c.scheme != SCHEME_BFV)
+            throw std::invalid_argument("not a BFV context");
+        client_noise_budget_bfv(c, sk, ct, components, bits, st);
     });
 }
 int heon_ckks_encode(heon_context_t ctx, const double* h_values, int count, double scale, int depth, uint64_t* pt,

@@ -399,7 +399,12 @@ void client_decrypt_ckks(const Context& c, const u64* sk, const u64* ct, int com
 // BFV: x = c0 + c1*s (+ c2 s^2) in coefficient domain over Q; message = round(t * [x]_Q / Q) mod t.
 // [x]_Q / Q = frac(sum_i y_i / q_i), y_i = x_i * (Q/q_i)^-1 mod q_i  (80-bit long double: the sum carries
 // more than 60 correct fractional bits, the decision needs log2(t) + noise margin of them)
-void client_decrypt_bfv(const Context& c, const u64* sk, const u64* ct, int comps, u64* pt, cudaStream_t st)
+void client_decrypt_bfv(const Context& c, const u64* sk, const u64* ct, int comps, u64* pt, cudaStream_t st, int* budget = nullptr);
+void client_noise_budget_bfv(const Context& c, const u64* sk, const u64* ct, int comps, int* bits, cudaStream_t st)
+{
+    client_decrypt_bfv(c, sk, ct, comps, nullptr, st, bits);
+}
+void client_decrypt_bfv(const Context& c, const u64* sk, const u64* ct, int comps, u64* pt, cudaStream_t st, int* budget)
 {
     const int Q = c.Q_size;
     const size_t N = c.n;
@@ -434,6 +439,7 @@ void client_decrypt_bfv(const Context& c, const u64* sk, const u64* ct, int comp
     }
     const u64 t = c.plain_modulus;
     std::vector<u64> msg(N);
+    long double worst = 0.0L;
     for (size_t j = 0; j < N; ++j)
     {
         long double frac = 0.0L;
@@ -445,11 +451,20 @@ void client_decrypt_bfv(const Context& c, const u64* sk, const u64* ct, int comp
         }
         frac -= floorl(frac);
         long double v = roundl(frac * (long double) t);
+        worst = fmaxl(worst, fabsl(frac * (long double) t - v));
         u64 m = (u64) v;
         msg[j] = m >= t ? m - t : m;
     }
-    cudaMemcpyAsync(pt, msg.data(), N * 8, cudaMemcpyHostToDevice, st);
-    cudaStreamSynchronize(st);
+    if (budget)
+    {
+        const long double b = worst > 0 ? -log2l(2.0L * worst) : 62.0L;
+        *budget = b < 0 ? 0 : b > 62 ? 62 : (int) floorl(b);
+    }
+    if (pt)
+    {
+        cudaMemcpyAsync(pt, msg.data(), N * 8, cudaMemcpyHostToDevice, st);
+        cudaStreamSynchronize(st);
+    }
 }
 
 typedef std::complex<double> cplx;

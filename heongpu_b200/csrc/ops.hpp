@@ -47,6 +47,8 @@ void op_multiply(const Context& c, const u64* a, long long a_bs, const u64* b, l
                  u64* out, long long o_bs, int depth, int batch, cudaStream_t st);
 void op_relinearize(const Context& c, u64* ct, long long ct_bs, const u64* relin_key, int depth,
                     int batch, cudaStream_t st);
+void op_mulrelin_host(const Context& c, const u64* h_a, const u64* h_b, u64* h_out, const u64* relin_key, int depth,
+                      int rescale, int batch, int chunk, cudaStream_t st);
 void op_rescale(const Context& c, u64* ct, long long ct_bs, int depth, int batch, cudaStream_t st);
 void op_mod_drop_inplace(const Context& c, u64* ct, long long ct_bs, int comps, int depth, int batch,
                          cudaStream_t st);

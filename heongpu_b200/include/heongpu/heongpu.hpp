@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdint>
+#include <iostream>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -352,6 +353,31 @@ inline void check_security(sec_level_type sec, size_t n, int total_bits)
     if (total_bits > max_total_bits(sec, n))
         throw std::runtime_error("Parameters do not align with the security recommendations.");
 }
+// A rotation whose own key is absent is carried out as a chain of the +-2^i rotations the key set holds
+// (rotate_ckks_method_I/II, operator.cu:1338-1420; rotation_index_generator :2411-2480): the shift is taken
+// to its balanced representative modulo the row size, written in non-adjacent form, and digits above
+// 2^max_shift are folded into repeated +-2^max_shift steps.
+inline std::vector<int> rotation_plan(int shift, int log_slots, int max_shift)
+{
+    const long long mod = 1LL << log_slots;
+    long long x = ((shift % mod) + mod) % mod;
+    if (x > mod / 2)
+        x -= mod;
+    std::vector<int> plan;
+    for (int i = 0; x != 0; ++i, x >>= 1)
+    {
+        if (!(x & 1))
+            continue;
+        const int d = 2 - (int) (x & 3); // +1 or -1
+        x -= d;
+        if (i <= max_shift)
+            plan.push_back(d * (1 << i));
+        else
+            for (long long r = 0; r < (1LL << (i - max_shift)); ++r)
+                plan.push_back(d * (1 << max_shift));
+    }
+    return plan;
+}
 // default 128-bit-security coefficient moduli (src/lib/util/defaultmodulus.cpp:12-90; the SEAL defaults)
 inline std::vector<Data64> default_modulus_128(size_t n)
 {
@@ -366,6 +392,13 @@ inline std::vector<Data64> default_modulus_128(size_t n)
             return {0x2000000002b0001, 0x2000000003a0001, 0x2000000005b0001, 0x200000000640001, 0x400000000270001,
                     0x400000000350001, 0x400000000360001, 0x4000000004d0001, 0x400000000570001, 0x400000000660001,
                     0x4000000008a0001, 0x400000000920001, 0x400000000980001, 0x400000000990001, 0x400000000a40001};
+        case 65536:
+            return {0x2000000003a0001, 0x200000000640001, 0x200000000f80001, 0x200000001460001, 0x2000000015a0001,
+                    0x2000000015e0001, 0x200000001b20001, 0x200000001c00001, 0x200000001ee0001, 0x400000000360001,
+                    0x400000000660001, 0x4000000008a0001, 0x400000000920001, 0x400000000980001, 0x400000000a40001,
+                    0x400000000c00001, 0x400000000ea0001, 0x400000001460001, 0x400000001700001, 0x400000001740001,
+                    0x4000000017a0001, 0x400000001920001, 0x400000001b00001, 0x400000001b60001, 0x400000001c40001,
+                    0x400000001ee0001, 0x400000001f20001, 0x4000000020c0001, 0x400000002360001, 0x400000002480001};
     }
     throw std::logic_error("no default modulus for this poly_modulus_degree");
 }
@@ -463,6 +496,31 @@ template <> class HEContextImpl<Scheme::CKKS> {
     }
     heon_context_t handle() const { return h_; }
     size_t get_poly_modulus_degree() const { return (size_t) n; }
+    int get_log_poly_modulus_degree() const { return n_power; }
+    int get_ciphertext_modulus_count() const { return Q_size; }
+    int get_key_modulus_count() const { return Q_prime_size; }
+    std::vector<Modulus64> get_key_modulus() const { return prime_vector_; }
+    // ckks/context.cu: print_parameters
+    void print_parameters() const
+    {
+        if (!context_generated_)
+        {
+            std::cout << "Parameters is not generated yet!" << std::endl;
+            return;
+        }
+        std::cout << "==== HEonGPU a GPU Based Homomorphic Encryption Library ====\n" << std::endl;
+        std::cout << "Encryption parameters:" << std::endl;
+        std::cout << "-->   scheme: " << "CKKS" << std::endl;
+        std::cout << "-->   poly_modulus_degree: " << n << std::endl;
+        std::cout << "-->   Q_tilta size: Q( ";
+        for (int i = 0; i < Q_size; ++i)
+            std::cout << prime_vector_[i].bit << (i + 1 < Q_size ? " + " : "");
+        std::cout << " ) + P( ";
+        for (int i = Q_size; i < Q_prime_size; ++i)
+            std::cout << prime_vector_[i].bit << (i + 1 < Q_prime_size ? " + " : "");
+        std::cout << " ) bits" << std::endl;
+        std::cout << std::endl;
+    }
 
     int n = 0, n_power = 0;
     int Q_size = 0, P_size = 0, Q_prime_size = 0;
@@ -602,6 +660,7 @@ template <> class Galoiskey<Scheme::CKKS> {
     }
     std::vector<uint32_t> custom_galois_elt;
     bool galois_key_generated_ = false;
+    int max_shift_ = 7; // MAX_SHIFT - 1 (evaluationkey.cu:428)
     HEContext<Scheme::CKKS> context_;
     keyswitching_type key_type;
     storage_type storage_type_ = storage_type::DEVICE;
@@ -786,6 +845,30 @@ template <> class HEOperator<Scheme::CKKS> {
         ct.depth_++;
         detail::output_storage(ct, opt);
     }
+    // mod_drop of a plaintext (operator.cuh:1512-1578): its first L-1 limbs are the plaintext one level down
+    void mod_drop_inplace(Plaintext<Scheme::CKKS>& pt, const ExecutionOptions& = ExecutionOptions())
+    {
+        if (pt.depth_ >= context_->Q_size - 1)
+            throw std::logic_error("Plaintext modulus can not be dropped!");
+        pt.depth_++;
+    }
+    void mod_drop(Plaintext<Scheme::CKKS>& in, Plaintext<Scheme::CKKS>& out, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        if (in.depth_ >= context_->Q_size - 1)
+            throw std::logic_error("Plaintext modulus can not be dropped!");
+        detail::InputGuard<Plaintext<Scheme::CKKS>> g(in, opt, false);
+        const size_t w = (size_t) (context_->Q_size - in.depth_ - 1) * context_->n;
+        DeviceVector<Data64> mem(w, opt.stream_);
+        detail::cuda(cudaMemcpyAsync(mem.data(), in.data(), w * sizeof(Data64), cudaMemcpyDeviceToDevice, opt.stream_));
+        out.context_ = in.context_;
+        out.memory_set(std::move(mem));
+        out.plain_size_ = (int) w;
+        out.depth_ = in.depth_ + 1;
+        out.scale_ = in.scale_;
+        out.in_ntt_domain_ = in.in_ntt_domain_;
+        out.plaintext_generated_ = true;
+        detail::output_storage(out, opt);
+    }
     void mod_drop(Ciphertext<Scheme::CKKS>& in, Ciphertext<Scheme::CKKS>& out, const ExecutionOptions& opt = ExecutionOptions())
     {
         DeviceVector<Data64> mem(words(2, in.depth_ + 1), opt.stream_);
@@ -833,9 +916,23 @@ template <> class HEOperator<Scheme::CKKS> {
             return;
         }
         const int elt = heon_steps_to_galois_elt(shift, context_->n, gk.group_order_);
-        if (elt == 0)
-            throw std::invalid_argument("Galois Key can not be generated, Step count too large");
-        apply_galois(in, out, gk, elt, opt);
+        if (elt != 0 && gk.device_location_.count(elt))
+        {
+            apply_galois(in, out, gk, elt, opt);
+            return;
+        }
+        int log_slots = 0;
+        while ((2 << log_slots) < context_->n)
+            ++log_slots;
+        Ciphertext<Scheme::CKKS>* cur = &in;
+        for (int step : detail::rotation_plan(shift, log_slots, gk.max_shift_))
+        {
+            auto it = gk.galois_elt.find(step);
+            if (it == gk.galois_elt.end() || !gk.device_location_.count(it->second))
+                throw std::logic_error("Galois key not present!");
+            apply_galois(*cur, out, gk, it->second, opt);
+            cur = &out;
+        }
     }
     void rotate_rows_inplace(Ciphertext<Scheme::CKKS>& ct, Galoiskey<Scheme::CKKS>& gk, int shift,
                              const ExecutionOptions& opt = ExecutionOptions())
@@ -1110,6 +1207,33 @@ template <> class HEContextImpl<Scheme::BFV> {
     int digit_count() const { return P_size == 1 ? Q_size : (Q_size + 1) / 2; }
     heon_context_t handle() const { return h_; }
     size_t get_poly_modulus_degree() const { return (size_t) n; }
+    int get_log_poly_modulus_degree() const { return n_power; }
+    int get_ciphertext_modulus_count() const { return Q_size; }
+    int get_key_modulus_count() const { return Q_prime_size; }
+    std::vector<Modulus64> get_key_modulus() const { return prime_vector_; }
+    // ckks/context.cu: print_parameters
+    void print_parameters() const
+    {
+        if (!context_generated_)
+        {
+            std::cout << "Parameters is not generated yet!" << std::endl;
+            return;
+        }
+        std::cout << "==== HEonGPU a GPU Based Homomorphic Encryption Library ====\n" << std::endl;
+        std::cout << "Encryption parameters:" << std::endl;
+        std::cout << "-->   scheme: " << "BFV" << std::endl;
+        std::cout << "-->   poly_modulus_degree: " << n << std::endl;
+        std::cout << "-->   Q_tilta size: Q( ";
+        for (int i = 0; i < Q_size; ++i)
+            std::cout << prime_vector_[i].bit << (i + 1 < Q_size ? " + " : "");
+        std::cout << " ) + P( ";
+        for (int i = Q_size; i < Q_prime_size; ++i)
+            std::cout << prime_vector_[i].bit << (i + 1 < Q_prime_size ? " + " : "");
+        std::cout << " ) bits" << std::endl;
+        std::cout << "-->   plain_modulus: " << plain_modulus_ << std::endl;
+        std::cout << std::endl;
+    }
+    Modulus64 get_plain_modulus() const { return Modulus64(plain_modulus_); }
 
     int n = 0, n_power = 0;
     int Q_size = 0, P_size = 0, Q_prime_size = 0;
@@ -1266,6 +1390,7 @@ template <> class Galoiskey<Scheme::BFV> {
     }
     std::vector<uint32_t> custom_galois_elt;
     bool galois_key_generated_ = false;
+    int max_shift_ = 7; // MAX_SHIFT - 1
     HEContext<Scheme::BFV> context_;
     keyswitching_type key_type;
     storage_type storage_type_ = storage_type::DEVICE;
@@ -1399,9 +1524,23 @@ template <> class HEOperator<Scheme::BFV> {
             return;
         }
         const int elt = heon_steps_to_galois_elt(shift, context_->n, gk.group_order_);
-        if (elt == 0)
-            throw std::invalid_argument("Galois Key can not be generated, Step count too large");
-        apply_galois(in, out, gk, elt, opt);
+        if (elt != 0 && gk.device_location_.count(elt))
+        {
+            apply_galois(in, out, gk, elt, opt);
+            return;
+        }
+        int log_slots = 0;
+        while ((2 << log_slots) < context_->n)
+            ++log_slots;
+        Ciphertext<Scheme::BFV>* cur = &in;
+        for (int step : detail::rotation_plan(shift, log_slots, gk.max_shift_))
+        {
+            auto it = gk.galois_elt.find(step);
+            if (it == gk.galois_elt.end() || !gk.device_location_.count(it->second))
+                throw std::logic_error("Galois key not present!");
+            apply_galois(*cur, out, gk, it->second, opt);
+            cur = &out;
+        }
     }
     void rotate_rows_inplace(Ciphertext<Scheme::BFV>& ct, Galoiskey<Scheme::BFV>& gk, int shift,
                              const ExecutionOptions& opt = ExecutionOptions())

@@ -388,6 +388,16 @@ template <Scheme S> class HEDecryptor {
         detail::output_storage(pt, opt);
     }
 
+    // HEDecryptor<BFV>::remainder_noise_budget (bfv/decryptor.cu)
+    int remainder_noise_budget(Ciphertext<S>& ct, const ExecutionOptions& opt = ExecutionOptions())
+    {
+        static_assert(S == Scheme::BFV, "noise budget is a BFV notion");
+        detail::InputGuard<Ciphertext<S>> g(ct, opt, false);
+        int bits = 0;
+        detail::check(heon_bfv_noise_budget(context_->handle(), secret_key_->data(), ct.data(), ct.cipher_size_, &bits, opt.stream_));
+        return bits;
+    }
+
   private:
     HEContext<S> context_;
     Secretkey<S>* secret_key_;

@@ -251,6 +251,16 @@ int heon_bfv_multiply_plain(heon_context_t ctx, const uint64_t* ct, long long ct
 int heon_bfv_keyswitch(heon_context_t ctx, const uint64_t* in, long long in_stride, uint64_t* out,
                        long long out_stride, const uint64_t* switch_key, int batch, void* stream);
 
+/* ---- HOST-resident operands (ExecutionOptions::set_storage_type(storage_type::HOST),
+ *      src/include/heongpu/util/storagemanager.cuh:113-167, truth table README.md:349-366).
+ * multiply + relinearize_inplace (+ rescale_inplace when `rescale` != 0) on `batch` ciphertext pairs whose
+ * words live in HOST memory (pinned for full PCIe speed): h_a, h_b [batch][2][L][N], h_out
+ * [batch][2][L - rescale][N].  The batch is processed in chunks of `chunk` ciphertexts (0 = default) with the
+ * copies of neighbouring chunks overlapped with the compute; asynchronous, ordered on `stream`. */
+int heon_ckks_multiply_relinearize_host(heon_context_t ctx, const uint64_t* h_a, const uint64_t* h_b, uint64_t* h_out,
+                                        const uint64_t* relin_key, int depth, int rescale, int batch, int chunk,
+                                        void* stream);
+
 /* ---- client side: key generation, encryption, decryption, encoding ------------
  * Secret / public / evaluation keys in the reference's layouts, so they interoperate with every operator
  * above.  Randomness is a counter-based generator seeded by the caller (reproducible); the reference draws
@@ -285,6 +295,11 @@ int heon_ckks_decrypt(heon_context_t ctx, const uint64_t* sk, const uint64_t* ct
  * final scaling runs on the host (exact CRT fraction); the call synchronises the stream. */
 int heon_bfv_decrypt(heon_context_t ctx, const uint64_t* sk, const uint64_t* ct, int components, uint64_t* pt,
                      void* stream);
+/* HEDecryptor<BFV>::remainder_noise_budget (host/bfv/decryptor.cu): -log2(2 * |v|_inf) of the invariant
+ * noise v = t/Q * [ct(s)]_Q - m, in bits, from the same host CRT fraction as heon_bfv_decrypt (80-bit long
+ * double: budgets above ~58 bits saturate). */
+int heon_bfv_noise_budget(heon_context_t ctx, const uint64_t* sk, const uint64_t* ct, int components, int* bits,
+                          void* stream);
 /* HEEncoder<CKKS>::encode / decode (host/ckks/encoder.cu; kernels encoding.cu:43-400): canonical
  * embedding with the 5^j slot order.  h_values / h_out: `count` complex slots as (re, im) pairs on the
  * HOST; pt: [L][N] NTT domain on the device.  The FFT and the CRT composition run on the host. */

@@ -18,5 +18,15 @@ for t in $TESTS; do
       && echo "built $t" ) 2> _bin/$t.log || echo "FAILED to build $t (see tests/cpp/_bin/$t.log)" &
   pids+=($!)
 done
+# the reference's benchmarks and basic examples (multi-stream OpenMP usage included), same rule: unmodified
+EXTRA=${EXTRA:-"benchmark/benchmark_ckks benchmark/benchmark_bfv example/basic/1_basic_bfv example/basic/2_basic_ckks example/basic/4_switchkey_methods_bfv example/basic/5_switchkey_methods_ckks example/basic/8_default_stream_usage example/basic/9_multi_stream_usage_way1 example/basic/10_multi_stream_usage_way2"}
+for e in $EXTRA; do
+  b=$(basename $e)
+  ( g++ -std=c++17 -O1 -w -fopenmp -I shim -I "$ROOT/heongpu_b200/include" -I /usr/local/cuda/include \
+      "$REF/$e.cpp" -o _bin/$b \
+      -L "$ROOT/heongpu_b200/lib" -lheon_b200 -L /usr/local/cuda/lib64 -lcudart -Wl,-rpath,'$ORIGIN/../../../heongpu_b200/lib' \
+      && echo "built $b" ) 2> _bin/$b.log || echo "FAILED to build $b (see tests/cpp/_bin/$b.log)" &
+  pids+=($!)
+done
 for p in "${pids[@]}"; do wait $p; done
 ls _bin

@@ -21,7 +21,33 @@ def test_reference_test_source_passes_against_this_class_layer(name):
     exe = os.path.join(BIN, name)
     if not os.path.exists(exe):
         pytest.skip("tests/cpp/_bin not built (needs /root/reference at build time)")
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    # test_bfv_addition.cpp computes its own expectation with `sum > t ? sum - t : sum`, which is wrong when
+    # m1 + m2 == t (probability ~ N/t per block, ~16 % per run over its five blocks); this engine's exact
+    # result is pinned by tests/test_client_side.py.  A run that trips on it is repeated.
+    tries = 4 if name == "test_bfv_addition" else 1
+    for _ in range(tries):
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+        if r.returncode == 0:
+            break
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     assert " 0 failed" in r.stdout, tail
+
+
+EXTRA = ["benchmark_ckks", "benchmark_bfv", "1_basic_bfv", "2_basic_ckks", "4_switchkey_methods_bfv",
+         "5_switchkey_methods_ckks", "8_default_stream_usage", "9_multi_stream_usage_way1", "10_multi_stream_usage_way2"]
+
+
+@pytest.mark.parametrize("name", EXTRA)
+def test_reference_benchmarks_and_examples_run_against_this_class_layer(name):
+    """benchmark/benchmark_{ckks,bfv}.cpp and example/basic/*.cpp, unmodified: they must run to completion
+    (the multi-stream examples drive one operator object from several OpenMP threads, one stream each)."""
+    exe = os.path.join(BIN, name)
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/_bin not built (needs /root/reference at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    out_dir = os.path.join(os.path.dirname(BIN), "..", "..", "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, f"refcpp_{name}.txt"), "w") as f:
+            f.write(r.stdout[-20000:])
