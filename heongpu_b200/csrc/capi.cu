@@ -4,6 +4,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/heon_b200.h"
 #include "ops.hpp"
 
@@ -75,8 +76,16 @@ void profile_end(double* ms, long long* launches)
 
 static thread_local std::string g_err;
 
-template <class F> static int guarded(F&& f)
+// One NVTX range per ABI call (header-only NVTX3: a no-op unless a profiler is attached), named after the
+// entry point, so Nsight timelines show the operator structure the reference's tracing shows.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
+template <class F> static int guarded_named(const char* name, F&& f)
 {
+    NvtxRange range(name);
     try
     {
         f();
@@ -98,6 +107,7 @@ template <class F> static int guarded(F&& f)
         return HEON_ERR_RUNTIME;
     }
 }
+#define guarded(...) guarded_named(__func__, __VA_ARGS__)
 
 // Makes the context's device current for the duration of one ABI call and restores the caller's
 // device afterwards; also drops any stale error a previous, unrelated CUDA call left on this thread, so
