@@ -68,6 +68,9 @@ SIGNATURES = {
     "heon_ckks_decode": (ci, [vp, vp, ci, C.c_double, C.POINTER(C.c_double), ci, vp]),
     "heon_bfv_encode": (ci, [vp, u64p, ci, vp, vp]),
     "heon_bfv_decode": (ci, [vp, vp, u64p, ci, vp]),
+    "heon_compress_bound": (C.c_size_t, [C.c_size_t]),
+    "heon_compress": (ci, [vp, C.c_size_t, vp, C.POINTER(C.c_size_t)]),
+    "heon_decompress": (ci, [vp, C.c_size_t, vp, C.POINTER(C.c_size_t)]),
     "heon_profile_begin": (ci, []),
     "heon_profile_end": (ci, [C.POINTER(C.c_double), i64p, ci]),
     "heon_profile_class_name": (C.c_char_p, [ci]),

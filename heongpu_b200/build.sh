@@ -16,5 +16,5 @@ for f in $SRCS; do
 done
 for p in "${pids[@]}"; do wait $p; done
 OBJS=""; for f in $SRCS; do OBJS="$OBJS $OBJ/$f.o"; done
-$NVCC $FLAGS -shared $OBJS -o lib/$OUT
+$NVCC $FLAGS -shared $OBJS -o lib/$OUT -lz
 echo "built $(pwd)/lib/$OUT"

@@ -5,6 +5,7 @@
 #include <memory>
 #include <mutex>
 #include <nvtx3/nvToolsExt.h>
+#include <zlib.h>
 #include "../../include/heon_b200.h"
 #include "ops.hpp"
 
@@ -920,6 +921,31 @@ int heon_bfv_decode(heon_context_t ctx, const uint64_t* pt, uint64_t* h_message,
             throw std::invalid_argument("null argument");
         client_bfv_decode(c, pt, h_message, count, st);
     });
+}
+
+size_t heon_compress_bound(size_t n) { return (size_t) compressBound((uLong) n); }
+int heon_compress(const uint8_t* in, size_t n, uint8_t* out, size_t* out_len)
+{
+    if (!in || !out || !out_len)
+        return HEON_ERR_INVALID;
+    uLongf len = (uLongf) *out_len;
+    if (::compress(out, &len, in, (uLong) n) != Z_OK)
+        return HEON_ERR_RUNTIME;
+    *out_len = (size_t) len;
+    return HEON_OK;
+}
+int heon_decompress(const uint8_t* in, size_t n, uint8_t* out, size_t* out_len)
+{
+    if (!in || !out || !out_len)
+        return HEON_ERR_INVALID;
+    uLongf len = (uLongf) *out_len;
+    const int rc = ::uncompress(out, &len, in, (uLong) n);
+    if (rc == Z_BUF_ERROR)
+        return HEON_ERR_LOGIC; // output buffer too small: the caller retries with a larger one
+    if (rc != Z_OK)
+        return HEON_ERR_RUNTIME;
+    *out_len = (size_t) len;
+    return HEON_OK;
 }
 
 int heon_profile_begin(void)

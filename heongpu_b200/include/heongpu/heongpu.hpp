@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdint>
+#include <iosfwd>
 #include <iostream>
 #include <memory>
 #include <stdexcept>
@@ -546,6 +547,8 @@ template <Scheme S> class Ciphertext;
 template <> class Ciphertext<Scheme::CKKS> : public detail::Storable {
   public:
     Ciphertext() = default;
+    void save(std::ostream& os) const;
+    void load(std::istream& is);
     // empty ciphertext bound to a context (ckks/ciphertext.cu:8-31); filled by the encryptor / operators
     explicit Ciphertext(HEContext<Scheme::CKKS> ctx, const ExecutionOptions& = ExecutionOptions()) : context_(ctx)
     {
@@ -596,6 +599,8 @@ template <Scheme S> class Relinkey;
 template <> class Relinkey<Scheme::CKKS> {
   public:
     explicit Relinkey(HEContext<Scheme::CKKS> ctx) : context_(ctx), key_type(ctx->keyswitching_type_) {}
+    void save(std::ostream& os) const;
+    void load(std::istream& is);
     // [digit][2][Q'_0][N] NTT-domain words (keygeneration.cu:180-183)
     void set_data(const std::vector<Data64>& words, cudaStream_t st = cudaStreamDefault)
     {
@@ -658,6 +663,9 @@ template <> class Galoiskey<Scheme::CKKS> {
         zero_device_location_ = std::move(key);
         galois_elt_zero = elt;
     }
+    const Data64* zero_key_data() const { return zero_device_location_.data(); }
+    void save(std::ostream& os) const;
+    void load(std::istream& is);
     std::vector<uint32_t> custom_galois_elt;
     bool galois_key_generated_ = false;
     int max_shift_ = 7; // MAX_SHIFT - 1 (evaluationkey.cu:428)
@@ -678,6 +686,8 @@ template <Scheme S> class Plaintext;
 template <> class Plaintext<Scheme::CKKS> : public detail::Storable {
   public:
     Plaintext() = default;
+    void save(std::ostream& os) const;
+    void load(std::istream& is);
     explicit Plaintext(HEContext<Scheme::CKKS> ctx, const ExecutionOptions& = ExecutionOptions()) : context_(ctx) {}
     Plaintext(HEContext<Scheme::CKKS> ctx, const std::vector<Data64>& words, int depth = 0, double scale = 1.0,
               const ExecutionOptions& opt = ExecutionOptions())
@@ -1255,6 +1265,8 @@ template <> class HEContextImpl<Scheme::BFV> {
 template <> class Ciphertext<Scheme::BFV> : public detail::Storable {
   public:
     Ciphertext() = default;
+    void save(std::ostream& os) const;
+    void load(std::istream& is);
     explicit Ciphertext(HEContext<Scheme::BFV> ctx, const ExecutionOptions& = ExecutionOptions()) : context_(ctx)
     {
         ring_size_ = ctx->n;
@@ -1297,6 +1309,8 @@ template <> class Ciphertext<Scheme::BFV> : public detail::Storable {
 template <> class Plaintext<Scheme::BFV> : public detail::Storable {
   public:
     Plaintext() = default;
+    void save(std::ostream& os) const;
+    void load(std::istream& is);
     explicit Plaintext(HEContext<Scheme::BFV> ctx, const ExecutionOptions& = ExecutionOptions()) : context_(ctx) {}
     Plaintext(HEContext<Scheme::BFV> ctx, const std::vector<Data64>& words, const ExecutionOptions& opt = ExecutionOptions())
         : context_(ctx)
@@ -1316,6 +1330,8 @@ template <> class Plaintext<Scheme::BFV> : public detail::Storable {
 template <> class Relinkey<Scheme::BFV> {
   public:
     explicit Relinkey(HEContext<Scheme::BFV> ctx) : context_(ctx), key_type(ctx->keyswitching_type_) {}
+    void save(std::ostream& os) const;
+    void load(std::istream& is);
     void set_data(const std::vector<Data64>& words, cudaStream_t st = cudaStreamDefault)
     {
         const size_t need = (size_t) context_->digit_count() * 2 * context_->Q_prime_size * context_->n;
@@ -1388,6 +1404,15 @@ template <> class Galoiskey<Scheme::BFV> {
         device_location_[elt] = std::move(key);
         galois_elt_zero = elt;
     }
+    const Data64* zero_key_data() const
+    {
+        auto it = device_location_.find(galois_elt_zero);
+        if (it == device_location_.end())
+            throw std::logic_error("Galois key not present!");
+        return it->second.data();
+    }
+    void save(std::ostream& os) const;
+    void load(std::istream& is);
     std::vector<uint32_t> custom_galois_elt;
     bool galois_key_generated_ = false;
     int max_shift_ = 7; // MAX_SHIFT - 1
@@ -1655,3 +1680,4 @@ template <> class HEArithmeticOperator<Scheme::BFV> : public HEOperator<Scheme::
 } // namespace heongpu
 
 #include "heongpu_client.hpp"
+#include "heongpu_serial.hpp"

@@ -30,14 +30,21 @@ template <Scheme S> class Secretkey : public detail::Storable {
     {
         if (!ctx || !ctx->context_generated_)
             throw std::invalid_argument("HEContext is not generated!");
+        ring_size_ = ctx->n;
+        coeff_modulus_count_ = ctx->Q_prime_size;
     }
     Secretkey(HEContext<S> ctx, int hamming_weight) : context_(ctx), hamming_weight_(hamming_weight)
     {
         if (hamming_weight <= 0 || hamming_weight > ctx->n)
             throw std::invalid_argument("hamming weight has to be in range 0 to ring size.");
+        ring_size_ = ctx->n;
+        coeff_modulus_count_ = ctx->Q_prime_size;
     }
-    int coeff_modulus_count() const { return context_->Q_prime_size; }
+    int coeff_modulus_count() const { return coeff_modulus_count_; }
+    void save(std::ostream& os) const;
+    void load(std::istream& is);
     HEContext<S> context_;
+    int ring_size_ = 0, coeff_modulus_count_ = 0;
     int hamming_weight_;
     bool in_ntt_domain_ = false, secret_key_generated_ = false;
 };
@@ -49,8 +56,13 @@ template <Scheme S> class Publickey : public detail::Storable {
     {
         if (!ctx || !ctx->context_generated_)
             throw std::invalid_argument("HEContext is not generated!");
+        ring_size_ = ctx->n;
+        coeff_modulus_count_ = ctx->Q_prime_size;
     }
+    void save(std::ostream& os) const;
+    void load(std::istream& is);
     HEContext<S> context_;
+    int ring_size_ = 0, coeff_modulus_count_ = 0;
     bool in_ntt_domain_ = false, public_key_generated_ = false;
 };
 

@@ -312,6 +312,13 @@ int heon_ckks_decode(heon_context_t ctx, const uint64_t* pt, int depth, double s
 int heon_bfv_encode(heon_context_t ctx, const uint64_t* h_message, int count, uint64_t* pt, void* stream);
 int heon_bfv_decode(heon_context_t ctx, const uint64_t* pt, uint64_t* h_message, int count, void* stream);
 
+/* ---- serialization helpers (heongpu::serializer, src/lib/util/serializer.cpp:20-50): zlib compress /
+ * uncompress of a byte buffer, so that consumers of the header-only class layer need not link zlib.
+ * *out_len: capacity on entry, bytes written on return.  heon_compress_bound(n) = a sufficient capacity. */
+size_t heon_compress_bound(size_t n);
+int heon_compress(const uint8_t* in, size_t n, uint8_t* out, size_t* out_len);
+int heon_decompress(const uint8_t* in, size_t n, uint8_t* out, size_t* out_len);
+
 /* Per-kernel-class CUDA-event profiler (used by bench.py for the roofline
  * line): begin() arms it, end() synchronises the device and returns, per
  * class, the summed device time in ms and the launch count; the return value

@@ -10,12 +10,12 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build():
-    exe = os.path.join(tempfile.mkdtemp(), "class_layer_test")
+def _build(name="class_layer_test"):
+    exe = os.path.join(tempfile.mkdtemp(), name)
     lib = os.path.join(ROOT, "heongpu_b200", "lib")
     subprocess.check_call([
         "g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "heongpu_b200", "include"), "-I/usr/local/cuda/include",
-        os.path.join(ROOT, "tests", "cpp", "class_layer_test.cpp"), "-o", exe,
+        os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe,
         "-L", lib, "-lheon_b200", "-L/usr/local/cuda/lib64", "-lcudart", f"-Wl,-rpath,{lib}", "-Wl,-rpath,/usr/local/cuda/lib64"])
     return exe
 
@@ -31,3 +31,16 @@ def test_class_layer_matches_c_abi_on_gpu():
     exe = _build()
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
+
+
+def test_serialization_test_compiles_and_links():
+    _build("serialization_test")
+
+
+@pytest.mark.gpu
+def test_serialization_round_trips_on_gpu():
+    """save / load, heongpu::serializer (zlib) and file round trips of every object, then operators on the
+    reloaded objects (example/basic/13_bfv_serialization.cpp, 14_ckks_serialization.cpp)."""
+    exe = _build("serialization_test")
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "round trips OK" in out.stdout, out.stdout + out.stderr
