@@ -171,6 +171,32 @@ __device__ __forceinline__ void addsub_ptx(u64& X, u64& Y, u64 T, u64 C)
 // ---------------------------------------------------------------------------
 #define HEON_FP_MAGIC 6755399441055744.0 /* 1.5 * 2^52 */
 
+// Alternative form of the quotient (compile with -DHEON_FP_FRND=1): q = rint(RN(Y * winv)) with the rounding
+// done by cvt.rni.f64.f64 (FRND), which does not issue on the FP64 pipe -- seven FP64-pipe instructions per
+// butterfly instead of eight.  Register-resident it measures 15.5 instead of 16.7 SM sub-partition cycles per
+// warp-butterfly (profiles/r2_microbench4.txt), but inside the real kernels it gained nothing (column pass
+// 93 instead of 89 us/op, fused row pass + inner product unchanged at 114 us/op at C3-II: the conversion
+// unit becomes the next limiter), so the magic-constant rounding stays the default.  Bounds of the FRND form,
+// kept because the host emulation (tests/host_emul.cpp) covers both: the product is rounded before the
+// integer rounding, so for |Y| < 2^52
+//   |q - Y*w/p| <= 1/2 + ulp(Y*winv)/2 + |Y|*2^-54 <= 1/2 + 1/4 + 1/4   ->   |T| <= p,
+// and <= 0.75 p while |Y| < 2^51.  Every later step is exact as before (h - q*p is an integer below 2^52,
+// l is the error-free remainder), values stay below 2^52 (VAR 4: at most 2.25 p, tests/host_emul.cpp), and
+// canonical results are unchanged bit for bit (153 GPU parity tests passed with it).
+#ifndef HEON_FP_FRND
+#define HEON_FP_FRND 0
+#endif
+__device__ __forceinline__ double fp_rint(double x)
+{
+#ifndef __CUDA_ARCH__
+    return nearbyint(x); // host emulation (round to nearest even, like cvt.rni)
+#else
+    double r;
+    asm("cvt.rni.f64.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+#endif
+}
+
 __device__ __forceinline__ double u2d(u64 x) { return __longlong_as_double((long long) x); }
 __device__ __forceinline__ u64 d2u(double x) { return (u64) __double_as_longlong(x); }
 
@@ -179,7 +205,11 @@ __device__ __forceinline__ double fp_mulmod(double y, double w, double winv, dou
 #ifdef HEON_FP_TRACK
     heon_fp_track(y); // host emulation only: records max |Y| to check the 2^51 operand bound
 #endif
+#if HEON_FP_FRND
+    const double q = fp_rint(__dmul_rn(y, winv));
+#else
     const double q = __dsub_rn(__fma_rn(y, winv, HEON_FP_MAGIC), HEON_FP_MAGIC);
+#endif
     const double h = __dmul_rn(y, w);
     const double l = __fma_rn(y, w, -h);
     const double r = __fma_rn(q, np, h);
@@ -189,7 +219,11 @@ __device__ __forceinline__ double fp_mulmod(double y, double w, double winv, dou
 // x - rint(x/p)*p: |result| <= p/2 (+1), exact for |x| < 2^52
 __device__ __forceinline__ double fp_reduce(double x, double pinv, double np)
 {
+#if HEON_FP_FRND
+    const double q = fp_rint(__dmul_rn(x, pinv));
+#else
     const double q = __dsub_rn(__fma_rn(x, pinv, HEON_FP_MAGIC), HEON_FP_MAGIC);
+#endif
     return __fma_rn(q, np, x);
 }
 

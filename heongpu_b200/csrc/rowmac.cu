@@ -280,8 +280,9 @@ void launch_row_mac(const Context& c, const u64* tmp, const u64* key, u64* acc, 
     const CUtensorMap tm_key = make_line_map(key, wk, rows * 16);
     const CUtensorMap tm_out = make_line_map(acc, wa, rows * 16);
     const int tiles = (1 << (c.logn - 8)) / rows;
-    // |T| <= p per term: the double accumulator stays exact while (terms + 1/2) * p < 2^53
-    const int red_lo = 60, red_hi = 7;
+    // |T| <= 1.3 p per term (lazy x up to 2.25 p, quotient rounded by FRND): the double accumulator stays exact
+    // while (1.3 * terms + 1/2) * p < 2^53 -> every 5 terms for p < 2^50, every 40 for p < 2^47
+    const int red_lo = 40, red_hi = 5;
     auto go = [&](auto kfn, int nl, const LimbList& list, int smem) {
         if (nl == 0)
             return;
