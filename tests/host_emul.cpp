@@ -289,18 +289,21 @@ int main()
             s = s * 6364136223846793005ULL + 1442695040888963407ULL;
             u64 w = (it % 7 == 0) ? p - 1 : (it % 11 == 0) ? 1 : (s >> 4) % p;
             s = s * 6364136223846793005ULL + 1442695040888963407ULL;
-            u64 y = s >> 12; // < 2^52
+            // operand range: 2^52 with the FRND rounding, 2^51 with the magic constant (its sum has to stay
+            // inside one binade: |q| < 2^51)
+            const int top = HEON_FP_FRND ? 52 : 51;
+            u64 y = s >> (64 - top);
             if (it % 5 == 0) y = (y / p) * p + (it % 3) - 1 + (y < p ? p : 0); // multiples of p, +-1
-            if (it % 13 == 0) y = (1ull << 52) - 1 - (it & 7);
-            if (it % 17 == 0) y = (1ull << 51) - 4 + (it & 7);
-            if (y >= (1ull << 52)) y = (1ull << 52) - 1;
+            if (it % 13 == 0) y = (1ull << top) - 1 - (it & 7);
+            if (it % 17 == 0) y = (1ull << 51) - 9 + (it & 7);
+            if (y >= (1ull << top)) y = (1ull << top) - 1;
             const bool neg = (it & 1);
             const double yd = neg ? -(double) y : (double) y;
             const double wd = (double) w, winv = wd / dp;
             const double t = fp_mulmod(yd, wd, winv, -dp);
             // |T| <= p*(1/2 + ulp(Y*winv)/2 + |Y|*2^-54) and T == Y*w (mod p); ulp(Y*winv)/2 <= 1/4 below 2^52
             // (1/8 below 2^51; 0 for the magic-constant rounding)
-            const double lim = dp * (0.5 + (y < (1ull << 51) ? 0.125 : 0.25) + (double) y * 0x1p-54) + 1.0;
+            const double lim = dp * (0.5 + (HEON_FP_FRND ? (y < (1ull << 51) ? 0.125 : 0.25) : 0.0) + (double) y * 0x1p-54) + 1.0;
             u64 want = mulmod(y % p, w, p);
             if (neg && want) want = p - want;
             long long ti = (long long) t;
@@ -314,9 +317,9 @@ int main()
             ++failures;
         }
     }
-    // the FP64 butterflies are exact only while every multiplied operand stays below 2^52
+    // the FP64 butterflies are exact only while every multiplied operand stays below 2^51 (2^52 with FRND)
     printf("max |Y| inside the FP64 transforms: 2^%.2f\n", std::log2(ntt_fp_max));
-    if (!(ntt_fp_max < 0x1p52))
+    if (!(ntt_fp_max < (HEON_FP_FRND ? 0x1p52 : 0x1p51)))
     {
         printf("FAIL: FP64 operand bound exceeded\n");
         ++failures;
