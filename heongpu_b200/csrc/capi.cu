@@ -169,6 +169,8 @@ static void finish_context(Context& c, int device, int log_n, int n_q, int n_p, 
         c.row_tile = atoi(v);
     if (const char* v = getenv("HEON_SKIP_OWN"))
         c.skip_own = atoi(v);
+    if (const char* v = getenv("HEON_COL_TMA"))
+        c.col_tma = atoi(v);
     if (const char* v = getenv("HEON_ROW_MAC"))
         c.row_mac = atoi(v);
     if (const char* v = getenv("HEON_MODUP_FUSED"))

@@ -1116,6 +1116,62 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 }
 
 // ---------------------------------------------------------------------------
+// Column pass through TMA (N = 2^16): one CTA owns a tile of 16 columns x 256 rows (32 KiB).  A 3-D tensor
+// map {16 words, 16 lines per row, rows} with box {16, 1, 256} brings the tile into shared memory with the
+// 128-byte swizzle (one bulk copy instead of 16 strided 8-byte loads per thread through the LSU, which kept
+// L1 80 % busy in the register-resident form), the eight stages run out of registers with one in-place
+// transposition through the same buffer (pipe_col_tile), and the lazy words leave through a TMA store.
+// The map's per-word transform (fused Method-I mod-up, divide-round stage one) is applied as the words are
+// read from shared memory.
+// ---------------------------------------------------------------------------
+template <class Map>
+__global__ void __launch_bounds__(256, 3)
+    ntt_col_pass_tma(Map map, const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+                     const u64* in_base, const u64* out_base, const TwPair* __restrict__ tw_all,
+                     const PrimeConst* __restrict__ pcs, int variant)
+{
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    unsigned char* buf = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const long long z = blockIdx.x >> 4;
+    const int tile = blockIdx.x & 15;
+    const u64* in;
+    u64* out;
+    int prime, aux;
+    map.get(z, in, out, prime, aux);
+    if (threadIdx.x == 0)
+    {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        mbar_arrive_expect_tx(&bar, kRowTileBytes);
+        tma_load_3d(buf, &tm_in, &bar, 0, tile, (int) ((in - in_base) >> 8));
+    }
+    const PrimeConst pc = pcs[prime];
+    const TwPair* tw = tw_all + ((long long) prime << 16);
+    mbar_wait(&bar, 0);
+    if (pc.fp_var == 3)
+        pipe_col_tile<3>(buf, map, prime, pc, tw, aux, threadIdx.x, 1);
+    else if (pc.fp_var == 4)
+        pipe_col_tile<4>(buf, map, prime, pc, tw, aux, threadIdx.x, 1);
+    else if (variant == 1 || !pc.nc_ok)
+        pipe_col_tile<1>(buf, map, prime, pc, tw, aux, threadIdx.x, 1);
+    else
+        pipe_col_tile<2>(buf, map, prime, pc, tw, aux, threadIdx.x, 1);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        tma_store_3d(&tm_out, buf, 0, tile, (int) ((out - out_base) >> 8));
+        tma_store_commit();
+        tma_store_wait_read<0>();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
 
@@ -1336,6 +1392,34 @@ static bool launch_fwd_fused(const Context& c, const Map& m, long long n_polys, 
     return true;
 }
 
+// forward column pass through TMA tiles (N = 2^16, polynomials on 2 KiB row boundaries); false: not applicable
+template <class Map>
+static bool launch_col_tma(const Context& c, const Map& m, long long n_polys, const Extent& e, cudaStream_t st)
+{
+    if constexpr (Map::kGather)
+        return false;
+    else
+    {
+        // measured on B200: +4.5 % for the maps that transform their input (Method-I mod-up: 16-byte segments of a
+        // source 38 outputs share), -6 % for the in-place maps, which keep the 128-thread register-resident form
+        if (c.col_tma == 0 || (c.col_tma < 0 && !Map::kXform) || !c.use_tma || c.logn != 16 || !e.col_in_base || n_polys < 1)
+            return false;
+        if ((reinterpret_cast<uintptr_t>(e.col_in_base) | reinterpret_cast<uintptr_t>(e.out_base)) & 127)
+            return false;
+        if (n_polys * 16 > 0x7fffffffll)
+            return false;
+        const CUtensorMap tm_in = make_col_map(e.col_in_base, e.col_in_words);
+        const CUtensorMap tm_out = make_col_map(e.out_base, e.out_words);
+        auto kfn = ntt_col_pass_tma<Map>;
+        const int smem = kRowTileBytes + 1024;
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        LaunchScope scope(KC_NTT_FWD_COL, st);
+        kfn<<<(unsigned) (n_polys * 16), 256, smem, st>>>(m, tm_in, tm_out, e.col_in_base, e.out_base, c.d_fwd, c.d_pc,
+                                                        c.ntt_variant);
+        return true;
+    }
+}
+
 template <class Map>
 static void run_ntt(const Context& c, const Map& m, long long n_polys, bool inverse, const Extent& e,
                     cudaStream_t st, bool col_only = false)
@@ -1345,7 +1429,8 @@ static void run_ntt(const Context& c, const Map& m, long long n_polys, bool inve
     if (col_only)
     {
         // first n-8 stages only: the row stages run inside the fused inner-product kernel (k_row_mac)
-        launch_col<false>(c, m, n_polys, true, st);
+        if (!launch_col_tma(c, m, n_polys, e, st))
+            launch_col<false>(c, m, n_polys, true, st);
         return;
     }
     // TMA needs 16-byte aligned bases; fall back to the LSU row pass otherwise
@@ -1359,7 +1444,8 @@ static void run_ntt(const Context& c, const Map& m, long long n_polys, bool inve
             if (tma && launch_fwd_fused(c, m, n_polys, e, st))
                 return;
         }
-        launch_col<false>(c, m, n_polys, true, st);
+        if (!launch_col_tma(c, m, n_polys, e, st))
+            launch_col<false>(c, m, n_polys, true, st);
         if (tma)
             launch_row_tma<false>(c, m, n_polys, false, e, st);
         else

@@ -27,7 +27,7 @@ void launch_ntt_digit_skip(const Context& c, u64* tmp, int d, const int* I_loc, 
     m.prefix[d] = (short) acc;
     m.per_b = acc;
     const long long w = (batch * d * Qpl) << c.logn;
-    run_ntt(c, m, batch * acc, false, Extent{tmp, w, tmp, w}, st, col_only);
+    run_ntt(c, m, batch * acc, false, Extent{tmp, w, tmp, w, tmp, w}, st, col_only);
 }
 
 } // namespace heon

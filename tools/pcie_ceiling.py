@@ -64,6 +64,9 @@ if rank == 0:
            "per_gpu_gbs": [{"h2d_alone": p[0], "d2h_alone": p[1], "each_direction_when_both": p[2]} for p in per],
            "aggregate_each_direction_when_both_gbs": sum(both),
            "c3_ii_e2e_ceiling_ops_per_s_per_gpu": min(both) * 1e9 / 65.0e6,
+           # whole box: every GPU limited by its own link (65 MB in per op) AND all of them by the host's aggregate
+           # pinned-copy bandwidth (65 MB in + 32.5 MB out per op over the sum of both directions)
+           "c3_ii_e2e_ceiling_ops_per_s_box": min(sum(both) * 1e9 / 65.0e6, 2 * sum(both) * 1e9 / 97.5e6),
            "note": "both: H2D and D2H streams run concurrently, GB/s quoted per direction"}
     print(json.dumps(out))
 if world > 1:
