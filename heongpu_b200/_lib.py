@@ -48,6 +48,9 @@ SIGNATURES = {
     "heon_ckks_add_plain": (ci, [vp, vp, ll, vp, ll, vp, ll, ci, ci, ci, vp]),
     "heon_ckks_sub_plain": (ci, [vp, vp, ll, vp, ll, vp, ll, ci, ci, ci, vp]),
     "heon_ckks_rotate_hoisted": (ci, [vp, vp, ll, vp, ll, ll, C.POINTER(vp), C.POINTER(C.c_uint32), ci, ci, ci, vp]),
+    "heon_ckks_multiply_matrix": (ci, [vp, vp, vp, vp, C.POINTER(C.c_uint32), C.POINTER(vp), ci, C.POINTER(C.c_uint32),
+                                       C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), ci, ci, vp]),
+    "heon_ckks_multiply_plain_accumulate": (ci, [vp, vp, vp, vp, ci, ci, vp]),
     "heon_ckks_keyswitch": (ci, [vp, vp, ll, vp, ll, vp, ci, ci, vp]),
     "heon_ckks_conjugate": (ci, [vp, vp, ll, vp, ll, vp, ci, ci, vp]),
     "heon_ckks_rescale": (ci, [vp, vp, ll, ci, ci, vp]),

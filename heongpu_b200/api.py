@@ -460,6 +460,54 @@ class HEArithmeticOperator:
         return out_data
 
 
+    def multiply_plain_accumulate(self, cts, pts, out, depth=0):
+        """out = sum_i cts[i] * pts[i]: the giant-step inner sum of the single-hoisting BSGS product
+        (cipherplain_multiply_accumulate_kernel, multiplication.cu:374-403; ckks/operator.cu:2843-2853).
+        cts: [count][2][L][N] (e.g. rotate_rows_hoisted's output), pts: [count][L][N], out: [2][L][N]."""
+        c = self.context_
+        _check(lib.heon_ckks_multiply_plain_accumulate(c._h, _ptr(cts), _ptr(pts), _ptr(out), cts.shape[0], depth, _stream()))
+        return out
+
+    @staticmethod
+    def bsgs_plan(n, group_order, diags_bsgs, rot_n1, rot_n2):
+        """Resolves one matrix's BSGS description the way multiply_matrix_v2 does (ckks/operator.cu:2926,
+        3176-3193): rot_n2 = the baby-step shifts (sorted first), rot_n1[j] = giant-step shift of group j,
+        diags_bsgs[j][k] - rot_n1[j] = the baby-step shift term k of group j reads."""
+        baby = sorted(rot_n2)
+        elt = lambda s: 0 if s == 0 else lib.heon_steps_to_galois_elt(s, n, group_order)
+        terms = []
+        for j, group in enumerate(diags_bsgs):
+            for dg in group:
+                terms.append(baby.index(dg - rot_n1[j]))
+        return ([elt(s) for s in baby], [elt(s) for s in rot_n1], [len(g) for g in diags_bsgs], terms)
+
+    def multiply_matrix(self, ct, out, matrix, diags_bsgs, rot_n1, rot_n2, galois_key, rescale=True):
+        """One matrix of HEOperator<CKKS>::multiply_matrix_v2 (ckks/operator.cu:2898-3390): BSGS diagonal
+        matrix-vector product with double hoisting in PQ_l, then rescale.  `matrix`: [terms][L+K][N] device
+        words, the diagonals encoded over PQ_l in the NTT domain, in group order."""
+        c = self.context_
+        if ct.batch != 1:
+            raise HeonError("multiply_matrix takes one ciphertext")
+        baby, giant, sizes, terms = self.bsgs_plan(c.n, galois_key.group_order_, diags_bsgs, rot_n1, rot_n2)
+        for e in baby + giant:
+            if e and e not in galois_key.device_location_:
+                raise HeonLogicError("Galois key not present!")
+        kp = lambda e: galois_key.device_location_[e].data_ptr() if e else None
+        bk = (C.c_void_p * len(baby))(*[kp(e) for e in baby])
+        gk = (C.c_void_p * len(giant))(*[kp(e) for e in giant])
+        _check(lib.heon_ckks_multiply_matrix(
+            c._h, _ptr(ct.data), _ptr(out.data), _ptr(matrix), (C.c_uint32 * len(baby))(*baby), bk, len(baby),
+            (C.c_uint32 * len(giant))(*giant), gk, (C.c_int * len(sizes))(*sizes), (C.c_int * len(terms))(*terms),
+            len(giant), ct.depth_, _stream()))
+        out.depth_, out.cipher_size_ = ct.depth_, 2
+        # the reference multiplies the scale by prime_vector_[current_decomp_count] (:3384) before rescaling
+        out.scale_ = ct.scale_ * float(c.primes[c.Q_size - ct.depth_])
+        out.rescale_required_, out.relinearization_required_ = True, False
+        if rescale:
+            self.rescale_inplace(out)
+        return out
+
+
 # ---------------------------------------------------------------------------------------------
 # client side (SURVEY.md 8(f) rank 2): key generation, encryption, decryption, encoding
 # ---------------------------------------------------------------------------------------------

@@ -709,6 +709,34 @@ int heon_ckks_rotate_hoisted(heon_context_t ctx, const uint64_t* in, long long i
     });
 }
 
+int heon_ckks_multiply_matrix(heon_context_t ctx, const uint64_t* in, uint64_t* out, const uint64_t* diags,
+                              const uint32_t* h_baby_elts, const uint64_t* const* h_baby_keys, int n1,
+                              const uint32_t* h_giant_elts, const uint64_t* const* h_giant_keys,
+                              const int* h_group_sizes, const int* h_term_baby, int n2, int depth, void* stream)
+{
+    return guarded([&] {
+        const int batch = 1;
+        HEON_OP_PROLOGUE
+        if (!in || !out || !diags || !h_baby_elts || !h_baby_keys || !h_giant_elts || !h_giant_keys || !h_group_sizes ||
+            !h_term_baby)
+            throw std::invalid_argument("null argument");
+        op_bsgs_matvec(c, in, out, diags, h_baby_elts, (const u64* const*) h_baby_keys, n1, h_giant_elts,
+                       (const u64* const*) h_giant_keys, h_group_sizes, h_term_baby, n2, depth, st);
+    });
+}
+
+int heon_ckks_multiply_plain_accumulate(heon_context_t ctx, const uint64_t* cts, const uint64_t* pts, uint64_t* out,
+                                        int count, int depth, void* stream)
+{
+    return guarded([&] {
+        const int batch = 1;
+        HEON_OP_PROLOGUE
+        if (!cts || !pts || !out)
+            throw std::invalid_argument("null argument");
+        op_multiply_plain_accumulate(c, cts, pts, out, count, depth, st);
+    });
+}
+
 int heon_ckks_relinearize(heon_context_t ctx, uint64_t* ct, long long cs, const uint64_t* relin_key,
                           int depth, int batch, void* stream)
 {

@@ -41,6 +41,11 @@ void op_plain(const Context& c, const u64* ct, long long ct_bs, const u64* pt, l
 void op_rotate_hoisted(const Context& c, const u64* in, long long in_bs, u64* out, long long out_bs,
                        long long out_rs, const u64* const* galois_keys, const unsigned* galois_elts, int count,
                        int depth, int batch, cudaStream_t st);
+void op_bsgs_matvec(const Context& c, const u64* in, u64* out, const u64* diags, const unsigned* baby_elts,
+                    const u64* const* baby_keys, int n1, const unsigned* giant_elts, const u64* const* giant_keys,
+                    const int* group_sizes, const int* term_baby, int n2, int depth, cudaStream_t st);
+void op_multiply_plain_accumulate(const Context& c, const u64* cts, const u64* pts, u64* out, int count, int depth,
+                                  cudaStream_t st);
 void op_keyswitch(const Context& c, const u64* in, long long in_bs, u64* out, long long out_bs,
                   const u64* switch_key, int depth, int batch, cudaStream_t st);
 void op_multiply(const Context& c, const u64* a, long long a_bs, const u64* b, long long b_bs,

@@ -990,6 +990,191 @@ template <> class HEOperator<Scheme::CKKS> {
         return out;
     }
 
+    // BSGS diagonal matrix-vector products with SINGLE hoisting: HEOperator<CKKS>::multiply_matrix
+    // (operator.cu:2803-2895) and multiply_matrix_less_memory (:3398-3496), protected in the reference, public
+    // here.  diags_matrices_bsgs_[m][0] = the baby-step shifts (hoisted: one decomposition for all of them),
+    // diags_matrices_bsgs_[m][j][0] = the giant-step shift of group j (or the chain real_shift[m][j] of shifts
+    // the Galois key holds); matrix[m]: [terms][L][N] diagonals over Q_l in the NTT domain, group order.
+    // Each matrix is followed by scale *= scale_boot_ and rescale_inplace, as in the reference.
+    double scale_boot_ = 1.0;
+    void set_matrix_scale(double s) { scale_boot_ = s; }
+    Ciphertext<Scheme::CKKS> multiply_matrix(Ciphertext<Scheme::CKKS>& cipher, std::vector<DeviceVector<Data64>>& matrix,
+                                             std::vector<std::vector<std::vector<int>>>& diags_matrices_bsgs_,
+                                             Galoiskey<Scheme::CKKS>& galois_key,
+                                             const ExecutionOptions& opt = ExecutionOptions())
+    {
+        return matrix_single_hoisting(cipher, matrix, diags_matrices_bsgs_, nullptr, galois_key, opt);
+    }
+    Ciphertext<Scheme::CKKS> multiply_matrix_less_memory(Ciphertext<Scheme::CKKS>& cipher,
+                                                         std::vector<DeviceVector<Data64>>& matrix,
+                                                         std::vector<std::vector<std::vector<int>>>& diags_matrices_bsgs_,
+                                                         std::vector<std::vector<std::vector<int>>>& real_shift,
+                                                         Galoiskey<Scheme::CKKS>& galois_key,
+                                                         const ExecutionOptions& opt = ExecutionOptions())
+    {
+        return matrix_single_hoisting(cipher, matrix, diags_matrices_bsgs_, &real_shift, galois_key, opt);
+    }
+
+  private:
+    Ciphertext<Scheme::CKKS> matrix_single_hoisting(Ciphertext<Scheme::CKKS>& cipher,
+                                                    std::vector<DeviceVector<Data64>>& matrix,
+                                                    std::vector<std::vector<std::vector<int>>>& diags,
+                                                    std::vector<std::vector<std::vector<int>>>* real_shift,
+                                                    Galoiskey<Scheme::CKKS>& gk, const ExecutionOptions& opt)
+    {
+        detail::InputGuard<Ciphertext<Scheme::CKKS>> g(cipher, opt, false);
+        Ciphertext<Scheme::CKKS> result;
+        copy_meta(cipher, result);
+        {
+            const size_t w = words(2, cipher.depth_);
+            DeviceVector<Data64> mem(w, opt.stream_);
+            detail::cuda(cudaMemcpyAsync(mem.data(), cipher.data(), w * sizeof(Data64), cudaMemcpyDeviceToDevice, opt.stream_));
+            result.memory_set(std::move(mem));
+            result.cipher_size_ = 2;
+        }
+        for (int m = (int) diags.size() - 1; m > -1; m--)
+        {
+            const std::vector<int>& baby = diags[m][0];
+            const int n1 = (int) baby.size();
+            const int L = context_->Q_size - result.depth_;
+            const size_t w = words(2, result.depth_);
+            // fast_single_hoisting_rotation_ckks: every baby-step rotation from one decomposition
+            DeviceVector<Data64> rotated(w * n1, opt.stream_);
+            for (int i = 0; i < n1;)
+            {
+                if (baby[i] == 0)
+                {
+                    detail::cuda(cudaMemcpyAsync(rotated.data() + i * w, result.data(), w * sizeof(Data64),
+                                                 cudaMemcpyDeviceToDevice, opt.stream_));
+                    ++i;
+                    continue;
+                }
+                std::vector<const uint64_t*> keys;
+                std::vector<uint32_t> elts;
+                int e = i;
+                for (; e < n1 && baby[e] != 0; ++e)
+                {
+                    const int elt = heon_steps_to_galois_elt(baby[e], context_->n, gk.group_order_);
+                    auto it = gk.device_location_.find(elt);
+                    if (it == gk.device_location_.end())
+                        throw std::logic_error("Galois key not present!");
+                    keys.push_back(it->second.data());
+                    elts.push_back((uint32_t) elt);
+                }
+                detail::check(heon_ckks_rotate_hoisted(h(), result.data(), 0, rotated.data() + i * w, 0, (long long) w,
+                                                       keys.data(), elts.data(), e - i, result.depth_, 1, opt.stream_));
+                i = e;
+            }
+            Ciphertext<Scheme::CKKS> acc;
+            size_t counter = 0;
+            for (size_t j = 0; j < diags[m].size(); ++j)
+            {
+                const int inner_n1 = (int) diags[m][j].size();
+                if (inner_n1 > n1 || matrix[m].size() < (counter + inner_n1) * (size_t) L * context_->n)
+                    throw std::invalid_argument("matrix diagonals: wrong size");
+                Ciphertext<Scheme::CKKS> inner_sum;
+                copy_meta(result, inner_sum);
+                DeviceVector<Data64> mem(w, opt.stream_);
+                detail::check(heon_ckks_multiply_plain_accumulate(h(), rotated.data(),
+                                                                  matrix[m].data() + counter * (size_t) L * context_->n,
+                                                                  mem.data(), inner_n1, result.depth_, opt.stream_));
+                inner_sum.memory_set(std::move(mem));
+                inner_sum.cipher_size_ = 2;
+                counter += inner_n1;
+                if (real_shift)
+                    for (int sft : (*real_shift)[m][j])
+                        rotate_rows_inplace(inner_sum, gk, sft, opt);
+                else
+                    rotate_rows_inplace(inner_sum, gk, diags[m][j][0], opt);
+                if (j == 0)
+                    acc = std::move(inner_sum);
+                else
+                    add(acc, inner_sum, acc, opt);
+            }
+            result = std::move(acc);
+            result.scale_ = result.scale_ * scale_boot_;
+            result.rescale_required_ = true;
+            rescale_inplace(result, opt);
+        }
+        return result;
+    }
+
+  public:
+    // BSGS diagonal matrix-vector products with double hoisting, the linear transforms of CKKS bootstrapping:
+    // HEOperator<CKKS>::multiply_matrix_v2 (operator.cu:2898-3390; protected in the reference, public here) with
+    // the reference's arguments.  matrix[m] holds the diagonals of matrix m encoded over PQ_l in the NTT domain,
+    // [terms][L+K][N] in group order; diags_matrices_bsgs_[m][j][k] = rot_n1_[m][j] + (a shift of rot_n2_[m]).
+    // The matrices are applied last to first, each followed by rescale_inplace (:3382-3387).
+    Ciphertext<Scheme::CKKS> multiply_matrix_v2(Ciphertext<Scheme::CKKS>& cipher,
+                                                std::vector<DeviceVector<Data64>>& matrix,
+                                                std::vector<std::vector<std::vector<int>>>& diags_matrices_bsgs_,
+                                                std::vector<std::vector<int>>& diags_matrices_bsgs_rot_n1_,
+                                                std::vector<std::vector<int>>& diags_matrices_bsgs_rot_n2_,
+                                                Galoiskey<Scheme::CKKS>& galois_key,
+                                                const ExecutionOptions& opt = ExecutionOptions())
+    {
+        detail::InputGuard<Ciphertext<Scheme::CKKS>> g(cipher, opt, false);
+        Ciphertext<Scheme::CKKS> result;
+        copy_meta(cipher, result);
+        {
+            const size_t w = words(2, cipher.depth_);
+            DeviceVector<Data64> mem(w, opt.stream_);
+            detail::cuda(cudaMemcpyAsync(mem.data(), cipher.data(), w * sizeof(Data64), cudaMemcpyDeviceToDevice, opt.stream_));
+            result.memory_set(std::move(mem));
+            result.cipher_size_ = 2;
+        }
+        const int matrix_count = (int) diags_matrices_bsgs_.size();
+        for (int m = matrix_count - 1; m > -1; m--)
+        {
+            std::sort(diags_matrices_bsgs_rot_n2_[m].begin(), diags_matrices_bsgs_rot_n2_[m].end());
+            const std::vector<int>& baby = diags_matrices_bsgs_rot_n2_[m];
+            auto resolve = [&](int shift, uint32_t& elt, const uint64_t*& key) {
+                elt = 0;
+                key = nullptr;
+                if (shift == 0)
+                    return;
+                elt = (uint32_t) heon_steps_to_galois_elt(shift, context_->n, galois_key.group_order_);
+                auto it = galois_key.device_location_.find((int) elt);
+                if (it == galois_key.device_location_.end())
+                    throw std::logic_error("Galois key not present!");
+                key = it->second.data();
+            };
+            std::vector<uint32_t> baby_elts(baby.size()), giant_elts(diags_matrices_bsgs_[m].size());
+            std::vector<const uint64_t*> baby_keys(baby.size()), giant_keys(giant_elts.size());
+            std::vector<int> sizes, terms;
+            for (size_t i = 0; i < baby.size(); ++i)
+                resolve(baby[i], baby_elts[i], baby_keys[i]);
+            for (size_t j = 0; j < giant_elts.size(); ++j)
+            {
+                const int real_shift = diags_matrices_bsgs_rot_n1_[m][j];
+                resolve(real_shift, giant_elts[j], giant_keys[j]);
+                sizes.push_back((int) diags_matrices_bsgs_[m][j].size());
+                for (int dg : diags_matrices_bsgs_[m][j])
+                {
+                    auto it = std::find(baby.begin(), baby.end(), dg - real_shift);
+                    if (it == baby.end())
+                        throw std::invalid_argument("BSGS diagonal without a baby step");
+                    terms.push_back((int) std::distance(baby.begin(), it));
+                }
+            }
+            const int L = context_->Q_size - result.depth_;
+            if (matrix[m].size() < terms.size() * (size_t) (L + context_->P_size) * context_->n)
+                throw std::invalid_argument("matrix diagonals: wrong size");
+            DeviceVector<Data64> mem(words(2, result.depth_), opt.stream_);
+            detail::check(heon_ckks_multiply_matrix(h(), result.data(), mem.data(), matrix[m].data(), baby_elts.data(),
+                                                    baby_keys.data(), (int) baby.size(), giant_elts.data(), giant_keys.data(),
+                                                    sizes.data(), terms.data(), (int) giant_elts.size(), result.depth_,
+                                                    opt.stream_));
+            result.memory_set(std::move(mem));
+            result.in_ntt_domain_ = true;
+            result.relinearization_required_ = false;
+            result.scale_ = result.scale_ * (double) context_->prime_vector_[L].value;
+            result.rescale_required_ = true;
+            rescale_inplace(result, opt);
+        }
+        return result;
+    }
+
     // operator.cuh:718-884 + multiply_plain_ckks (operator.cu:839-871)
     void multiply_plain(Ciphertext<Scheme::CKKS>& a, Plaintext<Scheme::CKKS>& p, Ciphertext<Scheme::CKKS>& out,
                         const ExecutionOptions& opt = ExecutionOptions())

@@ -214,6 +214,31 @@ int heon_ckks_rotate_hoisted(heon_context_t ctx, const uint64_t* in, long long i
                              long long out_stride, long long out_rot_stride, const uint64_t* const* h_galois_keys,
                              const uint32_t* h_galois_elts, int count, int depth, int batch, void* stream);
 
+/* ---- HEOperator<CKKS>::multiply_matrix_v2 (src/lib/host/ckks/operator.cu:2898-3390), one matrix of
+ *      the chain: BSGS diagonal matrix-vector product with DOUBLE hoisting in the PQ_l domain, the
+ *      linear-transform core of CKKS bootstrapping (CoeffToSlot / SlotToCoeff).  Method II only, as in
+ *      the reference.  in, out: [2][L][N], NTT domain, same depth (the reference applies
+ *      rescale_inplace afterwards: heon_ckks_rescale).  PQ_l = limbs {q_0..q_{L-1}, p_0..p_{K-1}}.
+ *      The BSGS plan is passed resolved, as the reference host code resolves it (:3176-3193), all
+ *      index arrays on the HOST:
+ *        baby step i  (n1 of them): Galois element h_baby_elts[i] (0 = no rotation) and DEVICE key
+ *                     h_baby_keys[i] (ignored for element 0);
+ *        giant step j (n2 of them): element h_giant_elts[j] (0 = none), key h_giant_keys[j],
+ *                     h_group_sizes[j] terms; term t (counted over the groups in order) multiplies baby
+ *                     step h_term_baby[t] with the diagonal plaintext diags + t*(L+K)*N, layout
+ *                     [L+K][N] in the NTT domain over PQ_l (DEVICE). */
+int heon_ckks_multiply_matrix(heon_context_t ctx, const uint64_t* in, uint64_t* out, const uint64_t* diags,
+                              const uint32_t* h_baby_elts, const uint64_t* const* h_baby_keys, int n1,
+                              const uint32_t* h_giant_elts, const uint64_t* const* h_giant_keys,
+                              const int* h_group_sizes, const int* h_term_baby, int n2, int depth, void* stream);
+
+/* ---- the giant-step inner sum of the single-hoisting BSGS product (HEOperator<CKKS>::multiply_matrix,
+ *      operator.cu:2803-2895): cipherplain_multiply_accumulate_kernel (multiplication.cu:374-403).
+ *      out = sum_i cts[i] * pts[i];  cts: [count][2][L][N] (e.g. the output of heon_ckks_rotate_hoisted),
+ *      pts: [count][L][N], out: [2][L][N], all in the NTT domain at `depth`. */
+int heon_ckks_multiply_plain_accumulate(heon_context_t ctx, const uint64_t* cts, const uint64_t* pts, uint64_t* out,
+                                        int count, int depth, void* stream);
+
 /* ---- HEOperator<BFV>::multiply_bfv (src/lib/host/bfv/operator.cu:336-430) --
  * BEHZ multiplication.  a, b: [2][Q][N], out: [3][Q][N], all in the
  * COEFFICIENT domain (BFV ciphertexts are not kept in the NTT domain). */

@@ -160,6 +160,17 @@ class RefGpu:
     def apply_galois(self, a, out, key, galois_elt, depth=0, stream=None):
         self._chk(self.L.refgpu_apply_galois(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(key.data_ptr()), int(galois_elt), depth, self._s(stream)))
 
+    def bsgs_matvec(self, ct, out, matrix, baby_elts, baby_keys, giant_elts, giant_keys, group_sizes, term_baby, depth=0,
+                    stream=None):
+        """multiply_matrix_v2, one matrix, without the trailing rescale (ckks/operator.cu:2898-3383)."""
+        vp = C.c_void_p
+        kp = lambda k: k.data_ptr() if k is not None else None
+        self._chk(self.L.refgpu_bsgs_matvec(
+            self._h, vp(ct.data_ptr()), vp(out.data_ptr()), vp(matrix.data_ptr()), (C.c_int * len(baby_elts))(*baby_elts),
+            (vp * len(baby_keys))(*[kp(k) for k in baby_keys]), len(baby_elts), (C.c_int * len(giant_elts))(*giant_elts),
+            (vp * len(giant_keys))(*[kp(k) for k in giant_keys]), (C.c_int * len(group_sizes))(*group_sizes),
+            (C.c_int * len(term_baby))(*term_baby), len(giant_elts), depth, self._s(stream)))
+
 
 def tables_for_refgpu(n_power, primes, Q, K, use_ref_host=None, scheme="CKKS", plain_modulus=786433):
     """Build the table bundle RefGpu needs, from the reference's own host code

@@ -331,6 +331,160 @@ int refgpu_relinearize(void* hv, Data64* ct, Data64* relin_key, int depth, void*
     return (int) cudaGetLastError();
 }
 
+// multiply_matrix_v2, one matrix of the chain (operator.cu:2898-3390): BSGS diagonal mat-vec with double
+// hoisting in PQ_l.  The BSGS plan arrives resolved (Galois elements, key pointers, baby-step index per term)
+// exactly as the reference host code resolves it from diags_matrices_bsgs_ / rot_n1_ / rot_n2_ (:3176-3193).
+// The trailing rescale_inplace (:3387) is refgpu_rescale.
+int refgpu_bsgs_matvec(void* hv, Data64* ct, Data64* out, Data64* matrix, const int* baby_elts, Data64** baby_keys,
+                       int n1, const int* giant_elts, Data64** giant_keys, const int* group_sizes, const int* term_baby,
+                       int n2, int depth, void* stream_v)
+{
+    RefGpu* h = (RefGpu*) hv;
+    cudaStream_t stream = (cudaStream_t) stream_v;
+    const int n = h->n, n_power = h->n_power, Q_size = h->Q, P_size = h->K;
+    const int first_rns_mod_count = h->Qp;
+    const int current_level = depth;
+    const int current_decomp_count = Q_size - current_level;
+    const int current_rns_mod_count = h->Qp - current_level;
+    const int pql_count = current_decomp_count + P_size;
+
+    std::vector<Data64> primes(h->Qp);
+    {
+        std::vector<Modulus64> m(h->Qp);
+        cudaMemcpy(m.data(), h->modulus, sizeof(Modulus64) * h->Qp, cudaMemcpyDeviceToHost);
+        for (int i = 0; i < h->Qp; i++)
+            primes[i] = m[i].value;
+    }
+    std::vector<Modulus64> pq_mod_host;
+    for (int j = 0; j < current_decomp_count; j++)
+        pq_mod_host.push_back(Modulus64(primes[j]));
+    for (int k = 0; k < P_size; k++)
+        pq_mod_host.push_back(Modulus64(primes[Q_size + k]));
+    Modulus64* pq_modulus_dev = up(pq_mod_host.data(), pq_mod_host.size());
+    std::vector<Data64> P_mod_q_host(current_decomp_count);
+    for (int j = 0; j < current_decomp_count; j++)
+    {
+        uint64_t p_mod_qj = 1, qj = primes[j];
+        for (int k = 0; k < P_size; k++)
+        {
+            __uint128_t tmp = (__uint128_t) p_mod_qj * (primes[Q_size + k] % qj);
+            p_mod_qj = (uint64_t) (tmp % qj);
+        }
+        P_mod_q_host[j] = p_mod_qj;
+    }
+    Data64* P_mod_q_dev = up(P_mod_q_host.data(), P_mod_q_host.size());
+
+    int counter_loc = first_rns_mod_count, location = 0;
+    for (int i = 0; i < current_level; i++)
+    {
+        location += counter_loc;
+        counter_loc--;
+    }
+    auto cfg_intt = cfg_of(h, true, h->n_inverse, stream);
+    auto cfg_ntt = cfg_of(h, false, nullptr, stream);
+    RefLevel2& l = h->lvl2[current_level];
+    const int d_level = l.d;
+    const int iteration_count_1 = d_level / 4, iteration_count_2 = d_level % 4;
+    const size_t baby_ct_size = (size_t) 2 * pql_count * n;
+
+    auto dmalloc = [](size_t words) {
+        Data64* p = nullptr;
+        cudaMalloc(&p, words * sizeof(Data64));
+        return p;
+    };
+    Data64* temp0 = dmalloc((size_t) 2 * n * Q_size);
+    Data64* temp3 = dmalloc((size_t) 2 * n * d_level * current_rns_mod_count);
+    Data64* baby_results = dmalloc(baby_ct_size * n1);
+    Data64* temp4 = dmalloc((size_t) 2 * n * current_rns_mod_count);
+    Data64* Pc0 = dmalloc((size_t) pql_count * n);
+    Data64* gs_accum = dmalloc(baby_ct_size);
+    Data64* u_pql = dmalloc(baby_ct_size);
+    Data64* u1_Q = dmalloc((size_t) current_decomp_count * n);
+    Data64* temp3_gs = dmalloc((size_t) 2 * n * d_level * current_rns_mod_count);
+    Data64* temp4_gs = dmalloc((size_t) 2 * n * current_rns_mod_count);
+    Data64* permuted_gs = dmalloc(baby_ct_size);
+    int total_terms = 0;
+    for (int j = 0; j < n2; j++)
+        total_terms += group_sizes[j];
+    int* ct_indices_all = up(term_baby, total_terms);
+
+    gpuntt::GPU_INTT(ct, temp0, h->intt_table, h->modulus, cfg_intt, 2 * current_decomp_count, current_decomp_count);
+    base_conversion_DtoQtilde_relin_leveled_kernel<<<dim3((n >> 8), d_level, 1), 256, 0, stream>>>(
+        temp0 + (current_decomp_count << n_power), temp3, h->modulus, l.bc, l.mi, l.pr, l.Ij, l.Iloc, n_power, d_level,
+        current_rns_mod_count, current_decomp_count, current_level, h->prime_location_leveled + location);
+    gpuntt::GPU_NTT_Modulus_Ordered_Inplace(temp3, h->ntt_table, h->modulus, cfg_ntt, d_level * current_rns_mod_count,
+                                            current_rns_mod_count, h->new_prime_locations + location);
+    broadcast_scale_P_kernel<<<dim3((n >> 8), pql_count, 1), 256, 0, stream>>>(ct, Pc0, P_mod_q_dev, pq_modulus_dev, n_power,
+                                                                             current_decomp_count, pql_count);
+    for (int i = 0; i < n1; i++)
+    {
+        Data64* baby = baby_results + baby_ct_size * i;
+        if (baby_elts[i] == 0)
+        {
+            cudaMemcpyAsync(baby, Pc0, (size_t) pql_count * n * sizeof(Data64), cudaMemcpyDeviceToDevice, stream);
+            broadcast_scale_P_kernel<<<dim3((n >> 8), pql_count, 1), 256, 0, stream>>>(
+                ct + ((size_t) current_decomp_count * n), baby + ((size_t) pql_count * n), P_mod_q_dev, pq_modulus_dev, n_power,
+                current_decomp_count, pql_count);
+            continue;
+        }
+        keyswitch_multiply_accumulate_leveled_method_II_kernel<<<dim3((n >> 8), current_rns_mod_count, 1), 256, 0, stream>>>(
+            temp3, baby_keys[i], temp4, h->modulus, first_rns_mod_count, current_decomp_count, current_rns_mod_count,
+            iteration_count_1, iteration_count_2, current_level, n_power);
+        addition_pql_kernel<<<dim3((n >> 8), pql_count, 1), 256, 0, stream>>>(temp4, Pc0, temp4, pq_modulus_dev, n_power,
+                                                                            pql_count);
+        galois_permute_ntt_pql_kernel<<<dim3((n >> 8), pql_count, 2), 256, 0, stream>>>(temp4, baby, baby_elts[i], n_power,
+                                                                                      pql_count);
+    }
+    cudaMemsetAsync(gs_accum, 0, baby_ct_size * sizeof(Data64), stream);
+    int counter = 0;
+    for (int j = 0; j < n2; j++)
+    {
+        const int inner_n1 = group_sizes[j];
+        cipherplain_multiply_accumulate_indexed_kernel<<<dim3((n >> 8), pql_count, 2), 256, 0, stream>>>(
+            baby_results, matrix + (((size_t) counter * pql_count) << n_power), u_pql, pq_modulus_dev, ct_indices_all + counter,
+            inner_n1, pql_count, pql_count, n_power);
+        counter += inner_n1;
+        if (giant_elts[j] == 0)
+        {
+            addition_pql_kernel<<<dim3((n >> 8), pql_count, 2), 256, 0, stream>>>(gs_accum, u_pql, gs_accum, pq_modulus_dev,
+                                                                                n_power, pql_count);
+            continue;
+        }
+        gpuntt::GPU_NTT_Modulus_Ordered_Inplace(u_pql + ((size_t) pql_count * n), h->intt_table, h->modulus, cfg_intt, pql_count,
+                                                pql_count, h->new_prime_locations + location);
+        divide_round_lastq_extended_leveled_kernel<<<dim3((n >> 8), current_decomp_count, 1), 256, 0, stream>>>(
+            u_pql + ((size_t) pql_count * n), u1_Q, h->modulus, h->half, h->half_mod, h->last_q_modinv, n_power, pql_count,
+            current_decomp_count, first_rns_mod_count, Q_size, P_size);
+        base_conversion_DtoQtilde_relin_leveled_kernel<<<dim3((n >> 8), d_level, 1), 256, 0, stream>>>(
+            u1_Q, temp3_gs, h->modulus, l.bc, l.mi, l.pr, l.Ij, l.Iloc, n_power, d_level, current_rns_mod_count,
+            current_decomp_count, current_level, h->prime_location_leveled + location);
+        gpuntt::GPU_NTT_Modulus_Ordered_Inplace(temp3_gs, h->ntt_table, h->modulus, cfg_ntt, d_level * current_rns_mod_count,
+                                                current_rns_mod_count, h->new_prime_locations + location);
+        keyswitch_multiply_accumulate_leveled_method_II_kernel<<<dim3((n >> 8), current_rns_mod_count, 1), 256, 0, stream>>>(
+            temp3_gs, giant_keys[j], temp4_gs, h->modulus, first_rns_mod_count, current_decomp_count, current_rns_mod_count,
+            iteration_count_1, iteration_count_2, current_level, n_power);
+        addition_pql_kernel<<<dim3((n >> 8), pql_count, 1), 256, 0, stream>>>(temp4_gs, u_pql, temp4_gs, pq_modulus_dev, n_power,
+                                                                            pql_count);
+        galois_permute_ntt_pql_kernel<<<dim3((n >> 8), pql_count, 2), 256, 0, stream>>>(temp4_gs, permuted_gs, giant_elts[j],
+                                                                                      n_power, pql_count);
+        addition_pql_kernel<<<dim3((n >> 8), pql_count, 2), 256, 0, stream>>>(gs_accum, permuted_gs, gs_accum, pq_modulus_dev,
+                                                                            n_power, pql_count);
+    }
+    gpuntt::GPU_NTT_Modulus_Ordered_Inplace(gs_accum, h->intt_table, h->modulus, cfg_intt, 2 * pql_count, pql_count,
+                                            h->new_prime_locations + location);
+    divide_round_lastq_extended_leveled_kernel<<<dim3((n >> 8), current_decomp_count, 2), 256, 0, stream>>>(
+        gs_accum, out, h->modulus, h->half, h->half_mod, h->last_q_modinv, n_power, pql_count, current_decomp_count,
+        first_rns_mod_count, Q_size, P_size);
+    gpuntt::GPU_NTT_Inplace(out, h->ntt_table, h->modulus, cfg_ntt, 2 * current_decomp_count, current_decomp_count);
+    cudaStreamSynchronize(stream);
+    int err = (int) cudaGetLastError();
+    for (Data64* p : {temp0, temp3, baby_results, temp4, Pc0, gs_accum, u_pql, u1_Q, temp3_gs, temp4_gs, permuted_gs, P_mod_q_dev})
+        cudaFree(p);
+    cudaFree(pq_modulus_dev);
+    cudaFree(ct_indices_all);
+    return err;
+}
+
 // rescale_inplace_ckks_leveled: operator.cu:1156-1244
 int refgpu_rescale(void* hv, Data64* ct, int depth, void* stream)
 {

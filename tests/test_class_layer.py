@@ -44,3 +44,16 @@ def test_serialization_round_trips_on_gpu():
     exe = _build("serialization_test")
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "round trips OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_bsgs_test_compiles_and_links():
+    _build("bsgs_test")
+
+
+@pytest.mark.gpu
+def test_bsgs_matrix_products_decrypt_correctly_on_gpu():
+    """multiply_matrix (single hoisting), multiply_matrix_less_memory and multiply_matrix_v2 (double hoisting in
+    PQ_l) of the class layer against the plain diagonal product (ckks/operator.cu:2803-3496)."""
+    exe = _build("bsgs_test")
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "BSGS OK" in out.stdout, out.stdout + out.stderr

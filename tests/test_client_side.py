@@ -139,3 +139,41 @@ def test_bfv_batching_multiply_relinearize_rotate_decrypts_correctly(log_n, qb, 
     out = api.Ciphertext(ctx, torch.zeros(1, 2, Q, n, dtype=torch.int64, device="cuda"))
     op.rotate_columns_bfv(c1, out, gk)
     assert np.array_equal(enc.decode(dec.decrypt(out)), np.concatenate([m1[half:], m1[:half]]).astype(np.uint64))
+
+
+def test_ckks_bsgs_matrix_product_decrypts_correctly():
+    """multiply_matrix_v2 (ckks/operator.cu:2898-3390) with real keys: sum_j rot_{G_j}( sum_k diag_jk * rot_{b_k}(x) )
+    against numpy.  The diagonals are encoded over PQ_0 by a second context whose Q chain is this one's Q' chain."""
+    api, ctx, kg, sk, pk = _ckks(13, [50, 40, 40, 40, 40], [50, 50, 50])
+    spare = api.HEContext(13, [45], [46], device=0).primes[1]
+    wide = api.HEContext(13, q_values=list(ctx.primes), p_values=[spare], device=0)
+    enc, cry, dec = api.HEEncoder(ctx), api.HEEncryptor(ctx, pk), api.HEDecryptor(ctx, sk)
+    wenc = api.HEEncoder(wide)
+    op = api.HEArithmeticOperator(ctx)
+    rot_n2, rot_n1 = [0, 1, 2, 3], [0, 4, 8]
+    diags_bsgs = [[0, 1, 2, 3], [4, 5, 7], [8, 10, 11]]
+    gk = kg.generate_galois_key(sk, shifts=[1, 2, 3, 4, 8])
+    rng = np.random.default_rng(5)
+    slots = ctx.n // 2
+    x = rng.uniform(-1, 1, slots)
+    scale = 2.0 ** 40
+    ct = cry.encrypt(enc.encode(x, scale))
+    want = np.zeros(slots)
+    planes = []
+    for j, group in enumerate(diags_bsgs):
+        inner = np.zeros(slots)
+        for dg in group:
+            p = rng.uniform(-1, 1, slots)
+            planes.append(wenc.encode(p, scale).data.reshape(-1, ctx.n))
+            inner += p * np.roll(x, -(dg - rot_n1[j]))
+        want += np.roll(inner, -rot_n1[j])
+    matrix = torch.stack(planes).contiguous()
+    L, n = ctx.Q_size, ctx.n
+    assert matrix.shape == (len(planes), L + ctx.P_size, n)
+    out = api.Ciphertext(ctx, torch.zeros(1, 2, L, n, dtype=torch.int64, device="cuda"))
+    op.multiply_matrix(ct, out, matrix, diags_bsgs, rot_n1, rot_n2, gk)
+    assert out.depth_ == 1
+    out.scale_ = scale * scale / float(ctx.primes[L - 1])
+    got = enc.decode(dec.decrypt(out)).real
+    err = np.abs(got - want)
+    assert err.max() < 1e-4 and np.median(err) < 1e-6, (err.max(), np.median(err))

@@ -202,3 +202,93 @@ def test_rotate_rows_shift_zero_is_identity():
     Bo = api.Ciphertext(bctx, torch.zeros(1, 2, ob.Q, ob.n, dtype=torch.int64, device="cuda"))
     bop.rotate_rows_bfv(Bc, Bo, api.Galoiskey(bctx, {2 * ob.n - 1: bkey}), 0)
     assert np.array_equal(to_host(Bo.data), b)
+
+
+# ------------------------- BSGS mat-vec with double hoisting (multiply_matrix_v2) --
+def _bsgs_case(api, name, depth, seed, rot_n2, rot_n1, diags_bsgs):
+    ctx, oc, rg = gpu_ctx(name), oracle_ctx(name), ref_gpu(name)
+    L, n, K = oc.Q - depth, oc.n, oc.K
+    pql = L + K
+    a = ciphertext(seed, oc.primes, L, n, 2, 1)
+    baby, giant, sizes, terms = api.HEArithmeticOperator.bsgs_plan(n, 5, diags_bsgs, rot_n1, rot_n2)
+    keys = {}
+    for i, e in enumerate(sorted(set(baby + giant) - {0})):
+        keys[e] = to_dev(eval_key(seed + 10 + i, oc.primes, oc.digits(0), n))
+    pq_primes = list(oc.primes[:L]) + list(oc.primes[oc.Q:])
+    matrix = to_dev(residues(seed + 5, pq_primes, n, (len(terms),)))
+    assert matrix.shape == (len(terms), pql, n)
+    return ctx, oc, rg, L, n, a, keys, matrix, (baby, giant, sizes, terms)
+
+
+@needs_ref
+@pytest.mark.parametrize("name,depth", [("n13_II", 0), ("n13_II", 2), ("n15_II", 1), ("C3_II", 3)])
+def test_bsgs_matvec_bit_exact_vs_reference_kernels(name, depth):
+    """heon_ckks_multiply_matrix against the replay of multiply_matrix_v2 (ckks/operator.cu:2898-3390) on the
+    reference's own kernels: baby steps {0,1,2,3}, giant steps {0,4,8} with ragged groups, then rescale."""
+    from heongpu_b200 import api
+    rot_n2 = [3, 0, 1, 2]  # unsorted on purpose: the reference sorts it (:2926)
+    rot_n1 = [0, 4, 8]
+    diags_bsgs = [[0, 1, 3], [4, 5, 6, 7], [9, 11]]
+    ctx, oc, rg, L, n, a, keys, matrix, plan = _bsgs_case(api, name, depth, 300, rot_n2, rot_n1, diags_bsgs)
+    baby, giant, sizes, terms = plan
+    op = api.HEArithmeticOperator(ctx)
+    A = api.Ciphertext(ctx, to_dev(a), depth=depth)
+    out = api.Ciphertext(ctx, torch.zeros(1, 2, L, n, dtype=torch.int64, device="cuda"), depth=depth)
+    gk = api.Galoiskey(ctx, keys)
+    op.multiply_matrix(A, out, matrix, diags_bsgs, rot_n1, rot_n2, gk, rescale=False)
+    ro = torch.zeros(2, L, n, dtype=torch.int64, device="cuda")
+    rg.bsgs_matvec(to_dev(a[0]), ro, matrix, baby, [keys.get(e) for e in baby], giant, [keys.get(e) for e in giant],
+                   sizes, terms, depth)
+    torch.cuda.synchronize()
+    assert torch.equal(out.data[0], ro), "BSGS mat-vec differs from the reference kernels"
+    assert torch.equal(A.data[0], to_dev(a[0])), "input ciphertext modified"
+    op.rescale_inplace(out)
+    rg.rescale(ro, depth)
+    torch.cuda.synchronize()
+    assert torch.equal(out.words()[0], ro.reshape(-1)[: 2 * (L - 1) * n].reshape(2, L - 1, n))
+
+
+@needs_ref
+def test_bsgs_matvec_single_group_and_missing_key():
+    from heongpu_b200 import api
+    rot_n2, rot_n1, diags_bsgs = [1, 2], [16], [[17, 18]]  # no zero rotation anywhere
+    ctx, oc, rg, L, n, a, keys, matrix, plan = _bsgs_case(api, "n13_II", 1, 320, rot_n2, rot_n1, diags_bsgs)
+    baby, giant, sizes, terms = plan
+    op = api.HEArithmeticOperator(ctx)
+    A = api.Ciphertext(ctx, to_dev(a), depth=1)
+    out = api.Ciphertext(ctx, torch.zeros(1, 2, L, n, dtype=torch.int64, device="cuda"), depth=1)
+    op.multiply_matrix(A, out, matrix, diags_bsgs, rot_n1, rot_n2, api.Galoiskey(ctx, keys), rescale=False)
+    ro = torch.zeros(2, L, n, dtype=torch.int64, device="cuda")
+    rg.bsgs_matvec(to_dev(a[0]), ro, matrix, baby, [keys.get(e) for e in baby], giant, [keys.get(e) for e in giant],
+                   sizes, terms, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(out.data[0], ro)
+    some = next(iter(keys))
+    fewer = {e: k for e, k in keys.items() if e != some}
+    with pytest.raises(api.HeonLogicError):
+        op.multiply_matrix(A, out, matrix, diags_bsgs, rot_n1, rot_n2, api.Galoiskey(ctx, fewer))
+    with pytest.raises(api.HeonError):  # Method I context: the reference's path is Method II only
+        c1 = gpu_ctx("n13_I")
+        op1 = api.HEArithmeticOperator(c1)
+        o1 = oracle_ctx("n13_I")
+        a1 = api.Ciphertext(c1, to_dev(ciphertext(1, o1.primes, o1.Q, o1.n, 2, 1)), depth=0)
+        k1 = {e: to_dev(eval_key(2, o1.primes, o1.digits(0), o1.n)) for e in set(baby + giant)}
+        m1 = to_dev(residues(3, list(o1.primes), o1.n, (len(terms),)))
+        op1.multiply_matrix(a1, a1, m1, diags_bsgs, rot_n1, rot_n2, api.Galoiskey(c1, k1))
+
+
+@pytest.mark.parametrize("name,depth,count", [("n12_II", 0, 1), ("n13_II", 1, 5), ("mixed", 0, 9), ("n13_I", 2, 16)])
+def test_multiply_plain_accumulate_vs_integer_arithmetic(name, depth, count):
+    """cipherplain_multiply_accumulate_kernel (multiplication.cu:374-403): sum of canonical products, canonical."""
+    from heongpu_b200 import api
+    ctx, oc = gpu_ctx(name), oracle_ctx(name)
+    L, n = oc.Q - depth, oc.n
+    cts = residues(400, oc.primes[:L], n, (count, 2))
+    pts = residues(401, oc.primes[:L], n, (count,))
+    out = torch.zeros(2, L, n, dtype=torch.int64, device="cuda")
+    api.HEArithmeticOperator(ctx).multiply_plain_accumulate(to_dev(cts), to_dev(pts), out, depth)
+    want = np.zeros((2, L, n), dtype=object)
+    p = np.array([int(x) for x in oc.primes[:L]], dtype=object).reshape(1, L, 1)
+    for i in range(count):
+        want = (want + cts[i].astype(object) * pts[i].astype(object)[None]) % p
+    assert np.array_equal(to_host(out), want.astype(np.uint64))
