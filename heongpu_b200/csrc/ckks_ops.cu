@@ -1677,6 +1677,29 @@ __global__ void __launch_bounds__(256)
     const long long off = idx + ((long long) y << logn) + (((long long) pql << logn) * blockIdx.z);
     out[off] = mod_add(a[off], b[off], mods[level_prime(y, L, depth)].value);
 }
+// out[idx] (+)= acc[pi(idx)] + (component 0 ? add0[pi(idx)] : 0): addition_pql_kernel on component 0, then
+// galois_permute_ntt_pql_kernel, then (ACCUM) addition_pql_kernel into the giant-step accumulator, as one pass.
+// Sums of canonical words reduced once per addition, exactly as the three reference kernels do.
+template <bool ACCUM>
+__global__ void __launch_bounds__(256)
+    k_pql_add_permute(const u64* __restrict__ acc, const u64* __restrict__ add0, u64* __restrict__ out,
+                      const Mod64* __restrict__ mods, int logn, int L, int depth, int pql, unsigned galois_elt)
+{
+    const unsigned idx = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y, c = blockIdx.z;
+    const unsigned k = __brev(idx) >> (32 - logn);
+    const unsigned f = (((2u * k + 1u) * galois_elt) & ((2u << logn) - 1u)) >> 1;
+    const unsigned src = __brev(f) >> (32 - logn);
+    const long long limb = (long long) (c * pql + y) << logn;
+    const u64 p = mods[level_prime(y, L, depth)].value;
+    u64 v = acc[limb + src];
+    if (c == 0)
+        v = mod_add(v, add0[((long long) y << logn) + src], p);
+    if (ACCUM)
+        v = mod_add(out[limb + idx], v, p);
+    out[limb + idx] = v;
+}
+
 // u[c][y] = sum_i baby[index[i]][c][y] * diag[i][y]   (cipherplain_multiply_accumulate_indexed_kernel);
 // lazy 128-bit accumulation, one reduction: the canonical value of the reference's per-term Barrett sum
 __global__ void __launch_bounds__(256)
@@ -1753,7 +1776,7 @@ void op_bsgs_matvec(const Context& c, const u64* in, u64* out, const u64* diags,
     Scratch coef1((size_t) L * N * 8, st);
     Scratch tmp(ks_tmp_words(c, depth, 1) * 8, st);
     Scratch acc(ct_words * 8, st), Pc0((size_t) pql * N * 8, st), baby(ct_words * n1 * 8, st);
-    Scratch accum(ct_words * 8, st), u(ct_words * 8, st), u1q((size_t) L * N * 8, st), perm(ct_words * 8, st);
+    Scratch accum(ct_words * 8, st), u(ct_words * 8, st), u1q((size_t) L * N * 8, st);
     const dim3 g1(c.n >> 8, pql, 1), g2(c.n >> 8, pql, 2);
     const PrimeList pl = level_primes(L, K, depth);
 
@@ -1780,11 +1803,7 @@ void op_bsgs_matvec(const Context& c, const u64* in, u64* out, const u64* diags,
         keyswitch_mac(c, tmp.w(), baby_keys[i], acc.w(), d, depth, 1, st);
         {
             LaunchScope scope(KC_ELEMENTWISE, st);
-            k_pql_add<<<g1, 256, 0, st>>>(acc.w(), Pc0.w(), acc.w(), c.d_mod, c.logn, L, depth, pql);
-        }
-        {
-            LaunchScope scope(KC_ELEMENTWISE, st);
-            k_galois_permute_ntt<<<g2, 256, 0, st>>>(acc.w(), 0, bi, 0, c.logn, pql, baby_elts[i]);
+            k_pql_add_permute<false><<<g2, 256, 0, st>>>(acc.w(), Pc0.w(), bi, c.d_mod, c.logn, L, depth, pql, baby_elts[i]);
         }
     }
     check_launch();
@@ -1814,23 +1833,16 @@ void op_bsgs_matvec(const Context& c, const u64* in, u64* out, const u64* diags,
             k_moddown_ext<false><<<dim3(c.n >> 8, 1), 256, 0, st>>>(u1, u1q.w(), 0, nullptr, c.d_pc, c.d_half, c.d_half_mod,
                                                                  c.d_lqm_pair, 0, c.logn, pql, L, c.Qp, c.Q_size, K, 0);
         }
-        keyswitch_modup_ntt(c, u1q.w(), L * N, tmp.w(), depth, 1, st, false);
-        keyswitch_mac(c, tmp.w(), giant_keys[j], acc.w(), d, depth, 1, st);
+        // the giant step's own decomposition reuses the buffer of the hoisted digits (the reference keeps two,
+        // temp3 / temp3_gs): the baby steps are complete at this point.  The digits are used by one key only, so
+        // the fused key switch applies (row stages inside the inner product)
+        keyswitch_core(c, u1q.w(), L * N, giant_keys[j], tmp.w(), acc.w(), depth, 1, st, false);
         {
             LaunchScope scope(KC_ELEMENTWISE, st);
-            k_pql_add<<<g1, 256, 0, st>>>(acc.w(), u.w(), acc.w(), c.d_mod, c.logn, L, depth, pql);
-        }
-        {
-            LaunchScope scope(KC_ELEMENTWISE, st);
-            k_galois_permute_ntt<<<g2, 256, 0, st>>>(acc.w(), 0, perm.w(), 0, c.logn, pql, giant_elts[j]);
-        }
-        {
-            LaunchScope scope(KC_ELEMENTWISE, st);
-            k_pql_add<<<g2, 256, 0, st>>>(accum.w(), perm.w(), accum.w(), c.d_mod, c.logn, L, depth, pql);
+            k_pql_add_permute<true><<<g2, 256, 0, st>>>(acc.w(), u.w(), accum.w(), c.d_mod, c.logn, L, depth, pql,
+                                                        giant_elts[j]);
         }
         check_launch();
-        // the hoisted digits of the INPUT were overwritten by the giant step's own decomposition: the reference
-        // keeps two buffers (temp3 / temp3_gs); baby steps are complete at this point, so one buffer serves both
     }
     // final mod-down of both components: PQ_l -> Q_l
     launch_ntt(c, accum.w(), accum.w(), 2 * pql, pl, true, st);

@@ -40,6 +40,8 @@ struct RefGpu {
     std::vector<RefLevel2> lvl2;
     Data64* temp; // big scratch
     size_t temp_words;
+    Data64* bsgs_ws = nullptr; // multiply_matrix_v2 temporaries (the reference draws them from its stream-ordered pool)
+    size_t bsgs_words = 0;
 };
 
 template <class T> static T* up(const T* h, size_t count)
@@ -160,6 +162,7 @@ void refgpu_destroy(void* hv)
         cudaFree(l.Iloc);
     }
     cudaFree(h->temp);
+    cudaFree(h->bsgs_ws);
     delete h;
 }
 
@@ -387,9 +390,19 @@ int refgpu_bsgs_matvec(void* hv, Data64* ct, Data64* out, Data64* matrix, const 
     const int iteration_count_1 = d_level / 4, iteration_count_2 = d_level % 4;
     const size_t baby_ct_size = (size_t) 2 * pql_count * n;
 
-    auto dmalloc = [](size_t words) {
-        Data64* p = nullptr;
-        cudaMalloc(&p, words * sizeof(Data64));
+    const size_t ws_need = (size_t) 2 * n * Q_size + 2 * ((size_t) 2 * n * d_level * current_rns_mod_count) + baby_ct_size * n1 +
+                           2 * ((size_t) 2 * n * current_rns_mod_count) + (size_t) pql_count * n + 3 * baby_ct_size +
+                           (size_t) current_decomp_count * n;
+    if (h->bsgs_words < ws_need)
+    {
+        cudaFree(h->bsgs_ws);
+        cudaMalloc(&h->bsgs_ws, ws_need * sizeof(Data64));
+        h->bsgs_words = ws_need;
+    }
+    Data64* ws_next = h->bsgs_ws;
+    auto dmalloc = [&](size_t words) {
+        Data64* p = ws_next;
+        ws_next += words;
         return p;
     };
     Data64* temp0 = dmalloc((size_t) 2 * n * Q_size);
@@ -478,8 +491,7 @@ int refgpu_bsgs_matvec(void* hv, Data64* ct, Data64* out, Data64* matrix, const 
     gpuntt::GPU_NTT_Inplace(out, h->ntt_table, h->modulus, cfg_ntt, 2 * current_decomp_count, current_decomp_count);
     cudaStreamSynchronize(stream);
     int err = (int) cudaGetLastError();
-    for (Data64* p : {temp0, temp3, baby_results, temp4, Pc0, gs_accum, u_pql, u1_Q, temp3_gs, temp4_gs, permuted_gs, P_mod_q_dev})
-        cudaFree(p);
+    cudaFree(P_mod_q_dev);
     cudaFree(pq_modulus_dev);
     cudaFree(ct_indices_all);
     return err;
