@@ -171,6 +171,10 @@ static void finish_context(Context& c, int device, int log_n, int n_q, int n_p, 
         c.skip_own = atoi(v);
     if (const char* v = getenv("HEON_COL_TMA"))
         c.col_tma = atoi(v);
+    if (const char* v = getenv("HEON_COL_TMA_TILES"))
+        c.col_tma_tiles = atoi(v);
+    if (const char* v = getenv("HEON_COL_TMA_BUFS"))
+        c.col_tma_bufs = atoi(v);
     if (const char* v = getenv("HEON_ROW_MAC"))
         c.row_mac = atoi(v);
     if (const char* v = getenv("HEON_MODUP_FUSED"))

@@ -117,7 +117,9 @@ struct Context {
     int galois_ntt = 1; // CKKS automorphisms as NTT-domain permutations after an NTT-domain key switch (HEON_GALOIS_NTT=0: coefficient-domain path)
     int ntt_fused = 0; // forward transform as one ticket-ordered kernel, pass-to-pass data in L2 (HEON_NTT_FUSED=1 enables; superseded by the pipelined kernel)
     int use_fp64 = 1; // FP64-pipe quotient for primes < 2^50 (HEON_NTT_FP64=0 disables)
-    int col_tma = -1; // forward column pass at N = 2^16 through TMA tiles: -1 = only for the maps that transform their input (fused Method-I mod-up, divide-round), 1 = always, 0 = never (HEON_COL_TMA)
+    int col_tma = 1;             // HEON_COL_TMA: forward column pass at N = 2^16 through pipelined TMA tiles (0: register-resident LSU form)
+    int col_tma_bufs = 2;        // HEON_COL_TMA_BUFS: tile buffers per CTA of the pipelined TMA column pass (2: 3 CTAs/SM, 3: 2 CTAs/SM)
+    int col_tma_tiles = 0;       // HEON_COL_TMA_TILES: tiles one CTA of the TMA column pass walks (0 = by grid size)
     int row_mac = 1; // key switch: forward row pass fused with the inner product (HEON_ROW_MAC=0: separate kernels)
     int modup_fused = 0; // HEON_MODUP_FUSED=1: Method-II mod-up computed inside the column-pass load (no converted-digit buffer; measured slower than the separate FP64 kernel on B200, kept opt-in)
     int row_mac_rows = 4; // rows per CTA of the fused kernel: 4 (default, 6 CTAs/SM: +2 % measured) or 8 (HEON_ROW_MAC_ROWS)

@@ -347,13 +347,22 @@ __device__ __forceinline__ void gs_bfly(u64& X, u64& Y, const TwPair& w, const B
 
 // One stage on the 16 registers; butterflies pair k and k + 2^LS, the
 // twiddle changes every 2^(LS+1) registers.
-template <int LS, bool INV, int VAR, int GSTRIDE = 1, bool RED = false>
+// SMTW: the twiddles were staged in shared memory (plain loads instead of ld.global.nc)
+template <int LS, bool INV, int VAR, int GSTRIDE = 1, bool RED = false, bool SMTW = false>
 __device__ __forceinline__ void stage16(u64 (&v)[16], const TwPair* __restrict__ tw, const BflyConst& c)
 {
 #pragma unroll
     for (int g = 0; g < (8 >> LS); ++g)
     {
-        const TwPair w = ld_tw(tw + g * GSTRIDE);
+        TwPair w;
+        if constexpr (SMTW)
+        {
+            const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(tw + g * GSTRIDE);
+            w.w = t.x;
+            w.ws = t.y;
+        }
+        else
+            w = ld_tw(tw + g * GSTRIDE);
 #pragma unroll
         for (int j = 0; j < (1 << LS); ++j)
         {
@@ -418,14 +427,14 @@ __device__ __forceinline__ void ct_round_b_sm(u64 (&v)[16], const double* rowtw,
 // PH: VAR 4 reduces X on every other stage; PH = 0 gives the pattern -,R,-,R (column pass, whose
 // input is canonical), PH = 1 gives R,-,R,- (row pass: its first stage follows an unreduced or
 // reduced column-pass stage alike).
-template <int VAR, int PH = 0>
+template <int VAR, int PH = 0, bool SMTW = false>
 __device__ __forceinline__ void ct_round_a(u64 (&v)[16], const TwPair* __restrict__ tw, int s0, int q,
                                            const BflyConst& c)
 {
-    stage16<3, false, VAR, 1, PH == 1>(v, tw + (1 << (s0 + 0)) + (q << 0), c);
-    stage16<2, false, VAR, 1, PH == 0>(v, tw + (1 << (s0 + 1)) + (q << 1), c);
-    stage16<1, false, VAR, 1, PH == 1>(v, tw + (1 << (s0 + 2)) + (q << 2), c);
-    stage16<0, false, VAR, 1, PH == 0>(v, tw + (1 << (s0 + 3)) + (q << 3), c);
+    stage16<3, false, VAR, 1, PH == 1, SMTW>(v, tw + (1 << (s0 + 0)) + (q << 0), c);
+    stage16<2, false, VAR, 1, PH == 0, SMTW>(v, tw + (1 << (s0 + 1)) + (q << 1), c);
+    stage16<1, false, VAR, 1, PH == 1, SMTW>(v, tw + (1 << (s0 + 2)) + (q << 2), c);
+    stage16<0, false, VAR, 1, PH == 0, SMTW>(v, tw + (1 << (s0 + 3)) + (q << 3), c);
 }
 
 template <int GVAR>
@@ -481,19 +490,19 @@ __device__ __forceinline__ void gs_round_a_final(u64 (&v)[16], const TwPair* __r
 
 // Round B: the S-4 stages with strides < 16 when the thread holds the 16
 // contiguous indices idx = 16*tt + k.
-template <int S, int VAR, int PH = 0>
+template <int S, int VAR, int PH = 0, bool SMTW = false>
 __device__ __forceinline__ void ct_round_b(u64 (&v)[16], const TwPair* __restrict__ tw, int s0, int q,
                                            int tt, const BflyConst& c)
 {
     // pass-stage u = 4..S-1, register stride 2^(S-1-u)
     if constexpr (S >= 5)
-        stage16<S - 5, false, VAR, 1, PH == 1>(v, tw + (1 << (s0 + 4)) + (q << 4) + (tt << (8 - S)), c);
+        stage16<S - 5, false, VAR, 1, PH == 1, SMTW>(v, tw + (1 << (s0 + 4)) + (q << 4) + (tt << (8 - S)), c);
     if constexpr (S >= 6)
-        stage16<S - 6, false, VAR, 1, PH == 0>(v, tw + (1 << (s0 + 5)) + (q << 5) + (tt << (9 - S)), c);
+        stage16<S - 6, false, VAR, 1, PH == 0, SMTW>(v, tw + (1 << (s0 + 5)) + (q << 5) + (tt << (9 - S)), c);
     if constexpr (S >= 7)
-        stage16<S - 7, false, VAR, 1, PH == 1>(v, tw + (1 << (s0 + 6)) + (q << 6) + (tt << (10 - S)), c);
+        stage16<S - 7, false, VAR, 1, PH == 1, SMTW>(v, tw + (1 << (s0 + 6)) + (q << 6) + (tt << (10 - S)), c);
     if constexpr (S >= 8)
-        stage16<S - 8, false, VAR, 1, PH == 0>(v, tw + (1 << (s0 + 7)) + (q << 7) + (tt << (11 - S)), c);
+        stage16<S - 8, false, VAR, 1, PH == 0, SMTW>(v, tw + (1 << (s0 + 7)) + (q << 7) + (tt << (11 - S)), c);
 }
 
 // Round B of the 256-point row transform with the lane-major twiddle block of

@@ -234,6 +234,10 @@ __device__ __forceinline__ void col_pass_body(const Map& map, const u64* in, u64
     const int tt = threadIdx.x / C;
     const int col = tile * C + c;
     u64 v[16];
+    // transposition space: row r of the column tile at word smi(r).  With 8 columns a row is half a bank line and
+    // the rows 16 apart that a half-warp reads back would share their banks: the row's lowest bit is flipped by
+    // its bit 4, which keeps the writes (adjacent rows) and the reads (rows 16 apart) conflict-free
+    auto smi = [&](int r) { return (C == 8 ? (r ^ ((r >> 4) & 1)) : r) * C + c; };
 
     if constexpr (!INV)
     {
@@ -261,11 +265,11 @@ __device__ __forceinline__ void col_pass_body(const Map& map, const u64* in, u64
         {
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-                sm[(tt + T * k) * C + c] = v[k];
+                sm[smi(tt + T * k)] = v[k];
             __syncthreads();
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-                v[k] = sm[(16 * tt + k) * C + c];
+                v[k] = sm[smi(16 * tt + k)];
             ct_round_b<S, VAR>(v, tw, 0, 0, tt, bc);
 #pragma unroll
             for (int k = 0; k < 16; ++k)
@@ -290,11 +294,11 @@ __device__ __forceinline__ void col_pass_body(const Map& map, const u64* in, u64
             gs_round_b<S, VAR>(v, tw, 0, 0, tt, bc);
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-                sm[(16 * tt + k) * C + c] = v[k];
+                sm[smi(16 * tt + k)] = v[k];
             __syncthreads();
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-                v[k] = sm[(tt + T * k) * C + c];
+                v[k] = sm[smi(tt + T * k)];
         }
         else
         {
@@ -819,7 +823,7 @@ constexpr int kPipeStages = 6;
 constexpr int kPipeGroups = 2;
 constexpr int kPipeThreads = 64 + 256 * kPipeGroups;
 
-template <int VAR, class Map>
+template <int VAR, class Map, bool SMTW = false>
 __device__ __forceinline__ void pipe_col_tile(unsigned char* tile, const Map& map, int prime, const PrimeConst& pc,
                                               const TwPair* __restrict__ tw, int aux, int tid, int bar_id)
 {
@@ -835,7 +839,7 @@ __device__ __forceinline__ void pipe_col_tile(unsigned char* tile, const Map& ma
             x = map.xform(x, prime, pc, aux);
         v[k] = ct_prep<VAR>(x, bc, Map::kLazyIn);
     }
-    ct_round_a<VAR>(v, tw, 0, 0, bc);
+    ct_round_a<VAR, 0, SMTW>(v, tw, 0, 0, bc);
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         *reinterpret_cast<u64*>(pa + k * 2048) = v[k];
@@ -844,7 +848,7 @@ __device__ __forceinline__ void pipe_col_tile(unsigned char* tile, const Map& ma
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         v[k] = *reinterpret_cast<const u64*>(pb + k * 128 + (((c >> 1) ^ (k & 7)) << 4));
-    ct_round_b<8, VAR>(v, tw, 0, 0, tt, bc);
+    ct_round_b<8, VAR, 0, SMTW>(v, tw, 0, 0, tt, bc);
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         *reinterpret_cast<u64*>(pb + k * 128 + (((c >> 1) ^ (k & 7)) << 4)) = v[k]; // lazy, finished by the row tile
@@ -1171,6 +1175,86 @@ __global__ void __launch_bounds__(256, 3)
     }
 }
 
+// The same tile, pipelined: one CTA walks G consecutive tiles of a polynomial through two 32 KiB buffers.  The
+// load of tile i+1 is in flight while tile i is transformed, and the store of tile i leaves while tile i+1 is
+// transformed, so the arithmetic of a CTA never waits for DRAM after its first tile (the single-tile form keeps
+// the FP64 pipe 56-69 % busy: three resident CTAs cannot cover each other's load latency).
+template <class Map, int G, int NB>
+__global__ void __launch_bounds__(256, NB == 3 ? 2 : 3)
+    ntt_col_pass_tma_pipe(Map map, const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+                          const u64* in_base, const u64* out_base, const TwPair* __restrict__ tw_all,
+                          const PrimeConst* __restrict__ pcs, int variant)
+{
+    static_assert(16 % G == 0, "the tiles of a CTA belong to one polynomial");
+    static_assert(NB == 2 || NB == 3, "two or three tile buffers");
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar[NB];
+    __shared__ __align__(8) uint64_t twbar;
+    __shared__ __align__(16) TwPair twsm[256]; // the 255 twiddles of the eight column stages of this prime
+    unsigned char* buf0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const long long z = blockIdx.x / (16 / G);
+    const int tile0 = (blockIdx.x % (16 / G)) * G;
+    const u64* in;
+    u64* out;
+    int prime, aux;
+    map.get(z, in, out, prime, aux);
+    const int row_in = (int) ((in - in_base) >> 8), row_out = (int) ((out - out_base) >> 8);
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+            mbar_init(&bar[b], 1);
+        mbar_init(&twbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        mbar_arrive_expect_tx(&bar[0], kRowTileBytes);
+        tma_load_3d(buf0, &tm_in, &bar[0], 0, tile0, row_in);
+        mbar_arrive_expect_tx(&twbar, sizeof(twsm));
+        tma_load_1d(twsm, tw_all + ((long long) prime << 16), sizeof(twsm), &twbar);
+    }
+    const PrimeConst pc = pcs[prime];
+    const TwPair* tw = twsm;
+    mbar_wait(&twbar, 0);
+    int b = 0, ph = 0; // buffer and mbarrier phase of tile i
+#pragma unroll 1
+    for (int i = 0; i < G; ++i)
+    {
+        unsigned char* buf = buf0 + b * kRowTileBytes;
+        const int bn = (b + 1 == NB) ? 0 : b + 1;
+        if (threadIdx.x == 0 && i + 1 < G)
+        {
+            // buffer bn was stored NB-1 tiles ago: with three buffers the store issued last may still be reading
+            tma_store_wait_read<NB - 2>();
+            mbar_arrive_expect_tx(&bar[bn], kRowTileBytes);
+            tma_load_3d(buf0 + bn * kRowTileBytes, &tm_in, &bar[bn], 0, tile0 + i + 1, row_in);
+        }
+        mbar_wait(&bar[b], ph);
+        if (pc.fp_var == 3)
+            pipe_col_tile<3, Map, true>(buf, map, prime, pc, tw, aux, threadIdx.x, 1);
+        else if (pc.fp_var == 4)
+            pipe_col_tile<4, Map, true>(buf, map, prime, pc, tw, aux, threadIdx.x, 1);
+        else if (variant == 1 || !pc.nc_ok)
+            pipe_col_tile<1, Map, true>(buf, map, prime, pc, tw, aux, threadIdx.x, 1);
+        else
+            pipe_col_tile<2, Map, true>(buf, map, prime, pc, tw, aux, threadIdx.x, 1);
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            tma_store_3d(&tm_out, buf, 0, tile0 + i, row_out);
+            tma_store_commit();
+        }
+        if (bn == 0)
+            ph ^= 1;
+        b = bn;
+    }
+    if (threadIdx.x == 0)
+        tma_store_wait_read<0>();
+}
+
 // ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
@@ -1400,9 +1484,10 @@ static bool launch_col_tma(const Context& c, const Map& m, long long n_polys, co
         return false;
     else
     {
-        // measured on B200: +4.5 % for the maps that transform their input (Method-I mod-up: 16-byte segments of a
-        // source 38 outputs share), -6 % for the in-place maps, which keep the 128-thread register-resident form
-        if (c.col_tma == 0 || (c.col_tma < 0 && !Map::kXform) || !c.use_tma || c.logn != 16 || !e.col_in_base || n_polys < 1)
+        // measured on B200 (C3-II, per op): register-resident LSU form 91.9 us, one TMA tile per CTA 94.7 us,
+        // pipelined walk over 8 tiles with the stage twiddles in shared memory 77.5 us (two buffers, 3 CTAs/SM;
+        // three buffers at 2 CTAs/SM: 82.4 us)
+        if (c.col_tma == 0 || !c.use_tma || c.logn != 16 || !e.col_in_base || n_polys < 1)
             return false;
         if ((reinterpret_cast<uintptr_t>(e.col_in_base) | reinterpret_cast<uintptr_t>(e.out_base)) & 127)
             return false;
@@ -1410,12 +1495,27 @@ static bool launch_col_tma(const Context& c, const Map& m, long long n_polys, co
             return false;
         const CUtensorMap tm_in = make_col_map(e.col_in_base, e.col_in_words);
         const CUtensorMap tm_out = make_col_map(e.out_base, e.out_words);
-        auto kfn = ntt_col_pass_tma<Map>;
-        const int smem = kRowTileBytes + 1024;
-        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         LaunchScope scope(KC_NTT_FWD_COL, st);
-        kfn<<<(unsigned) (n_polys * 16), 256, smem, st>>>(m, tm_in, tm_out, e.col_in_base, e.out_base, c.d_fwd, c.d_pc,
-                                                        c.ntt_variant);
+        auto go = [&](auto kfn, int G, int nb) {
+            const int smem = (G > 1 ? nb : 1) * kRowTileBytes + 1024;
+            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            kfn<<<(unsigned) (n_polys * 16 / G), 256, smem, st>>>(m, tm_in, tm_out, e.col_in_base, e.out_base, c.d_fwd, c.d_pc,
+                                                                c.ntt_variant);
+        };
+        // tiles per CTA: enough CTAs to fill the GPU three deep before the walk is lengthened
+        const long long tiles = n_polys * 16;
+        const int want = c.col_tma_tiles > 0 ? c.col_tma_tiles : (tiles >= 16 * 444 ? 8 : tiles >= 4 * 444 ? 4 : 1);
+        const bool three = c.col_tma_bufs == 3;
+        if (want >= 16)
+            three ? go(ntt_col_pass_tma_pipe<Map, 16, 3>, 16, 3) : go(ntt_col_pass_tma_pipe<Map, 16, 2>, 16, 2);
+        else if (want >= 8)
+            three ? go(ntt_col_pass_tma_pipe<Map, 8, 3>, 8, 3) : go(ntt_col_pass_tma_pipe<Map, 8, 2>, 8, 2);
+        else if (want >= 4)
+            three ? go(ntt_col_pass_tma_pipe<Map, 4, 3>, 4, 3) : go(ntt_col_pass_tma_pipe<Map, 4, 2>, 4, 2);
+        else if (want >= 2)
+            go(ntt_col_pass_tma_pipe<Map, 2, 2>, 2, 2);
+        else
+            go(ntt_col_pass_tma<Map>, 1, 1);
         return true;
     }
 }

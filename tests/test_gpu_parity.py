@@ -286,7 +286,10 @@ def _ctx_with_env(name, **env):
 
 @pytest.mark.parametrize("env", [{"HEON_NTT_PIPE": 1}, {"HEON_NTT_FUSED": 1}, {"HEON_NTT_FP64": 0}, {"HEON_NTT_TMA": 0},
                                  {"HEON_ROW_TILE": 16}, {"HEON_ROW_TILE": 4}, {"HEON_COL_THREADS": 256},
-                                 {"HEON_COL_THREADS": 128}, {"HEON_NTT_PERSISTENT": 1}, {"HEON_COL_TMA": 0}, {"HEON_COL_TMA": 1}])
+                                 {"HEON_COL_THREADS": 128}, {"HEON_NTT_PERSISTENT": 1}, {"HEON_COL_TMA": 0}, {"HEON_COL_TMA_TILES": 1},
+                                 {"HEON_COL_TMA_TILES": 2}, {"HEON_COL_TMA_TILES": 8}, {"HEON_COL_TMA_TILES": 16},
+                                 {"HEON_COL_TMA_TILES": 4, "HEON_COL_TMA_BUFS": 3},
+                                 {"HEON_COL_TMA_TILES": 16, "HEON_COL_TMA_BUFS": 3}])
 def test_alternate_ntt_paths_agree(env):
     """The opt-in transforms (warp-specialised pipelined kernel, ticket-ordered fused kernel), the
     integer-only butterflies and the LSU row pass must give the default path's words."""
@@ -314,7 +317,9 @@ def test_alternate_ntt_paths_agree(env):
                                       ("n16_II_small", {"HEON_MODUP_FUSED": 1}), ("n13_II", {"HEON_MODUP_FUSED": 1}),
                                       ("n16_II_small", {"HEON_MODUP_FUSED": 1, "HEON_SKIP_OWN": 0}),
                                       ("n15_II", {"HEON_MODUP_FUSED": 1, "HEON_ROW_MAC": 0}),
-                                      ("n16_II_small", {"HEON_COL_TMA": 1}), ("n16_I_small", {"HEON_COL_TMA": 0})])
+                                      ("n16_II_small", {"HEON_COL_TMA": 0}), ("n16_I_small", {"HEON_COL_TMA": 0}),
+                                      ("n16_II_small", {"HEON_COL_TMA_TILES": 8}), ("n16_I_small", {"HEON_COL_TMA_TILES": 4}),
+                                      ("n16_I_small", {"HEON_COL_TMA_TILES": 16, "HEON_COL_TMA_BUFS": 3})])
 def test_alternate_operator_paths_agree(name, env):
     """multiply + relinearize + rotation through the alternate paths equal the default path."""
     api = _api()

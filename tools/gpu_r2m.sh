@@ -1,4 +1,21 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 1700 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/r2m_pytest.txt 2>&1; echo "pytest exit $?" >> gpurun_out/r2m_pytest.txt
-tail -15 gpurun_out/r2m_pytest.txt
+# pipelined TMA column pass: parity + step timing by tiles per CTA / buffers
+HEON_COL_TMA=1 HEON_COL_TMA_BUFS=3 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "ntt or reference_kernels" 2>&1 | tail -3
+run() { # workload env...
+  wl=$1; shift
+  env "$@" python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2m.json 2> gpurun_out/r2m.err
+  python - "$wl $*" <<PY
+import json,sys
+d=json.loads([l for l in open('gpurun_out/r2m.json') if l.startswith('{')][-1])
+ks={k['kernel']: round(k['ms_per_op']*1000,1) for k in d['kernels']}
+print(sys.argv[1], 'value', round(d['value'],1), 'ntt frac', round(d['roofline_ntt']['frac'],4), 'col', ks.get('ntt_fwd_col_pass'))
+PY
+}
+run C3_II HEON_COL_TMA=-1
+run C3_II HEON_COL_TMA=1 HEON_COL_TMA_TILES=8 HEON_COL_TMA_BUFS=2
+run C3_II HEON_COL_TMA=1 HEON_COL_TMA_TILES=8 HEON_COL_TMA_BUFS=3
+run C3_II HEON_COL_TMA=1 HEON_COL_TMA_TILES=16 HEON_COL_TMA_BUFS=3
+run C3_II HEON_COL_TMA=1 HEON_COL_TMA_TILES=4 HEON_COL_TMA_BUFS=3
+run C3_I HEON_COL_TMA=-1
+run C3_I HEON_COL_TMA=1 HEON_COL_TMA_TILES=8 HEON_COL_TMA_BUFS=2
+run C3_I HEON_COL_TMA=1 HEON_COL_TMA_TILES=8 HEON_COL_TMA_BUFS=3
