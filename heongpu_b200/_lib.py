@@ -74,6 +74,18 @@ SIGNATURES = {
     "heon_compress_bound": (C.c_size_t, [C.c_size_t]),
     "heon_compress": (ci, [vp, C.c_size_t, vp, C.POINTER(C.c_size_t)]),
     "heon_decompress": (ci, [vp, C.c_size_t, vp, C.POINTER(C.c_size_t)]),
+    "heon_tfhe_create": (ci, [ci, C.POINTER(vp)]),
+    "heon_tfhe_destroy": (None, [vp]),
+    "heon_tfhe_params": (ci, [vp, C.POINTER(ci)]),
+    "heon_tfhe_gate": (ci, [vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, vp]),
+    "heon_tfhe_gate_linear": (ci, [vp, ci, vp, vp, vp, vp, vp, vp, ci, ci, vp]),
+    "heon_tfhe_bootstrap": (ci, [vp, vp, vp, vp, vp, vp, ci, vp]),
+    "heon_tfhe_keyswitch": (ci, [vp, vp, vp, vp, vp, vp, vp, ci, vp]),
+    "heon_tfhe_keygen_secret": (ci, [vp, C.c_uint64, vp, vp, vp]),
+    "heon_tfhe_keygen_boot": (ci, [vp, vp, vp, C.c_uint64, vp, vp, vp, vp]),
+    "heon_tfhe_encrypt": (ci, [vp, vp, vp, C.c_uint64, vp, vp, ci, vp]),
+    "heon_tfhe_phase": (ci, [vp, vp, vp, vp, vp, ci, ci, vp]),
+    "heon_tfhe_ntt": (ci, [vp, vp, ci, ci, vp]),
     "heon_profile_begin": (ci, []),
     "heon_profile_end": (ci, [C.POINTER(C.c_double), i64p, ci]),
     "heon_profile_class_name": (C.c_char_p, [ci]),

@@ -994,11 +994,153 @@ int heon_profile_end(double* ms, long long* launches, int capacity)
     profile_end(ms, launches);
     return KC_COUNT;
 }
+// ---- TFHE gate bootstrapping (csrc/tfhe.cu) ----
+struct heon_tfhe_s {
+    TfheContext* c;
+};
+struct TfheGuard {
+    int prev = -1;
+    explicit TfheGuard(heon_tfhe_s* h)
+    {
+        if (!h || !h->c)
+            throw std::invalid_argument("null TFHE context");
+        cudaGetDevice(&prev);
+        cudaSetDevice(tfhe_device(h->c));
+        cudaGetLastError();
+    }
+    ~TfheGuard()
+    {
+        if (prev >= 0)
+            cudaSetDevice(prev);
+    }
+};
+
+int heon_tfhe_create(int device, heon_tfhe_t* out)
+{
+    return guarded([&] {
+        if (!out)
+            throw std::invalid_argument("null argument");
+        *out = nullptr;
+        auto h = std::make_unique<heon_tfhe_s>();
+        h->c = tfhe_create(device);
+        *out = h.release();
+    });
+}
+void heon_tfhe_destroy(heon_tfhe_t h)
+{
+    if (h)
+    {
+        tfhe_destroy(h->c);
+        delete h;
+    }
+}
+int heon_tfhe_params(heon_tfhe_t h, int* out7)
+{
+    return guarded([&] {
+        if (!h || !h->c || !out7)
+            throw std::invalid_argument("null argument");
+        tfhe_params(h->c, out7);
+    });
+}
+int heon_tfhe_gate_linear(heon_tfhe_t h, int gate, const int32_t* a1, const int32_t* b1, const int32_t* a2, const int32_t* b2,
+                          int32_t* out_a, int32_t* out_b, int n, int shape, void* stream)
+{
+    return guarded([&] {
+        TfheGuard g(h);
+        if (!a1 || !b1 || !out_a || !out_b || (gate != 7 && (!a2 || !b2)))
+            throw std::invalid_argument("null argument");
+        tfhe_gate_linear(*h->c, gate, a1, b1, a2, b2, out_a, out_b, n, shape, (cudaStream_t) stream);
+    });
+}
+int heon_tfhe_bootstrap(heon_tfhe_t h, const int32_t* in_a, const int32_t* in_b, int32_t* out_a, int32_t* out_b,
+                        const uint64_t* boot_key, int shape, void* stream)
+{
+    return guarded([&] {
+        TfheGuard g(h);
+        if (!in_a || !in_b || !out_a || !out_b || !boot_key)
+            throw std::invalid_argument("null argument");
+        tfhe_bootstrap(*h->c, in_a, in_b, out_a, out_b, (const u64*) boot_key, shape, (cudaStream_t) stream);
+    });
+}
+int heon_tfhe_keyswitch(heon_tfhe_t h, const int32_t* in_a, const int32_t* in_b, int32_t* out_a, int32_t* out_b,
+                        const int32_t* ks_a, const int32_t* ks_b, int shape, void* stream)
+{
+    return guarded([&] {
+        TfheGuard g(h);
+        if (!in_a || !in_b || !out_a || !out_b || !ks_a || !ks_b)
+            throw std::invalid_argument("null argument");
+        tfhe_keyswitch(*h->c, in_a, in_b, out_a, out_b, ks_a, ks_b, shape, (cudaStream_t) stream);
+    });
+}
+int heon_tfhe_gate(heon_tfhe_t h, int gate, const int32_t* a1, const int32_t* b1, const int32_t* a2, const int32_t* b2,
+                   const int32_t* a3, const int32_t* b3, int32_t* out_a, int32_t* out_b, const uint64_t* boot_key,
+                   const int32_t* ks_a, const int32_t* ks_b, int shape, void* stream)
+{
+    return guarded([&] {
+        TfheGuard g(h);
+        if (!a1 || !b1 || !out_a || !out_b)
+            throw std::invalid_argument("null argument");
+        if (gate != 7 && (!a2 || !b2 || !boot_key || !ks_a || !ks_b))
+            throw std::invalid_argument("null argument");
+        tfhe_gate(*h->c, gate, a1, b1, a2, b2, a3, b3, out_a, out_b, (const u64*) boot_key, ks_a, ks_b, shape,
+                  (cudaStream_t) stream);
+    });
+}
+int heon_tfhe_keygen_secret(heon_tfhe_t h, uint64_t seed, int32_t* lwe_key, int32_t* tlwe_key, void* stream)
+{
+    return guarded([&] {
+        TfheGuard g(h);
+        if (!lwe_key || !tlwe_key)
+            throw std::invalid_argument("null argument");
+        tfhe_keygen_secret(*h->c, seed, lwe_key, tlwe_key, (cudaStream_t) stream);
+    });
+}
+int heon_tfhe_keygen_boot(heon_tfhe_t h, const int32_t* lwe_key, const int32_t* tlwe_key, uint64_t seed, uint64_t* boot_key,
+                          int32_t* ks_a, int32_t* ks_b, void* stream)
+{
+    return guarded([&] {
+        TfheGuard g(h);
+        if (!lwe_key || !tlwe_key || !boot_key || !ks_a || !ks_b)
+            throw std::invalid_argument("null argument");
+        tfhe_keygen_boot(*h->c, lwe_key, tlwe_key, seed, (u64*) boot_key, ks_a, ks_b, (cudaStream_t) stream);
+    });
+}
+int heon_tfhe_encrypt(heon_tfhe_t h, const int32_t* lwe_key, const int32_t* d_messages, uint64_t seed, int32_t* out_a,
+                      int32_t* out_b, int shape, void* stream)
+{
+    return guarded([&] {
+        TfheGuard g(h);
+        if (!lwe_key || !d_messages || !out_a || !out_b)
+            throw std::invalid_argument("null argument");
+        tfhe_encrypt(*h->c, lwe_key, d_messages, seed, out_a, out_b, shape, (cudaStream_t) stream);
+    });
+}
+int heon_tfhe_phase(heon_tfhe_t h, const int32_t* lwe_key, const int32_t* in_a, const int32_t* in_b, int32_t* d_phase, int n,
+                    int shape, void* stream)
+{
+    return guarded([&] {
+        TfheGuard g(h);
+        if (!lwe_key || !in_a || !in_b || !d_phase)
+            throw std::invalid_argument("null argument");
+        tfhe_phase(*h->c, lwe_key, in_a, in_b, d_phase, n, shape, (cudaStream_t) stream);
+    });
+}
+int heon_tfhe_ntt(heon_tfhe_t h, uint64_t* data, int count, int inverse, void* stream)
+{
+    return guarded([&] {
+        TfheGuard g(h);
+        if (!data)
+            throw std::invalid_argument("null argument");
+        tfhe_ntt(*h->c, (u64*) data, count, inverse != 0, (cudaStream_t) stream);
+    });
+}
+
 const char* heon_profile_class_name(int cls)
 {
     static const char* names[KC_COUNT] = {"ntt_fwd_col_pass", "ntt_fwd_row_pass", "ntt_inv_row_pass",
                                           "ntt_inv_col_pass", "keyswitch_mac",   "modup_method2",
-                                          "moddown",          "cross_multiply",  "elementwise", "keyswitch_row_mac"};
+                                          "moddown",          "cross_multiply",  "elementwise", "keyswitch_row_mac",
+                                          "tfhe_blind_rotate", "tfhe_keyswitch"};
     return (cls >= 0 && cls < KC_COUNT) ? names[cls] : "";
 }
 

@@ -19,6 +19,8 @@ enum KernelClass {
     KC_CROSS_MULTIPLY,
     KC_ELEMENTWISE,
     KC_ROW_MAC,
+    KC_TFHE_BLIND_ROTATE,
+    KC_TFHE_KEYSWITCH,
     KC_COUNT
 };
 
@@ -70,5 +72,29 @@ void op_bfv_relinearize(const Context& c, u64* ct, long long ct_bs, const u64* r
 void op_apply_galois(const Context& c, const u64* in, long long in_bs, u64* out, long long out_bs,
                      const u64* galois_key, unsigned galois_elt, int depth, int batch,
                      cudaStream_t st);
+
+
+// TFHE gate bootstrapping (csrc/tfhe.cu)
+struct TfheContext;
+TfheContext* tfhe_create(int device);
+void tfhe_destroy(TfheContext* c);
+int tfhe_device(const TfheContext* c);
+void tfhe_params(const TfheContext* c, int* out7);
+void tfhe_gate_linear(const TfheContext& c, int gate, const int* a1, const int* b1, const int* a2, const int* b2, int* oa,
+                      int* ob, int n, int shape, cudaStream_t st);
+void tfhe_bootstrap(const TfheContext& c, const int* in_a, const int* in_b, int* out_a, int* out_b, const u64* bk, int shape,
+                    cudaStream_t st);
+void tfhe_keyswitch(const TfheContext& c, const int* in_a, const int* in_b, int* out_a, int* out_b, const int* ks_a,
+                    const int* ks_b, int shape, cudaStream_t st);
+void tfhe_gate(const TfheContext& c, int gate, const int* a1, const int* b1, const int* a2, const int* b2, const int* a3,
+               const int* b3, int* oa, int* ob, const u64* bk, const int* ks_a, const int* ks_b, int shape, cudaStream_t st);
+void tfhe_keygen_secret(const TfheContext& c, u64 seed, int* lwe_key, int* tlwe_key, cudaStream_t st);
+void tfhe_keygen_boot(const TfheContext& c, const int* lwe_key, const int* tlwe_key, u64 seed, u64* bk, int* ks_a, int* ks_b,
+                      cudaStream_t st);
+void tfhe_encrypt(const TfheContext& c, const int* lwe_key, const int* d_messages, u64 seed, int* out_a, int* out_b, int shape,
+                  cudaStream_t st);
+void tfhe_phase(const TfheContext& c, const int* lwe_key, const int* in_a, const int* in_b, int* d_phase, int n, int shape,
+                cudaStream_t st);
+void tfhe_ntt(const TfheContext& c, u64* data, int count, bool inverse, cudaStream_t st);
 
 } // namespace heon

@@ -344,6 +344,59 @@ size_t heon_compress_bound(size_t n);
 int heon_compress(const uint8_t* in, size_t n, uint8_t* out, size_t* out_len);
 int heon_decompress(const uint8_t* in, size_t n, uint8_t* out, size_t* out_len);
 
+/* ==== TFHE gate bootstrapping (BASELINE config 5) ==================================
+ * The reference's fixed parameter set (src/lib/host/tfhe/context.cu:23-56): LWE n = 512, ring N = 1024, k = 1,
+ * bootstrapping-key decomposition l = 2 / Bg = 2^10, key-switch base 4 x 8 digits, NTT prime
+ * 1152921504606877697.  Ciphertexts are batches of `shape` LWE samples: a = int32[shape][n], b = int32[shape]
+ * (Ciphertext<TFHE>::a_device_location_, b_device_location_).  Keys (Bootstrappingkey<TFHE>):
+ *   boot_key uint64[n][k+1][l][k+1][N], NTT domain (boot_key_device_location_),
+ *   ks_a int32[kN][8][3][n], ks_b int32[kN][8][3] (switch_key_device_location_a_/_b_).
+ * All pointers are DEVICE pointers unless named h_*. */
+typedef struct heon_tfhe_s* heon_tfhe_t;
+int heon_tfhe_create(int device, heon_tfhe_t* out); /* HEContextImpl<TFHE>::HEContextImpl */
+void heon_tfhe_destroy(heon_tfhe_t ctx);
+/* out7 = {n, N, k, l, bg_bit, ks_base_bit, ks_length} */
+int heon_tfhe_params(heon_tfhe_t ctx, int* out7);
+/* gate codes */
+#define HEON_TFHE_NAND 0
+#define HEON_TFHE_AND 1
+#define HEON_TFHE_NOR 2
+#define HEON_TFHE_OR 3
+#define HEON_TFHE_XNOR 4
+#define HEON_TFHE_XOR 5
+#define HEON_TFHE_ANDNY 6 /* AND with the first input negated (AND_N_pre_computation) */
+#define HEON_TFHE_NOT 7
+#define HEON_TFHE_MUX 8
+/* HELogicOperator<TFHE>::NAND / AND / NOR / OR / XNOR / XOR / NOT / MUX (src/include/heongpu/host/tfhe/
+ * operator.cuh:53-812): linear part, blind rotation + sample extraction, key switch.  MUX(in1, in2, control):
+ * a3, b3 = control.  NOT needs no keys. */
+int heon_tfhe_gate(heon_tfhe_t ctx, int gate, const int32_t* a1, const int32_t* b1, const int32_t* a2, const int32_t* b2,
+                   const int32_t* a3, const int32_t* b3, int32_t* out_a, int32_t* out_b, const uint64_t* boot_key,
+                   const int32_t* ks_a, const int32_t* ks_b, int shape, void* stream);
+/* the three steps of a gate, separately:
+ *  *_pre_computation / NOT_computation (tfhe/operator.cu:24-196; bootstrapping.cu:378-660) on samples of n words, */
+int heon_tfhe_gate_linear(heon_tfhe_t ctx, int gate, const int32_t* a1, const int32_t* b1, const int32_t* a2, const int32_t* b2,
+                          int32_t* out_a, int32_t* out_b, int n, int shape, void* stream);
+/*  HELogicOperator<TFHE>::bootstrapping (tfhe/operator.cu:198-266: tfhe_bootstrapping_kernel_unique_step1/2,
+ *  _regular_step1/2 x 511, tfhe_sample_extraction_kernel) as ONE launch: out_a int32[shape][kN], out_b int32[shape], */
+int heon_tfhe_bootstrap(heon_tfhe_t ctx, const int32_t* in_a, const int32_t* in_b, int32_t* out_a, int32_t* out_b,
+                        const uint64_t* boot_key, int shape, void* stream);
+/*  HELogicOperator<TFHE>::key_switching (tfhe/operator.cu:268-290; tfhe_key_switching_kernel). */
+int heon_tfhe_keyswitch(heon_tfhe_t ctx, const int32_t* in_a, const int32_t* in_b, int32_t* out_a, int32_t* out_b,
+                        const int32_t* ks_a, const int32_t* ks_b, int shape, void* stream);
+/* client side: HEKeyGenerator<TFHE>::generate_secret_key / generate_bootstrapping_key (tfhe/keygenerator.cu),
+ * HEEncryptor<TFHE>::encrypt_lwe_symmetric (d_messages: torus32 words, +-2^29 for true / false),
+ * HEDecryptor<TFHE>::decrypt_lwe (phase = b - <a, s>; the bit is phase > 0). */
+int heon_tfhe_keygen_secret(heon_tfhe_t ctx, uint64_t seed, int32_t* lwe_key, int32_t* tlwe_key, void* stream);
+int heon_tfhe_keygen_boot(heon_tfhe_t ctx, const int32_t* lwe_key, const int32_t* tlwe_key, uint64_t seed, uint64_t* boot_key,
+                          int32_t* ks_a, int32_t* ks_b, void* stream);
+int heon_tfhe_encrypt(heon_tfhe_t ctx, const int32_t* lwe_key, const int32_t* d_messages, uint64_t seed, int32_t* out_a,
+                      int32_t* out_b, int shape, void* stream);
+int heon_tfhe_phase(heon_tfhe_t ctx, const int32_t* lwe_key, const int32_t* in_a, const int32_t* in_b, int32_t* d_phase, int n,
+                    int shape, void* stream);
+/* SmallForwardNTT / SmallInverseNTT (src/lib/kernel/small_ntt.cu) of `count` polynomials of 1024 words, in place */
+int heon_tfhe_ntt(heon_tfhe_t ctx, uint64_t* data, int count, int inverse, void* stream);
+
 /* Per-kernel-class CUDA-event profiler (used by bench.py for the roofline
  * line): begin() arms it, end() synchronises the device and returns, per
  * class, the summed device time in ms and the launch count; the return value

@@ -303,3 +303,52 @@ class RefContext:
         out = np.zeros(max(n, 1), dtype=np.uint64)
         call(_p(out), n)
         return out[:n]
+
+
+# ---------------------------------------------------------------------------------------------
+# TFHE: the reference's small_ntt.cu + bootstrapping.cu kernels and the launch replay of
+# src/lib/host/tfhe/operator.cu (oracle/ref_tfhe_harness.cu)
+# ---------------------------------------------------------------------------------------------
+TFHE_SO = os.path.join(_HERE, "_ref", "libref_tfhe.so")
+
+
+def have_tfhe():
+    return os.path.exists(TFHE_SO)
+
+
+class RefTfhe:
+    def __init__(self):
+        L = C.CDLL(TFHE_SO)
+        L.reftfhe_create.restype = C.c_void_p
+        self.L = L
+        self._h = C.c_void_p(L.reftfhe_create())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.L.reftfhe_destroy(self._h)
+            self._h = None
+
+    @staticmethod
+    def _s():
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    @staticmethod
+    def _chk(rc):
+        if rc:
+            raise RuntimeError(f"reference kernel launch failed: {rc}")
+
+    def gate_linear(self, gate, a1, b1, a2, b2, oa, ob, n, shape):
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        self._chk(self.L.reftfhe_gate_linear(self._h, gate, p(a1), p(b1), p(a2), p(b2), p(oa), p(ob), n, shape, self._s()))
+
+    def bootstrap(self, in_a, in_b, out_a, out_b, bk, shape):
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._chk(self.L.reftfhe_bootstrap(self._h, p(in_a), p(in_b), p(out_a), p(out_b), p(bk), shape, self._s()))
+
+    def keyswitch(self, in_a, in_b, out_a, out_b, ks_a, ks_b, shape):
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._chk(self.L.reftfhe_keyswitch(self._h, p(in_a), p(in_b), p(out_a), p(out_b), p(ks_a), p(ks_b), shape, self._s()))
+
+    def ntt(self, data, inverse=False):
+        self._chk(self.L.reftfhe_ntt(self._h, C.c_void_p(data.data_ptr()), data.numel() // 1024, int(inverse), self._s()))
