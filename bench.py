@@ -44,8 +44,9 @@ WORKLOADS = {
     "n14_C2": "CKKS N=2^14 {50,40,40,40}/{48} L=4 K=1 (logq~218) mul+relin+rescale depth 0 (BASELINE config 2)",
     "M4_bfv_rot": "BFV N=2^15 default 128-bit modulus (14+1 primes, defaultmodulus.cpp:34-51) rotate_rows sweep over steps +-2^0..2^7 (BASELINE config 4)",
     "M1_bfv_latency": "BFV N=4096 {36,36}/{37} t=1032193 (test_bfv_multiplication.cpp:12-19), ONE ct x ct multiply + relinearize: latency (BASELINE config 1)",
+    "M5_tfhe_nand": "TFHE n=512 N=1024 k=1 l=2 Bg=2^10 (tfhe/context.cu:23-56) bootstrapped NAND gates on a batch of LWE samples (BASELINE config 5)",
 }
-DEFAULT_BATCH = {"C3_II": 16, "C3_I": 8, "n14_C2": 1024, "M4_bfv_rot": 512, "M1_bfv_latency": 1}
+DEFAULT_BATCH = {"C3_II": 16, "C3_I": 8, "n14_C2": 1024, "M4_bfv_rot": 512, "M1_bfv_latency": 1, "M5_tfhe_nand": 2368}
 # src/lib/util/defaultmodulus.cpp:34-51 (N = 32768, 128-bit security): the last prime is P
 BFV_32768_MODULUS = [0x2000000002b0001, 0x2000000003a0001, 0x2000000005b0001, 0x200000000640001, 0x400000000270001,
                      0x400000000350001, 0x400000000360001, 0x4000000004d0001, 0x400000000570001, 0x400000000660001,
@@ -523,6 +524,101 @@ def run_m1(args, local, reference):
     return dict(value=ops / (ms * 1e-3), ms=ms, launches=launches, latency_us=ms * 1e3 / ops, reps=reps, graphed=graphed)
 
 
+def run_tfhe(args, rank, world, local, reference):
+    """BASELINE config 5: bootstrapped NAND on `batch` LWE samples per GPU (real keys from this engine's key
+    generator in both arms).  A step is one gate over the whole batch; value = gates/s."""
+    from heongpu_b200 import tfhe as T
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1234 + rank)
+    shape = args.batch
+    if reference:
+        from oracle import ref as R
+        if not R.have_tfhe():
+            return None
+        rt = R.RefTfhe()
+    ctx = T.HEContext(local)
+    kg = T.HEKeyGenerator(ctx, seed=99)
+    sk = kg.generate_secret_key(T.Secretkey(ctx))
+    bk = kg.generate_bootstrapping_key(T.Bootstrappingkey(ctx), sk)
+    enc, dec, logic = T.HEEncryptor(ctx, sk), T.HEDecryptor(ctx, sk), T.HELogicOperator(ctx)
+    bits1 = torch.randint(0, 2, (shape,), generator=g, device="cuda").bool().cpu().numpy()
+    bits2 = torch.randint(0, 2, (shape,), generator=g, device="cuda").bool().cpu().numpy()
+    c1, c2 = enc.encrypt(bits1), enc.encrypt(bits2)
+    n, N = ctx.n_, ctx.N_
+    if reference:
+        ta, tb = torch.zeros(shape, n, dtype=torch.int32, device="cuda"), torch.zeros(shape, dtype=torch.int32, device="cuda")
+        ea, eb = torch.zeros(shape, N, dtype=torch.int32, device="cuda"), torch.zeros(shape, dtype=torch.int32, device="cuda")
+        oa, ob = torch.zeros(shape, n, dtype=torch.int32, device="cuda"), torch.zeros(shape, dtype=torch.int32, device="cuda")
+
+        def step():
+            rt.gate_linear(0, c1.a_device_location_, c1.b_device_location_, c2.a_device_location_, c2.b_device_location_, ta, tb,
+                           n, shape)
+            rt.bootstrap(ta, tb, ea, eb, bk.boot_key_device_location_, shape)
+            rt.keyswitch(ea, eb, oa, ob, bk.switch_key_device_location_a_, bk.switch_key_device_location_b_, shape)
+        result = lambda: T.Ciphertext(ctx, oa, ob)
+    else:
+        holder = {}
+
+        def step():
+            holder["out"] = logic.NAND(c1, c2, bk)
+        result = lambda: holder["out"]
+    for _ in range(args.warmup):
+        step()
+    ok = dec.decrypt(result()) == list(~(bits1 & bits2))
+    if not reference:
+        T.lib.heon_kernel_launches(1)
+    clocks = ClockSampler(local) if not reference else None
+    if clocks:
+        clocks.start()
+    ms = timed(step, args.steps, world)
+    cl = clocks.stop() if clocks else None
+    launches = None if reference else int(T.lib.heon_kernel_launches(0))
+    res = dict(value=shape * world * args.steps / (ms * 1e-3), ms=ms, launches=launches, clocks=cl, correct=bool(ok))
+    if reference:
+        return res
+    # e2e: host ciphertexts in, host ciphertexts out, copies inside the timed region
+    ha1, hb1 = c1.a_device_location_.cpu().pin_memory(), c1.b_device_location_.cpu().pin_memory()
+    ha2, hb2 = c2.a_device_location_.cpu().pin_memory(), c2.b_device_location_.cpu().pin_memory()
+    hoa, hob = torch.empty(shape, n, dtype=torch.int32).pin_memory(), torch.empty(shape, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        x1 = T.Ciphertext(ctx, ha1.cuda(non_blocking=True), hb1.cuda(non_blocking=True))
+        x2 = T.Ciphertext(ctx, ha2.cuda(non_blocking=True), hb2.cuda(non_blocking=True))
+        o = logic.NAND(x1, x2, bk)
+        hoa.copy_(o.a_device_location_, non_blocking=True)
+        hob.copy_(o.b_device_location_, non_blocking=True)
+    e2e_step()
+    ems = timed(e2e_step, args.steps, world)
+    res["e2e"] = shape * world * args.steps / (ems * 1e-3)
+    res["h2d"] = 2 * (shape * n * 4 + shape * 4)
+    res["d2h"] = shape * n * 4 + shape * 4
+    # kernel classes
+    T.lib.heon_profile_begin()
+    step()
+    msv, cnt = (C.c_double * 16)(), (C.c_longlong * 16)()
+    ncls = T.lib.heon_profile_end(msv, cnt, 16)
+    tot = sum(msv[i] for i in range(ncls))
+    res["kernels"] = [{"kernel": T.lib.heon_profile_class_name(i).decode(), "launches_per_step": int(cnt[i]),
+                       "ms_per_step": msv[i], "share": msv[i] / tot if tot else None} for i in range(ncls) if cnt[i]]
+    # the blind rotation is bound by the integer multiplier (60-bit Shoup butterflies, 31 SM sub-partition cycles
+    # per warp-butterfly, tools/microbench4.cu): report its achieved fraction of that bound next to the L2 stream
+    br = next((k for k in res["kernels"] if k["kernel"] == "tfhe_blind_rotate"), None)
+    if br:
+        steps_n = ctx.n_
+        warp_bfly = 6 * 5120 / 32 * steps_n  # 4 forward + 2 inverse 1024-point transforms per step
+        warp_mac = 8 * 1024 / 32 * steps_n
+        cyc = (warp_bfly * 31.0 + warp_mac * 33.5) * shape
+        sm_mhz = (cl or {}).get("sm_mhz") or 1965.0
+        bound_ms = cyc / (148 * 4) / (sm_mhz * 1e3)
+        key_bytes = steps_n * 8 * 1024 * 8 * shape
+        res["roof"] = {"bound": "int-multiplier", "kernel": "tfhe_blind_rotate", "achieved": bound_ms / br["ms_per_step"],
+                       "peak": 1.0, "unit": "fraction of the integer-multiplier bound", "frac": bound_ms / br["ms_per_step"],
+                       "traffic": None, "l2_key_stream_gbs": key_bytes / (br["ms_per_step"] * 1e-3) / 1e9,
+                       "note": "per gate and sample: 512 steps x (6 transforms of 1024 points + 8192 products) on a 60-bit prime "
+                               "(no FP64 form); the bootstrapping key (33.5 MB) streams from L2, nothing else leaves the SM"}
+    return res
+
+
 def cpu_baseline(inp, workload):
     """The CPU oracle (port of the reference algorithm) on a bounded sample: one
     multiply+relinearize of the same workload with all host threads (OpenMP)."""
@@ -665,6 +761,37 @@ def main():
             # kernels per op are the same 13 either way; replayed from a graph they are not counted by the library
             line["gpu_launches"] = r["launches"] if not r["graphed"] else 13 * r["reps"] * args.steps
             line["cuda_graph"] = r["graphed"]
+        print(json.dumps(line))
+        return
+
+    if args.workload == "M5_tfhe_nand":
+        base["metric"] = "TFHE bootstrapped NAND gates/sec"
+        base["unit"] = "gates/s"
+        base["dtype"] = "int32 torus / u64 NTT"
+        config["l2_policy"] = "the bootstrapping key (33.5 MB) and the key-switch key (50 MB) are meant to stay in L2; inputs are re-read every step"
+        config["parallelism"] = f"LWE samples sharded over {world} GPU(s), keys replicated, no collective"
+        if args.impl == "reference":
+            r = run_tfhe(args, 0, 1, local, True)
+            if r is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_tfhe.so not built"}))
+                return
+            line = dict(base)
+            line.update({"impl": "reference", "value": r["value"], "n_gpus": 1, "ms_per_step": r["ms"] / args.steps,
+                         "decrypts_correctly": r["correct"],
+                         "cpu_baseline": {"value": r["value"], "unit": "gates/s", "cores": 0, "kind": "reference",
+                                          "sample": "the reference's own CUDA kernels (sm_100a build; 1026 launches per gate batch) on one B200"},
+                         "e2e": {"value": r["value"], "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+            print(json.dumps(line))
+            return
+        r = run_tfhe(args, rank, world, local, False)
+        if rank != 0:
+            return
+        line = dict(base)
+        line.update({"value": r["value"], "ms_per_step": r["ms"] / args.steps, "gpu_launches": r["launches"], "clocks": r["clocks"],
+                     "decrypts_correctly": r["correct"], "roofline": r.get("roof"), "kernels": r["kernels"],
+                     "e2e": {"value": r["e2e"], "unit": "gates/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+                     "cpu_baseline": {"value": None, "unit": "gates/s", "cores": 0, "kind": "port",
+                                      "sample": "not timed for this workload (see the default workload's line)"}})
         print(json.dumps(line))
         return
 

@@ -66,10 +66,12 @@ __device__ __forceinline__ int t_mod_switch(int x)
     return (int) (r >> (63 - TLOGN));
 }
 
-// shared-buffer index of coefficient c: the 16-byte chunk inside a 128-byte line is XORed with bits 6..8 of c,
-// which makes the three access patterns of the transform (c = j + 64k, c = 64B + r + 4k, c = 16j + k) and the
-// linear pattern of the inner product free of bank conflicts
-__device__ __forceinline__ int t_sw(int c) { return c ^ (((c >> 6) & 7) << 1); }
+// shared-buffer index of coefficient c: the 16-byte chunk inside a 128-byte line is XORed with a 3-bit function of
+// the line index that separates (i) the eight consecutive lines a quarter-warp touches with 128-bit accesses
+// (c = 16j + 2m) and (ii) the four lines 64 words apart a half-warp touches in the middle round (c = 64B + r + 4k);
+// the linear patterns (c = j + 64k, c = tid + 128m) stay inside one line per half-warp.  Measured before this
+// function had the second term: 16 wavefronts per 128-bit access instead of 4.
+__device__ __forceinline__ int t_sw(int c) { return c ^ ((((c >> 4) ^ (c >> 6)) & 7) << 1); }
 
 // coefficient c of X^a * acc (a in [0, 2N)), acc a negacyclic polynomial of int32
 __device__ __forceinline__ int t_rot(const int* acc, int c, int a)
@@ -192,27 +194,31 @@ struct TfheDev {
     int n;
 };
 
-constexpr int kBrSmem = 2 * TN * 4 + 4 * TN * 8 + 2 * TN * 8;
+constexpr int kBrThreads = 128;
+constexpr int kBrSmem = 2 * TN * 4 + 4 * TN * 8;
 
-__global__ void __launch_bounds__(256, 2)
+// 128 threads = two groups of 64.  Per step, group g transforms the two digit polynomials of accumulator
+// component g (one after the other: both come from the same rotated difference), all threads form the inner
+// products, and group g runs the inverse transform of output component g: six transforms of equal cost on two
+// groups in three rounds, nobody idles.  The inner-product sums overwrite the first two digit buffers (every
+// thread owns its coefficient columns in that phase), so a CTA needs 40 KiB and five fit on an SM.
+__global__ void __launch_bounds__(kBrThreads, 4)
     k_tfhe_blind_rotate(const int* __restrict__ in_a, const int* __restrict__ in_b, int* __restrict__ out_a,
                         int* __restrict__ out_b, const u64* __restrict__ bk, const TwPair* __restrict__ fwd,
                         const TwPair* __restrict__ inv, const TfheDev P)
 {
     extern __shared__ __align__(16) unsigned char t_smem[];
     int* acc = reinterpret_cast<int*>(t_smem); // [2][1024]
-    u64* work = reinterpret_cast<u64*>(t_smem + 2 * TN * 4); // [4][1024] transformed digits
-    u64* outb = work + 4 * TN; // [2][1024] inner-product sums
+    u64* work = reinterpret_cast<u64*>(t_smem + 2 * TN * 4); // [4][1024] transformed digits; [0..1] reused for the sums
     const int tid = threadIdx.x;
     const long long s = blockIdx.x;
     const BflyConst bc = make_bc(P.pc);
-    const int q = tid >> 6, j = tid & 63;
-    const int y = q >> 1, z = q & 1;
+    const int g = tid >> 6, j = tid & 63;
 
     // accumulator = (0, X^{-b~} * testvector), testvector = mu at every coefficient (bootstrapping.cu:912-937)
     {
         const int bN = 2 * TN - t_mod_switch(in_b[s]);
-        for (int c = tid; c < TN; c += 256)
+        for (int c = tid; c < TN; c += kBrThreads)
         {
             int t;
             if (bN < TN)
@@ -224,7 +230,6 @@ __global__ void __launch_bounds__(256, 2)
         }
     }
     __syncthreads();
-    const int shift = 32 - P.bk_bit * (z + 1);
 #pragma unroll 1
     for (int i = 0; i < P.n; ++i)
     {
@@ -232,36 +237,42 @@ __global__ void __launch_bounds__(256, 2)
         if (a == 0)
             continue; // (X^0 - 1) * acc = 0: every digit is 0
         u64 v[16];
-        // digit z of (X^a - 1) * acc_y, as a residue
         {
-            const int* ay = acc + y * TN;
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
+            // digit z of (X^a - 1) * acc_g at the coefficients j + 64k, as residues
+            const int* ay = acc + g * TN;
+#pragma unroll 1
+            for (int z = 0; z < 2; ++z)
             {
-                const int c = j + 64 * k;
-                const int diff = (int) ((unsigned) t_rot(ay, c, a) - (unsigned) ay[c]);
-                const int dg = (int) ((((unsigned) diff + (unsigned) P.bk_offset) >> shift) & (unsigned) P.bk_mask) - P.bk_half;
-                v[k] = dg < 0 ? P.pc.p + (u64) (long long) dg : (u64) dg;
-            }
-        }
-        t_ntt_fwd(v, work + q * TN, j, 1 + q, fwd, bc);
+                const int shift = 32 - P.bk_bit * (z + 1);
 #pragma unroll
-        for (int m = 0; m < 8; ++m)
-        {
-            ulonglong2 t;
-            t.x = csub(v[2 * m], bc.p4);
-            t.y = csub(v[2 * m + 1], bc.p4);
-            *reinterpret_cast<ulonglong2*>(work + q * TN + t_sw(16 * j + 2 * m)) = t;
+                for (int k = 0; k < 16; ++k)
+                {
+                    const int c = j + 64 * k;
+                    const unsigned diff = (unsigned) t_rot(ay, c, a) - (unsigned) ay[c];
+                    const int dg = (int) (((diff + (unsigned) P.bk_offset) >> shift) & (unsigned) P.bk_mask) - P.bk_half;
+                    v[k] = dg < 0 ? P.pc.p + (u64) (long long) dg : (u64) dg;
+                }
+                u64* wq = work + (g * 2 + z) * TN;
+                t_ntt_fwd(v, wq, j, 1 + g, fwd, bc);
+#pragma unroll
+                for (int m = 0; m < 8; ++m)
+                {
+                    ulonglong2 t;
+                    t.x = csub(v[2 * m], bc.p4);
+                    t.y = csub(v[2 * m + 1], bc.p4);
+                    *reinterpret_cast<ulonglong2*>(wq + t_sw(16 * j + 2 * m)) = t;
+                }
+            }
         }
         __syncthreads();
         // out_jj[c] = sum over (y, z) of digit word * bk[i][y][z][jj][c]: canonical, as the reference's sum of
         // canonical products (bootstrapping.cu:1127-1139, 1263-1283)
         {
             const u64* bki = bk + (size_t) i * 8 * TN;
-#pragma unroll
-            for (int m = 0; m < 4; ++m)
+#pragma unroll 1
+            for (int m = 0; m < TN / kBrThreads; ++m)
             {
-                const int c = tid + 256 * m, cs = t_sw(c);
+                const int c = tid + kBrThreads * m, cs = t_sw(c);
                 u64 l0 = 0, h0 = 0, l1 = 0, h1 = 0;
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq)
@@ -270,24 +281,23 @@ __global__ void __launch_bounds__(256, 2)
                     mac128(l0, h0, x, __ldg(bki + (qq * 2 + 0) * TN + c));
                     mac128(l1, h1, x, __ldg(bki + (qq * 2 + 1) * TN + c));
                 }
-                outb[cs] = reduce_u128(l0, h0, P.pc);
-                outb[TN + cs] = reduce_u128(l1, h1, P.pc);
+                work[cs] = reduce_u128(l0, h0, P.pc); // column cs of every buffer belongs to this thread here
+                work[TN + cs] = reduce_u128(l1, h1, P.pc);
             }
         }
         __syncthreads();
-        if (tid < 128)
         {
-            const int jj = tid >> 6;
+            u64* ob = work + g * TN;
 #pragma unroll
             for (int m = 0; m < 8; ++m)
             {
-                const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(outb + jj * TN + t_sw(16 * j + 2 * m));
+                const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(ob + t_sw(16 * j + 2 * m));
                 v[2 * m] = t.x;
                 v[2 * m + 1] = t.y;
             }
-            t_ntt_inv(v, outb + jj * TN, j, 5 + jj, inv, P.ninv, P.wninv, bc);
+            t_ntt_inv(v, ob, j, 1 + g, inv, P.ninv, P.wninv, bc);
             const u64 thr = P.pc.p >> 1;
-            int* aj = acc + jj * TN;
+            int* aj = acc + g * TN;
 #pragma unroll
             for (int k = 0; k < 16; ++k)
             {
@@ -299,7 +309,7 @@ __global__ void __launch_bounds__(256, 2)
         __syncthreads();
     }
     // sample extraction at index 0 (bootstrapping.cu:1314-1349)
-    for (int c = tid; c < TN; c += 256)
+    for (int c = tid; c < TN; c += kBrThreads)
         out_a[s * TN + c] = (c < 1) ? acc[c] : -acc[TN - c];
     if (tid == 0)
         out_b[s] = acc[TN];
@@ -680,7 +690,7 @@ void tfhe_bootstrap(const TfheContext& c, const int* in_a, const int* in_b, int*
     if (shape < 1)
         throw std::invalid_argument("empty ciphertext");
     LaunchScope scope(KC_TFHE_BLIND_ROTATE, st);
-    k_tfhe_blind_rotate<<<shape, 256, kBrSmem, st>>>(in_a, in_b, out_a, out_b, bk, c.d_fwd, c.d_inv, c.dev);
+    k_tfhe_blind_rotate<<<shape, kBrThreads, kBrSmem, st>>>(in_a, in_b, out_a, out_b, bk, c.d_fwd, c.d_inv, c.dev);
     t_check_launch();
 }
 

@@ -25,6 +25,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <iosfwd>
 #include <iostream>
@@ -1866,3 +1867,4 @@ template <> class HEArithmeticOperator<Scheme::BFV> : public HEOperator<Scheme::
 
 #include "heongpu_client.hpp"
 #include "heongpu_serial.hpp"
+#include "heongpu_tfhe.hpp"

@@ -1484,3 +1484,233 @@ void oracle_bfv_plain(const obfv* c, const u64* ct, const u64* pt, u64* out, int
         }
     free(tp);
 }
+
+/* =======================================================================================================
+ * TFHE gate bootstrapping.  Restates, loop for loop, the reference's kernels:
+ *   tables            src/lib/host/tfhe/context.cu:23-104
+ *   1024-point NTT    src/lib/kernel/small_ntt.cu:10-126 (CooleyTukeyUnit / GentlemanSandeUnit of GPU-NTT)
+ *   gate linear part  src/lib/kernel/bootstrapping.cu:378-660
+ *   blind rotation    src/lib/kernel/bootstrapping.cu:662-674 (modulus switch), 875-1312 (steps), 1314-1349
+ *   key switch        src/lib/kernel/bootstrapping.cu:1351-1437
+ * Pinned by tests/golden/tfhe_golden.json (outputs of the reference kernels captured on a B200 by
+ * tests/golden/make_tfhe_golden.py) and live against oracle/_ref/libref_tfhe.so in the -m gpu suite.
+ * ===================================================================================================== */
+#define TFHE_N 1024
+#define TFHE_LOGN 10
+static const u64 TFHE_P = 1152921504606877697ULL, TFHE_PSI = 1689264667710614ULL;
+
+static u64 t_mulmod(u64 a, u64 b) { return (u64) (((u128) a * b) % TFHE_P); }
+static u64 t_powmod(u64 b, u64 e)
+{
+    u64 r = 1;
+    while (e)
+    {
+        if (e & 1)
+            r = t_mulmod(r, b);
+        b = t_mulmod(b, b);
+        e >>= 1;
+    }
+    return r;
+}
+static int t_bitrev(int x, int bits)
+{
+    int r = 0;
+    for (int i = 0; i < bits; i++)
+        r |= ((x >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+/* compute_ntt_table (tfhe/context.cu:80-104): table[j] = root^bitreverse(j) */
+void oracle_tfhe_table(u64* table, int inverse)
+{
+    u64 root = inverse ? t_powmod(TFHE_PSI, TFHE_P - 2) : TFHE_PSI;
+    static u64 pw[TFHE_N];
+    pw[0] = 1;
+    for (int j = 1; j < TFHE_N; j++)
+        pw[j] = t_mulmod(pw[j - 1], root);
+    for (int j = 0; j < TFHE_N; j++)
+        table[j] = pw[t_bitrev(j, TFHE_LOGN)];
+}
+/* SmallForwardNTT / SmallInverseNTT (small_ntt.cu): thread idx handles the pair at ((idx >> t_) << t_) + idx */
+void oracle_tfhe_ntt(u64* a, const u64* table, int inverse)
+{
+    if (!inverse)
+    {
+        int t_ = 9, m = 1;
+        for (int lp = 0; lp < 10; lp++)
+        {
+            int t = 1 << t_;
+            for (int idx = 0; idx < 512; idx++)
+            {
+                int addr = ((idx >> t_) << t_) + idx;
+                u64 w = table[m + (idx >> t_)];
+                u64 u = a[addr], v = t_mulmod(a[addr + t], w); /* CooleyTukeyUnit */
+                a[addr] = (u + v) % TFHE_P;
+                a[addr + t] = (u + TFHE_P - v) % TFHE_P;
+            }
+            t_ -= 1;
+            m <<= 1;
+        }
+    }
+    else
+    {
+        int t_ = 0, m = 512;
+        for (int lp = 0; lp < 10; lp++)
+        {
+            int t = 1 << t_;
+            for (int idx = 0; idx < 512; idx++)
+            {
+                int addr = ((idx >> t_) << t_) + idx;
+                u64 w = table[m + (idx >> t_)];
+                u64 u = a[addr], v = a[addr + t]; /* GentlemanSandeUnit */
+                a[addr] = (u + v) % TFHE_P;
+                a[addr + t] = t_mulmod((u + TFHE_P - v) % TFHE_P, w);
+            }
+            t_ += 1;
+            m >>= 1;
+        }
+        u64 ninv = t_powmod(TFHE_N, TFHE_P - 2);
+        for (int i = 0; i < TFHE_N; i++)
+            a[i] = t_mulmod(a[i], ninv);
+    }
+}
+static int32_t t_encode(uint32_t mu, uint32_t m_size) /* encode_to_torus32 (tfhe/operator.cu:316-322) */
+{
+    uint64_t interval = ((1ULL << 63) / m_size) * 2;
+    return (int32_t) ((mu * interval) >> 32);
+}
+/* *_pre_computation / NOT_computation; gate codes of include/heon_b200.h */
+int oracle_tfhe_gate_linear(int gate, const int32_t* a1, const int32_t* b1, const int32_t* a2, const int32_t* b2, int32_t* oa,
+                            int32_t* ob, int n, int shape)
+{
+    int32_t e8 = t_encode(1, 8), e4 = t_encode(1, 4);
+    int32_t enc;
+    int s1, s2;
+    switch (gate)
+    {
+    case 0: enc = e8, s1 = -1, s2 = -1; break;
+    case 1: enc = -e8, s1 = 1, s2 = 1; break;
+    case 2: enc = -e8, s1 = -1, s2 = -1; break;
+    case 3: enc = e8, s1 = 1, s2 = 1; break;
+    case 4: enc = -e4, s1 = -2, s2 = -2; break;
+    case 5: enc = e4, s1 = 2, s2 = 2; break;
+    case 6: enc = -e8, s1 = -1, s2 = 1; break;
+    case 7: enc = 0, s1 = -1, s2 = 0; break;
+    default: return -1;
+    }
+    for (long long i = 0; i < (long long) shape * n; i++)
+        oa[i] = (int32_t) ((uint32_t) s1 * (uint32_t) a1[i] + (gate == 7 ? 0u : (uint32_t) s2 * (uint32_t) a2[i]));
+    for (int i = 0; i < shape; i++)
+        ob[i] = (int32_t) ((uint32_t) enc + (uint32_t) s1 * (uint32_t) b1[i] + (gate == 7 ? 0u : (uint32_t) s2 * (uint32_t) b2[i]));
+    return 0;
+}
+static int32_t t_mod_switch(int32_t x) /* torus_modulus_switch_log, N_power = 10 */
+{
+    uint64_t range_log = 63 - TFHE_LOGN, half_range = 1ULL << (range_log - 1);
+    uint64_t r = (((uint64_t) (uint32_t) x) << 32) + half_range;
+    return (int32_t) (r >> range_log);
+}
+/* X^a * acc at coefficient c (the two branches of bootstrapping.cu:952-988) */
+static int32_t t_rot(const int32_t* acc, int c, int a)
+{
+    if (a < TFHE_N)
+        return (c < a) ? (int32_t) (0u - (uint32_t) acc[TFHE_N - a + c]) : acc[c - a];
+    int am = a - TFHE_N;
+    return (c < am) ? acc[TFHE_N - am + c] : (int32_t) (0u - (uint32_t) acc[c - am]);
+}
+/* HELogicOperator<TFHE>::bootstrapping (tfhe/operator.cu:198-266): n steps + sample extraction.
+ * bk: [n][k+1][l][k+1][N] NTT-domain words; out_a [shape][N], out_b [shape]. */
+void oracle_tfhe_bootstrap(const int32_t* in_a, const int32_t* in_b, int32_t* out_a, int32_t* out_b, const u64* bk, int n,
+                           int shape)
+{
+    static u64 fwd[TFHE_N], inv[TFHE_N];
+    oracle_tfhe_table(fwd, 0);
+    oracle_tfhe_table(inv, 1);
+    const int l = 2, bg_bit = 10, half = 512, mask = 1023;
+    const int32_t mu = t_encode(1, 8);
+    int64_t sum = 0;
+    for (int i = 1; i <= l; i++)
+        sum += ((int64_t) 1) << (32 - i * bg_bit);
+    const int32_t offset = (int32_t) (sum * half);
+    #pragma omp parallel for schedule(dynamic)
+    for (int s = 0; s < shape; s++)
+    {
+        int32_t acc[2][TFHE_N];
+        u64 dig[4][TFHE_N], out[TFHE_N];
+        int bN = 2 * TFHE_N - t_mod_switch(in_b[s]);
+        for (int c = 0; c < TFHE_N; c++)
+        {
+            acc[0][c] = 0;
+            if (bN < TFHE_N)
+                acc[1][c] = (c < bN) ? -mu : mu;
+            else
+                acc[1][c] = (c < bN - TFHE_N) ? mu : -mu;
+        }
+        for (int i = 0; i < n; i++)
+        {
+            int a = t_mod_switch(in_a[(long long) s * n + i]);
+            for (int y = 0; y < 2; y++)
+                for (int z = 0; z < l; z++)
+                {
+                    int shift = 32 - bg_bit * (z + 1);
+                    u64* d = dig[y * 2 + z];
+                    for (int c = 0; c < TFHE_N; c++)
+                    {
+                        uint32_t diff = (uint32_t) t_rot(acc[y], c, a) - (uint32_t) acc[y][c];
+                        int32_t dg = (int32_t) (((diff + (uint32_t) offset) >> shift) & (uint32_t) mask) - half;
+                        d[c] = dg < 0 ? TFHE_P + (u64) (int64_t) dg : (u64) dg;
+                    }
+                    oracle_tfhe_ntt(d, fwd, 0);
+                }
+            for (int jj = 0; jj < 2; jj++)
+            {
+                for (int c = 0; c < TFHE_N; c++)
+                {
+                    u64 accm = 0;
+                    for (int q = 0; q < 4; q++)
+                        accm = (accm + t_mulmod(dig[q][c], bk[((((size_t) i * 4 + q) * 2) + jj) * TFHE_N + c])) % TFHE_P;
+                    out[c] = accm;
+                }
+                oracle_tfhe_ntt(out, inv, 1);
+                for (int c = 0; c < TFHE_N; c++)
+                {
+                    int32_t add = (out[c] >= (TFHE_P >> 1)) ? (int32_t) (int64_t) (out[c] - TFHE_P) : (int32_t) (int64_t) out[c];
+                    acc[jj][c] = (int32_t) ((uint32_t) acc[jj][c] + (uint32_t) add);
+                }
+            }
+        }
+        for (int c = 0; c < TFHE_N; c++)
+            out_a[(long long) s * TFHE_N + c] = (c < 1) ? acc[0][c] : (int32_t) (0u - (uint32_t) acc[0][TFHE_N - c]);
+        out_b[s] = acc[1][0];
+    }
+}
+/* tfhe_key_switching_kernel (bootstrapping.cu:1351-1437) */
+void oracle_tfhe_keyswitch(const int32_t* in_a, const int32_t* in_b, int32_t* out_a, int32_t* out_b, const int32_t* ks_a,
+                           const int32_t* ks_b, int base_bit, int length, int n, int Nk, int shape)
+{
+    const int mask = (1 << base_bit) - 1;
+    const uint32_t prec = 1u << (32 - (1 + base_bit * length));
+    #pragma omp parallel for
+    for (int s = 0; s < shape; s++)
+    {
+        uint32_t accb = (uint32_t) in_b[s];
+        uint32_t* acc = (uint32_t*) calloc(n, sizeof(uint32_t));
+        for (int i = 0; i < Nk; i++)
+        {
+            uint32_t av = (uint32_t) in_a[(long long) s * Nk + i] + prec;
+            for (int i2 = 0; i2 < length; i2++)
+            {
+                int dg = (int) ((av >> (32 - (i2 + 1) * base_bit)) & (uint32_t) mask);
+                if (dg == 0)
+                    continue;
+                size_t row = ((size_t) i * length + i2) * mask + (dg - 1);
+                for (int t = 0; t < n; t++)
+                    acc[t] -= (uint32_t) ks_a[row * n + t];
+                accb -= (uint32_t) ks_b[row];
+            }
+        }
+        for (int t = 0; t < n; t++)
+            out_a[(long long) s * n + t] = (int32_t) acc[t];
+        out_b[s] = (int32_t) accb;
+        free(acc);
+    }
+}

@@ -268,3 +268,58 @@ class BfvOracle:
         out = np.zeros_like(ct)
         lib().oracle_bfv_apply_galois(self._h, _p(ct), _p(out), _p(np.ascontiguousarray(key)), int(galois_elt))
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# TFHE gate bootstrapping (restatement of small_ntt.cu + bootstrapping.cu; heon_oracle.c)
+# ---------------------------------------------------------------------------------------------
+class TfheOracle:
+    P = 1152921504606877697
+    n, N, k, l, bg_bit, ks_base_bit, ks_length = 512, 1024, 1, 2, 10, 2, 8
+
+    def __init__(self):
+        self.L = lib()
+        self.fwd, self.inv = np.zeros(1024, dtype=np.uint64), np.zeros(1024, dtype=np.uint64)
+        self.L.oracle_tfhe_table(_p(self.fwd), 0)
+        self.L.oracle_tfhe_table(_p(self.inv), 1)
+
+    def ntt(self, polys, inverse=False):
+        out = np.ascontiguousarray(polys, dtype=np.uint64).copy()
+        flat = out.reshape(-1, 1024)
+        for row in flat:
+            self.L.oracle_tfhe_ntt(_p(row), _p(self.inv if inverse else self.fwd), int(inverse))
+        return out
+
+    def gate_linear(self, gate, a1, b1, a2=None, b2=None):
+        a1, b1 = np.ascontiguousarray(a1, dtype=np.int32), np.ascontiguousarray(b1, dtype=np.int32)
+        a2 = np.ascontiguousarray(a2 if a2 is not None else a1, dtype=np.int32)
+        b2 = np.ascontiguousarray(b2 if b2 is not None else b1, dtype=np.int32)
+        oa, ob = np.zeros_like(a1), np.zeros_like(b1)
+        rc = self.L.oracle_tfhe_gate_linear(gate, _ip(a1), _ip(b1), _ip(a2), _ip(b2), _ip(oa), _ip(ob), a1.shape[1], a1.shape[0])
+        assert rc == 0
+        return oa, ob
+
+    def bootstrap(self, a, b, bk):
+        a, b = np.ascontiguousarray(a, dtype=np.int32), np.ascontiguousarray(b, dtype=np.int32)
+        bk = np.ascontiguousarray(bk, dtype=np.uint64)
+        oa, ob = np.zeros((a.shape[0], 1024), dtype=np.int32), np.zeros(a.shape[0], dtype=np.int32)
+        self.L.oracle_tfhe_bootstrap(_ip(a), _ip(b), _ip(oa), _ip(ob), _p(bk.reshape(-1)), a.shape[1], a.shape[0])
+        return oa, ob
+
+    def keyswitch(self, a, b, ks_a, ks_b):
+        a, b = np.ascontiguousarray(a, dtype=np.int32), np.ascontiguousarray(b, dtype=np.int32)
+        ks_a, ks_b = np.ascontiguousarray(ks_a, dtype=np.int32), np.ascontiguousarray(ks_b, dtype=np.int32)
+        oa, ob = np.zeros((a.shape[0], self.n), dtype=np.int32), np.zeros(a.shape[0], dtype=np.int32)
+        self.L.oracle_tfhe_keyswitch(_ip(a), _ip(b), _ip(oa), _ip(ob), _ip(ks_a.reshape(-1)), _ip(ks_b.reshape(-1)),
+                                     self.ks_base_bit, self.ks_length, self.n, self.k * self.N, a.shape[0])
+        return oa, ob
+
+    # plain host keys / encryption for CPU-side checks (not the product's generator)
+    def keygen(self, rng, boot_steps=None):
+        n = boot_steps or self.n
+        lwe = rng.integers(0, 2, n).astype(np.int32)
+        tlwe = rng.integers(0, 2, self.N).astype(np.int32)
+        return lwe, tlwe
+
+    def phase(self, a, b, lwe):
+        return (b.astype(np.int64) - (a.astype(np.int64) * lwe.astype(np.int64)).sum(axis=1)).astype(np.int64) & 0xFFFFFFFF

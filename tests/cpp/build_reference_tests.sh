@@ -9,7 +9,7 @@ REF=${REF:-/root/reference}
 ROOT=$(cd ../.. && pwd)
 mkdir -p _bin
 [ -d "$REF/test" ] || { echo "no reference tree: skipping"; exit 0; }
-TESTS=${TESTS:-"test_ckks_encoding test_ckks_encryption test_ckks_addition test_ckks_multiplication test_ckks_relinearization test_ckks_rotation_method_1 test_ckks_rotation_method_2 test_bfv_encoding test_bfv_encryption test_bfv_addition test_bfv_multiplication test_bfv_relinearization test_bfv_rotation_method_1 test_bfv_rotation_method_2"}
+TESTS=${TESTS:-"test_ckks_encoding test_ckks_encryption test_ckks_addition test_ckks_multiplication test_ckks_relinearization test_ckks_rotation_method_1 test_ckks_rotation_method_2 test_bfv_encoding test_bfv_encryption test_bfv_addition test_bfv_multiplication test_bfv_relinearization test_bfv_rotation_method_1 test_bfv_rotation_method_2 test_tfhe_gate_boot"}
 pids=()
 for t in $TESTS; do
   ( g++ -std=c++17 -O1 -w -I shim -I "$ROOT/heongpu_b200/include" -I /usr/local/cuda/include \
@@ -19,7 +19,7 @@ for t in $TESTS; do
   pids+=($!)
 done
 # the reference's benchmarks and basic examples (multi-stream OpenMP usage included), same rule: unmodified
-EXTRA=${EXTRA:-"benchmark/benchmark_ckks benchmark/benchmark_bfv example/basic/1_basic_bfv example/basic/2_basic_ckks example/basic/4_switchkey_methods_bfv example/basic/5_switchkey_methods_ckks example/basic/8_default_stream_usage example/basic/9_multi_stream_usage_way1 example/basic/10_multi_stream_usage_way2"}
+EXTRA=${EXTRA:-"benchmark/benchmark_ckks benchmark/benchmark_bfv example/basic/1_basic_bfv example/basic/2_basic_ckks example/basic/4_switchkey_methods_bfv example/basic/5_switchkey_methods_ckks example/basic/8_default_stream_usage example/basic/9_multi_stream_usage_way1 example/basic/10_multi_stream_usage_way2 example/basic/15_basic_tfhe"}
 for e in $EXTRA; do
   b=$(basename $e)
   ( g++ -std=c++17 -O1 -w -fopenmp -I shim -I "$ROOT/heongpu_b200/include" -I /usr/local/cuda/include \

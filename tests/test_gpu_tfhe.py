@@ -149,3 +149,29 @@ def test_gate_errors():
         logic.AND(enc.encrypt([True, False]), enc.encrypt([True]), bk)
     with pytest.raises(t.HeonError):
         t.HEEncryptor(ctx, t.Secretkey(ctx))
+
+
+def test_blind_rotation_and_key_switch_match_cpu_oracle():
+    """The CUDA path against the CPU restatement (oracle/heon_oracle.c) on the seeded golden inputs."""
+    from oracle import oracle as O
+    from tests.tfhe_common import golden_inputs
+    t = _t()
+    ctx, _, _ = _keys()
+    op, orc = t.HELogicOperator(ctx), O.TfheOracle()
+    g = golden_inputs()
+    dev = lambda a: torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a).cuda()
+    key = t.Bootstrappingkey(ctx)
+    key.boot_key_device_location_ = dev(g["bk"])
+    key.switch_key_device_location_a_, key.switch_key_device_location_b_ = dev(g["ks_a"]), dev(g["ks_b"])
+    out = op.bootstrapping(t.Ciphertext(ctx, dev(g["boot_a"]), dev(g["boot_b"])), key)
+    oa, ob = orc.bootstrap(g["boot_a"], g["boot_b"], g["bk"])
+    assert np.array_equal(out.a_device_location_.cpu().numpy(), oa) and np.array_equal(out.b_device_location_.cpu().numpy(), ob)
+    ks = op.key_switching(t.Ciphertext(ctx, dev(g["ks_in_a"]), dev(g["ks_in_b"])), key)
+    ka, kb = orc.keyswitch(g["ks_in_a"], g["ks_in_b"], g["ks_a"], g["ks_b"])
+    assert np.array_equal(ks.a_device_location_.cpu().numpy(), ka) and np.array_equal(ks.b_device_location_.cpu().numpy(), kb)
+    for gate in range(8):
+        c1, c2 = t.Ciphertext(ctx, dev(g["a1"]), dev(g["b1"])), t.Ciphertext(ctx, dev(g["a2"]), dev(g["b2"]))
+        name = [k for k, v in t.GATES.items() if v == gate][0]
+        got = op.gate_linear(name, c1, None if gate == 7 else c2)
+        wa, wb = orc.gate_linear(gate, g["a1"], g["b1"], g["a2"], g["b2"])
+        assert np.array_equal(got.a_device_location_.cpu().numpy(), wa) and np.array_equal(got.b_device_location_.cpu().numpy(), wb)

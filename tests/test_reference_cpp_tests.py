@@ -1,4 +1,4 @@
-"""GPU: the reference's OWN test sources (/root/reference/test/test_{ckks,bfv}_*.cpp) compiled UNMODIFIED
+"""GPU: the reference's OWN test sources (/root/reference/test/test_{ckks,bfv,tfhe}_*.cpp) compiled UNMODIFIED
 against this repository's class layer (heongpu.hpp + libheon_b200.so) by tests/cpp/build_reference_tests.sh
 in the build container; the binaries travel to the GPU box.  Each must exit 0 (every EXPECT of the
 reference test holds): the north-star's literal acceptance test for the class layer -- context, key
@@ -13,7 +13,8 @@ BIN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "_bin")
 NAMES = ["test_ckks_encoding", "test_ckks_encryption", "test_ckks_addition", "test_ckks_multiplication",
          "test_ckks_relinearization", "test_ckks_rotation_method_1", "test_ckks_rotation_method_2",
          "test_bfv_encoding", "test_bfv_encryption", "test_bfv_addition", "test_bfv_multiplication",
-         "test_bfv_relinearization", "test_bfv_rotation_method_1", "test_bfv_rotation_method_2"]
+         "test_bfv_relinearization", "test_bfv_rotation_method_1", "test_bfv_rotation_method_2",
+         "test_tfhe_gate_boot"]
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -35,7 +36,8 @@ def test_reference_test_source_passes_against_this_class_layer(name):
 
 
 EXTRA = ["benchmark_ckks", "benchmark_bfv", "1_basic_bfv", "2_basic_ckks", "4_switchkey_methods_bfv",
-         "5_switchkey_methods_ckks", "8_default_stream_usage", "9_multi_stream_usage_way1", "10_multi_stream_usage_way2"]
+         "5_switchkey_methods_ckks", "8_default_stream_usage", "9_multi_stream_usage_way1", "10_multi_stream_usage_way2",
+         "15_basic_tfhe"]
 
 
 @pytest.mark.parametrize("name", EXTRA)

@@ -1,6 +1,5 @@
 #!/bin/bash
-# source-level ncu capture of the pipelined TMA column pass (main launch of the key switch)
-export HEON_COL_TMA=1 HEON_COL_TMA_TILES=8
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"ntt_col_pass_tma_pipe<heon::MapDigitSkip" -s 1 -c 1 -o gpurun_out/r2_colpipe -f python bench.py --workload C3_II --steps 2 --warmup 3 --batch 4 --no-cpu-baseline > gpurun_out/ncu_colpipe.log 2>&1
-tail -2 gpurun_out/ncu_colpipe.log | cut -c1-300
-ls -la gpurun_out/*.ncu-rep
+# source-level ncu capture of the TFHE blind rotation (one full wave of CTAs)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_tfhe_blind_rotate" -s 1 -c 1 -o gpurun_out/r2_tfhe_br -f python bench.py --workload M5_tfhe_nand --batch 592 --steps 1 --warmup 3 > gpurun_out/ncu_tfhe.log 2>&1
+tail -2 gpurun_out/ncu_tfhe.log | cut -c1-200
+ls -la gpurun_out/r2_tfhe_br.ncu-rep
