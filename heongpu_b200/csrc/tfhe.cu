@@ -316,45 +316,107 @@ __global__ void __launch_bounds__(kBrThreads, 4)
 }
 
 // ---------------------------------------------------------------------------
-// key switching N -> n (bootstrapping.cu:1351-1437): one CTA per sample, one thread per output coefficient
+// key switching N -> n (bootstrapping.cu:1351-1437): out = (0, b) - sum over (i, digit i2) of row(i, i2, value).
+// One CTA takes KS_S samples and one thread one output coefficient: the three candidate rows of a (i, i2) are
+// loaded once for all KS_S samples (the reference and a one-sample CTA stream 12 MB of key per sample from L2).
+// The 2-bit digits of every input coefficient are packed into 16 bits in shared memory first.
 // ---------------------------------------------------------------------------
+constexpr int KS_S = 8;
 __global__ void __launch_bounds__(512)
     k_tfhe_keyswitch(const int* __restrict__ in_a, const int* __restrict__ in_b, int* __restrict__ out_a,
                      int* __restrict__ out_b, const int* __restrict__ ks_a, const int* __restrict__ ks_b, int base_bit,
-                     int length, int n, int Nk)
+                     int length, int n, int Nk, int shape)
 {
-    __shared__ int sa[TN];
+    __shared__ unsigned short dgs[KS_S][TN];
     const int tid = threadIdx.x;
-    const long long s = blockIdx.x;
-    for (int c = tid; c < Nk; c += blockDim.x)
-        sa[c] = in_a[s * Nk + c];
-    __syncthreads();
+    const long long s0 = (long long) blockIdx.x * KS_S;
+    const int ns = (int) min((long long) KS_S, shape - s0);
     const int mask = (1 << base_bit) - 1;
     const unsigned prec = 1u << (32 - (1 + base_bit * length));
-    unsigned acc = 0, accb = (tid == 0) ? (unsigned) in_b[s] : 0u;
-    if (tid < n)
+    for (int e = tid; e < KS_S * Nk; e += blockDim.x)
     {
+        const int sidx = e / Nk, c = e - sidx * Nk;
+        unsigned short pk = 0;
+        if (sidx < ns)
+        {
+            const unsigned av = (unsigned) in_a[(s0 + sidx) * Nk + c] + prec;
+            for (int i2 = 0; i2 < length; ++i2)
+                pk |= (unsigned short) (((av >> (32 - (i2 + 1) * base_bit)) & (unsigned) mask) << (2 * i2));
+        }
+        dgs[sidx][c] = pk;
+    }
+    __syncthreads();
+    unsigned acc[KS_S];
+#pragma unroll
+    for (int q = 0; q < KS_S; ++q)
+        acc[q] = 0;
+    unsigned accb = (tid < ns) ? (unsigned) in_b[s0 + tid] : 0u;
+    if (base_bit == 2 && length == 8 && tid < n)
+    {
+#pragma unroll 1
         for (int i = 0; i < Nk; ++i)
         {
-            const unsigned av = (unsigned) sa[i] + prec;
-            const size_t row_i = (size_t) i * length * mask;
-#pragma unroll 4
-            for (int i2 = 0; i2 < length; ++i2)
+            unsigned short d[KS_S];
+#pragma unroll
+            for (int q = 0; q < KS_S; ++q)
+                d[q] = dgs[q][i];
+            const int* rowp = ks_a + ((size_t) i * 24) * n + tid;
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2)
             {
-                const int dg = (int) ((av >> (32 - (i2 + 1) * base_bit)) & (unsigned) mask);
-                if (dg != 0)
+                const unsigned r1 = (unsigned) __ldg(rowp + (size_t) (i2 * 3 + 0) * n);
+                const unsigned r2 = (unsigned) __ldg(rowp + (size_t) (i2 * 3 + 1) * n);
+                const unsigned r3 = (unsigned) __ldg(rowp + (size_t) (i2 * 3 + 2) * n);
+#pragma unroll
+                for (int q = 0; q < KS_S; ++q)
                 {
-                    const size_t row = row_i + (size_t) i2 * mask + (dg - 1);
-                    acc -= (unsigned) __ldg(ks_a + row * n + tid);
-                    if (tid == 0)
-                        accb -= (unsigned) __ldg(ks_b + row);
+                    const unsigned dg = (d[q] >> (2 * i2)) & 3u;
+                    const unsigned x = dg == 1 ? r1 : (dg == 2 ? r2 : r3);
+                    acc[q] -= dg ? x : 0u;
+                }
+            }
+            if (tid < ns)
+            {
+                const unsigned short dd = dgs[tid][i];
+#pragma unroll
+                for (int i2 = 0; i2 < 8; ++i2)
+                {
+                    const unsigned dg = (dd >> (2 * i2)) & 3u;
+                    if (dg)
+                        accb -= (unsigned) __ldg(ks_b + (size_t) i * 24 + i2 * 3 + (dg - 1));
                 }
             }
         }
-        out_a[s * n + tid] = (int) acc;
     }
-    if (tid == 0)
-        out_b[s] = (int) accb;
+    else if (tid < n)
+    {
+        // general (base, length): one sample at a time
+        for (int q = 0; q < ns; ++q)
+            for (int i = 0; i < Nk; ++i)
+            {
+                const unsigned av = (unsigned) in_a[(s0 + q) * Nk + i] + prec;
+                for (int i2 = 0; i2 < length; ++i2)
+                {
+                    const int dg = (int) ((av >> (32 - (i2 + 1) * base_bit)) & (unsigned) mask);
+                    if (dg)
+                    {
+                        const size_t row = ((size_t) i * length + i2) * mask + (dg - 1);
+                        acc[q] -= (unsigned) __ldg(ks_a + row * n + tid);
+                        if (tid == q)
+                            accb -= (unsigned) __ldg(ks_b + row);
+                    }
+                }
+            }
+    }
+    if (tid < n)
+    {
+#pragma unroll
+        for (int q = 0; q < KS_S; ++q)
+            if (q < ns)
+                out_a[(s0 + q) * n + tid] = (int) acc[q];
+    }
+    if (tid < ns)
+        out_b[s0 + tid] = (int) accb;
 }
 
 // ---------------------------------------------------------------------------
@@ -700,7 +762,8 @@ void tfhe_keyswitch(const TfheContext& c, const int* in_a, const int* in_b, int*
     if (shape < 1)
         throw std::invalid_argument("empty ciphertext");
     LaunchScope scope(KC_TFHE_KEYSWITCH, st);
-    k_tfhe_keyswitch<<<shape, 512, 0, st>>>(in_a, in_b, out_a, out_b, ks_a, ks_b, c.ks_base_bit, c.ks_length, c.n, c.k * c.N);
+    k_tfhe_keyswitch<<<(shape + KS_S - 1) / KS_S, 512, 0, st>>>(in_a, in_b, out_a, out_b, ks_a, ks_b, c.ks_base_bit, c.ks_length, c.n,
+                                                               c.k * c.N, shape);
     t_check_launch();
 }
 
