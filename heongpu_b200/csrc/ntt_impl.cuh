@@ -1,4 +1,5 @@
 #pragma once
+#include <type_traits>
 // Template implementation of the batched NTT (maps, kernels, launch helpers).  Included by the ntt_*.cu
 // translation units, each of which instantiates it for a few polynomial maps (parallel compilation).
 // Batched negacyclic NTT / INTT over RNS limbs for sm_100a.
@@ -661,6 +662,105 @@ __global__ void __launch_bounds__(ROWS * 16, HEON_NTT_MINBLOCKS * 16 / ROWS)
         tma_store_wait_read<0>();
 }
 
+
+// Forward row pass, walking form (MapContig: polynomial z uses prime pl[z % count]): one CTA owns (row tile,
+// prime slot) and walks the G polynomials z = y + count*(g*G + k) that share this prime.  The tile's FP64 twiddles
+// are staged once per CTA; data tiles go through two buffers, so the load of polynomial k+1 and the store of
+// polynomial k-1 overlap the arithmetic of polynomial k (the structure of k_row_mac's digit walk).  ROWS = 8:
+// 16 KiB of twiddles + 2 x 16 KiB of data per CTA, four CTAs per SM.
+template <class Map, int G>
+__global__ void __launch_bounds__(128, 4)
+    ntt_row_pass_tma_walk(Map map, const __grid_constant__ CUtensorMap tm_out, const u64* out_base,
+                          const TwPair* __restrict__ tw_all, const TwPair* __restrict__ rowb_all,
+                          const PrimeConst* __restrict__ pcs, int logn, int variant, long long n_polys,
+                          const double* __restrict__ rowc_all)
+{
+    constexpr int ROWS = 8;
+    constexpr int kTileBytes = ROWS * 2048;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ __align__(8) uint64_t twbar;
+    unsigned char* buf0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* twbuf = buf0 + 2 * kTileBytes;
+    const int S1 = logn - 8;
+    const int tiles = (1 << S1) / ROWS;
+    const int period = map.pl.count;
+    const int tile_idx = blockIdx.x % tiles;
+    const int y = (blockIdx.x / tiles) % period;
+    const long long grp = blockIdx.x / ((long long) tiles * period);
+    const int tt = threadIdx.x & 15, rl = threadIdx.x >> 4;
+    auto poly = [&](int k) { return (long long) y + (long long) period * (grp * G + k); };
+    int cnt = 0;
+    while (cnt < G && poly(cnt) < n_polys)
+        ++cnt;
+    if (cnt == 0)
+        return;
+    const int prime = map.pl.idx[y];
+    const PrimeConst pc = pcs[prime];
+    const bool twsm = rowc_all && pc.fp_var != 0;
+    auto line_of = [&](int k) {
+        const u64* in;
+        u64* out;
+        int pr, aux;
+        map.get(poly(k), in, out, pr, aux);
+        return (int) ((out - out_base) >> 4) + tile_idx * (ROWS * 16);
+    };
+    if (threadIdx.x == 0)
+    {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_init(&twbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        mbar_arrive_expect_tx(&bar[0], kTileBytes);
+        tma_load_2d(buf0, &tm_out, &bar[0], 0, line_of(0));
+        if (twsm)
+        {
+            mbar_arrive_expect_tx(&twbar, kTileBytes);
+            tma_load_1d(twbuf, rowc_all + ((((long long) prime << S1) + tile_idx * ROWS) << 8), kTileBytes, &twbar);
+        }
+    }
+    const TwPair* tw = tw_all + ((long long) prime << logn);
+    const int r = tile_idx * ROWS + rl;
+    const TwPair* blk = rowb_all + ((((long long) prime << S1) + r) << 8);
+    const double* rowtw = twsm ? reinterpret_cast<const double*>(twbuf) + rl * 256 : nullptr;
+    if (twsm)
+        mbar_wait(&twbar, 0);
+#pragma unroll 1
+    for (int k = 0; k < cnt; ++k)
+    {
+        const int b = k & 1;
+        unsigned char* tile = buf0 + b * kTileBytes;
+        if (threadIdx.x == 0 && k + 1 < cnt)
+        {
+            tma_store_wait_read<0>(); // the other buffer: its store (polynomial k-1) has read it
+            mbar_arrive_expect_tx(&bar[b ^ 1], kTileBytes);
+            tma_load_2d(buf0 + (b ^ 1) * kTileBytes, &tm_out, &bar[b ^ 1], 0, line_of(k + 1));
+        }
+        mbar_wait(&bar[b], (k >> 1) & 1);
+        unsigned char* rowp = tile + rl * 2048;
+        if (pc.fp_var == 3)
+            row_pass_tma_body<false, 3>(rowp, pc, tw, blk, S1, r, tt, rowtw);
+        else if (pc.fp_var == 4)
+            row_pass_tma_body<false, 4>(rowp, pc, tw, blk, S1, r, tt, rowtw);
+        else if (variant == 1 || !pc.nc_ok)
+            row_pass_tma_body<false, 1>(rowp, pc, tw, blk, S1, r, tt, nullptr);
+        else
+            row_pass_tma_body<false, 2>(rowp, pc, tw, blk, S1, r, tt, nullptr);
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            tma_store_2d(&tm_out, tile, 0, line_of(k));
+            tma_store_commit();
+        }
+    }
+    if (threadIdx.x == 0)
+        tma_store_wait_read<0>();
+}
 
 // ---------------------------------------------------------------------------
 // Fused forward transform: ONE persistent kernel runs the column tiles and the
@@ -1369,10 +1469,51 @@ static void launch_row_tma_rows(const Context& c, const Map& m, long long n_poly
                                        n_tiles, (!INV && !c.ntt_persistent && c.use_fp64) ? c.d_fwd_rowc : nullptr);
 }
 
+// forward row pass walking same-prime polynomials (MapContig, second pass); false: not applicable
+template <bool INV, class Map>
+static bool launch_row_walk(const Context& c, const Map& m, long long n_polys, bool first, const Extent& e, cudaStream_t st)
+{
+    if constexpr (INV || !std::is_same<Map, MapContig>::value)
+        return false;
+    else
+    {
+        const int period = m.pl.count;
+        if (first || c.row_walk == 0 || !c.use_fp64 || c.ntt_persistent || c.logn < 11 || period < 1)
+            return false;
+        const long long per_prime = (n_polys + period - 1) / period;
+        if (per_prime < 4)
+            return false;
+        const int S = c.logn - 8;
+        const int tiles = (1 << S) / 8;
+        const int G = c.row_walk > 0 ? c.row_walk : 8;
+        const long long groups = (per_prime + G - 1) / G;
+        const long long grid = groups * period * tiles;
+        if (grid > 0x7fffffffll)
+            return false;
+        const CUtensorMap tm_out = make_line_map(e.out_base, e.out_words, 8 * 16);
+        const int smem = 3 * 8 * 2048 + 1024;
+        LaunchScope scope(KC_NTT_FWD_ROW, st);
+        auto go = [&](auto kfn) {
+            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            kfn<<<(unsigned) grid, 128, smem, st>>>(m, tm_out, e.out_base, c.d_fwd, c.d_fwd_rowb, c.d_pc, c.logn, c.ntt_variant,
+                                                   n_polys, c.d_fwd_rowc);
+        };
+        if (G >= 8)
+            go(ntt_row_pass_tma_walk<Map, 8>);
+        else if (G >= 4)
+            go(ntt_row_pass_tma_walk<Map, 4>);
+        else
+            go(ntt_row_pass_tma_walk<Map, 2>);
+        return true;
+    }
+}
+
 template <bool INV, class Map>
 static void launch_row_tma(const Context& c, const Map& m, long long n_polys, bool first, const Extent& e,
                            cudaStream_t st)
 {
+    if (launch_row_walk<INV>(c, m, n_polys, first, e, st))
+        return;
     if (c.row_tile == 4 && !c.ntt_persistent)
         launch_row_tma_rows<INV, Map, 4>(c, m, n_polys, first, e, st);
     else if (c.row_tile == 8 && !c.ntt_persistent)

@@ -289,14 +289,15 @@ def _ctx_with_env(name, **env):
                                  {"HEON_COL_THREADS": 128}, {"HEON_NTT_PERSISTENT": 1}, {"HEON_COL_TMA": 0}, {"HEON_COL_TMA_TILES": 1},
                                  {"HEON_COL_TMA_TILES": 2}, {"HEON_COL_TMA_TILES": 8}, {"HEON_COL_TMA_TILES": 16},
                                  {"HEON_COL_TMA_TILES": 4, "HEON_COL_TMA_BUFS": 3},
-                                 {"HEON_COL_TMA_TILES": 16, "HEON_COL_TMA_BUFS": 3}])
+                                 {"HEON_COL_TMA_TILES": 16, "HEON_COL_TMA_BUFS": 3}, {"HEON_ROW_WALK": 0}, {"HEON_ROW_WALK": 2},
+                                 {"HEON_ROW_WALK": 4}])
 def test_alternate_ntt_paths_agree(env):
     """The opt-in transforms (warp-specialised pipelined kernel, ticket-ordered fused kernel), the
     integer-only butterflies and the LSU row pass must give the default path's words."""
     name = "n16_II_small"
     ctx, alt, oc = gpu_ctx(name), _ctx_with_env(name, **env), oracle_ctx(name)
     order = ctx.level_primes(0)
-    x = residues(130, [oc.primes[i] for i in order], oc.n, (3,))  # 3 polys per prime
+    x = residues(130, [oc.primes[i] for i in order], oc.n, (5,))  # 5 polys per prime (a ragged walk of 4 + 1)
     a, b = to_dev(x), to_dev(x)
     ctx.ntt(a, order)
     alt.ntt(b, order)
