@@ -118,6 +118,7 @@ struct Context {
     int ntt_fused = 0; // forward transform as one ticket-ordered kernel, pass-to-pass data in L2 (HEON_NTT_FUSED=1 enables; superseded by the pipelined kernel)
     int use_fp64 = 1; // FP64-pipe quotient for primes < 2^50 (HEON_NTT_FP64=0 disables)
     int col_tma = 1;             // HEON_COL_TMA: forward column pass at N = 2^16 through pipelined TMA tiles (0: register-resident LSU form)
+    int row_mac_overlap = 0;     // HEON_ROW_MAC_OVERLAP: CTAs per SM of the persistent integer-limb launch that runs next to the FP64 launch (0 = back to back)
     int row_walk = -1;           // HEON_ROW_WALK: forward row pass walks this many same-prime polynomials per CTA (-1 = 8, 0 = one tile per CTA)
     int col_tma_bufs = 2;        // HEON_COL_TMA_BUFS: tile buffers per CTA of the pipelined TMA column pass (2: 3 CTAs/SM, 3: 2 CTAs/SM)
     int col_tma_tiles = 0;       // HEON_COL_TMA_TILES: tiles one CTA of the TMA column pass walks (0 = by grid size)
