@@ -173,8 +173,8 @@ static void finish_context(Context& c, int device, int log_n, int n_q, int n_p, 
         c.col_tma = atoi(v);
     if (const char* v = getenv("HEON_COL_TMA_TILES"))
         c.col_tma_tiles = atoi(v);
-    if (const char* v = getenv("HEON_ROW_MAC_OVERLAP"))
-        c.row_mac_overlap = atoi(v);
+    if (const char* v = getenv("HEON_MODUP_DOUBLES"))
+        c.modup_doubles = atoi(v);
     if (const char* v = getenv("HEON_ROW_WALK"))
         c.row_walk = atoi(v);
     if (const char* v = getenv("HEON_COL_TMA_BUFS"))

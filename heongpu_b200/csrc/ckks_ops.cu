@@ -356,7 +356,7 @@ template <int IJ>
 __device__ __forceinline__ void modup2_fast_body(const u64* __restrict__ pc_in, u64* __restrict__ po,
                                                  const PrimeConst* __restrict__ pcs,
                                                  const TwPair* __restrict__ mi_inv, const Mu2Rec* rec,
-                                                 const u64* srp, int I_loc, int logn, int Qpl, bool skip_own)
+                                                 const u64* srp, int I_loc, int logn, int Qpl, bool skip_own, bool emit_doubles)
 {
     u64 x[IJ][2], partial[IJ][2];
     double pd[IJ][2];
@@ -421,8 +421,17 @@ __device__ __forceinline__ void modup2_fast_body(const u64* __restrict__ pc_in, 
                 a0 = __dadd_rn(a0, fp_mulmod(pd[j][0], w, wi, dnp));
                 a1 = __dadd_rn(a1, fp_mulmod(pd[j][1], w, wi, dnp));
             }
-            res.x = fp_canon(__dsub_rn(a0, fp_from_u64(rp0[k])), rc.pinv, dnp, rc.dp);
-            res.y = fp_canon(__dsub_rn(a1, fp_from_u64(rp1[k])), rc.pinv, dnp, rc.dp);
+            if (emit_doubles)
+            {
+                // the column pass that follows works on integer-valued doubles: leave |v| <= p/2 as it is
+                res.x = d2u(fp_reduce(__dsub_rn(a0, fp_from_u64(rp0[k])), rc.pinv, dnp));
+                res.y = d2u(fp_reduce(__dsub_rn(a1, fp_from_u64(rp1[k])), rc.pinv, dnp));
+            }
+            else
+            {
+                res.x = fp_canon(__dsub_rn(a0, fp_from_u64(rp0[k])), rc.pinv, dnp, rc.dp);
+                res.y = fp_canon(__dsub_rn(a1, fp_from_u64(rp1[k])), rc.pinv, dnp, rc.dp);
+            }
         }
         else
         {
@@ -476,10 +485,10 @@ __global__ void __launch_bounds__(256)
     u64* po = out + (((bz * d + dg) * Qpl) << logn) + idx;
     switch (I_j)
     {
-        case 1: modup2_fast_body<1>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, skip_own != 0); break;
-        case 2: modup2_fast_body<2>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, skip_own != 0); break;
-        case 3: modup2_fast_body<3>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, skip_own != 0); break;
-        case 4: modup2_fast_body<4>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, skip_own != 0); break;
+        case 1: modup2_fast_body<1>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, (skip_own & 1) != 0, (skip_own & 2) != 0); break;
+        case 2: modup2_fast_body<2>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, (skip_own & 1) != 0, (skip_own & 2) != 0); break;
+        case 3: modup2_fast_body<3>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, (skip_own & 1) != 0, (skip_own & 2) != 0); break;
+        case 4: modup2_fast_body<4>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, (skip_own & 1) != 0, (skip_own & 2) != 0); break;
     }
 }
 
@@ -1209,10 +1218,22 @@ static int keyswitch_modup_ntt(const Context& c, const u64* coef, long long coef
             check_launch();
             return d;
         }
+        // digits whose source primes all have an FP64 form leave their FP64-prime target words as integer-valued
+        // doubles (the column pass of MapDigitSkip takes them as they are): only with the fast kernel and the skip map
+        unsigned long long dbl_mask = 0;
         // two coefficients per thread when the digits are short and the buffers 16-byte aligned
         const bool wide = K <= 4 && c.n >= 512 && (coef_bs & 1) == 0 &&
                           ((reinterpret_cast<uintptr_t>(coef) | reinterpret_cast<uintptr_t>(tmp)) & 15) == 0;
         dim3 g(wide ? c.n >> 9 : c.n >> 8, d, batch);
+        if (own_stashed && wide && Qpl <= kMu2MaxQ && K <= 4 && c.modup_doubles && c.use_fp64)
+            for (int i = 0; i < d; ++i)
+            {
+                bool fp = true;
+                for (int j = 0; j < t.I_j[i]; ++j)
+                    fp = fp && c.mod[t.I_loc[i] + j].bit <= 50;
+                if (fp)
+                    dbl_mask |= 1ull << i;
+            }
         {
             LaunchScope scope(KC_MODUP2, st);
             if (own_stashed && !(wide && Qpl <= kMu2MaxQ && K <= 4))
@@ -1220,7 +1241,7 @@ static int keyswitch_modup_ntt(const Context& c, const u64* coef, long long coef
             if (wide && Qpl <= kMu2MaxQ && K <= 4)
                 k_modup2_fast<<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_pc, t.d_base_change_pair, t.d_mi_inv_pair,
                                               t.d_rprod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth, K,
-                                              own_stashed ? 1 : 0);
+                                              (own_stashed ? 1 : 0) | (dbl_mask ? 2 : 0));
             else if (wide)
                 k_modup2<2><<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_pc, t.d_base_change_pair, t.d_mi_inv_pair,
                                             t.d_rprod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth);
@@ -1230,7 +1251,7 @@ static int keyswitch_modup_ntt(const Context& c, const u64* coef, long long coef
         }
         check_launch();
         if (own_stashed)
-            launch_ntt_digit_skip(c, tmp, d, t.I_loc.data(), t.I_j.data(), L, depth, batch, st, col_only);
+            launch_ntt_digit_skip(c, tmp, d, t.I_loc.data(), t.I_j.data(), L, depth, batch, st, col_only, dbl_mask);
         else
             launch_ntt(c, tmp, tmp, (long long) batch * d * Qpl, level_primes(L, K, depth), false, st, col_only);
     }

@@ -118,7 +118,7 @@ struct Context {
     int ntt_fused = 0; // forward transform as one ticket-ordered kernel, pass-to-pass data in L2 (HEON_NTT_FUSED=1 enables; superseded by the pipelined kernel)
     int use_fp64 = 1; // FP64-pipe quotient for primes < 2^50 (HEON_NTT_FP64=0 disables)
     int col_tma = 1;             // HEON_COL_TMA: forward column pass at N = 2^16 through pipelined TMA tiles (0: register-resident LSU form)
-    int row_mac_overlap = 0;     // HEON_ROW_MAC_OVERLAP: CTAs per SM of the persistent integer-limb launch that runs next to the FP64 launch (0 = back to back)
+    int modup_doubles = 1;       // HEON_MODUP_DOUBLES: the fast Method-II mod-up leaves FP64-prime words as doubles for the column pass
     int row_walk = -1;           // HEON_ROW_WALK: forward row pass walks this many same-prime polynomials per CTA (-1 = 8, 0 = one tile per CTA)
     int col_tma_bufs = 2;        // HEON_COL_TMA_BUFS: tile buffers per CTA of the pipelined TMA column pass (2: 3 CTAs/SM, 3: 2 CTAs/SM)
     int col_tma_tiles = 0;       // HEON_COL_TMA_TILES: tiles one CTA of the TMA column pass walks (0 = by grid size)
@@ -181,7 +181,7 @@ void upload_bfv_tables(Context& c);
 void launch_ntt(const Context& c, const u64* src, u64* dst, long long n_polys, const PrimeList& pl,
                 bool inverse, cudaStream_t st, bool col_only = false);
 void launch_ntt_digit_skip(const Context& c, u64* tmp, int d, const int* I_loc, const int* I_j, int L, int depth,
-                           long long batch, cudaStream_t st, bool col_only = false);
+                           long long batch, cudaStream_t st, bool col_only = false, unsigned long long dbl_mask = 0);
 bool modup2_fused_available(const Context& c, int depth, const u64* coef, long long coef_bs);
 void launch_modup2_ntt(const Context& c, const u64* coef, long long coef_bs, u64* tmp, u64* part, unsigned char* rq,
                        int depth, long long batch, bool own_stashed, bool col_only, cudaStream_t st);

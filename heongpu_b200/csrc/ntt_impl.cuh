@@ -129,6 +129,7 @@ struct MapStridedCopy {
 struct MapDigitSkip {
     u64* base;
     int d, Qpl, L, depth, logn, per_b;
+    unsigned long long dbl_mask; // bit i: the FP64-prime words of digit i are integer-valued doubles
     short prefix[66], I_loc[65], I_j[65];
     __device__ __forceinline__ void get(long long z, const u64*& in, u64*& out, int& prime, int& aux) const
     {
@@ -142,7 +143,7 @@ struct MapDigitSkip {
             y += I_j[i];
         in = out = base + (((b * d + i) * Qpl + y) << logn);
         prime = level_prime(y, L, depth);
-        aux = 0;
+        aux = (int) ((dbl_mask >> i) & 1ull);
     }
     static constexpr bool kXform = false;
     static constexpr bool kGather = false;
@@ -216,6 +217,12 @@ struct MapDivRoundOne {
     }
 };
 
+// kDoubleAux<Map>: `aux` = 1 marks a polynomial whose FP64-prime words were left as integer-valued doubles
+// (|v| <= p/2) by the producer (the fast Method-II mod-up): the column pass takes them as they are instead of
+// converting canonical integers.
+template <class Map> struct MapDoubleAux { static constexpr bool value = false; };
+template <> struct MapDoubleAux<MapDigitSkip> { static constexpr bool value = true; };
+
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
@@ -258,7 +265,13 @@ __device__ __forceinline__ void col_pass_body(const Map& map, const u64* in, u64
                 u64 x = in[(long long) (tt + T * k) * 256 + col];
                 if (Map::kXform && first_pass)
                     x = map.xform(x, prime, pc, aux);
-                v[k] = ct_prep<VAR>(x, bc, Map::kLazyIn);
+                if (MapDoubleAux<Map>::value && VAR >= 3 && aux)
+                    v[k] = x;
+                else
+                    if (MapDoubleAux<Map>::value && VAR >= 3 && aux)
+            v[k] = x;
+        else
+            v[k] = ct_prep<VAR>(x, bc, Map::kLazyIn);
             }
         }
         ct_round_a<VAR>(v, tw, 0, 0, bc);
@@ -937,7 +950,10 @@ __device__ __forceinline__ void pipe_col_tile(unsigned char* tile, const Map& ma
         u64 x = *reinterpret_cast<const u64*>(pa + k * 2048);
         if (Map::kXform)
             x = map.xform(x, prime, pc, aux);
-        v[k] = ct_prep<VAR>(x, bc, Map::kLazyIn);
+        if (MapDoubleAux<Map>::value && VAR >= 3 && aux)
+            v[k] = x;
+        else
+            v[k] = ct_prep<VAR>(x, bc, Map::kLazyIn);
     }
     ct_round_a<VAR, 0, SMTW>(v, tw, 0, 0, bc);
 #pragma unroll
@@ -1485,7 +1501,12 @@ static bool launch_row_walk(const Context& c, const Map& m, long long n_polys, b
             return false;
         const int S = c.logn - 8;
         const int tiles = (1 << S) / 8;
-        const int G = c.row_walk > 0 ? c.row_walk : 8;
+        // walking serialises tiles that would otherwise run side by side: only when the GPU stays full
+        // (four resident CTAs per SM, a few waves deep); small transforms are latency-bound and keep one tile per CTA
+        const long long all_tiles = per_prime * period * tiles;
+        if (c.row_walk < 0 && all_tiles < 16ll * c.num_sms)
+            return false;
+        const int G = c.row_walk > 0 ? c.row_walk : (int) std::min<long long>(8, std::max<long long>(2, all_tiles / (8ll * c.num_sms)));
         const long long groups = (per_prime + G - 1) / G;
         const long long grid = groups * period * tiles;
         if (grid > 0x7fffffffll)

@@ -4,7 +4,7 @@
 namespace heon {
 
 void launch_ntt_digit_skip(const Context& c, u64* tmp, int d, const int* I_loc, const int* I_j, int L, int depth,
-                           long long batch, cudaStream_t st, bool col_only)
+                           long long batch, cudaStream_t st, bool col_only, unsigned long long dbl_mask)
 {
     const int Qpl = L + c.P_size;
     if (d > 64)
@@ -16,6 +16,7 @@ void launch_ntt_digit_skip(const Context& c, u64* tmp, int d, const int* I_loc, 
     m.L = L;
     m.depth = depth;
     m.logn = c.logn;
+    m.dbl_mask = dbl_mask;
     int acc = 0;
     for (int i = 0; i < d; ++i)
     {

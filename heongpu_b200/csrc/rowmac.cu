@@ -1,6 +1,4 @@
 // Key-switch inner product fused behind the forward row pass (k_row_mac).
-#include <algorithm>
-#include <cstdlib>
 #include "ntt_impl.cuh"
 
 namespace heon {
@@ -45,8 +43,7 @@ __global__ void __launch_bounds__(ROWS * 16, FP ? 24 / ROWS : 16 / ROWS)
               const __grid_constant__ CUtensorMap tm_out, const TwPair* __restrict__ tw_all,
               const TwPair* __restrict__ rowb_all, const double* __restrict__ rowc_all,
               const PrimeConst* __restrict__ pcs, const LimbList limb_list, int logn, int L,
-              int Qpl, int Qp0, int depth, int variant, int red_period_lo, int red_period_hi, OwnLimbs own,
-              int batch, int tiles, long long n_jobs)
+              int Qpl, int Qp0, int depth, int variant, int red_period_lo, int red_period_hi, OwnLimbs own)
 {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar[2];
@@ -58,23 +55,9 @@ __global__ void __launch_bounds__(ROWS * 16, FP ? 24 / ROWS : 16 / ROWS)
     unsigned char* stw = buf0 + 3 * T;
     const int S1 = logn - 8;
     const int lpp = 1 << (logn - 4); // 128-byte lines per polynomial
-    if (threadIdx.x == 0)
-    {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    unsigned n0 = 0, n1 = 0; // completed phases of the two barriers (a CTA may walk several jobs)
-    // job = (ciphertext b, tile, limb slot), b fastest: the CTAs that need the same key tiles run together.  The grid
-    // covers every job once, or -- persistent form, used for the integer limbs when they run next to the FP64
-    // launch -- a few CTAs per SM stride over the jobs.
-#pragma unroll 1
-    for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x)
-    {
-    const long long b = job % batch;
-    const int tile_idx = (int) ((job / batch) % tiles);
-    const int y = limb_list.y[job / ((long long) batch * tiles)];
+    const long long b = blockIdx.x;
+    const int tile_idx = blockIdx.y;
+    const int y = limb_list.y[blockIdx.z];
     const int prime = level_prime(y, L, depth);
     const PrimeConst pc = pcs[prime];
     const BflyConst bc = make_bc(pc);
@@ -85,6 +68,13 @@ __global__ void __launch_bounds__(ROWS * 16, FP ? 24 / ROWS : 16 / ROWS)
     auto dline = [&](int i) { return (int) (((b * d + i) * Qpl + y) * lpp) + line0; };
     auto kline = [&](int i, int c) { return (int) ((((long long) i * 2 + c) * Qp0 + prime) * lpp) + line0; };
 
+    if (threadIdx.x == 0)
+    {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
     if (threadIdx.x == 0)
     {
         mbar_arrive_expect_tx(&bar[0], FP ? 2 * T : T);
@@ -123,8 +113,7 @@ __global__ void __launch_bounds__(ROWS * 16, FP ? 24 / ROWS : 16 / ROWS)
     for (int i = 0; i < d; ++i)
     {
         u64 v[16];
-        mbar_wait(&bar[0], n0 & 1);
-        ++n0;
+        mbar_wait(&bar[0], i & 1);
         const bool own_i = own.own && y < L && y >= own.I_loc[i] && y < own.I_loc[i] + own.I_j[i];
         if (own_i)
         {
@@ -169,8 +158,7 @@ __global__ void __launch_bounds__(ROWS * 16, FP ? 24 / ROWS : 16 / ROWS)
             mbar_arrive_expect_tx(&bar[0], T);
             tma_load_2d(sdata, &tm_tmp, &bar[0], 0, dline(i + 1));
         }
-        mbar_wait(&bar[1], n1 & 1);
-        ++n1;
+        mbar_wait(&bar[1], i & 1);
         if constexpr (FP)
         {
             const double pinv = bc.dpinv, dnp = bc.dnp;
@@ -250,8 +238,6 @@ __global__ void __launch_bounds__(ROWS * 16, FP ? 24 / ROWS : 16 / ROWS)
         tma_store_commit();
         tma_store_wait_read<0>();
     }
-    __syncthreads(); // the buffers are free for the next job
-    }
 }
 
 // true when the fused row-pass + inner-product kernel can serve this key switch
@@ -263,21 +249,6 @@ bool row_mac_available(const Context& c, const u64* tmp, const u64* key, const u
 
 // acc[b][2][Qpl][N] = sum_i rowpass(tmp[b][i][y]) (.) key[i][c][prime(y)]; tmp holds column-pass output
 // (lazy words), digit-own limbs (own_stashed) hold canonical NTT-domain words.
-// one non-blocking side stream per (host thread, device): operators may be driven by several host threads,
-// each on its own stream
-static cudaStream_t side_stream(int device)
-{
-    thread_local cudaStream_t streams[16] = {};
-    const int slot = device & 15;
-    if (!streams[slot])
-    {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        cudaStreamCreateWithPriority(&streams[slot], cudaStreamNonBlocking, hi);
-    }
-    return streams[slot];
-}
-
 void launch_row_mac(const Context& c, const u64* tmp, const u64* key, u64* acc, int d, int depth, int batch,
                     bool own_stashed, const int* I_loc, const int* I_j, cudaStream_t st)
 {
@@ -312,56 +283,23 @@ void launch_row_mac(const Context& c, const u64* tmp, const u64* key, u64* acc, 
     // |T| <= 1.3 p per term (lazy x up to 2.25 p, quotient rounded by FRND): the double accumulator stays exact
     // while (1.3 * terms + 1/2) * p < 2^53 -> every 5 terms for p < 2^50, every 40 for p < 2^47
     const int red_lo = 40, red_hi = 5;
-    static const int fp_pad = [] {
-        const char* v = getenv("HEON_ROW_MAC_FP_PAD"); // experiment: extra dynamic shared memory (KiB) per FP CTA
-        return v ? atoi(v) * 1024 : 0;
-    }();
-    // The integer limbs (58..61-bit primes) keep the integer pipes busy and the FP64 pipe idle, the FP64 limbs the
-    // opposite: when both exist and the batch is large, the integer launch runs as a persistent kernel of
-    // `row_mac_overlap` CTAs per SM on a side stream NEXT TO the FP64 launch (fork / join by events), so the two
-    // share the SMs instead of running back to back.
-    const long long jobs_fp = (long long) batch * tiles * nfp, jobs_int = (long long) batch * tiles * nint;
-    const bool overlap = c.row_mac_overlap > 0 && nfp > 0 && nint > 0 && jobs_int >= 4ll * c.num_sms;
-    auto go = [&](auto kfn, int nl, const LimbList& list, int smem, long long jobs, cudaStream_t s, long long grid) {
+    auto go = [&](auto kfn, int nl, const LimbList& list, int smem) {
         if (nl == 0)
             return;
-        if (&list == &lfp)
-            smem += fp_pad;
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        LaunchScope scope(KC_ROW_MAC, s);
-        kfn<<<(unsigned) grid, rows * 16, smem, s>>>(tm_tmp, tm_key, tm_out, c.d_fwd, c.d_fwd_rowb, c.d_fwd_rowc, c.d_pc, list,
-                                                  c.logn, L, Qpl, c.Qp, depth, c.ntt_variant, red_lo, red_hi, own, batch, tiles,
-                                                  jobs);
+        LaunchScope scope(KC_ROW_MAC, st);
+        kfn<<<dim3(batch, tiles, nl), rows * 16, smem, st>>>(tm_tmp, tm_key, tm_out, c.d_fwd, c.d_fwd_rowb, c.d_fwd_rowc, c.d_pc,
+                                                        list, c.logn, L, Qpl, c.Qp, depth, c.ntt_variant, red_lo, red_hi, own);
     };
-    cudaStream_t side = st;
-    cudaEvent_t ev_join = nullptr;
-    if (overlap)
-    {
-        side = side_stream(c.device);
-        cudaEvent_t ev_fork;
-        cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
-        cudaEventRecord(ev_fork, st);
-        cudaStreamWaitEvent(side, ev_fork, 0);
-        cudaEventDestroy(ev_fork);
-    }
-    const long long grid_int = overlap ? std::min<long long>(jobs_int, (long long) c.num_sms * c.row_mac_overlap) : jobs_int;
-    // the integer launch goes first so that its few persistent CTAs are resident before the FP64 CTAs fill the SMs
     if (rows == 8)
     {
-        go(k_row_mac<false, 8>, nint, lint, 3 * 8 * 2048 + 1024, jobs_int, side, grid_int);
-        go(k_row_mac<true, 8>, nfp, lfp, 4 * 8 * 2048 + 1024, jobs_fp, st, jobs_fp);
+        go(k_row_mac<true, 8>, nfp, lfp, 4 * 8 * 2048 + 1024);
+        go(k_row_mac<false, 8>, nint, lint, 3 * 8 * 2048 + 1024);
     }
     else
     {
-        go(k_row_mac<false, 4>, nint, lint, 3 * 4 * 2048 + 1024, jobs_int, side, grid_int);
-        go(k_row_mac<true, 4>, nfp, lfp, 4 * 4 * 2048 + 1024, jobs_fp, st, jobs_fp);
-    }
-    if (overlap)
-    {
-        cudaEventRecord(ev_join, side);
-        cudaStreamWaitEvent(st, ev_join, 0);
-        cudaEventDestroy(ev_join);
+        go(k_row_mac<true, 4>, nfp, lfp, 4 * 4 * 2048 + 1024);
+        go(k_row_mac<false, 4>, nint, lint, 3 * 4 * 2048 + 1024);
     }
 }
 

@@ -320,7 +320,9 @@ def test_alternate_ntt_paths_agree(env):
                                       ("n15_II", {"HEON_MODUP_FUSED": 1, "HEON_ROW_MAC": 0}),
                                       ("n16_II_small", {"HEON_COL_TMA": 0}), ("n16_I_small", {"HEON_COL_TMA": 0}),
                                       ("n16_II_small", {"HEON_COL_TMA_TILES": 8}), ("n16_I_small", {"HEON_COL_TMA_TILES": 4}),
-                                      ("n16_I_small", {"HEON_COL_TMA_TILES": 16, "HEON_COL_TMA_BUFS": 3})])
+                                      ("n16_I_small", {"HEON_COL_TMA_TILES": 16, "HEON_COL_TMA_BUFS": 3}),
+                                      ("n16_II_small", {"HEON_MODUP_DOUBLES": 0}), ("n13_II", {"HEON_MODUP_DOUBLES": 0}),
+                                      ("n15_II", {"HEON_MODUP_DOUBLES": 0, "HEON_ROW_MAC": 0})])
 def test_alternate_operator_paths_agree(name, env):
     """multiply + relinearize + rotation through the alternate paths equal the default path."""
     api = _api()
