@@ -268,10 +268,7 @@ __device__ __forceinline__ void col_pass_body(const Map& map, const u64* in, u64
                 if (MapDoubleAux<Map>::value && VAR >= 3 && aux)
                     v[k] = x;
                 else
-                    if (MapDoubleAux<Map>::value && VAR >= 3 && aux)
-            v[k] = x;
-        else
-            v[k] = ct_prep<VAR>(x, bc, Map::kLazyIn);
+                    v[k] = ct_prep<VAR>(x, bc, Map::kLazyIn);
             }
         }
         ct_round_a<VAR>(v, tw, 0, 0, bc);
@@ -1506,7 +1503,8 @@ static bool launch_row_walk(const Context& c, const Map& m, long long n_polys, b
         const long long all_tiles = per_prime * period * tiles;
         if (c.row_walk < 0 && all_tiles < 16ll * c.num_sms)
             return false;
-        const int G = c.row_walk > 0 ? c.row_walk : (int) std::min<long long>(8, std::max<long long>(2, all_tiles / (8ll * c.num_sms)));
+        const long long want = c.row_walk > 0 ? c.row_walk : all_tiles / (8ll * c.num_sms);
+        const int G = want >= 8 ? 8 : want >= 4 ? 4 : 2; // the instantiated walks
         const long long groups = (per_prime + G - 1) / G;
         const long long grid = groups * period * tiles;
         if (grid > 0x7fffffffll)

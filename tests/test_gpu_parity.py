@@ -290,7 +290,7 @@ def _ctx_with_env(name, **env):
                                  {"HEON_COL_TMA_TILES": 2}, {"HEON_COL_TMA_TILES": 8}, {"HEON_COL_TMA_TILES": 16},
                                  {"HEON_COL_TMA_TILES": 4, "HEON_COL_TMA_BUFS": 3},
                                  {"HEON_COL_TMA_TILES": 16, "HEON_COL_TMA_BUFS": 3}, {"HEON_ROW_WALK": 0}, {"HEON_ROW_WALK": 2},
-                                 {"HEON_ROW_WALK": 4}])
+                                 {"HEON_ROW_WALK": 4}, {"HEON_ROW_WALK": 3}, {"HEON_ROW_WALK": 6}])
 def test_alternate_ntt_paths_agree(env):
     """The opt-in transforms (warp-specialised pipelined kernel, ticket-ordered fused kernel), the
     integer-only butterflies and the LSU row pass must give the default path's words."""

@@ -21,5 +21,7 @@ timeout 300 python tools/bench_bsgs.py > gpurun_out/${R}_bsgs_C3_II.json 2> gpur
 # compute-sanitizer over the kernels added or changed since the last capture
 timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_tfhe.py tests/test_gpu_parity_r2.py tests/test_gpu_parity.py -q -x -k "tfhe or gate or blind or key_switch or bsgs or accumulate or alternate_ntt_paths or alternate_operator_paths" --timeout 1100 > gpurun_out/${R}_sanitizer_memcheck.txt 2>&1; echo "memcheck exit $?" >> gpurun_out/${R}_sanitizer_memcheck.txt
 tail -6 gpurun_out/${R}_sanitizer_memcheck.txt
-timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_tfhe.py tests/test_gpu_parity.py -q -x -k "blind_rotation_bit_exact and real_key or key_switch_bit_exact or (alternate_ntt_paths and (TILES or WALK)) or (alternate_operator_paths and n13_II)" --timeout 1100 > gpurun_out/${R}_sanitizer_racecheck.txt 2>&1; echo "racecheck exit $?" >> gpurun_out/${R}_sanitizer_racecheck.txt
+# racecheck: only tests that run THIS engine's kernels (the reference's own TFHE kernels report shared-memory hazards:
+# their SmallForwardNTT runs its last six stages without a barrier)
+timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_tfhe.py tests/test_gpu_parity.py -q -x -k "match_cpu_oracle or gate_errors or (alternate_ntt_paths and (TILES or WALK)) or (alternate_operator_paths and n13_II)" --timeout 1100 > gpurun_out/${R}_sanitizer_racecheck.txt 2>&1; echo "racecheck exit $?" >> gpurun_out/${R}_sanitizer_racecheck.txt
 tail -6 gpurun_out/${R}_sanitizer_racecheck.txt
