@@ -406,6 +406,49 @@ inline std::vector<Data64> default_modulus_128(size_t n)
 }
 } // namespace detail
 
+namespace detail {
+// Evaluation keys may live in host memory (ExecutionOptions::set_storage_type(HOST), store_in_host()): the
+// operators then stage the one key they need on their stream for the duration of the call, as the reference does
+// (e.g. ckks/operator.cu:3117-3131: DeviceVector<Data64> key_location(galois_key.host_location_[elt], stream)).
+struct KeyView {
+    DeviceVector<Data64> staged;
+    const Data64* ptr = nullptr;
+    KeyView() = default;
+    KeyView(const DeviceVector<Data64>& dev, const PinnedVector<Data64>& host, cudaStream_t st)
+    {
+        if (dev.data())
+            ptr = dev.data();
+        else if (host.data())
+        {
+            staged.resize(host.size(), st);
+            cuda(cudaMemcpyAsync(staged.data(), host.data(), host.size() * sizeof(Data64), cudaMemcpyHostToDevice, st));
+            ptr = staged.data();
+        }
+    }
+    KeyView(KeyView&&) = default;
+    KeyView& operator=(KeyView&&) = default;
+    explicit operator bool() const { return ptr != nullptr; }
+};
+inline void key_to_host(DeviceVector<Data64>& dev, PinnedVector<Data64>& host, cudaStream_t st)
+{
+    if (!dev.data())
+        return;
+    host.resize(dev.size());
+    cuda(cudaMemcpyAsync(host.data(), dev.data(), dev.size() * sizeof(Data64), cudaMemcpyDeviceToHost, st));
+    cuda(cudaStreamSynchronize(st));
+    dev = DeviceVector<Data64>();
+}
+inline void key_to_device(DeviceVector<Data64>& dev, PinnedVector<Data64>& host, cudaStream_t st)
+{
+    if (!host.data())
+        return;
+    dev.resize(host.size(), st);
+    cuda(cudaMemcpyAsync(dev.data(), host.data(), host.size() * sizeof(Data64), cudaMemcpyHostToDevice, st));
+    cuda(cudaStreamSynchronize(st));
+    host.clear();
+}
+} // namespace detail
+
 template <Scheme S> class HEContextImpl;
 template <Scheme S> using HEContext = std::shared_ptr<HEContextImpl<S>>;
 
@@ -616,6 +659,20 @@ template <> class Relinkey<Scheme::CKKS> {
     keyswitching_type key_type;
     storage_type storage_type_ = storage_type::DEVICE;
     DeviceVector<Data64> device_location_;
+    PinnedVector<Data64> host_location_;
+    // evaluationkey.cuh: store_in_host / store_in_device / is_on_device
+    void store_in_host(cudaStream_t st = cudaStreamDefault)
+    {
+        detail::key_to_host(device_location_, host_location_, st);
+        storage_type_ = storage_type::HOST;
+    }
+    void store_in_device(cudaStream_t st = cudaStreamDefault)
+    {
+        detail::key_to_device(device_location_, host_location_, st);
+        storage_type_ = storage_type::DEVICE;
+    }
+    bool is_on_device() const { return storage_type_ == storage_type::DEVICE; }
+    detail::KeyView view(cudaStream_t st) const { return detail::KeyView(device_location_, host_location_, st); }
     bool relin_key_generated_ = false;
 };
 
@@ -679,6 +736,35 @@ template <> class Galoiskey<Scheme::CKKS> {
     std::unordered_map<int, int> galois_elt; // shift -> galois element
     std::unordered_map<int, DeviceVector<Data64>> device_location_; // galois element -> key
     DeviceVector<Data64> zero_device_location_;
+    std::unordered_map<int, PinnedVector<Data64>> host_location_;
+    PinnedVector<Data64> zero_host_location_;
+    void store_in_host(cudaStream_t st = cudaStreamDefault)
+    {
+        for (auto& kv : device_location_)
+            detail::key_to_host(kv.second, host_location_[kv.first], st);
+        device_location_.clear();
+        detail::key_to_host(zero_device_location_, zero_host_location_, st);
+        storage_type_ = storage_type::HOST;
+    }
+    void store_in_device(cudaStream_t st = cudaStreamDefault)
+    {
+        for (auto& kv : host_location_)
+            detail::key_to_device(device_location_[kv.first], kv.second, st);
+        host_location_.clear();
+        detail::key_to_device(zero_device_location_, zero_host_location_, st);
+        storage_type_ = storage_type::DEVICE;
+    }
+    bool is_on_device() const { return storage_type_ == storage_type::DEVICE; }
+    bool has_key(int elt) const { return device_location_.count(elt) || host_location_.count(elt); }
+    detail::KeyView view(int elt, cudaStream_t st) const
+    {
+        static const DeviceVector<Data64> no_dev;
+        static const PinnedVector<Data64> no_host;
+        auto d = device_location_.find(elt);
+        auto h = host_location_.find(elt);
+        return detail::KeyView(d == device_location_.end() ? no_dev : d->second, h == host_location_.end() ? no_host : h->second, st);
+    }
+    detail::KeyView zero_view(cudaStream_t st) const { return detail::KeyView(zero_device_location_, zero_host_location_, st); }
 };
 
 template <Scheme S> class Plaintext;
@@ -726,6 +812,20 @@ template <> class Switchkey<Scheme::CKKS> {
     keyswitching_type key_type;
     storage_type storage_type_ = storage_type::DEVICE;
     DeviceVector<Data64> device_location_;
+    PinnedVector<Data64> host_location_;
+    // evaluationkey.cuh: store_in_host / store_in_device / is_on_device
+    void store_in_host(cudaStream_t st = cudaStreamDefault)
+    {
+        detail::key_to_host(device_location_, host_location_, st);
+        storage_type_ = storage_type::HOST;
+    }
+    void store_in_device(cudaStream_t st = cudaStreamDefault)
+    {
+        detail::key_to_device(device_location_, host_location_, st);
+        storage_type_ = storage_type::DEVICE;
+    }
+    bool is_on_device() const { return storage_type_ == storage_type::DEVICE; }
+    detail::KeyView view(cudaStream_t st) const { return detail::KeyView(device_location_, host_location_, st); }
     bool switch_key_generated_ = false;
 };
 
@@ -829,7 +929,8 @@ template <> class HEOperator<Scheme::CKKS> {
         if (ct.memory_size() < words(3, ct.depth_))
             throw std::invalid_argument("Invalid Ciphertexts size!");
         detail::InputGuard<Ciphertext<Scheme::CKKS>> g(ct, opt, true);
-        detail::check(heon_ckks_relinearize(h(), ct.data(), 0, rk.data(), ct.depth_, 1, opt.stream_));
+        const detail::KeyView key = rk.view(opt.stream_);
+        detail::check(heon_ckks_relinearize(h(), ct.data(), 0, key.ptr, ct.depth_, 1, opt.stream_));
         ct.relinearization_required_ = false;
         ct.cipher_size_ = 2;
         detail::output_storage(ct, opt);
@@ -895,12 +996,12 @@ template <> class HEOperator<Scheme::CKKS> {
     {
         if (in.rescale_required_ || in.relinearization_required_)
             throw std::invalid_argument("Ciphertext can not be rotated because of the non-linear part or noise!");
-        auto it = gk.device_location_.find(galois_elt);
-        if (it == gk.device_location_.end())
+        const detail::KeyView key = gk.view(galois_elt, opt.stream_);
+        if (!key)
             throw std::logic_error("Galois key not present!");
         detail::InputGuard<Ciphertext<Scheme::CKKS>> g(in, opt, &in == &out);
         DeviceVector<Data64> mem(words(2, in.depth_), opt.stream_);
-        detail::check(heon_ckks_apply_galois(h(), in.data(), 0, mem.data(), 0, it->second.data(),
+        detail::check(heon_ckks_apply_galois(h(), in.data(), 0, mem.data(), 0, key.ptr,
                                              (uint32_t) galois_elt, in.depth_, 1, opt.stream_));
         copy_meta(in, out);
         out.memory_set(std::move(mem));
@@ -927,7 +1028,7 @@ template <> class HEOperator<Scheme::CKKS> {
             return;
         }
         const int elt = heon_steps_to_galois_elt(shift, context_->n, gk.group_order_);
-        if (elt != 0 && gk.device_location_.count(elt))
+        if (elt != 0 && gk.has_key(elt))
         {
             apply_galois(in, out, gk, elt, opt);
             return;
@@ -939,7 +1040,7 @@ template <> class HEOperator<Scheme::CKKS> {
         for (int step : detail::rotation_plan(shift, log_slots, gk.max_shift_))
         {
             auto it = gk.galois_elt.find(step);
-            if (it == gk.galois_elt.end() || !gk.device_location_.count(it->second))
+            if (it == gk.galois_elt.end() || !gk.has_key(it->second))
                 throw std::logic_error("Galois key not present!");
             apply_galois(*cur, out, gk, it->second, opt);
             cur = &out;
@@ -962,16 +1063,17 @@ template <> class HEOperator<Scheme::CKKS> {
         if (in.rescale_required_ || in.relinearization_required_)
             throw std::invalid_argument("Ciphertext can not be rotated because of the non-linear part or noise!");
         std::vector<const uint64_t*> keys;
+        std::vector<detail::KeyView> views;
         std::vector<uint32_t> elts;
         for (int s : shifts)
         {
             if (s == 0)
                 throw std::invalid_argument("rotate_rows_hoisted: shift 0 is the identity, use the input itself");
             const int elt = heon_steps_to_galois_elt(s, context_->n, gk.group_order_);
-            auto it = gk.device_location_.find(elt);
-            if (elt == 0 || it == gk.device_location_.end())
+            if (elt == 0 || !gk.has_key(elt))
                 throw std::logic_error("Galois key not present!");
-            keys.push_back(it->second.data());
+            views.emplace_back(gk.view(elt, opt.stream_));
+            keys.push_back(views.back().ptr);
             elts.push_back((uint32_t) elt);
         }
         const size_t w = words(2, in.depth_);
@@ -1051,15 +1153,16 @@ template <> class HEOperator<Scheme::CKKS> {
                     continue;
                 }
                 std::vector<const uint64_t*> keys;
+                std::vector<detail::KeyView> views;
                 std::vector<uint32_t> elts;
                 int e = i;
                 for (; e < n1 && baby[e] != 0; ++e)
                 {
                     const int elt = heon_steps_to_galois_elt(baby[e], context_->n, gk.group_order_);
-                    auto it = gk.device_location_.find(elt);
-                    if (it == gk.device_location_.end())
+                    if (!gk.has_key(elt))
                         throw std::logic_error("Galois key not present!");
-                    keys.push_back(it->second.data());
+                    views.emplace_back(gk.view(elt, opt.stream_));
+                    keys.push_back(views.back().ptr);
                     elts.push_back((uint32_t) elt);
                 }
                 detail::check(heon_ckks_rotate_hoisted(h(), result.data(), 0, rotated.data() + i * w, 0, (long long) w,
@@ -1129,16 +1232,18 @@ template <> class HEOperator<Scheme::CKKS> {
         {
             std::sort(diags_matrices_bsgs_rot_n2_[m].begin(), diags_matrices_bsgs_rot_n2_[m].end());
             const std::vector<int>& baby = diags_matrices_bsgs_rot_n2_[m];
+            std::vector<detail::KeyView> views; // keys staged from host memory live until the call is enqueued
+            views.reserve(baby.size() + diags_matrices_bsgs_[m].size());
             auto resolve = [&](int shift, uint32_t& elt, const uint64_t*& key) {
                 elt = 0;
                 key = nullptr;
                 if (shift == 0)
                     return;
                 elt = (uint32_t) heon_steps_to_galois_elt(shift, context_->n, galois_key.group_order_);
-                auto it = galois_key.device_location_.find((int) elt);
-                if (it == galois_key.device_location_.end())
+                if (!galois_key.has_key((int) elt))
                     throw std::logic_error("Galois key not present!");
-                key = it->second.data();
+                views.emplace_back(galois_key.view((int) elt, opt.stream_));
+                key = views.back().ptr;
             };
             std::vector<uint32_t> baby_elts(baby.size()), giant_elts(diags_matrices_bsgs_[m].size());
             std::vector<const uint64_t*> baby_keys(baby.size()), giant_keys(giant_elts.size());
@@ -1218,7 +1323,8 @@ template <> class HEOperator<Scheme::CKKS> {
         if (!sk.switch_key_generated_)
             throw std::invalid_argument("Switchkey is not generated!");
         DeviceVector<Data64> mem(words(2, in.depth_), opt.stream_);
-        detail::check(heon_ckks_keyswitch(h(), in.data(), 0, mem.data(), 0, sk.data(), in.depth_, 1, opt.stream_));
+        const detail::KeyView key = sk.view(opt.stream_);
+        detail::check(heon_ckks_keyswitch(h(), in.data(), 0, mem.data(), 0, key.ptr, in.depth_, 1, opt.stream_));
         copy_meta(in, out);
         out.memory_set(std::move(mem));
         out.cipher_size_ = 2;
@@ -1233,10 +1339,11 @@ template <> class HEOperator<Scheme::CKKS> {
     {
         if (in.rescale_required_ || in.relinearization_required_)
             throw std::invalid_argument("Ciphertext can not be conjugated because of the non-linear part or noise!");
-        if (!gk.c_data())
+        const detail::KeyView key = gk.zero_view(opt.stream_);
+        if (!key)
             throw std::logic_error("Conjugation key not present!");
         DeviceVector<Data64> mem(words(2, in.depth_), opt.stream_);
-        detail::check(heon_ckks_conjugate(h(), in.data(), 0, mem.data(), 0, gk.c_data(), in.depth_, 1, opt.stream_));
+        detail::check(heon_ckks_conjugate(h(), in.data(), 0, mem.data(), 0, key.ptr, in.depth_, 1, opt.stream_));
         copy_meta(in, out);
         out.memory_set(std::move(mem));
         out.cipher_size_ = 2;
@@ -1531,6 +1638,20 @@ template <> class Relinkey<Scheme::BFV> {
     keyswitching_type key_type;
     storage_type storage_type_ = storage_type::DEVICE;
     DeviceVector<Data64> device_location_;
+    PinnedVector<Data64> host_location_;
+    // evaluationkey.cuh: store_in_host / store_in_device / is_on_device
+    void store_in_host(cudaStream_t st = cudaStreamDefault)
+    {
+        detail::key_to_host(device_location_, host_location_, st);
+        storage_type_ = storage_type::HOST;
+    }
+    void store_in_device(cudaStream_t st = cudaStreamDefault)
+    {
+        detail::key_to_device(device_location_, host_location_, st);
+        storage_type_ = storage_type::DEVICE;
+    }
+    bool is_on_device() const { return storage_type_ == storage_type::DEVICE; }
+    detail::KeyView view(cudaStream_t st) const { return detail::KeyView(device_location_, host_location_, st); }
     bool relin_key_generated_ = false;
 };
 
@@ -1550,6 +1671,20 @@ template <> class Switchkey<Scheme::BFV> {
     keyswitching_type key_type;
     storage_type storage_type_ = storage_type::DEVICE;
     DeviceVector<Data64> device_location_;
+    PinnedVector<Data64> host_location_;
+    // evaluationkey.cuh: store_in_host / store_in_device / is_on_device
+    void store_in_host(cudaStream_t st = cudaStreamDefault)
+    {
+        detail::key_to_host(device_location_, host_location_, st);
+        storage_type_ = storage_type::HOST;
+    }
+    void store_in_device(cudaStream_t st = cudaStreamDefault)
+    {
+        detail::key_to_device(device_location_, host_location_, st);
+        storage_type_ = storage_type::DEVICE;
+    }
+    bool is_on_device() const { return storage_type_ == storage_type::DEVICE; }
+    detail::KeyView view(cudaStream_t st) const { return detail::KeyView(device_location_, host_location_, st); }
     bool switch_key_generated_ = false;
 };
 
@@ -1610,6 +1745,32 @@ template <> class Galoiskey<Scheme::BFV> {
     int galois_elt_zero = 0; // column rotation
     std::unordered_map<int, int> galois_elt;
     std::unordered_map<int, DeviceVector<Data64>> device_location_;
+    std::unordered_map<int, PinnedVector<Data64>> host_location_;
+    void store_in_host(cudaStream_t st = cudaStreamDefault)
+    {
+        for (auto& kv : device_location_)
+            detail::key_to_host(kv.second, host_location_[kv.first], st);
+        device_location_.clear();
+        storage_type_ = storage_type::HOST;
+    }
+    void store_in_device(cudaStream_t st = cudaStreamDefault)
+    {
+        for (auto& kv : host_location_)
+            detail::key_to_device(device_location_[kv.first], kv.second, st);
+        host_location_.clear();
+        storage_type_ = storage_type::DEVICE;
+    }
+    bool is_on_device() const { return storage_type_ == storage_type::DEVICE; }
+    bool has_key(int elt) const { return device_location_.count(elt) || host_location_.count(elt); }
+    detail::KeyView view(int elt, cudaStream_t st) const
+    {
+        static const DeviceVector<Data64> no_dev;
+        static const PinnedVector<Data64> no_host;
+        auto d = device_location_.find(elt);
+        auto h = host_location_.find(elt);
+        return detail::KeyView(d == device_location_.end() ? no_dev : d->second, h == host_location_.end() ? no_host : h->second, st);
+    }
+    detail::KeyView zero_view(cudaStream_t st) const { return view(galois_elt_zero, st); }
 };
 
 template <> class HEOperator<Scheme::BFV> {
@@ -1695,7 +1856,8 @@ template <> class HEOperator<Scheme::BFV> {
         if (ct.memory_size() < words(3))
             throw std::invalid_argument("Invalid Ciphertexts size!");
         detail::InputGuard<Ciphertext<Scheme::BFV>> g(ct, opt, true);
-        detail::check(heon_bfv_relinearize(h(), ct.data(), 0, rk.data(), 1, opt.stream_));
+        const detail::KeyView key = rk.view(opt.stream_);
+        detail::check(heon_bfv_relinearize(h(), ct.data(), 0, key.ptr, 1, opt.stream_));
         ct.relinearization_required_ = false;
         ct.cipher_size_ = 2;
         detail::output_storage(ct, opt);
@@ -1706,12 +1868,12 @@ template <> class HEOperator<Scheme::BFV> {
     {
         if (in.relinearization_required_)
             throw std::invalid_argument("Ciphertext can not be rotated because of the non-linear part!");
-        auto it = gk.device_location_.find(galois_elt);
-        if (it == gk.device_location_.end())
+        const detail::KeyView key = gk.view(galois_elt, opt.stream_);
+        if (!key)
             throw std::logic_error("Galois key not present!");
         detail::InputGuard<Ciphertext<Scheme::BFV>> g(in, opt, &in == &out);
         DeviceVector<Data64> mem(words(2), opt.stream_);
-        detail::check(heon_bfv_apply_galois(h(), in.data(), 0, mem.data(), 0, it->second.data(), (uint32_t) galois_elt, 1,
+        detail::check(heon_bfv_apply_galois(h(), in.data(), 0, mem.data(), 0, key.ptr, (uint32_t) galois_elt, 1,
                                             opt.stream_));
         copy_meta(in, out);
         out.memory_set(std::move(mem));
@@ -1735,7 +1897,7 @@ template <> class HEOperator<Scheme::BFV> {
             return;
         }
         const int elt = heon_steps_to_galois_elt(shift, context_->n, gk.group_order_);
-        if (elt != 0 && gk.device_location_.count(elt))
+        if (elt != 0 && gk.has_key(elt))
         {
             apply_galois(in, out, gk, elt, opt);
             return;
@@ -1747,7 +1909,7 @@ template <> class HEOperator<Scheme::BFV> {
         for (int step : detail::rotation_plan(shift, log_slots, gk.max_shift_))
         {
             auto it = gk.galois_elt.find(step);
-            if (it == gk.galois_elt.end() || !gk.device_location_.count(it->second))
+            if (it == gk.galois_elt.end() || !gk.has_key(it->second))
                 throw std::logic_error("Galois key not present!");
             apply_galois(*cur, out, gk, it->second, opt);
             cur = &out;
@@ -1793,7 +1955,8 @@ template <> class HEOperator<Scheme::BFV> {
         if (!sk.switch_key_generated_)
             throw std::invalid_argument("Switchkey is not generated!");
         DeviceVector<Data64> mem(words(2), opt.stream_);
-        detail::check(heon_bfv_keyswitch(h(), in.data(), 0, mem.data(), 0, sk.data(), 1, opt.stream_));
+        const detail::KeyView key = sk.view(opt.stream_);
+        detail::check(heon_bfv_keyswitch(h(), in.data(), 0, mem.data(), 0, key.ptr, 1, opt.stream_));
         copy_meta(in, out);
         out.memory_set(std::move(mem));
         out.cipher_size_ = 2;

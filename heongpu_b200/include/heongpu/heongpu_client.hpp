@@ -116,6 +116,8 @@ template <Scheme S> class HEKeyGenerator {
         detail::check(heon_keygen_relin(context_->handle(), sk.data(), next(), mem.data(), opt.stream_));
         rk.device_location_ = std::move(mem);
         rk.relin_key_generated_ = true;
+        if (opt.storage_ == storage_type::HOST) // output_storage_manager of the reference
+            rk.store_in_host(opt.stream_);
     }
     // every shift of the key's table plus the conjugation / column-rotation element 2N-1
     void generate_galois_key(Galoiskey<S>& gk, Secretkey<S>& sk, const ExecutionOptions& opt = ExecutionOptions())
@@ -148,6 +150,8 @@ template <Scheme S> class HEKeyGenerator {
         detail::check(heon_keygen_galois(context_->handle(), sk.data(), (uint32_t) zero, next(), mem.data(), opt.stream_));
         gk.set_zero_key(zero, std::move(mem));
         gk.galois_key_generated_ = true;
+        if (opt.storage_ == storage_type::HOST)
+            gk.store_in_host(opt.stream_);
     }
     void generate_switch_key(Switchkey<S>& swk, Secretkey<S>& new_sk, Secretkey<S>& old_sk,
                              const ExecutionOptions& opt = ExecutionOptions())
@@ -161,6 +165,8 @@ template <Scheme S> class HEKeyGenerator {
         detail::check(heon_keygen_switch(context_->handle(), new_sk.data(), old_sk.data(), next(), mem.data(), opt.stream_));
         swk.device_location_ = std::move(mem);
         swk.switch_key_generated_ = true;
+        if (opt.storage_ == storage_type::HOST)
+            swk.store_in_host(opt.stream_);
     }
 
   private:

@@ -328,7 +328,8 @@ template <Scheme S> void save(const Relinkey<S>& k, std::ostream& os)
     detail::put(os, (uint8_t) storage_type::DEVICE);
     detail::put(os, (bool) true);
     detail::put(os, words);
-    detail::put_dev(os, k.data(), (size_t) words);
+    const detail::KeyView kv_ = k.view(cudaStreamDefault); // stages a host-stored key
+    detail::put_dev(os, kv_.ptr, (size_t) words);
 }
 template <Scheme S> void load(Relinkey<S>& k, std::istream& is)
 {
@@ -397,19 +398,30 @@ template <Scheme S> void save(const Galoiskey<S>& k, std::ostream& os)
     }
     detail::put(os, (int) k.galois_elt_zero);
     detail::put(os, words);
-    uint32_t count = 0;
+    std::vector<int> present; // keys on the device or (store_in_host) in host memory
     for (const auto& kv : k.device_location_)
-        if (kv.first != k.galois_elt_zero || S == Scheme::CKKS)
+        present.push_back(kv.first);
+    for (const auto& kv : k.host_location_)
+        present.push_back(kv.first);
+    uint32_t count = 0;
+    for (int e : present)
+        if (e != k.galois_elt_zero || S == Scheme::CKKS)
             ++count;
     detail::put(os, count);
-    for (const auto& kv : k.device_location_)
+    for (int e : present)
     {
-        if (!(kv.first != k.galois_elt_zero || S == Scheme::CKKS))
+        if (!(e != k.galois_elt_zero || S == Scheme::CKKS))
             continue;
-        detail::put(os, (int) kv.first);
-        detail::put_dev(os, kv.second.data(), (size_t) words);
+        detail::put(os, e);
+        const detail::KeyView v = k.view(e, cudaStreamDefault);
+        detail::put_dev(os, v.ptr, (size_t) words);
     }
-    detail::put_dev(os, k.zero_key_data(), (size_t) words); // the conjugation / column-rotation key
+    {
+        const detail::KeyView v = k.zero_view(cudaStreamDefault); // the conjugation / column-rotation key
+        if (!v)
+            throw std::logic_error("Galois key not present!");
+        detail::put_dev(os, v.ptr, (size_t) words);
+    }
 }
 template <Scheme S> void load(Galoiskey<S>& k, std::istream& is)
 {

@@ -57,3 +57,16 @@ def test_bsgs_matrix_products_decrypt_correctly_on_gpu():
     exe = _build("bsgs_test")
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "BSGS OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_host_keys_test_compiles_and_links():
+    _build("host_keys_test")
+
+
+@pytest.mark.gpu
+def test_evaluation_keys_in_host_memory_give_identical_words_on_gpu():
+    """Relinkey / Galoiskey / Switchkey store_in_host, store_in_device, key generation with storage_type::HOST and
+    save() of a host-stored key (src/include/heongpu/host/{ckks,bfv}/evaluationkey.cuh)."""
+    exe = _build("host_keys_test")
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "host keys OK" in out.stdout, out.stdout + out.stderr
