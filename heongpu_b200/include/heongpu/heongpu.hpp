@@ -534,6 +534,104 @@ template <> class HEContextImpl<Scheme::CKKS> {
             prime_vector_.push_back(Modulus64{raw[i], raw[i + 1], raw[i + 2]});
         context_generated_ = true;
     }
+    // ckks/context.cu:576-700: the reference serialises the parameters chosen at set_coeff_modulus time (the primes
+    // included) and load() regenerates the context from them.  This class picks its primes inside generate(), so an
+    // ungenerated context asks a scratch context for them first.
+    void save(std::ostream& os) const
+    {
+        if (!poly_modulus_degree_specified_ || !coeff_modulus_specified_)
+            throw std::runtime_error("Context has no enough parameters to serialize!");
+        std::vector<Modulus64> primes = prime_vector_;
+        int q_size = Q_size, p_size = P_size;
+        uint8_t ks = (uint8_t) keyswitching_type_;
+        if (!context_generated_)
+        {
+            HEContextImpl scratch(sec_level_type::none, device_);
+            scratch.set_poly_modulus_degree((size_t) n);
+            if (by_value_)
+                scratch.set_coeff_modulus_values(q_vals_, p_vals_);
+            else
+                scratch.set_coeff_modulus_bit_sizes(q_bits_, p_bits_);
+            scratch.generate();
+            primes = scratch.prime_vector_;
+            q_size = scratch.Q_size;
+            p_size = scratch.P_size;
+            ks = (uint8_t) scratch.keyswitching_type_;
+        }
+        auto put = [&](const auto& v) { os.write(reinterpret_cast<const char*>(&v), sizeof(v)); };
+        put((uint8_t) 0x2); // scheme_type::ckks
+        put((uint8_t) sec_level_);
+        put(ks);
+        put((int) n);
+        put((int) n_power);
+        put((int) (q_size + p_size)); // coeff_modulus
+        int total_bits = 0;
+        for (const auto& m : primes)
+            total_bits += (int) m.bit;
+        put(total_bits);
+        put((int) (q_size + p_size));
+        put(q_size);
+        put(p_size);
+        put((uint32_t) primes.size());
+        os.write(reinterpret_cast<const char*>(primes.data()), (std::streamsize) (sizeof(Modulus64) * primes.size()));
+        put((uint32_t) q_size); // base_q
+        for (int i = 0; i < q_size; ++i)
+            put((Data64) primes[i].value);
+        auto put_bits = [&](int from, int to) {
+            put((uint32_t) (to - from));
+            for (int i = from; i < to; ++i)
+                put((int) primes[i].bit);
+        };
+        put_bits(0, q_size + p_size);
+        put_bits(0, q_size);
+        put_bits(q_size, q_size + p_size);
+    }
+    void load(std::istream& is)
+    {
+        if (context_generated_)
+            throw std::runtime_error("Context has been already exist!");
+        auto get = [&](auto& v) {
+            is.read(reinterpret_cast<char*>(&v), sizeof(v));
+            if (!is)
+                throw std::runtime_error("Invalid context binary!");
+        };
+        uint8_t scheme, sec, ks;
+        int coeff_modulus, total_bits, qp, q, pz;
+        get(scheme);
+        if (scheme != 0x2)
+            throw std::runtime_error("Invalid scheme binary!");
+        get(sec);
+        get(ks);
+        get(n);
+        get(n_power);
+        get(coeff_modulus);
+        get(total_bits);
+        get(qp);
+        get(q);
+        get(pz);
+        uint32_t cnt;
+        get(cnt);
+        std::vector<Modulus64> primes(cnt);
+        is.read(reinterpret_cast<char*>(primes.data()), (std::streamsize) (sizeof(Modulus64) * cnt));
+        for (int v = 0; v < 4; ++v) // base_q and the three bit-size vectors
+        {
+            get(cnt);
+            is.ignore((std::streamsize) cnt * (v == 0 ? sizeof(Data64) : sizeof(int)));
+        }
+        if (!is || q + pz != (int) primes.size() || q < 1 || pz < 1)
+            throw std::runtime_error("Invalid context binary!");
+        sec_level_ = (sec_level_type) sec;
+        q_vals_.clear();
+        p_vals_.clear();
+        for (int i = 0; i < q; ++i)
+            q_vals_.push_back(primes[i].value);
+        for (int i = q; i < q + pz; ++i)
+            p_vals_.push_back(primes[i].value);
+        by_value_ = true;
+        poly_modulus_degree_specified_ = true;
+        coeff_modulus_specified_ = true;
+        generate();
+    }
     int digit_count(int depth) const
     {
         const int L = Q_size - depth;
@@ -642,7 +740,12 @@ template <> class Ciphertext<Scheme::CKKS> : public detail::Storable {
 template <Scheme S> class Relinkey;
 template <> class Relinkey<Scheme::CKKS> {
   public:
-    explicit Relinkey(HEContext<Scheme::CKKS> ctx) : context_(ctx), key_type(ctx->keyswitching_type_) {}
+    Relinkey() = default; // filled by load() (serializer::deserialize / load_from_file)
+    explicit Relinkey(HEContext<Scheme::CKKS> ctx) : context_(ctx), key_type(ctx->keyswitching_type_)
+    {
+        ring_size = ctx->n, Q_prime_size_ = ctx->Q_prime_size, Q_size_ = ctx->Q_size, d_ = ctx->digit_count(0);
+    }
+    int ring_size = 0, Q_prime_size_ = 0, Q_size_ = 0, d_ = 0;
     void save(std::ostream& os) const;
     void load(std::istream& is);
     // [digit][2][Q'_0][N] NTT-domain words (keygeneration.cu:180-183)
@@ -656,7 +759,7 @@ template <> class Relinkey<Scheme::CKKS> {
     }
     Data64* data() const { return device_location_.data(); }
     HEContext<Scheme::CKKS> context_;
-    keyswitching_type key_type;
+    keyswitching_type key_type = keyswitching_type::NONE;
     storage_type storage_type_ = storage_type::DEVICE;
     DeviceVector<Data64> device_location_;
     PinnedVector<Data64> host_location_;
@@ -679,8 +782,12 @@ template <> class Relinkey<Scheme::CKKS> {
 template <Scheme S> class Galoiskey;
 template <> class Galoiskey<Scheme::CKKS> {
   public:
+    Galoiskey() = default; // filled by load()
+    int ring_size = 0, Q_prime_size_ = 0, Q_size_ = 0, d_ = 0;
+    void bind_meta(const HEContextImpl<Scheme::CKKS>& c_) { ring_size = c_.n, Q_prime_size_ = c_.Q_prime_size, Q_size_ = c_.Q_size, d_ = c_.digit_count(0); }
     explicit Galoiskey(HEContext<Scheme::CKKS> ctx) : context_(ctx), key_type(ctx->keyswitching_type_)
     {
+        bind_meta(*ctx);
         for (int i = 0; i < 8; ++i) // default keys for +-2^i, i < MAX_SHIFT (evaluationkey.cu:306-345)
         {
             galois_elt[1 << i] = heon_steps_to_galois_elt(1 << i, ctx->n, group_order_);
@@ -689,6 +796,7 @@ template <> class Galoiskey<Scheme::CKKS> {
     }
     Galoiskey(HEContext<Scheme::CKKS> ctx, const std::vector<int>& shifts) : context_(ctx), key_type(ctx->keyswitching_type_)
     {
+        bind_meta(*ctx);
         customized = true;
         for (int s : shifts)
             galois_elt[s] = heon_steps_to_galois_elt(s, ctx->n, group_order_);
@@ -714,6 +822,7 @@ template <> class Galoiskey<Scheme::CKKS> {
     Galoiskey(HEContext<Scheme::CKKS> ctx, const std::vector<uint32_t>& elts)
         : context_(ctx), key_type(ctx->keyswitching_type_), custom_galois_elt(elts)
     {
+        bind_meta(*ctx);
         customized = true;
     }
     void set_zero_key(int elt, DeviceVector<Data64>&& key)
@@ -728,7 +837,7 @@ template <> class Galoiskey<Scheme::CKKS> {
     bool galois_key_generated_ = false;
     int max_shift_ = 7; // MAX_SHIFT - 1 (evaluationkey.cu:428)
     HEContext<Scheme::CKKS> context_;
-    keyswitching_type key_type;
+    keyswitching_type key_type = keyswitching_type::NONE;
     storage_type storage_type_ = storage_type::DEVICE;
     int group_order_ = 5;
     bool customized = false;
@@ -798,7 +907,12 @@ template <> class Plaintext<Scheme::CKKS> : public detail::Storable {
 template <Scheme S> class Switchkey;
 template <> class Switchkey<Scheme::CKKS> {
   public:
-    explicit Switchkey(HEContext<Scheme::CKKS> ctx) : context_(ctx), key_type(ctx->keyswitching_type_) {}
+    Switchkey() = default;
+    explicit Switchkey(HEContext<Scheme::CKKS> ctx) : context_(ctx), key_type(ctx->keyswitching_type_)
+    {
+        ring_size = ctx->n, Q_prime_size_ = ctx->Q_prime_size, Q_size_ = ctx->Q_size, d_ = ctx->digit_count(0);
+    }
+    int ring_size = 0, Q_prime_size_ = 0, Q_size_ = 0, d_ = 0;
     void set_data(const std::vector<Data64>& words, cudaStream_t st = cudaStreamDefault)
     {
         const size_t need = (size_t) context_->digit_count(0) * 2 * context_->Q_prime_size * context_->n;
@@ -809,7 +923,7 @@ template <> class Switchkey<Scheme::CKKS> {
     }
     Data64* data() const { return device_location_.data(); }
     HEContext<Scheme::CKKS> context_;
-    keyswitching_type key_type;
+    keyswitching_type key_type = keyswitching_type::NONE;
     storage_type storage_type_ = storage_type::DEVICE;
     DeviceVector<Data64> device_location_;
     PinnedVector<Data64> host_location_;
@@ -1506,6 +1620,111 @@ template <> class HEContextImpl<Scheme::BFV> {
             prime_vector_.push_back(Modulus64{raw[i], raw[i + 1], raw[i + 2]});
         context_generated_ = true;
     }
+    // bfv/context.cu:803-930: the reference serialises the parameters chosen at set_coeff_modulus time (the primes
+    // included) and load() regenerates the context from them.  This class picks its primes inside generate(), so an
+    // ungenerated context asks a scratch context for them first.
+    void save(std::ostream& os) const
+    {
+        if (!poly_modulus_degree_specified_ || !coeff_modulus_specified_ || !plain_modulus_specified_)
+            throw std::runtime_error("Context has no enough parameters to serialize!");
+        std::vector<Modulus64> primes = prime_vector_;
+        int q_size = Q_size, p_size = P_size;
+        uint8_t ks = (uint8_t) keyswitching_type_;
+        if (!context_generated_)
+        {
+            HEContextImpl scratch(sec_level_type::none, device_);
+            scratch.set_poly_modulus_degree((size_t) n);
+            if (by_value_)
+                scratch.set_coeff_modulus_values(q_vals_, p_vals_);
+            else
+                scratch.set_coeff_modulus_bit_sizes(q_bits_, p_bits_);
+            scratch.set_plain_modulus((int) plain_modulus_);
+            scratch.generate();
+            primes = scratch.prime_vector_;
+            q_size = scratch.Q_size;
+            p_size = scratch.P_size;
+            ks = (uint8_t) scratch.keyswitching_type_;
+        }
+        auto put = [&](const auto& v) { os.write(reinterpret_cast<const char*>(&v), sizeof(v)); };
+        put((uint8_t) 0x1); // scheme_type::bfv
+        put((uint8_t) sec_level_);
+        put(ks);
+        put((int) n);
+        put((int) n_power);
+        put((int) (q_size + p_size)); // coeff_modulus
+        int total_bits = 0;
+        for (const auto& m : primes)
+            total_bits += (int) m.bit;
+        put(total_bits);
+        put((int) (q_size + p_size));
+        put(q_size);
+        put(p_size);
+        put((uint32_t) primes.size());
+        os.write(reinterpret_cast<const char*>(primes.data()), (std::streamsize) (sizeof(Modulus64) * primes.size()));
+        put((uint32_t) q_size); // base_q
+        for (int i = 0; i < q_size; ++i)
+            put((Data64) primes[i].value);
+        auto put_bits = [&](int from, int to) {
+            put((uint32_t) (to - from));
+            for (int i = from; i < to; ++i)
+                put((int) primes[i].bit);
+        };
+        put_bits(0, q_size + p_size);
+        put_bits(0, q_size);
+        put_bits(q_size, q_size + p_size);
+        const Modulus64 t(plain_modulus_);
+        put(t);
+    }
+    void load(std::istream& is)
+    {
+        if (context_generated_)
+            throw std::runtime_error("Context has been already exist!");
+        auto get = [&](auto& v) {
+            is.read(reinterpret_cast<char*>(&v), sizeof(v));
+            if (!is)
+                throw std::runtime_error("Invalid context binary!");
+        };
+        uint8_t scheme, sec, ks;
+        int coeff_modulus, total_bits, qp, q, pz;
+        get(scheme);
+        if (scheme != 0x1)
+            throw std::runtime_error("Invalid scheme binary!");
+        get(sec);
+        get(ks);
+        get(n);
+        get(n_power);
+        get(coeff_modulus);
+        get(total_bits);
+        get(qp);
+        get(q);
+        get(pz);
+        uint32_t cnt;
+        get(cnt);
+        std::vector<Modulus64> primes(cnt);
+        is.read(reinterpret_cast<char*>(primes.data()), (std::streamsize) (sizeof(Modulus64) * cnt));
+        for (int v = 0; v < 4; ++v) // base_q and the three bit-size vectors
+        {
+            get(cnt);
+            is.ignore((std::streamsize) cnt * (v == 0 ? sizeof(Data64) : sizeof(int)));
+        }
+        Modulus64 t;
+        get(t);
+        if (!is || q + pz != (int) primes.size() || q < 1 || pz < 1)
+            throw std::runtime_error("Invalid context binary!");
+        plain_modulus_ = t.value;
+        plain_modulus_specified_ = true;
+        sec_level_ = (sec_level_type) sec;
+        q_vals_.clear();
+        p_vals_.clear();
+        for (int i = 0; i < q; ++i)
+            q_vals_.push_back(primes[i].value);
+        for (int i = q; i < q + pz; ++i)
+            p_vals_.push_back(primes[i].value);
+        by_value_ = true;
+        poly_modulus_degree_specified_ = true;
+        coeff_modulus_specified_ = true;
+        generate();
+    }
     // Method II digits have size 2 in the reference's BFV context whatever |P| is (contextpool.hpp:29)
     int digit_count() const { return P_size == 1 ? Q_size : (Q_size + 1) / 2; }
     heon_context_t handle() const { return h_; }
@@ -1622,7 +1841,12 @@ template <> class Plaintext<Scheme::BFV> : public detail::Storable {
 
 template <> class Relinkey<Scheme::BFV> {
   public:
-    explicit Relinkey(HEContext<Scheme::BFV> ctx) : context_(ctx), key_type(ctx->keyswitching_type_) {}
+    Relinkey() = default; // filled by load() (serializer::deserialize / load_from_file)
+    explicit Relinkey(HEContext<Scheme::BFV> ctx) : context_(ctx), key_type(ctx->keyswitching_type_)
+    {
+        ring_size = ctx->n, Q_prime_size_ = ctx->Q_prime_size, Q_size_ = ctx->Q_size, d_ = ctx->digit_count();
+    }
+    int ring_size = 0, Q_prime_size_ = 0, Q_size_ = 0, d_ = 0;
     void save(std::ostream& os) const;
     void load(std::istream& is);
     void set_data(const std::vector<Data64>& words, cudaStream_t st = cudaStreamDefault)
@@ -1635,7 +1859,7 @@ template <> class Relinkey<Scheme::BFV> {
     }
     Data64* data() const { return device_location_.data(); }
     HEContext<Scheme::BFV> context_;
-    keyswitching_type key_type;
+    keyswitching_type key_type = keyswitching_type::NONE;
     storage_type storage_type_ = storage_type::DEVICE;
     DeviceVector<Data64> device_location_;
     PinnedVector<Data64> host_location_;
@@ -1657,7 +1881,12 @@ template <> class Relinkey<Scheme::BFV> {
 
 template <> class Switchkey<Scheme::BFV> {
   public:
-    explicit Switchkey(HEContext<Scheme::BFV> ctx) : context_(ctx), key_type(ctx->keyswitching_type_) {}
+    Switchkey() = default;
+    explicit Switchkey(HEContext<Scheme::BFV> ctx) : context_(ctx), key_type(ctx->keyswitching_type_)
+    {
+        ring_size = ctx->n, Q_prime_size_ = ctx->Q_prime_size, Q_size_ = ctx->Q_size, d_ = ctx->digit_count();
+    }
+    int ring_size = 0, Q_prime_size_ = 0, Q_size_ = 0, d_ = 0;
     void set_data(const std::vector<Data64>& words, cudaStream_t st = cudaStreamDefault)
     {
         const size_t need = (size_t) context_->digit_count() * 2 * context_->Q_prime_size * context_->n;
@@ -1668,7 +1897,7 @@ template <> class Switchkey<Scheme::BFV> {
     }
     Data64* data() const { return device_location_.data(); }
     HEContext<Scheme::BFV> context_;
-    keyswitching_type key_type;
+    keyswitching_type key_type = keyswitching_type::NONE;
     storage_type storage_type_ = storage_type::DEVICE;
     DeviceVector<Data64> device_location_;
     PinnedVector<Data64> host_location_;
@@ -1690,8 +1919,12 @@ template <> class Switchkey<Scheme::BFV> {
 
 template <> class Galoiskey<Scheme::BFV> {
   public:
+    Galoiskey() = default; // filled by load()
+    int ring_size = 0, Q_prime_size_ = 0, Q_size_ = 0, d_ = 0;
+    void bind_meta(const HEContextImpl<Scheme::BFV>& c_) { ring_size = c_.n, Q_prime_size_ = c_.Q_prime_size, Q_size_ = c_.Q_size, d_ = c_.digit_count(); }
     explicit Galoiskey(HEContext<Scheme::BFV> ctx) : context_(ctx), key_type(ctx->keyswitching_type_)
     {
+        bind_meta(*ctx);
         for (int i = 0; i < 8; ++i) // default keys for +-2^i, i < MAX_SHIFT (bfv/evaluationkey.cu:306-345)
         {
             galois_elt[1 << i] = heon_steps_to_galois_elt(1 << i, ctx->n, group_order_);
@@ -1701,6 +1934,7 @@ template <> class Galoiskey<Scheme::BFV> {
     }
     Galoiskey(HEContext<Scheme::BFV> ctx, const std::vector<int>& shifts) : context_(ctx), key_type(ctx->keyswitching_type_)
     {
+        bind_meta(*ctx);
         customized = true;
         for (int s : shifts)
             galois_elt[s] = heon_steps_to_galois_elt(s, ctx->n, group_order_);
@@ -1716,6 +1950,7 @@ template <> class Galoiskey<Scheme::BFV> {
     Galoiskey(HEContext<Scheme::BFV> ctx, const std::vector<uint32_t>& elts)
         : context_(ctx), key_type(ctx->keyswitching_type_), custom_galois_elt(elts)
     {
+        bind_meta(*ctx);
         customized = true;
         galois_elt_zero = 2 * ctx->n - 1;
     }
@@ -1738,7 +1973,7 @@ template <> class Galoiskey<Scheme::BFV> {
     bool galois_key_generated_ = false;
     int max_shift_ = 7; // MAX_SHIFT - 1
     HEContext<Scheme::BFV> context_;
-    keyswitching_type key_type;
+    keyswitching_type key_type = keyswitching_type::NONE;
     storage_type storage_type_ = storage_type::DEVICE;
     int group_order_ = 3;
     bool customized = false;

@@ -26,6 +26,7 @@ template <Scheme S> size_t evk_words(const HEContext<S>& c)
 // ---- Secretkey<S>: [Q'][N] NTT-domain words (secretkey.cu) -------------------------------------------
 template <Scheme S> class Secretkey : public detail::Storable {
   public:
+    Secretkey() = default; // filled by load() (serializer::deserialize / load_from_file)
     explicit Secretkey(HEContext<S> ctx) : context_(ctx), hamming_weight_(ctx->n >> 1)
     {
         if (!ctx || !ctx->context_generated_)
@@ -45,13 +46,14 @@ template <Scheme S> class Secretkey : public detail::Storable {
     void load(std::istream& is);
     HEContext<S> context_;
     int ring_size_ = 0, coeff_modulus_count_ = 0;
-    int hamming_weight_;
+    int hamming_weight_ = 0;
     bool in_ntt_domain_ = false, secret_key_generated_ = false;
 };
 
 // ---- Publickey<S>: [2][Q'][N] NTT-domain words (publickey.cu) ----------------------------------------
 template <Scheme S> class Publickey : public detail::Storable {
   public:
+    Publickey() = default;
     explicit Publickey(HEContext<S> ctx) : context_(ctx)
     {
         if (!ctx || !ctx->context_generated_)

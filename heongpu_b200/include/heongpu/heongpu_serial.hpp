@@ -314,14 +314,13 @@ template <Scheme S> void save(const Relinkey<S>& k, std::ostream& os)
 {
     if (!k.relin_key_generated_)
         throw std::runtime_error("Relinkey is not generated so can not be serialized!");
-    const auto& c = *k.context_;
-    const int d = detail::digits0(c);
-    const Data64 words = (Data64) d * 2 * c.Q_prime_size * c.n;
+    const int d = k.d_;
+    const Data64 words = (Data64) d * 2 * k.Q_prime_size_ * k.ring_size;
     detail::put(os, detail::scheme_tag(S));
     detail::put(os, (uint8_t) k.key_type);
-    detail::put(os, (int) c.n);
-    detail::put(os, (int) c.Q_prime_size);
-    detail::put(os, (int) c.Q_size);
+    detail::put(os, (int) k.ring_size);
+    detail::put(os, (int) k.Q_prime_size_);
+    detail::put(os, (int) k.Q_size_);
     detail::put(os, d);
     detail::put(os, (int) 0); // d_tilda_ (Method III, unused)
     detail::put(os, (int) 0); // r_prime_
@@ -352,10 +351,16 @@ template <Scheme S> void load(Relinkey<S>& k, std::istream& is)
     detail::get(is, st);
     detail::get(is, b);
     detail::get(is, words);
-    const auto& c = *k.context_;
-    if (n != c.n || qp != c.Q_prime_size || q != c.Q_size || d != detail::digits0(c) ||
-        words != (Data64) d * 2 * qp * n)
-        throw std::runtime_error("Invalid relinkey binary for this context!");
+    if (words != (Data64) d * 2 * qp * n)
+        throw std::runtime_error("Invalid relinkey binary!");
+    if (k.context_) // an object bound to a context only accepts that context's keys
+    {
+        const auto& c = *k.context_;
+        if (n != c.n || qp != c.Q_prime_size || q != c.Q_size || d != detail::digits0(c))
+            throw std::runtime_error("Invalid relinkey binary for this context!");
+    }
+    k.key_type = (keyswitching_type) kt;
+    k.ring_size = n, k.Q_prime_size_ = qp, k.Q_size_ = q, k.d_ = d;
     k.device_location_ = detail::get_dev(is, (size_t) words);
     k.relin_key_generated_ = true;
 }
@@ -365,14 +370,13 @@ template <Scheme S> void save(const Galoiskey<S>& k, std::ostream& os)
 {
     if (!k.galois_key_generated_)
         throw std::runtime_error("Galoiskey is not generated so can not be serialized!");
-    const auto& c = *k.context_;
-    const int d = detail::digits0(c);
-    const Data64 words = (Data64) d * 2 * c.Q_prime_size * c.n;
+    const int d = k.d_;
+    const Data64 words = (Data64) d * 2 * k.Q_prime_size_ * k.ring_size;
     detail::put(os, detail::scheme_tag(S));
     detail::put(os, (uint8_t) k.key_type);
-    detail::put(os, (int) c.n);
-    detail::put(os, (int) c.Q_prime_size);
-    detail::put(os, (int) c.Q_size);
+    detail::put(os, (int) k.ring_size);
+    detail::put(os, (int) k.Q_prime_size_);
+    detail::put(os, (int) k.Q_size_);
     detail::put(os, d);
     detail::put(os, (bool) k.customized);
     detail::put(os, (int) k.group_order_);
@@ -443,9 +447,14 @@ template <Scheme S> void load(Galoiskey<S>& k, std::istream& is)
     detail::get(is, order);
     detail::get(is, st);
     detail::get(is, b);
-    const auto& c = *k.context_;
-    if (n != c.n || qp != c.Q_prime_size || q != c.Q_size || d != detail::digits0(c))
-        throw std::runtime_error("Invalid galoiskey binary for this context!");
+    if (k.context_)
+    {
+        const auto& c = *k.context_;
+        if (n != c.n || qp != c.Q_prime_size || q != c.Q_size || d != detail::digits0(c))
+            throw std::runtime_error("Invalid galoiskey binary for this context!");
+    }
+    k.key_type = (keyswitching_type) kt;
+    k.ring_size = n, k.Q_prime_size_ = qp, k.Q_size_ = q, k.d_ = d;
     k.customized = customized;
     k.group_order_ = order;
     uint32_t cnt;
@@ -547,6 +556,12 @@ template <class T> T& deserialize(const std::vector<uint8_t>& buffer, T& obj)
     obj.load(ss);
     return obj;
 }
+template <class T> T deserialize(const std::vector<uint8_t>& buffer)
+{
+    T obj;
+    deserialize(buffer, obj);
+    return obj;
+}
 template <class T> void save_to_file(const T& obj, const std::string& filename)
 {
     const std::vector<uint8_t> data = serialize(obj);
@@ -567,6 +582,12 @@ template <class T> T& load_from_file(const std::string& filename, T& obj)
     std::vector<uint8_t> buffer(size);
     ifs.read(reinterpret_cast<char*>(buffer.data()), (std::streamsize) size);
     return deserialize(buffer, obj);
+}
+template <class T> T load_from_file(const std::string& filename)
+{
+    T obj;
+    load_from_file(filename, obj);
+    return obj;
 }
 } // namespace serializer
 } // namespace heongpu

@@ -37,7 +37,7 @@ def test_reference_test_source_passes_against_this_class_layer(name):
 
 EXTRA = ["benchmark_ckks", "benchmark_bfv", "1_basic_bfv", "2_basic_ckks", "4_switchkey_methods_bfv",
          "5_switchkey_methods_ckks", "8_default_stream_usage", "9_multi_stream_usage_way1", "10_multi_stream_usage_way2",
-         "15_basic_tfhe"]
+         "13_bfv_serialization", "14_ckks_serialization", "15_basic_tfhe"]
 
 
 @pytest.mark.parametrize("name", EXTRA)
