@@ -7,6 +7,7 @@
 //   last_q_modinv, half, half_mod src/lib/util/util.cu:700-767
 //   rescale tables                src/lib/host/ckks/context.cu:342-368
 //   Method-II level tables        src/lib/kernel/contextpool.cpp:11-66,193-438
+#include <cstdlib>
 #include <cstring>
 #include "heon_internal.hpp"
 #include "modarith.cuh"
@@ -327,8 +328,14 @@ void upload_tables(Context& c)
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess)
         {
-            unsigned long long thr = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            // ... unless the caller has configured the pool already (MemoryPoolConfig of the class layer)
+            unsigned long long thr = 0;
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            if (thr == 0 && !getenv("HEON_POOL_KEEP_DEFAULT"))
+            {
+                thr = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
         }
     }
     c.d_mod = upload(c.mod);

@@ -30,6 +30,7 @@
 #include <iosfwd>
 #include <iostream>
 #include <memory>
+#include <optional>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -449,6 +450,104 @@ inline void key_to_device(DeviceVector<Data64>& dev, PinnedVector<Data64>& host,
 }
 } // namespace detail
 
+// ---- MemoryPoolConfig / MemoryPool (src/include/heongpu/util/memorypool.cuh:38-140) ---------------------------
+// The reference keeps an RMM pool behind a process-wide singleton.  This engine allocates stream-ordered from the
+// CUDA driver's per-device memory pool (cudaMallocAsync); the same configuration surface is mapped onto it: the
+// `max_*` limits become the pool's release threshold (memory above it goes back to the driver at the next
+// synchronisation), `initial_*` pre-reserves that much by one allocate / free, and `use_memory_pool(false)` sets the
+// threshold to zero (every free returns memory to the driver, i.e. plain cudaMalloc / cudaFree behaviour).
+// Fractions accept 0.0-1.0 (ratio) or 0-100 (percentage), as in the reference.
+struct MemoryPoolConfig {
+    std::optional<float> initial_device_fraction, max_device_fraction;
+    std::optional<size_t> initial_device_bytes, max_device_bytes;
+    std::optional<float> initial_host_fraction, max_host_fraction;
+    std::optional<size_t> initial_host_bytes, max_host_bytes;
+    bool use_memory_pool = true;
+    static MemoryPoolConfig Defaults()
+    {
+        MemoryPoolConfig c;
+        c.initial_device_fraction = 0.5f; // memorypool.cu: half of the free device memory up front, 80 % at most
+        c.max_device_fraction = 0.8f;
+        return c;
+    }
+};
+class MemoryPool {
+  public:
+    static MemoryPool& instance()
+    {
+        static MemoryPool pool;
+        return pool;
+    }
+    void initialize() { initialize(MemoryPoolConfig::Defaults()); }
+    void initialize(const MemoryPoolConfig& config)
+    {
+        config_ = config;
+        int dev = 0;
+        detail::cuda(cudaGetDevice(&dev));
+        cudaMemPool_t pool;
+        detail::cuda(cudaDeviceGetDefaultMemPool(&pool, dev));
+        size_t free_b = 0, total_b = 0;
+        detail::cuda(cudaMemGetInfo(&free_b, &total_b));
+        auto frac = [](float f) { return f > 1.0f ? f / 100.0f : f; };
+        unsigned long long threshold = ~0ull; // keep everything: allocation never goes back to the driver mid-run
+        if (config.max_device_bytes)
+            threshold = *config.max_device_bytes;
+        else if (config.max_device_fraction)
+            threshold = (unsigned long long) ((double) total_b * frac(*config.max_device_fraction));
+        if (!config.use_memory_pool)
+            threshold = 1; // effectively nothing stays cached (0 would read as "not configured" to the library)
+        detail::cuda(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+        size_t initial = 0;
+        if (config.initial_device_bytes)
+            initial = *config.initial_device_bytes;
+        else if (config.initial_device_fraction)
+            initial = (size_t) ((double) free_b * frac(*config.initial_device_fraction));
+        if (config.use_memory_pool && initial > 0)
+        {
+            initial = std::min<size_t>(initial, (size_t) std::min<unsigned long long>(threshold, free_b / 10 * 9));
+            void* p = nullptr;
+            if (cudaMallocAsync(&p, initial, cudaStreamDefault) == cudaSuccess)
+                cudaFreeAsync(p, cudaStreamDefault); // stays reserved in the pool (below the release threshold)
+            else
+                cudaGetLastError();
+        }
+        initialized_ = true;
+    }
+    void use_memory_pool(bool use)
+    {
+        config_.use_memory_pool = use;
+        initialize(config_);
+    }
+    bool is_initialized() const { return initialized_; }
+    void print_memory_pool_status() const
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess)
+            return;
+        unsigned long long reserved = 0, used = 0, reserved_high = 0, used_high = 0, threshold = 0;
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemHigh, &reserved_high);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &used_high);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        const double mb = 1.0 / (1024.0 * 1024.0);
+        std::cout << "==== Memory pool status (device " << dev << ", CUDA stream-ordered pool) ====" << std::endl;
+        std::cout << "-->   reserved: " << reserved * mb << " MB (peak " << reserved_high * mb << " MB)" << std::endl;
+        std::cout << "-->   in use:   " << used * mb << " MB (peak " << used_high * mb << " MB)" << std::endl;
+        if (threshold == ~0ull)
+            std::cout << "-->   release threshold: unlimited" << std::endl;
+        else
+            std::cout << "-->   release threshold: " << threshold * mb << " MB" << std::endl;
+    }
+
+  private:
+    MemoryPool() = default;
+    MemoryPoolConfig config_ = MemoryPoolConfig::Defaults();
+    bool initialized_ = false;
+};
+
 template <Scheme S> class HEContextImpl;
 template <Scheme S> using HEContext = std::shared_ptr<HEContextImpl<S>>;
 
@@ -507,6 +606,16 @@ template <> class HEContextImpl<Scheme::CKKS> {
         p_vals_ = p;
         by_value_ = true;
         coeff_modulus_specified_ = true;
+    }
+    // generate(const MemoryPoolConfig&) (context.cu: the pool is configured before the tables are built)
+    void generate(const MemoryPoolConfig& pool_config)
+    {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(device_);
+        MemoryPool::instance().initialize(pool_config);
+        cudaSetDevice(prev);
+        generate();
     }
     void generate()
     {
@@ -1593,6 +1702,16 @@ template <> class HEContextImpl<Scheme::BFV> {
             throw std::logic_error("Plain modulus cannot be changed after the context is generated!");
         plain_modulus_ = (Data64) t;
         plain_modulus_specified_ = true;
+    }
+    // generate(const MemoryPoolConfig&) (context.cu: the pool is configured before the tables are built)
+    void generate(const MemoryPoolConfig& pool_config)
+    {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(device_);
+        MemoryPool::instance().initialize(pool_config);
+        cudaSetDevice(prev);
+        generate();
     }
     void generate()
     {

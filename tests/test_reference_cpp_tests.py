@@ -35,7 +35,7 @@ def test_reference_test_source_passes_against_this_class_layer(name):
     assert " 0 failed" in r.stdout, tail
 
 
-EXTRA = ["benchmark_ckks", "benchmark_bfv", "1_basic_bfv", "2_basic_ckks", "4_switchkey_methods_bfv",
+EXTRA = ["benchmark_ckks", "benchmark_bfv", "1_basic_bfv", "2_basic_ckks", "3_basic_memorypool_config", "4_switchkey_methods_bfv",
          "5_switchkey_methods_ckks", "8_default_stream_usage", "9_multi_stream_usage_way1", "10_multi_stream_usage_way2",
          "13_bfv_serialization", "14_ckks_serialization", "15_basic_tfhe"]
 
