@@ -548,6 +548,21 @@ class MemoryPool {
     bool initialized_ = false;
 };
 
+namespace detail {
+// Like the reference, the class layer is single-device per host thread: ciphertexts, plaintexts and keys allocate on
+// the CURRENT CUDA device.  A context created for another device would hand the operators buffers from the wrong
+// GPU, so generate() refuses it (cudaSetDevice(device) first; the C ABI itself takes any device per call).
+inline void require_current_device(int device)
+{
+    int cur = -1;
+    cuda(cudaGetDevice(&cur));
+    if (cur != device)
+        throw std::invalid_argument("HEContext: the context's device (" + std::to_string(device) +
+                                    ") is not the current CUDA device (" + std::to_string(cur) +
+                                    "); call cudaSetDevice first");
+}
+} // namespace detail
+
 template <Scheme S> class HEContextImpl;
 template <Scheme S> using HEContext = std::shared_ptr<HEContextImpl<S>>;
 
@@ -621,6 +636,7 @@ template <> class HEContextImpl<Scheme::CKKS> {
     {
         if (context_generated_ || !poly_modulus_degree_specified_ || !coeff_modulus_specified_)
             throw std::runtime_error("Context is already generated!");
+        detail::require_current_device(device_);
         if (by_value_)
             detail::check(heon_ckks_context_create_values(device_, n_power, q_vals_.data(), (int) q_vals_.size(),
                                                           p_vals_.data(), (int) p_vals_.size(), &h_));
@@ -1717,6 +1733,7 @@ template <> class HEContextImpl<Scheme::BFV> {
     {
         if (context_generated_ || !poly_modulus_degree_specified_ || !coeff_modulus_specified_ || !plain_modulus_specified_)
             throw std::runtime_error("Context is already generated or not fully specified!");
+        detail::require_current_device(device_);
         if (by_value_)
             detail::check(heon_bfv_context_create_values(device_, n_power, q_vals_.data(), (int) q_vals_.size(), p_vals_.data(),
                                                          (int) p_vals_.size(), plain_modulus_, &h_));
