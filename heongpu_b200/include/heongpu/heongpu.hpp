@@ -2402,3 +2402,4 @@ template <> class HEArithmeticOperator<Scheme::BFV> : public HEOperator<Scheme::
 #include "heongpu_client.hpp"
 #include "heongpu_serial.hpp"
 #include "heongpu_tfhe.hpp"
+#include "heongpu_logic.hpp"

@@ -19,7 +19,7 @@ for t in $TESTS; do
   pids+=($!)
 done
 # the reference's benchmarks and basic examples (multi-stream OpenMP usage included), same rule: unmodified
-EXTRA=${EXTRA:-"benchmark/benchmark_ckks benchmark/benchmark_bfv example/basic/1_basic_bfv example/basic/2_basic_ckks example/basic/3_basic_memorypool_config example/basic/4_switchkey_methods_bfv example/basic/5_switchkey_methods_ckks example/basic/8_default_stream_usage example/basic/9_multi_stream_usage_way1 example/basic/10_multi_stream_usage_way2 example/basic/13_bfv_serialization example/basic/14_ckks_serialization example/basic/15_basic_tfhe"}
+EXTRA=${EXTRA:-"benchmark/benchmark_ckks benchmark/benchmark_bfv example/basic/1_basic_bfv example/basic/2_basic_ckks example/basic/3_basic_memorypool_config example/basic/4_switchkey_methods_bfv example/basic/5_switchkey_methods_ckks example/basic/8_default_stream_usage example/basic/9_multi_stream_usage_way1 example/basic/10_multi_stream_usage_way2 example/basic/11_basic_bfv_logic example/basic/12_basic_ckks_logic example/basic/13_bfv_serialization example/basic/14_ckks_serialization example/basic/15_basic_tfhe"}
 for e in $EXTRA; do
   b=$(basename $e)
   ( g++ -std=c++17 -O1 -w -fopenmp -I shim -I "$ROOT/heongpu_b200/include" -I /usr/local/cuda/include \

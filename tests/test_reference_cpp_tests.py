@@ -37,7 +37,7 @@ def test_reference_test_source_passes_against_this_class_layer(name):
 
 EXTRA = ["benchmark_ckks", "benchmark_bfv", "1_basic_bfv", "2_basic_ckks", "3_basic_memorypool_config", "4_switchkey_methods_bfv",
          "5_switchkey_methods_ckks", "8_default_stream_usage", "9_multi_stream_usage_way1", "10_multi_stream_usage_way2",
-         "13_bfv_serialization", "14_ckks_serialization", "15_basic_tfhe"]
+         "11_basic_bfv_logic", "13_bfv_serialization", "14_ckks_serialization", "15_basic_tfhe"]
 
 
 @pytest.mark.parametrize("name", EXTRA)
@@ -53,3 +53,18 @@ def test_reference_benchmarks_and_examples_run_against_this_class_layer(name):
     if os.path.isdir(out_dir):
         with open(os.path.join(out_dir, f"refcpp_{name}.txt"), "w") as f:
             f.write(r.stdout[-20000:])
+
+
+def test_reference_ckks_logic_example_reproduces_the_reference_behaviour():
+    """example/basic/12_basic_ckks_logic.cpp, unmodified: AND(C1, C1) decrypts correctly; its second half calls
+    XNOR_inplace(ciphertext, plaintext), whose composition in the reference (ckks/operator.cuh: XOR with a plaintext =
+    add_plain(a, p) - 2 * rescale(multiply_plain(a, p))) subtracts ciphertexts one level apart and therefore throws
+    "Ciphertexts leveled are not equal" from HEOperator<CKKS>::sub (ckks/operator.cu:160-163).  The mirror composes the
+    gate the same way and raises the same exception."""
+    exe = os.path.join(BIN, "12_basic_ckks_logic")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/_bin not built (needs /root/reference at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    out = r.stdout + r.stderr
+    assert "[ 1.000, 1.000, -0.000, 1.000" in out or "[ 1.000, 1.000, 0.000, 1.000" in out, out[-2000:]
+    assert r.returncode != 0 and "Ciphertexts leveled are not equal" in out, out[-2000:]
