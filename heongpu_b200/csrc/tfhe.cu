@@ -353,20 +353,31 @@ __global__ void __launch_bounds__(512)
     unsigned accb = (tid < ns) ? (unsigned) in_b[s0 + tid] : 0u;
     if (base_bit == 2 && length == 8 && tid < n)
     {
+        // the 24 key words of coefficient i + 1 are requested before coefficient i is consumed: the kernel is bound by
+        // the latency of these L2 reads (ncu: long_scoreboard 8.6 per issue without the prefetch), not by bandwidth
+        unsigned cur[24], nxt[24];
+        const int* rowp = ks_a + tid;
+#pragma unroll
+        for (int e = 0; e < 24; ++e)
+            cur[e] = (unsigned) __ldg(rowp + (size_t) e * n);
 #pragma unroll 1
         for (int i = 0; i < Nk; ++i)
         {
+            if (i + 1 < Nk)
+            {
+                const int* nrow = ks_a + ((size_t) (i + 1) * 24) * n + tid;
+#pragma unroll
+                for (int e = 0; e < 24; ++e)
+                    nxt[e] = (unsigned) __ldg(nrow + (size_t) e * n);
+            }
             unsigned short d[KS_S];
 #pragma unroll
             for (int q = 0; q < KS_S; ++q)
                 d[q] = dgs[q][i];
-            const int* rowp = ks_a + ((size_t) i * 24) * n + tid;
 #pragma unroll
             for (int i2 = 0; i2 < 8; ++i2)
             {
-                const unsigned r1 = (unsigned) __ldg(rowp + (size_t) (i2 * 3 + 0) * n);
-                const unsigned r2 = (unsigned) __ldg(rowp + (size_t) (i2 * 3 + 1) * n);
-                const unsigned r3 = (unsigned) __ldg(rowp + (size_t) (i2 * 3 + 2) * n);
+                const unsigned r1 = cur[i2 * 3 + 0], r2 = cur[i2 * 3 + 1], r3 = cur[i2 * 3 + 2];
 #pragma unroll
                 for (int q = 0; q < KS_S; ++q)
                 {
@@ -386,6 +397,9 @@ __global__ void __launch_bounds__(512)
                         accb -= (unsigned) __ldg(ks_b + (size_t) i * 24 + i2 * 3 + (dg - 1));
                 }
             }
+#pragma unroll
+            for (int e = 0; e < 24; ++e)
+                cur[e] = nxt[e];
         }
     }
     else if (tid < n)
