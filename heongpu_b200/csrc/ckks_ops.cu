@@ -1322,6 +1322,16 @@ static void moddown_add(const Context& c, u64* acc, u64* tmp, const u64* ct_in, 
         // P limb of both components: acc + (b*2+c)*Qpl*N + L*N
         launch_ntt_strided(c, acc + (long long) L * N, Qpl * N, 1, 0, (long long) batch * 2,
                            range_primes(c.Q_size, 1), true, st);
+        if (row_final_available(c, tmp, acc, ct_in, ct_bs, out, out_bs, L, batch))
+        {
+            // column stages of the corrections (divide-and-round stage one in their load), then row stages +
+            // stage two in one kernel
+            launch_divround1_ntt(c, acc + (long long) L * N, 2 * Qpl * N, Qpl * N, tmp, L, c.half[0],
+                                 c.mod[c.Q_size].value, c.d_half_mod, batch, st, true);
+            launch_row_final(c, tmp, acc, ct_in, ct_bs, out, out_bs, depth, batch, add_mask, st);
+            check_launch();
+            return;
+        }
         launch_divround1_ntt(c, acc + (long long) L * N, 2 * Qpl * N, Qpl * N, tmp, L, c.half[0],
                              c.mod[c.Q_size].value, c.d_half_mod, batch, st);
         dim3 g(c.n >> 8, L, batch * 2);
@@ -1358,6 +1368,15 @@ static void moddown_add(const Context& c, u64* acc, u64* tmp, const u64* ct_in, 
                 }
             }
             check_launch();
+            if (row_final_available(c, tmp, acc, ct_in, ct_bs, out, out_bs, L, batch))
+            {
+                // column stages of the corrections, then row stages + final combination in one kernel: the
+                // transformed corrections never travel through HBM
+                launch_ntt(c, tmp, tmp, (long long) batch * 2 * L, range_primes(0, L), false, st, true);
+                launch_row_final(c, tmp, acc, ct_in, ct_bs, out, out_bs, depth, batch, add_mask, st);
+                check_launch();
+                return;
+            }
             launch_ntt(c, tmp, tmp, (long long) batch * 2 * L, range_primes(0, L), false, st);
             {
                 dim3 g(c.n >> 9, L, batch * 2);

@@ -5,7 +5,7 @@ namespace heon {
 
 void launch_divround1_ntt(const Context& c, const u64* src, long long bstride, long long cstride,
                           u64* out, int Lout, u64 half, u64 plast, const u64* d_half_mod,
-                          long long batch, cudaStream_t st)
+                          long long batch, cudaStream_t st, bool col_only)
 {
     MapDivRoundOne m{src, out, bstride, cstride, Lout, c.logn, half, plast, d_half_mod};
     const long long wo = (batch * 2 * Lout) << c.logn;
@@ -15,7 +15,7 @@ void launch_divround1_ntt(const Context& c, const u64* src, long long bstride, l
         e.col_in_base = src;
         e.col_in_words = (batch - 1) * bstride + cstride + (1ll << c.logn);
     }
-    run_ntt(c, m, batch * 2 * Lout, false, e, st);
+    run_ntt(c, m, batch * 2 * Lout, false, e, st, col_only);
 }
 
 } // namespace heon

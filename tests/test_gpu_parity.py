@@ -322,7 +322,13 @@ def test_alternate_ntt_paths_agree(env):
                                       ("n16_II_small", {"HEON_COL_TMA_TILES": 8}), ("n16_I_small", {"HEON_COL_TMA_TILES": 4}),
                                       ("n16_I_small", {"HEON_COL_TMA_TILES": 16, "HEON_COL_TMA_BUFS": 3}),
                                       ("n16_II_small", {"HEON_MODUP_DOUBLES": 0}), ("n13_II", {"HEON_MODUP_DOUBLES": 0}),
-                                      ("n15_II", {"HEON_MODUP_DOUBLES": 0, "HEON_ROW_MAC": 0})])
+                                      ("n15_II", {"HEON_MODUP_DOUBLES": 0, "HEON_ROW_MAC": 0}),
+                                      # the Method-II mod-down with its last row pass and final combination in separate kernels
+                                      ("n16_II_small", {"HEON_ROW_FINAL": 0}), ("n13_II", {"HEON_ROW_FINAL": 0}),
+                                      ("n15_II", {"HEON_ROW_FINAL": 0, "HEON_NTT_FP64": 0}),
+                                      ("n16_II_small", {"HEON_ROW_FINAL": 3}), ("n13_II", {"HEON_ROW_FINAL": 8}),
+                                      ("n16_I_small", {"HEON_ROW_FINAL": 0}), ("n12_I", {"HEON_ROW_FINAL": 0}),
+                                      ("n16_I_small", {"HEON_ROW_FINAL": 3})])
 def test_alternate_operator_paths_agree(name, env):
     """multiply + relinearize + rotation through the alternate paths equal the default path."""
     api = _api()
