@@ -9,7 +9,7 @@ OBJ=${HEON_OBJDIR:-lib}
 mkdir -p $OBJ
 FLAGS="$HEON_EXTRA -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -cudart static"
 pids=()
-SRCS="ntt ntt_maps ntt_skip ntt_modup1 ntt_modup2 ntt_divround rowmac ckks_ops bfv_ops client hostpipe tfhe context capi"
+SRCS="ntt ntt_maps ntt_skip ntt_modup1 ntt_modup2 ntt_divround rowmac modup2col ckks_ops bfv_ops client hostpipe tfhe context capi"
 for f in $SRCS; do
   $NVCC $FLAGS -c csrc/$f.cu -o $OBJ/$f.o &
   pids+=($!)

@@ -1209,6 +1209,13 @@ static int keyswitch_modup_ntt(const Context& c, const u64* coef, long long coef
         d = t.d;
         if (d > 64)
             throw std::invalid_argument("too many key-switch digits");
+        if (modup2_col_available(c, depth, coef, coef_bs, tmp, batch, own_stashed, col_only))
+        {
+            // conversion + column stages in one kernel, the digit's source tiles staged once for all targets
+            launch_modup2_col(c, coef, coef_bs, tmp, depth, batch, st);
+            check_launch();
+            return d;
+        }
         if (modup2_fused_available(c, depth, coef, coef_bs))
         {
             // the conversion runs inside the column-pass load: the converted digits are never stored

@@ -125,6 +125,7 @@ struct Context {
     int row_mac = 1; // key switch: forward row pass fused with the inner product (HEON_ROW_MAC=0: separate kernels)
     int modup_fused = 0; // HEON_MODUP_FUSED=1: Method-II mod-up computed inside the column-pass load (no converted-digit buffer; measured slower than the separate FP64 kernel on B200, kept opt-in)
     int row_final = 1; // Method-II mod-down: forward row pass of the corrections fused with the final combination (HEON_ROW_FINAL=0: separate kernels; > 1: polynomials one CTA walks)
+    int modup_col = 1; // HEON_MODUP_COL: Method-II mod-up fused with the column pass, source tiles staged once per CTA (N = 2^16; 0: separate kernels, 2: also for tiny grids)
     int row_mac_rows = 4; // rows per CTA of the fused kernel: 4 (default, 6 CTAs/SM: +2 % measured) or 8 (HEON_ROW_MAC_ROWS)
     u64* d_last_q_modinv = nullptr;
     TwPair* d_lqm_pair = nullptr; // last_q_modinv with Shoup words
@@ -189,6 +190,10 @@ void launch_modup2_ntt(const Context& c, const u64* coef, long long coef_bs, u64
 bool row_mac_available(const Context& c, const u64* tmp, const u64* key, const u64* acc, int d);
 void launch_row_mac(const Context& c, const u64* tmp, const u64* key, u64* acc, int d, int depth, int batch,
                     bool own_stashed, const int* I_loc, const int* I_j, cudaStream_t st);
+bool modup2_col_available(const Context& c, int depth, const u64* coef, long long coef_bs, const u64* tmp, int batch,
+                          bool own_stashed, bool col_only);
+void launch_modup2_col(const Context& c, const u64* coef, long long coef_bs, u64* tmp, int depth, long long batch,
+                       cudaStream_t st);
 bool row_final_available(const Context& c, const u64* tmp, const u64* acc, const u64* ct_in, long long ct_bs,
                          const u64* out, long long out_bs, int L, int batch);
 void launch_row_final(const Context& c, const u64* tmp, const u64* acc, const u64* ct_in, long long ct_bs, u64* out,
