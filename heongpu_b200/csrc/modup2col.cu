@@ -31,17 +31,24 @@ struct Mu2ColDigits {
 
 constexpr int kMcTile = kRowTileBytes; // 32 KiB
 
+// per-target constants of the CTA's digit, staged in shared memory once (no global loads between targets)
+struct __align__(16) McRec {
+    TwPair m[4];   // conversion factors {M, companion}: doubles {M, RN(M/t)} or Shoup pairs
+    u64 rp[5];     // r * prod mod t for r = 0..I_j
+    int y, prime;  // limb slot in Q'_l, prime index
+    PrimeConst pc;
+};
+
 // the thread's 16 input words of target y in ct_prep<VAR> form; src = the thread's slot in source tile 0
 template <int VAR>
-__device__ __forceinline__ void mc_gather(const unsigned char* src, int ij, bool fp_src, bool fp, const TwPair* __restrict__ m,
-                                          const u64* __restrict__ rprod_y, long long rstep, unsigned long long rpack,
-                                          u64 (&v)[16], const BflyConst& c)
+__device__ __forceinline__ void mc_gather(const unsigned char* src, int ij, bool fp_src, bool fp, const McRec& rc,
+                                          unsigned long long rpack, u64 (&v)[16], const BflyConst& c)
 {
     u64 rp[5];
 #pragma unroll
     for (int r = 0; r < 5; ++r)
     {
-        const u64 t = r <= ij ? __ldg(rprod_y + r * rstep) : 0;
+        const u64 t = rc.rp[r];
         rp[r] = (VAR >= 3 && fp) ? d2u(fp_from_u64(t)) : t;
     }
     if (VAR >= 3 && fp)
@@ -54,7 +61,7 @@ __device__ __forceinline__ void mc_gather(const unsigned char* src, int ij, bool
         for (int j = 0; j < 4; ++j)
             if (j < ij)
             {
-                const TwPair t = ld_tw(m + j);
+                const TwPair t = rc.m[j];
                 const double w = u2d(t.w), wi = u2d(t.ws);
 #pragma unroll
                 for (int k = 0; k < 16; ++k)
@@ -79,7 +86,7 @@ __device__ __forceinline__ void mc_gather(const unsigned char* src, int ij, bool
     for (int j = 0; j < 4; ++j)
         if (j < ij)
         {
-            const TwPair t = ld_tw(m + j);
+            const TwPair t = rc.m[j];
 #pragma unroll
             for (int k = 0; k < 16; ++k)
             {
@@ -102,14 +109,13 @@ __device__ __forceinline__ void mc_gather(const unsigned char* src, int ij, bool
 // one target: conversion, eight column stages, TMA store of the lazy words
 template <int VAR>
 __device__ __forceinline__ void mc_target(const unsigned char* src, unsigned char* otile, const TwPair* twsm, int ij,
-                                          bool fp_src, const PrimeConst& pc, const TwPair* __restrict__ m,
-                                          const u64* __restrict__ rprod_y, long long rstep, unsigned long long rpack,
-                                          int tid, int bar_id)
+                                          bool fp_src, const McRec& rc, unsigned long long rpack, int tid, int bar_id)
 {
+    const PrimeConst& pc = rc.pc;
     const BflyConst bc = make_bc(pc);
     const int c = tid & 15, tt = tid >> 4;
     u64 v[16];
-    mc_gather<VAR>(src, ij, fp_src, fp_src && pc.fp_var != 0, m, rprod_y, rstep, rpack, v, bc);
+    mc_gather<VAR>(src, ij, fp_src, fp_src && pc.fp_var != 0, rc, rpack, v, bc);
     ct_round_a<VAR, 0, true>(v, twsm, 0, 0, bc);
     // the output tile: its previous store must have finished reading it
     if (tid == 0)
@@ -145,6 +151,7 @@ __global__ void __launch_bounds__(512, 1)
     unsigned char* sout = buf0 + ij_max * kMcTile;        // one output tile per group
     TwPair* stw = reinterpret_cast<TwPair*>(sout + 2 * kMcTile); // [group][buffer][256]
     unsigned char* srs = reinterpret_cast<unsigned char*>(stw + 4 * 256); // r per coefficient [16][256]
+    McRec* rec = reinterpret_cast<McRec*>(srs + 4096);                    // [n_targets]
     const int tile = blockIdx.x;
     const int dg = blockIdx.y;
     const long long b = blockIdx.z;
@@ -152,8 +159,15 @@ __global__ void __launch_bounds__(512, 1)
     const int grp = threadIdx.x >> 8, tid = threadIdx.x & 255;
     const bool fp_src = (dfp_mask >> dg) & 1;
     const int n_targets = Qpl - ij;
-    // t-th target of the digit (own limbs skipped)
-    auto target = [&](int t) { return t < iloc ? t : t + ij; };
+    // t-th target of the digit: the special limbs first (their 60-bit primes cost 2.75 x an FP64 target: spread
+    // over both groups), then the Q limbs with the digit's own limbs skipped
+    const int Ksp = Qpl - L;
+    auto target = [&](int t) {
+        if (t < Ksp)
+            return L + t;
+        t -= Ksp;
+        return t < iloc ? t : t + ij;
+    };
 
     if (threadIdx.x == 0)
     {
@@ -176,6 +190,20 @@ __global__ void __launch_bounds__(512, 1)
         const int prime = level_prime(target(grp), L, depth);
         mbar_arrive_expect_tx(&twbar[grp][0], 256 * sizeof(TwPair));
         tma_load_1d(stw + (grp * 2 + 0) * 256, tw_all + ((long long) prime << 16), 256 * sizeof(TwPair), &twbar[grp][0]);
+    }
+    // per-target constants (overlaps the source tiles' flight)
+    for (int t = threadIdx.x; t < n_targets; t += 512)
+    {
+        McRec rc;
+        rc.y = target(t);
+        rc.prime = level_prime(rc.y, L, depth);
+        rc.pc = pcs[rc.prime];
+        const TwPair* m = bc_pair + (long long) iloc * Qpl + (long long) rc.y * ij;
+        for (int j = 0; j < 4; ++j)
+            rc.m[j] = j < ij ? m[j] : TwPair{0, 0};
+        for (int r = 0; r < 5; ++r)
+            rc.rp[r] = r <= ij ? rprod[((long long) r * d + dg) * Qpl + rc.y] : 0;
+        rec[t] = rc;
     }
     const int c = tid & 15, tt = tid >> 4;
     const unsigned slot = tt * 128 + ((((c >> 1) ^ (tt & 7)) << 4) | ((c & 1) << 3)); // rows tt + 16k: + k*2048
@@ -218,31 +246,27 @@ __global__ void __launch_bounds__(512, 1)
 #pragma unroll 1
     for (int t = grp; t < n_targets; t += 2, ++it)
     {
-        const int y = target(t);
-        const int prime = level_prime(y, L, depth);
-        const PrimeConst pc = pcs[prime];
+        const McRec& rc = rec[t];
+        const int y = rc.y;
+        const unsigned fpv = rc.pc.fp_var, ncok = rc.pc.nc_ok;
         const int tb = it & 1;
         if (tid == 0 && t + 2 < n_targets)
         {
             // the other twiddle buffer served the previous target, finished behind a group barrier
-            const int pn = level_prime(target(t + 2), L, depth);
             mbar_arrive_expect_tx(&twbar[grp][tb ^ 1], 256 * sizeof(TwPair));
-            tma_load_1d(stw + (grp * 2 + (tb ^ 1)) * 256, tw_all + ((long long) pn << 16), 256 * sizeof(TwPair),
+            tma_load_1d(stw + (grp * 2 + (tb ^ 1)) * 256, tw_all + ((long long) rec[t + 2].prime << 16), 256 * sizeof(TwPair),
                         &twbar[grp][tb ^ 1]);
         }
-        const TwPair* m = bc_pair + (long long) iloc * Qpl + (long long) y * ij;
-        const u64* rprod_y = rprod + (long long) dg * Qpl + y;
-        const long long rstep = (long long) d * Qpl;
         const TwPair* twsm = stw + (grp * 2 + tb) * 256;
         mbar_wait(&twbar[grp][tb], (it >> 1) & 1);
-        if (pc.fp_var == 3)
-            mc_target<3>(ssrc + slot, otile, twsm, ij, fp_src, pc, m, rprod_y, rstep, rpack, tid, bar_id);
-        else if (pc.fp_var == 4)
-            mc_target<4>(ssrc + slot, otile, twsm, ij, fp_src, pc, m, rprod_y, rstep, rpack, tid, bar_id);
-        else if (variant == 1 || !pc.nc_ok)
-            mc_target<1>(ssrc + slot, otile, twsm, ij, fp_src, pc, m, rprod_y, rstep, rpack, tid, bar_id);
+        if (fpv == 3)
+            mc_target<3>(ssrc + slot, otile, twsm, ij, fp_src, rc, rpack, tid, bar_id);
+        else if (fpv == 4)
+            mc_target<4>(ssrc + slot, otile, twsm, ij, fp_src, rc, rpack, tid, bar_id);
+        else if (variant == 1 || !ncok)
+            mc_target<1>(ssrc + slot, otile, twsm, ij, fp_src, rc, rpack, tid, bar_id);
         else
-            mc_target<2>(ssrc + slot, otile, twsm, ij, fp_src, pc, m, rprod_y, rstep, rpack, tid, bar_id);
+            mc_target<2>(ssrc + slot, otile, twsm, ij, fp_src, rc, rpack, tid, bar_id);
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 256);
         if (tid == 0)
@@ -255,6 +279,11 @@ __global__ void __launch_bounds__(512, 1)
         tma_store_wait_read<0>();
 }
 
+static int mc_smem_bytes(int ij_max, int Qpl)
+{
+    return (ij_max + 2) * kMcTile + 4 * 256 * (int) sizeof(TwPair) + 4096 + Qpl * (int) sizeof(McRec) + 1024;
+}
+
 // true when the fused mod-up + column pass can serve this key switch (column stages only: the row stages
 // follow inside k_row_mac)
 bool modup2_col_available(const Context& c, int depth, const u64* coef, long long coef_bs, const u64* tmp, int batch,
@@ -265,9 +294,15 @@ bool modup2_col_available(const Context& c, int depth, const u64* coef, long lon
     const LevelTablesII& t = c.lvl2[depth];
     if (t.d > 64)
         return false;
+    int ij_max = 1;
     for (int i = 0; i < t.d; ++i)
+    {
         if (t.I_j[i] > 4)
             return false;
+        ij_max = std::max(ij_max, t.I_j[i]);
+    }
+    if (mc_smem_bytes(ij_max, c.Q_size - depth + c.P_size) > 227 * 1024)
+        return false;
     if ((coef_bs & 255) != 0 || ((reinterpret_cast<uintptr_t>(coef) | reinterpret_cast<uintptr_t>(tmp)) & 127) != 0)
         return false;
     const int L = c.Q_size - depth, Qpl = L + c.P_size;
@@ -303,7 +338,7 @@ void launch_modup2_col(const Context& c, const u64* coef, long long coef_bs, u64
     const long long wo = (batch * t.d * Qpl) << c.logn;
     const CUtensorMap tm_coef = make_col_map(coef, wi);
     const CUtensorMap tm_out = make_col_map(tmp, wo);
-    const int smem = (ij_max + 2) * kMcTile + 4 * 256 * (int) sizeof(TwPair) + 4096 + 1024;
+    const int smem = mc_smem_bytes(ij_max, Qpl);
     cudaFuncSetAttribute(k_modup2_col, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     LaunchScope scope(KC_MODUP2, st);
     k_modup2_col<<<dim3(16, t.d, (unsigned) batch), 512, smem, st>>>(tm_coef, tm_out, c.d_pc, t.d_mi_inv_pair,

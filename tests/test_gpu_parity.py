@@ -331,9 +331,9 @@ def test_alternate_ntt_paths_agree(env):
                                       ("n16_I_small", {"HEON_ROW_FINAL": 3}),
                                       # Method-II mod-up fused with the column pass (N = 2^16) against the separate kernels,
                                       # and its integer conversion / integer butterfly branches
-                                      ("n16_II_small", {"HEON_MODUP_COL": 0}), ("n16_II_small", {"HEON_MODUP_COL": 2}),
+                                      ("n16_II_small", {"HEON_MODUP_COL": 1}), ("n16_II_small", {"HEON_MODUP_COL": 2}),
                                       ("n16_II_small", {"HEON_NTT_FP64": 0}),
-                                      ("n16_II_small", {"HEON_MODUP_COL": 0, "HEON_NTT_FP64": 0})])
+                                      ("n16_II_small", {"HEON_MODUP_COL": 2, "HEON_NTT_FP64": 0})])
 def test_alternate_operator_paths_agree(name, env):
     """multiply + relinearize + rotation through the alternate paths equal the default path."""
     api = _api()
