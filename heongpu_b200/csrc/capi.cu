@@ -183,6 +183,8 @@ static void finish_context(Context& c, int device, int log_n, int n_q, int n_p, 
         c.row_mac = atoi(v);
     if (const char* v = getenv("HEON_MODUP_FUSED"))
         c.modup_fused = atoi(v);
+    if (const char* v = getenv("HEON_MODUP_CW"))
+        c.modup_cw = atoi(v);
     if (const char* v = getenv("HEON_MODUP_COL"))
         c.modup_col = atoi(v);
     if (const char* v = getenv("HEON_ROW_FINAL"))

@@ -352,104 +352,128 @@ struct __align__(16) Mu2Rec {
 };
 constexpr int kMu2MaxQ = 128;
 
-template <int IJ>
+template <int IJ, int CW>
 __device__ __forceinline__ void modup2_fast_body(const u64* __restrict__ pc_in, u64* __restrict__ po,
                                                  const PrimeConst* __restrict__ pcs,
                                                  const TwPair* __restrict__ mi_inv, const Mu2Rec* rec,
                                                  const u64* srp, int I_loc, int logn, int Qpl, bool skip_own, bool emit_doubles)
 {
-    u64 x[IJ][2], partial[IJ][2];
-    double pd[IJ][2];
+    // CW adjacent coefficients per thread: 2 by default; 4 (HEON_MODUP_CW=4) pays the per-target record, the loop and
+    // the address arithmetic once for four words but needs 119 registers -- measured 54.8 against 51.2 us/op at C3-II
+    u64 x[IJ][CW], partial[IJ][CW];
+    double pd[IJ][CW];
     bool dfp = true;
-    float r[2] = {0.f, 0.f};
+    float r[CW];
+#pragma unroll
+    for (int e = 0; e < CW; ++e)
+        r[e] = 0.f;
 #pragma unroll
     for (int i = 0; i < IJ; ++i)
     {
         const PrimeConst pi = pcs[I_loc + i];
         dfp = dfp && pi.fp_var != 0;
-        const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(pc_in + ((long long) i << logn));
-        x[i][0] = t.x;
-        x[i][1] = t.y;
+#pragma unroll
+        for (int h = 0; h < CW / 2; ++h)
+        {
+            const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(pc_in + ((long long) i << logn) + 2 * h);
+            x[i][2 * h] = t.x;
+            x[i][2 * h + 1] = t.y;
+        }
         const TwPair mi = mi_inv[I_loc + i];
         const float mod = __ull2float_rn(pi.p);
 #pragma unroll
-        for (int e = 0; e < 2; ++e)
+        for (int e = 0; e < CW; ++e)
         {
             partial[i][e] = csub(shoup_mul_lazy(x[i][e], mi.w, mi.ws, pi.p), pi.p);
             const float div = __ull2float_rn(partial[i][e]);
             r[e] = __fadd_rn(r[e], __fdiv_rn(div, mod));
         }
     }
-    const u64* rp0 = srp + (unsigned) roundf(r[0]) * Qpl;
-    const u64* rp1 = srp + (unsigned) roundf(r[1]) * Qpl;
+    const u64* rp[CW];
+#pragma unroll
+    for (int e = 0; e < CW; ++e)
+        rp[e] = srp + (unsigned) roundf(r[e]) * Qpl;
     if (dfp)
     {
 #pragma unroll
         for (int i = 0; i < IJ; ++i)
-        {
-            pd[i][0] = fp_from_u64(partial[i][0]);
-            pd[i][1] = fp_from_u64(partial[i][1]);
-        }
+#pragma unroll
+            for (int e = 0; e < CW; ++e)
+                pd[i][e] = fp_from_u64(partial[i][e]);
     }
     const long long lstep = 1ll << logn;
 #pragma unroll 2
     for (int k = 0; k < Qpl; ++k, po += lstep)
     {
         const Mu2Rec& rc = rec[k];
-        ulonglong2 res;
+        u64 res[CW];
         if (rc.self >= 0)
         {
             if (skip_own)
                 continue; // the slot already holds the original NTT-domain words
-            res.x = res.y = 0;
+#pragma unroll
+            for (int e = 0; e < CW; ++e)
+                res[e] = 0;
 #pragma unroll
             for (int i = 0; i < IJ; ++i)
                 if (rc.self == i)
                 {
-                    res.x = x[i][0];
-                    res.y = x[i][1];
+#pragma unroll
+                    for (int e = 0; e < CW; ++e)
+                        res[e] = x[i][e];
                 }
         }
         else if (dfp && rc.fp)
         {
             const double dnp = -rc.dp;
-            double a0 = 0.0, a1 = 0.0; // |acc| <= IJ * 0.6p, exact
+            double a[CW]; // |acc| <= IJ * 0.6p, exact
+#pragma unroll
+            for (int e = 0; e < CW; ++e)
+                a[e] = 0.0;
 #pragma unroll
             for (int j = 0; j < IJ; ++j)
             {
                 const double w = u2d(rc.m[j].w), wi = u2d(rc.m[j].ws);
-                a0 = __dadd_rn(a0, fp_mulmod(pd[j][0], w, wi, dnp));
-                a1 = __dadd_rn(a1, fp_mulmod(pd[j][1], w, wi, dnp));
+#pragma unroll
+                for (int e = 0; e < CW; ++e)
+                    a[e] = __dadd_rn(a[e], fp_mulmod(pd[j][e], w, wi, dnp));
             }
-            if (emit_doubles)
+#pragma unroll
+            for (int e = 0; e < CW; ++e)
             {
-                // the column pass that follows works on integer-valued doubles: leave |v| <= p/2 as it is
-                res.x = d2u(fp_reduce(__dsub_rn(a0, fp_from_u64(rp0[k])), rc.pinv, dnp));
-                res.y = d2u(fp_reduce(__dsub_rn(a1, fp_from_u64(rp1[k])), rc.pinv, dnp));
-            }
-            else
-            {
-                res.x = fp_canon(__dsub_rn(a0, fp_from_u64(rp0[k])), rc.pinv, dnp, rc.dp);
-                res.y = fp_canon(__dsub_rn(a1, fp_from_u64(rp1[k])), rc.pinv, dnp, rc.dp);
+                const double v = __dsub_rn(a[e], fp_from_u64(rp[e][k]));
+                // emit_doubles: the column pass that follows works on integer-valued doubles: leave |v| <= p/2 as it is
+                res[e] = emit_doubles ? d2u(fp_reduce(v, rc.pinv, dnp)) : fp_canon(v, rc.pinv, dnp, rc.dp);
             }
         }
         else
         {
             const u64 pkp = rc.p, p4 = 4 * pkp, np = 0 - pkp;
-            u64 a0 = 0, a1 = 0;
+            u64 a[CW];
+#pragma unroll
+            for (int e = 0; e < CW; ++e)
+                a[e] = 0;
 #pragma unroll
             for (int j = 0; j < IJ; ++j)
-            {
-                a0 = csub(a0 + shoup_lazy_ptx(partial[j][0], rc.m[j].w, rc.m[j].ws, np), p4);
-                a1 = csub(a1 + shoup_lazy_ptx(partial[j][1], rc.m[j].w, rc.m[j].ws, np), p4);
-            }
-            res.x = mod_sub(csub(csub(a0, 2 * pkp), pkp), rp0[k], pkp);
-            res.y = mod_sub(csub(csub(a1, 2 * pkp), pkp), rp1[k], pkp);
+#pragma unroll
+                for (int e = 0; e < CW; ++e)
+                    a[e] = csub(a[e] + shoup_lazy_ptx(partial[j][e], rc.m[j].w, rc.m[j].ws, np), p4);
+#pragma unroll
+            for (int e = 0; e < CW; ++e)
+                res[e] = mod_sub(csub(csub(a[e], 2 * pkp), pkp), rp[e][k], pkp);
         }
-        *reinterpret_cast<ulonglong2*>(po) = res;
+#pragma unroll
+        for (int h = 0; h < CW / 2; ++h)
+        {
+            ulonglong2 t;
+            t.x = res[2 * h];
+            t.y = res[2 * h + 1];
+            *reinterpret_cast<ulonglong2*>(po + 2 * h) = t;
+        }
     }
 }
 
+template <int CW>
 __global__ void __launch_bounds__(256)
     k_modup2_fast(const u64* __restrict__ coef, long long coef_bs, u64* __restrict__ out,
                   const PrimeConst* __restrict__ pcs, const TwPair* __restrict__ base_change,
@@ -459,7 +483,7 @@ __global__ void __launch_bounds__(256)
 {
     __shared__ Mu2Rec rec[kMu2MaxQ];
     __shared__ u64 srp[kMu2MaxQ * 5];
-    const int idx = (blockIdx.x * 256 + threadIdx.x) * 2;
+    const int idx = (blockIdx.x * 256 + threadIdx.x) * CW;
     const int dg = blockIdx.y;
     const long long bz = blockIdx.z;
     const int I_j = I_j_[dg];
@@ -485,10 +509,10 @@ __global__ void __launch_bounds__(256)
     u64* po = out + (((bz * d + dg) * Qpl) << logn) + idx;
     switch (I_j)
     {
-        case 1: modup2_fast_body<1>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, (skip_own & 1) != 0, (skip_own & 2) != 0); break;
-        case 2: modup2_fast_body<2>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, (skip_own & 1) != 0, (skip_own & 2) != 0); break;
-        case 3: modup2_fast_body<3>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, (skip_own & 1) != 0, (skip_own & 2) != 0); break;
-        case 4: modup2_fast_body<4>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, (skip_own & 1) != 0, (skip_own & 2) != 0); break;
+        case 1: modup2_fast_body<1, CW>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, (skip_own & 1) != 0, (skip_own & 2) != 0); break;
+        case 2: modup2_fast_body<2, CW>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, (skip_own & 1) != 0, (skip_own & 2) != 0); break;
+        case 3: modup2_fast_body<3, CW>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, (skip_own & 1) != 0, (skip_own & 2) != 0); break;
+        case 4: modup2_fast_body<4, CW>(pin, po, pcs, mi_inv, rec, srp, I_loc, logn, Qpl, (skip_own & 1) != 0, (skip_own & 2) != 0); break;
     }
 }
 
@@ -1246,9 +1270,18 @@ static int keyswitch_modup_ntt(const Context& c, const u64* coef, long long coef
             if (own_stashed && !(wide && Qpl <= kMu2MaxQ && K <= 4))
                 throw std::logic_error("own-limb shortcut needs the fast mod-up");
             if (wide && Qpl <= kMu2MaxQ && K <= 4)
-                k_modup2_fast<<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_pc, t.d_base_change_pair, t.d_mi_inv_pair,
-                                              t.d_rprod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth, K,
-                                              (own_stashed ? 1 : 0) | (dbl_mask ? 2 : 0));
+            {
+                // opt-in: four coefficients per thread (only when the grid keeps every SM busy with half the CTAs)
+                const bool cw4 = c.modup_cw == 4 && c.n >= 1024 && (long long) (c.n >> 10) * d * batch >= 2ll * c.num_sms;
+                if (cw4)
+                    k_modup2_fast<4><<<dim3(c.n >> 10, d, batch), 256, 0, st>>>(
+                        coef, coef_bs, tmp, c.d_pc, t.d_base_change_pair, t.d_mi_inv_pair, t.d_rprod, t.d_I_j, t.d_I_loc,
+                        c.logn, d, Qpl, L, depth, K, (own_stashed ? 1 : 0) | (dbl_mask ? 2 : 0));
+                else
+                    k_modup2_fast<2><<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_pc, t.d_base_change_pair, t.d_mi_inv_pair,
+                                                     t.d_rprod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth, K,
+                                                     (own_stashed ? 1 : 0) | (dbl_mask ? 2 : 0));
+            }
             else if (wide)
                 k_modup2<2><<<g, 256, 0, st>>>(coef, coef_bs, tmp, c.d_pc, t.d_base_change_pair, t.d_mi_inv_pair,
                                             t.d_rprod, t.d_I_j, t.d_I_loc, c.logn, d, Qpl, L, depth);

@@ -126,6 +126,7 @@ struct Context {
     int modup_fused = 0; // HEON_MODUP_FUSED=1: Method-II mod-up computed inside the column-pass load (no converted-digit buffer; measured slower than the separate FP64 kernel on B200, kept opt-in)
     int row_final = 1; // Method-II mod-down: forward row pass of the corrections fused with the final combination (HEON_ROW_FINAL=0: separate kernels; > 1: polynomials one CTA walks)
     int modup_col = 0; // HEON_MODUP_COL=1: Method-II mod-up fused with the column pass, source tiles staged once per CTA (N = 2^16; 2: also for tiny grids).  Bit-exact, measured slower than the separate kernels on B200 (153 against 117 us/op at C3-II: one 185 KB CTA per SM keeps the FP64 pipe 42 % busy), kept opt-in
+    int modup_cw = 2; // HEON_MODUP_CW: coefficients per thread of the fast Method-II mod-up (2; 4 measured slower: 54.8 against 51.2 us/op at C3-II, 119 registers halve the resident warps)
     int row_mac_rows = 4; // rows per CTA of the fused kernel: 4 (default, 6 CTAs/SM: +2 % measured) or 8 (HEON_ROW_MAC_ROWS)
     u64* d_last_q_modinv = nullptr;
     TwPair* d_lqm_pair = nullptr; // last_q_modinv with Shoup words

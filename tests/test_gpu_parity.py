@@ -333,7 +333,9 @@ def test_alternate_ntt_paths_agree(env):
                                       # and its integer conversion / integer butterfly branches
                                       ("n16_II_small", {"HEON_MODUP_COL": 1}), ("n16_II_small", {"HEON_MODUP_COL": 2}),
                                       ("n16_II_small", {"HEON_NTT_FP64": 0}),
-                                      ("n16_II_small", {"HEON_MODUP_COL": 2, "HEON_NTT_FP64": 0})])
+                                      ("n16_II_small", {"HEON_MODUP_COL": 2, "HEON_NTT_FP64": 0}),
+                                      # the fast mod-up with four coefficients per thread (default: two)
+                                      ("n16_II_small", {"HEON_MODUP_CW": 4}), ("n16_II_small", {"HEON_MODUP_CW": 4, "HEON_SKIP_OWN": 0})])
 def test_alternate_operator_paths_agree(name, env):
     """multiply + relinearize + rotation through the alternate paths equal the default path."""
     api = _api()
