@@ -7,7 +7,8 @@
 // over two sets of device staging buffers, so the link is busy in both directions while the SMs work
 // and the call is bounded by max(PCIe time, compute time) instead of their sum.  The call is
 // asynchronous with respect to the host: it is ordered after `stream` at entry and `stream` is ordered
-// after it at exit.
+// after it at exit.  Calls issued on different caller streams overlap (the pipeline's three internal streams are
+// shared per host thread, so their chunks simply queue behind each other).
 #include "ops.hpp"
 
 namespace heon {
@@ -15,7 +16,7 @@ namespace heon {
 namespace {
 struct Pipe {
     cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_entry = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_entry = nullptr, ev_exit = nullptr;
     int device = -1;
     void init(int dev)
     {
@@ -32,6 +33,7 @@ struct Pipe {
             cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming);
         }
         cudaEventCreateWithFlags(&ev_entry, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_exit, cudaEventDisableTiming);
     }
 };
 thread_local Pipe t_pipe; // one pipeline per host thread (the reference's threading contract: one stream per thread)
@@ -93,17 +95,14 @@ void op_mulrelin_host(const Context& c, const u64* h_a, const u64* h_b, u64* h_o
         cudaEventRecord(p.ev_out[j], p.s_out);
         used[j] = true;
     }
-    // free after the last consumers; order the caller's stream after the whole pipeline
-    cudaStreamWaitEvent(p.s_in, p.ev_cmp[(n_chunks - 1) & 1], 0);
-    cudaStreamWaitEvent(p.s_in, p.ev_out[(n_chunks - 1) & 1], 0);
-    if (n_chunks > 1)
-    {
-        cudaStreamWaitEvent(p.s_in, p.ev_cmp[n_chunks & 1], 0);
-        cudaStreamWaitEvent(p.s_in, p.ev_out[n_chunks & 1], 0);
-    }
-    cudaFreeAsync(stage, p.s_in);
-    cudaEventRecord(p.ev_entry, p.s_in);
-    cudaStreamWaitEvent(st, p.ev_entry, 0);
+    // The D2H stream finishes last (its copy of the last chunk follows that chunk's compute, which follows its H2D,
+    // and the earlier chunks precede them in stream order): free the staging there and order the caller's stream
+    // after it.  Nothing is queued behind the pipeline on the H2D or compute streams, so a following call on ANOTHER
+    // caller stream (the reference's multi-stream usage, example/basic/9_multi_stream_usage_way1.cpp) starts its
+    // copies while this call's last chunks are still computing / leaving: no fill / drain bubble between calls.
+    cudaFreeAsync(stage, p.s_out);
+    cudaEventRecord(p.ev_exit, p.s_out);
+    cudaStreamWaitEvent(st, p.ev_exit, 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
         throw std::runtime_error(std::string("host pipeline: ") + cudaGetErrorString(e));

@@ -292,3 +292,41 @@ def test_multiply_plain_accumulate_vs_integer_arithmetic(name, depth, count):
     for i in range(count):
         want = (want + cts[i].astype(object) * pts[i].astype(object)[None]) % p
     assert np.array_equal(to_host(out), want.astype(np.uint64))
+
+
+# ------------------------------------------------------------------ HOST-resident operands ---------
+@pytest.mark.parametrize("name,chunk,rescale", [("n13_II", 1, False), ("n13_II", 2, True), ("n13_II", 3, False),
+                                                ("n12_I", 2, True), ("n16_II_small", 2, False)])
+def test_host_operand_pipeline_equals_device_path(name, chunk, rescale):
+    """heon_ckks_multiply_relinearize_host (storage_type::HOST operands, storagemanager.cuh:113-167) returns the words
+    of the device-resident multiply + relinearize_inplace (+ rescale_inplace): on one caller stream, and with calls
+    issued alternately on two caller streams (they overlap inside the library's pipeline; ragged last chunk)."""
+    api = _api()
+    ctx, oc = gpu_ctx(name), oracle_ctx(name)
+    batch, L, n = 5, oc.Q, oc.n
+    a = ciphertext(301, oc.primes, L, n, 2, batch)
+    b = ciphertext(302, oc.primes, L, n, 2, batch)
+    key = to_dev(eval_key(303, oc.primes, oc.digits(0), n))
+    op = api.HEArithmeticOperator(ctx)
+    rk = api.Relinkey(ctx, key)
+    A, B = api.Ciphertext(ctx, to_dev(a)), api.Ciphertext(ctx, to_dev(b))
+    Cc = api.Ciphertext(ctx, torch.zeros(batch, 3, L, n, dtype=torch.int64, device="cuda"))
+    op.multiply(A, B, Cc)
+    op.relinearize_inplace(Cc, rk)
+    if rescale:
+        op.rescale_inplace(Cc)
+    torch.cuda.synchronize()
+    want = Cc.words().cpu()[:, :2]
+    Lout = L - 1 if rescale else L
+    ha, hb = torch.from_numpy(a.astype(np.int64)).pin_memory(), torch.from_numpy(b.astype(np.int64)).pin_memory()
+    res = [torch.zeros(batch, 2, Lout, n, dtype=torch.int64).pin_memory() for _ in range(4)]
+    op.multiply_relinearize_host(ha, hb, res[0], rk, depth=0, rescale=rescale, chunk=chunk)
+    torch.cuda.synchronize()
+    assert torch.equal(res[0], want), "host-operand path differs from the device path"
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for i in range(1, 4):
+        with torch.cuda.stream(streams[i & 1]):
+            op.multiply_relinearize_host(ha, hb, res[i], rk, depth=0, rescale=rescale, chunk=chunk)
+    torch.cuda.synchronize()
+    for i in range(1, 4):
+        assert torch.equal(res[i], want), f"overlapped call {i} differs from the device path"
