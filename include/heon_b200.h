@@ -281,7 +281,9 @@ int heon_bfv_keyswitch(heon_context_t ctx, const uint64_t* in, long long in_stri
  * multiply + relinearize_inplace (+ rescale_inplace when `rescale` != 0) on `batch` ciphertext pairs whose
  * words live in HOST memory (pinned for full PCIe speed): h_a, h_b [batch][2][L][N], h_out
  * [batch][2][L - rescale][N].  The batch is processed in chunks of `chunk` ciphertexts (0 = default) with the
- * copies of neighbouring chunks overlapped with the compute; asynchronous, ordered on `stream`. */
+ * copies of neighbouring chunks overlapped with the compute; asynchronous, ordered on `stream`.  Calls issued
+ * on different streams overlap each other (the copies of one call start while the last chunks of the previous
+ * one are still computing / leaving): alternate two streams to keep the link busy across calls. */
 int heon_ckks_multiply_relinearize_host(heon_context_t ctx, const uint64_t* h_a, const uint64_t* h_b, uint64_t* h_out,
                                         const uint64_t* relin_key, int depth, int rescale, int batch, int chunk,
                                         void* stream);
