@@ -358,3 +358,27 @@ def test_alternate_operator_paths_agree(name, env):
         res.append((Cc.data.clone(), R_.data.clone()))
     assert torch.equal(res[0][0], res[1][0]), ("relinearize", env)
     assert torch.equal(res[0][1], res[1][1]), ("apply_galois", env)
+
+
+@pytest.mark.parametrize("name,walk", [("n13_II", 8), ("n12_I", 8), ("n13_II", 5), ("n16_II_small", 8)])
+def test_row_final_long_walks(name, walk):
+    """k_row_final with walks of eight polynomials per CTA and a ragged last group (the default at the BASELINE batch
+    sizes; the small test batches otherwise walk two): relinearize equals the separate-kernel path and the oracle."""
+    api = _api()
+    ctx, alt, oc = _ctx_with_env(name, HEON_ROW_FINAL=walk), _ctx_with_env(name, HEON_ROW_FINAL=0), oracle_ctx(name)
+    batch, L, n = 5, oc.Q, oc.n
+    a = ciphertext(141, oc.primes, L, n, 3, batch)
+    key_h = eval_key(143, oc.primes, oc.digits(0), n)
+    key = to_dev(key_h)
+    res = []
+    for c in (ctx, alt):
+        op = api.HEArithmeticOperator(c)
+        Cc = api.Ciphertext(c, to_dev(a))
+        Cc.cipher_size_, Cc.relinearization_required_ = 3, True
+        op.relinearize_inplace(Cc, api.Relinkey(c, key))
+        torch.cuda.synchronize()
+        res.append(Cc.data.clone())
+    assert torch.equal(res[0][:, :2], res[1][:, :2]), (name, walk)
+    if n <= 8192:
+        want = oc.relinearize(a[4], key_h)[:2]
+        assert np.array_equal(to_host(res[0])[4, :2], want), "differs from the oracle"
